@@ -1,0 +1,117 @@
+"""Seeded synthetic checkpoints and inputs (no trained weights ship with the reference:
+model_example.pth / infos_example.pkl are git-LFS pointer stubs).
+
+`synth_state_dict` draws a reference-layout state_dict (layout.state_spec) from a seeded CPU
+generator: Xavier-uniform for every >1-D tensor (what make_model does, TransformerModel.py:1621-1623),
+small uniform biases, mildly perturbed LayerNorm gains/offsets (so the affine part is exercised),
+the closed-form sinusoid table for `pe` (TransformerModel.py:1496-1503).
+
+A randomly initialised bounding head predicts EOS for every image.  `apply_calibration` rescales
+the two classifier heads with constants that were fitted ONCE against the unmodified reference in
+the build container (oracle/make_golden.py, SURVEY.md Appendix A recipe) and are committed in
+boficap_b200/data/synth_calib.json, so that any box regenerates bit-identical weights without
+running any model code.
+
+`synth_inputs` follows SURVEY.md section 8(d): att_feats = rand(B,R,2048) (bottom-up features are
+post-ReLU, non-negative), fc_feats = att_feats.mean(1); adaptive: n_i ~ randint(10,R+1), row 0 forced to
+R, float32 prefix masks, features zeroed beyond n_i.
+"""
+import json
+import math
+import os
+from collections import OrderedDict
+
+import torch
+
+from .layout import BofiConfig, state_spec
+
+_CALIB_PATH = os.path.join(os.path.dirname(__file__), "data", "synth_calib.json")
+
+
+def sinusoid_table(max_len, d):
+    pe = torch.zeros(max_len, d)
+    position = torch.arange(0, max_len).unsqueeze(1).float()
+    div_term = torch.exp(torch.arange(0, d, 2).float() * -(math.log(10000.0) / d))
+    pe[:, 0::2] = torch.sin(position * div_term)
+    pe[:, 1::2] = torch.cos(position * div_term)
+    return pe.unsqueeze(0)
+
+
+def synth_state_dict(cfg=None, seed=0, calib=None):
+    cfg = cfg or BofiConfig()
+    g = torch.Generator().manual_seed(seed)
+    sd = OrderedDict()
+    for name, (shape, kind) in state_spec(cfg).items():
+        if kind in ("matrix", "embedding"):
+            fan_out, fan_in = shape
+            a = math.sqrt(6.0 / (fan_in + fan_out))
+            t = (torch.rand(shape, generator=g) * 2 - 1) * a
+        elif kind == "bias":
+            t = (torch.rand(shape, generator=g) * 2 - 1) * 0.05
+        elif kind == "ones":
+            t = 1.0 + 0.1 * (torch.rand(shape, generator=g) * 2 - 1)
+        elif kind == "zeros":
+            t = 0.05 * (torch.rand(shape, generator=g) * 2 - 1)
+        elif kind == "pe":
+            t = sinusoid_table(shape[1], shape[2])
+        else:
+            raise ValueError(kind)
+        sd[name] = t.contiguous()
+    if calib is not None:
+        apply_calibration(sd, cfg, seed, calib)
+    return sd
+
+
+def calibration_key(cfg, seed, calib):
+    return "%s/seed%d/Nenc%d_Ndec%d_Nlen%d_V%d" % (calib, seed, cfg.N_enc, cfg.N_dec, cfg.N_len, cfg.vocab_size)
+
+
+def load_calibration_table():
+    with open(_CALIB_PATH) as f:
+        return json.load(f)
+
+
+def apply_calibration(sd, cfg, seed, calib):
+    table = load_calibration_table()
+    key = calibration_key(cfg, seed, calib)
+    if key not in table:
+        raise KeyError("no committed calibration for %s (have: %s)" % (key, sorted(table)))
+    entry = table[key]
+    lp = "model.length_predictor."
+    for head, name in (("len", "Length_classifier2"), ("syn", "Syntactic_classifier2")):
+        sd[lp + name + ".weight"] = sd[lp + name + ".weight"] * float(entry[head + "_gain"])
+        sd[lp + name + ".bias"] = torch.tensor(entry[head + "_bias"], dtype=torch.float32)
+    # guard against RNG drift between torch builds: the constants only fit these exact weights
+    probe = float(sd["model.length_predictor.Length_classifier1.weight"].double().abs().sum())
+    if abs(probe - entry["probe"]) > 1e-6 * max(1.0, abs(entry["probe"])):
+        raise RuntimeError("synthetic weights differ from the calibrated ones (probe %r vs %r)" % (probe, entry["probe"]))
+    return sd
+
+
+def synth_inputs(B, R=36, seed=1, adaptive=False, feat=2048, min_regions=10):
+    g = torch.Generator().manual_seed(seed)
+    att = torch.rand(B, R, feat, generator=g)
+    masks = None
+    if adaptive:
+        n = torch.randint(min_regions, R + 1, (B,), generator=g)
+        n[0] = R
+        masks = (torch.arange(R)[None, :] < n[:, None]).float()
+        att = att * masks[:, :, None]
+    fc = att.mean(1)
+    return fc, att, masks
+
+
+def make_infos(cfg, opt_namespace=None):
+    """`infos.pkl` payload in the reference's format (tools/train.py:55-69): the drop-in loads
+    `infos['opt']` / `infos['vocab']` exactly as tools/eval.py:49-63 does."""
+    import argparse
+    vocab = {str(i): "w%d" % i for i in range(4, cfg.vocab_size + 4)}
+    if opt_namespace is None:
+        opt_namespace = argparse.Namespace(
+            caption_model="transformer", vocab_size=cfg.vocab_size, input_encoding_size=cfg.d_model,
+            rnn_size=cfg.d_ff, num_layers=cfg.N_enc, drop_prob_lm=cfg.drop_prob_lm, seq_length=cfg.seq_length,
+            max_length=cfg.seq_length, fc_feat_size=2048, att_feat_size=cfg.att_feat_size, att_hid_size=512,
+            use_bn=0, logit_layers=1, train_mode=cfg.train_mode, decoder_input_mode=cfg.decoder_input_mode,
+            N_enc=cfg.N_enc, N_dec=cfg.N_dec, N_len=cfg.N_len, d_model=cfg.d_model, d_ff=cfg.d_ff,
+            num_att_heads=cfg.h, dropout=cfg.dropout)
+    return {"iter": 0, "epoch": 0, "vocab": vocab, "opt": opt_namespace, "best_val_score": None}

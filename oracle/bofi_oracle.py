@@ -1,0 +1,335 @@
+"""CPU oracle for the BoFiCap greedy Bounding-and-Filling decode path.
+
+TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+`--impl reference` legs may import this file.  The product path (boficap_b200/) never does.
+
+A plain PyTorch-fp32 functional restatement of the reference algorithm, operating directly on
+the reference's 311-key state_dict.  It follows the REFERENCE FORMULATION (all 22 bounding rows
+recomputed every step, memory K/V re-projected every call) so that, timed on host cores, it is
+an honest stand-in for the reference's own CPU path.  The per-row python loops of the reference
+are restated as vectorised index arithmetic (same results; slightly *faster* than the
+reference, i.e. conservative as a baseline).
+
+Parity pinning: the reference ships no tests/golden vectors.  This oracle is
+pinned against the UNMODIFIED reference model imported in the build container
+(oracle/make_golden.py -> tests/golden/*.npz; tests/test_oracle_vs_reference.py runs the live
+comparison whenever /root/reference is present).
+
+Reference citations (relative to /root/reference/captioning/models/):
+  prepare           TransformerModel.py:1674-1711, AttModel.py:33-51 (pack_wrapper), :113-120 (clip_att)
+  layer_norm        TransformerModel.py:1338-1349
+  mha / attention   TransformerModel.py:1421-1467
+  ffn               TransformerModel.py:1469-1478
+  encode            TransformerModel.py:1325-1336, :1365-1377, :470-474
+  embed / pos       TransformerModel.py:1480-1507
+  bounding_head     TransformerModel.py:357-383, :1016-1029
+  decode_naic       TransformerModel.py:1823-1876, AttModel.py:203-210, :419-429
+  decode_saic       TransformerModel.py:1878-1986, :515-530
+  sample_next_word  CaptionModel.py:383-437
+"""
+import math
+import time
+
+import torch
+import torch.nn.functional as F
+
+SYN_LOWER, SYN_UPPER = 4, 6      # TransformerModel.py:41-42,186-187,331-332
+LENGTH_DIM, SYN_DIM = 20, 10     # TransformerModel.py:329-330
+
+
+class OracleConfig:
+    def __init__(self, **kw):
+        self.N_enc = 6
+        self.N_dec = 6
+        self.N_len = 1
+        self.d_model = 512
+        self.d_ff = 2048
+        self.h = 8
+        self.seq_length = 20
+        self.vocab_size = 9487
+        self.pad_idx, self.bos_idx, self.eos_idx, self.len_idx = 0, 1, 2, 3
+        self.decoder_input_mode = "add"
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+    @property
+    def tgt_vocab(self):
+        return self.vocab_size + 4
+
+
+class BofiOracle:
+    def __init__(self, state_dict, cfg=None, record=False):
+        self.sd = {k: v.detach().float() for k, v in state_dict.items()}
+        self.cfg = cfg or OracleConfig()
+        self.record = record
+        self.trace = {}
+
+    # ---- primitives -----------------------------------------------------------------------
+    def lin(self, p, x):
+        return F.linear(x, self.sd[p + ".weight"], self.sd[p + ".bias"])
+
+    def layer_norm(self, p, x, eps=1e-6):
+        mean = x.mean(-1, keepdim=True)
+        std = x.std(-1, keepdim=True)          # unbiased (N-1); eps added to std, not variance
+        return self.sd[p + ".a_2"] * (x - mean) / (std + eps) + self.sd[p + ".b_2"]
+
+    def mha(self, p, q_in, kv_in, mask):
+        """mask: bool/float broadcastable to [B,1,Tq,Tk] after unsqueeze(1); 0 => -inf."""
+        h, d = self.cfg.h, self.cfg.d_model
+        dk = d // h
+        nb = q_in.size(0)
+        q = self.lin(p + ".linears.0", q_in).view(nb, -1, h, dk).transpose(1, 2)
+        k = self.lin(p + ".linears.1", kv_in).view(nb, -1, h, dk).transpose(1, 2)
+        v = self.lin(p + ".linears.2", kv_in).view(nb, -1, h, dk).transpose(1, 2)
+        scores = torch.matmul(q, k.transpose(-2, -1)) / math.sqrt(dk)
+        if mask is not None:
+            scores = scores.masked_fill(mask.unsqueeze(1) == 0, float("-inf"))
+        pattn = F.softmax(scores, dim=-1)      # all-masked row -> NaN (kept on purpose)
+        x = torch.matmul(pattn, v).transpose(1, 2).contiguous().view(nb, -1, d)
+        return self.lin(p + ".linears.3", x)
+
+    def ffn(self, p, x):
+        return self.lin(p + ".w_2", F.relu(self.lin(p + ".w_1", x)))
+
+    def embed(self, table, ids):
+        return F.embedding(ids, self.sd["model.%s.lut.weight" % table]) * math.sqrt(self.cfg.d_model)
+
+    def pos(self, x):
+        return x + self.sd["model.pos_embed.pe"][:, : x.size(1)]
+
+    # ---- A1: feature preparation ----------------------------------------------------------
+    def prepare(self, att_feats, att_masks):
+        att_feats = att_feats.float()
+        if att_masks is not None:
+            lens = att_masks.long().sum(1)
+            max_len = int(lens.max())
+            att_feats = att_feats[:, :max_len].contiguous()
+            att_masks = att_masks[:, :max_len].contiguous()
+            x = F.relu(self.lin("att_embed.0", att_feats))
+            # pack_wrapper: the module only sees the first `lens[b]` rows; padded rows come back 0
+            keep = torch.arange(max_len)[None, :] < lens[:, None]
+            x = x * keep[:, :, None].to(x.dtype)
+            mask = att_masks
+        else:
+            x = F.relu(self.lin("att_embed.0", att_feats))
+            mask = torch.ones(att_feats.shape[:2], dtype=torch.bool)
+        return x, mask.unsqueeze(-2)
+
+    # ---- A2: encoder ----------------------------------------------------------------------
+    def encode(self, x, src_mask):
+        for l in range(self.cfg.N_enc):
+            p = "model.encoder.layers.%d" % l
+            y = self.layer_norm(p + ".sublayer.0.norm", x)
+            x = x + self.mha(p + ".self_attn", y, y, src_mask)
+            x = x + self.ffn(p + ".feed_forward", self.layer_norm(p + ".sublayer.1.norm", x))
+        return self.layer_norm("model.encoder.norm", x)
+
+    def _dec_layer(self, p, ffname, x, memory, src_mask, tgt_mask):
+        y = self.layer_norm(p + ".sublayer.0.norm", x)
+        x = x + self.mha(p + ".self_attn", y, y, tgt_mask)
+        x = x + self.mha(p + ".src_attn", self.layer_norm(p + ".sublayer.1.norm", x), memory, src_mask)
+        return x + self.ffn(p + "." + ffname, self.layer_norm(p + ".sublayer.2.norm", x))
+
+    # ---- A8: bounding head ----------------------------------------------------------------
+    def bounding_head(self, x, memory, src_mask, tgt_mask):
+        lp = "model.length_predictor"
+        if self.cfg.N_len == 0:
+            y = self.layer_norm(lp + ".LengthPredictor.norm", x)
+            out = self.layer_norm(lp + ".norm", x + self.mha(lp + ".length_attn", y, memory, src_mask))
+        else:
+            for l in range(self.cfg.N_len):
+                x = self._dec_layer(lp + ".LengthPredictor.%d" % l, "ff", x, memory, src_mask, tgt_mask)
+            out = self.layer_norm(lp + ".norm", x)
+        hrow = out[:, 0, :]
+        len_logp = F.log_softmax(self.lin(lp + ".Length_classifier2",
+                                          F.relu(self.lin(lp + ".Length_classifier1", hrow))), dim=-1)
+        syn_logp = F.log_softmax(self.lin(lp + ".Syntactic_classifier2",
+                                          F.relu(self.lin(lp + ".Syntactic_classifier1", hrow))), dim=-1)
+        return len_logp.argmax(1).int(), len_logp, syn_logp.argmax(1).long(), syn_logp, hrow
+
+    # ---- A10: decoder stack ---------------------------------------------------------------
+    def decoder(self, x, memory, src_mask, tgt_mask):
+        for l in range(self.cfg.N_dec):
+            x = self._dec_layer("model.decoder.layers.%d" % l, "feed_forward", x, memory, src_mask, tgt_mask)
+        return self.layer_norm("model.decoder.norm", x)
+
+    def decoder_input(self, word_ids, syn_ids):
+        mode = self.cfg.decoder_input_mode
+        if mode == "add":
+            return self.pos(self.embed("tgt_embed", word_ids) + self.embed("syn_embed", syn_ids))
+        raise NotImplementedError("decoder_input_mode=%s (uic_sd.yml uses 'add')" % mode)
+
+    def logit(self, hid):
+        return self.lin("model.generator.proj", hid)
+
+    # ---- box bookkeeping shared by NAIC / SAIC --------------------------------------------
+    def _box_rule(self, len_n, syn_n, last, finished):
+        """Returns (write[B] bool, new_len[B] int, finished'[B]).  TransformerModel.py:1843-1867."""
+        L = self.cfg.seq_length
+        active = ~finished
+        eos = (len_n == 0) | (syn_n < SYN_LOWER) | (syn_n > SYN_UPPER)
+        clip = (len_n + last) >= (L + 1)
+        new_len = torch.where(clip, (L + 1) - last, len_n)
+        write = active & ~eos
+        finished = finished | (active & (eos | clip))
+        return write, new_len, finished
+
+    # ---- A9 + A13: NAIC -------------------------------------------------------------------
+    def decode_naic(self, memory, src_mask, output_logsoftmax=1, sample_method="greedy",
+                    temperature=1.0, generator=None):
+        c = self.cfg
+        B, Lb, L = memory.size(0), c.seq_length + 2, c.seq_length
+        phrase_num = torch.zeros(B, dtype=torch.int32)
+        phrase_length = torch.zeros(B, Lb, dtype=torch.int32)
+        phrase_syn = torch.full((B, Lb), c.pad_idx, dtype=torch.long)
+        ext = torch.full((B, Lb), c.pad_idx, dtype=torch.long)
+        tgt_mask = torch.zeros(B, Lb, Lb, dtype=torch.bool)
+        last = torch.zeros(B, dtype=torch.int32)
+        finished = torch.zeros(B, dtype=torch.bool)
+        ar = torch.arange(Lb)
+        steps, step_len_logp, step_syn_logp = 0, [], []
+        for i in range(L):
+            if i == 0:
+                ext[:, 0] = c.len_idx
+                tgt_mask[:, :, 0] = True
+                last[:] = 1
+            len_n, len_logp, syn_n, syn_logp, _ = self.bounding_head(
+                self.pos(self.embed("syn_embed", ext)), memory, src_mask, tgt_mask)
+            steps += 1
+            if self.record:
+                step_len_logp.append(len_logp)
+                step_syn_logp.append(syn_logp)
+            write, new_len, finished = self._box_rule(len_n, syn_n, last, finished)
+            wl = torch.where(write, new_len, torch.zeros_like(new_len))
+            phrase_length[:, i] = wl
+            phrase_syn[:, i] = torch.where(write, syn_n, torch.zeros_like(syn_n))
+            phrase_num += write.int()
+            span = (ar[None, :] >= last[:, None]) & (ar[None, :] < (last + wl)[:, None])
+            ext = torch.where(span, syn_n[:, None].expand(-1, Lb), ext)
+            newlast = last + wl
+            # tgt_mask[j, last:, :last+len] = True ; tgt_mask[j, 0, :last'] = True
+            rows = (ar[None, :, None] >= last[:, None, None]) | (ar[None, :, None] == 0)
+            cols = ar[None, None, :] < newlast[:, None, None]
+            tgt_mask = tgt_mask | (rows & cols & write[:, None, None])
+            last = newlast
+            if bool(finished.all()):
+                break
+        w = int(last[B - 1]) - 1   # stale loop index j == B-1 at TransformerModel.py:1871-1873
+        fill_mask = torch.zeros(B, L, L, dtype=torch.bool)
+        fill_mask[:, :, :max(w, 0)] = True
+        word = torch.full((B, L), c.bos_idx, dtype=torch.long)
+        hidden = self.decoder(self.decoder_input(word, ext[:, 1:-1]), memory, src_mask, fill_mask)
+        logits = self.logit(hidden)
+        logp = F.log_softmax(logits, dim=2) if output_logsoftmax else logits
+        seq = self.sample_next_word(logp, sample_method, temperature, generator)
+        total = phrase_length.sum(1)
+        seq = torch.where(torch.arange(L)[None, :] >= total[:, None], torch.zeros_like(seq), seq)
+        if self.record:
+            self.trace.update(steps=steps, last=last.clone(), fill_width=w, ext=ext.clone(),
+                              fill_hidden=hidden, logits=logits,
+                              step_len_logp=step_len_logp, step_syn_logp=step_syn_logp)
+        self.last_steps = steps
+        return seq, logp, phrase_num, phrase_length[:, :-2], phrase_syn[:, :-2]
+
+    # ---- A14: SAIC ------------------------------------------------------------------------
+    def decode_saic(self, memory, src_mask, output_logsoftmax=1, sample_method="greedy",
+                    temperature=1.0, generator=None):
+        c = self.cfg
+        B, Lb, L, V = memory.size(0), c.seq_length + 2, c.seq_length, c.tgt_vocab
+        phrase_num = torch.zeros(B, dtype=torch.int32)
+        phrase_length = torch.zeros(B, Lb, dtype=torch.int32)
+        phrase_syn = torch.full((B, Lb), c.pad_idx, dtype=torch.long)
+        seq = torch.full((B, Lb), c.pad_idx, dtype=torch.long)
+        seq_logp = torch.zeros(B, Lb, V)
+        ext_len = torch.full((B, Lb), c.pad_idx, dtype=torch.long)
+        ext = torch.full((B, Lb), c.pad_idx, dtype=torch.long)
+        ext_syn = torch.full((B, Lb), c.pad_idx, dtype=torch.long)
+        len_mask = torch.zeros(B, Lb, Lb, dtype=torch.bool)
+        phrase_mask = torch.zeros(B, Lb, Lb, dtype=torch.bool)
+        finished = torch.zeros(B, dtype=torch.bool)
+        seq_last = torch.zeros(B, dtype=torch.int32)
+        phrase_last = torch.zeros(B, dtype=torch.int32)
+        ar = torch.arange(Lb)
+        steps = 0
+        for i in range(1, L + 1):
+            if i == 1:
+                seq[:, 0] = c.bos_idx
+                phrase_length[:, 0] = 1
+                ext_len[:, 0] = c.len_idx
+                len_mask[:, :, 0] = True
+                phrase_last[:] = 1
+            len_n, _, syn_n, _, _ = self.bounding_head(
+                self.pos(self.embed("tgt_embed", ext_len)), memory, src_mask, len_mask)
+            steps += 1
+            write, new_len, finished = self._box_rule(len_n, syn_n, phrase_last, finished)
+            n = torch.where(write, new_len, torch.zeros_like(new_len))
+            phrase_length[:, i] = n
+            phrase_syn[:, i] = torch.where(write, syn_n, torch.zeros_like(syn_n))
+            phrase_num += write.int()
+            m = phrase_length[:, i - 1]
+            # position-wise copy of the previous phrase (TransformerModel.py:1928-1948)
+            for j in range(B):
+                nj, mj, p, s = int(n[j]), int(m[j]), int(phrase_last[j]), int(seq_last[j])
+                if nj == 0:
+                    continue
+                ext_syn[j, p:p + nj] = phrase_syn[j, i]
+                if nj <= mj:
+                    ext[j, p:p + nj] = seq[j, s + (mj - nj): s + mj]
+                else:
+                    pre_less, ct = mj - (nj % mj), nj // mj
+                    reps = torch.tensor([ct if k < pre_less else ct + 1 for k in range(mj)])
+                    ext[j, p:p + nj] = torch.repeat_interleave(seq[j, s:s + mj], reps)
+                phrase_mask[j, p:, :p + nj] = True
+            hidden = self.decoder(self.decoder_input(ext[:, 1:-1], ext_syn[:, 1:-1]), memory, src_mask,
+                                  phrase_mask[:, 1:-1, 1:-1])
+            logits = self.logit(hidden)
+            logp = F.log_softmax(logits, dim=2) if output_logsoftmax else logits
+            if bool(torch.isnan(logp).any()):      # "phrase nan!" early return (:1956-1958)
+                self.last_steps = steps
+                return seq[:, 1:-1], seq_logp[:, 1:-1], phrase_num, phrase_length[:, 1:-1], phrase_syn[:, 1:-1]
+            tok = self.sample_next_word(logp, sample_method, temperature, generator)
+            for j in range(B):
+                nj, p = int(n[j]), int(phrase_last[j])
+                if nj == 0:
+                    continue
+                seq[j, p:p + nj] = tok[j, p - 1:p - 1 + nj]
+                seq_logp[j, p:p + nj] = logp[j, p - 1:p - 1 + nj]
+                ext_len[j, p:p + nj] = tok[j, p - 1:p - 1 + nj]
+                len_mask[j, p:, :p + nj] = True
+                phrase_last[j] += nj
+                len_mask[j, 0, :int(phrase_last[j])] = True
+                seq_last[j] += int(m[j])
+            if bool(finished.all()):
+                break
+        self.last_steps = steps
+        return seq[:, 1:-1], seq_logp[:, 1:-1], phrase_num, phrase_length[:, 1:-1], phrase_syn[:, 1:-1]
+
+    # ---- A12 ------------------------------------------------------------------------------
+    @staticmethod
+    def sample_next_word(logp, sample_method="greedy", temperature=1.0, generator=None):
+        if sample_method == "greedy":
+            return logp.argmax(2)            # first maximal index, like torch.max(dim=2)
+        lp = logp / temperature
+        lp = lp.masked_fill(torch.isnan(lp), -10.0)
+        probs = F.softmax(lp, dim=-1)
+        flat = torch.multinomial(probs.view(-1, probs.size(-1)), 1, generator=generator)
+        return flat.view(logp.shape[:2])
+
+    # ---- A13: the `_sample` entry ---------------------------------------------------------
+    @torch.no_grad()
+    def sample(self, fc_feats, att_feats, att_masks=None, opt=None):
+        opt = opt or {}
+        mode = opt.get("train_mode", "NAIC")
+        sample_n = int(opt.get("sample_n", 1))
+        x, src_mask = self.prepare(att_feats, att_masks)
+        memory = self.encode(x, src_mask)
+        if self.record:
+            self.trace["memory"] = memory
+        if sample_n > 1:
+            memory = memory.repeat_interleave(sample_n, 0)
+            src_mask = src_mask.repeat_interleave(sample_n, 0)
+        t0 = time.time()
+        fn = {"NAIC": self.decode_naic, "SAIC": self.decode_saic}[mode]
+        out = fn(memory, src_mask, opt.get("output_logsoftmax", 1),
+                 opt.get("sample_method", "greedy"), opt.get("temperature", 1.0))
+        return tuple(out) + (time.time() - t0,)
