@@ -1,0 +1,273 @@
+#!/usr/bin/env python
+"""Benchmark of the BoFi greedy decode hot path (BASELINE.json: captions/sec/GPU, uic_sd, 36x2048 regions).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--regions R]
+                  [--precision bf16|fp32] [--mode NAIC] [--no-logprobs]
+
+One "step" = one `_sample` of a batch of B synthetic images on each GPU (encode + bounding + filling +
+vocab log-softmax/argmax).  N > 1 runs one process per GPU under torchrun (batch sharded by image, no
+collective on the data path, weak scaling: B images per GPU).  Rank 0 prints ONE JSON line.
+
+The `reference` arm times the reference algorithm's CPU restatement (oracle/bofi_oracle.py, "port") on the
+host cores of this box on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "captions/sec/GPU greedy BoFi decode (uic_sd, 36x2048 regions)"
+CPU_SAMPLE_IMAGES = 64
+
+
+def useful_flops_per_caption(R, S, V=9491, n_enc=6, n_dec=6, d=512, dff=2048, L=20, Lb=22):
+    """SURVEY.md Appendix C, 'useful' formulation (N_len = 1)."""
+    mm = lambda m, n, k: 2.0 * m * n * k
+    att = lambda q, k: 2.0 * mm(q, k, d)
+    enc = 4 * mm(R, d, d) + att(R, R) + 2 * mm(R, dff, d)
+    dec = 6 * mm(L, d, d) + 2 * mm(R, d, d) + att(L, L) + att(L, R) + 2 * mm(L, dff, d)
+    heads = 2 * mm(1, 100, d) + mm(1, 20, 100) + mm(1, 10, 100)
+    bound = 2 * mm(Lb, d, d) + 2 * mm(R, d, d) + S * (4 * mm(1, d, d) + att(1, Lb) + att(1, R) + 2 * mm(1, dff, d) + heads)
+    return mm(R, d, 2048) + n_enc * enc + bound + n_dec * dec + mm(L, V, d)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+def cpu_reference_run(steps, warmup, cfg, sd, R, mode, images=CPU_SAMPLE_IMAGES):
+    """The reference algorithm on host cores (oracle port), bounded sample of the workload."""
+    from boficap_b200 import synth
+    from oracle.bofi_oracle import BofiOracle, OracleConfig
+    torch.set_num_threads(os.cpu_count() or 1)
+    fc, att, _ = synth.synth_inputs(images, R, seed=1)
+    o = BofiOracle(sd, OracleConfig(**cfg.to_dict()))
+    kw = {"sample_method": "greedy", "beam_size": 1, "sample_n": 1, "train_mode": mode}
+    for _ in range(warmup):
+        o.sample(fc, att, None, kw)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.sample(fc, att, None, kw)
+    dt = time.perf_counter() - t0
+    return images * steps / dt, dt / steps, torch.get_num_threads(), o.last_steps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="images per GPU per step")
+    ap.add_argument("--regions", type=int, default=36)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--mode", default="NAIC", choices=["NAIC"])
+    ap.add_argument("--calib", default="s_real")
+    ap.add_argument("--no-logprobs", action="store_true", help="skip materialising the [B,20,V] log-prob tensor")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    a = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+
+    from boficap_b200 import synth
+    from boficap_b200.layout import BofiConfig
+    cfg = BofiConfig()
+    workload = "uic_sd greedy BoFi decode (%s), batch %d/GPU, %d regions x 2048, %s" % (a.mode, a.batch, a.regions, a.precision)
+    config = {"workload": workload, "checkpoint": "synthetic seed 0, calibration " + a.calib, "global_batch": a.batch * world,
+              "regions": a.regions, "parallelism": "image-sharded replicas x%d" % world,
+              "l2": "per-step input (%.0f MB/GPU) and activations exceed the 126 MB L2" % (a.batch * a.regions * 2048 * 4 / 1e6),
+              "logprobs": "skipped" if a.no_logprobs else "materialised [B,20,V] fp32"}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        sd = synth.synth_state_dict(cfg, 0, a.calib)
+        cps, sec, cores, S = cpu_reference_run(max(1, a.steps), max(1, a.warmup), cfg, sd, a.regions, a.mode)
+        sample = "%d images/step x %d steps, oracle port of the reference formulation, fp32, S=%d" % (CPU_SAMPLE_IMAGES, a.steps, S)
+        line = {"impl": "reference", "metric": METRIC, "value": cps, "unit": "captions/s", "n_gpus": a.gpus, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": cps, "unit": "captions/s", "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": cps, "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from boficap_b200.engine import BofiEngine
+
+    sd = synth.synth_state_dict(cfg, 0, a.calib)
+    eng = BofiEngine(cfg, local_rank, a.precision).load_state_dict(sd)
+    B, R = a.batch, a.regions
+    fc, att_host, _ = synth.synth_inputs(B, R, seed=1 + rank)
+    att_host = att_host.pin_memory()
+    att = att_host.cuda(non_blocking=True)
+    want_lp = not a.no_logprobs
+
+    def step():
+        eng.encode(att, None)
+        return eng.decode(a.mode, 1, 1, want_lp)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        out = step()
+    torch.cuda.synchronize()
+    info = eng.decode_info()
+    launches_per_step = info["kernel_launches"]
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(a.steps):
+        out = step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: the host-buffer entry point (H2D of the features and D2H of captions + boxes inside the timed region)
+    host_out = eng.sample_host(att_host, None, a.mode, 1, 1, want_logprobs=False)
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        eng.sample_host(att_host, None, a.mode, 1, 1, out=host_out)
+    e1.record()
+    barrier()
+    ms_e2e = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3 * 0.0)
+    h2d = att_host.numel() * 4
+    d2h = sum(host_out[k].numel() * host_out[k].element_size() for k in ("seq", "pnum", "plen", "psyn"))
+
+    if dist is not None:
+        t = torch.tensor([ms, ms_e2e], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+
+    # ---- per-kernel-class profile of one more step (CUDA events around every launch of the library)
+    eng.set_profiling(True)
+    step()
+    prof = eng.get_profile()
+    eng.set_profiling(False)
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    S = info["bounding_steps"]
+    value = world * B * a.steps / (ms / 1e3)
+    e2e_value = world * B * a.steps / (ms_e2e / 1e3)
+    burst, sustained, hbm, how = measured_peaks()
+    g = prof["gemm_tcgen05"] if a.precision == "bf16" else prof["gemm_ffma"]
+    gemm_tflops = g["flops"] / (g["ms"] / 1e3) / 1e12 if g["ms"] > 0 else 0.0
+    peak = sustained if a.precision == "bf16" else 75.0
+    total_ms = sum(v["ms"] for v in prof.values())
+    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05)" if a.precision == "bf16" else "gemm_simt_kernel (FFMA)",
+                "achieved": gemm_tflops, "peak": peak, "unit": "TFLOP/s", "frac": gemm_tflops / peak if peak else None,
+                "peak_source": "%s bf16 sustained (kernel timed inside a long step)" % how if a.precision == "bf16" else "nominal fp32 FFMA",
+                "traffic": None, "launches_per_step": g["launches"], "ms_per_step": g["ms"],
+                "share_of_step": g["ms"] / total_ms if total_ms else None,
+                "whole_path_useful_tflops": value / world * useful_flops_per_caption(R, S) / 1e12,
+                "whole_path_frac_of_burst": value / world * useful_flops_per_caption(R, S) / 1e12 / burst,
+                "classes": {k: {"launches": v["launches"], "ms": round(v["ms"], 4),
+                                "tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 2) if v["ms"] > 0 else 0.0,
+                                "gbs": round(v["bytes"] / (v["ms"] / 1e3) / 1e9, 1) if v["ms"] > 0 else 0.0}
+                            for k, v in prof.items()}}
+
+    cpu = None
+    if world == 1 or True:
+        cps, sec, cores, Scpu = cpu_reference_run(a.cpu_steps, 1, cfg, sd, R, a.mode)
+        cpu = {"value": cps, "unit": "captions/s", "cores": cores, "kind": "port",
+               "sample": "%d images x %d calls of the oracle port (reference formulation, fp32), S=%d" % (CPU_SAMPLE_IMAGES, a.cpu_steps, Scpu)}
+
+    line = {"metric": METRIC, "value": value, "unit": "captions/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": a.precision, "data": "synthetic", "config": config,
+            "e2e": {"value": e2e_value, "unit": "captions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / a.steps, "api": "bofi_sample_host (pinned host buffers)"},
+            "gpu_launches": launches_per_step * a.steps, "bounding_steps": S, "fill_width": info["fill_width"],
+            "nan_batch": info["nan_batch"], "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

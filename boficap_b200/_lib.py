@@ -1,0 +1,77 @@
+"""ctypes binding of libbofi_b200.so (include/bofi_b200.h).  There is no fallback: if the shared
+library is missing or does not export the ABI declared in the header, importing raises."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libbofi_b200.so")
+
+ABI_VERSION = 1
+OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NOMEM = 0, 1, 2, 3, 4
+PRECISION = {"fp32": 0, "bf16": 1}
+MODE = {"NAIC": 0, "SAIC": 1}
+
+
+class BofiConfigC(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "abi_version", "tgt_vocab", "att_feat_size", "n_enc", "n_dec", "n_len", "d_model", "d_ff", "heads",
+        "seq_length", "pad_idx", "bos_idx", "eos_idx", "len_idx", "precision")]
+
+
+class DecodeInfoC(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("bounding_steps", "fill_width", "kernel_launches", "nan_batch")]
+
+
+class BofiError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libbofi_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+_P = C.c_void_p
+_I = C.c_int32
+_SIGNATURES = {
+    "bofi_last_error": (C.c_char_p, []),
+    "bofi_abi_version": (C.c_int, []),
+    "bofi_create": (C.c_int, [C.POINTER(BofiConfigC), C.c_int, C.POINTER(_P)]),
+    "bofi_destroy": (C.c_int, [_P]),
+    "bofi_set_weight": (C.c_int, [_P, C.c_char_p, _P, C.c_int64]),
+    "bofi_missing_weights": (C.c_int, [_P]),
+    "bofi_finalize_weights": (C.c_int, [_P, _P]),
+    "bofi_workspace_bytes": (C.c_int64, [_P, _I, _I, _I]),
+    "bofi_encode": (C.c_int, [_P, _P, _P, _P, _I, _I, _P]),
+    "bofi_decode": (C.c_int, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "bofi_sample_host": (C.c_int, [_P, _P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P]),
+    "bofi_get_decode_info": (C.c_int, [_P, _P, C.POINTER(DecodeInfoC)]),
+    "bofi_set_profiling": (C.c_int, [_P, _I]),
+    "bofi_get_profile": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "bofi_layernorm_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, _I]),
+    "bofi_linear_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I]),
+    "bofi_attention_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I]),
+}
+EXPORTS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s is missing: build it with `python -m boficap_b200.build` "
+                          "(there is no CPU / PyTorch fallback for this path)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)        # AttributeError if the .so does not export the header's ABI
+        fn.restype = res
+        fn.argtypes = args
+    if lib.bofi_abi_version() != ABI_VERSION:
+        raise ImportError("libbofi_b200.so ABI %d != binding ABI %d" % (lib.bofi_abi_version(), ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def check(code):
+    if code != OK:
+        raise BofiError(code, load().bofi_last_error().decode("utf-8", "replace"))

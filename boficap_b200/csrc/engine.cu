@@ -1,0 +1,857 @@
+// libbofi_b200.so -- host orchestration + C ABI (include/bofi_b200.h) of the BoFi decode path.
+//
+// Data layout in HBM (rows are always d_model = 512 wide, row-major):
+//   residual stream x      fp32 [rows, 512]            (kept fp32 in both precisions)
+//   GEMM operands          T    [rows, K]              T = float (fp32 mode) | bf16 (bf16 mode)
+//   fused QKV              T    [rows, 1536]           Q | K | V column blocks, heads 64 wide inside each
+//   cross K/V of `memory`  T    [B*R, 1024] per decoder-style layer, projected ONCE per decode
+//   logits                 fp32 [rows*L, Vpad]         Vpad = V rounded to 32 (16-byte pitched rows)
+// Reference citations are relative to /root/reference/captioning/models/.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/bofi_b200.h"
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+
+using namespace bofi;
+
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CU_TRY(expr)                                                                                   \
+  do {                                                                                                 \
+    cudaError_t e__ = (expr);                                                                          \
+    if (e__ != cudaSuccess)                                                                            \
+      return fail(BOFI_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+  } while (0)
+#define RC_TRY(expr)            \
+  do {                          \
+    int rc__ = (expr);          \
+    if (rc__ != BOFI_OK) return rc__; \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return BOFI_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + (bytes >> 3) + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(BOFI_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    }
+    cap = want;
+    return BOFI_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename U> U* as() const { return reinterpret_cast<U*>(p); }
+};
+
+struct Lin {          // nn.Linear: weight [N,K] (K-major), bias [N]
+  const float* w32 = nullptr;
+  const bf16* w16 = nullptr;
+  const float* b = nullptr;
+  int N = 0, K = 0;
+};
+struct Norm { const float* a = nullptr; const float* b = nullptr; };
+struct SelfAttn { Lin qkv, o; };
+struct CrossAttn { Lin q, kv, o; };
+struct Layer {        // EncoderLayer (cross == false) / DecoderLayer / LengthPredictorLayer
+  bool cross = false;
+  SelfAttn sa;
+  CrossAttn ca;
+  Lin w1, w2;
+  Norm ln[3];
+};
+
+struct WeightEntry { float* dev = nullptr; int64_t numel = 0; bool loaded = false; bool used = true; };
+
+// Optional per-launch CUDA-event timing (bofi_set_profiling): one record per kernel launch.
+enum { PC_GEMM_TC = 0, PC_GEMM_SIMT, PC_ATTENTION, PC_LAYERNORM, PC_VOCAB, PC_OTHER, PC_COUNT };
+struct ProfRec { int cls; double flops, bytes; cudaEvent_t a, b; };
+
+struct bofi_engine {
+  bofi_config_t cfg;
+  int device = 0;
+  int Lb = 22, L = 20, V = 0, Vpad = 0;
+  bool bf16_mode = false;
+  bool use_tc = true;
+  bool finalized = false;
+  std::unordered_map<std::string, WeightEntry> weights;
+  std::vector<std::string> order;
+  std::vector<DevBuf> packed;          // fused / converted weight storage
+  // model
+  Lin att_embed, generator, head1;     // head1 = [Length_classifier1 ; Syntactic_classifier1]  (N = 200)
+  std::vector<Layer> enc, dec, lp;
+  Layer lp0;                           // N_len == 0: cross attention only (length_attn + LengthPredictor.norm)
+  Norm enc_norm, dec_norm, lp_norm;
+  const float *w_len2 = nullptr, *b_len2 = nullptr, *w_syn2 = nullptr, *b_syn2 = nullptr;
+  DevBuf bound_in, fill_in;            // (id, position) input tables
+  // workspace
+  DevBuf attT, x, y, qkv, ao, q, ffh, memT, attlen, hrow, hid, logits, state_i32, tok;
+  std::vector<DevBuf> kv;              // cross K/V per bounding layer then per decoder layer
+  DevBuf h_in, h_len, h_seq, h_logp, h_pnum, h_plen, h_psyn;   // device staging of the *_host entry point
+  DevBuf unit_a, unit_w, unit_o;
+  // batch left by bofi_encode
+  int B = 0, R = 0;
+  bool have_len = false;
+  bool have_memory = false;
+  int launches = 0;
+  bool profiling = false;
+  std::vector<ProfRec> recs;
+  DecodeState st{};
+  int st_rows = 0;
+};
+
+static int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+struct ProfScope {
+  bofi_engine* e;
+  cudaStream_t s;
+  size_t idx = 0;
+  bool on;
+  ProfScope(bofi_engine* e_, cudaStream_t s_, int cls, double flops, double bytes) : e(e_), s(s_), on(e_->profiling) {
+    e->launches++;
+    if (!on) return;
+    ProfRec r{cls, flops, bytes, nullptr, nullptr};
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, s);
+    idx = e->recs.size();
+    e->recs.push_back(r);
+  }
+  ~ProfScope() {
+    if (on) cudaEventRecord(e->recs[idx].b, s);
+  }
+};
+
+// ---- state_dict spec (mirrors boficap_b200/layout.py:state_spec) ---------------------------------
+static void spec_add(bofi_engine* e, const std::string& name, int64_t numel, bool used = true) {
+  WeightEntry w;
+  w.numel = numel;
+  w.used = used;
+  e->weights[name] = w;
+  e->order.push_back(name);
+}
+static void spec_attn(bofi_engine* e, const std::string& p, int d, bool used = true) {
+  for (int i = 0; i < 4; ++i) {
+    spec_add(e, p + ".linears." + std::to_string(i) + ".weight", (int64_t)d * d, used);
+    spec_add(e, p + ".linears." + std::to_string(i) + ".bias", d, used);
+  }
+}
+static void spec_ffn(bofi_engine* e, const std::string& p, int d, int dff, bool used = true) {
+  spec_add(e, p + ".w_1.weight", (int64_t)dff * d, used);
+  spec_add(e, p + ".w_1.bias", dff, used);
+  spec_add(e, p + ".w_2.weight", (int64_t)d * dff, used);
+  spec_add(e, p + ".w_2.bias", d, used);
+}
+static void spec_norm(bofi_engine* e, const std::string& p, int d) {
+  spec_add(e, p + ".a_2", d);
+  spec_add(e, p + ".b_2", d);
+}
+static void spec_layer(bofi_engine* e, const std::string& p, int d, int dff, bool cross, const char* ff) {
+  spec_attn(e, p + ".self_attn", d);
+  if (cross) spec_attn(e, p + ".src_attn", d);
+  spec_ffn(e, p + "." + ff, d, dff);
+  for (int s = 0; s < (cross ? 3 : 2); ++s) spec_norm(e, p + ".sublayer." + std::to_string(s) + ".norm", d);
+}
+static void build_spec(bofi_engine* e) {
+  const bofi_config_t& c = e->cfg;
+  const int d = c.d_model, dff = c.d_ff;
+  spec_add(e, "att_embed.0.weight", (int64_t)d * c.att_feat_size);
+  spec_add(e, "att_embed.0.bias", d);
+  for (int l = 0; l < c.n_enc; ++l) spec_layer(e, "model.encoder.layers." + std::to_string(l), d, dff, false, "feed_forward");
+  spec_norm(e, "model.encoder.norm", d);
+  for (int l = 0; l < c.n_dec; ++l) spec_layer(e, "model.decoder.layers." + std::to_string(l), d, dff, true, "feed_forward");
+  spec_norm(e, "model.decoder.norm", d);
+  spec_add(e, "model.syn_embed.lut.weight", 10LL * d);
+  spec_add(e, "model.tgt_embed.lut.weight", (int64_t)c.tgt_vocab * d);
+  spec_add(e, "model.pos_embed.pe", 5000LL * d);
+  spec_add(e, "model.generator.proj.weight", (int64_t)c.tgt_vocab * d);
+  spec_add(e, "model.generator.proj.bias", c.tgt_vocab);
+  const std::string lp = "model.length_predictor";
+  const bool lp_direct = (c.n_len == 0);          // length_attn / ff are only live when N_len == 0 (:369-370)
+  spec_attn(e, lp + ".length_attn", d, lp_direct);
+  spec_ffn(e, lp + ".ff", d, dff, false);
+  spec_norm(e, lp + ".norm", d);
+  spec_add(e, lp + ".Length_classifier1.weight", 100LL * d);
+  spec_add(e, lp + ".Length_classifier1.bias", 100);
+  spec_add(e, lp + ".Length_classifier2.weight", 20LL * 100);
+  spec_add(e, lp + ".Length_classifier2.bias", 20);
+  spec_add(e, lp + ".Syntactic_classifier1.weight", 100LL * d);
+  spec_add(e, lp + ".Syntactic_classifier1.bias", 100);
+  spec_add(e, lp + ".Syntactic_classifier2.weight", 10LL * 100);
+  spec_add(e, lp + ".Syntactic_classifier2.bias", 10);
+  if (c.n_len == 0) spec_norm(e, lp + ".LengthPredictor.norm", d);
+  for (int l = 0; l < c.n_len; ++l) spec_layer(e, lp + ".LengthPredictor." + std::to_string(l), d, dff, true, "ff");
+}
+
+// ---- launch helpers ------------------------------------------------------------------------------
+template <typename T> struct Ctx {
+  bofi_engine* e;
+  cudaStream_t s;
+};
+
+template <typename T> static const T* lin_w(const Lin& l);
+template <> const float* lin_w<float>(const Lin& l) { return l.w32; }
+template <> const bf16* lin_w<bf16>(const Lin& l) { return l.w16; }
+
+template <typename T, typename TOut>
+static int linear(bofi_engine* e, cudaStream_t s, const T* A, int lda, const Lin& l, const float* resid, int ldr,
+                  TOut* out, int ldc, int M, int relu, const int* live) {
+  cudaError_t err;
+  const bool tcpath = std::is_same<T, bf16>::value && e->use_tc;
+  ProfScope prof(e, s, tcpath ? PC_GEMM_TC : PC_GEMM_SIMT, 2.0 * M * l.N * l.K,
+                 (double)sizeof(T) * ((double)M * l.K + (double)l.N * l.K) + (double)sizeof(TOut) * M * l.N + (resid ? 4.0 * M * l.N : 0.0));
+  if constexpr (std::is_same<T, bf16>::value) {
+    if (e->use_tc)
+      err = tc::gemm_tc<TOut>(s, A, lda, l.w16, l.K, l.b, resid, ldr, out, ldc, M, l.N, l.K, relu, live);
+    else
+      err = gemm_simt<bf16, TOut>(s, A, lda, l.w16, l.K, l.b, resid, ldr, out, ldc, M, l.N, l.K, relu, live);
+  } else {
+    err = gemm_simt<float, TOut>(s, A, lda, l.w32, l.K, l.b, resid, ldr, out, ldc, M, l.N, l.K, relu, live);
+  }
+  if (err != cudaSuccess) return fail(BOFI_ERR_CUDA, "gemm M=%d N=%d K=%d: %s", M, l.N, l.K, cudaGetErrorString(err));
+  return BOFI_OK;
+}
+
+template <typename TOut>
+static int layernorm(bofi_engine* e, cudaStream_t s, const float* x, size_t in_stride, const Norm& n, TOut* out,
+                     size_t out_stride, int rows, float* f32_copy, const int* live) {
+  if (rows <= 0) return BOFI_OK;
+  ProfScope prof(e, s, PC_LAYERNORM, 8.0 * rows * kD, (double)rows * kD * (4 + sizeof(TOut) + (f32_copy ? 4 : 0)));
+  layernorm_kernel<TOut><<<ceil_div(rows, 8), 256, 0, s>>>(x, in_stride, n.a, n.b, out, out_stride, rows, f32_copy, live);
+  CU_TRY(cudaGetLastError());
+  return BOFI_OK;
+}
+
+template <typename T>
+static int attention(bofi_engine* e, cudaStream_t s, const T* Q, int ldq, const T* K, const T* V, int ldkv, T* O, int ldo,
+                     int nb, int Tq, int Tk, const int* vis, int vis_bs, int vis_qs, int vis_div, int kv_div,
+                     const int* live) {
+  if (nb <= 0) return BOFI_OK;
+  if (Tk > kMaxKeys) return fail(BOFI_ERR_INVALID, "attention over %d keys (max %d)", Tk, kMaxKeys);
+  const size_t smem = attention_smem_bytes(Tk);
+  static size_t configured_f = 0, configured_h = 0;
+  size_t& configured = std::is_same<T, float>::value ? configured_f : configured_h;
+  if (smem > configured) {
+    CU_TRY(cudaFuncSetAttribute(attention_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attention_smem_bytes(kMaxKeys)));
+    configured = attention_smem_bytes(kMaxKeys);
+  }
+  dim3 grid(e->cfg.heads, nb);
+  ProfScope prof(e, s, PC_ATTENTION, 4.0 * nb * Tq * Tk * kD, (double)sizeof(T) * kD * ((double)nb * Tq * 2 + 2.0 * (nb / kv_div) * Tk));
+  attention_kernel<T><<<grid, 128, smem, s>>>(Q, ldq, K, V, ldkv, O, ldo, Tq, Tk, vis, vis_bs, vis_qs, vis_div, kv_div,
+                                              1.0f / sqrtf((float)kHeadDim), live);
+  CU_TRY(cudaGetLastError());
+  return BOFI_OK;
+}
+
+// One pre-norm layer (SublayerConnection, TransformerModel.py:1351-1363) over x fp32 [nb*T, 512]:
+//   encoder layer (:1365-1377)          self-attn over the nb*T rows' own block, keys masked by self_vis
+//   decoder / bounding layer (:1398-1413, :1016-1029)   + cross attention over memory K/V
+template <typename T>
+static int run_layer(bofi_engine* e, cudaStream_t s, const Layer& ly, float* x, int nb, int T_, const int* self_vis,
+                     int self_vis_bs, int self_vis_qs, const T* kvmem, int R, const int* mem_len, int kv_div,
+                     const int* live) {
+  const int rows = nb * T_;
+  T* y = e->y.as<T>();
+  T* qkv = e->qkv.as<T>();
+  T* ao = e->ao.as<T>();
+  T* ffh = e->ffh.as<T>();
+  RC_TRY(layernorm<T>(e, s, x, kD, ly.ln[0], y, kD, rows, nullptr, live));
+  RC_TRY((linear<T, T>(e, s, y, kD, ly.sa.qkv, nullptr, 0, qkv, 3 * kD, rows, 0, live)));
+  RC_TRY(attention<T>(e, s, qkv, 3 * kD, qkv + kD, qkv + 2 * kD, 3 * kD, ao, kD, nb, T_, T_, self_vis, self_vis_bs,
+                      self_vis_qs, 1, 1, live));
+  RC_TRY((linear<T, float>(e, s, ao, kD, ly.sa.o, x, kD, x, kD, rows, 0, live)));
+  int f = 1;
+  if (ly.cross) {
+    T* q = e->q.as<T>();
+    RC_TRY(layernorm<T>(e, s, x, kD, ly.ln[1], y, kD, rows, nullptr, live));
+    RC_TRY((linear<T, T>(e, s, y, kD, ly.ca.q, nullptr, 0, q, kD, rows, 0, live)));
+    RC_TRY(attention<T>(e, s, q, kD, kvmem, kvmem + kD, 2 * kD, ao, kD, nb, T_, R, mem_len, 1, 0, kv_div, kv_div, live));
+    RC_TRY((linear<T, float>(e, s, ao, kD, ly.ca.o, x, kD, x, kD, rows, 0, live)));
+    f = 2;
+  }
+  RC_TRY(layernorm<T>(e, s, x, kD, ly.ln[f], y, kD, rows, nullptr, live));
+  RC_TRY((linear<T, T>(e, s, y, kD, ly.w1, nullptr, 0, ffh, e->cfg.d_ff, rows, 1, live)));
+  RC_TRY((linear<T, float>(e, s, ffh, e->cfg.d_ff, ly.w2, x, kD, x, kD, rows, 0, live)));
+  return BOFI_OK;
+}
+
+// ---- weight packing --------------------------------------------------------------------------------
+static const float* W(bofi_engine* e, const std::string& name) { return e->weights[name].dev; }
+
+static int pack_rows(bofi_engine* e, cudaStream_t s, const std::vector<const float*>& srcs, const std::vector<int64_t>& numels,
+                     float** out32, bf16** out16) {
+  int64_t total = 0;
+  for (int64_t n : numels) total += n;
+  e->packed.emplace_back();
+  DevBuf& b32 = e->packed.back();
+  RC_TRY(b32.reserve(total * sizeof(float)));
+  int64_t off = 0;
+  for (size_t i = 0; i < srcs.size(); ++i) {
+    CU_TRY(cudaMemcpyAsync(b32.as<float>() + off, srcs[i], numels[i] * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    off += numels[i];
+  }
+  *out32 = b32.as<float>();
+  *out16 = nullptr;
+  if (e->bf16_mode) {
+    e->packed.emplace_back();
+    DevBuf& b16 = e->packed.back();
+    RC_TRY(b16.reserve(total * sizeof(bf16)));
+    cast_kernel<bf16><<<ceil_div(total / 4, 256), 256, 0, s>>>(*out32, b16.as<bf16>(), (size_t)(total / 4));
+    CU_TRY(cudaGetLastError());
+    *out16 = b16.as<bf16>();
+  }
+  return BOFI_OK;
+}
+
+static int make_lin(bofi_engine* e, cudaStream_t s, const std::vector<std::string>& prefixes, int N_each, int K, Lin* out) {
+  std::vector<const float*> ws, bs;
+  std::vector<int64_t> wn, bn;
+  for (const std::string& p : prefixes) {
+    ws.push_back(W(e, p + ".weight"));
+    wn.push_back((int64_t)N_each * K);
+    bs.push_back(W(e, p + ".bias"));
+    bn.push_back(N_each);
+  }
+  float *w32, *b32;
+  bf16 *w16, *b16;
+  RC_TRY(pack_rows(e, s, ws, wn, &w32, &w16));
+  bool keep = e->bf16_mode;
+  e->bf16_mode = false;                           // biases stay fp32
+  int rc = pack_rows(e, s, bs, bn, &b32, &b16);
+  e->bf16_mode = keep;
+  RC_TRY(rc);
+  out->w32 = w32;
+  out->w16 = w16;
+  out->b = b32;
+  out->N = N_each * (int)prefixes.size();
+  out->K = K;
+  return BOFI_OK;
+}
+
+static Norm make_norm(bofi_engine* e, const std::string& p) { return Norm{W(e, p + ".a_2"), W(e, p + ".b_2")}; }
+
+static int make_layer(bofi_engine* e, cudaStream_t s, const std::string& p, bool cross, const char* ff, Layer* ly) {
+  const int d = e->cfg.d_model, dff = e->cfg.d_ff;
+  ly->cross = cross;
+  const std::string sa = p + ".self_attn.linears.";
+  RC_TRY(make_lin(e, s, {sa + "0", sa + "1", sa + "2"}, d, d, &ly->sa.qkv));
+  RC_TRY(make_lin(e, s, {sa + "3"}, d, d, &ly->sa.o));
+  if (cross) {
+    const std::string ca = p + ".src_attn.linears.";
+    RC_TRY(make_lin(e, s, {ca + "0"}, d, d, &ly->ca.q));
+    RC_TRY(make_lin(e, s, {ca + "1", ca + "2"}, d, d, &ly->ca.kv));
+    RC_TRY(make_lin(e, s, {ca + "3"}, d, d, &ly->ca.o));
+  }
+  RC_TRY(make_lin(e, s, {p + "." + ff + ".w_1"}, dff, d, &ly->w1));
+  RC_TRY(make_lin(e, s, {p + "." + ff + ".w_2"}, d, dff, &ly->w2));
+  for (int i = 0; i < (cross ? 3 : 2); ++i) ly->ln[i] = make_norm(e, p + ".sublayer." + std::to_string(i) + ".norm");
+  return BOFI_OK;
+}
+
+// ---- workspace ---------------------------------------------------------------------------------------
+static size_t tsize(bofi_engine* e) { return e->bf16_mode ? 2 : 4; }
+
+static int reserve_encode(bofi_engine* e, int B, int R) {
+  const size_t M = (size_t)B * R, ts = tsize(e);
+  if (e->bf16_mode) RC_TRY(e->attT.reserve(M * e->cfg.att_feat_size * ts));
+  RC_TRY(e->x.reserve(M * kD * 4));
+  RC_TRY(e->y.reserve(M * kD * ts));
+  RC_TRY(e->qkv.reserve(M * 3 * kD * ts));
+  RC_TRY(e->ao.reserve(M * kD * ts));
+  RC_TRY(e->ffh.reserve(M * e->cfg.d_ff * ts));
+  RC_TRY(e->memT.reserve(M * kD * ts));
+  RC_TRY(e->attlen.reserve((size_t)B * 4));
+  return BOFI_OK;
+}
+
+static int state_ints(int rows, int Lb, int L) { return rows * (8 * Lb + L + 6) + 16; }
+
+static int reserve_decode(bofi_engine* e, int B, int R, int sn) {
+  const size_t M = (size_t)B * R, ts = tsize(e), rows = (size_t)B * sn, dr = rows * e->Lb;
+  RC_TRY(e->x.reserve(dr * kD * 4));
+  RC_TRY(e->y.reserve(dr * kD * ts));
+  RC_TRY(e->qkv.reserve(dr * 3 * kD * ts));
+  RC_TRY(e->ao.reserve(dr * kD * ts));
+  RC_TRY(e->q.reserve(dr * kD * ts));
+  RC_TRY(e->ffh.reserve(dr * e->cfg.d_ff * ts));
+  RC_TRY(e->hrow.reserve(rows * kD * 4));
+  RC_TRY(e->hid.reserve(rows * 200 * 4));
+  RC_TRY(e->logits.reserve(rows * e->L * (size_t)e->Vpad * 4));
+  RC_TRY(e->tok.reserve(rows * e->L * 4));
+  const int nkv = std::max(1, e->cfg.n_len) + e->cfg.n_dec;
+  if ((int)e->kv.size() < nkv) e->kv.resize(nkv);
+  for (int i = 0; i < nkv; ++i) RC_TRY(e->kv[i].reserve(M * 2 * kD * ts));
+  RC_TRY(e->state_i32.reserve((size_t)state_ints((int)rows, e->Lb, e->L) * 4));
+  // carve the state arrays
+  int* p = e->state_i32.as<int>();
+  const int r = (int)rows, Lb = e->Lb, L = e->L;
+  DecodeState& st = e->st;
+  st.counters = p; p += 16;
+  st.ext = p; p += r * Lb;
+  st.ext_word = p; p += r * Lb;
+  st.ext_syn = p; p += r * Lb;
+  st.seq22 = p; p += r * Lb;
+  st.vis = p; p += r * Lb;
+  st.phrase_length = p; p += r * Lb;
+  st.phrase_syn = p; p += r * Lb;
+  st.vis_fill = p; p += r * L;
+  st.last = p; p += r;
+  st.seq_last = p; p += r;
+  st.step_len = p; p += r;
+  st.finished = p; p += r;
+  st.phrase_num = p; p += r;
+  e->st_rows = r;
+  return BOFI_OK;
+}
+
+// ---- encode --------------------------------------------------------------------------------------------
+template <typename T>
+static int encode_impl(bofi_engine* e, cudaStream_t s, const float* att, const int* att_len, int B, int R, float* memory_out) {
+  const int M = B * R, F = e->cfg.att_feat_size;
+  RC_TRY(reserve_encode(e, B, R));
+  float* x = e->x.as<float>();
+  const T* a_in;
+  if constexpr (std::is_same<T, bf16>::value) {
+    const size_t n4 = (size_t)M * F / 4;
+    {
+      ProfScope prof(e, s, PC_OTHER, 0.0, (double)M * F * 6.0);
+      cast_kernel<bf16><<<(int)std::min<size_t>((n4 + 255) / 256, 148 * 16), 256, 0, s>>>(att, e->attT.as<bf16>(), n4);
+    }
+    CU_TRY(cudaGetLastError());
+    a_in = e->attT.as<bf16>();
+  } else {
+    a_in = att;
+  }
+  // att_embed = Linear(2048, 512) + ReLU (TransformerModel.py:1642-1647); padded rows -> 0 (AttModel.py:46-51)
+  RC_TRY((linear<T, float>(e, s, a_in, F, e->att_embed, nullptr, 0, x, kD, M, 1, nullptr)));
+  const int* len_dev = nullptr;
+  e->have_len = (att_len != nullptr);
+  if (att_len) {
+    if (att_len != e->attlen.as<int>())
+      CU_TRY(cudaMemcpyAsync(e->attlen.p, att_len, (size_t)B * 4, cudaMemcpyDeviceToDevice, s));
+    len_dev = e->attlen.as<int>();
+    {
+      ProfScope prof(e, s, PC_OTHER, 0.0, 0.0);
+      zero_padded_rows_kernel<<<ceil_div(M, 8), 256, 0, s>>>(x, len_dev, B, R);
+    }
+    CU_TRY(cudaGetLastError());
+  }
+  for (const Layer& ly : e->enc)
+    RC_TRY(run_layer<T>(e, s, ly, x, B, R, len_dev, 1, 0, (const T*)nullptr, 0, nullptr, 1, nullptr));
+  RC_TRY(layernorm<T>(e, s, x, kD, e->enc_norm, e->memT.as<T>(), kD, M, memory_out, nullptr));
+  e->B = B;
+  e->R = R;
+  e->have_memory = true;
+  return BOFI_OK;
+}
+
+// ---- decode --------------------------------------------------------------------------------------------
+template <typename T>
+static int project_memory_kv(bofi_engine* e, cudaStream_t s, const Lin& kv, DevBuf& out) {
+  return linear<T, T>(e, s, e->memT.as<T>(), kD, kv, nullptr, 0, out.as<T>(), 2 * kD, e->B * e->R, 0, nullptr);
+}
+
+// One bounding step of core_NAIC / core_SAIC: bounding head on the current slots, then the box rule.
+template <typename T>
+static int bounding_step(bofi_engine* e, cudaStream_t s, int rows, int sn, int step_col, int saic) {
+  const bofi_config_t& c = e->cfg;
+  const int Lb = e->Lb;
+  const int* live = e->st.counters;
+  const int* mem_len = e->have_len ? e->attlen.as<int>() : nullptr;
+  float* x = e->x.as<float>();
+  const int Tb = (c.n_len == 0) ? 1 : Lb;   // without self-attention only the [LEN] row matters (:369-375)
+  {
+    ProfScope prof(e, s, PC_OTHER, 0.0, 0.0);
+    if (!saic) {
+      gather_table_kernel<<<ceil_div(rows * Tb, 8), 256, 0, s>>>(e->bound_in.as<float>(), Lb, e->st.ext, Lb, 0, x, rows * Tb, Tb, live);
+    } else {
+      embed_words_kernel<<<ceil_div(rows * Tb, 8), 256, 0, s>>>(W(e, "model.tgt_embed.lut.weight"), nullptr, W(e, "model.pos_embed.pe"),
+                                                                e->st.ext, nullptr, Lb, 0, sqrtf((float)kD), x, rows * Tb, Tb, live);
+    }
+  }
+  CU_TRY(cudaGetLastError());
+  if (c.n_len == 0) {
+    const Layer& ly = e->lp0;
+    T* y = e->y.as<T>();
+    T* q = e->q.as<T>();
+    T* ao = e->ao.as<T>();
+    RC_TRY(layernorm<T>(e, s, x, kD, ly.ln[0], y, kD, rows, nullptr, live));
+    RC_TRY((linear<T, T>(e, s, y, kD, ly.ca.q, nullptr, 0, q, kD, rows, 0, live)));
+    RC_TRY(attention<T>(e, s, q, kD, e->kv[0].as<T>(), e->kv[0].as<T>() + kD, 2 * kD, ao, kD, rows, 1, e->R, mem_len, 1, 0, sn, sn, live));
+    RC_TRY((linear<T, float>(e, s, ao, kD, ly.ca.o, x, kD, x, kD, rows, 0, live)));
+  } else {
+    for (int l = 0; l < c.n_len; ++l)
+      RC_TRY(run_layer<T>(e, s, e->lp[l], x, rows, Lb, e->st.vis, Lb, 1, e->kv[l].as<T>(), e->R, mem_len, sn, live));
+  }
+  // norm -> [LEN] row -> classifier1 of both heads (always fp32: the heads are gain sensitive)
+  RC_TRY(layernorm<float>(e, s, x, (size_t)Tb * kD, e->lp_norm, e->hrow.as<float>(), kD, rows, nullptr, live));
+  {
+    ProfScope prof(e, s, PC_GEMM_SIMT, 2.0 * rows * 200 * kD, 4.0 * (rows * (kD + 200.0) + 200.0 * kD));
+    cudaError_t err = gemm_simt<float, float>(s, e->hrow.as<float>(), kD, e->head1.w32, kD, e->head1.b, nullptr, 0,
+                                              e->hid.as<float>(), 200, rows, 200, kD, 1, live);
+    if (err != cudaSuccess) return fail(BOFI_ERR_CUDA, "head gemm: %s", cudaGetErrorString(err));
+  }
+  const size_t smem = sizeof(float) * (30 * 100 + 4 * 200 + 4 * 32);
+  {
+    ProfScope prof(e, s, PC_OTHER, 0.0, 0.0);
+    bound_head_kernel<<<ceil_div(rows, 4), 128, smem, s>>>(e->hid.as<float>(), 100, e->w_len2, e->b_len2, e->w_syn2, e->b_syn2,
+                                                         20, 10, e->st, rows, Lb, e->L, step_col, saic ? step_col : step_col + 1, 4, 6, saic);
+  }
+  CU_TRY(cudaGetLastError());
+  return BOFI_OK;
+}
+
+template <typename T>
+static int decode_naic(bofi_engine* e, cudaStream_t s, int sn, int output_logsoftmax, long long* seq, float* logprobs,
+                       int* phrase_num, int* phrase_length, long long* phrase_syn) {
+  const bofi_config_t& c = e->cfg;
+  const int rows = e->B * sn, Lb = e->Lb, L = e->L;
+  const int* mem_len = e->have_len ? e->attlen.as<int>() : nullptr;
+  const int nb_layers = std::max(1, c.n_len);
+  // memory K/V of every decoder-style layer, projected once (the reference re-projects per call)
+  if (c.n_len == 0) {
+    RC_TRY(project_memory_kv<T>(e, s, e->lp0.ca.kv, e->kv[0]));
+  } else {
+    for (int l = 0; l < c.n_len; ++l) RC_TRY(project_memory_kv<T>(e, s, e->lp[l].ca.kv, e->kv[l]));
+  }
+  for (int l = 0; l < c.n_dec; ++l) RC_TRY(project_memory_kv<T>(e, s, e->dec[l].ca.kv, e->kv[nb_layers + l]));
+
+  {
+    ProfScope prof(e, s, PC_OTHER, 0.0, 0.0);
+    init_state_kernel<<<ceil_div(rows, 128), 128, 0, s>>>(e->st, rows, Lb, L, c.len_idx, c.bos_idx, 0);
+  }
+  CU_TRY(cudaGetLastError());
+  for (int i = 0; i < L; ++i) RC_TRY(bounding_step<T>(e, s, rows, sn, i, 0));
+
+  // filling step (decode_NA, :570-587): all L slots of every row in parallel
+  {
+    ProfScope prof(e, s, PC_OTHER, 0.0, 0.0);
+    fill_window_kernel<<<ceil_div(rows * L, 256), 256, 0, s>>>(e->st, rows, L);
+  }
+  CU_TRY(cudaGetLastError());
+  float* x = e->x.as<float>();
+  {
+    ProfScope prof(e, s, PC_OTHER, 0.0, 0.0);
+    gather_table_kernel<<<ceil_div(rows * L, 8), 256, 0, s>>>(e->fill_in.as<float>(), L, e->st.ext, Lb, 1, x, rows * L, L, nullptr);
+  }
+  CU_TRY(cudaGetLastError());
+  for (int l = 0; l < c.n_dec; ++l)
+    RC_TRY(run_layer<T>(e, s, e->dec[l], x, rows, L, e->st.vis_fill, L, 1, e->kv[nb_layers + l].as<T>(), e->R, mem_len, sn, nullptr));
+  RC_TRY(layernorm<T>(e, s, x, kD, e->dec_norm, e->y.as<T>(), kD, rows * L, nullptr, nullptr));
+  RC_TRY((linear<T, float>(e, s, e->y.as<T>(), kD, e->generator, nullptr, 0, e->logits.as<float>(), e->Vpad, rows * L, 0, nullptr)));
+  {
+    ProfScope prof(e, s, PC_VOCAB, 0.0, 0.0);
+    vocab_epilogue_kernel<<<rows * L, 256, 0, s>>>(e->logits.as<float>(), e->Vpad, e->V, logprobs, seq, e->st.last, -1, L,
+                                                 output_logsoftmax, nullptr);
+  }
+  CU_TRY(cudaGetLastError());
+  {
+    ProfScope prof(e, s, PC_OTHER, 0.0, 0.0);
+    export_boxes_kernel<<<ceil_div(rows * L, 256), 256, 0, s>>>(e->st, rows, Lb, L, 0, phrase_num, phrase_length, phrase_syn);
+  }
+  CU_TRY(cudaGetLastError());
+  return BOFI_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* bofi_last_error(void) { return g_err; }
+int bofi_abi_version(void) { return BOFI_ABI_VERSION; }
+
+int bofi_create(const bofi_config_t* cfg, int device, bofi_handle_t* out) {
+  if (!cfg || !out) return fail(BOFI_ERR_INVALID, "null argument");
+  if (cfg->abi_version != BOFI_ABI_VERSION) return fail(BOFI_ERR_INVALID, "abi_version %d != %d", cfg->abi_version, BOFI_ABI_VERSION);
+  if (cfg->d_model != kD || cfg->heads * kHeadDim != kD)
+    return fail(BOFI_ERR_INVALID, "kernels are specialised for d_model=512, 8 heads (got d_model=%d heads=%d)", cfg->d_model, cfg->heads);
+  if (cfg->d_ff % 64 || cfg->att_feat_size % 64) return fail(BOFI_ERR_INVALID, "d_ff / att_feat_size must be multiples of 64");
+  if (cfg->seq_length + 2 > 32 || cfg->seq_length < 1) return fail(BOFI_ERR_INVALID, "seq_length %d unsupported", cfg->seq_length);
+  if (cfg->n_enc < 0 || cfg->n_dec < 1 || cfg->n_len < 0) return fail(BOFI_ERR_INVALID, "bad layer counts");
+  if (cfg->precision != BOFI_PRECISION_FP32 && cfg->precision != BOFI_PRECISION_BF16) return fail(BOFI_ERR_INVALID, "bad precision");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return fail(BOFI_ERR_CUDA, "no usable CUDA device %d (found %d); this library has no CPU fallback", device, ndev);
+  }
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(BOFI_ERR_CUDA, "device %d is sm_%d%d; the kernels are built for sm_100a only", device, prop.major, prop.minor);
+  CU_TRY(cudaSetDevice(device));
+  bofi_engine* e = new bofi_engine();
+  e->cfg = *cfg;
+  e->device = device;
+  e->L = cfg->seq_length;
+  e->Lb = cfg->seq_length + 2;
+  e->V = cfg->tgt_vocab;
+  e->Vpad = (cfg->tgt_vocab + 31) / 32 * 32;
+  e->bf16_mode = (cfg->precision == BOFI_PRECISION_BF16);
+  const char* g = getenv("BOFI_GEMM");
+  e->use_tc = !(g && strcmp(g, "simt") == 0);
+  build_spec(e);
+  *out = e;
+  return BOFI_OK;
+}
+
+int bofi_destroy(bofi_handle_t e) {
+  if (!e) return BOFI_OK;
+  cudaSetDevice(e->device);
+  for (auto& kv : e->weights)
+    if (kv.second.dev) cudaFree(kv.second.dev);
+  for (DevBuf& b : e->packed) b.release();
+  for (DevBuf& b : e->kv) b.release();
+  DevBuf* all[] = {&e->bound_in, &e->fill_in, &e->attT, &e->x, &e->y, &e->qkv, &e->ao, &e->q, &e->ffh, &e->memT, &e->attlen,
+                   &e->hrow, &e->hid, &e->logits, &e->state_i32, &e->tok, &e->h_in, &e->h_len, &e->h_seq, &e->h_logp,
+                   &e->h_pnum, &e->h_plen, &e->h_psyn, &e->unit_a, &e->unit_w, &e->unit_o};
+  for (DevBuf* b : all) b->release();
+  delete e;
+  return BOFI_OK;
+}
+
+int bofi_set_weight(bofi_handle_t e, const char* name, const float* host_data, int64_t numel) {
+  if (!e || !name || !host_data) return fail(BOFI_ERR_INVALID, "null argument");
+  auto it = e->weights.find(name);
+  if (it == e->weights.end()) return fail(BOFI_ERR_INVALID, "unexpected state_dict key '%s'", name);
+  WeightEntry& w = it->second;
+  if (w.numel != numel) return fail(BOFI_ERR_INVALID, "size mismatch for '%s': got %lld elements, expected %lld", name, (long long)numel, (long long)w.numel);
+  CU_TRY(cudaSetDevice(e->device));
+  if (!w.used) { w.loaded = true; return BOFI_OK; }
+  if (!w.dev) CU_TRY(cudaMalloc(&w.dev, (size_t)numel * sizeof(float)));
+  CU_TRY(cudaMemcpy(w.dev, host_data, (size_t)numel * sizeof(float), cudaMemcpyHostToDevice));
+  w.loaded = true;
+  e->finalized = false;
+  return BOFI_OK;
+}
+
+int bofi_missing_weights(bofi_handle_t e) {
+  if (!e) return -1;
+  int n = 0;
+  for (auto& kv : e->weights) n += kv.second.loaded ? 0 : 1;
+  return n;
+}
+
+int bofi_finalize_weights(bofi_handle_t e, void* stream) {
+  if (!e) return fail(BOFI_ERR_INVALID, "null handle");
+  for (const std::string& n : e->order)
+    if (!e->weights[n].loaded) return fail(BOFI_ERR_STATE, "missing state_dict key '%s'", n.c_str());
+  CU_TRY(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const bofi_config_t& c = e->cfg;
+  for (DevBuf& b : e->packed) b.release();
+  e->packed.clear();
+  e->packed.reserve(4096);
+  e->enc.assign(c.n_enc, Layer());
+  e->dec.assign(c.n_dec, Layer());
+  e->lp.assign(c.n_len, Layer());
+  RC_TRY(make_lin(e, s, {"att_embed.0"}, c.d_model, c.att_feat_size, &e->att_embed));
+  for (int l = 0; l < c.n_enc; ++l) RC_TRY(make_layer(e, s, "model.encoder.layers." + std::to_string(l), false, "feed_forward", &e->enc[l]));
+  for (int l = 0; l < c.n_dec; ++l) RC_TRY(make_layer(e, s, "model.decoder.layers." + std::to_string(l), true, "feed_forward", &e->dec[l]));
+  const std::string lp = "model.length_predictor";
+  for (int l = 0; l < c.n_len; ++l) RC_TRY(make_layer(e, s, lp + ".LengthPredictor." + std::to_string(l), true, "ff", &e->lp[l]));
+  if (c.n_len == 0) {
+    const std::string ca = lp + ".length_attn.linears.";
+    e->lp0.cross = true;
+    RC_TRY(make_lin(e, s, {ca + "0"}, c.d_model, c.d_model, &e->lp0.ca.q));
+    RC_TRY(make_lin(e, s, {ca + "1", ca + "2"}, c.d_model, c.d_model, &e->lp0.ca.kv));
+    RC_TRY(make_lin(e, s, {ca + "3"}, c.d_model, c.d_model, &e->lp0.ca.o));
+    e->lp0.ln[0] = make_norm(e, lp + ".LengthPredictor.norm");
+  }
+  e->enc_norm = make_norm(e, "model.encoder.norm");
+  e->dec_norm = make_norm(e, "model.decoder.norm");
+  e->lp_norm = make_norm(e, lp + ".norm");
+  RC_TRY(make_lin(e, s, {"model.generator.proj"}, c.tgt_vocab, c.d_model, &e->generator));
+  {
+    bool keep = e->bf16_mode;
+    e->bf16_mode = false;
+    int rc = make_lin(e, s, {lp + ".Length_classifier1", lp + ".Syntactic_classifier1"}, 100, c.d_model, &e->head1);
+    e->bf16_mode = keep;
+    RC_TRY(rc);
+  }
+  e->w_len2 = W(e, lp + ".Length_classifier2.weight");
+  e->b_len2 = W(e, lp + ".Length_classifier2.bias");
+  e->w_syn2 = W(e, lp + ".Syntactic_classifier2.weight");
+  e->b_syn2 = W(e, lp + ".Syntactic_classifier2.bias");
+  RC_TRY(e->bound_in.reserve((size_t)10 * e->Lb * kD * 4));
+  RC_TRY(e->fill_in.reserve((size_t)10 * e->L * kD * 4));
+  build_tables_kernel<<<dim3(10, e->Lb), 128, 0, s>>>(W(e, "model.syn_embed.lut.weight"), W(e, "model.tgt_embed.lut.weight"),
+                                                      W(e, "model.pos_embed.pe"), c.bos_idx, 10, e->Lb, e->L, sqrtf((float)kD),
+                                                      e->bound_in.as<float>(), e->fill_in.as<float>());
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaStreamSynchronize(s));
+  e->finalized = true;
+  return BOFI_OK;
+}
+
+int64_t bofi_workspace_bytes(bofi_handle_t e, int32_t B, int32_t R, int32_t sn) {
+  if (!e || B <= 0 || R <= 0 || sn <= 0) return -1;
+  const int64_t M = (int64_t)B * R, ts = e->bf16_mode ? 2 : 4, rows = (int64_t)B * sn, dr = std::max<int64_t>(rows * e->Lb, M);
+  int64_t t = 0;
+  if (e->bf16_mode) t += M * e->cfg.att_feat_size * ts;
+  t += dr * kD * 4 + dr * kD * ts * 3 + dr * 3 * kD * ts + dr * e->cfg.d_ff * ts + M * kD * ts;
+  t += (int64_t)(std::max(1, e->cfg.n_len) + e->cfg.n_dec) * M * 2 * kD * ts;
+  t += rows * e->L * (int64_t)e->Vpad * 4 + rows * (kD + 200) * 4 + (int64_t)state_ints((int)rows, e->Lb, e->L) * 4;
+  return t + t / 8;
+}
+
+int bofi_encode(bofi_handle_t e, void* stream, const float* att_feats, const int32_t* att_len, int32_t B, int32_t R, float* memory_out) {
+  if (!e || !att_feats) return fail(BOFI_ERR_INVALID, "null argument");
+  if (!e->finalized) return fail(BOFI_ERR_STATE, "weights not finalised");
+  if (B <= 0 || R <= 0 || R > kMaxKeys) return fail(BOFI_ERR_INVALID, "bad batch B=%d R=%d (R <= %d)", B, R, kMaxKeys);
+  CU_TRY(cudaSetDevice(e->device));
+  e->launches = 0;
+  e->have_memory = false;
+  cudaStream_t s = (cudaStream_t)stream;
+  return e->bf16_mode ? encode_impl<bf16>(e, s, att_feats, att_len, B, R, memory_out)
+                      : encode_impl<float>(e, s, att_feats, att_len, B, R, memory_out);
+}
+
+int bofi_decode(bofi_handle_t e, void* stream, int32_t mode, int32_t sn, int32_t output_logsoftmax, int64_t* seq, float* logprobs,
+                int32_t* phrase_num, int32_t* phrase_length, int64_t* phrase_syn) {
+  if (!e || !seq || !phrase_num || !phrase_length || !phrase_syn) return fail(BOFI_ERR_INVALID, "null argument");
+  if (!e->have_memory) return fail(BOFI_ERR_STATE, "bofi_decode needs a preceding bofi_encode");
+  if (sn < 1) return fail(BOFI_ERR_INVALID, "sample_n %d", sn);
+  if (mode != BOFI_MODE_NAIC) return fail(BOFI_ERR_INVALID, "mode %d not built yet (NAIC only)", mode);
+  CU_TRY(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  RC_TRY(reserve_decode(e, e->B, e->R, sn));
+  return e->bf16_mode ? decode_naic<bf16>(e, s, sn, output_logsoftmax, (long long*)seq, logprobs, phrase_num, phrase_length, (long long*)phrase_syn)
+                      : decode_naic<float>(e, s, sn, output_logsoftmax, (long long*)seq, logprobs, phrase_num, phrase_length, (long long*)phrase_syn);
+}
+
+int bofi_sample_host(bofi_handle_t e, void* stream, int32_t mode, int32_t sn, int32_t output_logsoftmax, const float* att_feats,
+                     const int32_t* att_len, int32_t B, int32_t R, int64_t* seq, float* logprobs, int32_t* phrase_num,
+                     int32_t* phrase_length, int64_t* phrase_syn) {
+  if (!e || !att_feats || !seq || !phrase_num || !phrase_length || !phrase_syn) return fail(BOFI_ERR_INVALID, "null argument");
+  if (B <= 0 || R <= 0 || sn < 1) return fail(BOFI_ERR_INVALID, "bad batch");
+  CU_TRY(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t rows = (size_t)B * sn, L = e->L;
+  RC_TRY(e->h_in.reserve((size_t)B * R * e->cfg.att_feat_size * 4));
+  RC_TRY(e->attlen.reserve((size_t)B * 4));
+  RC_TRY(e->h_seq.reserve(rows * L * 8));
+  RC_TRY(e->h_pnum.reserve(rows * 4));
+  RC_TRY(e->h_plen.reserve(rows * L * 4));
+  RC_TRY(e->h_psyn.reserve(rows * L * 8));
+  if (logprobs) RC_TRY(e->h_logp.reserve(rows * L * (size_t)e->V * 4));
+  CU_TRY(cudaMemcpyAsync(e->h_in.p, att_feats, (size_t)B * R * e->cfg.att_feat_size * 4, cudaMemcpyHostToDevice, s));
+  if (att_len) CU_TRY(cudaMemcpyAsync(e->attlen.p, att_len, (size_t)B * 4, cudaMemcpyHostToDevice, s));
+  RC_TRY(bofi_encode(e, stream, e->h_in.as<float>(), att_len ? e->attlen.as<int>() : nullptr, B, R, nullptr));
+  RC_TRY(bofi_decode(e, stream, mode, sn, output_logsoftmax, e->h_seq.as<int64_t>(), logprobs ? e->h_logp.as<float>() : nullptr,
+                     e->h_pnum.as<int>(), e->h_plen.as<int>(), e->h_psyn.as<int64_t>()));
+  CU_TRY(cudaMemcpyAsync(seq, e->h_seq.p, rows * L * 8, cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaMemcpyAsync(phrase_num, e->h_pnum.p, rows * 4, cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaMemcpyAsync(phrase_length, e->h_plen.p, rows * L * 4, cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaMemcpyAsync(phrase_syn, e->h_psyn.p, rows * L * 8, cudaMemcpyDeviceToHost, s));
+  if (logprobs) CU_TRY(cudaMemcpyAsync(logprobs, e->h_logp.p, rows * L * (size_t)e->V * 4, cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  return BOFI_OK;
+}
+
+int bofi_get_decode_info(bofi_handle_t e, void* stream, bofi_decode_info_t* out) {
+  if (!e || !out) return fail(BOFI_ERR_INVALID, "null argument");
+  if (!e->st.counters) return fail(BOFI_ERR_STATE, "no decode has run");
+  CU_TRY(cudaSetDevice(e->device));
+  int c[4];
+  CU_TRY(cudaMemcpyAsync(c, e->st.counters, sizeof(c), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  out->bounding_steps = c[1];
+  out->fill_width = c[2];
+  out->nan_batch = c[3];
+  out->kernel_launches = e->launches;
+  return BOFI_OK;
+}
+
+int bofi_set_profiling(bofi_handle_t e, int32_t enable) {
+  if (!e) return fail(BOFI_ERR_INVALID, "null handle");
+  for (ProfRec& r : e->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  e->recs.clear();
+  e->profiling = enable != 0;
+  return BOFI_OK;
+}
+
+int bofi_get_profile(bofi_handle_t e, void* stream, int32_t* launches, double* ms, double* flops, double* bytes) {
+  if (!e || !launches || !ms || !flops || !bytes) return fail(BOFI_ERR_INVALID, "null argument");
+  CU_TRY(cudaSetDevice(e->device));
+  CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  for (int c = 0; c < PC_COUNT; ++c) { launches[c] = 0; ms[c] = flops[c] = bytes[c] = 0.0; }
+  for (ProfRec& r : e->recs) {
+    float t = 0.f;
+    CU_TRY(cudaEventElapsedTime(&t, r.a, r.b));
+    launches[r.cls] += 1;
+    ms[r.cls] += t;
+    flops[r.cls] += r.flops;
+    bytes[r.cls] += r.bytes;
+  }
+  return BOFI_OK;
+}
+
+// ---- unit entry points -------------------------------------------------------------------------------
+int bofi_layernorm_f32(bofi_handle_t e, void* stream, const float* x, const float* a2, const float* b2, float* out, int32_t rows) {
+  if (!e || !x || !a2 || !b2 || !out) return fail(BOFI_ERR_INVALID, "null argument");
+  CU_TRY(cudaSetDevice(e->device));
+  Norm n{a2, b2};
+  return layernorm<float>(e, (cudaStream_t)stream, x, kD, n, out, kD, rows, nullptr, nullptr);
+}
+
+int bofi_linear_f32(bofi_handle_t e, void* stream, const float* A, const float* Wt, const float* bias, const float* residual,
+                    float* out, int32_t M, int32_t N, int32_t K, int32_t relu) {
+  if (!e || !A || !Wt || !out) return fail(BOFI_ERR_INVALID, "null argument");
+  CU_TRY(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  Lin l;
+  l.N = N;
+  l.K = K;
+  l.b = bias;
+  if (!e->bf16_mode) {
+    l.w32 = Wt;
+    if (N % 4) {   // unit path writes straight into the caller's [M,N] tensor
+      cudaError_t err = gemm_simt<float, float>(s, A, K, Wt, K, bias, residual, N, out, N, M, N, K, relu, nullptr);
+      if (err != cudaSuccess) return fail(BOFI_ERR_CUDA, "gemm: %s", cudaGetErrorString(err));
+      return BOFI_OK;
+    }
+    return linear<float, float>(e, s, A, K, l, residual, N, out, N, M, relu, nullptr);
+  }
+  if (N % 8) return fail(BOFI_ERR_INVALID, "bf16 unit GEMM needs N %% 8 == 0");
+  RC_TRY(e->unit_a.reserve((size_t)M * K * 2));
+  RC_TRY(e->unit_w.reserve((size_t)N * K * 2));
+  cast_kernel<bf16><<<ceil_div((size_t)M * K / 4, 256), 256, 0, s>>>(A, e->unit_a.as<bf16>(), (size_t)M * K / 4);
+  cast_kernel<bf16><<<ceil_div((size_t)N * K / 4, 256), 256, 0, s>>>(Wt, e->unit_w.as<bf16>(), (size_t)N * K / 4);
+  CU_TRY(cudaGetLastError());
+  l.w16 = e->unit_w.as<bf16>();
+  return linear<bf16, float>(e, s, e->unit_a.as<bf16>(), K, l, residual, N, out, N, M, relu, nullptr);
+}
+
+int bofi_attention_f32(bofi_handle_t e, void* stream, const float* q, const float* k, const float* v, const int32_t* vis,
+                       float* out, int32_t B, int32_t Tq, int32_t Tk) {
+  if (!e || !q || !k || !v || !out) return fail(BOFI_ERR_INVALID, "null argument");
+  CU_TRY(cudaSetDevice(e->device));
+  return attention<float>(e, (cudaStream_t)stream, q, kD, k, v, kD, out, kD, B, Tq, Tk, vis, Tq, 1, 1, 1, nullptr);
+}
+
+}  // extern "C"

@@ -1,0 +1,286 @@
+// tcgen05 GEMM for sm_100a:  C[M,N] = act(A[M,K] . W[N,K]^T + bias) (+ residual), bf16 in, fp32 accumulate.
+//
+//   * A (activations) and W (nn.Linear weight) are both K-major bf16, fetched by TMA
+//     (cp.async.bulk.tensor.2d, 128-byte swizzle) into a multi-stage shared-memory ring;
+//   * one elected thread issues tcgen05.mma (cta_group::1, kind::f16, M=128 x N=BN x K=16) with the
+//     accumulator tile living in tensor memory (BN fp32 columns x 128 lanes);
+//   * four epilogue warps read the accumulator back with tcgen05.ld (32x32b: one row per thread) and
+//     fuse bias, ReLU, residual add and the fp32 / bf16 down-conversion before the global stores.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quadrant = warp % 4).
+// Pipelines: full[s]/empty[s] mbarriers between TMA and MMA, one tmem_full mbarrier MMA -> epilogue.
+// Two CTAs are resident per SM (STAGES x 32 KB of smem each), so one CTA's epilogue overlaps the
+// other's main loop without a persistent scheduler.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+namespace bofi {
+namespace tc {
+
+constexpr int kBM = 128;   // UMMA M (TMEM lanes)
+constexpr int kBK = 64;    // 64 bf16 = one 128-byte swizzle row
+constexpr int kUK = 16;    // UMMA K for 16-bit inputs
+constexpr int kThreads = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a mis-programmed pipeline traps (error surfaces on the host) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled operand tile (rows of 64 bf16, 8-row groups 1024 B apart):
+// start address >> 4 | LBO (ignored for swizzled K-major) = 1 | SBO = 1024 B | version 1 | SWIZZLE_128B.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, N >> 3, M >> 4.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = STAGES * kStageBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;   // barriers + alignment slack
+};
+
+template <int BN, int STAGES, typename TOut>
+__global__ void __launch_bounds__(kThreads)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const float* __restrict__ bias, const float* residual, int ldr, TOut* C, int ldc,
+               int M, int N, int K, int relu, const int* live_rows) {
+  if (step_is_dead(live_rows)) return;
+  using L = SmemLayout<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* full_bar = bars;                 // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * BN;
+  const int nk = K / kBK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(smem_u32(&full_bar[s]), 1);
+        mbar_init(smem_u32(&empty_bar[s]), 1);
+      }
+      mbar_init(smem_u32(tmem_full_bar), 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+        const uint32_t fb = smem_u32(&full_bar[s]);
+        mbar_expect_tx(fb, L::kStageBytes);
+        const uint32_t a_dst = smem_u32(smem + s * L::kStageBytes);
+        tma_load_2d(a_dst, &tmA, fb, kb * kBK, m0);
+        tma_load_2d(a_dst + L::kABytes, &tmB, fb, kb * kBK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN);
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(smem_u32(&full_bar[s]), ph);
+        tcgen05_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
+        const uint64_t adesc = make_sw128_desc(a_addr);
+        const uint64_t bdesc = make_sw128_desc(a_addr + L::kABytes);
+#pragma unroll
+        for (int k = 0; k < kBK / kUK; ++k) {
+          // +32 bytes per K step inside the 128-byte swizzle row (encoded >> 4)
+          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        }
+        umma_commit(smem_u32(&empty_bar[s]));   // frees the smem stage when these MMAs retire
+      }
+      umma_commit(smem_u32(tmem_full_bar));     // accumulator complete
+    }
+  } else {
+    const int quad = warp & 3;                  // TMEM lanes [32*quad, 32*quad+32)
+    const int row = m0 + quad * 32 + lane;
+    mbar_wait(smem_u32(tmem_full_bar), 0);
+    tcgen05_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32), r);
+      const int n = n0 + c * 32;
+      if (row < M && n < N) {
+        float v[32];
+        const bool full = (n + 32 <= N);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(r[j]);
+          if (full || n + j < N) {
+            if (bias) x += bias[n + j];
+            if (relu) x = fmaxf(x, 0.f);
+            if (residual) x += residual[(size_t)row * ldr + n + j];
+          }
+          v[j] = x;
+        }
+        TOut* dst = C + (size_t)row * ldc + n;
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) store4(dst + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+        } else {
+          for (int j = 0; j < 32 && n + j < N; ++j) dst[j] = from_float<TOut>(v[j]);
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor [rows, cols] with row pitch ld (elements); box = 64 cols x box_rows, 128 B swizzle.
+inline bool make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int BN, int STAGES, typename TOut>
+inline cudaError_t launch(cudaStream_t s, const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias,
+                          const float* residual, int ldr, TOut* C, int ldc, int M, int N, int K, int relu,
+                          const int* live_rows) {
+  using L = SmemLayout<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, TOut>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid((N + BN - 1) / BN, (M + kBM - 1) / kBM);
+  gemm_tc_kernel<BN, STAGES, TOut><<<grid, kThreads, L::kTotal, s>>>(tmA, tmB, bias, residual, ldr, C, ldc, M, N, K, relu, live_rows);
+  return cudaGetLastError();
+}
+
+// A [M,K] bf16 (pitch lda), W [N,K] bf16 (pitch ldw).  Requires K % 64 == 0, 16-byte aligned pitches.
+template <typename TOut>
+inline cudaError_t gemm_tc(cudaStream_t s, const bf16* A, int lda, const bf16* W, int ldw, const float* bias,
+                           const float* residual, int ldr, TOut* C, int ldc, int M, int N, int K, int relu,
+                           const int* live_rows) {
+  if (M <= 0 || N <= 0) return cudaSuccess;
+  if (K % kBK != 0 || lda % 8 != 0 || ldw % 8 != 0 || ldc % 8 != 0) return cudaErrorInvalidValue;
+  constexpr int BN = 128, STAGES = 3;
+  CUtensorMap tmA, tmB;
+  if (!make_tmap_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBM)) return cudaErrorInvalidValue;
+  if (!make_tmap_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, BN)) return cudaErrorInvalidValue;
+  return launch<BN, STAGES, TOut>(s, tmA, tmB, bias, residual, ldr, C, ldc, M, N, K, relu, live_rows);
+}
+
+}  // namespace tc
+}  // namespace bofi

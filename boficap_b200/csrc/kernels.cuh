@@ -1,0 +1,429 @@
+// Memory-bound and short-sequence kernels of the BoFi decode path (sm_100a).
+// Reference semantics cited per kernel (paths relative to /root/reference/captioning/models/).
+#pragma once
+#include "common.cuh"
+
+namespace bofi {
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm of TransformerModel.py:1338-1349:  a_2 * (x - mean) / (std_unbiased + 1e-6) + b_2.
+// NOT nn.LayerNorm: N-1 divisor and eps added to the standard deviation.
+// One warp per 512-wide row, 4 x 128-bit loads per lane, shuffle reductions, two-pass variance.
+// `in_stride` lets the caller normalise one row out of every block (the [LEN] row, :375).
+// ---------------------------------------------------------------------------------------------
+template <typename TOut>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, size_t in_stride, const float* __restrict__ a2,
+                 const float* __restrict__ b2, TOut* __restrict__ out, size_t out_stride, int rows,
+                 float* __restrict__ out_f32_copy, const int* live_rows) {
+  if (step_is_dead(live_rows)) return;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + (size_t)row * in_stride;
+  float4 v[4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[i] = load4(xr + (i * 32 + lane) * 4);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.0f / kD);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    ss += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  }
+  const float denom = sqrtf(warp_sum(ss) * (1.0f / (kD - 1))) + 1e-6f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    const float4 a = load4(a2 + c), b = load4(b2 + c);
+    float4 o;
+    o.x = a.x * v[i].x / denom + b.x;
+    o.y = a.y * v[i].y / denom + b.y;
+    o.z = a.z * v[i].z / denom + b.z;
+    o.w = a.w * v[i].w / denom + b.w;
+    store4(out + (size_t)row * out_stride + c, o);
+    if (out_f32_copy) store4(out_f32_copy + (size_t)row * kD + c, o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Scaled-dot-product attention of TransformerModel.py:1421-1432 for short sequences, one CTA per
+// (head, batch row).  The mask tensors of the reference ([B,1,R] region padding, [B,T,T] phrase
+// masks) are all PREFIX masks, so a query only needs its visible-key count:
+//     nvis = vis[(b / vis_div) * vis_bs + t * vis_qs]      (vis == nullptr -> all Tk keys)
+// nvis == 0 reproduces the reference's all-masked softmax row: NaN.
+// K/V of batch row b live at row (b / kv_div) (sample_n repeats share the image's memory).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128)
+attention_kernel(const T* __restrict__ Q, int ldq, const T* __restrict__ K, const T* __restrict__ V, int ldkv,
+                 T* __restrict__ O, int ldo, int Tq, int Tk, const int* __restrict__ vis, int vis_bs, int vis_qs,
+                 int vis_div, int kv_div, float scale, const int* live_rows) {
+  if (step_is_dead(live_rows)) return;
+  extern __shared__ float smem[];
+  float* Ks = smem;                         // [Tk][65]
+  float* Vs = Ks + Tk * (kHeadDim + 1);     // [Tk][64]
+  float* qs = Vs + Tk * kHeadDim;           // [4][64]
+  float* ps = qs + 4 * kHeadDim;            // [4][kMaxKeys]
+  const int head = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const size_t kvrow0 = (size_t)(b / kv_div) * Tk;
+  for (int idx = tid; idx < Tk * (kHeadDim / 4); idx += 128) {
+    const int j = idx >> 4, c = (idx & 15) * 4;
+    const float4 kq = load4(K + (kvrow0 + j) * ldkv + head * kHeadDim + c);
+    const float4 vq = load4(V + (kvrow0 + j) * ldkv + head * kHeadDim + c);
+    float* kd = Ks + j * (kHeadDim + 1) + c;
+    kd[0] = kq.x; kd[1] = kq.y; kd[2] = kq.z; kd[3] = kq.w;
+    *reinterpret_cast<float4*>(Vs + j * kHeadDim + c) = vq;
+  }
+  __syncthreads();
+  float* q = qs + warp * kHeadDim;
+  float* p = ps + warp * kMaxKeys;
+  for (int t = warp; t < Tq; t += 4) {
+    const T* qg = Q + ((size_t)b * Tq + t) * ldq + head * kHeadDim;
+    q[lane] = to_float<T>(qg[lane]);
+    q[lane + 32] = to_float<T>(qg[lane + 32]);
+    __syncwarp();
+    int nvis = vis ? vis[(size_t)(b / vis_div) * vis_bs + (size_t)t * vis_qs] : Tk;
+    nvis = min(nvis, Tk);
+    float sc[kMaxKeys / 32];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < kMaxKeys / 32; ++jj) {
+      const int j = jj * 32 + lane;
+      float s = -INFINITY;
+      if (j < nvis) {
+        const float* kr = Ks + j * (kHeadDim + 1);
+        float d = 0.f;
+#pragma unroll 16
+        for (int c = 0; c < kHeadDim; ++c) d = fmaf(q[c], kr[c], d);
+        s = d * scale;
+      }
+      sc[jj] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < kMaxKeys / 32; ++jj) {
+      const int j = jj * 32 + lane;
+      const float e = (j < nvis) ? expf(sc[jj] - mx) : 0.f;
+      sc[jj] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+#pragma unroll
+    for (int jj = 0; jj < kMaxKeys / 32; ++jj) {
+      const int j = jj * 32 + lane;
+      if (j < Tk) p[j] = sc[jj] / sum;
+    }
+    __syncwarp();
+    float o0 = 0.f, o1 = 0.f;
+    for (int j = 0; j < nvis; ++j) {
+      const float pj = p[j];
+      o0 = fmaf(pj, Vs[j * kHeadDim + lane], o0);
+      o1 = fmaf(pj, Vs[j * kHeadDim + lane + 32], o1);
+    }
+    if (nvis <= 0) o0 = o1 = __int_as_float(0x7fc00000);   // softmax over an all -inf row
+    T* og = O + ((size_t)b * Tq + t) * ldo + head * kHeadDim;
+    og[lane] = from_float<T>(o0);
+    og[lane + 32] = from_float<T>(o1);
+    __syncwarp();
+  }
+}
+
+inline size_t attention_smem_bytes(int Tk) {
+  return sizeof(float) * ((size_t)Tk * (kHeadDim + 1) + (size_t)Tk * kHeadDim + 4 * kHeadDim + 4 * kMaxKeys);
+}
+
+// fp32 -> T, 128-bit vectorised (n % 4 == 0)
+template <typename T>
+__global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ in, T* __restrict__ out, size_t n4) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) store4(out + i * 4, load4(in + i * 4));
+}
+
+// pack_wrapper (AttModel.py:46-51): rows of padded regions come back as zeros.
+__global__ void __launch_bounds__(256)
+zero_padded_rows_kernel(float* __restrict__ x, const int* __restrict__ att_len, int B, int R) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= B * R) return;
+  const int b = row / R, r = row - b * R;
+  if (r < att_len[b]) return;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) store4(x + (size_t)row * kD + (i * 32 + lane) * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+}
+
+// (id, position) input tables.  Embeddings (x sqrt(d), TransformerModel.py:1480-1487) + sinusoid
+// (:1489-1507) are pure functions of (id, pos):
+//   bound_in[s][p] = syn_embed[s]*sqrt(d) + pe[p]                              (:568)
+//   fill_in [s][p] = (tgt_embed[bos]*sqrt(d) + syn_embed[s]*sqrt(d)) + pe[p]   (:572-577)
+// built with the reference's own operation order so the rows are bit-identical.
+__global__ void build_tables_kernel(const float* __restrict__ syn_lut, const float* __restrict__ tgt_lut,
+                                    const float* __restrict__ pe, int bos, int n_syn, int Lb, int L,
+                                    float sqrt_d, float* __restrict__ bound_in, float* __restrict__ fill_in) {
+  const int s = blockIdx.x, p = blockIdx.y;
+  for (int c = threadIdx.x; c < kD; c += blockDim.x) {
+    const float se = syn_lut[s * kD + c] * sqrt_d;
+    bound_in[((size_t)s * Lb + p) * kD + c] = se + pe[p * kD + c];
+    if (p < L) fill_in[((size_t)s * L + p) * kD + c] = (tgt_lut[(size_t)bos * kD + c] * sqrt_d + se) + pe[p * kD + c];
+  }
+}
+
+// x[(b*T + r), :] = table[ids[b*ids_stride + ids_off + r]][r]   (one warp per row)
+__global__ void __launch_bounds__(256)
+gather_table_kernel(const float* __restrict__ table, int P, const int* __restrict__ ids, int ids_stride, int ids_off,
+                    float* __restrict__ x, int rows, int T, const int* live_rows) {
+  if (step_is_dead(live_rows)) return;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int b = row / T, r = row - b * T;
+  const int id = ids[(size_t)b * ids_stride + ids_off + r];
+  const float* src = table + ((size_t)id * P + r) * kD;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) store4(x + (size_t)row * kD + (i * 32 + lane) * 4, load4(src + (i * 32 + lane) * 4));
+}
+
+// x[(b*T + r), :] = word_lut[w]*sqrt(d) (+ syn_lut[s]*sqrt(d)) + pe[r]   -- SAIC inputs, where the
+// word id is data dependent (TransformerModel.py:518, :522).  syn_ids == nullptr -> word only.
+__global__ void __launch_bounds__(256)
+embed_words_kernel(const float* __restrict__ word_lut, const float* __restrict__ syn_lut, const float* __restrict__ pe,
+                   const int* __restrict__ word_ids, const int* __restrict__ syn_ids, int ids_stride, int ids_off,
+                   float sqrt_d, float* __restrict__ x, int rows, int T, const int* live_rows) {
+  if (step_is_dead(live_rows)) return;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int b = row / T, r = row - b * T;
+  const int w = word_ids[(size_t)b * ids_stride + ids_off + r];
+  const int s = syn_ids ? syn_ids[(size_t)b * ids_stride + ids_off + r] : -1;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    float4 e = load4(word_lut + (size_t)w * kD + c);
+    e.x *= sqrt_d; e.y *= sqrt_d; e.z *= sqrt_d; e.w *= sqrt_d;
+    if (s >= 0) {
+      const float4 g = load4(syn_lut + (size_t)s * kD + c);
+      e.x += g.x * sqrt_d; e.y += g.y * sqrt_d; e.z += g.z * sqrt_d; e.w += g.w * sqrt_d;
+    }
+    const float4 pp = load4(pe + (size_t)r * kD + c);
+    e.x += pp.x; e.y += pp.y; e.z += pp.z; e.w += pp.w;
+    store4(x + (size_t)row * kD + c, e);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-row decode state (core_NAIC, TransformerModel.py:1825-1838; core_SAIC :1879-1905).
+// ---------------------------------------------------------------------------------------------
+struct DecodeState {
+  int* ext;            // [rows, Lb] NAIC: syn id per slot (slot 0 = len_idx) ; SAIC: words fed to the bounding head
+  int* ext_word;       // [rows, Lb] SAIC: words fed to the decoder
+  int* ext_syn;        // [rows, Lb] SAIC: syn ids fed to the decoder
+  int* seq22;          // [rows, Lb] SAIC: generated words incl. bos slot
+  int* vis;            // [rows, Lb] visible-key count of every bounding row (prefix form of tgt_mask / len_mask)
+  int* vis_fill;       // [rows, L]  visible-key count of every fill / decoder row
+  int* last;           // [rows]     end of assigned slots (NAIC `last`, SAIC `phrase_last`)
+  int* seq_last;       // [rows]     SAIC
+  int* step_len;       // [rows]     phrase length accepted at the current step (0 = none)
+  int* finished;       // [rows]
+  int* phrase_num;     // [rows]
+  int* phrase_length;  // [rows, Lb]
+  int* phrase_syn;     // [rows, Lb]
+  int* counters;       // [0] live rows, [1] bounding steps executed, [2] fill width w, [3] nan flag
+};
+
+__global__ void init_state_kernel(DecodeState st, int rows, int Lb, int L, int len_idx, int bos_idx, int saic) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == 0) { st.counters[0] = rows; st.counters[1] = 0; st.counters[2] = 0; st.counters[3] = 0; }
+  if (b >= rows) return;
+  for (int r = 0; r < Lb; ++r) {
+    st.ext[b * Lb + r] = (r == 0) ? len_idx : 0;
+    st.ext_word[b * Lb + r] = 0;
+    st.ext_syn[b * Lb + r] = 0;
+    st.seq22[b * Lb + r] = (saic && r == 0) ? bos_idx : 0;
+    st.vis[b * Lb + r] = 1;                       // tgt_mask[:, :, 0] = True
+    st.phrase_length[b * Lb + r] = (saic && r == 0) ? 1 : 0;
+    st.phrase_syn[b * Lb + r] = 0;
+  }
+  for (int r = 0; r < L; ++r) st.vis_fill[b * L + r] = 0;
+  st.last[b] = 1;
+  st.seq_last[b] = 0;
+  st.step_len[b] = 0;
+  st.finished[b] = 0;
+  st.phrase_num[b] = 0;
+}
+
+// Bounding heads + box rule for one step, one warp per row.
+//   hid [rows, 2*Hh] = relu(classifier1(h)) of both heads (length first), computed by the GEMM before;
+//   logits -> log_softmax -> first-max argmax (TransformerModel.py:376-383);
+//   EOS / clip / write rule (:1843-1867 NAIC, :1910-1926 SAIC).
+// NAIC (`saic == 0`) also writes the syn id into ext[last:last+len] and advances `last`/`vis`;
+// SAIC defers that to saic_commit_kernel (the slots are filled with generated words).
+__global__ void __launch_bounds__(128)
+bound_head_kernel(const float* __restrict__ hid, int Hh, const float* __restrict__ w_len, const float* __restrict__ b_len,
+                  const float* __restrict__ w_syn, const float* __restrict__ b_syn, int n_len, int n_syn,
+                  DecodeState st, int rows, int Lb, int L, int step_col, int step_no, int syn_lo, int syn_hi, int saic) {
+  if (st.counters[0] == 0) return;
+  extern __shared__ float hsm[];
+  float* wl = hsm;                      // [n_len][Hh]
+  float* ws = wl + n_len * Hh;          // [n_syn][Hh]
+  float* hrow = ws + n_syn * Hh;        // [4][2*Hh]
+  float* lg = hrow + 4 * 2 * Hh;        // [4][32]
+  for (int i = threadIdx.x; i < n_len * Hh; i += blockDim.x) wl[i] = w_len[i];
+  for (int i = threadIdx.x; i < n_syn * Hh; i += blockDim.x) ws[i] = w_syn[i];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 4 + warp;
+  if (b < rows)
+    for (int i = lane; i < 2 * Hh; i += 32) hrow[warp * 2 * Hh + i] = hid[(size_t)b * 2 * Hh + i];
+  __syncthreads();
+  if (b >= rows) return;
+  const float* hr = hrow + warp * 2 * Hh;
+  if (lane < n_len + n_syn) {
+    const bool is_len = lane < n_len;
+    const float* w = is_len ? wl + lane * Hh : ws + (lane - n_len) * Hh;
+    const float* h = is_len ? hr : hr + Hh;
+    float acc = 0.f;
+    for (int c = 0; c < Hh; ++c) acc = fmaf(h[c], w[c], acc);
+    lg[warp * 32 + lane] = acc + (is_len ? b_len[lane] : b_syn[lane - n_len]);
+  }
+  __syncwarp();
+  if (lane != 0) return;
+  if (st.finished[b]) { st.step_len[b] = 0; return; }
+  atomicMax(&st.counters[1], step_no);   // bounding iterations that still had a live row
+  // log_softmax then torch.max: first maximal index
+  auto argmax_logp = [&](const float* z, int n) {
+    float m = z[0];
+    for (int i = 1; i < n; ++i) m = fmaxf(m, z[i]);
+    float s = 0.f;
+    for (int i = 0; i < n; ++i) s += expf(z[i] - m);
+    const float lse = logf(s);
+    int best = 0;
+    float bv = (z[0] - m) - lse;
+    for (int i = 1; i < n; ++i) {
+      const float v = (z[i] - m) - lse;
+      if (v > bv) { bv = v; best = i; }
+    }
+    return best;
+  };
+  int len_n = argmax_logp(lg + warp * 32, n_len);
+  const int syn_n = argmax_logp(lg + warp * 32 + n_len, n_syn);
+  const int last = st.last[b];
+  if (len_n == 0 || syn_n < syn_lo || syn_n > syn_hi) {
+    st.finished[b] = 1;
+    st.step_len[b] = 0;
+    atomicSub(st.counters, 1);
+    return;
+  }
+  if (len_n + last >= L + 1) {
+    len_n = L + 1 - last;
+    st.finished[b] = 1;
+    atomicSub(st.counters, 1);
+  }
+  st.phrase_length[b * Lb + step_col] = len_n;
+  st.phrase_syn[b * Lb + step_col] = syn_n;
+  st.phrase_num[b] += 1;
+  st.step_len[b] = len_n;
+  if (!saic) {
+    for (int r = last; r < last + len_n; ++r) st.ext[b * Lb + r] = syn_n;
+    const int nl = last + len_n;
+    for (int r = last; r < Lb; ++r) st.vis[b * Lb + r] = nl;   // tgt_mask[j, last:, :last+len] = True
+    st.vis[b * Lb] = nl;                                        // tgt_mask[j, 0, :last] = True
+    st.last[b] = nl;
+  }
+}
+
+// NAIC fill window: every row uses w = last[rows-1] - 1 (the reference's stale loop index,
+// TransformerModel.py:1871-1873).  Also records w and the NaN-batch flag.
+__global__ void fill_window_kernel(DecodeState st, int rows, int L) {
+  const int w = st.last[rows - 1] - 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) { st.counters[2] = w; st.counters[3] = (w <= 0) ? 1 : 0; }
+  if (i < rows * L) st.vis_fill[i] = w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Vocab epilogue: log_softmax over V (AttModel.py:206-209), greedy first-max argmax with torch's
+// NaN-is-maximal rule (CaptionModel.py:389-390) and tail padding seq[b, sum(phrase_length[b]):] = 0
+// (AttModel.py:422-423).  One CTA per (row, slot); logits are read from the 16-byte-pitched
+// workspace, log-probs are written with coalesced 4-byte stores to the caller's [rows, L, V] tensor
+// (V = 9491 rows are not 16-byte aligned).
+// ---------------------------------------------------------------------------------------------
+struct ArgMax { float v; int i; };
+__device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {
+  const bool an = a.v != a.v, bn = b.v != b.v;
+  if (an || bn) {
+    if (an && bn) return a.i < b.i ? a : b;
+    return an ? a : b;
+  }
+  if (a.v > b.v) return a;
+  if (b.v > a.v) return b;
+  return a.i < b.i ? a : b;
+}
+
+__global__ void __launch_bounds__(256)
+vocab_epilogue_kernel(const float* __restrict__ logits, int ldl, int V, float* __restrict__ logp_out,
+                      long long* __restrict__ seq_out, const int* __restrict__ total_len, int total_off, int L,
+                      int do_logsoftmax, int* __restrict__ tok_out_i32) {
+  __shared__ ArgMax s_am[8];
+  __shared__ float s_sum[8];
+  const int row = blockIdx.x;              // b * L + t
+  const int b = row / L, t = row - b * L;
+  const float* z = logits + (size_t)row * ldl;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  ArgMax am = {-INFINITY, 0x7fffffff};
+  for (int c = tid; c < V; c += 256) am = better(am, ArgMax{z[c], c});
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ArgMax other = {__shfl_xor_sync(0xffffffffu, am.v, o), __shfl_xor_sync(0xffffffffu, am.i, o)};
+    am = better(am, other);
+  }
+  if (lane == 0) s_am[warp] = am;
+  __syncthreads();
+  am = s_am[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) am = better(am, s_am[w]);
+  const float mx = am.v;
+  if (logp_out) {
+    float* o = logp_out + (size_t)row * V;
+    if (do_logsoftmax) {
+      float s = 0.f;
+      for (int c = tid; c < V; c += 256) s += expf(z[c] - mx);
+      s = warp_sum(s);
+      if (lane == 0) s_sum[warp] = s;
+      __syncthreads();
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) tot += s_sum[w];
+      const float lse = logf(tot);
+      for (int c = tid; c < V; c += 256) o[c] = (z[c] - mx) - lse;
+    } else {
+      for (int c = tid; c < V; c += 256) o[c] = z[c];
+    }
+  }
+  if (tid == 0) {
+    int tok = am.i;
+    if (tok_out_i32) tok_out_i32[row] = tok;            // SAIC keeps the unpadded pick
+    if (seq_out) {
+      if (total_len && t >= total_len[b] + total_off) tok = 0;
+      seq_out[row] = tok;
+    }
+  }
+}
+
+// phrase_length[:, :L] / phrase_syn[:, :L] (i64) / phrase_num to the caller's tensors.
+// col0 = 0 for NAIC (phrase_length[:, :-2]), 1 for SAIC (phrase_length[:, 1:-1]).
+__global__ void export_boxes_kernel(DecodeState st, int rows, int Lb, int L, int col0, int* __restrict__ phrase_num,
+                                    int* __restrict__ phrase_length, long long* __restrict__ phrase_syn) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * L) return;
+  const int b = i / L, c = i - b * L;
+  phrase_length[i] = st.phrase_length[b * Lb + col0 + c];
+  phrase_syn[i] = st.phrase_syn[b * Lb + col0 + c];
+  if (c == 0) phrase_num[b] = st.phrase_num[b];
+}
+
+}  // namespace bofi

@@ -1,0 +1,151 @@
+"""Python handle over the C ABI: owns one bofi_handle_t, uploads a reference-layout state_dict,
+and runs encode / decode on raw device pointers of torch tensors (torch is only the allocator and
+the stream provider here)."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .layout import BofiConfig, state_spec
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class BofiEngine:
+    def __init__(self, cfg: BofiConfig, device=0, precision="fp32"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("boficap_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.precision = precision
+        self.device = torch.device("cuda", device if isinstance(device, int) else (device.index or 0))
+        c = _lib.BofiConfigC(
+            abi_version=_lib.ABI_VERSION, tgt_vocab=cfg.tgt_vocab, att_feat_size=cfg.att_feat_size,
+            n_enc=cfg.N_enc, n_dec=cfg.N_dec, n_len=cfg.N_len, d_model=cfg.d_model, d_ff=cfg.d_ff, heads=cfg.h,
+            seq_length=cfg.seq_length, pad_idx=cfg.pad_idx, bos_idx=cfg.bos_idx, eos_idx=cfg.eos_idx,
+            len_idx=cfg.len_idx, precision=_lib.PRECISION[precision])
+        self.handle = C.c_void_p()
+        _lib.check(self.lib.bofi_create(C.byref(c), self.device.index, C.byref(self.handle)))
+        self._batch = None
+
+    def close(self):
+        if getattr(self, "handle", None) and self.handle.value:
+            self.lib.bofi_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- weights ---------------------------------------------------------------------------
+    def load_state_dict(self, sd):
+        spec = state_spec(self.cfg)
+        missing = [k for k in spec if k not in sd]
+        unexpected = [k for k in sd if k not in spec]
+        if missing or unexpected:
+            raise RuntimeError("state_dict mismatch: missing %s unexpected %s" % (missing[:4], unexpected[:4]))
+        for name, (shape, _) in spec.items():
+            t = sd[name].detach().to("cpu", torch.float32).contiguous()
+            if tuple(t.shape) != tuple(shape):
+                raise RuntimeError("size mismatch for %s: %s vs %s" % (name, tuple(t.shape), tuple(shape)))
+            _lib.check(self.lib.bofi_set_weight(self.handle, name.encode(), C.c_void_p(t.data_ptr()), t.numel()))
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bofi_finalize_weights(self.handle, self._stream()))
+        return self
+
+    # ---- device path -------------------------------------------------------------------------
+    def encode(self, att_feats, att_len=None, want_memory=False):
+        assert att_feats.is_cuda and att_feats.dtype == torch.float32
+        att_feats = att_feats.contiguous()
+        B, R, _ = att_feats.shape
+        if att_len is not None:
+            att_len = att_len.to(device=att_feats.device, dtype=torch.int32).contiguous()
+        memory = torch.empty(B, R, self.cfg.d_model, device=att_feats.device) if want_memory else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bofi_encode(self.handle, self._stream(), _ptr(att_feats), _ptr(att_len), B, R, _ptr(memory)))
+        self._batch = (B, R, att_feats, att_len)      # keep inputs alive until decode is enqueued
+        return memory
+
+    def decode(self, mode="NAIC", sample_n=1, output_logsoftmax=1, want_logprobs=True):
+        B = self._batch[0]
+        rows, L, V = B * sample_n, self.cfg.seq_length, self.cfg.tgt_vocab
+        dev = self.device
+        seq = torch.empty(rows, L, dtype=torch.int64, device=dev)
+        logp = torch.empty(rows, L, V, dtype=torch.float32, device=dev) if want_logprobs else None
+        pnum = torch.empty(rows, dtype=torch.int32, device=dev)
+        plen = torch.empty(rows, L, dtype=torch.int32, device=dev)
+        psyn = torch.empty(rows, L, dtype=torch.int64, device=dev)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bofi_decode(self.handle, self._stream(), _lib.MODE[mode], sample_n, int(output_logsoftmax),
+                                            _ptr(seq), _ptr(logp), _ptr(pnum), _ptr(plen), _ptr(psyn)))
+        return seq, logp, pnum, plen, psyn
+
+    def sample_host(self, att_feats, att_len=None, mode="NAIC", sample_n=1, output_logsoftmax=1, out=None, want_logprobs=False):
+        """End-to-end call on HOST tensors (pinned or pageable): H2D, encode, decode, D2H, sync."""
+        assert not att_feats.is_cuda and att_feats.dtype == torch.float32 and att_feats.is_contiguous()
+        B, R, _ = att_feats.shape
+        rows, L, V = B * sample_n, self.cfg.seq_length, self.cfg.tgt_vocab
+        if out is None:
+            out = dict(seq=torch.empty(rows, L, dtype=torch.int64).pin_memory(),
+                       logp=torch.empty(rows, L, V).pin_memory() if want_logprobs else None,
+                       pnum=torch.empty(rows, dtype=torch.int32).pin_memory(),
+                       plen=torch.empty(rows, L, dtype=torch.int32).pin_memory(),
+                       psyn=torch.empty(rows, L, dtype=torch.int64).pin_memory())
+        if att_len is not None:
+            att_len = att_len.to(torch.int32).contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bofi_sample_host(
+                self.handle, self._stream(), _lib.MODE[mode], sample_n, int(output_logsoftmax), _ptr(att_feats), _ptr(att_len),
+                B, R, _ptr(out["seq"]), _ptr(out.get("logp")), _ptr(out["pnum"]), _ptr(out["plen"]), _ptr(out["psyn"])))
+        return out
+
+    def decode_info(self):
+        info = _lib.DecodeInfoC()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bofi_get_decode_info(self.handle, self._stream(), C.byref(info)))
+        return {n: getattr(info, n) for n, _ in info._fields_}
+
+    PROFILE_CLASSES = ("gemm_tcgen05", "gemm_ffma", "attention", "layernorm", "vocab_epilogue", "other")
+
+    def set_profiling(self, on):
+        _lib.check(self.lib.bofi_set_profiling(self.handle, int(on)))
+
+    def get_profile(self):
+        n = len(self.PROFILE_CLASSES)
+        launches, ms, fl, by = (C.c_int32 * n)(), (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bofi_get_profile(self.handle, self._stream(), launches, ms, fl, by))
+        return {c: dict(launches=launches[i], ms=ms[i], flops=fl[i], bytes=by[i]) for i, c in enumerate(self.PROFILE_CLASSES)}
+
+    def workspace_bytes(self, B, R, sample_n=1):
+        return int(self.lib.bofi_workspace_bytes(self.handle, B, R, sample_n))
+
+    # ---- unit entry points (parity tests) ------------------------------------------------------
+    def layernorm(self, x, a2, b2):
+        out = torch.empty_like(x)
+        _lib.check(self.lib.bofi_layernorm_f32(self.handle, self._stream(), _ptr(x), _ptr(a2), _ptr(b2), _ptr(out),
+                                               x.numel() // x.shape[-1]))
+        return out
+
+    def linear(self, a, w, bias=None, residual=None, relu=False):
+        M, K = a.shape
+        N = w.shape[0]
+        out = torch.empty(M, N, device=a.device, dtype=torch.float32)
+        _lib.check(self.lib.bofi_linear_f32(self.handle, self._stream(), _ptr(a), _ptr(w), _ptr(bias), _ptr(residual),
+                                            _ptr(out), M, N, K, int(relu)))
+        return out
+
+    def attention(self, q, k, v, vis=None):
+        B, Tq, _ = q.shape
+        Tk = k.shape[1]
+        out = torch.empty_like(q)
+        _lib.check(self.lib.bofi_attention_f32(self.handle, self._stream(), _ptr(q), _ptr(k), _ptr(v), _ptr(vis),
+                                               _ptr(out), B, Tq, Tk))
+        return out

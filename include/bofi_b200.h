@@ -1,0 +1,143 @@
+/*
+ * bofi_b200.h -- C ABI of the B200-native BoFiCap hot path (libbofi_b200.so).
+ *
+ * The reference (ChangxinWang/BoFiCap) has no FFI / plugin interface: its boundary for this path is
+ * the Python model class.  This header is the boundary a binding would target; every entry point
+ * names the reference code it replaces (paths relative to /root/reference/captioning/models/).
+ * The Python drop-in (boficap_b200/captioning/models) binds it with ctypes; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; all sizes explicit; int return codes (0 = BOFI_OK);
+ *     no exception crosses the ABI; bofi_last_error() returns the text of the last failure
+ *     on the calling thread.
+ *   - "dev" pointers are CUDA device pointers on the handle's device, "host" pointers are host memory.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Every *device*
+ *     entry point is asynchronous on that stream and never synchronises; the *_host entry points
+ *     copy H2D / D2H themselves and return after the results are in the host buffers.
+ *   - the library owns only its packed weights and its workspace (grown on demand, freed by
+ *     bofi_destroy); callers own every buffer they pass.
+ *   - one handle per device; a handle is not thread-safe, distinct handles are independent.
+ *   - there is no CPU fallback: every call fails with BOFI_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef BOFI_B200_H_
+#define BOFI_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BOFI_ABI_VERSION 1
+
+enum {
+  BOFI_OK = 0,
+  BOFI_ERR_INVALID = 1,   /* bad argument / unsupported configuration */
+  BOFI_ERR_CUDA = 2,      /* CUDA runtime / driver error              */
+  BOFI_ERR_STATE = 3,     /* call order (weights missing, not finalised, ...) */
+  BOFI_ERR_NOMEM = 4
+};
+
+enum { BOFI_PRECISION_FP32 = 0, BOFI_PRECISION_BF16 = 1 };
+enum { BOFI_MODE_NAIC = 0, BOFI_MODE_SAIC = 1 };
+
+/* Hyper-parameters the reference reads from `opt`
+ * (AttModel.py:56-75, TransformerModel.py:1631-1640, :404-411).  tgt_vocab = vocab_size + 4. */
+typedef struct bofi_config {
+  int32_t abi_version;    /* BOFI_ABI_VERSION */
+  int32_t tgt_vocab;      /* V, 9491 for uic_sd */
+  int32_t att_feat_size;  /* 2048 */
+  int32_t n_enc, n_dec, n_len;
+  int32_t d_model, d_ff, heads;
+  int32_t seq_length;     /* L = 20; bounding slots Lb = L + 2 */
+  int32_t pad_idx, bos_idx, eos_idx, len_idx;
+  int32_t precision;      /* BOFI_PRECISION_* : arithmetic of the dense contractions */
+} bofi_config_t;
+
+typedef struct bofi_engine* bofi_handle_t;
+
+/* Diagnostics of the last decode on a handle (device-resident counters read back on request). */
+typedef struct bofi_decode_info {
+  int32_t bounding_steps;   /* S: bounding iterations that did work (core_NAIC loop, :1833-1870) */
+  int32_t fill_width;       /* w = last[B-1]-1, the stale-index key window (:1871-1873)         */
+  int32_t kernel_launches;  /* kernels this library enqueued for the decode                     */
+  int32_t nan_batch;        /* 1 when w == 0 made the whole batch NaN (AttModel.py:427-428)     */
+} bofi_decode_info_t;
+
+const char* bofi_last_error(void);
+int bofi_abi_version(void);
+
+/* make_model UIC branch + TransformerModel.__init__ (TransformerModel.py:1558-1568, :1626-1666):
+ * allocates device storage for the 311-entry state_dict of `cfg` on CUDA device `device`. */
+int bofi_create(const bofi_config_t* cfg, int device, bofi_handle_t* out);
+int bofi_destroy(bofi_handle_t h);
+
+/* load_state_dict (tools/eval.py:103): one call per state_dict entry, `name` is the reference key
+ * (SURVEY.md Appendix B), `data` fp32 host memory with `numel` elements (shape is checked by count).
+ * Keys that the decode path never reads (model.length_predictor.length_attn.* / .ff.* when
+ * N_len >= 1) are accepted and ignored. */
+int bofi_set_weight(bofi_handle_t h, const char* name, const float* host_data, int64_t numel);
+/* Number of state_dict entries still missing (0 = complete). */
+int bofi_missing_weights(bofi_handle_t h);
+/* Packs weights for the device path (bf16 copies, fused QKV / KV matrices, (syn,pos) input tables). */
+int bofi_finalize_weights(bofi_handle_t h, void* stream);
+
+/* Workspace the library will hold for a batch of B images x R regions x sample_n (bytes). */
+int64_t bofi_workspace_bytes(bofi_handle_t h, int32_t B, int32_t R, int32_t sample_n);
+
+/* _prepare_feature (TransformerModel.py:1674-1711: clip_att, pack_wrapper(att_embed), encode):
+ *   att_feats  dev f32 [B,R,att_feat_size]
+ *   att_len    dev i32 [B] = number of valid (prefix) regions per image, or NULL when att_masks is None
+ *   memory_out dev f32 [B,R,d_model] or NULL (memory stays in the workspace for bofi_decode). */
+int bofi_encode(bofi_handle_t h, void* stream, const float* att_feats, const int32_t* att_len,
+                int32_t B, int32_t R, float* memory_out);
+
+/* core_NAIC / core_SAIC + logit + log_softmax + greedy sample_next_word + tail padding
+ * (TransformerModel.py:1823-1986, AttModel.py:203-210, :419-437, CaptionModel.py:383-390),
+ * on the memory left in the workspace by the preceding bofi_encode.  Rows = B * sample_n.
+ *   seq           dev i64 [rows, L]
+ *   logprobs      dev f32 [rows, L, V] or NULL (skip materialising the 759 KB/row tensor)
+ *   phrase_num    dev i32 [rows]; phrase_length dev i32 [rows, L]; phrase_syn dev i64 [rows, L]
+ *   output_logsoftmax: 1 = log-softmax (default of the reference), 0 = raw logits. */
+int bofi_decode(bofi_handle_t h, void* stream, int32_t mode, int32_t sample_n, int32_t output_logsoftmax,
+                int64_t* seq, float* logprobs, int32_t* phrase_num, int32_t* phrase_length,
+                int64_t* phrase_syn);
+
+/* AttModel._sample (AttModel.py:307-334, :419-437) end to end with HOST buffers: H2D of att_feats /
+ * att_len, encode, decode, D2H of the results, then a stream synchronise.  host pointers may be
+ * pageable or pinned; logprobs may be NULL. */
+int bofi_sample_host(bofi_handle_t h, void* stream, int32_t mode, int32_t sample_n, int32_t output_logsoftmax,
+                     const float* att_feats, const int32_t* att_len, int32_t B, int32_t R,
+                     int64_t* seq, float* logprobs, int32_t* phrase_num, int32_t* phrase_length,
+                     int64_t* phrase_syn);
+
+/* Counters of the last decode (synchronises `stream`). */
+int bofi_get_decode_info(bofi_handle_t h, void* stream, bofi_decode_info_t* out);
+
+/* Per-launch CUDA-event timing of the library's own kernels, for bench.py's roofline line.
+ * Classes: 0 tcgen05 GEMM, 1 FFMA GEMM, 2 attention, 3 LayerNorm, 4 vocab epilogue, 5 other.
+ * bofi_set_profiling(h, 1) clears the records and starts recording; bofi_get_profile synchronises
+ * `stream` and sums launches / milliseconds / algorithmic flops / algorithmic bytes per class
+ * (arrays of BOFI_PROFILE_CLASSES entries). */
+#define BOFI_PROFILE_CLASSES 6
+int bofi_set_profiling(bofi_handle_t h, int32_t enable);
+int bofi_get_profile(bofi_handle_t h, void* stream, int32_t* launches, double* ms, double* flops, double* bytes);
+
+/* ---- unit entry points (used by the parity tests to pin individual kernels) ------------------- */
+/* LayerNorm of TransformerModel.py:1338-1349 on rows x d_model fp32 (dev pointers). */
+int bofi_layernorm_f32(bofi_handle_t h, void* stream, const float* x, const float* a2, const float* b2,
+                       float* out, int32_t rows);
+/* out[M,N] = act(A[M,K] @ W[N,K]^T + bias) (+ residual) through the handle's GEMM backend
+ * (fp32: SIMT FFMA; bf16: tcgen05).  A, W, bias, residual, out are dev f32; conversion to the
+ * backend's operand type happens inside.  relu and residual are optional (0 / NULL). */
+int bofi_linear_f32(bofi_handle_t h, void* stream, const float* A, const float* W, const float* bias,
+                    const float* residual, float* out, int32_t M, int32_t N, int32_t K, int32_t relu);
+/* softmax(QK^T/sqrt(dk), keys >= vis masked) V for `heads` heads, fp32 dev tensors
+ * (TransformerModel.py:1421-1432): q [B,Tq,d], k/v [B,Tk,d], vis i32 [B,Tq] visible-key counts. */
+int bofi_attention_f32(bofi_handle_t h, void* stream, const float* q, const float* k, const float* v,
+                       const int32_t* vis, float* out, int32_t B, int32_t Tq, int32_t Tk);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BOFI_B200_H_ */

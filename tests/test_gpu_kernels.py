@@ -1,0 +1,99 @@
+"""GPU: each hand-written kernel through the C ABI unit entry points vs a plain PyTorch fp32 statement
+of the reference op (tolerances written per test)."""
+import math
+
+import pytest
+import torch
+
+from boficap_b200.layout import BofiConfig
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engines():
+    from boficap_b200.engine import BofiEngine
+    e32 = BofiEngine(BofiConfig(), 0, "fp32")
+    e16 = BofiEngine(BofiConfig(), 0, "bf16")
+    yield e32, e16
+    e32.close()
+    e16.close()
+
+
+def test_layernorm_matches_reference_formula(engines):
+    e32, _ = engines
+    g = torch.Generator().manual_seed(0)
+    x = (torch.randn(777, 512, generator=g) * 3 + 0.5).cuda()
+    a = (1 + 0.1 * torch.randn(512, generator=g)).cuda()
+    b = (0.1 * torch.randn(512, generator=g)).cuda()
+    out = e32.layernorm(x, a, b)
+    xd = x.double()
+    ref = a.double() * (xd - xd.mean(-1, keepdim=True)) / (xd.std(-1, keepdim=True) + 1e-6) + b.double()
+    assert (out.double() - ref).abs().max().item() < 2e-6     # fp32 rounding only
+    # NOT nn.LayerNorm: biased variance / eps inside the sqrt would differ at the 1e-3 level
+    wrong = torch.nn.functional.layer_norm(x, (512,), a, b, 1e-6)
+    assert (out - wrong).abs().max().item() > 1e-4
+
+
+@pytest.mark.parametrize("M,N,K,relu,resid", [(300, 512, 512, False, True), (128, 128, 64, True, False),
+                                              (1000, 1536, 2048, False, False), (77, 200, 512, True, False),
+                                              (260, 203, 512, False, False)])
+def test_linear_fp32_simt(engines, M, N, K, relu, resid):
+    e32, _ = engines
+    g = torch.Generator().manual_seed(M + N)
+    a = torch.randn(M, K, generator=g).cuda()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    res = torch.randn(M, N, generator=g).cuda() if resid else None
+    out = e32.linear(a, w, bias, res, relu)
+    ref = a.double() @ w.double().T + bias.double()
+    if relu:
+        ref = ref.relu()
+    if resid:
+        ref = ref + res.double()
+    assert (out.double() - ref).abs().max().item() < 5e-5     # fp32 accumulation order only
+
+
+@pytest.mark.parametrize("M,N,K,relu,resid", [(128, 128, 64, False, False), (300, 512, 512, False, True),
+                                              (1000, 1536, 2048, True, False), (257, 9496, 512, False, False),
+                                              (36864, 512, 2048, True, False)])
+def test_linear_bf16_tcgen05(engines, M, N, K, relu, resid):
+    _, e16 = engines
+    g = torch.Generator().manual_seed(M + N + 1)
+    a = torch.randn(M, K, generator=g).cuda()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    res = torch.randn(M, N, generator=g).cuda() if resid else None
+    out = e16.linear(a, w, bias, res, relu)
+    # operands are rounded to bf16 once, products accumulate in fp32: compare against exactly that
+    ref = a.bfloat16().double() @ w.bfloat16().double().T + bias.double()
+    if relu:
+        ref = ref.relu()
+    if resid:
+        ref = ref + res.double()
+    err = (out.double() - ref).abs().max().item()
+    assert err < 2e-4, err
+
+
+def test_attention_prefix_masks_and_nan_rows(engines):
+    e32, _ = engines
+    g = torch.Generator().manual_seed(5)
+    B, Tq, Tk, h = 9, 20, 100, 8
+    q = torch.randn(B, Tq, 512, generator=g).cuda()
+    k = torch.randn(B, Tk, 512, generator=g).cuda()
+    v = torch.randn(B, Tk, 512, generator=g).cuda()
+    vis = torch.randint(0, Tk + 1, (B, Tq), generator=g).int()
+    vis[0, 0] = 0                     # all-masked row -> NaN like softmax over -inf
+    vis[1, :] = Tk
+    out = e32.attention(q, k, v, vis.cuda()).cpu()
+    qh = q.cpu().view(B, Tq, h, 64).transpose(1, 2)
+    kh = k.cpu().view(B, Tk, h, 64).transpose(1, 2)
+    vh = v.cpu().view(B, Tk, h, 64).transpose(1, 2)
+    sc = qh @ kh.transpose(-2, -1) / 8.0
+    mask = torch.arange(Tk)[None, None, :] < vis[:, :, None]
+    sc = sc.masked_fill(~mask[:, None], float("-inf"))
+    ref = (torch.softmax(sc, -1) @ vh).transpose(1, 2).reshape(B, Tq, 512)
+    assert torch.isnan(out[0, 0]).all() and torch.isnan(ref[0, 0]).all()
+    ok = ~torch.isnan(ref)
+    assert (torch.isnan(out) == torch.isnan(ref)).all()
+    assert (out[ok] - ref[ok]).abs().max().item() < 2e-5
