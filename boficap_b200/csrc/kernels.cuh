@@ -66,7 +66,7 @@ attention_kernel(const T* __restrict__ Q, int ldq, const T* __restrict__ K, cons
   if (step_is_dead(live_rows)) return;
   extern __shared__ float smem[];
   float* Ks = smem;                         // [Tk][65]
-  float* Vs = Ks + Tk * (kHeadDim + 1);     // [Tk][64]
+  float* Vs = Ks + ((Tk * (kHeadDim + 1) + 3) & ~3);   // [Tk][64], 16-byte aligned
   float* qs = Vs + Tk * kHeadDim;           // [4][64]
   float* ps = qs + 4 * kHeadDim;            // [4][kMaxKeys]
   const int head = blockIdx.x, b = blockIdx.y;
@@ -137,7 +137,7 @@ attention_kernel(const T* __restrict__ Q, int ldq, const T* __restrict__ K, cons
 }
 
 inline size_t attention_smem_bytes(int Tk) {
-  return sizeof(float) * ((size_t)Tk * (kHeadDim + 1) + (size_t)Tk * kHeadDim + 4 * kHeadDim + 4 * kMaxKeys);
+  return sizeof(float) * ((((size_t)Tk * (kHeadDim + 1) + 3) & ~(size_t)3) + (size_t)Tk * kHeadDim + 4 * kHeadDim + 4 * kMaxKeys);
 }
 
 // fp32 -> T, 128-bit vectorised (n % 4 == 0)

@@ -123,7 +123,13 @@ def test_shard_invariance_at_bench_size():
     fc, att, _ = synth.synth_inputs(1024, 36, seed=1)
     full = run_cuda(eng, att, None)
     if int(full[3][-1].sum()) == 0:
-        pytest.skip("last row empty -> NaN batch")
+        # an empty last row makes the whole batch NaN (w == 0); boxes do not depend on the batch, so move
+        # an image that does produce phrases to the end and decode again
+        j = int((full[3].sum(1) > 0).nonzero()[-1])
+        att = att.clone()
+        att[[j, 1023]] = att[[1023, j]]
+        full = run_cuda(eng, att, None)
+    assert not torch.isnan(full[1]).any()
     idx = torch.cat([torch.arange(100, 164), torch.tensor([1023])])
     part = run_cuda(eng, att[idx], None)
     for a, b in zip(part, full):
