@@ -109,6 +109,8 @@ struct bofi_engine {
   Norm enc_norm, dec_norm, lp_norm;
   const float *w_len2 = nullptr, *b_len2 = nullptr, *w_syn2 = nullptr, *b_syn2 = nullptr;
   DevBuf bound_in, fill_in;            // (id, position) input tables
+  DevBuf tab_y, tab_qkv;               // N_len == 1: LN + QKV of every (syn, position) bounding input row
+  bool bound_fast = false;             // [LEN]-row-only bounding step (NAIC, N_len == 1)
   // workspace
   DevBuf attT, x, y, qkv, ao, q, ffh, memT, attlen, hrow, hid, logits, state_i32, tok;
   std::vector<DevBuf> kv;              // cross K/V per bounding layer then per decoder layer
@@ -526,6 +528,64 @@ static int bounding_step(bofi_engine* e, cudaStream_t s, int rows, int sn, int s
   return BOFI_OK;
 }
 
+// N_len == 1 bounding step restricted to the [LEN] row (the only row LengthPredictor_UIC.forward reads,
+// TransformerModel.py:375): tabulated self-attention K/V, then M = rows GEMMs instead of M = rows * 22.
+template <typename T>
+static int bounding_step_fast(bofi_engine* e, cudaStream_t s, int rows, int sn, int step_col) {
+  const bofi_config_t& c = e->cfg;
+  const int Lb = e->Lb;
+  const int* live = e->st.counters;
+  const int* mem_len = e->have_len ? e->attlen.as<int>() : nullptr;
+  const Layer& ly = e->lp[0];
+  float* x = e->x.as<float>();
+  T* y = e->y.as<T>();
+  T* q = e->q.as<T>();
+  T* ao = e->ao.as<T>();
+  T* ffh = e->ffh.as<T>();
+  const int q_row = c.len_idx * Lb;                                   // (syn = len_idx, position 0)
+  const float* x0 = e->bound_in.as<float>() + (size_t)q_row * kD;     // the constant [LEN] input row
+  {
+    ProfScope prof(e, s, PC_ATTENTION, 4.0 * rows * Lb * kD, 0.0);
+    bound_self_attn_kernel<T><<<rows, 256, 0, s>>>(e->tab_qkv.as<T>(), Lb, q_row, e->st.ext, e->st.last, ao,
+                                                   1.0f / sqrtf((float)kHeadDim), live);
+  }
+  CU_TRY(cudaGetLastError());
+  RC_TRY((linear<T, float>(e, s, ao, kD, ly.sa.o, x0, 0, x, kD, rows, 0, live)));          // residual = x0 broadcast
+  RC_TRY(layernorm<T>(e, s, x, kD, ly.ln[1], y, kD, rows, nullptr, live));
+  RC_TRY((linear<T, T>(e, s, y, kD, ly.ca.q, nullptr, 0, q, kD, rows, 0, live)));
+  RC_TRY(attention<T>(e, s, q, kD, e->kv[0].as<T>(), e->kv[0].as<T>() + kD, 2 * kD, ao, kD, rows, 1, e->R, mem_len, 1, 0, sn, sn, live));
+  RC_TRY((linear<T, float>(e, s, ao, kD, ly.ca.o, x, kD, x, kD, rows, 0, live)));
+  RC_TRY(layernorm<T>(e, s, x, kD, ly.ln[2], y, kD, rows, nullptr, live));
+  RC_TRY((linear<T, T>(e, s, y, kD, ly.w1, nullptr, 0, ffh, c.d_ff, rows, 1, live)));
+  RC_TRY((linear<T, float>(e, s, ffh, c.d_ff, ly.w2, x, kD, x, kD, rows, 0, live)));
+  RC_TRY(layernorm<float>(e, s, x, kD, e->lp_norm, e->hrow.as<float>(), kD, rows, nullptr, live));
+  {
+    ProfScope prof(e, s, PC_GEMM_SIMT, 2.0 * rows * 200 * kD, 4.0 * (rows * (kD + 200.0) + 200.0 * kD));
+    cudaError_t err = gemm_simt<float, float>(s, e->hrow.as<float>(), kD, e->head1.w32, kD, e->head1.b, nullptr, 0,
+                                              e->hid.as<float>(), 200, rows, 200, kD, 1, live);
+    if (err != cudaSuccess) return fail(BOFI_ERR_CUDA, "head gemm: %s", cudaGetErrorString(err));
+  }
+  const size_t smem = sizeof(float) * (30 * 100 + 4 * 200 + 4 * 32);
+  {
+    ProfScope prof(e, s, PC_OTHER, 0.0, 0.0);
+    bound_head_kernel<<<ceil_div(rows, 4), 128, smem, s>>>(e->hid.as<float>(), 100, e->w_len2, e->b_len2, e->w_syn2, e->b_syn2,
+                                                           20, 10, e->st, rows, Lb, e->L, step_col, step_col + 1, 4, 6, 0);
+  }
+  CU_TRY(cudaGetLastError());
+  return BOFI_OK;
+}
+
+// LN + fused QKV projection of all 10 x Lb possible bounding-layer input rows (once per checkpoint).
+template <typename T>
+static int build_bound_tables(bofi_engine* e, cudaStream_t s) {
+  const int rows = 10 * e->Lb;
+  RC_TRY(e->tab_y.reserve((size_t)rows * kD * sizeof(T)));
+  RC_TRY(e->tab_qkv.reserve((size_t)rows * 3 * kD * sizeof(T)));
+  RC_TRY(layernorm<T>(e, s, e->bound_in.as<float>(), kD, e->lp[0].ln[0], e->tab_y.as<T>(), kD, rows, nullptr, nullptr));
+  RC_TRY((linear<T, T>(e, s, e->tab_y.as<T>(), kD, e->lp[0].sa.qkv, nullptr, 0, e->tab_qkv.as<T>(), 3 * kD, rows, 0, nullptr)));
+  return BOFI_OK;
+}
+
 template <typename T>
 static int decode_naic(bofi_engine* e, cudaStream_t s, int sn, int output_logsoftmax, long long* seq, float* logprobs,
                        int* phrase_num, int* phrase_length, long long* phrase_syn) {
@@ -546,7 +606,10 @@ static int decode_naic(bofi_engine* e, cudaStream_t s, int sn, int output_logsof
     init_state_kernel<<<ceil_div(rows, 128), 128, 0, s>>>(e->st, rows, Lb, L, c.len_idx, c.bos_idx, 0);
   }
   CU_TRY(cudaGetLastError());
-  for (int i = 0; i < L; ++i) RC_TRY(bounding_step<T>(e, s, rows, sn, i, 0));
+  for (int i = 0; i < L; ++i) {
+    if (e->bound_fast) RC_TRY(bounding_step_fast<T>(e, s, rows, sn, i));
+    else RC_TRY(bounding_step<T>(e, s, rows, sn, i, 0));
+  }
 
   // filling step (decode_NA, :570-587): all L slots of every row in parallel
   {
@@ -627,7 +690,7 @@ int bofi_destroy(bofi_handle_t e) {
   for (DevBuf& b : e->packed) b.release();
   for (DevBuf& b : e->kv) b.release();
   DevBuf* all[] = {&e->bound_in, &e->fill_in, &e->attT, &e->x, &e->y, &e->qkv, &e->ao, &e->q, &e->ffh, &e->memT, &e->attlen,
-                   &e->hrow, &e->hid, &e->logits, &e->state_i32, &e->tok, &e->h_in, &e->h_len, &e->h_seq, &e->h_logp,
+                   &e->tab_y, &e->tab_qkv, &e->hrow, &e->hid, &e->logits, &e->state_i32, &e->tok, &e->h_in, &e->h_len, &e->h_seq, &e->h_logp,
                    &e->h_pnum, &e->h_plen, &e->h_psyn, &e->unit_a, &e->unit_w, &e->unit_o};
   for (DevBuf* b : all) b->release();
   delete e;
@@ -703,6 +766,9 @@ int bofi_finalize_weights(bofi_handle_t e, void* stream) {
                                                       W(e, "model.pos_embed.pe"), c.bos_idx, 10, e->Lb, e->L, sqrtf((float)kD),
                                                       e->bound_in.as<float>(), e->fill_in.as<float>());
   CU_TRY(cudaGetLastError());
+  const char* bg = getenv("BOFI_BOUND");
+  e->bound_fast = (c.n_len == 1) && !(bg && strcmp(bg, "generic") == 0);
+  if (e->bound_fast) RC_TRY(e->bf16_mode ? build_bound_tables<bf16>(e, s) : build_bound_tables<float>(e, s));
   CU_TRY(cudaStreamSynchronize(s));
   e->finalized = true;
   return BOFI_OK;

@@ -10,10 +10,11 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2..5 = epilogue (TMEM lane quadrant = warp % 4).
 // Pipelines: full[s]/empty[s] mbarriers between TMA and MMA, one tmem_full mbarrier MMA -> epilogue.
-// Two CTAs are resident per SM (STAGES x 32 KB of smem each), so one CTA's epilogue overlaps the
-// other's main loop without a persistent scheduler.
+// Persistent CTAs (one per SM) with a double-buffered TMEM accumulator: the epilogue of one tile overlaps
+// the main loop of the next.
 #pragma once
 #include <cuda.h>
+#include <unordered_map>
 #include "common.cuh"
 
 namespace bofi {
@@ -105,8 +106,15 @@ struct SmemLayout {
   static constexpr int kTotal = kBarOffset + 256 + 1024;   // barriers + alignment slack
 };
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Persistent: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, +gridDim.x, ... (N fastest, so
+// the CTAs resident at one time share A panels through L2).  Two accumulator tiles live in TMEM
+// (2 x BN columns): the epilogue of tile i overlaps the main loop of tile i+1.
 template <int BN, int STAGES, typename TOut>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const float* __restrict__ bias, const float* residual, int ldr, TOut* C, int ldc,
                int M, int N, int K, int relu, const int* live_rows) {
@@ -115,14 +123,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
-  uint64_t* full_bar = bars;                 // [STAGES]
-  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
-  uint64_t* tmem_full_bar = bars + 2 * STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  uint64_t* full_bar = bars;                      // [STAGES]  TMA -> MMA
+  uint64_t* empty_bar = bars + STAGES;            // [STAGES]  MMA -> TMA
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;    // [2]       MMA -> epilogue
+  uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;   // [2]   epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * BN;
   const int nk = K / kBK;
+  const int tiles_n = (N + BN - 1) / BN;
+  const int ntiles = ((M + kBM - 1) / kBM) * tiles_n;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -134,11 +144,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_init(smem_u32(&full_bar[s]), 1);
         mbar_init(smem_u32(&empty_bar[s]), 1);
       }
-      mbar_init(smem_u32(tmem_full_bar), 1);
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(smem_u32(&tmem_full_bar[a]), 1);
+        mbar_init(smem_u32(&tmem_empty_bar[a]), 4);   // one arrival per epilogue warp
+      }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -149,75 +162,107 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
-        const uint32_t fb = smem_u32(&full_bar[s]);
-        mbar_expect_tx(fb, L::kStageBytes);
-        const uint32_t a_dst = smem_u32(smem + s * L::kStageBytes);
-        tma_load_2d(a_dst, &tmA, fb, kb * kBK, m0);
-        tma_load_2d(a_dst + L::kABytes, &tmB, fb, kb * kBK, n0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * kBM, n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[s]);
+          mbar_expect_tx(fb, L::kStageBytes);
+          const uint32_t a_dst = smem_u32(smem + s * L::kStageBytes);
+          tma_load_2d(a_dst, &tmA, fb, kb * kBK, m0);
+          tma_load_2d(a_dst + L::kABytes, &tmB, fb, kb * kBK, n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(kBM, BN);
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(smem_u32(&full_bar[s]), ph);
+      int it = 0, t = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
+        const int as = t & 1;
+        const uint32_t aph = (t >> 1) & 1;
+        mbar_wait(smem_u32(&tmem_empty_bar[as]), aph ^ 1);     // epilogue drained this accumulator
         tcgen05_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
-        const uint64_t adesc = make_sw128_desc(a_addr);
-        const uint64_t bdesc = make_sw128_desc(a_addr + L::kABytes);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(smem_u32(&full_bar[s]), ph);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
+          const uint64_t adesc = make_sw128_desc(a_addr);
+          const uint64_t bdesc = make_sw128_desc(a_addr + L::kABytes);
 #pragma unroll
-        for (int k = 0; k < kBK / kUK; ++k) {
-          // +32 bytes per K step inside the 128-byte swizzle row (encoded >> 4)
-          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < kBK / kUK; ++k) {
+            // +32 bytes per K step inside the 128-byte swizzle row (encoded >> 4)
+            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(smem_u32(&empty_bar[s]));      // frees the smem stage when these MMAs retire
         }
-        umma_commit(smem_u32(&empty_bar[s]));   // frees the smem stage when these MMAs retire
+        umma_commit(smem_u32(&tmem_full_bar[as]));   // accumulator complete
       }
-      umma_commit(smem_u32(tmem_full_bar));     // accumulator complete
     }
   } else {
-    const int quad = warp & 3;                  // TMEM lanes [32*quad, 32*quad+32)
-    const int row = m0 + quad * 32 + lane;
-    mbar_wait(smem_u32(tmem_full_bar), 0);
-    tcgen05_fence_after();
+    const int quad = warp & 3;                       // TMEM lanes [32*quad, 32*quad+32)
+    int t = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
+      const int m0 = (tile / tiles_n) * kBM, n0 = (tile % tiles_n) * BN;
+      const int as = t & 1;
+      const uint32_t aph = (t >> 1) & 1;
+      const int row = m0 + quad * 32 + lane;
+      mbar_wait(smem_u32(&tmem_full_bar[as]), aph);
+      tcgen05_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32), r);
-      const int n = n0 + c * 32;
-      if (row < M && n < N) {
-        float v[32];
-        const bool full = (n + 32 <= N);
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n = n0 + c * 32;
+        if (n >= N) break;                            // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + c * 32), r);
+        if (row < M) {
+          float v[32];
+          TOut* dst = C + (size_t)row * ldc + n;
+          if (n + 32 <= N) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(r[j]);
-          if (full || n + j < N) {
-            if (bias) x += bias[n + j];
-            if (relu) x = fmaxf(x, 0.f);
-            if (residual) x += residual[(size_t)row * ldr + n + j];
+            for (int j = 0; j < 32; j += 4) {
+              float4 x = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                     __uint_as_float(r[j + 3]));
+              if (bias) {
+                const float4 bb = *reinterpret_cast<const float4*>(bias + n + j);
+                x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
+              }
+              if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+              if (residual) {
+                const float4 rr = *reinterpret_cast<const float4*>(residual + (size_t)row * ldr + n + j);
+                x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
+              }
+              v[j] = x.x; v[j + 1] = x.y; v[j + 2] = x.z; v[j + 3] = x.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) store4(dst + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+          } else {
+            for (int j = 0; j < 32 && n + j < N; ++j) {
+              float x = __uint_as_float(r[j]);
+              if (bias) x += bias[n + j];
+              if (relu) x = fmaxf(x, 0.f);
+              if (residual) x += residual[(size_t)row * ldr + n + j];
+              dst[j] = from_float<TOut>(x);
+            }
           }
-          v[j] = x;
-        }
-        TOut* dst = C + (size_t)row * ldc + n;
-        if (full) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) store4(dst + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-        } else {
-          for (int j = 0; j < 32 && n + j < N; ++j) dst[j] = from_float<TOut>(v[j]);
         }
       }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[as]));
     }
   }
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
   }
 }
 
@@ -252,6 +297,17 @@ inline bool make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t rows, uint
   return r == CUDA_SUCCESS;
 }
 
+inline int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
 template <int BN, int STAGES, typename TOut>
 inline cudaError_t launch(cudaStream_t s, const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias,
                           const float* residual, int ldr, TOut* C, int ldc, int M, int N, int K, int relu,
@@ -263,9 +319,36 @@ inline cudaError_t launch(cudaStream_t s, const CUtensorMap& tmA, const CUtensor
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  dim3 grid((N + BN - 1) / BN, (M + kBM - 1) / kBM);
+  const int ntiles = ((M + kBM - 1) / kBM) * ((N + BN - 1) / BN);
+  const int grid = ntiles < num_sms() ? ntiles : num_sms();
   gemm_tc_kernel<BN, STAGES, TOut><<<grid, kThreads, L::kTotal, s>>>(tmA, tmB, bias, residual, ldr, C, ldc, M, N, K, relu, live_rows);
   return cudaGetLastError();
+}
+
+// Tensor maps are pure functions of (pointer, shape, pitch, box): cache them (weights and workspace
+// buffers are stable across steps), so steady-state launches make no driver call.
+struct TmapKey {
+  const void* p; uint64_t rows, cols, ld; uint32_t box;
+  bool operator==(const TmapKey& o) const { return p == o.p && rows == o.rows && cols == o.cols && ld == o.ld && box == o.box; }
+};
+struct TmapHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.p);
+    h ^= k.rows * 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h ^= k.cols * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2);
+    h ^= (k.ld * 31 + k.box) + (h << 6) + (h >> 2);
+    return h;
+  }
+};
+inline const CUtensorMap* cached_tmap(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapHash> cache;
+  TmapKey key{ptr, rows, cols, ld, box_rows};
+  auto it = cache.find(key);
+  if (it != cache.end()) return &it->second;
+  if (cache.size() > 8192) cache.clear();
+  CUtensorMap tm;
+  if (!make_tmap_bf16(&tm, ptr, rows, cols, ld, box_rows)) return nullptr;
+  return &cache.emplace(key, tm).first->second;
 }
 
 // A [M,K] bf16 (pitch lda), W [N,K] bf16 (pitch ldw).  Requires K % 64 == 0, 16-byte aligned pitches.
@@ -274,12 +357,15 @@ inline cudaError_t gemm_tc(cudaStream_t s, const bf16* A, int lda, const bf16* W
                            const float* residual, int ldr, TOut* C, int ldc, int M, int N, int K, int relu,
                            const int* live_rows) {
   if (M <= 0 || N <= 0) return cudaSuccess;
-  if (K % kBK != 0 || lda % 8 != 0 || ldw % 8 != 0 || ldc % 8 != 0) return cudaErrorInvalidValue;
-  constexpr int BN = 128, STAGES = 3;
-  CUtensorMap tmA, tmB;
-  if (!make_tmap_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBM)) return cudaErrorInvalidValue;
-  if (!make_tmap_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, BN)) return cudaErrorInvalidValue;
-  return launch<BN, STAGES, TOut>(s, tmA, tmB, bias, residual, ldr, C, ldc, M, N, K, relu, live_rows);
+  if (K % kBK != 0 || lda % 8 != 0 || ldw % 8 != 0 || (ldc * sizeof(TOut)) % 16 != 0 || (residual && ldr % 4 != 0))
+    return cudaErrorInvalidValue;
+  const int tiles256 = ((M + kBM - 1) / kBM) * ((N + 255) / 256);
+  const bool wide = tiles256 >= num_sms() / 2;      // small problems: narrower tiles spread over more SMs
+  const CUtensorMap* tmA = cached_tmap(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBM);
+  const CUtensorMap* tmB = cached_tmap(W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, wide ? 256 : 64);
+  if (!tmA || !tmB) return cudaErrorInvalidValue;
+  if (wide) return launch<256, 4, TOut>(s, *tmA, *tmB, bias, residual, ldr, C, ldc, M, N, K, relu, live_rows);
+  return launch<64, 6, TOut>(s, *tmA, *tmB, bias, residual, ldr, C, ldc, M, N, K, relu, live_rows);
 }
 
 }  // namespace tc

@@ -136,6 +136,56 @@ attention_kernel(const T* __restrict__ Q, int ldq, const T* __restrict__ K, cons
   }
 }
 
+// Self-attention of the [LEN] row in the NAIC bounding layer when N_len == 1 (SURVEY.md Appendix A,
+// "F_useful"): the layer input is a pure function of (syn id, position), so LN + Q/K/V projections of
+// all 10 x Lb possible rows are tabulated per checkpoint (qkv_tab [10*Lb, 1536]); row 0 only attends
+// to the assigned slots k < last (tgt_mask[j, 0, :last], TransformerModel.py:1859,1867).
+// One CTA per batch row, one warp per head; arithmetic order mirrors attention_kernel so the result
+// is bit-identical to running the full 22-row layer.
+template <typename T>
+__global__ void __launch_bounds__(256)
+bound_self_attn_kernel(const T* __restrict__ qkv_tab, int Lb, int q_row, const int* __restrict__ ext,
+                       const int* __restrict__ last, T* __restrict__ O, float scale, const int* live_rows) {
+  if (step_is_dead(live_rows)) return;
+  __shared__ float qs[8][kHeadDim];
+  __shared__ int rowid[32];
+  const int b = blockIdx.x, head = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvis = min(last[b], Lb);
+  if (threadIdx.x < 32) rowid[lane] = (lane < Lb) ? ext[b * Lb + lane] * Lb + lane : 0;
+  const T* qg = qkv_tab + (size_t)q_row * 3 * kD + head * kHeadDim;
+  qs[head][lane] = to_float<T>(qg[lane]);
+  qs[head][lane + 32] = to_float<T>(qg[lane + 32]);
+  __syncthreads();
+  float s = -INFINITY;
+  if (lane < nvis) {
+    const T* kr = qkv_tab + (size_t)rowid[lane] * 3 * kD + kD + head * kHeadDim;
+    float d = 0.f;
+#pragma unroll
+    for (int c = 0; c < kHeadDim; c += 4) {
+      const float4 kq = load4(kr + c);
+      d = fmaf(qs[head][c], kq.x, d);
+      d = fmaf(qs[head][c + 1], kq.y, d);
+      d = fmaf(qs[head][c + 2], kq.z, d);
+      d = fmaf(qs[head][c + 3], kq.w, d);
+    }
+    s = d * scale;
+  }
+  const float mx = warp_max(s);
+  const float e = (lane < nvis) ? expf(s - mx) : 0.f;
+  const float sum = warp_sum(e);
+  const float p = e / sum;
+  float o0 = 0.f, o1 = 0.f;
+  for (int j = 0; j < nvis; ++j) {
+    const float pj = __shfl_sync(0xffffffffu, p, j);
+    const T* vr = qkv_tab + (size_t)rowid[j] * 3 * kD + 2 * kD + head * kHeadDim;
+    o0 = fmaf(pj, to_float<T>(vr[lane]), o0);
+    o1 = fmaf(pj, to_float<T>(vr[lane + 32]), o1);
+  }
+  T* og = O + (size_t)b * kD + head * kHeadDim;
+  og[lane] = from_float<T>(o0);
+  og[lane + 32] = from_float<T>(o1);
+}
+
 inline size_t attention_smem_bytes(int Tk) {
   return sizeof(float) * ((((size_t)Tk * (kHeadDim + 1) + 3) & ~(size_t)3) + (size_t)Tk * kHeadDim + 4 * kHeadDim + 4 * kMaxKeys);
 }

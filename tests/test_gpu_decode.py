@@ -168,3 +168,26 @@ def test_bf16_mode_logits_within_2e2_and_agreement_reported(gemm, capsys):
         with capsys.disabled():
             print("[bf16 vs fp32] max |dlogit| on box-agreeing images: %.4f" % err)
         assert err < 2e-2
+
+
+def test_fast_len_row_bounding_equals_full_layer_formulation(monkeypatch):
+    """N_len == 1: the [LEN]-row-only bounding step (tabulated self-attention K/V, M = rows GEMMs) must give
+    bit-identical boxes/tokens/log-probs to the reference formulation that recomputes all 22 rows."""
+    from boficap_b200.engine import BofiEngine
+    cfg = BofiConfig()
+    sd = checkpoint(cfg, "s_real")
+    fc, att, masks = synth.synth_inputs(48, 40, seed=21, adaptive=True)
+    for precision in ("fp32", "bf16"):
+        fast = BofiEngine(cfg, 0, precision).load_state_dict(sd)
+        monkeypatch.setenv("BOFI_BOUND", "generic")
+        full = BofiEngine(cfg, 0, precision).load_state_dict(sd)
+        monkeypatch.delenv("BOFI_BOUND")
+        a = run_cuda(fast, att, masks)
+        la = fast.decode_info()["kernel_launches"]
+        b = run_cuda(full, att, masks)
+        lb = full.decode_info()["kernel_launches"]
+        for x, y in zip(a, b):
+            assert torch.equal(torch.nan_to_num(x), torch.nan_to_num(y)), precision
+        assert la < lb
+        fast.close()
+        full.close()
