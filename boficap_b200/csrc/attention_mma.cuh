@@ -1,0 +1,235 @@
+// bf16 tensor-core attention for the short sequences of this path (<= 128 queries / keys per image):
+// softmax(Q K^T / sqrt(64) with keys >= nvis masked) V, one CTA per (head, batch row), one warp per
+// 16-query tile.  Q, K, V tiles are staged once in shared memory (row pitch 72 halves: conflict-free
+// ldmatrix); S = Q K^T and O = P V run on mma.sync.m16n8k16 (bf16 in, fp32 accumulate) with the whole
+// score row block kept in registers, so the softmax never leaves the register file (no materialised
+// mask, score or probability tensors; TransformerModel.py:1421-1432).
+// (The sequences are far too short for a tcgen05/TMEM pipeline to pay: a 36 x 36 x 64 problem is
+// 0.3 us of tensor work; the legacy warp-level MMA keeps all 4 SM sub-partitions busy instead.)
+#pragma once
+#include "common.cuh"
+
+namespace bofi {
+
+constexpr int kAttPitch = 72;   // halves per staged row (64 + 8 pad)
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// KT = number of 16-key tiles (Tk <= 16*KT).
+template <int KT>
+__global__ void __launch_bounds__(128)
+attention_mma_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restrict__ K, const bf16* __restrict__ V, int ldkv,
+                     bf16* __restrict__ O, int ldo, int Tq, int Tk, const int* __restrict__ vis, int vis_bs, int vis_qs,
+                     int vis_div, int kv_div, float scale, const int* live_rows) {
+  if (step_is_dead(live_rows)) return;
+  extern __shared__ __align__(16) uint8_t att_smem[];
+  constexpr int TKP = KT * 16;
+  bf16* Ks = reinterpret_cast<bf16*>(att_smem);          // [TKP][72]
+  bf16* Vs = Ks + TKP * kAttPitch;                       // [TKP][72]
+  bf16* Qs = Vs + TKP * kAttPitch;                       // [TQP][72]
+  const int TQP = (Tq + 15) & ~15;
+  const int head = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const size_t kvrow0 = (size_t)(b / kv_div) * Tk;
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  for (int idx = tid; idx < TKP * 8; idx += 128) {       // 8 x 16-byte chunks per row
+    const int j = idx >> 3, c = (idx & 7) * 8;
+    uint4 kq = zero4, vq = zero4;
+    if (j < Tk) {
+      kq = *reinterpret_cast<const uint4*>(K + (kvrow0 + j) * ldkv + head * kHeadDim + c);
+      vq = *reinterpret_cast<const uint4*>(V + (kvrow0 + j) * ldkv + head * kHeadDim + c);
+    }
+    *reinterpret_cast<uint4*>(Ks + j * kAttPitch + c) = kq;
+    *reinterpret_cast<uint4*>(Vs + j * kAttPitch + c) = vq;
+  }
+  for (int idx = tid; idx < TQP * 8; idx += 128) {
+    const int t = idx >> 3, c = (idx & 7) * 8;
+    uint4 qq = zero4;
+    if (t < Tq) qq = *reinterpret_cast<const uint4*>(Q + ((size_t)b * Tq + t) * ldq + head * kHeadDim + c);
+    *reinterpret_cast<uint4*>(Qs + t * kAttPitch + c) = qq;
+  }
+  __syncthreads();
+  const uint32_t ks_base = (uint32_t)__cvta_generic_to_shared(Ks);
+  const uint32_t vs_base = (uint32_t)__cvta_generic_to_shared(Vs);
+  const uint32_t qs_base = (uint32_t)__cvta_generic_to_shared(Qs);
+  const int g = lane >> 2, t4 = lane & 3;
+
+  for (int m0 = warp * 16; m0 < Tq; m0 += 64) {
+    // ---- Q fragments (16 x 64) ----
+    uint32_t qa[4][4];
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) {
+      const int row = m0 + (lane & 7) + ((lane >> 3) & 1) * 8, col = kt * 16 + (lane >> 4) * 8;
+      ldmatrix_x4(qa[kt], qs_base + (uint32_t)(row * kAttPitch + col) * 2u);
+    }
+    // ---- S = Q K^T ----
+    float sacc[2 * KT][4];
+#pragma unroll
+    for (int nt = 0; nt < 2 * KT; ++nt) {
+      sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
+#pragma unroll
+      for (int kp = 0; kp < 2; ++kp) {      // two k-tiles (32 dims) per ldmatrix.x4
+        uint32_t kb[4];
+        const int row = nt * 8 + (lane & 7), col = kp * 32 + (lane >> 3) * 8;
+        ldmatrix_x4(kb, ks_base + (uint32_t)(row * kAttPitch + col) * 2u);
+        mma_bf16_16816(sacc[nt], qa[2 * kp], kb[0], kb[1]);
+        mma_bf16_16816(sacc[nt], qa[2 * kp + 1], kb[2], kb[3]);
+      }
+    }
+    // ---- masked softmax over the row block (rows g and g+8 of this tile) ----
+    const int r0 = m0 + g, r1 = m0 + g + 8;
+    int nv0 = Tk, nv1 = Tk;
+    if (vis) {
+      const size_t vb = (size_t)(b / vis_div) * vis_bs;
+      nv0 = min(vis[vb + (size_t)min(r0, Tq - 1) * vis_qs], Tk);
+      nv1 = min(vis[vb + (size_t)min(r1, Tq - 1) * vis_qs], Tk);
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 2 * KT; ++nt) {
+      const int c = nt * 8 + 2 * t4;
+      sacc[nt][0] = (c < nv0) ? sacc[nt][0] * scale : -INFINITY;
+      sacc[nt][1] = (c + 1 < nv0) ? sacc[nt][1] * scale : -INFINITY;
+      sacc[nt][2] = (c < nv1) ? sacc[nt][2] * scale : -INFINITY;
+      sacc[nt][3] = (c + 1 < nv1) ? sacc[nt][3] * scale : -INFINITY;
+      mx0 = fmaxf(mx0, fmaxf(sacc[nt][0], sacc[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(sacc[nt][2], sacc[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float sub0 = (mx0 == -INFINITY) ? 0.f : mx0, sub1 = (mx1 == -INFINITY) ? 0.f : mx1;
+    float sum0 = 0.f, sum1 = 0.f;
+    uint32_t pa[KT][4];
+#pragma unroll
+    for (int nt = 0; nt < 2 * KT; ++nt) {
+      const float p0 = __expf(sacc[nt][0] - sub0), p1 = __expf(sacc[nt][1] - sub0);
+      const float p2 = __expf(sacc[nt][2] - sub1), p3 = __expf(sacc[nt][3] - sub1);
+      sum0 += p0 + p1;
+      sum1 += p2 + p3;
+      pa[nt >> 1][(nt & 1) * 2 + 0] = pack2_bf16(p0, p1);     // a0a1 / a4a5 : row g
+      pa[nt >> 1][(nt & 1) * 2 + 1] = pack2_bf16(p2, p3);     // a2a3 / a6a7 : row g+8
+    }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    // ---- O = P V ----
+    float oacc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) oacc[nt][0] = oacc[nt][1] = oacc[nt][2] = oacc[nt][3] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {      // two 8-dim n-tiles per ldmatrix.x4.trans
+        uint32_t vb4[4];
+        const int row = kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, col = np * 16 + (lane >> 4) * 8;
+        ldmatrix_x4_trans(vb4, vs_base + (uint32_t)(row * kAttPitch + col) * 2u);
+        mma_bf16_16816(oacc[2 * np], pa[kt], vb4[0], vb4[1]);
+        mma_bf16_16816(oacc[2 * np + 1], pa[kt], vb4[2], vb4[3]);
+      }
+    }
+    // all-masked row -> NaN, like softmax over -inf in the reference
+    const float nanv = __int_as_float(0x7fc00000);
+    const float inv0 = (nv0 <= 0) ? nanv : 1.f / sum0, inv1 = (nv1 <= 0) ? nanv : 1.f / sum1;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int c = head * kHeadDim + nt * 8 + 2 * t4;
+      if (r0 < Tq) *reinterpret_cast<uint32_t*>(O + ((size_t)b * Tq + r0) * ldo + c) = pack2_bf16(oacc[nt][0] * inv0, oacc[nt][1] * inv0);
+      if (r1 < Tq) *reinterpret_cast<uint32_t*>(O + ((size_t)b * Tq + r1) * ldo + c) = pack2_bf16(oacc[nt][2] * inv1, oacc[nt][3] * inv1);
+    }
+  }
+}
+
+inline size_t attention_mma_smem_bytes(int KT, int Tq) {
+  return (size_t)(2 * KT * 16 + ((Tq + 15) & ~15)) * kAttPitch * 2;
+}
+
+// Single-query attention (the [LEN] row against the image regions in the bounding step): one warp per
+// (row, head), K/V read straight from L2.  Arithmetic order mirrors attention_kernel (bit-identical to
+// the generic kernel's row in fp32).
+template <typename T>
+__global__ void __launch_bounds__(256)
+attention_row_kernel(const T* __restrict__ Q, int ldq, const T* __restrict__ K, const T* __restrict__ V, int ldkv,
+                     T* __restrict__ O, int ldo, int Tk, const int* __restrict__ vis, int vis_div, int kv_div, float scale,
+                     const int* live_rows) {
+  if (step_is_dead(live_rows)) return;
+  __shared__ float qs[8][kHeadDim];
+  __shared__ float ps[8][kMaxKeys];
+  const int b = blockIdx.x, head = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t kvrow0 = (size_t)(b / kv_div) * Tk;
+  const T* qg = Q + (size_t)b * ldq + head * kHeadDim;
+  qs[head][lane] = to_float<T>(qg[lane]);
+  qs[head][lane + 32] = to_float<T>(qg[lane + 32]);
+  __syncwarp();
+  int nvis = vis ? vis[b / vis_div] : Tk;
+  nvis = min(nvis, Tk);
+  float sc[kMaxKeys / 32];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int jj = 0; jj < kMaxKeys / 32; ++jj) {
+    const int j = jj * 32 + lane;
+    float s = -INFINITY;
+    if (j < nvis) {
+      const T* kr = K + (kvrow0 + j) * ldkv + head * kHeadDim;
+      float d = 0.f;
+#pragma unroll
+      for (int c = 0; c < kHeadDim; c += 4) {
+        const float4 kq = load4(kr + c);
+        d = fmaf(qs[head][c], kq.x, d);
+        d = fmaf(qs[head][c + 1], kq.y, d);
+        d = fmaf(qs[head][c + 2], kq.z, d);
+        d = fmaf(qs[head][c + 3], kq.w, d);
+      }
+      s = d * scale;
+    }
+    sc[jj] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int jj = 0; jj < kMaxKeys / 32; ++jj) {
+    const int j = jj * 32 + lane;
+    const float e = (j < nvis) ? expf(sc[jj] - mx) : 0.f;
+    sc[jj] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+#pragma unroll
+  for (int jj = 0; jj < kMaxKeys / 32; ++jj) {
+    const int j = jj * 32 + lane;
+    if (j < Tk) ps[head][j] = sc[jj] / sum;
+  }
+  __syncwarp();
+  float o0 = 0.f, o1 = 0.f;
+  for (int j = 0; j < nvis; ++j) {
+    const float pj = ps[head][j];
+    const T* vr = V + (kvrow0 + j) * ldkv + head * kHeadDim;
+    o0 = fmaf(pj, to_float<T>(vr[lane]), o0);
+    o1 = fmaf(pj, to_float<T>(vr[lane + 32]), o1);
+  }
+  if (nvis <= 0) o0 = o1 = __int_as_float(0x7fc00000);
+  T* og = O + (size_t)b * ldo + head * kHeadDim;
+  og[lane] = from_float<T>(o0);
+  og[lane + 32] = from_float<T>(o1);
+}
+
+}  // namespace bofi

@@ -20,6 +20,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
+#include "attention_mma.cuh"
 
 using namespace bofi;
 
@@ -90,7 +91,7 @@ struct WeightEntry { float* dev = nullptr; int64_t numel = 0; bool loaded = fals
 
 // Optional per-launch CUDA-event timing (bofi_set_profiling): one record per kernel launch.
 enum { PC_GEMM_TC = 0, PC_GEMM_SIMT, PC_ATTENTION, PC_LAYERNORM, PC_VOCAB, PC_OTHER, PC_COUNT };
-struct ProfRec { int cls; double flops, bytes; cudaEvent_t a, b; };
+struct ProfRec { int cls; double flops, bytes; cudaEvent_t a, b; int d0, d1, d2; };
 
 struct bofi_engine {
   bofi_config_t cfg;
@@ -98,6 +99,7 @@ struct bofi_engine {
   int Lb = 22, L = 20, V = 0, Vpad = 0;
   bool bf16_mode = false;
   bool use_tc = true;
+  bool attn_simt_only = false;         // BOFI_ATTN=simt: generic FFMA attention kernel everywhere
   bool finalized = false;
   std::unordered_map<std::string, WeightEntry> weights;
   std::vector<std::string> order;
@@ -109,6 +111,7 @@ struct bofi_engine {
   Norm enc_norm, dec_norm, lp_norm;
   const float *w_len2 = nullptr, *b_len2 = nullptr, *w_syn2 = nullptr, *b_syn2 = nullptr;
   DevBuf bound_in, fill_in;            // (id, position) input tables
+  DevBuf head1t;                       // [512][200] = [Length_classifier1 ; Syntactic_classifier1]^T
   DevBuf tab_y, tab_qkv;               // N_len == 1: LN + QKV of every (syn, position) bounding input row
   bool bound_fast = false;             // [LEN]-row-only bounding step (NAIC, N_len == 1)
   // workspace
@@ -134,10 +137,11 @@ struct ProfScope {
   cudaStream_t s;
   size_t idx = 0;
   bool on;
-  ProfScope(bofi_engine* e_, cudaStream_t s_, int cls, double flops, double bytes) : e(e_), s(s_), on(e_->profiling) {
+  ProfScope(bofi_engine* e_, cudaStream_t s_, int cls, double flops, double bytes, int d0 = 0, int d1 = 0, int d2 = 0)
+      : e(e_), s(s_), on(e_->profiling) {
     e->launches++;
     if (!on) return;
-    ProfRec r{cls, flops, bytes, nullptr, nullptr};
+    ProfRec r{cls, flops, bytes, nullptr, nullptr, d0, d1, d2};
     cudaEventCreate(&r.a);
     cudaEventCreate(&r.b);
     cudaEventRecord(r.a, s);
@@ -226,7 +230,8 @@ static int linear(bofi_engine* e, cudaStream_t s, const T* A, int lda, const Lin
   cudaError_t err;
   const bool tcpath = std::is_same<T, bf16>::value && e->use_tc;
   ProfScope prof(e, s, tcpath ? PC_GEMM_TC : PC_GEMM_SIMT, 2.0 * M * l.N * l.K,
-                 (double)sizeof(T) * ((double)M * l.K + (double)l.N * l.K) + (double)sizeof(TOut) * M * l.N + (resid ? 4.0 * M * l.N : 0.0));
+                 (double)sizeof(T) * ((double)M * l.K + (double)l.N * l.K) + (double)sizeof(TOut) * M * l.N + (resid ? 4.0 * M * l.N : 0.0),
+                 M, l.N, l.K);
   if constexpr (std::is_same<T, bf16>::value) {
     if (e->use_tc)
       err = tc::gemm_tc<TOut>(s, A, lda, l.w16, l.K, l.b, resid, ldr, out, ldc, M, l.N, l.K, relu, live);
@@ -243,10 +248,24 @@ template <typename TOut>
 static int layernorm(bofi_engine* e, cudaStream_t s, const float* x, size_t in_stride, const Norm& n, TOut* out,
                      size_t out_stride, int rows, float* f32_copy, const int* live) {
   if (rows <= 0) return BOFI_OK;
-  ProfScope prof(e, s, PC_LAYERNORM, 8.0 * rows * kD, (double)rows * kD * (4 + sizeof(TOut) + (f32_copy ? 4 : 0)));
+  ProfScope prof(e, s, PC_LAYERNORM, 8.0 * rows * kD, (double)rows * kD * (4 + sizeof(TOut) + (f32_copy ? 4 : 0)), rows);
   layernorm_kernel<TOut><<<ceil_div(rows, 8), 256, 0, s>>>(x, in_stride, n.a, n.b, out, out_stride, rows, f32_copy, live);
   CU_TRY(cudaGetLastError());
   return BOFI_OK;
+}
+
+template <int KT>
+static cudaError_t launch_attention_mma(cudaStream_t s, dim3 grid, size_t smem, const bf16* Q, int ldq, const bf16* K, const bf16* V,
+                                        int ldkv, bf16* O, int ldo, int Tq, int Tk, const int* vis, int vis_bs, int vis_qs,
+                                        int vis_div, int kv_div, float scale, const int* live) {
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t err = cudaFuncSetAttribute(attention_mma_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    configured = smem;
+  }
+  attention_mma_kernel<KT><<<grid, 128, smem, s>>>(Q, ldq, K, V, ldkv, O, ldo, Tq, Tk, vis, vis_bs, vis_qs, vis_div, kv_div, scale, live);
+  return cudaGetLastError();
 }
 
 template <typename T>
@@ -254,7 +273,31 @@ static int attention(bofi_engine* e, cudaStream_t s, const T* Q, int ldq, const 
                      int nb, int Tq, int Tk, const int* vis, int vis_bs, int vis_qs, int vis_div, int kv_div,
                      const int* live) {
   if (nb <= 0) return BOFI_OK;
-  if (Tk > kMaxKeys) return fail(BOFI_ERR_INVALID, "attention over %d keys (max %d)", Tk, kMaxKeys);
+  if (Tk > kMaxKeys || Tq > kMaxKeys) return fail(BOFI_ERR_INVALID, "attention over %d x %d (max %d)", Tq, Tk, kMaxKeys);
+  const float scale = 1.0f / sqrtf((float)kHeadDim);
+  ProfScope prof(e, s, PC_ATTENTION, 4.0 * nb * Tq * Tk * kD, (double)sizeof(T) * kD * ((double)nb * Tq * 2 + 2.0 * (nb / kv_div) * Tk),
+                 nb, Tq, Tk);
+  if (Tq == 1 && !e->attn_simt_only) {
+    attention_row_kernel<T><<<nb, 256, 0, s>>>(Q, ldq, K, V, ldkv, O, ldo, Tk, vis, vis_div, kv_div, scale, live);
+    CU_TRY(cudaGetLastError());
+    return BOFI_OK;
+  }
+  if constexpr (std::is_same<T, bf16>::value) {
+    if (!e->attn_simt_only) {
+      const int KT = (Tk + 15) / 16;
+      const size_t smem = attention_mma_smem_bytes(KT, Tq);
+      dim3 grid(e->cfg.heads, nb);
+      cudaError_t err = cudaErrorInvalidValue;
+#define BOFI_ATT_CASE(n) case n: err = launch_attention_mma<n>(s, grid, smem, Q, ldq, K, V, ldkv, O, ldo, Tq, Tk, vis, vis_bs, vis_qs, vis_div, kv_div, scale, live); break;
+      switch (KT) {
+        BOFI_ATT_CASE(1) BOFI_ATT_CASE(2) BOFI_ATT_CASE(3) BOFI_ATT_CASE(4)
+        BOFI_ATT_CASE(5) BOFI_ATT_CASE(6) BOFI_ATT_CASE(7) BOFI_ATT_CASE(8)
+      }
+#undef BOFI_ATT_CASE
+      if (err != cudaSuccess) return fail(BOFI_ERR_CUDA, "attention_mma: %s", cudaGetErrorString(err));
+      return BOFI_OK;
+    }
+  }
   const size_t smem = attention_smem_bytes(Tk);
   static size_t configured_f = 0, configured_h = 0;
   size_t& configured = std::is_same<T, float>::value ? configured_f : configured_h;
@@ -263,9 +306,7 @@ static int attention(bofi_engine* e, cudaStream_t s, const T* Q, int ldq, const 
     configured = attention_smem_bytes(kMaxKeys);
   }
   dim3 grid(e->cfg.heads, nb);
-  ProfScope prof(e, s, PC_ATTENTION, 4.0 * nb * Tq * Tk * kD, (double)sizeof(T) * kD * ((double)nb * Tq * 2 + 2.0 * (nb / kv_div) * Tk));
-  attention_kernel<T><<<grid, 128, smem, s>>>(Q, ldq, K, V, ldkv, O, ldo, Tq, Tk, vis, vis_bs, vis_qs, vis_div, kv_div,
-                                              1.0f / sqrtf((float)kHeadDim), live);
+  attention_kernel<T><<<grid, 128, smem, s>>>(Q, ldq, K, V, ldkv, O, ldo, Tq, Tk, vis, vis_bs, vis_qs, vis_div, kv_div, scale, live);
   CU_TRY(cudaGetLastError());
   return BOFI_OK;
 }
@@ -478,6 +519,17 @@ static int project_memory_kv(bofi_engine* e, cudaStream_t s, const Lin& kv, DevB
   return linear<T, T>(e, s, e->memT.as<T>(), kD, kv, nullptr, 0, out.as<T>(), 2 * kD, e->B * e->R, 0, nullptr);
 }
 
+// Final LayerNorm of the [LEN] row + both classifier heads + box rule, one fused launch per step.
+static int head_step(bofi_engine* e, cudaStream_t s, const float* x, size_t x_stride, int rows, int step_col, int step_no, int saic) {
+  const size_t smem = sizeof(float) * (kHeadRows * kD + kHeadRows * 200 + kHeadRows * 32);
+  ProfScope prof(e, s, PC_OTHER, 2.0 * rows * 200 * kD, 0.0, rows, 200, kD);
+  bound_head_kernel<<<ceil_div(rows, kHeadRows), 256, smem, s>>>(x, x_stride, e->lp_norm.a, e->lp_norm.b, e->head1t.as<float>(), e->head1.b, 100,
+                                                              e->w_len2, e->b_len2, e->w_syn2, e->b_syn2, 20, 10, e->st, rows, e->Lb, e->L,
+                                                              step_col, step_no, 4, 6, saic);
+  CU_TRY(cudaGetLastError());
+  return BOFI_OK;
+}
+
 // One bounding step of core_NAIC / core_SAIC: bounding head on the current slots, then the box rule.
 template <typename T>
 static int bounding_step(bofi_engine* e, cudaStream_t s, int rows, int sn, int step_col, int saic) {
@@ -510,21 +562,7 @@ static int bounding_step(bofi_engine* e, cudaStream_t s, int rows, int sn, int s
     for (int l = 0; l < c.n_len; ++l)
       RC_TRY(run_layer<T>(e, s, e->lp[l], x, rows, Lb, e->st.vis, Lb, 1, e->kv[l].as<T>(), e->R, mem_len, sn, live));
   }
-  // norm -> [LEN] row -> classifier1 of both heads (always fp32: the heads are gain sensitive)
-  RC_TRY(layernorm<float>(e, s, x, (size_t)Tb * kD, e->lp_norm, e->hrow.as<float>(), kD, rows, nullptr, live));
-  {
-    ProfScope prof(e, s, PC_GEMM_SIMT, 2.0 * rows * 200 * kD, 4.0 * (rows * (kD + 200.0) + 200.0 * kD));
-    cudaError_t err = gemm_simt<float, float>(s, e->hrow.as<float>(), kD, e->head1.w32, kD, e->head1.b, nullptr, 0,
-                                              e->hid.as<float>(), 200, rows, 200, kD, 1, live);
-    if (err != cudaSuccess) return fail(BOFI_ERR_CUDA, "head gemm: %s", cudaGetErrorString(err));
-  }
-  const size_t smem = sizeof(float) * (30 * 100 + 4 * 200 + 4 * 32);
-  {
-    ProfScope prof(e, s, PC_OTHER, 0.0, 0.0);
-    bound_head_kernel<<<ceil_div(rows, 4), 128, smem, s>>>(e->hid.as<float>(), 100, e->w_len2, e->b_len2, e->w_syn2, e->b_syn2,
-                                                         20, 10, e->st, rows, Lb, e->L, step_col, saic ? step_col : step_col + 1, 4, 6, saic);
-  }
-  CU_TRY(cudaGetLastError());
+  RC_TRY(head_step(e, s, x, (size_t)Tb * kD, rows, step_col, saic ? step_col : step_col + 1, saic));
   return BOFI_OK;
 }
 
@@ -558,20 +596,7 @@ static int bounding_step_fast(bofi_engine* e, cudaStream_t s, int rows, int sn, 
   RC_TRY(layernorm<T>(e, s, x, kD, ly.ln[2], y, kD, rows, nullptr, live));
   RC_TRY((linear<T, T>(e, s, y, kD, ly.w1, nullptr, 0, ffh, c.d_ff, rows, 1, live)));
   RC_TRY((linear<T, float>(e, s, ffh, c.d_ff, ly.w2, x, kD, x, kD, rows, 0, live)));
-  RC_TRY(layernorm<float>(e, s, x, kD, e->lp_norm, e->hrow.as<float>(), kD, rows, nullptr, live));
-  {
-    ProfScope prof(e, s, PC_GEMM_SIMT, 2.0 * rows * 200 * kD, 4.0 * (rows * (kD + 200.0) + 200.0 * kD));
-    cudaError_t err = gemm_simt<float, float>(s, e->hrow.as<float>(), kD, e->head1.w32, kD, e->head1.b, nullptr, 0,
-                                              e->hid.as<float>(), 200, rows, 200, kD, 1, live);
-    if (err != cudaSuccess) return fail(BOFI_ERR_CUDA, "head gemm: %s", cudaGetErrorString(err));
-  }
-  const size_t smem = sizeof(float) * (30 * 100 + 4 * 200 + 4 * 32);
-  {
-    ProfScope prof(e, s, PC_OTHER, 0.0, 0.0);
-    bound_head_kernel<<<ceil_div(rows, 4), 128, smem, s>>>(e->hid.as<float>(), 100, e->w_len2, e->b_len2, e->w_syn2, e->b_syn2,
-                                                           20, 10, e->st, rows, Lb, e->L, step_col, step_col + 1, 4, 6, 0);
-  }
-  CU_TRY(cudaGetLastError());
+  RC_TRY(head_step(e, s, x, kD, rows, step_col, step_col + 1, 0));
   return BOFI_OK;
 }
 
@@ -677,6 +702,8 @@ int bofi_create(const bofi_config_t* cfg, int device, bofi_handle_t* out) {
   e->bf16_mode = (cfg->precision == BOFI_PRECISION_BF16);
   const char* g = getenv("BOFI_GEMM");
   e->use_tc = !(g && strcmp(g, "simt") == 0);
+  const char* ga = getenv("BOFI_ATTN");
+  e->attn_simt_only = (ga && strcmp(ga, "simt") == 0);
   build_spec(e);
   *out = e;
   return BOFI_OK;
@@ -690,7 +717,7 @@ int bofi_destroy(bofi_handle_t e) {
   for (DevBuf& b : e->packed) b.release();
   for (DevBuf& b : e->kv) b.release();
   DevBuf* all[] = {&e->bound_in, &e->fill_in, &e->attT, &e->x, &e->y, &e->qkv, &e->ao, &e->q, &e->ffh, &e->memT, &e->attlen,
-                   &e->tab_y, &e->tab_qkv, &e->hrow, &e->hid, &e->logits, &e->state_i32, &e->tok, &e->h_in, &e->h_len, &e->h_seq, &e->h_logp,
+                   &e->head1t, &e->tab_y, &e->tab_qkv, &e->hrow, &e->hid, &e->logits, &e->state_i32, &e->tok, &e->h_in, &e->h_len, &e->h_seq, &e->h_logp,
                    &e->h_pnum, &e->h_plen, &e->h_psyn, &e->unit_a, &e->unit_w, &e->unit_o};
   for (DevBuf* b : all) b->release();
   delete e;
@@ -756,6 +783,9 @@ int bofi_finalize_weights(bofi_handle_t e, void* stream) {
     e->bf16_mode = keep;
     RC_TRY(rc);
   }
+  RC_TRY(e->head1t.reserve((size_t)200 * kD * 4));
+  transpose_kernel<<<dim3(ceil_div(kD, 32), ceil_div(200, 32)), dim3(32, 8), 0, s>>>(e->head1.w32, e->head1t.as<float>(), 200, kD);
+  CU_TRY(cudaGetLastError());
   e->w_len2 = W(e, lp + ".Length_classifier2.weight");
   e->b_len2 = W(e, lp + ".Length_classifier2.bias");
   e->w_syn2 = W(e, lp + ".Syntactic_classifier2.weight");
@@ -866,14 +896,19 @@ int bofi_get_profile(bofi_handle_t e, void* stream, int32_t* launches, double* m
   CU_TRY(cudaSetDevice(e->device));
   CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
   for (int c = 0; c < PC_COUNT; ++c) { launches[c] = 0; ms[c] = flops[c] = bytes[c] = 0.0; }
+  const char* dump = getenv("BOFI_PROFILE_DUMP");
+  FILE* df = dump ? fopen(dump, "w") : nullptr;
+  if (df) fprintf(df, "class,d0,d1,d2,ms,gflop\n");
   for (ProfRec& r : e->recs) {
     float t = 0.f;
     CU_TRY(cudaEventElapsedTime(&t, r.a, r.b));
+    if (df) fprintf(df, "%d,%d,%d,%d,%.5f,%.4f\n", r.cls, r.d0, r.d1, r.d2, t, r.flops * 1e-9);
     launches[r.cls] += 1;
     ms[r.cls] += t;
     flops[r.cls] += r.flops;
     bytes[r.cls] += r.bytes;
   }
+  if (df) fclose(df);
   return BOFI_OK;
 }
 
@@ -917,7 +952,24 @@ int bofi_attention_f32(bofi_handle_t e, void* stream, const float* q, const floa
                        float* out, int32_t B, int32_t Tq, int32_t Tk) {
   if (!e || !q || !k || !v || !out) return fail(BOFI_ERR_INVALID, "null argument");
   CU_TRY(cudaSetDevice(e->device));
-  return attention<float>(e, (cudaStream_t)stream, q, kD, k, v, kD, out, kD, B, Tq, Tk, vis, Tq, 1, 1, 1, nullptr);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!e->bf16_mode)
+    return attention<float>(e, s, q, kD, k, v, kD, out, kD, B, Tq, Tk, vis, Tq, 1, 1, 1, nullptr);
+  // bf16 engines run their own attention kernels (mma.sync / single-query row kernel) on bf16 copies
+  const size_t nq = (size_t)B * Tq * kD, nk = (size_t)B * Tk * kD;
+  RC_TRY(e->unit_a.reserve((nq + 2 * nk) * 2));
+  RC_TRY(e->unit_o.reserve(nq * 2));
+  bf16* qb = e->unit_a.as<bf16>();
+  bf16* kb = qb + nq;
+  bf16* vb = kb + nk;
+  cast_kernel<bf16><<<ceil_div(nq / 4, 256), 256, 0, s>>>(q, qb, nq / 4);
+  cast_kernel<bf16><<<ceil_div(nk / 4, 256), 256, 0, s>>>(k, kb, nk / 4);
+  cast_kernel<bf16><<<ceil_div(nk / 4, 256), 256, 0, s>>>(v, vb, nk / 4);
+  CU_TRY(cudaGetLastError());
+  RC_TRY(attention<bf16>(e, s, qb, kD, kb, vb, kD, e->unit_o.as<bf16>(), kD, B, Tq, Tk, vis, Tq, 1, 1, 1, nullptr));
+  widen_kernel<<<ceil_div(nq / 4, 256), 256, 0, s>>>(e->unit_o.as<bf16>(), out, nq / 4);
+  CU_TRY(cudaGetLastError());
+  return BOFI_OK;
 }
 
 }  // extern "C"

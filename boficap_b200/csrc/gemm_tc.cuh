@@ -4,8 +4,9 @@
 //     (cp.async.bulk.tensor.2d, 128-byte swizzle) into a multi-stage shared-memory ring;
 //   * one elected thread issues tcgen05.mma (cta_group::1, kind::f16, M=128 x N=BN x K=16) with the
 //     accumulator tile living in tensor memory (BN fp32 columns x 128 lanes);
-//   * four epilogue warps read the accumulator back with tcgen05.ld (32x32b: one row per thread) and
-//     fuse bias, ReLU, residual add and the fp32 / bf16 down-conversion before the global stores.
+//   * four epilogue warps read the accumulator back with tcgen05.ld (32x32b: one row per thread), fuse bias,
+//     ReLU, residual add and the fp32 / bf16 down-conversion, stage 32 x 128-byte sub-tiles in swizzled
+//     shared memory and write them with TMA stores (cp.async.bulk.tensor, M / N tails clipped in hardware).
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2..5 = epilogue (TMEM lane quadrant = warp % 4).
@@ -102,9 +103,25 @@ struct SmemLayout {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOffset = STAGES * kStageBytes;
+  static constexpr int kOutOffset = STAGES * kStageBytes;          // epilogue staging: 4 warps x 2 x 4 KB
+  static constexpr int kOutBytes = 4 * 2 * 4096;
+  static constexpr int kBarOffset = kOutOffset + kOutBytes;
   static constexpr int kTotal = kBarOffset + 256 + 1024;   // barriers + alignment slack
 };
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(tmap), "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -116,7 +133,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 template <int BN, int STAGES, typename TOut>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const float* __restrict__ bias, const float* residual, int ldr, TOut* C, int ldc,
+               const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, const float* residual, int ldr,
                int M, int N, int K, int relu, const int* live_rows) {
   if (step_is_dead(live_rows)) return;
   using L = SmemLayout<BN, STAGES>;
@@ -137,6 +154,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -206,57 +224,112 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
+    // Epilogue: TMEM -> registers (one accumulator row per thread) -> bias / ReLU / residual -> swizzled smem
+    // staging tile (32 rows x 128 B) -> TMA store.  Full-line coalesced writes, M / N tails clipped by the
+    // tensor map; two staging tiles per warp so the store of chunk i overlaps the math of chunk i+1.
+    constexpr int CC = 128 / (int)sizeof(TOut);      // output columns per 128-byte staging row
     const int quad = warp & 3;                       // TMEM lanes [32*quad, 32*quad+32)
-    int t = 0;
+    const uint32_t stage0 = smem_u32(smem + L::kOutOffset + quad * 8192);
+    int t = 0, nstore = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
       const int m0 = (tile / tiles_n) * kBM, n0 = (tile % tiles_n) * BN;
       const int as = t & 1;
       const uint32_t aph = (t >> 1) & 1;
       const int row = m0 + quad * 32 + lane;
-      mbar_wait(smem_u32(&tmem_full_bar[as]), aph);
-      tcgen05_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int n = n0 + c * 32;
-        if (n >= N) break;                            // warp-uniform
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + c * 32), r);
-        if (row < M) {
-          float v[32];
-          TOut* dst = C + (size_t)row * ldc + n;
-          if (n + 32 <= N) {
+      const bool row_ok = row < M;
+      constexpr int NC = BN / CC;
+      // The residual does not depend on the accumulator: fetch the first two chunks of this thread's row
+      // before waiting for the MMAs, and keep two chunks in flight while the tile drains.
+      constexpr int RV = (sizeof(TOut) == 4) ? 8 : 1;           // residual only exists on the fp32-output path
+      float4 res[3][RV];
+      auto fetch_res = [&](float4 (&dst)[RV], int c) {
+        if constexpr (sizeof(TOut) == 4) {
+          const int n = n0 + c * CC;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 x = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                     __uint_as_float(r[j + 3]));
-              if (bias) {
-                const float4 bb = *reinterpret_cast<const float4*>(bias + n + j);
-                x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
-              }
-              if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-              if (residual) {
-                const float4 rr = *reinterpret_cast<const float4*>(residual + (size_t)row * ldr + n + j);
-                x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
-              }
-              v[j] = x.x; v[j + 1] = x.y; v[j + 2] = x.z; v[j + 3] = x.w;
-            }
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) store4(dst + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-          } else {
-            for (int j = 0; j < 32 && n + j < N; ++j) {
-              float x = __uint_as_float(r[j]);
-              if (bias) x += bias[n + j];
-              if (relu) x = fmaxf(x, 0.f);
-              if (residual) x += residual[(size_t)row * ldr + n + j];
-              dst[j] = from_float<TOut>(x);
-            }
+          for (int j = 0; j < 8; ++j) {
+            dst[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (residual && row_ok && c < NC && n + 4 * j + 4 <= N)
+              dst[j] = *reinterpret_cast<const float4*>(residual + (size_t)row * ldr + n + 4 * j);
           }
         }
+      };
+      fetch_res(res[0], 0);
+      fetch_res(res[1], 1);
+      mbar_wait(smem_u32(&tmem_full_bar[as]), aph);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const int n = n0 + c * CC;
+        if (n >= N) break;                            // warp-uniform
+        fetch_res(res[(c + 2) % 3], c + 2);
+        uint32_t r[CC];
+        {
+          uint32_t(&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
+          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + c * CC), r0);
+          if constexpr (CC == 64) {
+            uint32_t(&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
+            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + c * CC + 32), r1);
+          }
+        }
+        const bool full = (n + CC <= N);
+#pragma unroll
+        for (int j = 0; j < CC; j += 4) {
+          float4 x = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                 __uint_as_float(r[j + 3]));
+          if (full) {
+            if (bias) {
+              const float4 bb = *reinterpret_cast<const float4*>(bias + n + j);
+              x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
+            }
+            if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+            if constexpr (sizeof(TOut) == 4) {
+              const float4 rr = res[c % 3][j / 4];    // zero when there is no residual
+              x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
+            }
+          } else {
+            float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (n + j + q < N) {
+                if (bias) xs[q] += bias[n + j + q];
+                if (relu) xs[q] = fmaxf(xs[q], 0.f);
+                if (residual && row_ok) xs[q] += residual[(size_t)row * ldr + n + j + q];
+              }
+            }
+            x = make_float4(xs[0], xs[1], xs[2], xs[3]);
+          }
+          r[j] = __float_as_uint(x.x); r[j + 1] = __float_as_uint(x.y);
+          r[j + 2] = __float_as_uint(x.z); r[j + 3] = __float_as_uint(x.w);
+        }
+        // the staging tile used two stores ago must have been read out by the TMA engine
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        const uint32_t sbuf = stage0 + (uint32_t)(nstore & 1) * 4096u;
+        const uint32_t srow = sbuf + (uint32_t)lane * 128u;
+        if constexpr (CC == 32) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            st_shared_v4(srow + (uint32_t)((j ^ (lane & 7)) * 16), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            st_shared_v4(srow + (uint32_t)((j ^ (lane & 7)) * 16),
+                         pack_bf16(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1])),
+                         pack_bf16(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])),
+                         pack_bf16(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])),
+                         pack_bf16(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) tma_store_2d(&tmC, sbuf, n, m0 + quad * 32);
+        ++nstore;
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[as]));
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncwarp();
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -283,15 +356,16 @@ inline EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 tensor [rows, cols] with row pitch ld (elements); box = 64 cols x box_rows, 128 B swizzle.
-inline bool make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+// 2-D tensor [rows, cols] of 2-byte (bf16) or 4-byte (fp32) elements with row pitch ld (elements);
+// box = 128 bytes of columns x box_rows, 128 B swizzle.
+inline bool make_tmap(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, int elt) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)kBK, box_rows};
+  cuuint64_t gstride[1] = {ld * (uint64_t)elt};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / elt), box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+  CUresult r = fn(tm, elt == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
@@ -309,8 +383,8 @@ inline int num_sms() {
 }
 
 template <int BN, int STAGES, typename TOut>
-inline cudaError_t launch(cudaStream_t s, const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias,
-                          const float* residual, int ldr, TOut* C, int ldc, int M, int N, int K, int relu,
+inline cudaError_t launch(cudaStream_t s, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                          const float* bias, const float* residual, int ldr, int M, int N, int K, int relu,
                           const int* live_rows) {
   using L = SmemLayout<BN, STAGES>;
   static bool configured = false;
@@ -321,33 +395,35 @@ inline cudaError_t launch(cudaStream_t s, const CUtensorMap& tmA, const CUtensor
   }
   const int ntiles = ((M + kBM - 1) / kBM) * ((N + BN - 1) / BN);
   const int grid = ntiles < num_sms() ? ntiles : num_sms();
-  gemm_tc_kernel<BN, STAGES, TOut><<<grid, kThreads, L::kTotal, s>>>(tmA, tmB, bias, residual, ldr, C, ldc, M, N, K, relu, live_rows);
+  gemm_tc_kernel<BN, STAGES, TOut><<<grid, kThreads, L::kTotal, s>>>(tmA, tmB, tmC, bias, residual, ldr, M, N, K, relu, live_rows);
   return cudaGetLastError();
 }
 
 // Tensor maps are pure functions of (pointer, shape, pitch, box): cache them (weights and workspace
 // buffers are stable across steps), so steady-state launches make no driver call.
 struct TmapKey {
-  const void* p; uint64_t rows, cols, ld; uint32_t box;
-  bool operator==(const TmapKey& o) const { return p == o.p && rows == o.rows && cols == o.cols && ld == o.ld && box == o.box; }
+  const void* p; uint64_t rows, cols, ld; uint32_t box; int elt;
+  bool operator==(const TmapKey& o) const {
+    return p == o.p && rows == o.rows && cols == o.cols && ld == o.ld && box == o.box && elt == o.elt;
+  }
 };
 struct TmapHash {
   size_t operator()(const TmapKey& k) const {
     size_t h = reinterpret_cast<size_t>(k.p);
     h ^= k.rows * 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
     h ^= k.cols * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2);
-    h ^= (k.ld * 31 + k.box) + (h << 6) + (h >> 2);
+    h ^= (k.ld * 31 + k.box * 7 + (uint64_t)k.elt) + (h << 6) + (h >> 2);
     return h;
   }
 };
-inline const CUtensorMap* cached_tmap(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+inline const CUtensorMap* cached_tmap(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, int elt = 2) {
   static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapHash> cache;
-  TmapKey key{ptr, rows, cols, ld, box_rows};
+  TmapKey key{ptr, rows, cols, ld, box_rows, elt};
   auto it = cache.find(key);
   if (it != cache.end()) return &it->second;
   if (cache.size() > 8192) cache.clear();
   CUtensorMap tm;
-  if (!make_tmap_bf16(&tm, ptr, rows, cols, ld, box_rows)) return nullptr;
+  if (!make_tmap(&tm, ptr, rows, cols, ld, box_rows, elt)) return nullptr;
   return &cache.emplace(key, tm).first->second;
 }
 
@@ -363,9 +439,10 @@ inline cudaError_t gemm_tc(cudaStream_t s, const bf16* A, int lda, const bf16* W
   const bool wide = tiles256 >= num_sms() / 2;      // small problems: narrower tiles spread over more SMs
   const CUtensorMap* tmA = cached_tmap(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBM);
   const CUtensorMap* tmB = cached_tmap(W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, wide ? 256 : 64);
-  if (!tmA || !tmB) return cudaErrorInvalidValue;
-  if (wide) return launch<256, 4, TOut>(s, *tmA, *tmB, bias, residual, ldr, C, ldc, M, N, K, relu, live_rows);
-  return launch<64, 6, TOut>(s, *tmA, *tmB, bias, residual, ldr, C, ldc, M, N, K, relu, live_rows);
+  const CUtensorMap* tmC = cached_tmap(C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, (int)sizeof(TOut));
+  if (!tmA || !tmB || !tmC) return cudaErrorInvalidValue;
+  if (wide) return launch<256, 4, TOut>(s, *tmA, *tmB, *tmC, bias, residual, ldr, M, N, K, relu, live_rows);
+  return launch<64, 6, TOut>(s, *tmA, *tmB, *tmC, bias, residual, ldr, M, N, K, relu, live_rows);
 }
 
 }  // namespace tc

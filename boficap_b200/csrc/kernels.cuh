@@ -198,6 +198,28 @@ __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ in,
   for (; i < n4; i += stride) store4(out + i * 4, load4(in + i * 4));
 }
 
+// bf16 -> fp32 (unit entry points only)
+__global__ void __launch_bounds__(256) widen_kernel(const bf16* __restrict__ in, float* __restrict__ out, size_t n4) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) store4(out + i * 4, load4(in + i * 4));
+}
+
+// out[c][r] = in[r][c]  (in: [rows][cols])
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? in[(size_t)r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) out[(size_t)c * rows + r] = tile[threadIdx.x][i];
+  }
+}
+
 // pack_wrapper (AttModel.py:46-51): rows of padded regions come back as zeros.
 __global__ void __launch_bounds__(256)
 zero_padded_rows_kernel(float* __restrict__ x, const int* __restrict__ att_len, int B, int R) {
@@ -307,37 +329,94 @@ __global__ void init_state_kernel(DecodeState st, int rows, int Lb, int L, int l
   st.phrase_num[b] = 0;
 }
 
-// Bounding heads + box rule for one step, one warp per row.
-//   hid [rows, 2*Hh] = relu(classifier1(h)) of both heads (length first), computed by the GEMM before;
-//   logits -> log_softmax -> first-max argmax (TransformerModel.py:376-383);
-//   EOS / clip / write rule (:1843-1867 NAIC, :1910-1926 SAIC).
+// Bounding heads + box rule for one step, fused: final LayerNorm of the [LEN] row (length_predictor.norm,
+// TransformerModel.py:374-375), classifier1 + ReLU of both heads (:376,:378; w1t = [512][2*Hh] = the two
+// classifier1 weights concatenated and transposed), classifier2, log_softmax, first-max argmax (:377-382),
+// then the EOS / clip / write rule (:1843-1867 NAIC, :1910-1926 SAIC).  8 rows per CTA, one warp per row.
+// Always fp32: the calibrated heads amplify their input.
 // NAIC (`saic == 0`) also writes the syn id into ext[last:last+len] and advances `last`/`vis`;
 // SAIC defers that to saic_commit_kernel (the slots are filled with generated words).
-__global__ void __launch_bounds__(128)
-bound_head_kernel(const float* __restrict__ hid, int Hh, const float* __restrict__ w_len, const float* __restrict__ b_len,
+constexpr int kHeadRows = 8;
+__global__ void __launch_bounds__(256)
+bound_head_kernel(const float* __restrict__ x, size_t x_stride, const float* __restrict__ ln_a, const float* __restrict__ ln_b,
+                  const float* __restrict__ w1t, const float* __restrict__ b1, int Hh,
+                  const float* __restrict__ w_len, const float* __restrict__ b_len,
                   const float* __restrict__ w_syn, const float* __restrict__ b_syn, int n_len, int n_syn,
                   DecodeState st, int rows, int Lb, int L, int step_col, int step_no, int syn_lo, int syn_hi, int saic) {
   if (st.counters[0] == 0) return;
   extern __shared__ float hsm[];
-  float* wl = hsm;                      // [n_len][Hh]
-  float* ws = wl + n_len * Hh;          // [n_syn][Hh]
-  float* hrow = ws + n_syn * Hh;        // [4][2*Hh]
-  float* lg = hrow + 4 * 2 * Hh;        // [4][32]
-  for (int i = threadIdx.x; i < n_len * Hh; i += blockDim.x) wl[i] = w_len[i];
-  for (int i = threadIdx.x; i < n_syn * Hh; i += blockDim.x) ws[i] = w_syn[i];
+  float* h = hsm;                               // [8][512]  normalised [LEN] rows
+  float* hid = h + kHeadRows * kD;              // [8][2*Hh]
+  float* lg = hid + kHeadRows * 2 * Hh;         // [8][32]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * 4 + warp;
-  if (b < rows)
-    for (int i = lane; i < 2 * Hh; i += 32) hrow[warp * 2 * Hh + i] = hid[(size_t)b * 2 * Hh + i];
+  const int b0 = blockIdx.x * kHeadRows;
+  {   // LayerNorm, same arithmetic as layernorm_kernel
+    const int b = b0 + warp;
+    if (b < rows) {
+      const float* xr = x + (size_t)b * x_stride;
+      float4 v[4];
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        v[i] = load4(xr + (i * 32 + lane) * 4);
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+      const float mean = warp_sum(s) * (1.0f / kD);
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+        ss += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+      }
+      const float denom = sqrtf(warp_sum(ss) * (1.0f / (kD - 1))) + 1e-6f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        const float4 a = load4(ln_a + c), bb = load4(ln_b + c);
+        float4 o;
+        o.x = a.x * v[i].x / denom + bb.x;
+        o.y = a.y * v[i].y / denom + bb.y;
+        o.z = a.z * v[i].z / denom + bb.z;
+        o.w = a.w * v[i].w / denom + bb.w;
+        *reinterpret_cast<float4*>(h + warp * kD + c) = o;
+      }
+    } else {
+      for (int c = lane; c < kD; c += 32) h[warp * kD + c] = 0.f;
+    }
+  }
   __syncthreads();
+  // classifier1 of both heads: thread o owns output column o for all 8 rows; w1t rows are contiguous in o
+  const int o = threadIdx.x;
+  if (o < 2 * Hh) {
+    float acc[kHeadRows];
+#pragma unroll
+    for (int r = 0; r < kHeadRows; ++r) acc[r] = 0.f;
+    for (int k = 0; k < kD; k += 4) {
+      const float w0 = w1t[(size_t)(k + 0) * 2 * Hh + o], w1 = w1t[(size_t)(k + 1) * 2 * Hh + o];
+      const float w2 = w1t[(size_t)(k + 2) * 2 * Hh + o], w3 = w1t[(size_t)(k + 3) * 2 * Hh + o];
+#pragma unroll
+      for (int r = 0; r < kHeadRows; ++r) {
+        const float4 hv = *reinterpret_cast<const float4*>(h + r * kD + k);
+        acc[r] = fmaf(hv.x, w0, acc[r]);
+        acc[r] = fmaf(hv.y, w1, acc[r]);
+        acc[r] = fmaf(hv.z, w2, acc[r]);
+        acc[r] = fmaf(hv.w, w3, acc[r]);
+      }
+    }
+    const float bias = b1[o];
+#pragma unroll
+    for (int r = 0; r < kHeadRows; ++r) hid[r * 2 * Hh + o] = fmaxf(acc[r] + bias, 0.f);
+  }
+  __syncthreads();
+  const int b = b0 + warp;
   if (b >= rows) return;
-  const float* hr = hrow + warp * 2 * Hh;
+  const float* hr = hid + warp * 2 * Hh;
   if (lane < n_len + n_syn) {
     const bool is_len = lane < n_len;
-    const float* w = is_len ? wl + lane * Hh : ws + (lane - n_len) * Hh;
-    const float* h = is_len ? hr : hr + Hh;
+    const float* w = is_len ? w_len + lane * Hh : w_syn + (lane - n_len) * Hh;
+    const float* hh = is_len ? hr : hr + Hh;
     float acc = 0.f;
-    for (int c = 0; c < Hh; ++c) acc = fmaf(h[c], w[c], acc);
+    for (int c = 0; c < Hh; ++c) acc = fmaf(hh[c], w[c], acc);
     lg[warp * 32 + lane] = acc + (is_len ? b_len[lane] : b_syn[lane - n_len]);
   }
   __syncwarp();

@@ -97,3 +97,49 @@ def test_attention_prefix_masks_and_nan_rows(engines):
     ok = ~torch.isnan(ref)
     assert (torch.isnan(out) == torch.isnan(ref)).all()
     assert (out[ok] - ref[ok]).abs().max().item() < 2e-5
+
+
+def _attention_reference(q, k, v, vis, h=8):
+    B, Tq, _ = q.shape
+    Tk = k.shape[1]
+    qh = q.view(B, Tq, h, 64).transpose(1, 2)
+    kh = k.view(B, Tk, h, 64).transpose(1, 2)
+    vh = v.view(B, Tk, h, 64).transpose(1, 2)
+    sc = qh @ kh.transpose(-2, -1) / 8.0
+    mask = torch.arange(Tk)[None, None, :] < vis[:, :, None]
+    sc = sc.masked_fill(~mask[:, None], float("-inf"))
+    return (torch.softmax(sc, -1) @ vh).transpose(1, 2).reshape(B, Tq, 512)
+
+
+@pytest.mark.parametrize("Tq,Tk", [(36, 36), (20, 20), (22, 22), (20, 36), (100, 100), (20, 100), (1, 36), (1, 100), (50, 77)])
+def test_attention_bf16_engine_kernels(engines, Tq, Tk):
+    """bf16 engines: mma.sync tensor-core attention (Tq > 1) and the single-query row kernel (Tq == 1) on
+    bf16-rounded q/k/v; probabilities are rounded to bf16 before P.V, outputs are bf16: 2e-2 absolute."""
+    _, e16 = engines
+    g = torch.Generator().manual_seed(Tq * 131 + Tk)
+    B = 5
+    q = torch.randn(B, Tq, 512, generator=g).bfloat16().float()
+    k = torch.randn(B, Tk, 512, generator=g).bfloat16().float()
+    v = torch.randn(B, Tk, 512, generator=g).bfloat16().float()
+    vis = torch.randint(1, Tk + 1, (B, Tq), generator=g).int()
+    vis[0, 0] = 0
+    vis[1, :] = Tk
+    out = e16.attention(q.cuda(), k.cuda(), v.cuda(), vis.cuda()).cpu()
+    ref = _attention_reference(q, k, v, vis)
+    assert torch.isnan(out[0, 0]).all()
+    assert (torch.isnan(out) == torch.isnan(ref)).all()
+    ok = ~torch.isnan(ref)
+    assert (out[ok] - ref[ok]).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("Tk", [36, 100])
+def test_attention_single_query_fp32(engines, Tk):
+    e32, _ = engines
+    g = torch.Generator().manual_seed(Tk)
+    B = 7
+    q = torch.randn(B, 1, 512, generator=g)
+    k = torch.randn(B, Tk, 512, generator=g)
+    v = torch.randn(B, Tk, 512, generator=g)
+    vis = torch.randint(1, Tk + 1, (B, 1), generator=g).int()
+    out = e32.attention(q.cuda(), k.cuda(), v.cuda(), vis.cuda()).cpu()
+    assert (out - _attention_reference(q, k, v, vis)).abs().max().item() < 2e-5
