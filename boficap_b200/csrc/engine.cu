@@ -939,6 +939,11 @@ int bofi_linear_f32(bofi_handle_t e, void* stream, const float* A, const float* 
     return linear<float, float>(e, s, A, K, l, residual, N, out, N, M, relu, nullptr);
   }
   if (N % 8) return fail(BOFI_ERR_INVALID, "bf16 unit GEMM needs N %% 8 == 0");
+  if (!bias) {
+    RC_TRY(e->unit_o.reserve((size_t)N * 4));
+    CU_TRY(cudaMemsetAsync(e->unit_o.p, 0, (size_t)N * 4, s));
+    l.b = e->unit_o.as<float>();
+  }
   RC_TRY(e->unit_a.reserve((size_t)M * K * 2));
   RC_TRY(e->unit_w.reserve((size_t)N * K * 2));
   cast_kernel<bf16><<<ceil_div((size_t)M * K / 4, 256), 256, 0, s>>>(A, e->unit_a.as<bf16>(), (size_t)M * K / 4);

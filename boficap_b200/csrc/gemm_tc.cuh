@@ -130,7 +130,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // Persistent: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, +gridDim.x, ... (N fastest, so
 // the CTAs resident at one time share A panels through L2).  Two accumulator tiles live in TMEM
 // (2 x BN columns): the epilogue of tile i overlaps the main loop of tile i+1.
-template <int BN, int STAGES, typename TOut>
+template <int BN, int STAGES, typename TOut, bool RELU, bool RESID>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, const float* residual, int ldr,
@@ -240,16 +240,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr int NC = BN / CC;
       // The residual does not depend on the accumulator: fetch the first two chunks of this thread's row
       // before waiting for the MMAs, and keep two chunks in flight while the tile drains.
-      constexpr int RV = (sizeof(TOut) == 4) ? 8 : 1;           // residual only exists on the fp32-output path
+      constexpr int RV = RESID ? 8 : 1;                         // residual only exists on the fp32-output path
       float4 res[3][RV];
       auto fetch_res = [&](float4 (&dst)[RV], int c) {
-        if constexpr (sizeof(TOut) == 4) {
+        if constexpr (RESID) {
           const int n = n0 + c * CC;
+          if (row_ok && c < NC && n + CC <= N) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            dst[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (residual && row_ok && c < NC && n + 4 * j + 4 <= N)
-              dst[j] = *reinterpret_cast<const float4*>(residual + (size_t)row * ldr + n + 4 * j);
+            for (int j = 0; j < 8; ++j) dst[j] = *reinterpret_cast<const float4*>(residual + (size_t)row * ldr + n + 4 * j);
           }
         }
       };
@@ -262,6 +260,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int n = n0 + c * CC;
         if (n >= N) break;                            // warp-uniform
         fetch_res(res[(c + 2) % 3], c + 2);
+        const bool full = (n + CC <= N);              // warp-uniform
+        float4 bb[CC / 4];
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < CC / 4; ++j) bb[j] = *reinterpret_cast<const float4*>(bias + n + 4 * j);
+        }
         uint32_t r[CC];
         {
           uint32_t(&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
@@ -271,35 +275,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + c * CC + 32), r1);
           }
         }
-        const bool full = (n + CC <= N);
+        if (full) {
 #pragma unroll
-        for (int j = 0; j < CC; j += 4) {
-          float4 x = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                 __uint_as_float(r[j + 3]));
-          if (full) {
-            if (bias) {
-              const float4 bb = *reinterpret_cast<const float4*>(bias + n + j);
-              x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
-            }
-            if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-            if constexpr (sizeof(TOut) == 4) {
-              const float4 rr = res[c % 3][j / 4];    // zero when there is no residual
-              x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
-            }
-          } else {
-            float xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (n + j + q < N) {
-                if (bias) xs[q] += bias[n + j + q];
-                if (relu) xs[q] = fmaxf(xs[q], 0.f);
-                if (residual && row_ok) xs[q] += residual[(size_t)row * ldr + n + j + q];
+          for (int j = 0; j < CC; j += 4) {
+            float4 x = make_float4(__uint_as_float(r[j]) + bb[j / 4].x, __uint_as_float(r[j + 1]) + bb[j / 4].y,
+                                   __uint_as_float(r[j + 2]) + bb[j / 4].z, __uint_as_float(r[j + 3]) + bb[j / 4].w);
+            if constexpr (RELU) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+            if constexpr (RESID) {
+              if (row_ok) {
+                const float4 rr = res[c % 3][j / 4];
+                x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
               }
             }
-            x = make_float4(xs[0], xs[1], xs[2], xs[3]);
+            r[j] = __float_as_uint(x.x); r[j + 1] = __float_as_uint(x.y);
+            r[j + 2] = __float_as_uint(x.z); r[j + 3] = __float_as_uint(x.w);
           }
-          r[j] = __float_as_uint(x.x); r[j + 1] = __float_as_uint(x.y);
-          r[j + 2] = __float_as_uint(x.z); r[j + 3] = __float_as_uint(x.w);
+        } else {
+          // N tail (only the last column tile of the vocab projection): guarded scalar path
+#pragma unroll
+          for (int j = 0; j < CC; ++j) {
+            float x = 0.f;
+            if (n + j < N) {
+              x = __uint_as_float(r[j]) + bias[n + j];
+              if constexpr (RELU) x = fmaxf(x, 0.f);
+              if constexpr (RESID) { if (row_ok) x += residual[(size_t)row * ldr + n + j]; }
+            }
+            r[j] = __float_as_uint(x);
+          }
         }
         // the staging tile used two stores ago must have been read out by the TMA engine
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -382,20 +384,20 @@ inline int num_sms() {
   return n;
 }
 
-template <int BN, int STAGES, typename TOut>
+template <int BN, int STAGES, typename TOut, bool RELU, bool RESID>
 inline cudaError_t launch(cudaStream_t s, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                           const float* bias, const float* residual, int ldr, int M, int N, int K, int relu,
                           const int* live_rows) {
   using L = SmemLayout<BN, STAGES>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, TOut>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, TOut, RELU, RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const int ntiles = ((M + kBM - 1) / kBM) * ((N + BN - 1) / BN);
   const int grid = ntiles < num_sms() ? ntiles : num_sms();
-  gemm_tc_kernel<BN, STAGES, TOut><<<grid, kThreads, L::kTotal, s>>>(tmA, tmB, tmC, bias, residual, ldr, M, N, K, relu, live_rows);
+  gemm_tc_kernel<BN, STAGES, TOut, RELU, RESID><<<grid, kThreads, L::kTotal, s>>>(tmA, tmB, tmC, bias, residual, ldr, M, N, K, relu, live_rows);
   return cudaGetLastError();
 }
 
@@ -441,8 +443,21 @@ inline cudaError_t gemm_tc(cudaStream_t s, const bf16* A, int lda, const bf16* W
   const CUtensorMap* tmB = cached_tmap(W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, wide ? 256 : 64);
   const CUtensorMap* tmC = cached_tmap(C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, (int)sizeof(TOut));
   if (!tmA || !tmB || !tmC) return cudaErrorInvalidValue;
-  if (wide) return launch<256, 4, TOut>(s, *tmA, *tmB, *tmC, bias, residual, ldr, M, N, K, relu, live_rows);
-  return launch<64, 6, TOut>(s, *tmA, *tmB, *tmC, bias, residual, ldr, M, N, K, relu, live_rows);
+  if (!bias) return cudaErrorInvalidValue;          // every nn.Linear of this model has a bias
+#define BOFI_TC_LAUNCH(BN_, ST_, RELU_, RESID_) \
+  launch<BN_, ST_, TOut, RELU_, RESID_>(s, *tmA, *tmB, *tmC, bias, residual, ldr, M, N, K, relu, live_rows)
+  if constexpr (sizeof(TOut) == 4) {
+    // fp32 outputs: plain (logits), +ReLU (att_embed), +residual (O-proj / FFN2 into the residual stream)
+    if (residual && relu) return cudaErrorInvalidValue;
+    if (residual) return wide ? BOFI_TC_LAUNCH(256, 4, false, true) : BOFI_TC_LAUNCH(64, 6, false, true);
+    if (relu) return wide ? BOFI_TC_LAUNCH(256, 4, true, false) : BOFI_TC_LAUNCH(64, 6, true, false);
+    return wide ? BOFI_TC_LAUNCH(256, 4, false, false) : BOFI_TC_LAUNCH(64, 6, false, false);
+  } else {
+    if (residual) return cudaErrorInvalidValue;
+    if (relu) return wide ? BOFI_TC_LAUNCH(256, 4, true, false) : BOFI_TC_LAUNCH(64, 6, true, false);
+    return wide ? BOFI_TC_LAUNCH(256, 4, false, false) : BOFI_TC_LAUNCH(64, 6, false, false);
+  }
+#undef BOFI_TC_LAUNCH
 }
 
 }  // namespace tc
