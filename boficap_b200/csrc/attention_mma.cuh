@@ -220,11 +220,24 @@ attention_row_kernel(const T* __restrict__ Q, int ldq, const T* __restrict__ K, 
   }
   __syncwarp();
   float o0 = 0.f, o1 = 0.f;
-  for (int j = 0; j < nvis; ++j) {
-    const float pj = ps[head][j];
-    const T* vr = V + (kvrow0 + j) * ldkv + head * kHeadDim;
-    o0 = fmaf(pj, to_float<T>(vr[lane]), o0);
-    o1 = fmaf(pj, to_float<T>(vr[lane + 32]), o1);
+  // V rows come from L2: issue 8 independent row loads per trip (the adds stay in key order)
+  for (int j0 = 0; j0 < nvis; j0 += 8) {
+    float v0[8], v1[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = min(j0 + u, nvis - 1);
+      const T* vr = V + (kvrow0 + j) * ldkv + head * kHeadDim;
+      v0[u] = to_float<T>(vr[lane]);
+      v1[u] = to_float<T>(vr[lane + 32]);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (j0 + u < nvis) {
+        const float pj = ps[head][j0 + u];
+        o0 = fmaf(pj, v0[u], o0);
+        o1 = fmaf(pj, v1[u], o1);
+      }
+    }
   }
   if (nvis <= 0) o0 = o1 = __int_as_float(0x7fc00000);
   T* og = O + (size_t)b * ldo + head * kHeadDim;

@@ -521,9 +521,14 @@ static int project_memory_kv(bofi_engine* e, cudaStream_t s, const Lin& kv, DevB
 
 // Final LayerNorm of the [LEN] row + both classifier heads + box rule, one fused launch per step.
 static int head_step(bofi_engine* e, cudaStream_t s, const float* x, size_t x_stride, int rows, int step_col, int step_no, int saic) {
-  const size_t smem = sizeof(float) * (kHeadRows * kD + kHeadRows * 200 + kHeadRows * 32);
+  const size_t smem = sizeof(float) * (kHeadRows * kD + kHeadRows * 200 + kHeadRows * 32 + 4 * kHeadRows * 200);
+  static bool configured = false;
+  if (!configured) {
+    CU_TRY(cudaFuncSetAttribute(bound_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
   ProfScope prof(e, s, PC_OTHER, 2.0 * rows * 200 * kD, 0.0, rows, 200, kD);
-  bound_head_kernel<<<ceil_div(rows, kHeadRows), 256, smem, s>>>(x, x_stride, e->lp_norm.a, e->lp_norm.b, e->head1t.as<float>(), e->head1.b, 100,
+  bound_head_kernel<<<ceil_div(rows, kHeadRows), 1024, smem, s>>>(x, x_stride, e->lp_norm.a, e->lp_norm.b, e->head1t.as<float>(), e->head1.b, 100,
                                                               e->w_len2, e->b_len2, e->w_syn2, e->b_syn2, 20, 10, e->st, rows, e->Lb, e->L,
                                                               step_col, step_no, 4, 6, saic);
   CU_TRY(cudaGetLastError());

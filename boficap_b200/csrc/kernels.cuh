@@ -175,11 +175,23 @@ bound_self_attn_kernel(const T* __restrict__ qkv_tab, int Lb, int q_row, const i
   const float sum = warp_sum(e);
   const float p = e / sum;
   float o0 = 0.f, o1 = 0.f;
-  for (int j = 0; j < nvis; ++j) {
-    const float pj = __shfl_sync(0xffffffffu, p, j);
-    const T* vr = qkv_tab + (size_t)rowid[j] * 3 * kD + 2 * kD + head * kHeadDim;
-    o0 = fmaf(pj, to_float<T>(vr[lane]), o0);
-    o1 = fmaf(pj, to_float<T>(vr[lane + 32]), o1);
+  for (int j0 = 0; j0 < nvis; j0 += 8) {       // 8 independent table-row loads per trip, adds in key order
+    float v0[8], v1[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = min(j0 + u, nvis - 1);
+      const T* vr = qkv_tab + (size_t)rowid[j] * 3 * kD + 2 * kD + head * kHeadDim;
+      v0[u] = to_float<T>(vr[lane]);
+      v1[u] = to_float<T>(vr[lane + 32]);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float pj = __shfl_sync(0xffffffffu, p, min(j0 + u, 31));
+      if (j0 + u < nvis) {
+        o0 = fmaf(pj, v0[u], o0);
+        o1 = fmaf(pj, v1[u], o1);
+      }
+    }
   }
   T* og = O + (size_t)b * kD + head * kHeadDim;
   og[lane] = from_float<T>(o0);
@@ -337,7 +349,7 @@ __global__ void init_state_kernel(DecodeState st, int rows, int Lb, int L, int l
 // NAIC (`saic == 0`) also writes the syn id into ext[last:last+len] and advances `last`/`vis`;
 // SAIC defers that to saic_commit_kernel (the slots are filled with generated words).
 constexpr int kHeadRows = 8;
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 bound_head_kernel(const float* __restrict__ x, size_t x_stride, const float* __restrict__ ln_a, const float* __restrict__ ln_b,
                   const float* __restrict__ w1t, const float* __restrict__ b1, int Hh,
                   const float* __restrict__ w_len, const float* __restrict__ b_len,
@@ -348,9 +360,10 @@ bound_head_kernel(const float* __restrict__ x, size_t x_stride, const float* __r
   float* h = hsm;                               // [8][512]  normalised [LEN] rows
   float* hid = h + kHeadRows * kD;              // [8][2*Hh]
   float* lg = hid + kHeadRows * 2 * Hh;         // [8][32]
+  float* part = lg + kHeadRows * 32;            // [4][8][2*Hh]  K-quarter partial sums
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b0 = blockIdx.x * kHeadRows;
-  {   // LayerNorm, same arithmetic as layernorm_kernel
+  if (warp < kHeadRows) {   // LayerNorm, same arithmetic as layernorm_kernel
     const int b = b0 + warp;
     if (b < rows) {
       const float* xr = x + (size_t)b * x_stride;
@@ -385,29 +398,43 @@ bound_head_kernel(const float* __restrict__ x, size_t x_stride, const float* __r
     }
   }
   __syncthreads();
-  // classifier1 of both heads: thread o owns output column o for all 8 rows; w1t rows are contiguous in o
-  const int o = threadIdx.x;
-  if (o < 2 * Hh) {
+  // classifier1 of both heads: 1024 threads = 4 K-quarters x 256 output columns.  A thread walks its 128-deep
+  // K slice of column o in batches of 32 independent coalesced loads (the weight lives in L2), so only four
+  // round trips sit on the critical path; the four partial sums are combined through shared memory.
+  {
+    const int o = threadIdx.x & 255, kq = threadIdx.x >> 8;
     float acc[kHeadRows];
 #pragma unroll
     for (int r = 0; r < kHeadRows; ++r) acc[r] = 0.f;
-    for (int k = 0; k < kD; k += 4) {
-      const float w0 = w1t[(size_t)(k + 0) * 2 * Hh + o], w1 = w1t[(size_t)(k + 1) * 2 * Hh + o];
-      const float w2 = w1t[(size_t)(k + 2) * 2 * Hh + o], w3 = w1t[(size_t)(k + 3) * 2 * Hh + o];
+    if (o < 2 * Hh) {
+      for (int k0 = kq * (kD / 4); k0 < (kq + 1) * (kD / 4); k0 += 32) {
+        float w[32];
 #pragma unroll
-      for (int r = 0; r < kHeadRows; ++r) {
-        const float4 hv = *reinterpret_cast<const float4*>(h + r * kD + k);
-        acc[r] = fmaf(hv.x, w0, acc[r]);
-        acc[r] = fmaf(hv.y, w1, acc[r]);
-        acc[r] = fmaf(hv.z, w2, acc[r]);
-        acc[r] = fmaf(hv.w, w3, acc[r]);
+        for (int u = 0; u < 32; ++u) w[u] = w1t[(size_t)(k0 + u) * 2 * Hh + o];
+#pragma unroll
+        for (int u = 0; u < 32; u += 4) {
+#pragma unroll
+          for (int r = 0; r < kHeadRows; ++r) {
+            const float4 hv = *reinterpret_cast<const float4*>(h + r * kD + k0 + u);
+            acc[r] = fmaf(hv.x, w[u], acc[r]);
+            acc[r] = fmaf(hv.y, w[u + 1], acc[r]);
+            acc[r] = fmaf(hv.z, w[u + 2], acc[r]);
+            acc[r] = fmaf(hv.w, w[u + 3], acc[r]);
+          }
+        }
       }
-    }
-    const float bias = b1[o];
 #pragma unroll
-    for (int r = 0; r < kHeadRows; ++r) hid[r * 2 * Hh + o] = fmaxf(acc[r] + bias, 0.f);
+      for (int r = 0; r < kHeadRows; ++r) part[(kq * kHeadRows + r) * 2 * Hh + o] = acc[r];
+    }
   }
   __syncthreads();
+  for (int i = threadIdx.x; i < kHeadRows * 2 * Hh; i += blockDim.x) {
+    const int o = i % (2 * Hh);
+    const float v = ((part[i] + part[kHeadRows * 2 * Hh + i]) + part[2 * kHeadRows * 2 * Hh + i]) + part[3 * kHeadRows * 2 * Hh + i];
+    hid[i] = fmaxf(v + b1[o], 0.f);
+  }
+  __syncthreads();
+  if (warp >= kHeadRows) return;
   const int b = b0 + warp;
   if (b >= rows) return;
   const float* hr = hid + warp * 2 * Hh;
