@@ -111,6 +111,7 @@ struct bofi_engine {
   Norm enc_norm, dec_norm, lp_norm;
   const float *w_len2 = nullptr, *b_len2 = nullptr, *w_syn2 = nullptr, *b_syn2 = nullptr;
   DevBuf bound_in, fill_in;            // (id, position) input tables
+  DevBuf sa_mx, sa_lse;                // SAIC: per (row, slot) max / log-sum-exp of the step's logits
   DevBuf head1t;                       // [512][200] = [Length_classifier1 ; Syntactic_classifier1]^T
   DevBuf tab_y, tab_qkv;               // N_len == 1: LN + QKV of every (syn, position) bounding input row
   bool bound_fast = false;             // [LEN]-row-only bounding step (NAIC, N_len == 1)
@@ -540,7 +541,7 @@ template <typename T>
 static int bounding_step(bofi_engine* e, cudaStream_t s, int rows, int sn, int step_col, int saic) {
   const bofi_config_t& c = e->cfg;
   const int Lb = e->Lb;
-  const int* live = e->st.counters;
+  const int* live = saic ? e->st.counters + 4 : e->st.counters;   // SAIC: live rows at the start of the step
   const int* mem_len = e->have_len ? e->attlen.as<int>() : nullptr;
   float* x = e->x.as<float>();
   const int Tb = (c.n_len == 0) ? 1 : Lb;   // without self-attention only the [LEN] row matters (:369-375)
@@ -671,6 +672,67 @@ static int decode_naic(bofi_engine* e, cudaStream_t s, int sn, int output_logsof
   return BOFI_OK;
 }
 
+#define LAUNCH_OTHER(...)                       \
+  do {                                          \
+    ProfScope prof__(e, s, PC_OTHER, 0.0, 0.0); \
+    __VA_ARGS__;                                \
+  } while (0);                                  \
+  CU_TRY(cudaGetLastError())
+
+// core_SAIC (TransformerModel.py:1878-1986): per phrase step the bounding head on the words generated so far,
+// then the full decoder over all L slots under the phrase-block-causal mask, vocab projection, greedy pick and
+// commit of the slots of the new phrase.  Everything stays on the device; steps after the last live row (or
+// after a NaN abort) return at their first instruction.
+template <typename T>
+static int decode_saic(bofi_engine* e, cudaStream_t s, int sn, int output_logsoftmax, long long* seq, float* logprobs,
+                       int* phrase_num, int* phrase_length, long long* phrase_syn) {
+  const bofi_config_t& c = e->cfg;
+  const int rows = e->B * sn, Lb = e->Lb, L = e->L;
+  const int* mem_len = e->have_len ? e->attlen.as<int>() : nullptr;
+  const int nb_layers = std::max(1, c.n_len);
+  RC_TRY(e->sa_mx.reserve((size_t)rows * L * 4));
+  RC_TRY(e->sa_lse.reserve((size_t)rows * L * 4));
+  if (c.n_len == 0) {
+    RC_TRY(project_memory_kv<T>(e, s, e->lp0.ca.kv, e->kv[0]));
+  } else {
+    for (int l = 0; l < c.n_len; ++l) RC_TRY(project_memory_kv<T>(e, s, e->lp[l].ca.kv, e->kv[l]));
+  }
+  for (int l = 0; l < c.n_dec; ++l) RC_TRY(project_memory_kv<T>(e, s, e->dec[l].ca.kv, e->kv[nb_layers + l]));
+  if (logprobs) CU_TRY(cudaMemsetAsync(logprobs, 0, (size_t)rows * L * e->V * sizeof(float), s));   // seq_logprobs = zeros (:1883)
+  LAUNCH_OTHER((init_state_kernel<<<ceil_div(rows, 128), 128, 0, s>>>(e->st, rows, Lb, L, c.len_idx, c.bos_idx, 1)));
+  const int* live = e->st.counters + 4;
+  float* x = e->x.as<float>();
+  const float sqrt_d = sqrtf((float)kD);
+  for (int i = 1; i <= L; ++i) {
+    LAUNCH_OTHER((saic_snapshot_kernel<<<1, 1, 0, s>>>(e->st)));
+    RC_TRY(bounding_step<T>(e, s, rows, sn, i, 1));
+    LAUNCH_OTHER((saic_prepare_kernel<<<ceil_div(rows, 128), 128, 0, s>>>(e->st, rows, Lb, L, i)));
+    LAUNCH_OTHER((embed_words_kernel<<<ceil_div(rows * L, 8), 256, 0, s>>>(
+        W(e, "model.tgt_embed.lut.weight"), W(e, "model.syn_embed.lut.weight"), W(e, "model.pos_embed.pe"), e->st.ext_word,
+        e->st.ext_syn, Lb, 1, sqrt_d, x, rows * L, L, live)));
+    for (int l = 0; l < c.n_dec; ++l)
+      RC_TRY(run_layer<T>(e, s, e->dec[l], x, rows, L, e->st.vis_fill, L, 1, e->kv[nb_layers + l].as<T>(), e->R, mem_len, sn, live));
+    RC_TRY(layernorm<T>(e, s, x, kD, e->dec_norm, e->y.as<T>(), kD, rows * L, nullptr, live));
+    RC_TRY((linear<T, float>(e, s, e->y.as<T>(), kD, e->generator, nullptr, 0, e->logits.as<float>(), e->Vpad, rows * L, 0, live)));
+    {
+      ProfScope prof(e, s, PC_VOCAB, 0.0, 0.0);
+      vocab_stats_kernel<<<rows * L, 256, 0, s>>>(e->logits.as<float>(), e->Vpad, e->V, e->tok.as<int>(), e->sa_mx.as<float>(),
+                                                 e->sa_lse.as<float>(), e->st);
+    }
+    CU_TRY(cudaGetLastError());
+    if (logprobs) {
+      ProfScope prof(e, s, PC_VOCAB, 0.0, 0.0);
+      saic_write_logp_kernel<<<rows * L, 256, 0, s>>>(e->logits.as<float>(), e->Vpad, e->V, e->sa_mx.as<float>(), e->sa_lse.as<float>(),
+                                                     logprobs, e->st, L, output_logsoftmax);
+    }
+    CU_TRY(cudaGetLastError());
+    LAUNCH_OTHER((saic_advance_kernel<<<ceil_div(rows, 128), 128, 0, s>>>(e->tok.as<int>(), e->st, rows, Lb, L, i)));
+  }
+  LAUNCH_OTHER((export_seq_kernel<<<ceil_div(rows * L, 256), 256, 0, s>>>(e->st, rows, Lb, L, seq)));
+  LAUNCH_OTHER((export_boxes_kernel<<<ceil_div(rows * L, 256), 256, 0, s>>>(e->st, rows, Lb, L, 1, phrase_num, phrase_length, phrase_syn)));
+  return BOFI_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
@@ -722,7 +784,7 @@ int bofi_destroy(bofi_handle_t e) {
   for (DevBuf& b : e->packed) b.release();
   for (DevBuf& b : e->kv) b.release();
   DevBuf* all[] = {&e->bound_in, &e->fill_in, &e->attT, &e->x, &e->y, &e->qkv, &e->ao, &e->q, &e->ffh, &e->memT, &e->attlen,
-                   &e->head1t, &e->tab_y, &e->tab_qkv, &e->hrow, &e->hid, &e->logits, &e->state_i32, &e->tok, &e->h_in, &e->h_len, &e->h_seq, &e->h_logp,
+                   &e->sa_mx, &e->sa_lse, &e->head1t, &e->tab_y, &e->tab_qkv, &e->hrow, &e->hid, &e->logits, &e->state_i32, &e->tok, &e->h_in, &e->h_len, &e->h_seq, &e->h_logp,
                    &e->h_pnum, &e->h_plen, &e->h_psyn, &e->unit_a, &e->unit_w, &e->unit_o};
   for (DevBuf* b : all) b->release();
   delete e;
@@ -837,10 +899,13 @@ int bofi_decode(bofi_handle_t e, void* stream, int32_t mode, int32_t sn, int32_t
   if (!e || !seq || !phrase_num || !phrase_length || !phrase_syn) return fail(BOFI_ERR_INVALID, "null argument");
   if (!e->have_memory) return fail(BOFI_ERR_STATE, "bofi_decode needs a preceding bofi_encode");
   if (sn < 1) return fail(BOFI_ERR_INVALID, "sample_n %d", sn);
-  if (mode != BOFI_MODE_NAIC) return fail(BOFI_ERR_INVALID, "mode %d not built yet (NAIC only)", mode);
+  if (mode != BOFI_MODE_NAIC && mode != BOFI_MODE_SAIC) return fail(BOFI_ERR_INVALID, "mode %d (NAIC = 0, SAIC = 1)", mode);
   CU_TRY(cudaSetDevice(e->device));
   cudaStream_t s = (cudaStream_t)stream;
   RC_TRY(reserve_decode(e, e->B, e->R, sn));
+  if (mode == BOFI_MODE_SAIC)
+    return e->bf16_mode ? decode_saic<bf16>(e, s, sn, output_logsoftmax, (long long*)seq, logprobs, phrase_num, phrase_length, (long long*)phrase_syn)
+                        : decode_saic<float>(e, s, sn, output_logsoftmax, (long long*)seq, logprobs, phrase_num, phrase_length, (long long*)phrase_syn);
   return e->bf16_mode ? decode_naic<bf16>(e, s, sn, output_logsoftmax, (long long*)seq, logprobs, phrase_num, phrase_length, (long long*)phrase_syn)
                       : decode_naic<float>(e, s, sn, output_logsoftmax, (long long*)seq, logprobs, phrase_num, phrase_length, (long long*)phrase_syn);
 }

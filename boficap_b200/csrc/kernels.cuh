@@ -322,7 +322,7 @@ struct DecodeState {
 
 __global__ void init_state_kernel(DecodeState st, int rows, int Lb, int L, int len_idx, int bos_idx, int saic) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b == 0) { st.counters[0] = rows; st.counters[1] = 0; st.counters[2] = 0; st.counters[3] = 0; }
+  if (b == 0) { st.counters[0] = rows; st.counters[1] = 0; st.counters[2] = 0; st.counters[3] = 0; st.counters[4] = rows; st.counters[5] = 0; }
   if (b >= rows) return;
   for (int r = 0; r < Lb; ++r) {
     st.ext[b * Lb + r] = (r == 0) ? len_idx : 0;
@@ -568,6 +568,128 @@ vocab_epilogue_kernel(const float* __restrict__ logits, int ldl, int V, float* _
       seq_out[row] = tok;
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// SAIC (core_SAIC, TransformerModel.py:1878-1986).  counters[4] is the live-row count at the START of the
+// step: a row that finishes by clipping in this step still has its last phrase decoded (:1917-1922), so the
+// kernels of a step test the snapshot, not the running counter.  counters[5] is the "phrase nan!" flag.
+// ---------------------------------------------------------------------------------------------
+__global__ void saic_snapshot_kernel(DecodeState st) { st.counters[4] = st.counters[0]; }
+
+// Decoder input of the phrase accepted at step i (:1928-1948): syn label + position-wise copy of the previous
+// phrase's words (last n words when n <= m, otherwise each word stretched ct or ct+1 times), and the
+// phrase-block-causal mask phrase_mask[p:, :p+n] = True in its prefix-count form.
+__global__ void saic_prepare_kernel(DecodeState st, int rows, int Lb, int L, int step) {
+  if (st.counters[4] == 0) return;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= rows) return;
+  const int n = st.step_len[b];
+  if (n == 0) return;
+  const int p = st.last[b], m = st.phrase_length[b * Lb + step - 1], s0 = st.seq_last[b];
+  const int syn = st.phrase_syn[b * Lb + step];
+  for (int k = 0; k < n; ++k) st.ext_syn[b * Lb + p + k] = syn;
+  if (n <= m) {
+    for (int k = 0; k < n; ++k) st.ext_word[b * Lb + p + k] = st.seq22[b * Lb + s0 + (m - n) + k];
+  } else {
+    const int pre_less = m - (n % m), ct = n / m;
+    int w = 0;
+    for (int k = 0; k < m; ++k) {
+      const int rep = (k < pre_less) ? ct : ct + 1;
+      const int tokv = st.seq22[b * Lb + s0 + k];
+      for (int r = 0; r < rep; ++r) st.ext_word[b * Lb + p + w++] = tokv;
+    }
+  }
+  // decoder rows q = slot-1 >= p-1 see decoder keys k < p+n-1  (phrase_mask[1:-1, 1:-1])
+  for (int q = p - 1; q < L; ++q) st.vis_fill[b * L + q] = p + n - 1;
+}
+
+// Per (row, slot): first-max argmax (NaN maximal), max and log-sum-exp of the logits; raises the NaN flag
+// (the reference aborts the whole batch when any log-prob of the step is NaN, :1956-1958).
+__global__ void __launch_bounds__(256)
+vocab_stats_kernel(const float* __restrict__ logits, int ldl, int V, int* __restrict__ tok, float* __restrict__ mx_out,
+                   float* __restrict__ lse_out, DecodeState st) {
+  if (st.counters[4] == 0) return;
+  __shared__ ArgMax s_am[8];
+  __shared__ float s_sum[8];
+  const int row = blockIdx.x;
+  const float* z = logits + (size_t)row * ldl;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  ArgMax am = {-INFINITY, 0x7fffffff};
+  for (int c = tid; c < V; c += 256) am = better(am, ArgMax{z[c], c});
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ArgMax other = {__shfl_xor_sync(0xffffffffu, am.v, o), __shfl_xor_sync(0xffffffffu, am.i, o)};
+    am = better(am, other);
+  }
+  if (lane == 0) s_am[warp] = am;
+  __syncthreads();
+  am = s_am[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) am = better(am, s_am[w]);
+  float s = 0.f;
+  for (int c = tid; c < V; c += 256) s += expf(z[c] - am.v);
+  s = warp_sum(s);
+  if (lane == 0) s_sum[warp] = s;
+  __syncthreads();
+  if (tid == 0) {
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += s_sum[w];
+    tok[row] = am.i;
+    mx_out[row] = am.v;
+    lse_out[row] = logf(tot);
+    if (am.v != am.v) atomicExch(&st.counters[5], 1);
+  }
+}
+
+// seq_logprobs[j, p:p+n] = phrase_logprobs[j, p-1:p-1+n]  (:1972) -- only the slots committed this step are
+// ever written; the caller's tensor is zero-filled once per decode.
+__global__ void __launch_bounds__(256)
+saic_write_logp_kernel(const float* __restrict__ logits, int ldl, int V, const float* __restrict__ mx, const float* __restrict__ lse,
+                       float* __restrict__ logp_out, DecodeState st, int L, int do_logsoftmax) {
+  if (st.counters[4] == 0 || st.counters[5] != 0) return;
+  const int row = blockIdx.x, b = row / L, t = row - b * L;
+  const int n = st.step_len[b], p = st.last[b];
+  if (n == 0 || t < p - 1 || t >= p - 1 + n) return;
+  const float* z = logits + (size_t)row * ldl;
+  float* o = logp_out + (size_t)row * V;
+  const float m = mx[row], l = lse[row];
+  if (do_logsoftmax) {
+    for (int c = threadIdx.x; c < V; c += 256) o[c] = (z[c] - m) - l;
+  } else {
+    for (int c = threadIdx.x; c < V; c += 256) o[c] = z[c];
+  }
+}
+
+// Commit of the step (:1968-1977): generated words into seq / the bounding-head input, len_mask, counters.
+__global__ void saic_advance_kernel(const int* __restrict__ tok, DecodeState st, int rows, int Lb, int L, int step) {
+  if (st.counters[4] == 0) return;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (st.counters[5] != 0) {           // "phrase nan!": return the state as it is, no further steps
+    if (b == 0) { st.counters[0] = 0; st.counters[3] = 1; }
+    return;
+  }
+  if (b >= rows) return;
+  const int n = st.step_len[b];
+  if (n == 0) return;
+  const int p = st.last[b];
+  for (int k = 0; k < n; ++k) {
+    const int w = tok[b * L + p - 1 + k];
+    st.seq22[b * Lb + p + k] = w;
+    st.ext[b * Lb + p + k] = w;
+  }
+  for (int r = p; r < Lb; ++r) st.vis[b * Lb + r] = p + n;   // len_mask[j, p:, :p+n] = True
+  st.vis[b * Lb] = p + n;                                     // len_mask[j, 0, :phrase_last] = True
+  st.last[b] = p + n;
+  st.seq_last[b] += st.phrase_length[b * Lb + step - 1];
+}
+
+__global__ void export_seq_kernel(DecodeState st, int rows, int Lb, int L, long long* __restrict__ seq) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * L) return;
+  const int b = i / L, c = i - b * L;
+  seq[i] = st.seq22[b * Lb + 1 + c];
 }
 
 // phrase_length[:, :L] / phrase_syn[:, :L] (i64) / phrase_num to the caller's tensors.

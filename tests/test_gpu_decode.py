@@ -56,6 +56,46 @@ def test_fp32_decode_matches_golden_and_oracle(name):
     assert info["kernel_launches"] > 0
 
 
+def test_fp32_saic_decode_matches_golden_and_oracle():
+    fix, cfg = load_golden("saic_b8_r36")
+    eng = engine_for(cfg, "s_cap", "fp32")
+    fc, att, masks = golden_inputs(fix)
+    seq, logp, pnum, plen, psyn = run_cuda(eng, att, masks, mode="SAIC")
+    logits = run_cuda(eng, att, masks, mode="SAIC", output_logsoftmax=0)[1]
+    check_against_golden(fix, seq, logp, pnum, plen, psyn, logits=None, atol=1e-4)
+    o = oracle_for(cfg, checkpoint(cfg, "s_cap"))
+    ref = o.sample(fc, att, masks, {"train_mode": "SAIC"})
+    raw = oracle_for(cfg, checkpoint(cfg, "s_cap")).sample(fc, att, masks, {"train_mode": "SAIC", "output_logsoftmax": 0})
+    assert torch.equal(seq, ref[0]) and torch.equal(pnum, ref[2]) and torch.equal(plen, ref[3]) and torch.equal(psyn, ref[4])
+    assert_close_nan(logp.numpy(), ref[1].numpy(), 1e-4, "SAIC log-probs (zeros where unfilled)")
+    assert_close_nan(logits.numpy(), raw[1].numpy(), 1e-4, "SAIC raw logits")
+    assert eng.decode_info()["bounding_steps"] == o.last_steps
+
+
+def test_saic_adaptive_regions_and_sample_n():
+    cfg = BofiConfig()
+    eng = engine_for(cfg, "s_cap", "fp32")
+    fc, att, masks = synth.synth_inputs(5, 44, seed=13, adaptive=True)
+    out = run_cuda(eng, att, masks, mode="SAIC", sample_n=2)
+    ref = oracle_for(cfg, checkpoint(cfg, "s_cap")).sample(fc, att, masks, {"train_mode": "SAIC", "sample_n": 2})
+    assert torch.equal(out[0], ref[0]) and torch.equal(out[3], ref[3]) and torch.equal(out[4], ref[4])
+    assert_close_nan(out[1].numpy(), ref[1].numpy(), 1e-4, "logp")
+
+
+def test_saic_phrase_nan_abort_matches_reference_behaviour():
+    """A row that predicts EOS at the first step has an all-False phrase mask -> NaN -> the reference prints
+    'phrase nan!' and returns the state as it is (TransformerModel.py:1956-1958)."""
+    cfg = BofiConfig()
+    eng = engine_for(cfg, "s_real", "fp32")          # s_real: several images stop at step 0
+    fc, att, _ = synth.synth_inputs(16, 36, seed=7)
+    out = run_cuda(eng, att, None, mode="SAIC")
+    ref = oracle_for(cfg, checkpoint(cfg, "s_real")).sample(fc, att, None, {"train_mode": "SAIC"})
+    assert (ref[0] == 0).all()                        # the oracle (== reference) aborted before any word
+    for a, b in zip(out, ref[:5]):
+        assert torch.equal(torch.nan_to_num(a.float()), torch.nan_to_num(b.float()))
+    assert eng.decode_info()["nan_batch"] == 1
+
+
 def test_encoder_memory_matches_oracle():
     cfg = BofiConfig()
     eng = engine_for(cfg, "s_real", "fp32")
