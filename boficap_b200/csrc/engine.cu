@@ -45,11 +45,14 @@ static int fail(int code, const char* fmt, ...) {
     if (rc__ != BOFI_OK) return rc__; \
   } while (0)
 
+static unsigned long long g_alloc_generation = 0;   // bumped whenever a workspace buffer moves (invalidates captured graphs)
+
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
   int reserve(size_t bytes) {
     if (bytes <= cap) return BOFI_OK;
+    ++g_alloc_generation;
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
@@ -129,6 +132,15 @@ struct bofi_engine {
   std::vector<ProfRec> recs;
   DecodeState st{};
   int st_rows = 0;
+  // The NAIC bounding loop (20 steps x ~12 small dependent kernels on internal buffers only) is captured once
+  // per shape into a CUDA graph and replayed: one launch instead of ~230.
+  bool use_graph = true;
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaGraphExec_t bound_exec = nullptr;
+  unsigned long long bound_key[6] = {0, 0, 0, 0, 0, 0};
+  int bound_launches = 0;
+  int bound_eager_runs = 0;
 };
 
 static int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
@@ -637,9 +649,55 @@ static int decode_naic(bofi_engine* e, cudaStream_t s, int sn, int output_logsof
     init_state_kernel<<<ceil_div(rows, 128), 128, 0, s>>>(e->st, rows, Lb, L, c.len_idx, c.bos_idx, 0);
   }
   CU_TRY(cudaGetLastError());
-  for (int i = 0; i < L; ++i) {
-    if (e->bound_fast) RC_TRY(bounding_step_fast<T>(e, s, rows, sn, i));
-    else RC_TRY(bounding_step<T>(e, s, rows, sn, i, 0));
+  auto enqueue_bounding = [&](cudaStream_t bs) -> int {
+    for (int i = 0; i < L; ++i) {
+      if (e->bound_fast) RC_TRY(bounding_step_fast<T>(e, bs, rows, sn, i));
+      else RC_TRY(bounding_step<T>(e, bs, rows, sn, i, 0));
+    }
+    return BOFI_OK;
+  };
+  const unsigned long long key[6] = {(unsigned long long)rows, (unsigned long long)e->R, (unsigned long long)sn,
+                                     (unsigned long long)e->have_len, g_alloc_generation, (unsigned long long)e->bound_fast};
+  const bool key_ok = memcmp(key, e->bound_key, sizeof(key)) == 0;
+  if (!e->use_graph || e->profiling) {
+    RC_TRY(enqueue_bounding(s));
+  } else if (e->bound_exec && key_ok) {
+    CU_TRY(cudaEventRecord(e->ev_fork, s));
+    CU_TRY(cudaStreamWaitEvent(e->aux_stream, e->ev_fork, 0));
+    CU_TRY(cudaGraphLaunch(e->bound_exec, e->aux_stream));
+    CU_TRY(cudaEventRecord(e->ev_join, e->aux_stream));
+    CU_TRY(cudaStreamWaitEvent(s, e->ev_join, 0));
+    e->launches += e->bound_launches;
+  } else if (!key_ok || e->bound_eager_runs < 1) {
+    // first decode of a shape runs eagerly (buffers grow, function attributes get set); the next one captures
+    if (!key_ok) {
+      if (e->bound_exec) { cudaGraphExecDestroy(e->bound_exec); e->bound_exec = nullptr; }
+      memcpy(e->bound_key, key, sizeof(key));
+      e->bound_eager_runs = 0;
+    }
+    RC_TRY(enqueue_bounding(s));
+    e->bound_eager_runs++;
+  } else {
+    if (!e->aux_stream) {
+      CU_TRY(cudaStreamCreateWithFlags(&e->aux_stream, cudaStreamNonBlocking));
+      CU_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+      CU_TRY(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+    }
+    CU_TRY(cudaEventRecord(e->ev_fork, s));
+    CU_TRY(cudaStreamWaitEvent(e->aux_stream, e->ev_fork, 0));
+    const int before = e->launches;
+    cudaGraph_t graph = nullptr;
+    CU_TRY(cudaStreamBeginCapture(e->aux_stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_bounding(e->aux_stream);
+    cudaError_t ce = cudaStreamEndCapture(e->aux_stream, &graph);
+    if (rc != BOFI_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return fail(BOFI_ERR_CUDA, "graph capture: %s", cudaGetErrorString(ce));
+    e->bound_launches = e->launches - before;
+    CU_TRY(cudaGraphInstantiate(&e->bound_exec, graph, 0));
+    cudaGraphDestroy(graph);
+    CU_TRY(cudaGraphLaunch(e->bound_exec, e->aux_stream));
+    CU_TRY(cudaEventRecord(e->ev_join, e->aux_stream));
+    CU_TRY(cudaStreamWaitEvent(s, e->ev_join, 0));
   }
 
   // filling step (decode_NA, :570-587): all L slots of every row in parallel
@@ -769,6 +827,8 @@ int bofi_create(const bofi_config_t* cfg, int device, bofi_handle_t* out) {
   e->bf16_mode = (cfg->precision == BOFI_PRECISION_BF16);
   const char* g = getenv("BOFI_GEMM");
   e->use_tc = !(g && strcmp(g, "simt") == 0);
+  const char* gg = getenv("BOFI_GRAPH");
+  e->use_graph = !(gg && strcmp(gg, "0") == 0);
   const char* ga = getenv("BOFI_ATTN");
   e->attn_simt_only = (ga && strcmp(ga, "simt") == 0);
   build_spec(e);
@@ -779,6 +839,10 @@ int bofi_create(const bofi_config_t* cfg, int device, bofi_handle_t* out) {
 int bofi_destroy(bofi_handle_t e) {
   if (!e) return BOFI_OK;
   cudaSetDevice(e->device);
+  if (e->bound_exec) cudaGraphExecDestroy(e->bound_exec);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
+  if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
   for (auto& kv : e->weights)
     if (kv.second.dev) cudaFree(kv.second.dev);
   for (DevBuf& b : e->packed) b.release();
