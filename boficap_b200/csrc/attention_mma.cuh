@@ -245,4 +245,128 @@ attention_row_kernel(const T* __restrict__ Q, int ldq, const T* __restrict__ K, 
   og[lane + 32] = from_float<T>(o1);
 }
 
+// bf16 single-query attention tuned for HBM streaming (the K/V of `memory`, 2 KB per region, are re-read at
+// every bounding step: 75 MB per step at B=1024, R=36).  4 rows x 8 heads per CTA, one warp per (row, head);
+// every global access is a 16-byte load and all loads of a phase are independent:
+//   scores : 4 lanes per key (16 dims each), 8 keys per pass            -> 2 loads / lane / pass
+//   P.V    : 8 lanes per key (8 dims each), 4 keys in flight per trip   -> 1 load / lane / key
+constexpr int kRowsPerCta = 4;
+__global__ void __launch_bounds__(kRowsPerCta * 256)
+attention_row_bf16_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restrict__ K, const bf16* __restrict__ V, int ldkv,
+                          bf16* __restrict__ O, int ldo, int nb, int Tk, const int* __restrict__ vis, int vis_div, int kv_div,
+                          float scale, const int* live_rows) {
+  if (step_is_dead(live_rows)) return;
+  __shared__ float ps[kRowsPerCta * 8][kMaxKeys];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * kRowsPerCta + (warp >> 3), head = warp & 7;
+  if (b >= nb) return;
+  const size_t kvrow0 = (size_t)(b / kv_div) * Tk;
+  int nvis = vis ? vis[b / vis_div] : Tk;
+  nvis = min(nvis, Tk);
+  // ---- scores ----
+  const int sub = lane & 3, kslot = lane >> 2;
+  float qf[16];
+  {
+    const bf16* qg = Q + (size_t)b * ldq + head * kHeadDim + sub * 16;
+    const uint4 q0 = *reinterpret_cast<const uint4*>(qg), q1 = *reinterpret_cast<const uint4*>(qg + 8);
+    const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+      qf[2 * i] = f.x;
+      qf[2 * i + 1] = f.y;
+    }
+  }
+  float sc[kMaxKeys / 8];
+  float mx = -INFINITY;
+  const int npass = (nvis + 7) >> 3;
+#pragma unroll
+  for (int p = 0; p < kMaxKeys / 8; ++p) {
+    sc[p] = -INFINITY;
+    if (p < npass) {
+      const int j = p * 8 + kslot;
+      float d = 0.f;
+      if (j < nvis) {
+        const bf16* kr = K + (kvrow0 + j) * ldkv + head * kHeadDim + sub * 16;
+        const uint4 k0 = *reinterpret_cast<const uint4*>(kr), k1 = *reinterpret_cast<const uint4*>(kr + 8);
+        const uint32_t w[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+          d = fmaf(qf[2 * i], f.x, d);
+          d = fmaf(qf[2 * i + 1], f.y, d);
+        }
+      }
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      d += __shfl_xor_sync(0xffffffffu, d, 2);
+      if (j < nvis) sc[p] = d * scale;
+      mx = fmaxf(mx, sc[p]);
+    }
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int p = 0; p < kMaxKeys / 8; ++p) {
+    if (p < npass) {
+      const int j = p * 8 + kslot;
+      const float e = (j < nvis) ? __expf(sc[p] - mx) : 0.f;
+      sc[p] = e;
+      if (sub == 0) sum += e;
+    }
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int p = 0; p < kMaxKeys / 8; ++p) {
+    if (p < npass && sub == 0) ps[warp][p * 8 + kslot] = sc[p] * inv;
+  }
+  __syncwarp();
+  // ---- P.V ----
+  const int g = lane & 7, ksub = lane >> 3;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int j0 = 0; j0 < nvis; j0 += 16) {
+    uint4 vv[4];
+    float pj[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * 4 + ksub;
+      pj[u] = 0.f;
+      vv[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (j < nvis) {
+        vv[u] = *reinterpret_cast<const uint4*>(V + (kvrow0 + j) * ldkv + head * kHeadDim + g * 8);
+        pj[u] = ps[warp][j];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t w[4] = {vv[u].x, vv[u].y, vv[u].z, vv[u].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+        acc[2 * i] = fmaf(pj[u], f.x, acc[2 * i]);
+        acc[2 * i + 1] = fmaf(pj[u], f.y, acc[2 * i + 1]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+  }
+  if (ksub == 0) {
+    if (nvis <= 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = __int_as_float(0x7fc00000);
+    }
+    uint4 o;
+    o.x = pack2_bf16(acc[0], acc[1]);
+    o.y = pack2_bf16(acc[2], acc[3]);
+    o.z = pack2_bf16(acc[4], acc[5]);
+    o.w = pack2_bf16(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(O + (size_t)b * ldo + head * kHeadDim + g * 8) = o;
+  }
+}
+
 }  // namespace bofi

@@ -291,7 +291,11 @@ static int attention(bofi_engine* e, cudaStream_t s, const T* Q, int ldq, const 
   ProfScope prof(e, s, PC_ATTENTION, 4.0 * nb * Tq * Tk * kD, (double)sizeof(T) * kD * ((double)nb * Tq * 2 + 2.0 * (nb / kv_div) * Tk),
                  nb, Tq, Tk);
   if (Tq == 1 && !e->attn_simt_only) {
-    attention_row_kernel<T><<<nb, 256, 0, s>>>(Q, ldq, K, V, ldkv, O, ldo, Tk, vis, vis_div, kv_div, scale, live);
+    if constexpr (std::is_same<T, bf16>::value)
+      attention_row_bf16_kernel<<<ceil_div(nb, kRowsPerCta), kRowsPerCta * 256, 0, s>>>(Q, ldq, K, V, ldkv, O, ldo, nb, Tk, vis, vis_div,
+                                                                                       kv_div, scale, live);
+    else
+      attention_row_kernel<T><<<nb, 256, 0, s>>>(Q, ldq, K, V, ldkv, O, ldo, Tk, vis, vis_div, kv_div, scale, live);
     CU_TRY(cudaGetLastError());
     return BOFI_OK;
   }
@@ -718,7 +722,7 @@ static int decode_naic(bofi_engine* e, cudaStream_t s, int sn, int output_logsof
   RC_TRY((linear<T, float>(e, s, e->y.as<T>(), kD, e->generator, nullptr, 0, e->logits.as<float>(), e->Vpad, rows * L, 0, nullptr)));
   {
     ProfScope prof(e, s, PC_VOCAB, 0.0, 0.0);
-    vocab_epilogue_kernel<<<rows * L, 256, 0, s>>>(e->logits.as<float>(), e->Vpad, e->V, logprobs, seq, e->st.last, -1, L,
+    vocab_epilogue_kernel<<<rows * L, kVocabThreads, 0, s>>>(e->logits.as<float>(), e->Vpad, e->V, logprobs, seq, e->st.last, -1, L,
                                                  output_logsoftmax, nullptr);
   }
   CU_TRY(cudaGetLastError());

@@ -520,18 +520,36 @@ __device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {
   return a.i < b.i ? a : b;
 }
 
-__global__ void __launch_bounds__(256)
+constexpr int kVocabThreads = 512;
+constexpr int kVocabVec = 5;    // float4 per thread: 512 threads x 5 x 4 = 10240 >= Vpad (9504)
+__global__ void __launch_bounds__(kVocabThreads, 3)
 vocab_epilogue_kernel(const float* __restrict__ logits, int ldl, int V, float* __restrict__ logp_out,
                       long long* __restrict__ seq_out, const int* __restrict__ total_len, int total_off, int L,
                       int do_logsoftmax, int* __restrict__ tok_out_i32) {
-  __shared__ ArgMax s_am[8];
-  __shared__ float s_sum[8];
+  // The whole row lives in registers: logits are read from HBM exactly once (128-bit loads, all independent),
+  // max / argmax / sum-exp are block reductions, and the log-probs are written once.
+  __shared__ ArgMax s_am[kVocabThreads / 32];
+  __shared__ float s_sum[kVocabThreads / 32];
   const int row = blockIdx.x;              // b * L + t
   const int b = row / L, t = row - b * L;
-  const float* z = logits + (size_t)row * ldl;
+  const float4* z4 = reinterpret_cast<const float4*>(logits + (size_t)row * ldl);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n4 = (V + 3) >> 2;             // ldl >= 4 * n4 (padded pitch); columns >= V are ignored below
+  float4 v[kVocabVec];
+#pragma unroll
+  for (int i = 0; i < kVocabVec; ++i) {
+    const int c4 = tid + i * kVocabThreads;
+    v[i] = (c4 < n4) ? z4[c4] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  }
   ArgMax am = {-INFINITY, 0x7fffffff};
-  for (int c = tid; c < V; c += 256) am = better(am, ArgMax{z[c], c});
+#pragma unroll
+  for (int i = 0; i < kVocabVec; ++i) {
+    const int c = (tid + i * kVocabThreads) * 4;
+    const float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (c + q < V) am = better(am, ArgMax{e[q], c + q});
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     ArgMax other = {__shfl_xor_sync(0xffffffffu, am.v, o), __shfl_xor_sync(0xffffffffu, am.i, o)};
@@ -541,23 +559,45 @@ vocab_epilogue_kernel(const float* __restrict__ logits, int ldl, int V, float* _
   __syncthreads();
   am = s_am[0];
 #pragma unroll
-  for (int w = 1; w < 8; ++w) am = better(am, s_am[w]);
+  for (int w = 1; w < kVocabThreads / 32; ++w) am = better(am, s_am[w]);
   const float mx = am.v;
   if (logp_out) {
     float* o = logp_out + (size_t)row * V;
+    float lse = 0.f;
     if (do_logsoftmax) {
       float s = 0.f;
-      for (int c = tid; c < V; c += 256) s += expf(z[c] - mx);
+#pragma unroll
+      for (int i = 0; i < kVocabVec; ++i) {
+        const int c = (tid + i * kVocabThreads) * 4;
+        const float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (c + q < V) s += expf(e[q] - mx);
+      }
       s = warp_sum(s);
       if (lane == 0) s_sum[warp] = s;
       __syncthreads();
       float tot = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) tot += s_sum[w];
-      const float lse = logf(tot);
-      for (int c = tid; c < V; c += 256) o[c] = (z[c] - mx) - lse;
-    } else {
-      for (int c = tid; c < V; c += 256) o[c] = z[c];
+      for (int w = 0; w < kVocabThreads / 32; ++w) tot += s_sum[w];
+      lse = logf(tot);
+    }
+    // rows of the caller's [rows, L, V] tensor are only 4-byte aligned (V = 9491): stage through shared memory so
+    // that each warp store covers 128 contiguous bytes
+    __shared__ float stage[kVocabThreads * 4];
+#pragma unroll
+    for (int i = 0; i < kVocabVec; ++i) {
+      const int c0 = i * kVocabThreads * 4;   // columns handled by this trip of the CTA
+      float4 w = v[i];
+      if (do_logsoftmax) { w.x = (w.x - mx) - lse; w.y = (w.y - mx) - lse; w.z = (w.z - mx) - lse; w.w = (w.w - mx) - lse; }
+      *reinterpret_cast<float4*>(stage + tid * 4) = w;
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int c = c0 + q * kVocabThreads + tid;
+        if (c < V) o[c] = stage[q * kVocabThreads + tid];
+      }
+      __syncthreads();
     }
   }
   if (tid == 0) {
