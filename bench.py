@@ -250,6 +250,7 @@ def main():
     eng.set_profiling(True)
     step()
     prof = eng.get_profile()
+    top = eng.get_profile_top_gemm() if a.precision == "bf16" else None
     eng.set_profiling(False)
 
     if rank != 0:
@@ -266,11 +267,24 @@ def main():
     gemm_tflops = g["flops"] / (g["ms"] / 1e3) / 1e12 if g["ms"] > 0 else 0.0
     peak = sustained if a.precision == "bf16" else 75.0
     total_ms = sum(v["ms"] for v in prof.values())
-    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05)" if a.precision == "bf16" else "gemm_simt_kernel (FFMA)",
-                "achieved": gemm_tflops, "peak": peak, "unit": "TFLOP/s", "frac": gemm_tflops / peak if peak else None,
+    if top and top["ms"] > 0:
+        # dominant kernel = the tcgen05 GEMM on the shape that takes the most time in a step; algorithmic flops per
+        # launch = 2*M*N*K, duration = CUDA events around each of its launches, averaged
+        achieved = top["flops"] / (top["ms"] / 1e3) / 1e12
+        kname = "gemm_tc_kernel (tcgen05) M=%d N=%d K=%d" % (top["M"], top["N"], top["K"])
+        # ncu --set full capture of this shape (profiles/r01_gemm_ffn_ncu_summary.txt): dram read + write per launch
+        traffic = 133.0e6 if (top["M"], top["N"], top["K"]) == (36864, 2048, 512) else None
+        dom = {"launches_per_step": top["launches"], "us_per_launch": top["ms"] / top["launches"] * 1e3,
+               "gflop_per_launch": top["flops"] / top["launches"] / 1e9, "share_of_step": top["ms"] / total_ms}
+    else:
+        achieved, kname, traffic = gemm_tflops, "gemm_simt_kernel (FFMA), all launches", None
+        dom = {"launches_per_step": g["launches"], "share_of_step": g["ms"] / total_ms if total_ms else None}
+    roofline = {"bound": "tensor", "kernel": kname,
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                 "peak_source": "%s bf16 sustained (kernel timed inside a long step)" % how if a.precision == "bf16" else "nominal fp32 FFMA",
-                "traffic": None, "launches_per_step": g["launches"], "ms_per_step": g["ms"],
-                "share_of_step": g["ms"] / total_ms if total_ms else None,
+                "traffic": traffic, "dominant": dom,
+                "all_gemm_launches": {"launches_per_step": g["launches"], "ms_per_step": g["ms"], "tflops": gemm_tflops,
+                                      "share_of_step": g["ms"] / total_ms if total_ms else None},
                 "whole_path_useful_tflops": value / world * useful_flops_per_caption(R, S) / 1e12,
                 "whole_path_frac_of_burst": value / world * useful_flops_per_caption(R, S) / 1e12 / burst,
                 "classes": {k: {"launches": v["launches"], "ms": round(v["ms"], 4),

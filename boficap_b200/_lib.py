@@ -45,6 +45,7 @@ _SIGNATURES = {
     "bofi_get_decode_info": (C.c_int, [_P, _P, C.POINTER(DecodeInfoC)]),
     "bofi_set_profiling": (C.c_int, [_P, _I]),
     "bofi_get_profile": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "bofi_get_profile_top_gemm": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "bofi_layernorm_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, _I]),
     "bofi_linear_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I]),
     "bofi_attention_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I]),

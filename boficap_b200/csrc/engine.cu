@@ -653,8 +653,10 @@ static int decode_naic(bofi_engine* e, cudaStream_t s, int sn, int output_logsof
     init_state_kernel<<<ceil_div(rows, 128), 128, 0, s>>>(e->st, rows, Lb, L, c.len_idx, c.bos_idx, 0);
   }
   CU_TRY(cudaGetLastError());
+  const char* dbg_steps = getenv("BOFI_DEBUG_MAX_BOUND_STEPS");   // timing experiments only (results are then wrong)
+  const int nsteps = dbg_steps ? std::min(L, atoi(dbg_steps)) : L;
   auto enqueue_bounding = [&](cudaStream_t bs) -> int {
-    for (int i = 0; i < L; ++i) {
+    for (int i = 0; i < nsteps; ++i) {
       if (e->bound_fast) RC_TRY(bounding_step_fast<T>(e, bs, rows, sn, i));
       else RC_TRY(bounding_step<T>(e, bs, rows, sn, i, 0));
     }
@@ -1047,6 +1049,37 @@ int bofi_get_profile(bofi_handle_t e, void* stream, int32_t* launches, double* m
     bytes[r.cls] += r.bytes;
   }
   if (df) fclose(df);
+  return BOFI_OK;
+}
+
+int bofi_get_profile_top_gemm(bofi_handle_t e, void* stream, int32_t* mnk, int32_t* launches, double* ms, double* flops) {
+  if (!e || !mnk || !launches || !ms || !flops) return fail(BOFI_ERR_INVALID, "null argument");
+  CU_TRY(cudaSetDevice(e->device));
+  CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  struct Acc { int n = 0; double ms = 0, fl = 0; };
+  std::unordered_map<unsigned long long, Acc> by_shape;
+  for (ProfRec& r : e->recs) {
+    if (r.cls != PC_GEMM_TC) continue;
+    float t = 0.f;
+    CU_TRY(cudaEventElapsedTime(&t, r.a, r.b));
+    Acc& a = by_shape[((unsigned long long)r.d0 << 40) | ((unsigned long long)r.d1 << 20) | (unsigned long long)r.d2];
+    a.n++;
+    a.ms += t;
+    a.fl += r.flops;
+  }
+  *launches = 0;
+  *ms = *flops = 0.0;
+  mnk[0] = mnk[1] = mnk[2] = 0;
+  for (auto& kv : by_shape) {
+    if (kv.second.ms > *ms) {
+      *ms = kv.second.ms;
+      *flops = kv.second.fl;
+      *launches = kv.second.n;
+      mnk[0] = (int)(kv.first >> 40);
+      mnk[1] = (int)((kv.first >> 20) & 0xFFFFF);
+      mnk[2] = (int)(kv.first & 0xFFFFF);
+    }
+  }
   return BOFI_OK;
 }
 

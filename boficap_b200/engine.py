@@ -124,6 +124,12 @@ class BofiEngine:
             _lib.check(self.lib.bofi_get_profile(self.handle, self._stream(), launches, ms, fl, by))
         return {c: dict(launches=launches[i], ms=ms[i], flops=fl[i], bytes=by[i]) for i, c in enumerate(self.PROFILE_CLASSES)}
 
+    def get_profile_top_gemm(self):
+        mnk, n, ms, fl = (C.c_int32 * 3)(), C.c_int32(), C.c_double(), C.c_double()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bofi_get_profile_top_gemm(self.handle, self._stream(), mnk, C.byref(n), C.byref(ms), C.byref(fl)))
+        return dict(M=mnk[0], N=mnk[1], K=mnk[2], launches=n.value, ms=ms.value, flops=fl.value)
+
     def workspace_bytes(self, B, R, sample_n=1):
         return int(self.lib.bofi_workspace_bytes(self.handle, B, R, sample_n))
 

@@ -122,6 +122,9 @@ int bofi_get_decode_info(bofi_handle_t h, void* stream, bofi_decode_info_t* out)
 #define BOFI_PROFILE_CLASSES 6
 int bofi_set_profiling(bofi_handle_t h, int32_t enable);
 int bofi_get_profile(bofi_handle_t h, void* stream, int32_t* launches, double* ms, double* flops, double* bytes);
+/* The (M, N, K) of the tcgen05 GEMM shape with the largest summed duration among the recorded launches
+ * (mnk[3]), with its launch count, milliseconds and 2*M*N*K flops summed over those launches. */
+int bofi_get_profile_top_gemm(bofi_handle_t h, void* stream, int32_t* mnk, int32_t* launches, double* ms, double* flops);
 
 /* ---- unit entry points (used by the parity tests to pin individual kernels) ------------------- */
 /* LayerNorm of TransformerModel.py:1338-1349 on rows x d_model fp32 (dev pointers). */
