@@ -41,49 +41,56 @@ def useful_flops_per_caption(R, S, V=9491, n_enc=6, n_dec=6, d=512, dff=2048, L=
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed regions (NVML, every 5 ms; B200_PROFILING.md clocks line)."""
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.bits, self.mx, self.power = index, [], 0, 0, 0.0
+        self.h = None
+        self._run = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.h = None
+
+    def _sample(self):
+        try:
+            self.sm.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            self.bits |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            self.power = max(self.power, self.nv.nvmlDeviceGetPowerUsage(self.h) / 1e3)
+        except Exception:
+            pass
+
+    def _loop(self):
+        while self._run:
+            self._sample()
+            time.sleep(0.005)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+        if self.h is None:
+            return
+        self._run = True
+        self.t = threading.Thread(target=self._loop, daemon=True)
+        self.t.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def pause(self):
+        if self.h is None or not self._run:
+            return
+        self._run = False
+        self.t.join()
 
     def stop(self):
-        if not self.proc:
+        self.pause()
+        if self.h is None or not self.sm:
             return None
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], 0, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                pass
-        if not sm:
-            return None
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": float(sm[len(sm) // 2]), "sm_min_mhz": float(sm[0]), "sm_max_mhz": float(self.mx),
+                "reasons": [n for b, n in self.REASONS if self.bits & b], "samples": len(sm), "power_w_max": round(self.power, 1)}
 
 
 def measured_peaks():
@@ -114,7 +121,7 @@ def cpu_reference_run(steps, warmup, cfg, sd, R, mode, images=CPU_SAMPLE_IMAGES)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="images per GPU per step")
@@ -125,6 +132,7 @@ def main():
     ap.add_argument("--calib", default="s_real")
     ap.add_argument("--no-logprobs", action="store_true", help="skip materialising the [B,20,V] log-prob tensor")
     ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--depth", type=int, default=2, help="batches in flight (engine handles x streams, boficap_b200/pipeline.py)")
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", 0))
@@ -161,10 +169,12 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from boficap_b200.engine import BofiEngine
+    from boficap_b200.pipeline import BofiPipeline
 
     sd = synth.synth_state_dict(cfg, 0, a.calib)
-    eng = BofiEngine(cfg, local_rank, a.precision).load_state_dict(sd)
+    pipe = BofiPipeline(cfg, sd, local_rank, a.precision, depth=max(1, a.depth))
+    eng = pipe.engines[0]
+    config["in_flight"] = "%d batches (one engine handle + stream each, round robin)" % pipe.depth
     B, R = a.batch, a.regions
     fc, att_host, masks = synth.synth_inputs(B, R, seed=1 + rank, adaptive=a.adaptive)
     att_host = att_host.pin_memory()
@@ -174,6 +184,7 @@ def main():
     if a.adaptive:
         config["regions"] = "adaptive 10..%d (mean %.1f), prefix masks" % (R, float(len_host.float().mean()))
     want_lp = not a.no_logprobs
+    main = torch.cuda.current_stream()
 
     def step():
         eng.encode(att, att_len)
@@ -208,8 +219,19 @@ def main():
             len_host[[j, B - 1]] = len_host[[B - 1, j]]
             att_len.copy_(len_host)
         config["last_image"] = "swapped with image %d so that the fill window is non-empty" % j
-    for _ in range(a.warmup):
-        out = step()
+    out = step()
+    torch.cuda.synchronize()
+    ref_seq = out[0].clone()
+
+    def run_device(n):
+        """n whole decodes, round robin over the in-flight slots; returns the tickets."""
+        pipe.fork_from(main)
+        ts = [pipe.submit_device(att, att_len, a.mode, 1, 1, want_lp) for _ in range(n)]
+        pipe.join_into(main)
+        return ts
+
+    for t in run_device(max(a.warmup, 2 * pipe.depth)):     # every slot: eager run, graph capture, replay
+        t.wait()
     torch.cuda.synchronize()
     info = eng.decode_info()
     launches_per_step = info["kernel_launches"]
@@ -219,26 +241,43 @@ def main():
         sampler.start()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(a.steps):
-        out = step()
-    ev1.record()
+    ev0.record(main)
+    tickets = run_device(a.steps)
+    ev1.record(main)
     barrier()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
+    sampler.pause()
+    out = tickets[-1].out
+    for t in tickets[-pipe.depth:]:                          # every slot reproduces the stand-alone decode
+        assert torch.equal(t.out[0], ref_seq), "pipelined decode differs from the stand-alone decode"
+    del tickets
 
-    # ---- e2e: the host-buffer entry point (H2D of the features and D2H of captions + boxes inside the timed region)
-    host_out = eng.sample_host(att_host, len_host, a.mode, 1, 1, want_logprobs=False)
+    # ---- e2e: the host-buffer entry point (H2D of the features and D2H of captions + boxes inside the timed region),
+    # pinned host input, `depth` batches in flight through bofi_sample_host_async
+    def run_host(n):
+        pipe.fork_from(main)
+        ts = [pipe.submit_host(att_host, len_host, a.mode, 1, 1) for _ in range(n)]
+        pipe.join_into(main)
+        return ts
+
+    for t in run_host(2 * pipe.depth):
+        host_out = t.wait()
     barrier()
-    t0 = time.perf_counter()
+    if rank == 0:
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(a.steps):
-        eng.sample_host(att_host, len_host, a.mode, 1, 1, out=host_out)
-    e1.record()
+    t0 = time.perf_counter()
+    e0.record(main)
+    tickets = run_host(a.steps)
+    e1.record(main)
+    for t in tickets:
+        host_out = t.wait()                                  # results are in host memory here
+    wall_e2e = (time.perf_counter() - t0) * 1e3
     barrier()
-    ms_e2e = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3 * 0.0)
-    h2d = att_host.numel() * 4
+    ms_e2e = max(e0.elapsed_time(e1), wall_e2e)              # device span vs host wall clock until the last result landed
+    clocks = sampler.stop() if rank == 0 else None
+    assert torch.equal(host_out["seq"], ref_seq.cpu()), "host-path captions differ from the device path"
+    h2d = att_host.numel() * 4 + (len_host.numel() * 4 if len_host is not None else 0)
     d2h = sum(host_out[k].numel() * host_out[k].element_size() for k in ("seq", "pnum", "plen", "psyn"))
 
     if dist is not None:
@@ -267,15 +306,19 @@ def main():
     gemm_tflops = g["flops"] / (g["ms"] / 1e3) / 1e12 if g["ms"] > 0 else 0.0
     peak = sustained if a.precision == "bf16" else 75.0
     total_ms = sum(v["ms"] for v in prof.values())
-    if top and top["ms"] > 0:
-        # dominant kernel = the tcgen05 GEMM on the shape that takes the most time in a step; algorithmic flops per
-        # launch = 2*M*N*K, duration = CUDA events around each of its launches, averaged
-        achieved = top["flops"] / (top["ms"] / 1e3) / 1e12
-        kname = "gemm_tc_kernel (tcgen05) M=%d N=%d K=%d" % (top["M"], top["N"], top["K"])
-        # ncu --set full capture of this shape (profiles/r01_gemm_ffn_ncu_summary.txt): dram read + write per launch
-        traffic = 133.0e6 if (top["M"], top["N"], top["K"]) == (36864, 2048, 512) else None
-        dom = {"launches_per_step": top["launches"], "us_per_launch": top["ms"] / top["launches"] * 1e3,
-               "gflop_per_launch": top["flops"] / top["launches"] / 1e9, "share_of_step": top["ms"] / total_ms}
+    if a.precision == "bf16" and g["ms"] > 0:
+        # dominant kernel = gemm_tc_kernel (tcgen05): algorithmic flops = sum of 2*M*N*K over its launches in one
+        # step, duration = sum of the CUDA-event durations around each launch (library-side, launching stream)
+        achieved, kname = gemm_tflops, "gemm_tc_kernel (tcgen05), all %d launches of a step" % g["launches"]
+        # ncu --set full capture of the FFN1 shape (profiles/r01_gemm_ffn_ncu_summary.txt): dram read + write per launch
+        traffic = 133.0e6
+        dom = {"launches_per_step": g["launches"], "us_per_launch": g["ms"] / g["launches"] * 1e3,
+               "gflop_per_launch": g["flops"] / g["launches"] / 1e9, "share_of_step": g["ms"] / total_ms,
+               "traffic_note": "traffic = ncu dram bytes of one M=36864 N=2048 K=512 launch (algorithmic 189 MB)"}
+        if top and top["ms"] > 0:
+            dom["slowest_shape"] = {"M": top["M"], "N": top["N"], "K": top["K"], "launches": top["launches"],
+                                    "us_per_launch": top["ms"] / top["launches"] * 1e3,
+                                    "tflops": top["flops"] / (top["ms"] / 1e3) / 1e12}
     else:
         achieved, kname, traffic = gemm_tflops, "gemm_simt_kernel (FFMA), all launches", None
         dom = {"launches_per_step": g["launches"], "share_of_step": g["ms"] / total_ms if total_ms else None}
@@ -302,7 +345,8 @@ def main():
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": a.precision, "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": "captions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / a.steps, "api": "bofi_sample_host (pinned host buffers)"},
+                    "ms_per_step": ms_e2e / a.steps,
+                    "api": "bofi_sample_host_async, pinned host buffers, %d batches in flight" % pipe.depth},
             "gpu_launches": launches_per_step * a.steps, "bounding_steps": S, "fill_width": info["fill_width"],
             "nan_batch": info["nan_batch"], "mean_caption_tokens": float(out[3].sum(1).float().mean()), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line))

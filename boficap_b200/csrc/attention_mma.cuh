@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(128)
 attention_mma_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restrict__ K, const bf16* __restrict__ V, int ldkv,
                      bf16* __restrict__ O, int ldo, int Tq, int Tk, const int* __restrict__ vis, int vis_bs, int vis_qs,
                      int vis_div, int kv_div, float scale, const int* live_rows) {
+  pdl_enter();
   if (step_is_dead(live_rows)) return;
   extern __shared__ __align__(16) uint8_t att_smem[];
   constexpr int TKP = KT * 16;
@@ -169,8 +170,10 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 attention_row_kernel(const T* __restrict__ Q, int ldq, const T* __restrict__ K, const T* __restrict__ V, int ldkv,
                      T* __restrict__ O, int ldo, int Tk, const int* __restrict__ vis, int vis_div, int kv_div, float scale,
-                     const int* live_rows) {
+                     const int* live_rows, const int* __restrict__ finished) {
+  pdl_enter();
   if (step_is_dead(live_rows)) return;
+  if (finished && finished[blockIdx.x]) return;
   __shared__ float qs[8][kHeadDim];
   __shared__ float ps[8][kMaxKeys];
   const int b = blockIdx.x, head = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -254,12 +257,14 @@ constexpr int kRowsPerCta = 4;
 __global__ void __launch_bounds__(kRowsPerCta * 256)
 attention_row_bf16_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restrict__ K, const bf16* __restrict__ V, int ldkv,
                           bf16* __restrict__ O, int ldo, int nb, int Tk, const int* __restrict__ vis, int vis_div, int kv_div,
-                          float scale, const int* live_rows) {
+                          float scale, const int* live_rows, const int* __restrict__ finished) {
+  pdl_enter();
   if (step_is_dead(live_rows)) return;
   __shared__ float ps[kRowsPerCta * 8][kMaxKeys];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * kRowsPerCta + (warp >> 3), head = warp & 7;
   if (b >= nb) return;
+  if (finished && finished[b]) return;     // bounding step: finished rows are ignored by the head
   const size_t kvrow0 = (size_t)(b / kv_div) * Tk;
   int nvis = vis ? vis[b / vis_div] : Tk;
   nvis = min(nvis, Tk);

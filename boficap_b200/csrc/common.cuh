@@ -50,6 +50,36 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Programmatic dependent launch (every kernel of the path is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization): let the next kernel's CTAs be scheduled as soon as
+// this grid has started, then block until everything this kernel depends on has completed and is visible.
+// EVERY kernel must execute pdl_wait() before its first global access (also before an early return):
+// completion of a grid must imply completion of its predecessors.
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_launch(); pdl_wait(); }
+
+// Host side: every kernel of the library goes through launch_k, which attaches the programmatic-dependent-launch
+// attribute (BOFI_PDL=0 turns it off).  Works in eager streams and under stream capture (programmatic graph edges).
+inline bool& pdl_enabled() {
+  static bool on = true;
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // Work of a bounding step is skipped once every row has finished (device-side `break` of
 // TransformerModel.py:1869-1870): kernels of the step read the live-row counter first.
 __device__ __forceinline__ bool step_is_dead(const int* live_rows) {

@@ -262,7 +262,7 @@ static int layernorm(bofi_engine* e, cudaStream_t s, const float* x, size_t in_s
                      size_t out_stride, int rows, float* f32_copy, const int* live) {
   if (rows <= 0) return BOFI_OK;
   ProfScope prof(e, s, PC_LAYERNORM, 8.0 * rows * kD, (double)rows * kD * (4 + sizeof(TOut) + (f32_copy ? 4 : 0)), rows);
-  layernorm_kernel<TOut><<<ceil_div(rows, 8), 256, 0, s>>>(x, in_stride, n.a, n.b, out, out_stride, rows, f32_copy, live);
+  launch_k(layernorm_kernel<TOut>, ceil_div(rows, 8), 256, 0, s, x, in_stride, n.a, n.b, out, out_stride, rows, f32_copy, live);
   CU_TRY(cudaGetLastError());
   return BOFI_OK;
 }
@@ -277,14 +277,14 @@ static cudaError_t launch_attention_mma(cudaStream_t s, dim3 grid, size_t smem, 
     if (err != cudaSuccess) return err;
     configured = smem;
   }
-  attention_mma_kernel<KT><<<grid, 128, smem, s>>>(Q, ldq, K, V, ldkv, O, ldo, Tq, Tk, vis, vis_bs, vis_qs, vis_div, kv_div, scale, live);
+  launch_k(attention_mma_kernel<KT>, grid, 128, smem, s, Q, ldq, K, V, ldkv, O, ldo, Tq, Tk, vis, vis_bs, vis_qs, vis_div, kv_div, scale, live);
   return cudaGetLastError();
 }
 
 template <typename T>
 static int attention(bofi_engine* e, cudaStream_t s, const T* Q, int ldq, const T* K, const T* V, int ldkv, T* O, int ldo,
                      int nb, int Tq, int Tk, const int* vis, int vis_bs, int vis_qs, int vis_div, int kv_div,
-                     const int* live) {
+                     const int* live, const int* finished = nullptr) {
   if (nb <= 0) return BOFI_OK;
   if (Tk > kMaxKeys || Tq > kMaxKeys) return fail(BOFI_ERR_INVALID, "attention over %d x %d (max %d)", Tq, Tk, kMaxKeys);
   const float scale = 1.0f / sqrtf((float)kHeadDim);
@@ -292,10 +292,10 @@ static int attention(bofi_engine* e, cudaStream_t s, const T* Q, int ldq, const 
                  nb, Tq, Tk);
   if (Tq == 1 && !e->attn_simt_only) {
     if constexpr (std::is_same<T, bf16>::value)
-      attention_row_bf16_kernel<<<ceil_div(nb, kRowsPerCta), kRowsPerCta * 256, 0, s>>>(Q, ldq, K, V, ldkv, O, ldo, nb, Tk, vis, vis_div,
-                                                                                       kv_div, scale, live);
+      launch_k(attention_row_bf16_kernel, ceil_div(nb, kRowsPerCta), kRowsPerCta * 256, 0, s, Q, ldq, K, V, ldkv, O, ldo, nb, Tk, vis, vis_div,
+               kv_div, scale, live, finished);
     else
-      attention_row_kernel<T><<<nb, 256, 0, s>>>(Q, ldq, K, V, ldkv, O, ldo, Tk, vis, vis_div, kv_div, scale, live);
+      launch_k(attention_row_kernel<T>, nb, 256, 0, s, Q, ldq, K, V, ldkv, O, ldo, Tk, vis, vis_div, kv_div, scale, live, finished);
     CU_TRY(cudaGetLastError());
     return BOFI_OK;
   }
@@ -323,7 +323,7 @@ static int attention(bofi_engine* e, cudaStream_t s, const T* Q, int ldq, const 
     configured = attention_smem_bytes(kMaxKeys);
   }
   dim3 grid(e->cfg.heads, nb);
-  attention_kernel<T><<<grid, 128, smem, s>>>(Q, ldq, K, V, ldkv, O, ldo, Tq, Tk, vis, vis_bs, vis_qs, vis_div, kv_div, scale, live);
+  launch_k(attention_kernel<T>, grid, 128, smem, s, Q, ldq, K, V, ldkv, O, ldo, Tq, Tk, vis, vis_bs, vis_qs, vis_div, kv_div, scale, live);
   CU_TRY(cudaGetLastError());
   return BOFI_OK;
 }
@@ -381,7 +381,7 @@ static int pack_rows(bofi_engine* e, cudaStream_t s, const std::vector<const flo
     e->packed.emplace_back();
     DevBuf& b16 = e->packed.back();
     RC_TRY(b16.reserve(total * sizeof(bf16)));
-    cast_kernel<bf16><<<ceil_div(total / 4, 256), 256, 0, s>>>(*out32, b16.as<bf16>(), (size_t)(total / 4));
+    launch_k(cast_kernel<bf16>, ceil_div(total / 4, 256), 256, 0, s, *out32, b16.as<bf16>(), (size_t)(total / 4));
     CU_TRY(cudaGetLastError());
     *out16 = b16.as<bf16>();
   }
@@ -500,7 +500,7 @@ static int encode_impl(bofi_engine* e, cudaStream_t s, const float* att, const i
     const size_t n4 = (size_t)M * F / 4;
     {
       ProfScope prof(e, s, PC_OTHER, 0.0, (double)M * F * 6.0);
-      cast_kernel<bf16><<<(int)std::min<size_t>((n4 + 255) / 256, 148 * 16), 256, 0, s>>>(att, e->attT.as<bf16>(), n4);
+      launch_k(cast_kernel<bf16>, (int)std::min<size_t>((n4 + 255) / 256, 148 * 16), 256, 0, s, att, e->attT.as<bf16>(), n4);
     }
     CU_TRY(cudaGetLastError());
     a_in = e->attT.as<bf16>();
@@ -517,7 +517,7 @@ static int encode_impl(bofi_engine* e, cudaStream_t s, const float* att, const i
     len_dev = e->attlen.as<int>();
     {
       ProfScope prof(e, s, PC_OTHER, 0.0, 0.0);
-      zero_padded_rows_kernel<<<ceil_div(M, 8), 256, 0, s>>>(x, len_dev, B, R);
+      launch_k(zero_padded_rows_kernel, ceil_div(M, 8), 256, 0, s, x, len_dev, B, R);
     }
     CU_TRY(cudaGetLastError());
   }
@@ -545,7 +545,7 @@ static int head_step(bofi_engine* e, cudaStream_t s, const float* x, size_t x_st
     configured = true;
   }
   ProfScope prof(e, s, PC_OTHER, 2.0 * rows * 200 * kD, 0.0, rows, 200, kD);
-  bound_head_kernel<<<ceil_div(rows, kHeadRows), 1024, smem, s>>>(x, x_stride, e->lp_norm.a, e->lp_norm.b, e->head1t.as<float>(), e->head1.b, 100,
+  launch_k(bound_head_kernel, ceil_div(rows, kHeadRows), 1024, smem, s, x, x_stride, e->lp_norm.a, e->lp_norm.b, e->head1t.as<float>(), e->head1.b, 100,
                                                               e->w_len2, e->b_len2, e->w_syn2, e->b_syn2, 20, 10, e->st, rows, e->Lb, e->L,
                                                               step_col, step_no, 4, 6, saic);
   CU_TRY(cudaGetLastError());
@@ -564,9 +564,9 @@ static int bounding_step(bofi_engine* e, cudaStream_t s, int rows, int sn, int s
   {
     ProfScope prof(e, s, PC_OTHER, 0.0, 0.0);
     if (!saic) {
-      gather_table_kernel<<<ceil_div(rows * Tb, 8), 256, 0, s>>>(e->bound_in.as<float>(), Lb, e->st.ext, Lb, 0, x, rows * Tb, Tb, live);
+      launch_k(gather_table_kernel, ceil_div(rows * Tb, 8), 256, 0, s, e->bound_in.as<float>(), Lb, e->st.ext, Lb, 0, x, rows * Tb, Tb, live);
     } else {
-      embed_words_kernel<<<ceil_div(rows * Tb, 8), 256, 0, s>>>(W(e, "model.tgt_embed.lut.weight"), nullptr, W(e, "model.pos_embed.pe"),
+      launch_k(embed_words_kernel, ceil_div(rows * Tb, 8), 256, 0, s, W(e, "model.tgt_embed.lut.weight"), nullptr, W(e, "model.pos_embed.pe"),
                                                                 e->st.ext, nullptr, Lb, 0, sqrtf((float)kD), x, rows * Tb, Tb, live);
     }
   }
@@ -606,14 +606,15 @@ static int bounding_step_fast(bofi_engine* e, cudaStream_t s, int rows, int sn, 
   const float* x0 = e->bound_in.as<float>() + (size_t)q_row * kD;     // the constant [LEN] input row
   {
     ProfScope prof(e, s, PC_ATTENTION, 4.0 * rows * Lb * kD, 0.0);
-    bound_self_attn_kernel<T><<<rows, 256, 0, s>>>(e->tab_qkv.as<T>(), Lb, q_row, e->st.ext, e->st.last, ao,
-                                                   1.0f / sqrtf((float)kHeadDim), live);
+    launch_k(bound_self_attn_kernel<T>, rows, 256, 0, s, e->tab_qkv.as<T>(), Lb, q_row, e->st.ext, e->st.last, ao,
+             1.0f / sqrtf((float)kHeadDim), live, e->st.finished);
   }
   CU_TRY(cudaGetLastError());
   RC_TRY((linear<T, float>(e, s, ao, kD, ly.sa.o, x0, 0, x, kD, rows, 0, live)));          // residual = x0 broadcast
   RC_TRY(layernorm<T>(e, s, x, kD, ly.ln[1], y, kD, rows, nullptr, live));
   RC_TRY((linear<T, T>(e, s, y, kD, ly.ca.q, nullptr, 0, q, kD, rows, 0, live)));
-  RC_TRY(attention<T>(e, s, q, kD, e->kv[0].as<T>(), e->kv[0].as<T>() + kD, 2 * kD, ao, kD, rows, 1, e->R, mem_len, 1, 0, sn, sn, live));
+  RC_TRY(attention<T>(e, s, q, kD, e->kv[0].as<T>(), e->kv[0].as<T>() + kD, 2 * kD, ao, kD, rows, 1, e->R, mem_len, 1, 0, sn, sn, live,
+                      e->st.finished));
   RC_TRY((linear<T, float>(e, s, ao, kD, ly.ca.o, x, kD, x, kD, rows, 0, live)));
   RC_TRY(layernorm<T>(e, s, x, kD, ly.ln[2], y, kD, rows, nullptr, live));
   RC_TRY((linear<T, T>(e, s, y, kD, ly.w1, nullptr, 0, ffh, c.d_ff, rows, 1, live)));
@@ -650,7 +651,7 @@ static int decode_naic(bofi_engine* e, cudaStream_t s, int sn, int output_logsof
 
   {
     ProfScope prof(e, s, PC_OTHER, 0.0, 0.0);
-    init_state_kernel<<<ceil_div(rows, 128), 128, 0, s>>>(e->st, rows, Lb, L, c.len_idx, c.bos_idx, 0);
+    launch_k(init_state_kernel, ceil_div(rows, 128), 128, 0, s, e->st, rows, Lb, L, c.len_idx, c.bos_idx, 0);
   }
   CU_TRY(cudaGetLastError());
   const char* dbg_steps = getenv("BOFI_DEBUG_MAX_BOUND_STEPS");   // timing experiments only (results are then wrong)
@@ -709,13 +710,13 @@ static int decode_naic(bofi_engine* e, cudaStream_t s, int sn, int output_logsof
   // filling step (decode_NA, :570-587): all L slots of every row in parallel
   {
     ProfScope prof(e, s, PC_OTHER, 0.0, 0.0);
-    fill_window_kernel<<<ceil_div(rows * L, 256), 256, 0, s>>>(e->st, rows, L);
+    launch_k(fill_window_kernel, ceil_div(rows * L, 256), 256, 0, s, e->st, rows, L);
   }
   CU_TRY(cudaGetLastError());
   float* x = e->x.as<float>();
   {
     ProfScope prof(e, s, PC_OTHER, 0.0, 0.0);
-    gather_table_kernel<<<ceil_div(rows * L, 8), 256, 0, s>>>(e->fill_in.as<float>(), L, e->st.ext, Lb, 1, x, rows * L, L, nullptr);
+    launch_k(gather_table_kernel, ceil_div(rows * L, 8), 256, 0, s, e->fill_in.as<float>(), L, e->st.ext, Lb, 1, x, rows * L, L, nullptr);
   }
   CU_TRY(cudaGetLastError());
   for (int l = 0; l < c.n_dec; ++l)
@@ -724,13 +725,13 @@ static int decode_naic(bofi_engine* e, cudaStream_t s, int sn, int output_logsof
   RC_TRY((linear<T, float>(e, s, e->y.as<T>(), kD, e->generator, nullptr, 0, e->logits.as<float>(), e->Vpad, rows * L, 0, nullptr)));
   {
     ProfScope prof(e, s, PC_VOCAB, 0.0, 0.0);
-    vocab_epilogue_kernel<<<rows * L, kVocabThreads, 0, s>>>(e->logits.as<float>(), e->Vpad, e->V, logprobs, seq, e->st.last, -1, L,
+    launch_k(vocab_epilogue_kernel, rows * L, kVocabThreads, 0, s, e->logits.as<float>(), e->Vpad, e->V, logprobs, seq, e->st.last, -1, L,
                                                  output_logsoftmax, nullptr);
   }
   CU_TRY(cudaGetLastError());
   {
     ProfScope prof(e, s, PC_OTHER, 0.0, 0.0);
-    export_boxes_kernel<<<ceil_div(rows * L, 256), 256, 0, s>>>(e->st, rows, Lb, L, 0, phrase_num, phrase_length, phrase_syn);
+    launch_k(export_boxes_kernel, ceil_div(rows * L, 256), 256, 0, s, e->st, rows, Lb, L, 0, phrase_num, phrase_length, phrase_syn);
   }
   CU_TRY(cudaGetLastError());
   return BOFI_OK;
@@ -763,15 +764,15 @@ static int decode_saic(bofi_engine* e, cudaStream_t s, int sn, int output_logsof
   }
   for (int l = 0; l < c.n_dec; ++l) RC_TRY(project_memory_kv<T>(e, s, e->dec[l].ca.kv, e->kv[nb_layers + l]));
   if (logprobs) CU_TRY(cudaMemsetAsync(logprobs, 0, (size_t)rows * L * e->V * sizeof(float), s));   // seq_logprobs = zeros (:1883)
-  LAUNCH_OTHER((init_state_kernel<<<ceil_div(rows, 128), 128, 0, s>>>(e->st, rows, Lb, L, c.len_idx, c.bos_idx, 1)));
+  LAUNCH_OTHER((launch_k(init_state_kernel, ceil_div(rows, 128), 128, 0, s, e->st, rows, Lb, L, c.len_idx, c.bos_idx, 1)));
   const int* live = e->st.counters + 4;
   float* x = e->x.as<float>();
   const float sqrt_d = sqrtf((float)kD);
   for (int i = 1; i <= L; ++i) {
-    LAUNCH_OTHER((saic_snapshot_kernel<<<1, 1, 0, s>>>(e->st)));
+    LAUNCH_OTHER((launch_k(saic_snapshot_kernel, 1, 1, 0, s, e->st)));
     RC_TRY(bounding_step<T>(e, s, rows, sn, i, 1));
-    LAUNCH_OTHER((saic_prepare_kernel<<<ceil_div(rows, 128), 128, 0, s>>>(e->st, rows, Lb, L, i)));
-    LAUNCH_OTHER((embed_words_kernel<<<ceil_div(rows * L, 8), 256, 0, s>>>(
+    LAUNCH_OTHER((launch_k(saic_prepare_kernel, ceil_div(rows, 128), 128, 0, s, e->st, rows, Lb, L, i)));
+    LAUNCH_OTHER((launch_k(embed_words_kernel, ceil_div(rows * L, 8), 256, 0, s, 
         W(e, "model.tgt_embed.lut.weight"), W(e, "model.syn_embed.lut.weight"), W(e, "model.pos_embed.pe"), e->st.ext_word,
         e->st.ext_syn, Lb, 1, sqrt_d, x, rows * L, L, live)));
     for (int l = 0; l < c.n_dec; ++l)
@@ -780,20 +781,20 @@ static int decode_saic(bofi_engine* e, cudaStream_t s, int sn, int output_logsof
     RC_TRY((linear<T, float>(e, s, e->y.as<T>(), kD, e->generator, nullptr, 0, e->logits.as<float>(), e->Vpad, rows * L, 0, live)));
     {
       ProfScope prof(e, s, PC_VOCAB, 0.0, 0.0);
-      vocab_stats_kernel<<<rows * L, 256, 0, s>>>(e->logits.as<float>(), e->Vpad, e->V, e->tok.as<int>(), e->sa_mx.as<float>(),
+      launch_k(vocab_stats_kernel, rows * L, 256, 0, s, e->logits.as<float>(), e->Vpad, e->V, e->tok.as<int>(), e->sa_mx.as<float>(),
                                                  e->sa_lse.as<float>(), e->st);
     }
     CU_TRY(cudaGetLastError());
     if (logprobs) {
       ProfScope prof(e, s, PC_VOCAB, 0.0, 0.0);
-      saic_write_logp_kernel<<<rows * L, 256, 0, s>>>(e->logits.as<float>(), e->Vpad, e->V, e->sa_mx.as<float>(), e->sa_lse.as<float>(),
+      launch_k(saic_write_logp_kernel, rows * L, 256, 0, s, e->logits.as<float>(), e->Vpad, e->V, e->sa_mx.as<float>(), e->sa_lse.as<float>(),
                                                      logprobs, e->st, L, output_logsoftmax);
     }
     CU_TRY(cudaGetLastError());
-    LAUNCH_OTHER((saic_advance_kernel<<<ceil_div(rows, 128), 128, 0, s>>>(e->tok.as<int>(), e->st, rows, Lb, L, i)));
+    LAUNCH_OTHER((launch_k(saic_advance_kernel, ceil_div(rows, 128), 128, 0, s, e->tok.as<int>(), e->st, rows, Lb, L, i)));
   }
-  LAUNCH_OTHER((export_seq_kernel<<<ceil_div(rows * L, 256), 256, 0, s>>>(e->st, rows, Lb, L, seq)));
-  LAUNCH_OTHER((export_boxes_kernel<<<ceil_div(rows * L, 256), 256, 0, s>>>(e->st, rows, Lb, L, 1, phrase_num, phrase_length, phrase_syn)));
+  LAUNCH_OTHER((launch_k(export_seq_kernel, ceil_div(rows * L, 256), 256, 0, s, e->st, rows, Lb, L, seq)));
+  LAUNCH_OTHER((launch_k(export_boxes_kernel, ceil_div(rows * L, 256), 256, 0, s, e->st, rows, Lb, L, 1, phrase_num, phrase_length, phrase_syn)));
   return BOFI_OK;
 }
 
@@ -835,6 +836,8 @@ int bofi_create(const bofi_config_t* cfg, int device, bofi_handle_t* out) {
   e->use_tc = !(g && strcmp(g, "simt") == 0);
   const char* gg = getenv("BOFI_GRAPH");
   e->use_graph = !(gg && strcmp(gg, "0") == 0);
+  const char* gp = getenv("BOFI_PDL");
+  if (gp) pdl_enabled() = strcmp(gp, "0") != 0;
   const char* ga = getenv("BOFI_ATTN");
   e->attn_simt_only = (ga && strcmp(ga, "simt") == 0);
   build_spec(e);
@@ -921,7 +924,7 @@ int bofi_finalize_weights(bofi_handle_t e, void* stream) {
     RC_TRY(rc);
   }
   RC_TRY(e->head1t.reserve((size_t)200 * kD * 4));
-  transpose_kernel<<<dim3(ceil_div(kD, 32), ceil_div(200, 32)), dim3(32, 8), 0, s>>>(e->head1.w32, e->head1t.as<float>(), 200, kD);
+  launch_k(transpose_kernel, dim3(ceil_div(kD, 32), ceil_div(200, 32)), dim3(32, 8), 0, s, e->head1.w32, e->head1t.as<float>(), 200, kD);
   CU_TRY(cudaGetLastError());
   e->w_len2 = W(e, lp + ".Length_classifier2.weight");
   e->b_len2 = W(e, lp + ".Length_classifier2.bias");
@@ -929,7 +932,7 @@ int bofi_finalize_weights(bofi_handle_t e, void* stream) {
   e->b_syn2 = W(e, lp + ".Syntactic_classifier2.bias");
   RC_TRY(e->bound_in.reserve((size_t)10 * e->Lb * kD * 4));
   RC_TRY(e->fill_in.reserve((size_t)10 * e->L * kD * 4));
-  build_tables_kernel<<<dim3(10, e->Lb), 128, 0, s>>>(W(e, "model.syn_embed.lut.weight"), W(e, "model.tgt_embed.lut.weight"),
+  launch_k(build_tables_kernel, dim3(10, e->Lb), 128, 0, s, W(e, "model.syn_embed.lut.weight"), W(e, "model.tgt_embed.lut.weight"),
                                                       W(e, "model.pos_embed.pe"), c.bos_idx, 10, e->Lb, e->L, sqrtf((float)kD),
                                                       e->bound_in.as<float>(), e->fill_in.as<float>());
   CU_TRY(cudaGetLastError());
@@ -980,9 +983,9 @@ int bofi_decode(bofi_handle_t e, void* stream, int32_t mode, int32_t sn, int32_t
                       : decode_naic<float>(e, s, sn, output_logsoftmax, (long long*)seq, logprobs, phrase_num, phrase_length, (long long*)phrase_syn);
 }
 
-int bofi_sample_host(bofi_handle_t e, void* stream, int32_t mode, int32_t sn, int32_t output_logsoftmax, const float* att_feats,
-                     const int32_t* att_len, int32_t B, int32_t R, int64_t* seq, float* logprobs, int32_t* phrase_num,
-                     int32_t* phrase_length, int64_t* phrase_syn) {
+int bofi_sample_host_async(bofi_handle_t e, void* stream, int32_t mode, int32_t sn, int32_t output_logsoftmax, const float* att_feats,
+                           const int32_t* att_len, int32_t B, int32_t R, int64_t* seq, float* logprobs, int32_t* phrase_num,
+                           int32_t* phrase_length, int64_t* phrase_syn) {
   if (!e || !att_feats || !seq || !phrase_num || !phrase_length || !phrase_syn) return fail(BOFI_ERR_INVALID, "null argument");
   if (B <= 0 || R <= 0 || sn < 1) return fail(BOFI_ERR_INVALID, "bad batch");
   CU_TRY(cudaSetDevice(e->device));
@@ -1005,7 +1008,15 @@ int bofi_sample_host(bofi_handle_t e, void* stream, int32_t mode, int32_t sn, in
   CU_TRY(cudaMemcpyAsync(phrase_length, e->h_plen.p, rows * L * 4, cudaMemcpyDeviceToHost, s));
   CU_TRY(cudaMemcpyAsync(phrase_syn, e->h_psyn.p, rows * L * 8, cudaMemcpyDeviceToHost, s));
   if (logprobs) CU_TRY(cudaMemcpyAsync(logprobs, e->h_logp.p, rows * L * (size_t)e->V * 4, cudaMemcpyDeviceToHost, s));
-  CU_TRY(cudaStreamSynchronize(s));
+  return BOFI_OK;
+}
+
+int bofi_sample_host(bofi_handle_t e, void* stream, int32_t mode, int32_t sn, int32_t output_logsoftmax, const float* att_feats,
+                     const int32_t* att_len, int32_t B, int32_t R, int64_t* seq, float* logprobs, int32_t* phrase_num,
+                     int32_t* phrase_length, int64_t* phrase_syn) {
+  RC_TRY(bofi_sample_host_async(e, stream, mode, sn, output_logsoftmax, att_feats, att_len, B, R, seq, logprobs, phrase_num,
+                                phrase_length, phrase_syn));
+  CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
   return BOFI_OK;
 }
 
@@ -1117,8 +1128,8 @@ int bofi_linear_f32(bofi_handle_t e, void* stream, const float* A, const float* 
   }
   RC_TRY(e->unit_a.reserve((size_t)M * K * 2));
   RC_TRY(e->unit_w.reserve((size_t)N * K * 2));
-  cast_kernel<bf16><<<ceil_div((size_t)M * K / 4, 256), 256, 0, s>>>(A, e->unit_a.as<bf16>(), (size_t)M * K / 4);
-  cast_kernel<bf16><<<ceil_div((size_t)N * K / 4, 256), 256, 0, s>>>(Wt, e->unit_w.as<bf16>(), (size_t)N * K / 4);
+  launch_k(cast_kernel<bf16>, ceil_div((size_t)M * K / 4, 256), 256, 0, s, A, e->unit_a.as<bf16>(), (size_t)M * K / 4);
+  launch_k(cast_kernel<bf16>, ceil_div((size_t)N * K / 4, 256), 256, 0, s, Wt, e->unit_w.as<bf16>(), (size_t)N * K / 4);
   CU_TRY(cudaGetLastError());
   l.w16 = e->unit_w.as<bf16>();
   return linear<bf16, float>(e, s, e->unit_a.as<bf16>(), K, l, residual, N, out, N, M, relu, nullptr);
@@ -1138,12 +1149,12 @@ int bofi_attention_f32(bofi_handle_t e, void* stream, const float* q, const floa
   bf16* qb = e->unit_a.as<bf16>();
   bf16* kb = qb + nq;
   bf16* vb = kb + nk;
-  cast_kernel<bf16><<<ceil_div(nq / 4, 256), 256, 0, s>>>(q, qb, nq / 4);
-  cast_kernel<bf16><<<ceil_div(nk / 4, 256), 256, 0, s>>>(k, kb, nk / 4);
-  cast_kernel<bf16><<<ceil_div(nk / 4, 256), 256, 0, s>>>(v, vb, nk / 4);
+  launch_k(cast_kernel<bf16>, ceil_div(nq / 4, 256), 256, 0, s, q, qb, nq / 4);
+  launch_k(cast_kernel<bf16>, ceil_div(nk / 4, 256), 256, 0, s, k, kb, nk / 4);
+  launch_k(cast_kernel<bf16>, ceil_div(nk / 4, 256), 256, 0, s, v, vb, nk / 4);
   CU_TRY(cudaGetLastError());
   RC_TRY(attention<bf16>(e, s, qb, kD, kb, vb, kD, e->unit_o.as<bf16>(), kD, B, Tq, Tk, vis, Tq, 1, 1, 1, nullptr));
-  widen_kernel<<<ceil_div(nq / 4, 256), 256, 0, s>>>(e->unit_o.as<bf16>(), out, nq / 4);
+  launch_k(widen_kernel, ceil_div(nq / 4, 256), 256, 0, s, e->unit_o.as<bf16>(), out, nq / 4);
   CU_TRY(cudaGetLastError());
   return BOFI_OK;
 }

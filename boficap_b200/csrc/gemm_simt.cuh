@@ -18,6 +18,7 @@ __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const TIn* __restrict__ A, int lda, const TIn* __restrict__ W, int ldw,
                  const float* __restrict__ bias, const float* residual, int ldr,
                  TOut* C, int ldc, int M, int N, int K, int relu, const int* live_rows) {
+  pdl_enter();
   if (step_is_dead(live_rows)) return;
   __shared__ __align__(16) float As[2][kSBK][kSBM + kSPad];
   __shared__ __align__(16) float Bs[2][kSBK][kSBN + kSPad];
@@ -107,7 +108,7 @@ inline cudaError_t gemm_simt(cudaStream_t s, const TIn* A, int lda, const TIn* W
   if (M <= 0 || N <= 0) return cudaSuccess;
   if (K % kSBK != 0 || lda % 4 != 0 || ldw % 4 != 0) return cudaErrorInvalidValue;
   dim3 grid((N + kSBN - 1) / kSBN, (M + kSBM - 1) / kSBM);
-  gemm_simt_kernel<TIn, TOut><<<grid, 256, 0, s>>>(A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, relu, live_rows);
+  launch_k(gemm_simt_kernel<TIn, TOut>, grid, 256, 0, s, A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, relu, live_rows);
   return cudaGetLastError();
 }
 

@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, const float* residual, int ldr,
                int M, int N, int K, int relu, const int* live_rows) {
-  if (step_is_dead(live_rows)) return;
+  pdl_launch();
   using L = SmemLayout<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -149,7 +149,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk = K / kBK;
   const int tiles_n = (N + BN - 1) / BN;
-  const int ntiles = ((M + kBM - 1) / kBM) * tiles_n;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -177,6 +176,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Everything above (barriers, TMEM, descriptor prefetch) overlaps the tail of the previous kernel; global
+  // memory is only touched after the programmatic-dependency wait.  A dead bounding step walks zero tiles.
+  pdl_wait();
+  const int ntiles = step_is_dead(live_rows) ? 0 : ((M + kBM - 1) / kBM) * tiles_n;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -397,7 +400,7 @@ inline cudaError_t launch(cudaStream_t s, const CUtensorMap& tmA, const CUtensor
   }
   const int ntiles = ((M + kBM - 1) / kBM) * ((N + BN - 1) / BN);
   const int grid = ntiles < num_sms() ? ntiles : num_sms();
-  gemm_tc_kernel<BN, STAGES, TOut, RELU, RESID><<<grid, kThreads, L::kTotal, s>>>(tmA, tmB, tmC, bias, residual, ldr, M, N, K, relu, live_rows);
+  launch_k(gemm_tc_kernel<BN, STAGES, TOut, RELU, RESID>, grid, kThreads, L::kTotal, s, tmA, tmB, tmC, bias, residual, ldr, M, N, K, relu, live_rows);
   return cudaGetLastError();
 }
 

@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, size_t in_stride, const float* __restrict__ a2,
                  const float* __restrict__ b2, TOut* __restrict__ out, size_t out_stride, int rows,
                  float* __restrict__ out_f32_copy, const int* live_rows) {
+  pdl_enter();
   if (step_is_dead(live_rows)) return;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(128)
 attention_kernel(const T* __restrict__ Q, int ldq, const T* __restrict__ K, const T* __restrict__ V, int ldkv,
                  T* __restrict__ O, int ldo, int Tq, int Tk, const int* __restrict__ vis, int vis_bs, int vis_qs,
                  int vis_div, int kv_div, float scale, const int* live_rows) {
+  pdl_enter();
   if (step_is_dead(live_rows)) return;
   extern __shared__ float smem[];
   float* Ks = smem;                         // [Tk][65]
@@ -145,8 +147,11 @@ attention_kernel(const T* __restrict__ Q, int ldq, const T* __restrict__ K, cons
 template <typename T>
 __global__ void __launch_bounds__(256)
 bound_self_attn_kernel(const T* __restrict__ qkv_tab, int Lb, int q_row, const int* __restrict__ ext,
-                       const int* __restrict__ last, T* __restrict__ O, float scale, const int* live_rows) {
+                       const int* __restrict__ last, T* __restrict__ O, float scale, const int* live_rows,
+                       const int* __restrict__ finished) {
+  pdl_enter();
   if (step_is_dead(live_rows)) return;
+  if (finished[blockIdx.x]) return;        // the head ignores finished rows; their activations may go stale
   __shared__ float qs[8][kHeadDim];
   __shared__ int rowid[32];
   const int b = blockIdx.x, head = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -205,6 +210,7 @@ inline size_t attention_smem_bytes(int Tk) {
 // fp32 -> T, 128-bit vectorised (n % 4 == 0)
 template <typename T>
 __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ in, T* __restrict__ out, size_t n4) {
+  pdl_enter();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n4; i += stride) store4(out + i * 4, load4(in + i * 4));
@@ -212,6 +218,7 @@ __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ in,
 
 // bf16 -> fp32 (unit entry points only)
 __global__ void __launch_bounds__(256) widen_kernel(const bf16* __restrict__ in, float* __restrict__ out, size_t n4) {
+  pdl_enter();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n4; i += stride) store4(out + i * 4, load4(in + i * 4));
@@ -219,6 +226,7 @@ __global__ void __launch_bounds__(256) widen_kernel(const bf16* __restrict__ in,
 
 // out[c][r] = in[r][c]  (in: [rows][cols])
 __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+  pdl_enter();
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -235,6 +243,7 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
 // pack_wrapper (AttModel.py:46-51): rows of padded regions come back as zeros.
 __global__ void __launch_bounds__(256)
 zero_padded_rows_kernel(float* __restrict__ x, const int* __restrict__ att_len, int B, int R) {
+  pdl_enter();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= B * R) return;
   const int b = row / R, r = row - b * R;
@@ -251,6 +260,7 @@ zero_padded_rows_kernel(float* __restrict__ x, const int* __restrict__ att_len, 
 __global__ void build_tables_kernel(const float* __restrict__ syn_lut, const float* __restrict__ tgt_lut,
                                     const float* __restrict__ pe, int bos, int n_syn, int Lb, int L,
                                     float sqrt_d, float* __restrict__ bound_in, float* __restrict__ fill_in) {
+  pdl_enter();
   const int s = blockIdx.x, p = blockIdx.y;
   for (int c = threadIdx.x; c < kD; c += blockDim.x) {
     const float se = syn_lut[s * kD + c] * sqrt_d;
@@ -263,6 +273,7 @@ __global__ void build_tables_kernel(const float* __restrict__ syn_lut, const flo
 __global__ void __launch_bounds__(256)
 gather_table_kernel(const float* __restrict__ table, int P, const int* __restrict__ ids, int ids_stride, int ids_off,
                     float* __restrict__ x, int rows, int T, const int* live_rows) {
+  pdl_enter();
   if (step_is_dead(live_rows)) return;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -279,6 +290,7 @@ __global__ void __launch_bounds__(256)
 embed_words_kernel(const float* __restrict__ word_lut, const float* __restrict__ syn_lut, const float* __restrict__ pe,
                    const int* __restrict__ word_ids, const int* __restrict__ syn_ids, int ids_stride, int ids_off,
                    float sqrt_d, float* __restrict__ x, int rows, int T, const int* live_rows) {
+  pdl_enter();
   if (step_is_dead(live_rows)) return;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -321,6 +333,7 @@ struct DecodeState {
 };
 
 __global__ void init_state_kernel(DecodeState st, int rows, int Lb, int L, int len_idx, int bos_idx, int saic) {
+  pdl_enter();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b == 0) { st.counters[0] = rows; st.counters[1] = 0; st.counters[2] = 0; st.counters[3] = 0; st.counters[4] = rows; st.counters[5] = 0; }
   if (b >= rows) return;
@@ -355,6 +368,7 @@ bound_head_kernel(const float* __restrict__ x, size_t x_stride, const float* __r
                   const float* __restrict__ w_len, const float* __restrict__ b_len,
                   const float* __restrict__ w_syn, const float* __restrict__ b_syn, int n_len, int n_syn,
                   DecodeState st, int rows, int Lb, int L, int step_col, int step_no, int syn_lo, int syn_hi, int saic) {
+  pdl_enter();
   if (st.counters[0] == 0) return;
   extern __shared__ float hsm[];
   float* h = hsm;                               // [8][512]  normalised [LEN] rows
@@ -495,6 +509,7 @@ bound_head_kernel(const float* __restrict__ x, size_t x_stride, const float* __r
 // NAIC fill window: every row uses w = last[rows-1] - 1 (the reference's stale loop index,
 // TransformerModel.py:1871-1873).  Also records w and the NaN-batch flag.
 __global__ void fill_window_kernel(DecodeState st, int rows, int L) {
+  pdl_enter();
   const int w = st.last[rows - 1] - 1;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) { st.counters[2] = w; st.counters[3] = (w <= 0) ? 1 : 0; }
@@ -526,6 +541,7 @@ __global__ void __launch_bounds__(kVocabThreads, 3)
 vocab_epilogue_kernel(const float* __restrict__ logits, int ldl, int V, float* __restrict__ logp_out,
                       long long* __restrict__ seq_out, const int* __restrict__ total_len, int total_off, int L,
                       int do_logsoftmax, int* __restrict__ tok_out_i32) {
+  pdl_enter();
   // The whole row lives in registers: logits are read from HBM exactly once (128-bit loads, all independent),
   // max / argmax / sum-exp are block reductions, and the log-probs are written once.
   __shared__ ArgMax s_am[kVocabThreads / 32];
@@ -615,12 +631,14 @@ vocab_epilogue_kernel(const float* __restrict__ logits, int ldl, int V, float* _
 // step: a row that finishes by clipping in this step still has its last phrase decoded (:1917-1922), so the
 // kernels of a step test the snapshot, not the running counter.  counters[5] is the "phrase nan!" flag.
 // ---------------------------------------------------------------------------------------------
-__global__ void saic_snapshot_kernel(DecodeState st) { st.counters[4] = st.counters[0]; }
+__global__ void saic_snapshot_kernel(DecodeState st) {
+  pdl_enter(); st.counters[4] = st.counters[0]; }
 
 // Decoder input of the phrase accepted at step i (:1928-1948): syn label + position-wise copy of the previous
 // phrase's words (last n words when n <= m, otherwise each word stretched ct or ct+1 times), and the
 // phrase-block-causal mask phrase_mask[p:, :p+n] = True in its prefix-count form.
 __global__ void saic_prepare_kernel(DecodeState st, int rows, int Lb, int L, int step) {
+  pdl_enter();
   if (st.counters[4] == 0) return;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= rows) return;
@@ -649,6 +667,7 @@ __global__ void saic_prepare_kernel(DecodeState st, int rows, int Lb, int L, int
 __global__ void __launch_bounds__(256)
 vocab_stats_kernel(const float* __restrict__ logits, int ldl, int V, int* __restrict__ tok, float* __restrict__ mx_out,
                    float* __restrict__ lse_out, DecodeState st) {
+  pdl_enter();
   if (st.counters[4] == 0) return;
   __shared__ ArgMax s_am[8];
   __shared__ float s_sum[8];
@@ -688,6 +707,7 @@ vocab_stats_kernel(const float* __restrict__ logits, int ldl, int V, int* __rest
 __global__ void __launch_bounds__(256)
 saic_write_logp_kernel(const float* __restrict__ logits, int ldl, int V, const float* __restrict__ mx, const float* __restrict__ lse,
                        float* __restrict__ logp_out, DecodeState st, int L, int do_logsoftmax) {
+  pdl_enter();
   if (st.counters[4] == 0 || st.counters[5] != 0) return;
   const int row = blockIdx.x, b = row / L, t = row - b * L;
   const int n = st.step_len[b], p = st.last[b];
@@ -704,6 +724,7 @@ saic_write_logp_kernel(const float* __restrict__ logits, int ldl, int V, const f
 
 // Commit of the step (:1968-1977): generated words into seq / the bounding-head input, len_mask, counters.
 __global__ void saic_advance_kernel(const int* __restrict__ tok, DecodeState st, int rows, int Lb, int L, int step) {
+  pdl_enter();
   if (st.counters[4] == 0) return;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (st.counters[5] != 0) {           // "phrase nan!": return the state as it is, no further steps
@@ -726,6 +747,7 @@ __global__ void saic_advance_kernel(const int* __restrict__ tok, DecodeState st,
 }
 
 __global__ void export_seq_kernel(DecodeState st, int rows, int Lb, int L, long long* __restrict__ seq) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * L) return;
   const int b = i / L, c = i - b * L;
@@ -736,6 +758,7 @@ __global__ void export_seq_kernel(DecodeState st, int rows, int Lb, int L, long 
 // col0 = 0 for NAIC (phrase_length[:, :-2]), 1 for SAIC (phrase_length[:, 1:-1]).
 __global__ void export_boxes_kernel(DecodeState st, int rows, int Lb, int L, int col0, int* __restrict__ phrase_num,
                                     int* __restrict__ phrase_length, long long* __restrict__ phrase_syn) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * L) return;
   const int b = i / L, c = i - b * L;

@@ -87,8 +87,11 @@ class BofiEngine:
                                             _ptr(seq), _ptr(logp), _ptr(pnum), _ptr(plen), _ptr(psyn)))
         return seq, logp, pnum, plen, psyn
 
-    def sample_host(self, att_feats, att_len=None, mode="NAIC", sample_n=1, output_logsoftmax=1, out=None, want_logprobs=False):
-        """End-to-end call on HOST tensors (pinned or pageable): H2D, encode, decode, D2H, sync."""
+    def sample_host(self, att_feats, att_len=None, mode="NAIC", sample_n=1, output_logsoftmax=1, out=None, want_logprobs=False,
+                    sync=True):
+        """End-to-end call on HOST tensors (pinned or pageable): H2D, encode, decode, D2H, sync.
+        sync=False only enqueues (bofi_sample_host_async): inputs / outputs must be pinned and stay alive until the
+        current stream has drained."""
         assert not att_feats.is_cuda and att_feats.dtype == torch.float32 and att_feats.is_contiguous()
         B, R, _ = att_feats.shape
         rows, L, V = B * sample_n, self.cfg.seq_length, self.cfg.tgt_vocab
@@ -101,7 +104,11 @@ class BofiEngine:
         if att_len is not None:
             att_len = att_len.to(torch.int32).contiguous()
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.bofi_sample_host(
+            fn = self.lib.bofi_sample_host if sync else self.lib.bofi_sample_host_async
+            if not sync:
+                assert att_feats.is_pinned() and out["seq"].is_pinned(), "asynchronous host path needs pinned buffers"
+                self._host_keep = (att_feats, att_len, out)
+            _lib.check(fn(
                 self.handle, self._stream(), _lib.MODE[mode], sample_n, int(output_logsoftmax), _ptr(att_feats), _ptr(att_len),
                 B, R, _ptr(out["seq"]), _ptr(out.get("logp")), _ptr(out["pnum"]), _ptr(out["plen"]), _ptr(out["psyn"])))
         return out

@@ -111,6 +111,16 @@ int bofi_sample_host(bofi_handle_t h, void* stream, int32_t mode, int32_t sample
                      int64_t* seq, float* logprobs, int32_t* phrase_num, int32_t* phrase_length,
                      int64_t* phrase_syn);
 
+/* Same work, enqueued only: nothing is synchronised, the results are in the host buffers once `stream` has
+ * drained (cudaStreamSynchronize / an event recorded after the call).  Host buffers must be PINNED for the
+ * copies to be asynchronous and must stay alive until then.  Two handles on two streams, fed alternately,
+ * overlap the H2D copy and the latency-bound bounding loop of one batch with the dense encoder / filling
+ * GEMMs of the other (boficap_b200/pipeline.py: the double-buffered feeder). */
+int bofi_sample_host_async(bofi_handle_t h, void* stream, int32_t mode, int32_t sample_n, int32_t output_logsoftmax,
+                           const float* att_feats, const int32_t* att_len, int32_t B, int32_t R,
+                           int64_t* seq, float* logprobs, int32_t* phrase_num, int32_t* phrase_length,
+                           int64_t* phrase_syn);
+
 /* Counters of the last decode (synchronises `stream`). */
 int bofi_get_decode_info(bofi_handle_t h, void* stream, bofi_decode_info_t* out);
 
