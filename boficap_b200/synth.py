@@ -115,3 +115,65 @@ def make_infos(cfg, opt_namespace=None):
             N_enc=cfg.N_enc, N_dec=cfg.N_dec, N_len=cfg.N_len, d_model=cfg.d_model, d_ff=cfg.d_ff,
             num_att_heads=cfg.h, dropout=cfg.dropout)
     return {"iter": 0, "epoch": 0, "vocab": vocab, "opt": opt_namespace, "best_val_score": None}
+
+
+def synth_xe_batch(B, seq_per_img=5, seq_length=16, seed=3, vocab_size=9487, len_idx=3, bos_idx=1, eos_idx=2,
+                   max_phrases=8):
+    """Synthetic teacher-forcing batch with the tensors the reference's collate_func builds for train_mode UIC
+    (captioning/data/dataloader.py:343-428): random phrase segmentations (syn labels 4..6, lengths 1..5, at most
+    `seq_length` words), random words, and the derived decoder inputs:
+      labels                [B, spi, L+2] i64   0, words..., 0 padding
+      phrase_num            [B, spi]      i64   number of phrases + 1 (the BOS pseudo-phrase)
+      phrase_length/_syn    [B, spi, L+2] i64   slot 0 = (1, bos); syn gets eos after the last phrase
+      extend_phrase_syn_seq [B, spi, L+2] i64   slot 0 = len_idx, then the syn label of every word slot
+      extend_phrase_seq     [B, spi, L]   i64   position-wise copy of the previous phrase's words
+      extend_phrase_seq_mask[B, spi, L*L] bool  phrase-block-causal mask (prefix form)
+    """
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    N, L = B * seq_per_img, seq_length
+    labels = np.zeros((N, L + 2), dtype=np.int64)
+    pnum = np.zeros(N, dtype=np.int64)
+    plen = np.zeros((N, L + 2), dtype=np.int64)
+    psyn = np.zeros((N, L + 2), dtype=np.int64)
+    ext_syn = np.zeros((N, L + 2), dtype=np.int64)
+    ext_seq = np.zeros((N, L), dtype=np.int64)
+    ext_mask = np.zeros((N, L, L), dtype=bool)
+    plen[:, 0] = 1
+    psyn[:, 0] = bos_idx
+    ext_syn[:, 0] = len_idx
+    for n in range(N):
+        lens, total = [], 0
+        for _ in range(int(rng.randint(1, max_phrases + 1))):
+            ln = int(rng.randint(1, 6))
+            if total + ln > L:
+                break
+            lens.append(ln)
+            total += ln
+        k = len(lens)
+        syns = rng.randint(4, 7, size=k)
+        labels[n, 1:1 + total] = rng.randint(4, vocab_size + 4, size=total)
+        pnum[n] = k + 1
+        plen[n, 1:k + 1] = lens
+        psyn[n, 1:k + 1] = syns
+        psyn[n, k + 1] = eos_idx
+        pos = 1
+        for j in range(k):
+            ext_syn[n, pos:pos + lens[j]] = syns[j]
+            pos += lens[j]
+        src, dst = 0, 0                      # start of the previous phrase in labels / of this phrase in the decoder input
+        for j in range(1, k + 1):
+            cur, prev = int(plen[n, j]), int(plen[n, j - 1])
+            if cur <= prev:                  # keep the last `cur` words of the previous phrase
+                ext_seq[n, dst:dst + cur] = labels[n, src + prev - cur:src + prev]
+            else:                            # stretch: the first words ct times, the rest ct + 1 times
+                few, ct = prev - cur % prev, cur // prev
+                reps = [ct if q < few else ct + 1 for q in range(prev)]
+                ext_seq[n, dst:dst + cur] = np.repeat(labels[n, src:src + prev], reps)
+            ext_mask[n, dst:, :dst + cur] = True
+            src += prev
+            dst += cur
+    t = lambda a, *shape: torch.from_numpy(a).reshape(B, seq_per_img, *shape)
+    return dict(labels=t(labels, L + 2), phrase_num=t(pnum), phrase_length=t(plen, L + 2), phrase_syn=t(psyn, L + 2),
+                extend_phrase_syn_seq=t(ext_syn, L + 2), extend_phrase_seq=t(ext_seq, L),
+                extend_phrase_seq_mask=t(ext_mask, L * L))

@@ -26,6 +26,8 @@ Reference citations (relative to /root/reference/captioning/models/):
   decode_naic       TransformerModel.py:1823-1876, AttModel.py:203-210, :419-429
   decode_saic       TransformerModel.py:1878-1986, :515-530
   sample_next_word  CaptionModel.py:383-437
+  forward_xe        TransformerModel.py:413-468 (glat_p < 0 branch), :476-565, :1713-1775 (train_mode UIC)
+  loss_xe           captioning/modules/losses.py:315-369 (LanguageModelCriterion_UIC, reduction='mean')
 """
 import math
 import time
@@ -333,3 +335,86 @@ class BofiOracle:
         out = fn(memory, src_mask, opt.get("output_logsoftmax", 1),
                  opt.get("sample_method", "greedy"), opt.get("temperature", 1.0))
         return tuple(out) + (time.time() - t0,)
+
+
+    # ---- A16: XE-training forward (teacher forcing) ---------------------------------------
+    def _teacher_bounding(self, x_in, memory, src_mask, phrase_num, phrase_length):
+        """get_predict_phrase_length_syn_SA / _NA (TransformerModel.py:476-513, :532-565): one bounding pass per
+        phrase index, every pass over all rows with the mask grown by the ground-truth boxes."""
+        N, Lb = phrase_length.shape
+        tgt_mask = torch.zeros(N, Lb, Lb, dtype=torch.bool)
+        len_logp = torch.zeros(N, Lb, LENGTH_DIM)
+        syn_logp = torch.zeros(N, Lb, SYN_DIM)
+        last = torch.ones(N, dtype=torch.long)
+        tgt_mask[:, :, 0] = True
+        _, ll, _, sl, _ = self.bounding_head(x_in, memory, src_mask, tgt_mask)
+        len_logp[:, 1], syn_logp[:, 1] = ll, sl
+        ar = torch.arange(Lb)
+        for i in range(1, int(phrase_num.max())):
+            grow = phrase_num > i
+            newlast = last + torch.where(grow, phrase_length[:, i], torch.zeros_like(last))
+            rows = (ar[None, :, None] >= last[:, None, None]) | (ar[None, :, None] == 0)
+            cols = ar[None, None, :] < newlast[:, None, None]
+            tgt_mask = tgt_mask | (rows & cols & grow[:, None, None])
+            last = newlast
+            _, ll, _, sl, _ = self.bounding_head(x_in, memory, src_mask, tgt_mask)
+            len_logp = torch.cat([len_logp[:, :i + 1], ll[:, None], len_logp[:, i + 2:]], 1)
+            syn_logp = torch.cat([syn_logp[:, :i + 1], sl[:, None], syn_logp[:, i + 2:]], 1)
+        return len_logp[:, 1:], syn_logp[:, 1:], last
+
+    def forward_xe(self, att_feats, att_masks, labels, phrase_num, phrase_length, extend_phrase_syn_seq,
+                   extend_phrase_seq, extend_phrase_seq_mask):
+        """`_forward` for train_mode UIC with glat_p < 0 and ss_prob == 0, dropout off (eval()).  Inputs may carry the
+        [B, seq_per_img, ...] layout of the loader.  Returns the six log-prob tensors of TransformerModel.py:1774-1775."""
+        c = self.cfg
+        if labels.dim() == 3:
+            labels = labels.reshape(-1, labels.shape[2])
+            phrase_num = phrase_num.reshape(-1)
+            phrase_length = phrase_length.reshape(-1, phrase_length.shape[2])
+            extend_phrase_syn_seq = extend_phrase_syn_seq.reshape(-1, extend_phrase_syn_seq.shape[2])
+            extend_phrase_seq = extend_phrase_seq.reshape(-1, extend_phrase_seq.shape[2])
+            L = extend_phrase_seq.shape[1]
+            extend_phrase_seq_mask = extend_phrase_seq_mask.reshape(-1, L, L)
+        spi = labels.shape[0] // att_feats.shape[0]
+        x, src_mask = self.prepare(att_feats, att_masks)
+        memory = self.encode(x, src_mask)                      # encoding once per image == encoding the repeats
+        memory = memory.repeat_interleave(spi, 0)
+        src_mask = src_mask.repeat_interleave(spi, 0)
+        phrase_num, phrase_length = phrase_num.long(), phrase_length.long()
+        word_seq = labels.clone().long()
+        word_seq[:, 0] = c.len_idx
+        sa_len, sa_syn, _ = self._teacher_bounding(self.pos(self.embed("tgt_embed", word_seq)), memory, src_mask,
+                                                   phrase_num, phrase_length)
+        sa_hidden = self.decoder(self.decoder_input(extend_phrase_seq, extend_phrase_syn_seq[:, 1:-1]), memory, src_mask,
+                                 extend_phrase_seq_mask)
+        na_len, na_syn, last = self._teacher_bounding(self.pos(self.embed("syn_embed", extend_phrase_syn_seq)), memory,
+                                                      src_mask, phrase_num, phrase_length)
+        L = extend_phrase_seq.shape[1]
+        syn_mask = torch.arange(L)[None, None, :] < (last - 1)[:, None, None]
+        syn_mask = syn_mask.expand(-1, L, -1)
+        bos = torch.full_like(extend_phrase_seq, c.bos_idx)
+        na_hidden = self.decoder(self.decoder_input(bos, extend_phrase_syn_seq[:, 1:-1]), memory, src_mask, syn_mask)
+        sa_logp = F.log_softmax(self.logit(sa_hidden), dim=-1)   # Generator.forward (TransformerModel.py:1315-1323)
+        na_logp = F.log_softmax(self.logit(na_hidden), dim=-1)
+        return sa_len, sa_syn, sa_logp, na_len, na_syn, na_logp
+
+    @staticmethod
+    def loss_xe(outs, phrase_num, phrase_length, phrase_syn, labels):
+        """LanguageModelCriterion_UIC, reduction='mean', self_dis=False (losses.py:315-369): six masked NLL sums, each
+        divided by the number of word slots."""
+        sa_len, sa_syn, sa_logp, na_len, na_syn, na_logp = outs
+        if labels.dim() == 3:
+            phrase_num = phrase_num.reshape(-1)
+            phrase_length = phrase_length.reshape(-1, phrase_length.shape[2])
+            phrase_syn = phrase_syn.reshape(-1, phrase_syn.shape[2])
+            labels = labels.reshape(-1, labels.shape[2])
+        words = labels[:, 1:-1].long()
+        T = words.shape[1]
+        word_mask = (torch.arange(T)[None, :] < (phrase_length.sum(1) - 1)[:, None]).to(sa_logp.dtype)
+        box_mask = (torch.arange(phrase_length.shape[1] - 1)[None, :] < phrase_num[:, None]).to(sa_logp.dtype)
+        len_t, syn_t = phrase_length[:, 1:].long(), phrase_syn[:, 1:].long()
+        nll = lambda lp, tgt, m: -(lp.gather(2, tgt.unsqueeze(2)).squeeze(2) * m).sum()
+        denom = word_mask.sum()
+        parts = [nll(sa_len, len_t, box_mask) / denom, nll(sa_logp, words, word_mask) / denom, nll(sa_syn, syn_t, box_mask) / denom,
+                 nll(na_len, len_t, box_mask) / denom, nll(na_logp, words, word_mask) / denom, nll(na_syn, syn_t, box_mask) / denom]
+        return sum(parts), parts
