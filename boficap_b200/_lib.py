@@ -47,6 +47,14 @@ _SIGNATURES = {
     "bofi_set_profiling": (C.c_int, [_P, _I]),
     "bofi_get_profile": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "bofi_get_profile_top_gemm": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "bofi_param_numel": (C.c_int64, [_P]),
+    "bofi_param_offset": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "bofi_train_bind": (C.c_int, [_P, _P, _P, _P]),
+    "bofi_refresh_weights": (C.c_int, [_P, _P]),
+    "bofi_train_forward": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I] + [_P] * 12),
+    "bofi_train_backward": (C.c_int, [_P, _P] + [_P] * 12),
+    "bofi_train_step_xe": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I] + [_P] * 8),
+    "bofi_train_launches": (C.c_int, [_P]),
     "bofi_layernorm_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, _I]),
     "bofi_linear_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I]),
     "bofi_attention_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I]),

@@ -36,6 +36,27 @@ def _attach(root, dotted, tensor, is_buffer):
         mod.register_parameter(parts[-1], nn.Parameter(tensor))
 
 
+class _XEForward(torch.autograd.Function):
+    """Autograd bridge of the teacher-forced forward: the six log-prob tensors come from bofi_train_forward; their
+    gradients go to bofi_train_backward, which accumulates straight into the parameters' `.grad` storage (the flat
+    gradient buffer), so no gradient is returned to autograd for the parameters themselves."""
+
+    @staticmethod
+    def forward(ctx, model, att_feats, att_len, batch, anchor):
+        eng = model._engine
+        outs = eng.train_forward(att_feats, att_len, batch)
+        ctx.model = model
+        ctx.save_for_backward(*outs)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        outs = ctx.saved_tensors
+        grads = [g if g is not None else torch.zeros_like(o) for g, o in zip(grads, outs)]
+        ctx.model._engine.train_backward(grads, outs)
+        return None, None, None, None, None
+
+
 class TransformerModel(nn.Module):
     def __init__(self, opt):
         super().__init__()
@@ -68,6 +89,39 @@ class TransformerModel(nn.Module):
             _attach(self, name, t, False)
         self._engine = None
         self._engine_key = None
+        self._bound = None          # (flat_w, flat_g, version stamp) once the parameters are views of the training buffers
+
+    # ---- training: parameters as views of the library's flat buffers ---------------------------
+    def train_bind(self, device=None, precision=None):
+        """Moves the parameters into the flat parameter buffer shared with libbofi_b200.so and their `.grad`s into the
+        flat gradient buffer (boficap_b200/engine.py:train_bind).  Call after the model is on its device; optimisers
+        must be created afterwards (they hold the re-pointed parameters)."""
+        eng = self.engine(device, precision)
+        flat_w, flat_g = eng.train_bind()
+        layout = eng.param_layout()
+        for name, p in list(self.named_parameters()) + list(self.named_buffers()):
+            off, n = layout[name]
+            p.data = flat_w[off:off + n].view(p.shape)
+            if isinstance(p, nn.Parameter):
+                p.grad = flat_g[off:off + n].view(p.shape)
+        self._bound = [flat_w, flat_g, self._version_stamp()]
+        self._engine_key = None
+        return self
+
+    def _version_stamp(self):
+        return sum(p._version for p in self.parameters())
+
+    def flat_grads(self):
+        return self._bound[1]
+
+    def flat_params(self):
+        return self._bound[0]
+
+    def zero_grad(self, set_to_none=False):          # the gradients are views of one buffer: always zero in place
+        if self._bound is not None:
+            self._bound[1].zero_()
+            return
+        super().zero_grad(set_to_none=set_to_none)
 
     # ---- engine management -----------------------------------------------------------------
     def _weights_key(self):
@@ -77,6 +131,12 @@ class TransformerModel(nn.Module):
         precision = precision or self.precision
         device = torch.device(device if device is not None else "cuda")
         index = device.index if device.index is not None else torch.cuda.current_device()
+        if self._bound is not None and self._engine is not None and self._engine.precision == precision:
+            stamp = self._version_stamp()               # optimiser steps write the shared buffer in place
+            if stamp != self._bound[2]:
+                self._engine.refresh_weights()
+                self._bound[2] = stamp
+            return self._engine
         key = (index, precision, self._weights_key())
         if self._engine is None or self._engine_key != key:
             if self._engine is not None:
@@ -90,9 +150,55 @@ class TransformerModel(nn.Module):
         mode = kwargs.pop("mode", "forward")
         return getattr(self, "_" + mode)(*args, **kwargs)
 
-    def _forward(self, *args, **kwargs):
-        raise NotImplementedError("the XE-training forward (TransformerModel._forward) is outside this round's "
-                                  "hot path; use the reference model for training")
+    @staticmethod
+    def _xe_batch(att_feats, seq, phrase_num, phrase_length, phrase_syn, extend_phrase_syn_seq, extend_phrase_seq,
+                  extend_phrase_seq_mask):
+        """The loader's [B, seq_per_img, ...] tensors as 2-D caption rows on the feature device (the reshape of
+        TransformerModel.py:1714-1722); the boolean phrase-block mask becomes its visible-key counts."""
+        dev = att_feats.device
+        r2 = lambda t: t.reshape(-1, t.shape[-1]).to(dev) if t is not None else None
+        labels = r2(seq)
+        ext_seq = r2(extend_phrase_seq)
+        L = ext_seq.shape[1]
+        mask = extend_phrase_seq_mask.reshape(-1, L, L).to(dev)
+        sa_vis = mask.sum(-1)
+        pn = phrase_num.reshape(-1)
+        return dict(labels=labels, phrase_num=pn.to(dev), phrase_length=r2(phrase_length), phrase_syn=r2(phrase_syn),
+                    extend_phrase_syn_seq=r2(extend_phrase_syn_seq), extend_phrase_seq=ext_seq, sa_vis=sa_vis, P=int(pn.max()))
+
+    def _train_engine(self, att_feats):
+        if not att_feats.is_cuda:
+            raise RuntimeError("boficap_b200 runs on CUDA tensors only (no CPU fallback)")
+        if self._bound is None:
+            self.train_bind(att_feats.device)
+        return self.engine(att_feats.device)
+
+    def _forward(self, fc_feats, att_feats, seq, att_masks=None, phrase_num=None, phrase_length=None, phrase_syn=None,
+                 extend_phrase_syn_seq=None, extend_phrase_seq=None, extend_phrase_seq_mask=None, glat_p=-1.0):
+        """TransformerModel._forward, train_mode UIC (TransformerModel.py:1713-1775): the six log-prob tensors
+        (SA length / syn / word, NA length / syn / word), differentiable w.r.t. the parameters."""
+        if glat_p >= 0:
+            raise NotImplementedError("glat_p >= 0 (glancing sampling, TransformerModel.py:437-464) is not built; "
+                                      "the reference default for _forward is glat_p = -1")
+        if self.ss_prob > 0:
+            raise NotImplementedError("scheduled sampling (ss_prob > 0, TransformerModel.py:1759-1766) is not built")
+        self._train_engine(att_feats)
+        batch = self._xe_batch(att_feats, seq, phrase_num, phrase_length, phrase_syn, extend_phrase_syn_seq, extend_phrase_seq,
+                               extend_phrase_seq_mask)
+        att_len = att_masks.data.long().sum(1).to(torch.int32) if att_masks is not None else None
+        anchor = next(self.parameters())                  # makes the outputs require grad
+        return _XEForward.apply(self, att_feats.float(), att_len, batch, anchor)
+
+    def xe_step(self, fc_feats, att_feats, seq, att_masks=None, phrase_num=None, phrase_length=None, phrase_syn=None,
+                extend_phrase_syn_seq=None, extend_phrase_seq=None, extend_phrase_seq_mask=None):
+        """One XE training step's forward + LanguageModelCriterion_UIC(reduction='mean') + backward in a single library
+        call (bofi_train_step_xe): gradients are accumulated into the parameters' `.grad`; returns the criterion's seven
+        values (total, SA_length, SA_phrase, SA_syn, NA_length, NA_phrase, NA_syn) as a device tensor."""
+        eng = self._train_engine(att_feats)
+        batch = self._xe_batch(att_feats, seq, phrase_num, phrase_length, phrase_syn, extend_phrase_syn_seq, extend_phrase_seq,
+                               extend_phrase_seq_mask)
+        att_len = att_masks.data.long().sum(1).to(torch.int32) if att_masks is not None else None
+        return eng.train_step_xe(att_feats.float(), att_len, batch)
 
     def _sample(self, fc_feats, att_feats, att_masks=None, opt={}):
         sample_method = opt.get("sample_method", "greedy")

@@ -7,6 +7,7 @@
 //   cross K/V of `memory`  T    [B*R, 1024] per decoder-style layer, projected ONCE per decode
 //   logits                 fp32 [rows*L, Vpad]         Vpad = V rounded to 32 (16-byte pitched rows)
 // Reference citations are relative to /root/reference/captioning/models/.
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -21,6 +22,7 @@
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
 #include "attention_mma.cuh"
+#include "train_kernels.cuh"
 
 using namespace bofi;
 
@@ -73,13 +75,15 @@ struct DevBuf {
   template <typename U> U* as() const { return reinterpret_cast<U*>(p); }
 };
 
-struct Lin {          // nn.Linear: weight [N,K] (K-major), bias [N]
+struct Lin {          // nn.Linear: weight [N,K] (K-major), bias [N]; possibly several reference Linears fused along N
   const float* w32 = nullptr;
   const bf16* w16 = nullptr;
   const float* b = nullptr;
   int N = 0, K = 0;
+  float* gw = nullptr;      // gradients (training, bofi_train_bind): same layout as w32 / b
+  float* gb = nullptr;
 };
-struct Norm { const float* a = nullptr; const float* b = nullptr; };
+struct Norm { const float* a = nullptr; const float* b = nullptr; float* ga = nullptr; float* gb = nullptr; };
 struct SelfAttn { Lin qkv, o; };
 struct CrossAttn { Lin q, kv, o; };
 struct Layer {        // EncoderLayer (cross == false) / DecoderLayer / LengthPredictorLayer
@@ -90,7 +94,11 @@ struct Layer {        // EncoderLayer (cross == false) / DecoderLayer / LengthPr
   Norm ln[3];
 };
 
-struct WeightEntry { float* dev = nullptr; int64_t numel = 0; bool loaded = false; bool used = true; };
+// Every state_dict entry lives at a fixed offset of ONE flat fp32 parameter buffer.  Entries that the kernels read
+// as one fused matrix (Q|K|V, K|V, the two classifier1 heads) are laid out back to back, so the fused views are
+// plain pointers into the buffer; a bf16 mirror (same offsets) feeds the tcgen05 GEMMs.  Training binds caller-owned
+// flat weight / gradient buffers with the same layout (bofi_train_bind).
+struct WeightEntry { int64_t off = -1; int64_t numel = 0; bool loaded = false; bool used = true; };
 
 // Optional per-launch CUDA-event timing (bofi_set_profiling): one record per kernel launch.
 enum { PC_GEMM_TC = 0, PC_GEMM_SIMT, PC_ATTENTION, PC_LAYERNORM, PC_VOCAB, PC_OTHER, PC_COUNT };
@@ -105,8 +113,11 @@ struct bofi_engine {
   bool attn_simt_only = false;         // BOFI_ATTN=simt: generic FFMA attention kernel everywhere
   bool finalized = false;
   std::unordered_map<std::string, WeightEntry> weights;
-  std::vector<std::string> order;
-  std::vector<DevBuf> packed;          // fused / converted weight storage
+  std::vector<std::string> order;      // layout order of the flat buffer
+  int64_t flat_numel = 0;
+  DevBuf flat_own, flat16;             // engine-owned fp32 parameters, bf16 mirror (bf16 mode)
+  float* flat_w = nullptr;             // = flat_own.p, or the caller's buffer after bofi_train_bind
+  float* flat_g = nullptr;             // caller's gradient buffer (training only)
   // model
   Lin att_embed, generator, head1;     // head1 = [Length_classifier1 ; Syntactic_classifier1]  (N = 200)
   std::vector<Layer> enc, dec, lp;
@@ -141,6 +152,7 @@ struct bofi_engine {
   unsigned long long bound_key[6] = {0, 0, 0, 0, 0, 0};
   int bound_launches = 0;
   int bound_eager_runs = 0;
+  struct TrainStateHolder* train = nullptr;   // XE-training tape (train.inl), created on first use
 };
 
 static int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
@@ -166,19 +178,37 @@ struct ProfScope {
   }
 };
 
-// ---- state_dict spec (mirrors boficap_b200/layout.py:state_spec) ---------------------------------
-static void spec_add(bofi_engine* e, const std::string& name, int64_t numel, bool used = true) {
-  WeightEntry w;
-  w.numel = numel;
-  w.used = used;
-  e->weights[name] = w;
-  e->order.push_back(name);
-}
-static void spec_attn(bofi_engine* e, const std::string& p, int d, bool used = true) {
-  for (int i = 0; i < 4; ++i) {
-    spec_add(e, p + ".linears." + std::to_string(i) + ".weight", (int64_t)d * d, used);
-    spec_add(e, p + ".linears." + std::to_string(i) + ".bias", d, used);
+// ---- state_dict spec (mirrors boficap_b200/layout.py:state_spec) + flat layout -------------------------
+// A "group" is laid out contiguously and starts on a 64-element boundary (256 B fp32 / 128 B bf16: TMA-friendly).
+static void spec_group(bofi_engine* e, const std::vector<std::pair<std::string, int64_t>>& entries, bool used = true) {
+  e->flat_numel = (e->flat_numel + 63) / 64 * 64;
+  for (const auto& en : entries) {
+    WeightEntry w;
+    w.off = e->flat_numel;
+    w.numel = en.second;
+    w.used = used;
+    e->weights[en.first] = w;
+    e->order.push_back(en.first);
+    e->flat_numel += en.second;
   }
+}
+static void spec_add(bofi_engine* e, const std::string& name, int64_t numel, bool used = true) { spec_group(e, {{name, numel}}, used); }
+// MultiHeadedAttention: linears.0..3.  `fuse` = how many leading linears form one fused matrix (3: Q|K|V for
+// self-attention, 1 then 2: Q and K|V for cross-attention).
+static void spec_attn(bofi_engine* e, const std::string& p, int d, bool self, bool used = true) {
+  auto w = [&](int i) { return std::make_pair(p + ".linears." + std::to_string(i) + ".weight", (int64_t)d * d); };
+  auto b = [&](int i) { return std::make_pair(p + ".linears." + std::to_string(i) + ".bias", (int64_t)d); };
+  if (self) {
+    spec_group(e, {w(0), w(1), w(2)}, used);
+    spec_group(e, {b(0), b(1), b(2)}, used);
+  } else {
+    spec_group(e, {w(0)}, used);
+    spec_group(e, {b(0)}, used);
+    spec_group(e, {w(1), w(2)}, used);
+    spec_group(e, {b(1), b(2)}, used);
+  }
+  spec_group(e, {w(3)}, used);
+  spec_group(e, {b(3)}, used);
 }
 static void spec_ffn(bofi_engine* e, const std::string& p, int d, int dff, bool used = true) {
   spec_add(e, p + ".w_1.weight", (int64_t)dff * d, used);
@@ -191,8 +221,8 @@ static void spec_norm(bofi_engine* e, const std::string& p, int d) {
   spec_add(e, p + ".b_2", d);
 }
 static void spec_layer(bofi_engine* e, const std::string& p, int d, int dff, bool cross, const char* ff) {
-  spec_attn(e, p + ".self_attn", d);
-  if (cross) spec_attn(e, p + ".src_attn", d);
+  spec_attn(e, p + ".self_attn", d, true);
+  if (cross) spec_attn(e, p + ".src_attn", d, false);
   spec_ffn(e, p + "." + ff, d, dff);
   for (int s = 0; s < (cross ? 3 : 2); ++s) spec_norm(e, p + ".sublayer." + std::to_string(s) + ".norm", d);
 }
@@ -212,19 +242,18 @@ static void build_spec(bofi_engine* e) {
   spec_add(e, "model.generator.proj.bias", c.tgt_vocab);
   const std::string lp = "model.length_predictor";
   const bool lp_direct = (c.n_len == 0);          // length_attn / ff are only live when N_len == 0 (:369-370)
-  spec_attn(e, lp + ".length_attn", d, lp_direct);
+  spec_attn(e, lp + ".length_attn", d, false, lp_direct);
   spec_ffn(e, lp + ".ff", d, dff, false);
   spec_norm(e, lp + ".norm", d);
-  spec_add(e, lp + ".Length_classifier1.weight", 100LL * d);
-  spec_add(e, lp + ".Length_classifier1.bias", 100);
+  spec_group(e, {{lp + ".Length_classifier1.weight", 100LL * d}, {lp + ".Syntactic_classifier1.weight", 100LL * d}});
+  spec_group(e, {{lp + ".Length_classifier1.bias", 100}, {lp + ".Syntactic_classifier1.bias", 100}});
   spec_add(e, lp + ".Length_classifier2.weight", 20LL * 100);
   spec_add(e, lp + ".Length_classifier2.bias", 20);
-  spec_add(e, lp + ".Syntactic_classifier1.weight", 100LL * d);
-  spec_add(e, lp + ".Syntactic_classifier1.bias", 100);
   spec_add(e, lp + ".Syntactic_classifier2.weight", 10LL * 100);
   spec_add(e, lp + ".Syntactic_classifier2.bias", 10);
   if (c.n_len == 0) spec_norm(e, lp + ".LengthPredictor.norm", d);
   for (int l = 0; l < c.n_len; ++l) spec_layer(e, lp + ".LengthPredictor." + std::to_string(l), d, dff, true, "ff");
+  e->flat_numel = (e->flat_numel + 63) / 64 * 64;
 }
 
 // ---- launch helpers ------------------------------------------------------------------------------
@@ -232,10 +261,6 @@ template <typename T> struct Ctx {
   bofi_engine* e;
   cudaStream_t s;
 };
-
-template <typename T> static const T* lin_w(const Lin& l);
-template <> const float* lin_w<float>(const Lin& l) { return l.w32; }
-template <> const bf16* lin_w<bf16>(const Lin& l) { return l.w16; }
 
 template <typename T, typename TOut>
 static int linear(bofi_engine* e, cudaStream_t s, const T* A, int lda, const Lin& l, const float* resid, int ldr,
@@ -360,76 +385,104 @@ static int run_layer(bofi_engine* e, cudaStream_t s, const Layer& ly, float* x, 
   return BOFI_OK;
 }
 
-// ---- weight packing --------------------------------------------------------------------------------
-static const float* W(bofi_engine* e, const std::string& name) { return e->weights[name].dev; }
+// ---- views into the flat parameter buffer ---------------------------------------------------------------
+static const float* W(bofi_engine* e, const std::string& name) { return e->flat_w + e->weights[name].off; }
+static float* G(bofi_engine* e, const std::string& name) { return e->flat_g ? e->flat_g + e->weights[name].off : nullptr; }
 
-static int pack_rows(bofi_engine* e, cudaStream_t s, const std::vector<const float*>& srcs, const std::vector<int64_t>& numels,
-                     float** out32, bf16** out16) {
-  int64_t total = 0;
-  for (int64_t n : numels) total += n;
-  e->packed.emplace_back();
-  DevBuf& b32 = e->packed.back();
-  RC_TRY(b32.reserve(total * sizeof(float)));
-  int64_t off = 0;
-  for (size_t i = 0; i < srcs.size(); ++i) {
-    CU_TRY(cudaMemcpyAsync(b32.as<float>() + off, srcs[i], numels[i] * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    off += numels[i];
+// Fused nn.Linear view: the entries `prefixes[i].weight` (and `.bias`) must be adjacent in the flat layout.
+static int make_lin(bofi_engine* e, const std::vector<std::string>& prefixes, int N_each, int K, Lin* out) {
+  const int64_t w0 = e->weights[prefixes[0] + ".weight"].off, b0 = e->weights[prefixes[0] + ".bias"].off;
+  for (size_t i = 0; i < prefixes.size(); ++i) {
+    if (e->weights[prefixes[i] + ".weight"].off != w0 + (int64_t)i * N_each * K || e->weights[prefixes[i] + ".bias"].off != b0 + (int64_t)i * N_each)
+      return fail(BOFI_ERR_STATE, "flat layout: %s is not adjacent to %s", prefixes[i].c_str(), prefixes[0].c_str());
   }
-  *out32 = b32.as<float>();
-  *out16 = nullptr;
-  if (e->bf16_mode) {
-    e->packed.emplace_back();
-    DevBuf& b16 = e->packed.back();
-    RC_TRY(b16.reserve(total * sizeof(bf16)));
-    launch_k(cast_kernel<bf16>, ceil_div(total / 4, 256), 256, 0, s, *out32, b16.as<bf16>(), (size_t)(total / 4));
-    CU_TRY(cudaGetLastError());
-    *out16 = b16.as<bf16>();
-  }
-  return BOFI_OK;
-}
-
-static int make_lin(bofi_engine* e, cudaStream_t s, const std::vector<std::string>& prefixes, int N_each, int K, Lin* out) {
-  std::vector<const float*> ws, bs;
-  std::vector<int64_t> wn, bn;
-  for (const std::string& p : prefixes) {
-    ws.push_back(W(e, p + ".weight"));
-    wn.push_back((int64_t)N_each * K);
-    bs.push_back(W(e, p + ".bias"));
-    bn.push_back(N_each);
-  }
-  float *w32, *b32;
-  bf16 *w16, *b16;
-  RC_TRY(pack_rows(e, s, ws, wn, &w32, &w16));
-  bool keep = e->bf16_mode;
-  e->bf16_mode = false;                           // biases stay fp32
-  int rc = pack_rows(e, s, bs, bn, &b32, &b16);
-  e->bf16_mode = keep;
-  RC_TRY(rc);
-  out->w32 = w32;
-  out->w16 = w16;
-  out->b = b32;
+  out->w32 = e->flat_w + w0;
+  out->w16 = e->bf16_mode ? e->flat16.as<bf16>() + w0 : nullptr;
+  out->b = e->flat_w + b0;
+  out->gw = e->flat_g ? e->flat_g + w0 : nullptr;
+  out->gb = e->flat_g ? e->flat_g + b0 : nullptr;
   out->N = N_each * (int)prefixes.size();
   out->K = K;
   return BOFI_OK;
 }
 
-static Norm make_norm(bofi_engine* e, const std::string& p) { return Norm{W(e, p + ".a_2"), W(e, p + ".b_2")}; }
+static Norm make_norm(bofi_engine* e, const std::string& p) {
+  return Norm{W(e, p + ".a_2"), W(e, p + ".b_2"), G(e, p + ".a_2"), G(e, p + ".b_2")};
+}
 
-static int make_layer(bofi_engine* e, cudaStream_t s, const std::string& p, bool cross, const char* ff, Layer* ly) {
+static int make_layer(bofi_engine* e, const std::string& p, bool cross, const char* ff, Layer* ly) {
   const int d = e->cfg.d_model, dff = e->cfg.d_ff;
   ly->cross = cross;
   const std::string sa = p + ".self_attn.linears.";
-  RC_TRY(make_lin(e, s, {sa + "0", sa + "1", sa + "2"}, d, d, &ly->sa.qkv));
-  RC_TRY(make_lin(e, s, {sa + "3"}, d, d, &ly->sa.o));
+  RC_TRY(make_lin(e, {sa + "0", sa + "1", sa + "2"}, d, d, &ly->sa.qkv));
+  RC_TRY(make_lin(e, {sa + "3"}, d, d, &ly->sa.o));
   if (cross) {
     const std::string ca = p + ".src_attn.linears.";
-    RC_TRY(make_lin(e, s, {ca + "0"}, d, d, &ly->ca.q));
-    RC_TRY(make_lin(e, s, {ca + "1", ca + "2"}, d, d, &ly->ca.kv));
-    RC_TRY(make_lin(e, s, {ca + "3"}, d, d, &ly->ca.o));
+    RC_TRY(make_lin(e, {ca + "0"}, d, d, &ly->ca.q));
+    RC_TRY(make_lin(e, {ca + "1", ca + "2"}, d, d, &ly->ca.kv));
+    RC_TRY(make_lin(e, {ca + "3"}, d, d, &ly->ca.o));
   }
-  RC_TRY(make_lin(e, s, {p + "." + ff + ".w_1"}, dff, d, &ly->w1));
-  RC_TRY(make_lin(e, s, {p + "." + ff + ".w_2"}, d, dff, &ly->w2));
+  RC_TRY(make_lin(e, {p + "." + ff + ".w_1"}, dff, d, &ly->w1));
+  RC_TRY(make_lin(e, {p + "." + ff + ".w_2"}, d, dff, &ly->w2));
   for (int i = 0; i < (cross ? 3 : 2); ++i) ly->ln[i] = make_norm(e, p + ".sublayer." + std::to_string(i) + ".norm");
+  return BOFI_OK;
+}
+
+// (Re)builds every host-side view from e->flat_w / flat16 / flat_g.  Pure pointer arithmetic.
+static int build_views(bofi_engine* e) {
+  const bofi_config_t& c = e->cfg;
+  e->enc.assign(c.n_enc, Layer());
+  e->dec.assign(c.n_dec, Layer());
+  e->lp.assign(c.n_len, Layer());
+  RC_TRY(make_lin(e, {"att_embed.0"}, c.d_model, c.att_feat_size, &e->att_embed));
+  for (int l = 0; l < c.n_enc; ++l) RC_TRY(make_layer(e, "model.encoder.layers." + std::to_string(l), false, "feed_forward", &e->enc[l]));
+  for (int l = 0; l < c.n_dec; ++l) RC_TRY(make_layer(e, "model.decoder.layers." + std::to_string(l), true, "feed_forward", &e->dec[l]));
+  const std::string lp = "model.length_predictor";
+  for (int l = 0; l < c.n_len; ++l) RC_TRY(make_layer(e, lp + ".LengthPredictor." + std::to_string(l), true, "ff", &e->lp[l]));
+  if (c.n_len == 0) {
+    const std::string ca = lp + ".length_attn.linears.";
+    e->lp0.cross = true;
+    RC_TRY(make_lin(e, {ca + "0"}, c.d_model, c.d_model, &e->lp0.ca.q));
+    RC_TRY(make_lin(e, {ca + "1", ca + "2"}, c.d_model, c.d_model, &e->lp0.ca.kv));
+    RC_TRY(make_lin(e, {ca + "3"}, c.d_model, c.d_model, &e->lp0.ca.o));
+    e->lp0.ln[0] = make_norm(e, lp + ".LengthPredictor.norm");
+  }
+  e->enc_norm = make_norm(e, "model.encoder.norm");
+  e->dec_norm = make_norm(e, "model.decoder.norm");
+  e->lp_norm = make_norm(e, lp + ".norm");
+  RC_TRY(make_lin(e, {"model.generator.proj"}, c.tgt_vocab, c.d_model, &e->generator));
+  RC_TRY(make_lin(e, {lp + ".Length_classifier1", lp + ".Syntactic_classifier1"}, 100, c.d_model, &e->head1));
+  e->head1.w16 = nullptr;          // the heads stay fp32 in both precisions
+  e->w_len2 = W(e, lp + ".Length_classifier2.weight");
+  e->b_len2 = W(e, lp + ".Length_classifier2.bias");
+  e->w_syn2 = W(e, lp + ".Syntactic_classifier2.weight");
+  e->b_syn2 = W(e, lp + ".Syntactic_classifier2.bias");
+  return BOFI_OK;
+}
+
+template <typename T> static int build_bound_tables(bofi_engine* e, cudaStream_t s);
+
+// Everything derived from the parameter values: the bf16 mirror, the transposed classifier1 matrix, the
+// (syn id, position) input tables and the bounding-layer LN + QKV table.  Re-run after the parameters change.
+static int refresh_derived(bofi_engine* e, cudaStream_t s) {
+  const bofi_config_t& c = e->cfg;
+  if (e->bf16_mode) {
+    RC_TRY(e->flat16.reserve((size_t)e->flat_numel * sizeof(bf16)));
+    launch_k(cast_kernel<bf16>, 148 * 8, 256, 0, s, e->flat_w, e->flat16.as<bf16>(), (size_t)(e->flat_numel / 4));
+    CU_TRY(cudaGetLastError());
+  }
+  RC_TRY(build_views(e));          // flat16 may just have been (re)allocated
+  RC_TRY(e->head1t.reserve((size_t)200 * kD * 4));
+  launch_k(transpose_kernel, dim3(ceil_div(kD, 32), ceil_div(200, 32)), dim3(32, 8), 0, s, e->head1.w32, e->head1t.as<float>(), 200, kD);
+  CU_TRY(cudaGetLastError());
+  RC_TRY(e->bound_in.reserve((size_t)10 * e->Lb * kD * 4));
+  RC_TRY(e->fill_in.reserve((size_t)10 * e->L * kD * 4));
+  launch_k(build_tables_kernel, dim3(10, e->Lb), 128, 0, s, W(e, "model.syn_embed.lut.weight"), W(e, "model.tgt_embed.lut.weight"),
+           W(e, "model.pos_embed.pe"), c.bos_idx, 10, e->Lb, e->L, sqrtf((float)kD), e->bound_in.as<float>(), e->fill_in.as<float>());
+  CU_TRY(cudaGetLastError());
+  const char* bg = getenv("BOFI_BOUND");
+  e->bound_fast = (c.n_len == 1) && !(bg && strcmp(bg, "generic") == 0);
+  if (e->bound_fast) RC_TRY(e->bf16_mode ? build_bound_tables<bf16>(e, s) : build_bound_tables<float>(e, s));
   return BOFI_OK;
 }
 
@@ -799,6 +852,25 @@ static int decode_saic(bofi_engine* e, cudaStream_t s, int sn, int output_logsof
 }
 
 // ---------------------------------------------------------------------------------------------
+// XE training (forward tape + backward)
+// ---------------------------------------------------------------------------------------------
+#include "train.inl"
+struct TrainStateHolder { TrainState st; };
+static TrainState* train_state(bofi_engine* e) {
+  if (!e->train) e->train = new TrainStateHolder();
+  return &e->train->st;
+}
+static void train_release(bofi_engine* e) {
+  if (!e->train) return;
+  TrainState& t = e->train->st;
+  t.arena.release();
+  DevBuf* all[] = {&t.tr_a, &t.tr_b, &t.tr_w, &t.zeros, &t.ln_partial, &t.scratch_f32, &t.dkv, &t.dmem};
+  for (DevBuf* b : all) b->release();
+  delete e->train;
+  e->train = nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
 extern "C" {
@@ -841,6 +913,9 @@ int bofi_create(const bofi_config_t* cfg, int device, bofi_handle_t* out) {
   const char* ga = getenv("BOFI_ATTN");
   e->attn_simt_only = (ga && strcmp(ga, "simt") == 0);
   build_spec(e);
+  if (e->flat_own.reserve((size_t)e->flat_numel * sizeof(float)) != BOFI_OK) { delete e; return BOFI_ERR_NOMEM; }
+  e->flat_w = e->flat_own.as<float>();
+  cudaMemset(e->flat_w, 0, (size_t)e->flat_numel * sizeof(float));
   *out = e;
   return BOFI_OK;
 }
@@ -852,9 +927,9 @@ int bofi_destroy(bofi_handle_t e) {
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
   if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
-  for (auto& kv : e->weights)
-    if (kv.second.dev) cudaFree(kv.second.dev);
-  for (DevBuf& b : e->packed) b.release();
+  train_release(e);
+  e->flat_own.release();
+  e->flat16.release();
   for (DevBuf& b : e->kv) b.release();
   DevBuf* all[] = {&e->bound_in, &e->fill_in, &e->attT, &e->x, &e->y, &e->qkv, &e->ao, &e->q, &e->ffh, &e->memT, &e->attlen,
                    &e->sa_mx, &e->sa_lse, &e->head1t, &e->tab_y, &e->tab_qkv, &e->hrow, &e->hid, &e->logits, &e->state_i32, &e->tok, &e->h_in, &e->h_len, &e->h_seq, &e->h_logp,
@@ -871,9 +946,7 @@ int bofi_set_weight(bofi_handle_t e, const char* name, const float* host_data, i
   WeightEntry& w = it->second;
   if (w.numel != numel) return fail(BOFI_ERR_INVALID, "size mismatch for '%s': got %lld elements, expected %lld", name, (long long)numel, (long long)w.numel);
   CU_TRY(cudaSetDevice(e->device));
-  if (!w.used) { w.loaded = true; return BOFI_OK; }
-  if (!w.dev) CU_TRY(cudaMalloc(&w.dev, (size_t)numel * sizeof(float)));
-  CU_TRY(cudaMemcpy(w.dev, host_data, (size_t)numel * sizeof(float), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy(e->flat_w + w.off, host_data, (size_t)numel * sizeof(float), cudaMemcpyHostToDevice));
   w.loaded = true;
   e->finalized = false;
   return BOFI_OK;
@@ -892,53 +965,7 @@ int bofi_finalize_weights(bofi_handle_t e, void* stream) {
     if (!e->weights[n].loaded) return fail(BOFI_ERR_STATE, "missing state_dict key '%s'", n.c_str());
   CU_TRY(cudaSetDevice(e->device));
   cudaStream_t s = (cudaStream_t)stream;
-  const bofi_config_t& c = e->cfg;
-  for (DevBuf& b : e->packed) b.release();
-  e->packed.clear();
-  e->packed.reserve(4096);
-  e->enc.assign(c.n_enc, Layer());
-  e->dec.assign(c.n_dec, Layer());
-  e->lp.assign(c.n_len, Layer());
-  RC_TRY(make_lin(e, s, {"att_embed.0"}, c.d_model, c.att_feat_size, &e->att_embed));
-  for (int l = 0; l < c.n_enc; ++l) RC_TRY(make_layer(e, s, "model.encoder.layers." + std::to_string(l), false, "feed_forward", &e->enc[l]));
-  for (int l = 0; l < c.n_dec; ++l) RC_TRY(make_layer(e, s, "model.decoder.layers." + std::to_string(l), true, "feed_forward", &e->dec[l]));
-  const std::string lp = "model.length_predictor";
-  for (int l = 0; l < c.n_len; ++l) RC_TRY(make_layer(e, s, lp + ".LengthPredictor." + std::to_string(l), true, "ff", &e->lp[l]));
-  if (c.n_len == 0) {
-    const std::string ca = lp + ".length_attn.linears.";
-    e->lp0.cross = true;
-    RC_TRY(make_lin(e, s, {ca + "0"}, c.d_model, c.d_model, &e->lp0.ca.q));
-    RC_TRY(make_lin(e, s, {ca + "1", ca + "2"}, c.d_model, c.d_model, &e->lp0.ca.kv));
-    RC_TRY(make_lin(e, s, {ca + "3"}, c.d_model, c.d_model, &e->lp0.ca.o));
-    e->lp0.ln[0] = make_norm(e, lp + ".LengthPredictor.norm");
-  }
-  e->enc_norm = make_norm(e, "model.encoder.norm");
-  e->dec_norm = make_norm(e, "model.decoder.norm");
-  e->lp_norm = make_norm(e, lp + ".norm");
-  RC_TRY(make_lin(e, s, {"model.generator.proj"}, c.tgt_vocab, c.d_model, &e->generator));
-  {
-    bool keep = e->bf16_mode;
-    e->bf16_mode = false;
-    int rc = make_lin(e, s, {lp + ".Length_classifier1", lp + ".Syntactic_classifier1"}, 100, c.d_model, &e->head1);
-    e->bf16_mode = keep;
-    RC_TRY(rc);
-  }
-  RC_TRY(e->head1t.reserve((size_t)200 * kD * 4));
-  launch_k(transpose_kernel, dim3(ceil_div(kD, 32), ceil_div(200, 32)), dim3(32, 8), 0, s, e->head1.w32, e->head1t.as<float>(), 200, kD);
-  CU_TRY(cudaGetLastError());
-  e->w_len2 = W(e, lp + ".Length_classifier2.weight");
-  e->b_len2 = W(e, lp + ".Length_classifier2.bias");
-  e->w_syn2 = W(e, lp + ".Syntactic_classifier2.weight");
-  e->b_syn2 = W(e, lp + ".Syntactic_classifier2.bias");
-  RC_TRY(e->bound_in.reserve((size_t)10 * e->Lb * kD * 4));
-  RC_TRY(e->fill_in.reserve((size_t)10 * e->L * kD * 4));
-  launch_k(build_tables_kernel, dim3(10, e->Lb), 128, 0, s, W(e, "model.syn_embed.lut.weight"), W(e, "model.tgt_embed.lut.weight"),
-                                                      W(e, "model.pos_embed.pe"), c.bos_idx, 10, e->Lb, e->L, sqrtf((float)kD),
-                                                      e->bound_in.as<float>(), e->fill_in.as<float>());
-  CU_TRY(cudaGetLastError());
-  const char* bg = getenv("BOFI_BOUND");
-  e->bound_fast = (c.n_len == 1) && !(bg && strcmp(bg, "generic") == 0);
-  if (e->bound_fast) RC_TRY(e->bf16_mode ? build_bound_tables<bf16>(e, s) : build_bound_tables<float>(e, s));
+  RC_TRY(refresh_derived(e, s));
   CU_TRY(cudaStreamSynchronize(s));
   e->finalized = true;
   return BOFI_OK;
@@ -1160,3 +1187,5 @@ int bofi_attention_f32(bofi_handle_t e, void* stream, const float* q, const floa
 }
 
 }  // extern "C"
+
+#include "train_abi.inl"

@@ -1,0 +1,198 @@
+// C ABI of the training path (declared in include/bofi_b200.h), included at the end of engine.cu.
+
+extern "C" int64_t bofi_param_numel(bofi_handle_t e) { return e ? e->flat_numel : -1; }
+
+extern "C" int bofi_param_offset(bofi_handle_t e, const char* name, int64_t* offset, int64_t* numel) {
+  if (!e || !name || !offset || !numel) return fail(BOFI_ERR_INVALID, "null argument");
+  auto it = e->weights.find(name);
+  if (it == e->weights.end()) return fail(BOFI_ERR_INVALID, "unknown state_dict key '%s'", name);
+  *offset = it->second.off;
+  *numel = it->second.numel;
+  return BOFI_OK;
+}
+
+extern "C" int bofi_train_bind(bofi_handle_t e, void* stream, float* flat_params, float* flat_grads) {
+  if (!e || !flat_params || !flat_grads) return fail(BOFI_ERR_INVALID, "null argument");
+  if (e->cfg.n_len != 1) return fail(BOFI_ERR_INVALID, "the training path is built for N_len == 1 (uic_sd.yml); got N_len = %d", e->cfg.n_len);
+  for (const std::string& n : e->order)
+    if (!e->weights[n].loaded) return fail(BOFI_ERR_STATE, "missing state_dict key '%s'", n.c_str());
+  CU_TRY(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (flat_params != e->flat_w) {
+    CU_TRY(cudaMemcpyAsync(flat_params, e->flat_w, (size_t)e->flat_numel * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    e->flat_own.release();
+    e->flat_w = flat_params;
+  }
+  e->flat_g = flat_grads;
+  RC_TRY(refresh_derived(e, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  e->finalized = true;
+  return BOFI_OK;
+}
+
+extern "C" int bofi_refresh_weights(bofi_handle_t e, void* stream) {
+  if (!e) return fail(BOFI_ERR_INVALID, "null handle");
+  CU_TRY(cudaSetDevice(e->device));
+  RC_TRY(refresh_derived(e, (cudaStream_t)stream));
+  e->finalized = true;
+  return BOFI_OK;
+}
+
+static int train_begin(bofi_handle_t e, cudaStream_t s, int32_t B, int32_t R, int32_t spi, int32_t Lt, int32_t P, const int32_t* labels,
+                       const int32_t* phrase_num, const int32_t* phrase_length, const int32_t* phrase_syn, const int32_t* ext_syn,
+                       const int32_t* ext_seq, const int32_t* sa_vis) {
+  if (!e->finalized) return fail(BOFI_ERR_STATE, "weights not finalised");
+  if (e->cfg.n_len != 1) return fail(BOFI_ERR_INVALID, "the training path is built for N_len == 1 (uic_sd.yml)");
+  if (B <= 0 || R <= 0 || R > kMaxKeys || spi <= 0 || Lt < 1 || Lt + 2 > 32 || P < 1 || P > Lt + 1)
+    return fail(BOFI_ERR_INVALID, "bad training batch B=%d R=%d seq_per_img=%d L=%d P=%d", B, R, spi, Lt, P);
+  if (!labels || !phrase_num || !phrase_length || !ext_syn || !ext_seq || !sa_vis) return fail(BOFI_ERR_INVALID, "null argument");
+  TrainState* ts = train_state(e);
+  ts->valid = false;
+  ts->arena.reset();
+  ts->B = B; ts->R = R; ts->spi = spi; ts->N = B * spi; ts->T = Lt; ts->Tb = Lt + 2; ts->P = P; ts->Mb = ts->N * P;
+  const int N = ts->N, Tb = ts->Tb;
+  RC_TRY(ts->zeros.reserve(16384 * 4));
+  CU_TRY(cudaMemsetAsync(ts->zeros.p, 0, 16384 * 4, s));
+  auto copy_i32 = [&](int*& dst, const int32_t* src, size_t n) -> int {
+    dst = aalloc<int>(ts, n);
+    A_TRY(dst);
+    CU_TRY(cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToDevice, s));
+    return BOFI_OK;
+  };
+  RC_TRY(copy_i32(ts->labels, labels, (size_t)N * Tb));
+  RC_TRY(copy_i32(ts->pnum, phrase_num, (size_t)N));
+  RC_TRY(copy_i32(ts->plen, phrase_length, (size_t)N * Tb));
+  ts->psyn = nullptr;
+  if (phrase_syn) RC_TRY(copy_i32(ts->psyn, phrase_syn, (size_t)N * Tb));
+  RC_TRY(copy_i32(ts->ext_syn, ext_syn, (size_t)N * Tb));
+  RC_TRY(copy_i32(ts->ext_seq, ext_seq, (size_t)N * Lt));
+  RC_TRY(copy_i32(ts->sa_vis, sa_vis, (size_t)N * Lt));
+  ts->word_seq = aalloc<int>(ts, (size_t)N * Tb); A_TRY(ts->word_seq);
+  ts->vis_b = aalloc<int>(ts, (size_t)N * P); A_TRY(ts->vis_b);
+  ts->na_vis = aalloc<int>(ts, (size_t)N); A_TRY(ts->na_vis);
+  ts->n_words = aalloc<int>(ts, (size_t)N); A_TRY(ts->n_words);
+  ts->total_words = aalloc<int>(ts, 64); A_TRY(ts->total_words);
+  return BOFI_OK;
+}
+
+extern "C" int bofi_train_forward(bofi_handle_t e, void* stream, const float* att_feats, const int32_t* att_len, int32_t B, int32_t R,
+                       int32_t seq_per_img, int32_t Lt, int32_t P, const int32_t* labels, const int32_t* phrase_num,
+                       const int32_t* phrase_length, const int32_t* ext_syn, const int32_t* ext_seq, const int32_t* sa_vis,
+                       float* sa_len_logp, float* sa_syn_logp, float* sa_logp, float* na_len_logp, float* na_syn_logp, float* na_logp) {
+  if (!e || !att_feats || !sa_len_logp || !sa_syn_logp || !sa_logp || !na_len_logp || !na_syn_logp || !na_logp)
+    return fail(BOFI_ERR_INVALID, "null argument");
+  CU_TRY(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  e->launches = 0;
+  RC_TRY(train_begin(e, s, B, R, seq_per_img, Lt, P, labels, phrase_num, phrase_length, nullptr, ext_syn, ext_seq, sa_vis));
+  TrainState* ts = train_state(e);
+  int rc = e->bf16_mode ? train_forward_impl<bf16>(e, s, ts, att_feats, att_len, sa_len_logp, sa_syn_logp, sa_logp, na_len_logp, na_syn_logp, na_logp, false)
+                        : train_forward_impl<float>(e, s, ts, att_feats, att_len, sa_len_logp, sa_syn_logp, sa_logp, na_len_logp, na_syn_logp, na_logp, false);
+  ts->valid = (rc == BOFI_OK);
+  return rc;
+}
+
+template <typename T>
+static int train_backward_dense(bofi_engine* e, cudaStream_t s, TrainState* ts, const float* g_sa_len, const float* g_sa_syn, const float* g_sa_logp,
+                                const float* g_na_len, const float* g_na_syn, const float* g_na_logp, const float* sa_len, const float* sa_syn,
+                                const float* sa_logp, const float* na_len, const float* na_syn, const float* na_logp) {
+  const int rows = ts->N * ts->T, ldz = round_up(e->V, 64);
+  RC_TRY(e->logits.reserve((size_t)2 * rows * ldz * sizeof(T)));
+  T* dz_sa = e->logits.as<T>();
+  T* dz_na = dz_sa + (size_t)rows * ldz;
+  e->launches += 2;
+  launch_k(logsoftmax_bwd_kernel<T>, rows, 512, 0, s, g_sa_logp, sa_logp, e->V, dz_sa, ldz);
+  CU_TRY(cudaGetLastError());
+  launch_k(logsoftmax_bwd_kernel<T>, rows, 512, 0, s, g_na_logp, na_logp, e->V, dz_na, ldz);
+  CU_TRY(cudaGetLastError());
+  return train_backward_impl<T>(e, s, ts, dz_sa, dz_na, ldz, g_sa_len, g_sa_syn, g_na_len, g_na_syn, sa_len, sa_syn, na_len, na_syn);
+}
+
+extern "C" int bofi_train_backward(bofi_handle_t e, void* stream, const float* g_sa_len, const float* g_sa_syn, const float* g_sa_logp,
+                        const float* g_na_len, const float* g_na_syn, const float* g_na_logp, const float* sa_len_logp,
+                        const float* sa_syn_logp, const float* sa_logp, const float* na_len_logp, const float* na_syn_logp,
+                        const float* na_logp) {
+  if (!e || !g_sa_len || !g_sa_syn || !g_sa_logp || !g_na_len || !g_na_syn || !g_na_logp || !sa_len_logp || !sa_syn_logp || !sa_logp ||
+      !na_len_logp || !na_syn_logp || !na_logp)
+    return fail(BOFI_ERR_INVALID, "null argument");
+  if (!e->flat_g) return fail(BOFI_ERR_STATE, "bofi_train_backward needs bofi_train_bind (gradient buffer)");
+  TrainState* ts = train_state(e);
+  if (!ts->valid) return fail(BOFI_ERR_STATE, "bofi_train_backward needs a preceding bofi_train_forward");
+  CU_TRY(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = e->bf16_mode ? train_backward_dense<bf16>(e, s, ts, g_sa_len, g_sa_syn, g_sa_logp, g_na_len, g_na_syn, g_na_logp, sa_len_logp, sa_syn_logp,
+                                                     sa_logp, na_len_logp, na_syn_logp, na_logp)
+                        : train_backward_dense<float>(e, s, ts, g_sa_len, g_sa_syn, g_sa_logp, g_na_len, g_na_syn, g_na_logp, sa_len_logp, sa_syn_logp,
+                                                      sa_logp, na_len_logp, na_syn_logp, na_logp);
+  ts->valid = false;          // the tape is consumed
+  return rc;
+}
+
+// Forward + LanguageModelCriterion_UIC (reduction='mean') + backward in one call; the [N, L, V] log-prob tensors and
+// their gradients are never materialised (the criterion's gradient is formed straight from the logits).
+template <typename T>
+static int train_step_impl(bofi_engine* e, cudaStream_t s, TrainState* ts, const float* att, const int* att_len, float* losses) {
+  const int N = ts->N, T_ = ts->T, Tb = ts->Tb, rows = N * T_, slots = N * (Tb - 1), ldz = round_up(e->V, 64);
+  // small outputs + loss scratch: [sa_len, sa_syn, na_len, na_syn] log-probs, their gradients, per-row NLLs, 6 sums
+  float* sa_len = aalloc<float>(ts, (size_t)slots * 20); A_TRY(sa_len);
+  float* sa_syn = aalloc<float>(ts, (size_t)slots * 10); A_TRY(sa_syn);
+  float* na_len = aalloc<float>(ts, (size_t)slots * 20); A_TRY(na_len);
+  float* na_syn = aalloc<float>(ts, (size_t)slots * 10); A_TRY(na_syn);
+  float* g_sa_len = aalloc<float>(ts, (size_t)slots * 20); A_TRY(g_sa_len);
+  float* g_sa_syn = aalloc<float>(ts, (size_t)slots * 10); A_TRY(g_sa_syn);
+  float* g_na_len = aalloc<float>(ts, (size_t)slots * 20); A_TRY(g_na_len);
+  float* g_na_syn = aalloc<float>(ts, (size_t)slots * 10); A_TRY(g_na_syn);
+  float* nll = aalloc<float>(ts, (size_t)2 * rows + 4 * slots); A_TRY(nll);
+  float* sums = aalloc<float>(ts, 64); A_TRY(sums);
+  CU_TRY(cudaMemsetAsync(ts->total_words, 0, 4, s));
+  launch_k(xe_count_words_kernel, ceil_div(N, 128), 128, 0, s, (const int*)ts->plen, N, Tb, ts->n_words, ts->total_words);
+  CU_TRY(cudaGetLastError());
+  RC_TRY(train_forward_impl<T>(e, s, ts, att, att_len, sa_len, sa_syn, nullptr, na_len, na_syn, nullptr, true));
+  RC_TRY(e->logits.reserve((size_t)2 * rows * ldz * sizeof(T)));
+  T* dz_sa = e->logits.as<T>();
+  T* dz_na = dz_sa + (size_t)rows * ldz;
+  float* nll_sa = nll, *nll_na = nll + rows, *nl_sa_len = nll + 2 * rows, *nl_sa_syn = nl_sa_len + slots, *nl_na_len = nl_sa_syn + slots,
+        *nl_na_syn = nl_na_len + slots;
+  e->launches += 11;
+  launch_k(xe_word_loss_bwd_kernel<T>, rows, 512, 0, s, (const float*)ts->sa_d.logits, e->Vpad, e->V, (const int*)ts->labels, Tb, 1, (const int*)ts->n_words,
+           T_, (const int*)ts->total_words, dz_sa, ldz, nll_sa);
+  CU_TRY(cudaGetLastError());
+  launch_k(xe_word_loss_bwd_kernel<T>, rows, 512, 0, s, (const float*)ts->na_d.logits, e->Vpad, e->V, (const int*)ts->labels, Tb, 1, (const int*)ts->n_words,
+           T_, (const int*)ts->total_words, dz_na, ldz, nll_na);
+  CU_TRY(cudaGetLastError());
+  launch_k(xe_box_loss_grad_kernel, ceil_div(slots, 128), 128, 0, s, (const float*)sa_len, (const float*)sa_syn, (const int*)ts->pnum, (const int*)ts->plen,
+           (const int*)ts->psyn, N, Tb, 20, 10, (const int*)ts->total_words, g_sa_len, g_sa_syn, nl_sa_len, nl_sa_syn);
+  CU_TRY(cudaGetLastError());
+  launch_k(xe_box_loss_grad_kernel, ceil_div(slots, 128), 128, 0, s, (const float*)na_len, (const float*)na_syn, (const int*)ts->pnum, (const int*)ts->plen,
+           (const int*)ts->psyn, N, Tb, 20, 10, (const int*)ts->total_words, g_na_len, g_na_syn, nl_na_len, nl_na_syn);
+  CU_TRY(cudaGetLastError());
+  // reference order: SA_length, SA_phrase, SA_syn, NA_length, NA_phrase, NA_syn
+  const float* parts[6] = {nl_sa_len, nll_sa, nl_sa_syn, nl_na_len, nll_na, nl_na_syn};
+  const int counts[6] = {slots, rows, slots, slots, rows, slots};
+  for (int i = 0; i < 6; ++i) {
+    launch_k(sum_kernel, 1, 1024, 0, s, parts[i], counts[i], sums + i, 1.0f);
+    CU_TRY(cudaGetLastError());
+  }
+  launch_k(xe_finish_losses_kernel, 1, 32, 0, s, (const float*)sums, (const int*)ts->total_words, losses);
+  CU_TRY(cudaGetLastError());
+  return train_backward_impl<T>(e, s, ts, dz_sa, dz_na, ldz, g_sa_len, g_sa_syn, g_na_len, g_na_syn, sa_len, sa_syn, na_len, na_syn);
+}
+
+extern "C" int bofi_train_step_xe(bofi_handle_t e, void* stream, const float* att_feats, const int32_t* att_len, int32_t B, int32_t R,
+                       int32_t seq_per_img, int32_t Lt, int32_t P, const int32_t* labels, const int32_t* phrase_num,
+                       const int32_t* phrase_length, const int32_t* phrase_syn, const int32_t* ext_syn, const int32_t* ext_seq,
+                       const int32_t* sa_vis, float* losses) {
+  if (!e || !att_feats || !losses || !phrase_syn) return fail(BOFI_ERR_INVALID, "null argument");
+  if (!e->flat_g) return fail(BOFI_ERR_STATE, "bofi_train_step_xe needs bofi_train_bind (gradient buffer)");
+  CU_TRY(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  e->launches = 0;
+  RC_TRY(train_begin(e, s, B, R, seq_per_img, Lt, P, labels, phrase_num, phrase_length, phrase_syn, ext_syn, ext_seq, sa_vis));
+  TrainState* ts = train_state(e);
+  int rc = e->bf16_mode ? train_step_impl<bf16>(e, s, ts, att_feats, att_len, losses) : train_step_impl<float>(e, s, ts, att_feats, att_len, losses);
+  ts->valid = false;
+  return rc;
+}
+
+extern "C" int bofi_train_launches(bofi_handle_t e) { return e ? e->launches : -1; }

@@ -140,6 +140,89 @@ class BofiEngine:
     def workspace_bytes(self, B, R, sample_n=1):
         return int(self.lib.bofi_workspace_bytes(self.handle, B, R, sample_n))
 
+    # ---- XE training (A16) ----------------------------------------------------------------------
+    def param_numel(self):
+        return int(self.lib.bofi_param_numel(self.handle))
+
+    def param_layout(self):
+        """name -> (offset, numel) inside the flat parameter / gradient buffers."""
+        out = {}
+        for name in state_spec(self.cfg):
+            off, n = C.c_int64(), C.c_int64()
+            _lib.check(self.lib.bofi_param_offset(self.handle, name.encode(), C.byref(off), C.byref(n)))
+            out[name] = (off.value, n.value)
+        return out
+
+    def train_bind(self):
+        """Allocates the flat parameter / gradient tensors, hands them to the library and returns them."""
+        n = self.param_numel()
+        self.flat_w = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.flat_g = torch.zeros(n, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bofi_train_bind(self.handle, self._stream(), _ptr(self.flat_w), _ptr(self.flat_g)))
+        return self.flat_w, self.flat_g
+
+    def refresh_weights(self):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bofi_refresh_weights(self.handle, self._stream()))
+
+    @staticmethod
+    def _i32(t):
+        return t.to(dtype=torch.int32).contiguous()
+
+    def _xe_inputs(self, att_feats, att_len, batch):
+        """batch: dict of 2-D caption-row tensors on the device (labels, phrase_num, phrase_length, [phrase_syn],
+        extend_phrase_syn_seq, extend_phrase_seq, sa_vis); returns the shapes and the int32 tensors (kept alive)."""
+        assert att_feats.is_cuda and att_feats.dtype == torch.float32
+        att_feats = att_feats.contiguous()
+        B, R, _ = att_feats.shape
+        labels = self._i32(batch["labels"])
+        N, Lb = labels.shape
+        assert N % B == 0, "caption rows must be a multiple of the image count"
+        ints = dict(labels=labels, phrase_num=self._i32(batch["phrase_num"]), phrase_length=self._i32(batch["phrase_length"]),
+                    ext_syn=self._i32(batch["extend_phrase_syn_seq"]), ext_seq=self._i32(batch["extend_phrase_seq"]),
+                    sa_vis=self._i32(batch["sa_vis"]))
+        if "phrase_syn" in batch and batch["phrase_syn"] is not None:
+            ints["phrase_syn"] = self._i32(batch["phrase_syn"])
+        if att_len is not None:
+            att_len = att_len.to(device=att_feats.device, dtype=torch.int32).contiguous()
+        P = int(batch["P"]) if "P" in batch else int(ints["phrase_num"].max())
+        return att_feats, att_len, ints, (B, R, N // B, Lb - 2, P, N, Lb)
+
+    def train_forward(self, att_feats, att_len, batch):
+        att_feats, att_len, ints, (B, R, spi, L, P, N, Lb) = self._xe_inputs(att_feats, att_len, batch)
+        V, dev = self.cfg.tgt_vocab, self.device
+        outs = [torch.empty(N, Lb - 1, 20, device=dev), torch.empty(N, Lb - 1, 10, device=dev), torch.empty(N, L, V, device=dev),
+                torch.empty(N, Lb - 1, 20, device=dev), torch.empty(N, Lb - 1, 10, device=dev), torch.empty(N, L, V, device=dev)]
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bofi_train_forward(
+                self.handle, self._stream(), _ptr(att_feats), _ptr(att_len), B, R, spi, L, P, _ptr(ints["labels"]),
+                _ptr(ints["phrase_num"]), _ptr(ints["phrase_length"]), _ptr(ints["ext_syn"]), _ptr(ints["ext_seq"]), _ptr(ints["sa_vis"]),
+                *[_ptr(o) for o in outs]))
+        self._train_keep = (att_feats, att_len, ints)      # fp32 mode reads att_feats again in the backward pass
+        return outs
+
+    def train_backward(self, grads, outs):
+        grads = [g.contiguous().float() for g in grads]
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bofi_train_backward(self.handle, self._stream(), *[_ptr(g) for g in grads], *[_ptr(o) for o in outs]))
+        self._train_keep = None
+
+    def train_step_xe(self, att_feats, att_len, batch):
+        """Fused forward + criterion + backward; returns the seven losses (device f32[7])."""
+        att_feats, att_len, ints, (B, R, spi, L, P, N, Lb) = self._xe_inputs(att_feats, att_len, batch)
+        losses = torch.empty(7, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bofi_train_step_xe(
+                self.handle, self._stream(), _ptr(att_feats), _ptr(att_len), B, R, spi, L, P, _ptr(ints["labels"]),
+                _ptr(ints["phrase_num"]), _ptr(ints["phrase_length"]), _ptr(ints["phrase_syn"]), _ptr(ints["ext_syn"]),
+                _ptr(ints["ext_seq"]), _ptr(ints["sa_vis"]), _ptr(losses)))
+        self._train_keep = (att_feats, att_len, ints)
+        return losses
+
+    def train_launches(self):
+        return int(self.lib.bofi_train_launches(self.handle))
+
     # ---- unit entry points (parity tests) ------------------------------------------------------
     def layernorm(self, x, a2, b2):
         out = torch.empty_like(x)

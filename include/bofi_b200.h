@@ -136,6 +136,52 @@ int bofi_get_profile(bofi_handle_t h, void* stream, int32_t* launches, double* m
  * (mnk[3]), with its launch count, milliseconds and 2*M*N*K flops summed over those launches. */
 int bofi_get_profile_top_gemm(bofi_handle_t h, void* stream, int32_t* mnk, int32_t* launches, double* ms, double* flops);
 
+/* ---- XE training --------------------------------------------------------------
+ * TransformerModel._forward for train_mode UIC (TransformerModel.py:1713-1775 -> EncoderDecoder_UIC.forward :413-468
+ * with glat_p < 0, ss_prob == 0) and its backward pass; LanguageModelCriterion_UIC (losses.py:315-369) fused in
+ * bofi_train_step_xe.  Built for N_len == 1 (uic_sd.yml).  Dropout is not applied (the reference's eval() arithmetic).
+ *
+ * Parameters and gradients live in two caller-owned flat fp32 device buffers of bofi_param_numel() elements;
+ * entry `name` of the state_dict occupies [offset, offset + numel) (bofi_param_offset).  The drop-in module makes
+ * its nn.Parameters views of these buffers, so an optimiser step on them needs no copy:
+ *   bofi_train_bind(h, stream, params, grads)    copy the loaded weights into `params`, adopt both buffers
+ *   bofi_refresh_weights(h, stream)              after the parameters changed: bf16 mirror + derived tables
+ * Gradients are ACCUMULATED into `grads` (zero them like optimizer.zero_grad()). */
+int64_t bofi_param_numel(bofi_handle_t h);
+int bofi_param_offset(bofi_handle_t h, const char* name, int64_t* offset, int64_t* numel);
+int bofi_train_bind(bofi_handle_t h, void* stream, float* flat_params, float* flat_grads);
+int bofi_refresh_weights(bofi_handle_t h, void* stream);
+
+/* Teacher-forced forward.  All pointers are device pointers; integer inputs are int32 with N = B * seq_per_img
+ * caption rows, L = loader seq_length (16), Lb = L + 2:
+ *   att_feats f32 [B,R,att_feat_size]; att_len i32 [B] or NULL
+ *   labels [N,Lb]; phrase_num [N]; phrase_length [N,Lb]; ext_syn = extend_phrase_syn_seq [N,Lb];
+ *   ext_seq = extend_phrase_seq [N,L]; sa_vis [N,L] = row sums of extend_phrase_seq_mask (a prefix mask,
+ *   dataloader.py:391); P = max(phrase_num) (bounding passes, :492).
+ * Outputs (f32, caller-owned, the six tensors of :1774-1775):
+ *   sa/na_len_logp [N,Lb-1,20], sa/na_syn_logp [N,Lb-1,10], sa/na_logp [N,L,V].
+ * Activations stay in the handle until the matching bofi_train_backward. */
+int bofi_train_forward(bofi_handle_t h, void* stream, const float* att_feats, const int32_t* att_len, int32_t B, int32_t R,
+                       int32_t seq_per_img, int32_t L, int32_t P, const int32_t* labels, const int32_t* phrase_num,
+                       const int32_t* phrase_length, const int32_t* ext_syn, const int32_t* ext_seq, const int32_t* sa_vis,
+                       float* sa_len_logp, float* sa_syn_logp, float* sa_logp, float* na_len_logp, float* na_syn_logp,
+                       float* na_logp);
+/* Backward of the last bofi_train_forward: g_* are the gradients of a scalar loss w.r.t. the six outputs (same shapes),
+ * the six outputs themselves are passed back (the handle does not keep them). */
+int bofi_train_backward(bofi_handle_t h, void* stream, const float* g_sa_len, const float* g_sa_syn, const float* g_sa_logp,
+                        const float* g_na_len, const float* g_na_syn, const float* g_na_logp, const float* sa_len_logp,
+                        const float* sa_syn_logp, const float* sa_logp, const float* na_len_logp, const float* na_syn_logp,
+                        const float* na_logp);
+/* One XE step without materialising the [N,L,V] log-probs: forward, criterion (reduction='mean'), backward.
+ * phrase_syn i32 [N,Lb] are the syn targets.  losses: device f32[7] = total, SA_length, SA_phrase, SA_syn, NA_length,
+ * NA_phrase, NA_syn (the return order of losses.py:369). */
+int bofi_train_step_xe(bofi_handle_t h, void* stream, const float* att_feats, const int32_t* att_len, int32_t B, int32_t R,
+                       int32_t seq_per_img, int32_t L, int32_t P, const int32_t* labels, const int32_t* phrase_num,
+                       const int32_t* phrase_length, const int32_t* phrase_syn, const int32_t* ext_syn, const int32_t* ext_seq,
+                       const int32_t* sa_vis, float* losses);
+/* Kernels enqueued by the last training call. */
+int bofi_train_launches(bofi_handle_t h);
+
 /* ---- unit entry points (used by the parity tests to pin individual kernels) ------------------- */
 /* LayerNorm of TransformerModel.py:1338-1349 on rows x d_model fp32 (dev pointers). */
 int bofi_layernorm_f32(bofi_handle_t h, void* stream, const float* x, const float* a2, const float* b2,

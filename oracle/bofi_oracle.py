@@ -408,10 +408,12 @@ class BofiOracle:
             phrase_length = phrase_length.reshape(-1, phrase_length.shape[2])
             phrase_syn = phrase_syn.reshape(-1, phrase_syn.shape[2])
             labels = labels.reshape(-1, labels.shape[2])
+        dev = sa_logp.device
+        phrase_num, phrase_length, phrase_syn, labels = [t.to(dev) for t in (phrase_num, phrase_length, phrase_syn, labels)]
         words = labels[:, 1:-1].long()
         T = words.shape[1]
-        word_mask = (torch.arange(T)[None, :] < (phrase_length.sum(1) - 1)[:, None]).to(sa_logp.dtype)
-        box_mask = (torch.arange(phrase_length.shape[1] - 1)[None, :] < phrase_num[:, None]).to(sa_logp.dtype)
+        word_mask = (torch.arange(T, device=dev)[None, :] < (phrase_length.sum(1) - 1)[:, None]).to(sa_logp.dtype)
+        box_mask = (torch.arange(phrase_length.shape[1] - 1, device=dev)[None, :] < phrase_num[:, None]).to(sa_logp.dtype)
         len_t, syn_t = phrase_length[:, 1:].long(), phrase_syn[:, 1:].long()
         nll = lambda lp, tgt, m: -(lp.gather(2, tgt.unsqueeze(2)).squeeze(2) * m).sum()
         denom = word_mask.sum()

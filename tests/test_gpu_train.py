@@ -1,0 +1,146 @@
+"""XE-training path through the drop-in model and the C ABI against the oracle:
+forward log-probs, criterion values and every parameter gradient.  The oracle itself is pinned to the unmodified
+reference by tests/test_oracle_golden_xe.py."""
+import numpy as np
+import pytest
+import torch
+
+from boficap_b200 import synth
+from boficap_b200.layout import BofiConfig
+
+pytestmark = pytest.mark.gpu
+
+CASES = [(2, 12, False, 3), (3, 20, True, 5)]
+_ORACLE = {}
+
+
+def oracle_run(B, R, adaptive, seed):
+    """Oracle forward + criterion + autograd gradients on the CPU (cached per case)."""
+    key = (B, R, adaptive, seed)
+    if key not in _ORACLE:
+        from oracle.bofi_oracle import BofiOracle, OracleConfig
+        cfg = BofiConfig()
+        sd = synth.synth_state_dict(cfg, 0, "s_real")
+        for k, v in sd.items():
+            if k != "model.pos_embed.pe":
+                v.requires_grad_(True)
+        o = BofiOracle.__new__(BofiOracle)
+        o.sd, o.cfg, o.record, o.trace = sd, OracleConfig(**cfg.to_dict()), False, {}
+        fc, att, masks = synth.synth_inputs(B, R, seed=7, adaptive=adaptive)
+        bt = synth.synth_xe_batch(B, seed=seed, vocab_size=cfg.vocab_size)
+        outs = o.forward_xe(att, masks, bt["labels"], bt["phrase_num"], bt["phrase_length"], bt["extend_phrase_syn_seq"],
+                            bt["extend_phrase_seq"], bt["extend_phrase_seq_mask"])
+        loss, parts = o.loss_xe(outs, bt["phrase_num"], bt["phrase_length"], bt["phrase_syn"], bt["labels"])
+        loss.backward()
+        grads = {k: (v.grad.detach().clone() if v.grad is not None else torch.zeros_like(v)) for k, v in sd.items() if k != "model.pos_embed.pe"}
+        _ORACLE[key] = dict(outs=[t.detach() for t in outs], losses=[float(loss)] + [float(p) for p in parts], grads=grads)
+    return _ORACLE[key]
+
+
+def build_model(precision):
+    from boficap_b200.captioning import models
+    cfg = BofiConfig()
+    sd = synth.synth_state_dict(cfg, 0, "s_real")
+    infos = synth.make_infos(cfg)
+    opt = infos["opt"]
+    opt.vocab = infos["vocab"]
+    opt.bofi_precision = precision
+    model = models.setup(opt)
+    model.load_state_dict(sd)
+    return model.cuda(), cfg
+
+
+def batch_args(B, R, adaptive, seed, cfg):
+    fc, att, masks = synth.synth_inputs(B, R, seed=7, adaptive=adaptive)
+    bt = synth.synth_xe_batch(B, seed=seed, vocab_size=cfg.vocab_size)
+    args = (fc.cuda(), att.cuda(), bt["labels"].cuda(), masks.cuda() if masks is not None else None, bt["phrase_num"].cuda(),
+            bt["phrase_length"].cuda(), bt["phrase_syn"].cuda(), bt["extend_phrase_syn_seq"].cuda(), bt["extend_phrase_seq"].cuda(),
+            bt["extend_phrase_seq_mask"].cuda())
+    return args, bt
+
+
+def grad_report(model, ref_grads):
+    """Worst per-parameter error |g - g_ref|_max / max(|g_ref|_max, floor) and the worst cosine.  floor = 1e-4 x the
+    largest gradient entry of the model: tensors whose true gradient is zero up to rounding (the K-projection biases:
+    softmax is invariant to a constant added to every score of a row) are compared on the absolute scale."""
+    gmax = max(float(r.abs().max()) for r in ref_grads.values())
+    floor = 1e-4 * gmax
+    worst, worst_name, worst_cos = 0.0, None, 1.0
+    for name, p in model.named_parameters():
+        g = p.grad.detach().float().cpu()
+        r = ref_grads[name]
+        err = float((g - r).abs().max()) / max(float(r.abs().max()), floor)
+        if err > worst:
+            worst, worst_name = err, name
+        if float(r.abs().max()) > floor:
+            cos = float((g.double().flatten() @ r.double().flatten()) / (g.double().norm() * r.double().norm() + 1e-30))
+            worst_cos = min(worst_cos, cos)
+    return worst, worst_name, worst_cos
+
+
+@pytest.mark.parametrize("B,R,adaptive,seed", CASES)
+def test_xe_forward_backward_fp32(B, R, adaptive, seed):
+    from oracle.bofi_oracle import BofiOracle
+    ref = oracle_run(B, R, adaptive, seed)
+    model, cfg = build_model("fp32")
+    args, bt = batch_args(B, R, adaptive, seed, cfg)
+    outs = model(*args)                                     # mode='forward' (CaptionModel.py:42-46)
+    for got, want, name in zip(outs, ref["outs"], ("sa_len", "sa_syn", "sa_logp", "na_len", "na_syn", "na_logp")):
+        err = float((got.detach().cpu() - want).abs().max())
+        assert err < 1e-4, (name, err)
+    loss, parts = BofiOracle.loss_xe(outs, bt["phrase_num"], bt["phrase_length"], bt["phrase_syn"], bt["labels"])
+    np.testing.assert_allclose([float(loss)] + [float(p) for p in parts], ref["losses"], rtol=2e-5)
+    model.zero_grad()
+    loss.backward()
+    worst, name, cos = grad_report(model, ref["grads"])
+    assert worst < 2e-3 and cos > 0.99999, (worst, name, cos)
+
+
+@pytest.mark.parametrize("B,R,adaptive,seed", CASES[:1])
+def test_xe_fused_step_fp32(B, R, adaptive, seed):
+    ref = oracle_run(B, R, adaptive, seed)
+    model, cfg = build_model("fp32")
+    args, bt = batch_args(B, R, adaptive, seed, cfg)
+    model.train_bind()
+    model.zero_grad()
+    losses = model.xe_step(*args)
+    np.testing.assert_allclose(losses.cpu().numpy(), ref["losses"], rtol=2e-5)
+    worst, name, cos = grad_report(model, ref["grads"])
+    assert worst < 2e-3 and cos > 0.99999, (worst, name, cos)
+    # gradients accumulate (optimizer.zero_grad semantics)
+    g1 = model.flat_grads().clone()
+    model.xe_step(*args)
+    torch.testing.assert_close(model.flat_grads(), 2 * g1, rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("B,R,adaptive,seed", CASES[:1])
+def test_xe_fused_step_bf16(B, R, adaptive, seed):
+    ref = oracle_run(B, R, adaptive, seed)
+    model, cfg = build_model("bf16")
+    args, bt = batch_args(B, R, adaptive, seed, cfg)
+    model.train_bind()
+    model.zero_grad()
+    losses = model.xe_step(*args).cpu().numpy()
+    np.testing.assert_allclose(losses, ref["losses"], rtol=2e-2)
+    worst, name, cos = grad_report(model, ref["grads"])
+    print("bf16 XE step: worst relative gradient error %.3f (%s), worst cosine %.5f" % (worst, name, cos))
+    assert cos > 0.98, (worst, name, cos)
+
+
+def test_xe_optimizer_step_refreshes_weights():
+    """An in-place optimiser step on the shared parameter buffer is picked up by the next forward."""
+    B, R, adaptive, seed = CASES[0]
+    model, cfg = build_model("fp32")
+    args, bt = batch_args(B, R, adaptive, seed, cfg)
+    model.train_bind()
+    opt = torch.optim.SGD(model.parameters(), lr=1e-3)
+    first = None
+    for _ in range(4):
+        model.zero_grad()
+        losses = model.xe_step(*args)
+        opt.step()
+        first = float(losses[0]) if first is None else first
+    assert float(losses[0]) < first, (first, float(losses[0]))
+    # the sampling path sees the updated weights as well
+    seq = model(args[0], args[1], None, opt={"sample_method": "greedy", "train_mode": "NAIC"}, mode="sample")[0]
+    assert seq.shape == (B, cfg.seq_length)
