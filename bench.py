@@ -118,6 +118,106 @@ def cpu_reference_run(steps, warmup, cfg, sd, R, mode, images=CPU_SAMPLE_IMAGES)
     return images * steps / dt, dt / steps, torch.get_num_threads(), o.last_steps
 
 
+def bench_xe(a, rank, local_rank, world):
+    """Config 5 of BASELINE.json: uic_sd XE training step, `--batch` images x 5 captions per GPU (default 256), forward +
+    LanguageModelCriterion_UIC + backward in the library, NCCL all-reduce of the flat gradient buffer, Adam on the flat
+    parameter buffer (torch's fused optimiser: plumbing), weight refresh.  One JSON line (not the headline metric)."""
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from boficap_b200 import synth
+    from boficap_b200.captioning import models
+    from boficap_b200.layout import BofiConfig
+    cfg = BofiConfig()
+    B = 256 if a.batch == 1024 else a.batch
+    R, spi = a.regions, 5
+    infos = synth.make_infos(cfg)
+    opt = infos["opt"]
+    opt.vocab = infos["vocab"]
+    opt.bofi_precision = a.precision
+    model = models.setup(opt)
+    model.load_state_dict(synth.synth_state_dict(cfg, 0, a.calib))
+    model = model.cuda()
+    model.train_bind()
+    flat_w, flat_g = model.flat_params(), model.flat_grads()
+    flat_p = torch.nn.Parameter(flat_w)          # same storage: Adam over the whole buffer == Adam over every tensor
+    flat_p.grad = flat_g
+    optim = torch.optim.Adam([flat_p], lr=1e-5, betas=(0.9, 0.98), eps=1e-9, fused=True)
+    fc, att, masks = synth.synth_inputs(B, R, seed=1 + rank, adaptive=a.adaptive)
+    bt = synth.synth_xe_batch(B, seq_per_img=spi, seed=11 + rank, vocab_size=cfg.vocab_size)
+    dev = lambda t: t.cuda() if t is not None else None
+    args = (dev(fc), dev(att), dev(bt["labels"]), dev(masks), dev(bt["phrase_num"]), dev(bt["phrase_length"]), dev(bt["phrase_syn"]),
+            dev(bt["extend_phrase_syn_seq"]), dev(bt["extend_phrase_seq"]), dev(bt["extend_phrase_seq_mask"]))
+    eng = model._engine
+
+    def step():
+        flat_g.zero_()
+        losses = model.xe_step(*args)
+        if dist is not None:
+            dist.all_reduce(flat_g)
+            flat_g.div_(world)
+        optim.step()
+        eng.refresh_weights()
+        return losses
+
+    for _ in range(max(3, a.warmup)):
+        losses = step()
+    torch.cuda.synchronize()
+    first = float(losses[0])
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        losses = step()
+    e1.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    launches = eng.train_launches()
+    # per-class profile of one more step
+    eng.set_profiling(True)
+    flat_g.zero_()
+    model.xe_step(*args)
+    prof = eng.get_profile()
+    eng.set_profiling(False)
+    if rank == 0:
+        g = prof["gemm_tcgen05"] if a.precision == "bf16" else prof["gemm_ffma"]
+        burst, sustained, hbm, how = measured_peaks()
+        tf = g["flops"] / (g["ms"] / 1e3) / 1e12 if g["ms"] > 0 else 0.0
+        total_ms = sum(v["ms"] for v in prof.values())
+        line = {"metric": "XE training images/sec (uic_sd, %d captions/image, %dx2048 regions)" % (spi, R),
+                "value": world * B * a.steps / (ms / 1e3), "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
+                "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": a.precision,
+                "data": "synthetic",
+                "config": {"workload": "uic_sd XE training step (forward + criterion + backward + all-reduce + Adam), %d images x %d captions per GPU, "
+                                       "%d regions, %s, dropout off" % (B, spi, R, a.precision),
+                           "parallelism": "data-parallel replicas x%d, one NCCL all-reduce of the %.0f MB flat gradient buffer" % (world, flat_g.numel() * 4 / 1e6)},
+                "loss_first": first, "loss_last": float(losses[0]), "gpu_launches": launches * a.steps, "clocks": clocks,
+                "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05), all %d launches of a step" % g["launches"],
+                             "achieved": tf, "peak": sustained, "unit": "TFLOP/s", "frac": tf / sustained, "traffic": None,
+                             "share_of_profiled_kernel_time": g["ms"] / total_ms if total_ms else None,
+                             "classes": {k: {"launches": v["launches"], "ms": round(v["ms"], 3)} for k, v in prof.items()}}}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -132,12 +232,16 @@ def main():
     ap.add_argument("--calib", default="s_real")
     ap.add_argument("--no-logprobs", action="store_true", help="skip materialising the [B,20,V] log-prob tensor")
     ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--workload", default="decode", choices=["decode", "xe"],
+                    help="decode = BASELINE.json's headline metric; xe = XE training step (config 5: 256 images x 5 captions per GPU)")
     ap.add_argument("--depth", type=int, default=2, help="batches in flight (engine handles x streams, boficap_b200/pipeline.py)")
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    if a.workload == "xe":
+        return bench_xe(a, rank, local_rank, world)
 
     from boficap_b200 import synth
     from boficap_b200.layout import BofiConfig

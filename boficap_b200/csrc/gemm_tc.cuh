@@ -70,9 +70,23 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, N >> 3, M >> 4.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// MN-major, 128-byte-swizzled operand tile: the source matrix is stored [contraction][MN] (MN contiguous), a TMA box of
+// 64 MN-elements x 64 contraction rows lands as 64 rows of 128 B (8-row swizzle atoms 1024 B apart = SBO), and the
+// 64-element MN blocks of a tile are 8192 B apart (= LBO).  Canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in
+// 16-byte units (cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::MN>).
+__device__ __forceinline__ uint64_t make_sw128_desc_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(8192u >> 4) << 16;
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, N >> 3, M >> 4; bits 15 / 16 = A / B is MN-major.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, bool a_mn = false, bool b_mn = false) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -130,7 +144,9 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // Persistent: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, +gridDim.x, ... (N fastest, so
 // the CTAs resident at one time share A panels through L2).  Two accumulator tiles live in TMEM
 // (2 x BN columns): the epilogue of tile i overlaps the main loop of tile i+1.
-template <int BN, int STAGES, typename TOut, bool RELU, bool RESID>
+// A_MN / B_MN: that operand is read from a [K, M] / [K, N] matrix (the contraction index is the ROW of the source):
+// weight gradients dW = dY^T . X (both MN-major) and input gradients dX = dY . W (B MN-major) need no transposed copies.
+template <int BN, int STAGES, typename TOut, bool RELU, bool RESID, bool A_MN = false, bool B_MN = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, const float* residual, int ldr,
@@ -147,7 +163,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nk = K / kBK;
+  const int nk = (K + kBK - 1) / kBK;          // a K tail is zero-filled by TMA (out-of-bounds box elements)
   const int tiles_n = (N + BN - 1) / BN;
 
   if (warp == 0 && lane == 0) {
@@ -193,14 +209,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t fb = smem_u32(&full_bar[s]);
           mbar_expect_tx(fb, L::kStageBytes);
           const uint32_t a_dst = smem_u32(smem + s * L::kStageBytes);
-          tma_load_2d(a_dst, &tmA, fb, kb * kBK, m0);
-          tma_load_2d(a_dst + L::kABytes, &tmB, fb, kb * kBK, n0);
+          if constexpr (!A_MN) {
+            tma_load_2d(a_dst, &tmA, fb, kb * kBK, m0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < kBM / 64; ++i) tma_load_2d(a_dst + i * 8192, &tmA, fb, m0 + 64 * i, kb * kBK);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(a_dst + L::kABytes, &tmB, fb, kb * kBK, n0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i) tma_load_2d(a_dst + L::kABytes + i * 8192, &tmB, fb, n0 + 64 * i, kb * kBK);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN);
+      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, A_MN, B_MN);
       int it = 0, t = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
         const int as = t & 1;
@@ -214,12 +240,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(smem_u32(&full_bar[s]), ph);
           tcgen05_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
-          const uint64_t adesc = make_sw128_desc(a_addr);
-          const uint64_t bdesc = make_sw128_desc(a_addr + L::kABytes);
+          const uint64_t adesc = A_MN ? make_sw128_desc_mn(a_addr) : make_sw128_desc(a_addr);
+          const uint64_t bdesc = B_MN ? make_sw128_desc_mn(a_addr + L::kABytes) : make_sw128_desc(a_addr + L::kABytes);
+          // per K step of 16: K-major +32 bytes inside the 128-byte swizzle row; MN-major +16 rows of 128 bytes (encoded >> 4)
+          constexpr uint64_t a_step = A_MN ? 128 : 2, b_step = B_MN ? 128 : 2;
 #pragma unroll
           for (int k = 0; k < kBK / kUK; ++k) {
-            // +32 bytes per K step inside the 128-byte swizzle row (encoded >> 4)
-            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            umma_bf16(tmem_d, adesc + a_step * k, bdesc + b_step * k, idesc, (kb | k) != 0);
           }
           umma_commit(smem_u32(&empty_bar[s]));      // frees the smem stage when these MMAs retire
         }
@@ -387,20 +414,20 @@ inline int num_sms() {
   return n;
 }
 
-template <int BN, int STAGES, typename TOut, bool RELU, bool RESID>
+template <int BN, int STAGES, typename TOut, bool RELU, bool RESID, bool A_MN = false, bool B_MN = false>
 inline cudaError_t launch(cudaStream_t s, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                           const float* bias, const float* residual, int ldr, int M, int N, int K, int relu,
                           const int* live_rows) {
   using L = SmemLayout<BN, STAGES>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, TOut, RELU, RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, TOut, RELU, RESID, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const int ntiles = ((M + kBM - 1) / kBM) * ((N + BN - 1) / BN);
   const int grid = ntiles < num_sms() ? ntiles : num_sms();
-  launch_k(gemm_tc_kernel<BN, STAGES, TOut, RELU, RESID>, grid, kThreads, L::kTotal, s, tmA, tmB, tmC, bias, residual, ldr, M, N, K, relu, live_rows);
+  launch_k(gemm_tc_kernel<BN, STAGES, TOut, RELU, RESID, A_MN, B_MN>, grid, kThreads, L::kTotal, s, tmA, tmB, tmC, bias, residual, ldr, M, N, K, relu, live_rows);
   return cudaGetLastError();
 }
 
@@ -438,7 +465,7 @@ inline cudaError_t gemm_tc(cudaStream_t s, const bf16* A, int lda, const bf16* W
                            const float* residual, int ldr, TOut* C, int ldc, int M, int N, int K, int relu,
                            const int* live_rows) {
   if (M <= 0 || N <= 0) return cudaSuccess;
-  if (K % kBK != 0 || lda % 8 != 0 || ldw % 8 != 0 || (ldc * sizeof(TOut)) % 16 != 0 || (residual && ldr % 4 != 0))
+  if (lda % 8 != 0 || ldw % 8 != 0 || (ldc * sizeof(TOut)) % 16 != 0 || (residual && ldr % 4 != 0))
     return cudaErrorInvalidValue;
   const int tiles256 = ((M + kBM - 1) / kBM) * ((N + 255) / 256);
   const bool wide = tiles256 >= num_sms() / 2;      // small problems: narrower tiles spread over more SMs
@@ -461,6 +488,36 @@ inline cudaError_t gemm_tc(cudaStream_t s, const bf16* A, int lda, const bf16* W
     return wide ? BOFI_TC_LAUNCH(256, 4, false, false) : BOFI_TC_LAUNCH(64, 6, false, false);
   }
 #undef BOFI_TC_LAUNCH
+}
+
+// Backward-pass contractions without transposed copies (bias must point at >= N zeros):
+//   dgrad:  C[M,N] (bf16)  = A[M,K] . Bt[K,N]                 A K-major (pitch lda), Bt = the weight as stored [K,N] (pitch ldb)
+//   wgrad:  C[M,N] (fp32) += At[K,M]^T . Bt[K,N]              At = dY as stored [rows, M], Bt = X as stored [rows, N]; residual = C
+inline cudaError_t gemm_tc_dgrad(cudaStream_t s, const bf16* A, int lda, const bf16* Bt, int ldb, const float* zero_bias, bf16* C, int ldc,
+                                 int M, int N, int K) {
+  if (M <= 0 || N <= 0) return cudaSuccess;
+  if (lda % 8 != 0 || ldb % 8 != 0 || ldc % 8 != 0) return cudaErrorInvalidValue;
+  const int tiles256 = ((M + kBM - 1) / kBM) * ((N + 255) / 256);
+  const bool wide = tiles256 >= num_sms() / 2;
+  const CUtensorMap* tmA = cached_tmap(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBM);
+  const CUtensorMap* tmB = cached_tmap(Bt, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64);
+  const CUtensorMap* tmC = cached_tmap(C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, 2);
+  if (!tmA || !tmB || !tmC) return cudaErrorInvalidValue;
+  return wide ? launch<256, 4, bf16, false, false, false, true>(s, *tmA, *tmB, *tmC, zero_bias, nullptr, 0, M, N, K, 0, nullptr)
+              : launch<64, 6, bf16, false, false, false, true>(s, *tmA, *tmB, *tmC, zero_bias, nullptr, 0, M, N, K, 0, nullptr);
+}
+inline cudaError_t gemm_tc_wgrad(cudaStream_t s, const bf16* At, int lda, const bf16* Bt, int ldb, const float* zero_bias, float* C, int ldc,
+                                 int M, int N, int K) {
+  if (M <= 0 || N <= 0) return cudaSuccess;
+  if (lda % 8 != 0 || ldb % 8 != 0 || ldc % 4 != 0) return cudaErrorInvalidValue;
+  const int tiles256 = ((M + kBM - 1) / kBM) * ((N + 255) / 256);
+  const bool wide = tiles256 >= num_sms() / 2;
+  const CUtensorMap* tmA = cached_tmap(At, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64);
+  const CUtensorMap* tmB = cached_tmap(Bt, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64);
+  const CUtensorMap* tmC = cached_tmap(C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, 4);
+  if (!tmA || !tmB || !tmC) return cudaErrorInvalidValue;
+  return wide ? launch<256, 4, float, false, true, true, true>(s, *tmA, *tmB, *tmC, zero_bias, C, ldc, M, N, K, 0, nullptr)
+              : launch<64, 6, float, false, true, true, true>(s, *tmA, *tmB, *tmC, zero_bias, C, ldc, M, N, K, 0, nullptr);
 }
 
 }  // namespace tc

@@ -92,7 +92,7 @@ struct TrainState {
   std::vector<void*> kv;          // [B*R, 1024] per bounding / decoder layer
   BoundTape sa_b, na_b;
   DecTape sa_d, na_d;
-  DevBuf tr_a, tr_b, tr_w, zeros, ln_partial, scratch_f32, dkv, dmem;
+  DevBuf tr_a, tr_b, tr_w, zeros, ln_partial, cs_partial, scratch_f32, dkv, dmem;
 };
 
 static TrainState* train_state(bofi_engine* e);
@@ -327,30 +327,67 @@ static int gemm_nt(bofi_engine* e, cudaStream_t s, TrainState* ts, const T* A, i
 
 template <typename TIn, typename TOut>
 static int transpose_pad(bofi_engine* e, cudaStream_t s, const TIn* in, int ld_in, TOut* out, int rows, int cols, int rows_pad) {
-  e->launches++;
+  ProfScope prof(e, s, PC_OTHER, 0.0, (double)rows * cols * sizeof(TIn) + (double)rows_pad * cols * sizeof(TOut));
   launch_k(transpose_pad_kernel<TIn, TOut>, dim3(ceil_div(cols, 32), ceil_div(rows_pad, 32)), dim3(32, 8), 0, s, in, ld_in, out, rows, cols,
            rows_pad);
   CU_TRY(cudaGetLastError());
   return BOFI_OK;
 }
 
+// gb[c] += sum_r dY[r, c] in two fixed-order stages (row chunks, then the chunk partials).
+template <typename T>
+static int colsum(bofi_engine* e, cudaStream_t s, TrainState* ts, const T* dY, int ldy, int M, int N, float* gb) {
+  const int chunks = std::max(1, std::min(64, M / 256));
+  RC_TRY(ts->cs_partial.reserve((size_t)chunks * N * 4));
+  {
+    ProfScope prof(e, s, PC_OTHER, 0.0, (double)M * N * sizeof(T));
+    launch_k(colsum_partial_kernel<T>, dim3(ceil_div(N, 32), chunks), dim3(32, 8), 0, s, dY, ldy, M, N, ts->cs_partial.as<float>());
+  }
+  CU_TRY(cudaGetLastError());
+  {
+    ProfScope prof(e, s, PC_OTHER, 0.0, 0.0);
+    launch_k(colsum_reduce_kernel, ceil_div(N, 256), 256, 0, s, (const float*)ts->cs_partial.as<float>(), chunks, N, gb);
+  }
+  CU_TRY(cudaGetLastError());
+  return BOFI_OK;
+}
+
 // Backward of y = x . W^T + b for one (possibly fused) Linear:  gW += dY^T . X,  gb += colsum(dY),  dX = dY . W.
-//   X [M, K] pitch ldx, dY [M, N] pitch ldy (pad columns up to round_up(N, 64) must be zero when N % 64 != 0).
+//   X [M, K] pitch ldx, dY [M, N] pitch ldy.
+// bf16 (tcgen05): both contractions read their operands as stored -- MN-major UMMA descriptors, no transposed copies.
+// fp32 (FFMA parity backend): explicit zero-padded transposes feed the NT kernel (dY pad columns up to
+// round_up(N, 64) must be zero when N % 64 != 0).
 template <typename T>
 static int lin_bwd(bofi_engine* e, cudaStream_t s, TrainState* ts, const Lin& lin, const T* X, int ldx, const T* dY, int ldy, int M,
                    T* dX, int lddx) {
   const int N = lin.N, K = lin.K, Mp = round_up(M, 64);
+  const bool tc = std::is_same<T, bf16>::value && e->use_tc;
   if (lin.gw) {
-    RC_TRY(ts->tr_a.reserve((size_t)N * Mp * sizeof(T)));
-    RC_TRY(ts->tr_b.reserve((size_t)K * Mp * sizeof(T)));
-    RC_TRY((transpose_pad<T, T>(e, s, dY, ldy, ts->tr_a.as<T>(), M, N, Mp)));
-    RC_TRY((transpose_pad<T, T>(e, s, X, ldx, ts->tr_b.as<T>(), M, K, Mp)));
-    RC_TRY((gemm_nt<T, float>(e, s, ts, ts->tr_a.as<T>(), Mp, ts->tr_b.as<T>(), Mp, N, K, Mp, lin.gw, K, lin.gw, K)));
-    e->launches++;
-    launch_k(colsum_kernel<T>, ceil_div(N, 32), dim3(32, 8), 0, s, dY, ldy, M, N, lin.gb, 1.0f, 1);
-    CU_TRY(cudaGetLastError());
+    if constexpr (std::is_same<T, bf16>::value) {
+      if (tc) {
+        ProfScope prof(e, s, PC_GEMM_TC, 2.0 * M * N * K, 2.0 * ((double)M * N + (double)M * K) + 8.0 * N * K, N, K, M);
+        cudaError_t err = tc::gemm_tc_wgrad(s, dY, ldy, X, ldx, ts->zeros.as<float>(), lin.gw, K, N, K, M);
+        if (err != cudaSuccess) return fail(BOFI_ERR_CUDA, "wgrad GEMM %dx%dx%d: %s", N, K, M, cudaGetErrorString(err));
+      }
+    }
+    if (!tc) {
+      RC_TRY(ts->tr_a.reserve((size_t)N * Mp * sizeof(T)));
+      RC_TRY(ts->tr_b.reserve((size_t)K * Mp * sizeof(T)));
+      RC_TRY((transpose_pad<T, T>(e, s, dY, ldy, ts->tr_a.as<T>(), M, N, Mp)));
+      RC_TRY((transpose_pad<T, T>(e, s, X, ldx, ts->tr_b.as<T>(), M, K, Mp)));
+      RC_TRY((gemm_nt<T, float>(e, s, ts, ts->tr_a.as<T>(), Mp, ts->tr_b.as<T>(), Mp, N, K, Mp, lin.gw, K, lin.gw, K)));
+    }
+    RC_TRY(colsum<T>(e, s, ts, dY, ldy, M, N, lin.gb));
   }
   if (dX) {
+    if constexpr (std::is_same<T, bf16>::value) {
+      if (tc) {
+        ProfScope prof(e, s, PC_GEMM_TC, 2.0 * M * N * K, 2.0 * ((double)M * N + (double)N * K + (double)M * K), M, K, N);
+        cudaError_t err = tc::gemm_tc_dgrad(s, dY, ldy, lin.w16, K, ts->zeros.as<float>(), dX, lddx, M, K, N);
+        if (err != cudaSuccess) return fail(BOFI_ERR_CUDA, "dgrad GEMM %dx%dx%d: %s", M, K, N, cudaGetErrorString(err));
+        return BOFI_OK;
+      }
+    }
     const int Np = round_up(N, 64);
     if (ldy < Np) return fail(BOFI_ERR_INVALID, "lin_bwd: dY pitch %d < padded N %d", ldy, Np);
     RC_TRY(ts->tr_w.reserve((size_t)K * Np * sizeof(T)));
@@ -370,10 +407,15 @@ static int ln_bwd(bofi_engine* e, cudaStream_t s, TrainState* ts, const Norm& n,
                   float* dx_out, T* dx_out_t, int rows) {
   const int grid = std::min(ceil_div(rows, 8), 148 * 4);
   RC_TRY(ts->ln_partial.reserve((size_t)grid * 2 * kD * 4));
-  e->launches += 2;
-  launch_k(layernorm_bwd_kernel<TG, T>, grid, 256, 0, s, x, n.a, dy, dres, dx_out, dx_out_t, rows, ts->ln_partial.as<float>());
+  {
+    ProfScope prof(e, s, PC_LAYERNORM, 0.0, (double)rows * kD * (4 + sizeof(TG) + 4 + 4 + sizeof(T)));
+    launch_k(layernorm_bwd_kernel<TG, T>, grid, 256, 0, s, x, n.a, dy, dres, dx_out, dx_out_t, rows, ts->ln_partial.as<float>());
+  }
   CU_TRY(cudaGetLastError());
-  launch_k(ln_param_reduce_kernel, 4, 256, 0, s, (const float*)ts->ln_partial.as<float>(), grid, n.ga, n.gb);
+  {
+    ProfScope prof(e, s, PC_LAYERNORM, 0.0, 0.0);
+    launch_k(ln_param_reduce_kernel, 4, 256, 0, s, (const float*)ts->ln_partial.as<float>(), grid, n.ga, n.gb);
+  }
   CU_TRY(cudaGetLastError());
   return BOFI_OK;
 }
@@ -387,7 +429,7 @@ static int attn_bwd(bofi_engine* e, cudaStream_t s, const T* Q, int ldq, const T
   const float scale = 1.0f / sqrtf((float)kHeadDim);
   const size_t smem = attention_bwd_smem_bytes(Tk);
   dim3 grid(e->cfg.heads, n_kv_blocks);
-  e->launches++;
+  ProfScope prof(e, s, PC_ATTENTION, 10.0 * n_kv_blocks * qpk * Tq * Tk * kD, 0.0, n_kv_blocks, qpk * Tq, Tk);
 #define BOFI_ATTB(KPT_)                                                                                                             \
   do {                                                                                                                              \
     static size_t configured = 0;                                                                                                   \

@@ -298,24 +298,35 @@ __global__ void transpose_pad_kernel(const TIn* __restrict__ in, int ld_in, TOut
   }
 }
 
-// gb[c] (+)= sum_r dY[r, c]   -- bias gradients.  One CTA per 32 columns, 8 row lanes, fixed summation order.
+// Bias gradients gb[c] += sum_r dY[r, c] in two fixed-order stages:
+//   partial[chunk, c] = sum over the rows of the chunk (CTA = 32 columns x 8 row lanes), then a sum over chunks.
 template <typename T>
 __global__ void __launch_bounds__(256)
-colsum_kernel(const T* __restrict__ dY, int ld, int rows, int cols, float* __restrict__ out, float scale, int accumulate) {
+colsum_partial_kernel(const T* __restrict__ dY, int ld, int rows, int cols, float* __restrict__ partial) {
   pdl_enter();
   __shared__ float part[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x, ry = threadIdx.y;
+  const int per = (rows + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
   float acc = 0.f;
   if (c < cols)
-    for (int r = ry; r < rows; r += 8) acc += to_float<T>(dY[(size_t)r * ld + c]);
+    for (int r = r0 + ry; r < r1; r += 8) acc += to_float<T>(dY[(size_t)r * ld + c]);
   part[ry][threadIdx.x] = acc;
   __syncthreads();
   if (ry == 0 && c < cols) {
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x];
-    out[c] = (accumulate ? out[c] : 0.f) + t * scale;
+    partial[(size_t)blockIdx.y * cols + c] = t;
   }
+}
+__global__ void __launch_bounds__(256)
+colsum_reduce_kernel(const float* __restrict__ partial, int chunks, int cols, float* __restrict__ out) {
+  pdl_enter();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= cols) return;
+  float t = 0.f;
+  for (int i = 0; i < chunks; ++i) t += partial[(size_t)i * cols + c];
+  out[c] += t;
 }
 
 // ---------------------------------------------------------------------------------------------
