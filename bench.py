@@ -330,7 +330,7 @@ def main():
     def run_device(n):
         """n whole decodes, round robin over the in-flight slots; returns the tickets."""
         pipe.fork_from(main)
-        ts = [pipe.submit_device(att, att_len, a.mode, 1, 1, want_lp) for _ in range(n)]
+        ts = [pipe.submit_device(att, att_len, a.mode, 1, 1, want_lp, reuse_outputs=True) for _ in range(n)]
         pipe.join_into(main)
         return ts
 

@@ -23,6 +23,7 @@
 #include "kernels.cuh"
 #include "attention_mma.cuh"
 #include "train_kernels.cuh"
+#include "attention_bwd_mma.cuh"
 
 using namespace bofi;
 
@@ -124,6 +125,7 @@ struct bofi_engine {
   Layer lp0;                           // N_len == 0: cross attention only (length_attn + LengthPredictor.norm)
   Norm enc_norm, dec_norm, lp_norm;
   const float *w_len2 = nullptr, *b_len2 = nullptr, *w_syn2 = nullptr, *b_syn2 = nullptr;
+  const bf16* head1_w16 = nullptr;
   DevBuf bound_in, fill_in;            // (id, position) input tables
   DevBuf sa_mx, sa_lse;                // SAIC: per (row, slot) max / log-sum-exp of the step's logits
   DevBuf head1t;                       // [512][200] = [Length_classifier1 ; Syntactic_classifier1]^T
@@ -452,7 +454,8 @@ static int build_views(bofi_engine* e) {
   e->lp_norm = make_norm(e, lp + ".norm");
   RC_TRY(make_lin(e, {"model.generator.proj"}, c.tgt_vocab, c.d_model, &e->generator));
   RC_TRY(make_lin(e, {lp + ".Length_classifier1", lp + ".Syntactic_classifier1"}, 100, c.d_model, &e->head1));
-  e->head1.w16 = nullptr;          // the heads stay fp32 in both precisions
+  e->head1_w16 = e->head1.w16;     // bf16 copy: only the training backward uses it
+  e->head1.w16 = nullptr;          // the forward heads stay fp32 in both precisions
   e->w_len2 = W(e, lp + ".Length_classifier2.weight");
   e->b_len2 = W(e, lp + ".Length_classifier2.bias");
   e->w_syn2 = W(e, lp + ".Syntactic_classifier2.weight");

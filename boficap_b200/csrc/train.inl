@@ -430,6 +430,27 @@ static int attn_bwd(bofi_engine* e, cudaStream_t s, const T* Q, int ldq, const T
   const size_t smem = attention_bwd_smem_bytes(Tk);
   dim3 grid(e->cfg.heads, n_kv_blocks);
   ProfScope prof(e, s, PC_ATTENTION, 10.0 * n_kv_blocks * qpk * Tq * Tk * kD, 0.0, n_kv_blocks, qpk * Tq, Tk);
+  if constexpr (std::is_same<T, bf16>::value) {
+    if (!e->attn_simt_only) {
+      const int KT = (Tk + 15) / 16;
+      const size_t sm = attention_bwd_mma_smem_bytes(KT);
+      cudaError_t err = cudaErrorInvalidValue;
+#define BOFI_ATTBM(n)                                                                                                                  \
+  case n: {                                                                                                                            \
+    static bool configured = false;                                                                                                    \
+    if (!configured) {                                                                                                                 \
+      CU_TRY(cudaFuncSetAttribute(attention_bwd_mma_kernel<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));                 \
+      configured = true;                                                                                                               \
+    }                                                                                                                                  \
+    err = launch_k(attention_bwd_mma_kernel<n>, grid, 128, sm, s, Q, ldq, K, V, ldkv, dO, ldo, dQ, lddq, dK, dV, lddkv, Tq, Tk, qpk, vis, \
+                   vis_bs, vis_qs, vis_div, scale, accumulate_kv);                                                                     \
+  } break;
+      switch (KT) { BOFI_ATTBM(1) BOFI_ATTBM(2) BOFI_ATTBM(3) BOFI_ATTBM(4) BOFI_ATTBM(5) BOFI_ATTBM(6) BOFI_ATTBM(7) BOFI_ATTBM(8) }
+#undef BOFI_ATTBM
+      if (err != cudaSuccess) return fail(BOFI_ERR_CUDA, "attention_bwd_mma: %s", cudaGetErrorString(err));
+      return BOFI_OK;
+    }
+  }
 #define BOFI_ATTB(KPT_)                                                                                                             \
   do {                                                                                                                              \
     static size_t configured = 0;                                                                                                   \
@@ -544,9 +565,38 @@ static int t_bound_bwd(bofi_engine* e, cudaStream_t s, TrainState* ts, BoundTape
   launch_k(xe_head2_dgrad_kernel, ceil_div((size_t)Mb * 200, 256), 256, 0, s, (const float*)dzh, (const float*)bt.hid, e->w_len2, e->w_syn2, 100,
            20, 10, dhid, 256, Mb);
   CU_TRY(cudaGetLastError());
-  RC_TRY(lin_bwd<float>(e, s, ts, e->head1, bt.hn, kD, dhid, 256, Mb, dhn, kD));
   const LayerTape& tp = bt.lt;
-  RC_TRY((ln_bwd<float, T>(e, s, ts, e->lp_norm, tp.x_out, dhn, nullptr, dx, dxT, Mb)));
+  bool head_tc = false;
+  if constexpr (std::is_same<T, bf16>::value) {
+    if (e->use_tc && e->head1_w16) {
+      // classifier1 backward on the tensor cores: bf16 copies of d hid / hn (two small casts), fp32 accumulation into gW
+      head_tc = true;
+      bf16* dhid16 = g2;                               // [Mb, 256]
+      bf16* hn16 = g2 + (size_t)Mb * 256;              // [Mb, 512]
+      bf16* dhn16 = g1;                                // [Mb, 512]
+      e->launches += 2;
+      launch_k(cast_kernel<bf16>, 148 * 4, 256, 0, s, (const float*)dhid, dhid16, (size_t)Mb * 256 / 4);
+      CU_TRY(cudaGetLastError());
+      launch_k(cast_kernel<bf16>, 148 * 4, 256, 0, s, (const float*)bt.hn, hn16, (size_t)Mb * kD / 4);
+      CU_TRY(cudaGetLastError());
+      {
+        ProfScope prof(e, s, PC_GEMM_TC, 2.0 * Mb * 200 * kD, 0.0, 200, kD, Mb);
+        cudaError_t err = tc::gemm_tc_wgrad(s, dhid16, 256, hn16, kD, ts->zeros.as<float>(), e->head1.gw, kD, 200, kD, Mb);
+        if (err != cudaSuccess) return fail(BOFI_ERR_CUDA, "head wgrad: %s", cudaGetErrorString(err));
+      }
+      RC_TRY(colsum<float>(e, s, ts, dhid, 256, Mb, 200, e->head1.gb));
+      {
+        ProfScope prof(e, s, PC_GEMM_TC, 2.0 * Mb * 200 * kD, 0.0, Mb, kD, 200);
+        cudaError_t err = tc::gemm_tc_dgrad(s, dhid16, 256, e->head1_w16, kD, ts->zeros.as<float>(), dhn16, kD, Mb, kD, 200);
+        if (err != cudaSuccess) return fail(BOFI_ERR_CUDA, "head dgrad: %s", cudaGetErrorString(err));
+      }
+      RC_TRY((ln_bwd<bf16, T>(e, s, ts, e->lp_norm, tp.x_out, dhn16, nullptr, dx, dxT, Mb)));
+    }
+  }
+  if (!head_tc) {
+    RC_TRY(lin_bwd<float>(e, s, ts, e->head1, bt.hn, kD, dhid, 256, Mb, dhn, kD));
+    RC_TRY((ln_bwd<float, T>(e, s, ts, e->lp_norm, tp.x_out, dhn, nullptr, dx, dxT, Mb)));
+  }
   // FFN + cross-attention of the (n, p) rows; K/V block = image, spi*P single-query rows per block
   T* dkv = ts->dkv.as<T>();
   RC_TRY(t_layer_bwd<T>(e, s, ts, ly, tp, dx, dxT, g1, g2, Mb, 1, nullptr, 0, 0, (const T*)ts->kv[0], dkv, first_pass ? 0 : 1, ts->R, mem_len,

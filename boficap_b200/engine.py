@@ -73,15 +73,19 @@ class BofiEngine:
         self._batch = (B, R, att_feats, att_len)      # keep inputs alive until decode is enqueued
         return memory
 
-    def decode(self, mode="NAIC", sample_n=1, output_logsoftmax=1, want_logprobs=True):
+    def decode(self, mode="NAIC", sample_n=1, output_logsoftmax=1, want_logprobs=True, out=None):
+        """out: optional (seq, logp, pnum, plen, psyn) tensors of a previous call with the same shapes to write into."""
         B = self._batch[0]
         rows, L, V = B * sample_n, self.cfg.seq_length, self.cfg.tgt_vocab
         dev = self.device
-        seq = torch.empty(rows, L, dtype=torch.int64, device=dev)
-        logp = torch.empty(rows, L, V, dtype=torch.float32, device=dev) if want_logprobs else None
-        pnum = torch.empty(rows, dtype=torch.int32, device=dev)
-        plen = torch.empty(rows, L, dtype=torch.int32, device=dev)
-        psyn = torch.empty(rows, L, dtype=torch.int64, device=dev)
+        if out is not None and out[0].shape[0] == rows and (out[1] is not None) == bool(want_logprobs):
+            seq, logp, pnum, plen, psyn = out
+        else:
+            seq = torch.empty(rows, L, dtype=torch.int64, device=dev)
+            logp = torch.empty(rows, L, V, dtype=torch.float32, device=dev) if want_logprobs else None
+            pnum = torch.empty(rows, dtype=torch.int32, device=dev)
+            plen = torch.empty(rows, L, dtype=torch.int32, device=dev)
+            psyn = torch.empty(rows, L, dtype=torch.int64, device=dev)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.bofi_decode(self.handle, self._stream(), _lib.MODE[mode], sample_n, int(output_logsoftmax),
                                             _ptr(seq), _ptr(logp), _ptr(pnum), _ptr(plen), _ptr(psyn)))

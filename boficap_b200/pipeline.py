@@ -32,6 +32,7 @@ class BofiPipeline:
         self.engines = [BofiEngine(cfg, device, precision).load_state_dict(state_dict) for _ in range(depth)]
         self.streams = [torch.cuda.Stream(self.device) for _ in range(depth)]
         self.host_out = [None] * depth
+        self.dev_out = [None] * depth
         self.n = 0
 
     @property
@@ -61,13 +62,16 @@ class BofiPipeline:
             ev.record(st)
             stream.wait_event(ev)
 
-    def submit_device(self, att_feats, att_len=None, mode="NAIC", sample_n=1, output_logsoftmax=1, want_logprobs=True):
-        """Device-resident inputs: encode + decode enqueued on the next slot's stream."""
+    def submit_device(self, att_feats, att_len=None, mode="NAIC", sample_n=1, output_logsoftmax=1, want_logprobs=True, reuse_outputs=False):
+        """Device-resident inputs: encode + decode enqueued on the next slot's stream.  reuse_outputs: write into the
+        slot's output tensors of the previous round (valid until the slot is reused; no allocation per call)."""
         slot = self._next()
         eng, st = self.engines[slot], self.streams[slot]
         with torch.cuda.stream(st):
             eng.encode(att_feats, att_len)
-            out = eng.decode(mode, sample_n, output_logsoftmax, want_logprobs)
+            out = eng.decode(mode, sample_n, output_logsoftmax, want_logprobs, out=self.dev_out[slot] if reuse_outputs else None)
+            if reuse_outputs:
+                self.dev_out[slot] = out
             ev = torch.cuda.Event()
             ev.record(st)
         return Ticket(ev, out, slot)
