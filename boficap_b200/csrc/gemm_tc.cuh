@@ -129,6 +129,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, uint32_t s
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tmap, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(tmap), "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -146,11 +152,14 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // (2 x BN columns): the epilogue of tile i overlaps the main loop of tile i+1.
 // A_MN / B_MN: that operand is read from a [K, M] / [K, N] matrix (the contraction index is the ROW of the source):
 // weight gradients dW = dY^T . X (both MN-major) and input gradients dX = dY . W (B MN-major) need no transposed copies.
-template <int BN, int STAGES, typename TOut, bool RELU, bool RESID, bool A_MN = false, bool B_MN = false>
+// REDUCE (fp32 output only): the K range is cut into `k_splits` slices handled by different CTAs and every slice is
+// ADDED to C with a TMA reduce store (cp.reduce.async.bulk.tensor ... .add): weight gradients have few output tiles and
+// a very long contraction, and accumulate into the gradient buffer anyway.
+template <int BN, int STAGES, typename TOut, bool RELU, bool RESID, bool A_MN = false, bool B_MN = false, bool REDUCE = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, const float* residual, int ldr,
-               int M, int N, int K, int relu, const int* live_rows) {
+               int M, int N, int K, int relu, const int* live_rows, int k_splits) {
   pdl_launch();
   using L = SmemLayout<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
@@ -163,7 +172,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nk = (K + kBK - 1) / kBK;          // a K tail is zero-filled by TMA (out-of-bounds box elements)
+  const int nk_all = (K + kBK - 1) / kBK;      // a K tail is zero-filled by TMA (out-of-bounds box elements)
+  const int nk_per = REDUCE ? (nk_all + k_splits - 1) / k_splits : nk_all;
   const int tiles_n = (N + BN - 1) / BN;
 
   if (warp == 0 && lane == 0) {
@@ -195,14 +205,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // Everything above (barriers, TMEM, descriptor prefetch) overlaps the tail of the previous kernel; global
   // memory is only touched after the programmatic-dependency wait.  A dead bounding step walks zero tiles.
   pdl_wait();
-  const int ntiles = step_is_dead(live_rows) ? 0 : ((M + kBM - 1) / kBM) * tiles_n;
+  const int ntiles_mn = ((M + kBM - 1) / kBM) * tiles_n;
+  const int ntiles = step_is_dead(live_rows) ? 0 : ntiles_mn * (REDUCE ? k_splits : 1);   // work items: (tile, K slice)
 
   if (warp == 0) {
     if (lane == 0) {
       int it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < ntiles; item += gridDim.x) {
+        const int tile = item % ntiles_mn, kb0 = (item / ntiles_mn) * nk_per, kb1 = min(nk_all, kb0 + nk_per);
         const int m0 = (tile / tiles_n) * kBM, n0 = (tile % tiles_n) * BN;
-        for (int kb = 0; kb < nk; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
@@ -228,13 +240,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, A_MN, B_MN);
       int it = 0, t = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
+      for (int item = blockIdx.x; item < ntiles; item += gridDim.x, ++t) {
+        const int kb0 = (item / ntiles_mn) * nk_per, kb1 = min(nk_all, kb0 + nk_per);
         const int as = t & 1;
         const uint32_t aph = (t >> 1) & 1;
         mbar_wait(smem_u32(&tmem_empty_bar[as]), aph ^ 1);     // epilogue drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-        for (int kb = 0; kb < nk; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(smem_u32(&full_bar[s]), ph);
@@ -246,7 +259,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           constexpr uint64_t a_step = A_MN ? 128 : 2, b_step = B_MN ? 128 : 2;
 #pragma unroll
           for (int k = 0; k < kBK / kUK; ++k) {
-            umma_bf16(tmem_d, adesc + a_step * k, bdesc + b_step * k, idesc, (kb | k) != 0);
+            umma_bf16(tmem_d, adesc + a_step * k, bdesc + b_step * k, idesc, ((kb - kb0) | k) != 0);
           }
           umma_commit(smem_u32(&empty_bar[s]));      // frees the smem stage when these MMAs retire
         }
@@ -261,7 +274,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int quad = warp & 3;                       // TMEM lanes [32*quad, 32*quad+32)
     const uint32_t stage0 = smem_u32(smem + L::kOutOffset + quad * 8192);
     int t = 0, nstore = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
+    for (int item = blockIdx.x; item < ntiles; item += gridDim.x, ++t) {
+      const int tile = item % ntiles_mn;
       const int m0 = (tile / tiles_n) * kBM, n0 = (tile % tiles_n) * BN;
       const int as = t & 1;
       const uint32_t aph = (t >> 1) & 1;
@@ -353,7 +367,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        if (lane == 0) tma_store_2d(&tmC, sbuf, n, m0 + quad * 32);
+        if (lane == 0) {
+          if constexpr (REDUCE) tma_reduce_add_2d(&tmC, sbuf, n, m0 + quad * 32);
+          else tma_store_2d(&tmC, sbuf, n, m0 + quad * 32);
+        }
         ++nstore;
       }
       tcgen05_fence_before();
@@ -414,20 +431,20 @@ inline int num_sms() {
   return n;
 }
 
-template <int BN, int STAGES, typename TOut, bool RELU, bool RESID, bool A_MN = false, bool B_MN = false>
+template <int BN, int STAGES, typename TOut, bool RELU, bool RESID, bool A_MN = false, bool B_MN = false, bool REDUCE = false>
 inline cudaError_t launch(cudaStream_t s, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                           const float* bias, const float* residual, int ldr, int M, int N, int K, int relu,
-                          const int* live_rows) {
+                          const int* live_rows, int k_splits = 1) {
   using L = SmemLayout<BN, STAGES>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, TOut, RELU, RESID, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, TOut, RELU, RESID, A_MN, B_MN, REDUCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const int ntiles = ((M + kBM - 1) / kBM) * ((N + BN - 1) / BN);
+  const int ntiles = ((M + kBM - 1) / kBM) * ((N + BN - 1) / BN) * k_splits;
   const int grid = ntiles < num_sms() ? ntiles : num_sms();
-  launch_k(gemm_tc_kernel<BN, STAGES, TOut, RELU, RESID, A_MN, B_MN>, grid, kThreads, L::kTotal, s, tmA, tmB, tmC, bias, residual, ldr, M, N, K, relu, live_rows);
+  launch_k(gemm_tc_kernel<BN, STAGES, TOut, RELU, RESID, A_MN, B_MN, REDUCE>, grid, kThreads, L::kTotal, s, tmA, tmB, tmC, bias, residual, ldr, M, N, K, relu, live_rows, k_splits);
   return cudaGetLastError();
 }
 
@@ -510,14 +527,19 @@ inline cudaError_t gemm_tc_wgrad(cudaStream_t s, const bf16* At, int lda, const 
                                  int M, int N, int K) {
   if (M <= 0 || N <= 0) return cudaSuccess;
   if (lda % 8 != 0 || ldb % 8 != 0 || ldc % 4 != 0) return cudaErrorInvalidValue;
+  // few output tiles, long contraction: 256-wide tiles and enough K slices to give every SM about two work items
   const int tiles256 = ((M + kBM - 1) / kBM) * ((N + 255) / 256);
-  const bool wide = tiles256 >= num_sms() / 2;
+  const int nk = (K + kBK - 1) / kBK;
+  int splits = (2 * num_sms()) / tiles256;
+  splits = splits < 1 ? 1 : splits;
+  if (splits > nk / 4) splits = nk / 4 < 1 ? 1 : nk / 4;
+  const int per = (nk + splits - 1) / splits;
+  splits = (nk + per - 1) / per;                      // no empty slice
   const CUtensorMap* tmA = cached_tmap(At, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64);
   const CUtensorMap* tmB = cached_tmap(Bt, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64);
   const CUtensorMap* tmC = cached_tmap(C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, 4);
   if (!tmA || !tmB || !tmC) return cudaErrorInvalidValue;
-  return wide ? launch<256, 4, float, false, true, true, true>(s, *tmA, *tmB, *tmC, zero_bias, C, ldc, M, N, K, 0, nullptr)
-              : launch<64, 6, float, false, true, true, true>(s, *tmA, *tmB, *tmC, zero_bias, C, ldc, M, N, K, 0, nullptr);
+  return launch<256, 4, float, false, false, true, true, true>(s, *tmA, *tmB, *tmC, zero_bias, nullptr, 0, M, N, K, 0, nullptr, splits);
 }
 
 }  // namespace tc
