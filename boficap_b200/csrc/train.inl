@@ -337,16 +337,39 @@ static int transpose_pad(bofi_engine* e, cudaStream_t s, const TIn* in, int ld_i
 // gb[c] += sum_r dY[r, c] in two fixed-order stages (row chunks, then the chunk partials).
 template <typename T>
 static int colsum(bofi_engine* e, cudaStream_t s, TrainState* ts, const T* dY, int ldy, int M, int N, float* gb) {
-  const int chunks = std::max(1, std::min(64, M / 256));
-  RC_TRY(ts->cs_partial.reserve((size_t)chunks * N * 4));
+  const int cols4 = round_up(N, 4);
+  if (cols4 > ldy) return fail(BOFI_ERR_INVALID, "colsum: pitch %d < %d", ldy, cols4);
+  const int col_blocks = ceil_div(cols4, 256);
+  const int chunks = std::max(1, std::min(std::min(64, M / 64), (4 * 148) / col_blocks));
+  RC_TRY(ts->cs_partial.reserve((size_t)chunks * cols4 * 4));
   {
     ProfScope prof(e, s, PC_OTHER, 0.0, (double)M * N * sizeof(T));
-    launch_k(colsum_partial_kernel<T>, dim3(ceil_div(N, 32), chunks), dim3(32, 8), 0, s, dY, ldy, M, N, ts->cs_partial.as<float>());
+    launch_k(colsum_partial_kernel<T>, dim3(col_blocks, chunks), 512, 0, s, dY, ldy, M, cols4, ts->cs_partial.as<float>());
   }
   CU_TRY(cudaGetLastError());
   {
     ProfScope prof(e, s, PC_OTHER, 0.0, 0.0);
-    launch_k(colsum_reduce_kernel, ceil_div(N, 256), 256, 0, s, (const float*)ts->cs_partial.as<float>(), chunks, N, gb);
+    launch_k(colsum_reduce_kernel, ceil_div(N, 256), 256, 0, s, (const float*)ts->cs_partial.as<float>(), chunks, N, cols4, gb);
+  }
+  CU_TRY(cudaGetLastError());
+  return BOFI_OK;
+}
+
+// g_lut[id] += sqrt(d) * sum of the dx rows with that id (tiny id space), two fixed-order stages.
+static int embed_small_bwd(bofi_engine* e, cudaStream_t s, TrainState* ts, const float* dx, const int* ids, int ids_stride, int ids_off,
+                           int const_id, int T_, int rows, float* g_lut) {
+  const int chunks = std::max(1, std::min(64, rows / 128));
+  RC_TRY(ts->cs_partial.reserve((size_t)chunks * kSmallIds * kD * 4));
+  {
+    ProfScope prof(e, s, PC_OTHER, 0.0, (double)rows * kD * 4);
+    launch_k(embed_small_partial_kernel, dim3(kD / 64, chunks), 256, 0, s, dx, ids, ids_stride, ids_off, T_, rows, ts->cs_partial.as<float>());
+  }
+  CU_TRY(cudaGetLastError());
+  {
+    ProfScope prof(e, s, PC_OTHER, 0.0, 0.0);
+    const int n_ids = ids ? kSmallIds : 1;
+    launch_k(embed_small_reduce_kernel, ceil_div(n_ids * kD, 256), 256, 0, s, (const float*)ts->cs_partial.as<float>(), chunks, n_ids,
+             ids ? -1 : const_id, sqrtf((float)kD), g_lut);
   }
   CU_TRY(cudaGetLastError());
   return BOFI_OK;
@@ -405,7 +428,7 @@ static int lin_bwd(bofi_engine* e, cudaStream_t s, TrainState* ts, const Lin& li
 template <typename TG, typename T>
 static int ln_bwd(bofi_engine* e, cudaStream_t s, TrainState* ts, const Norm& n, const float* x, const TG* dy, const float* dres,
                   float* dx_out, T* dx_out_t, int rows) {
-  const int grid = std::min(ceil_div(rows, 8), 148 * 4);
+  const int grid = std::min(ceil_div(rows, 8), 148 * 2);
   RC_TRY(ts->ln_partial.reserve((size_t)grid * 2 * kD * 4));
   {
     ProfScope prof(e, s, PC_LAYERNORM, 0.0, (double)rows * kD * (4 + sizeof(TG) + 4 + 4 + sizeof(T)));
@@ -414,7 +437,7 @@ static int ln_bwd(bofi_engine* e, cudaStream_t s, TrainState* ts, const Norm& n,
   CU_TRY(cudaGetLastError());
   {
     ProfScope prof(e, s, PC_LAYERNORM, 0.0, 0.0);
-    launch_k(ln_param_reduce_kernel, 4, 256, 0, s, (const float*)ts->ln_partial.as<float>(), grid, n.ga, n.gb);
+    launch_k(ln_param_reduce_kernel, 2 * kD / 32, dim3(32, 8), 0, s, (const float*)ts->ln_partial.as<float>(), grid, n.ga, n.gb);
   }
   CU_TRY(cudaGetLastError());
   return BOFI_OK;
@@ -526,17 +549,14 @@ static int t_dec_bwd(bofi_engine* e, cudaStream_t s, TrainState* ts, DecTape& dt
   }
   // input embeddings: x = tgt_embed(word)*sqrt(d) + syn_embed(syn)*sqrt(d) + pe
   const float sq = sqrtf((float)kD);
-  e->launches += 2;
   if (const_word) {
-    launch_k(embed_small_bwd_kernel, kD / 64, 256, 0, s, (const float*)dx, (const int*)nullptr, 0, 0, c.bos_idx, T_, rows, sq,
-             G(e, "model.tgt_embed.lut.weight"));
+    RC_TRY(embed_small_bwd(e, s, ts, dx, nullptr, 0, 0, c.bos_idx, T_, rows, G(e, "model.tgt_embed.lut.weight")));
   } else {
+    ProfScope prof(e, s, PC_OTHER, 0.0, (double)rows * kD * 8);
     launch_k(embed_bwd_kernel, ceil_div(rows, 8), 256, 0, s, (const float*)dx, word_ids, T_, 0, T_, rows, sq, G(e, "model.tgt_embed.lut.weight"));
   }
   CU_TRY(cudaGetLastError());
-  launch_k(embed_small_bwd_kernel, kD / 64, 256, 0, s, (const float*)dx, (const int*)ts->ext_syn, Tb, 1, 0, T_, rows, sq,
-           G(e, "model.syn_embed.lut.weight"));
-  CU_TRY(cudaGetLastError());
+  RC_TRY(embed_small_bwd(e, s, ts, dx, ts->ext_syn, Tb, 1, 0, T_, rows, G(e, "model.syn_embed.lut.weight")));
   return BOFI_OK;
 }
 
@@ -558,9 +578,17 @@ static int t_bound_bwd(bofi_engine* e, cudaStream_t s, TrainState* ts, BoundTape
   e->launches += 3;
   launch_k(xe_head_dz_kernel, ceil_div(Mb, 4), 128, 0, s, g_len, g_syn, len_logp, syn_logp, 20, 10, dzh, Mb, P, Tb - 1);
   CU_TRY(cudaGetLastError());
-  launch_k(xe_head2_wgrad_kernel, 30, 128, 0, s, (const float*)dzh, (const float*)bt.hid, 100, 20, Mb, G(e, lp + ".Length_classifier2.weight"),
-           G(e, lp + ".Length_classifier2.bias"), G(e, lp + ".Syntactic_classifier2.weight"), G(e, lp + ".Syntactic_classifier2.bias"));
-  CU_TRY(cudaGetLastError());
+  {
+    const int chunks = std::max(1, std::min(64, Mb / 128));
+    RC_TRY(ts->cs_partial.reserve((size_t)chunks * 30 * 128 * 4));
+    launch_k(xe_head2_wgrad_partial_kernel, dim3(30, chunks), 128, 0, s, (const float*)dzh, (const float*)bt.hid, 100, 20, Mb,
+             ts->cs_partial.as<float>());
+    CU_TRY(cudaGetLastError());
+    launch_k(xe_head2_wgrad_reduce_kernel, 30, 128, 0, s, (const float*)ts->cs_partial.as<float>(), chunks, 100, 20,
+             G(e, lp + ".Length_classifier2.weight"), G(e, lp + ".Length_classifier2.bias"), G(e, lp + ".Syntactic_classifier2.weight"),
+             G(e, lp + ".Syntactic_classifier2.bias"));
+    CU_TRY(cudaGetLastError());
+  }
   CU_TRY(cudaMemsetAsync(dhid, 0, (size_t)Mb * 256 * 4, s));
   launch_k(xe_head2_dgrad_kernel, ceil_div((size_t)Mb * 200, 256), 256, 0, s, (const float*)dzh, (const float*)bt.hid, e->w_len2, e->w_syn2, 100,
            20, 10, dhid, 256, Mb);
@@ -621,14 +649,15 @@ static int t_bound_bwd(bofi_engine* e, cudaStream_t s, TrainState* ts, BoundTape
   RC_TRY(ts->dmem.reserve((size_t)std::max(N * Tb, ts->B * ts->R) * kD * 4));
   float* dxin = ts->dmem.as<float>();
   RC_TRY((ln_bwd<T, T>(e, s, ts, ly.ln[0], bt.x_in, g1, nullptr, dxin, (T*)nullptr, N * Tb)));
-  e->launches += 3;
+  e->launches += 1;
   launch_k(sum_over_passes_kernel<float, float>, ceil_div(N, 8), 256, 0, s, (const float*)dx, P, dxin, (size_t)Tb * kD, N, 1);
   CU_TRY(cudaGetLastError());
   const float sq = sqrtf((float)kD);
   if (word_ids) {
+    ProfScope prof(e, s, PC_OTHER, 0.0, (double)N * Tb * kD * 8);
     launch_k(embed_bwd_kernel, ceil_div(N * Tb, 8), 256, 0, s, (const float*)dxin, word_ids, Tb, 0, Tb, N * Tb, sq, G(e, "model.tgt_embed.lut.weight"));
   } else {
-    launch_k(embed_small_bwd_kernel, kD / 64, 256, 0, s, (const float*)dxin, syn_ids, Tb, 0, 0, Tb, N * Tb, sq, G(e, "model.syn_embed.lut.weight"));
+    RC_TRY(embed_small_bwd(e, s, ts, dxin, syn_ids, Tb, 0, 0, Tb, N * Tb, G(e, "model.syn_embed.lut.weight")));
   }
   CU_TRY(cudaGetLastError());
   return BOFI_OK;

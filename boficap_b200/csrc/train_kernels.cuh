@@ -174,24 +174,39 @@ xe_head_dz_kernel(const float* __restrict__ g_len, const float* __restrict__ g_s
   dz[(size_t)row * 32 + lane] = out;
 }
 
-// classifier2 backward.  One CTA per output unit o (n_len + n_syn of them):
-//   gW2[o, c] += sum_rows dz[row, o] * hid[row, c (+Hh)],   gb2[o] += sum_rows dz[row, o]          (deterministic)
+// classifier2 backward, two fixed-order stages.  Stage 1: one CTA per (output unit o, row chunk):
+//   partial[chunk][o][c] = sum_{rows of chunk} dz[row, o] * hid[row, c (+Hh)]   (c == Hh holds the bias term sum dz[row, o])
+// Stage 2: gW2[o, c] += sum over chunks, gb2[o] likewise.
 __global__ void __launch_bounds__(128)
-xe_head2_wgrad_kernel(const float* __restrict__ dz, const float* __restrict__ hid, int Hh, int n_len, int Mb,
-                      float* __restrict__ gw_len, float* __restrict__ gb_len, float* __restrict__ gw_syn, float* __restrict__ gb_syn) {
+xe_head2_wgrad_partial_kernel(const float* __restrict__ dz, const float* __restrict__ hid, int Hh, int n_len, int Mb,
+                              float* __restrict__ partial) {
   pdl_enter();
-  const int o = blockIdx.x, c = threadIdx.x;
+  const int o = blockIdx.x, c = threadIdx.x, n_out = gridDim.x;
   const bool is_len = o < n_len;
   const float* h = hid + (is_len ? 0 : Hh);
-  float acc = 0.f, accb = 0.f;
-  for (int row = 0; row < Mb; ++row) {
+  const int per = (Mb + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * per, r1 = min(Mb, r0 + per);
+  float acc = 0.f;
+  for (int row = r0; row < r1; ++row) {
     const float d = dz[(size_t)row * 32 + o];
-    if (c < Hh) acc = fmaf(d, h[(size_t)row * 2 * Hh + c], acc);
-    accb += d;
+    acc = fmaf(d, c < Hh ? h[(size_t)row * 2 * Hh + c] : 1.0f, acc);
   }
-  float* gw = is_len ? gw_len + (size_t)o * Hh : gw_syn + (size_t)(o - n_len) * Hh;
-  if (c < Hh) gw[c] += acc;
-  if (c == 0) { if (is_len) gb_len[o] += accb; else gb_syn[o - n_len] += accb; }
+  if (c <= Hh) partial[((size_t)blockIdx.y * n_out + o) * 128 + c] = acc;
+}
+__global__ void __launch_bounds__(128)
+xe_head2_wgrad_reduce_kernel(const float* __restrict__ partial, int chunks, int Hh, int n_len, float* __restrict__ gw_len,
+                             float* __restrict__ gb_len, float* __restrict__ gw_syn, float* __restrict__ gb_syn) {
+  pdl_enter();
+  const int o = blockIdx.x, c = threadIdx.x, n_out = gridDim.x;
+  if (c > Hh) return;
+  float t = 0.f;
+  for (int ch = 0; ch < chunks; ++ch) t += partial[((size_t)ch * n_out + o) * 128 + c];
+  const bool is_len = o < n_len;
+  if (c < Hh) {
+    float* gw = is_len ? gw_len + (size_t)o * Hh : gw_syn + (size_t)(o - n_len) * Hh;
+    gw[c] += t;
+  } else {
+    if (is_len) gb_len[o] += t; else gb_syn[o - n_len] += t;
+  }
 }
 
 // dhid[row, c] = (sum_o dz[row, o] * W2[o, c]) * (hid[row, c] > 0)      (classifier2 dgrad + ReLU backward)
@@ -299,33 +314,47 @@ __global__ void transpose_pad_kernel(const TIn* __restrict__ in, int ld_in, TOut
 }
 
 // Bias gradients gb[c] += sum_r dY[r, c] in two fixed-order stages:
-//   partial[chunk, c] = sum over the rows of the chunk (CTA = 32 columns x 8 row lanes), then a sum over chunks.
+//   partial[chunk, c] = sum over the rows of the chunk (CTA = 256 columns x 8 row lanes, 8-byte / 16-byte loads of 4
+//   columns per thread), then a sum over chunks.  `cols4` = columns rounded up to 4 (pad columns of dY are zero).
 template <typename T>
-__global__ void __launch_bounds__(256)
-colsum_partial_kernel(const T* __restrict__ dY, int ld, int rows, int cols, float* __restrict__ partial) {
+__global__ void __launch_bounds__(512)
+colsum_partial_kernel(const T* __restrict__ dY, int ld, int rows, int cols4, float* __restrict__ partial) {
   pdl_enter();
-  __shared__ float part[8][33];
-  const int c = blockIdx.x * 32 + threadIdx.x, ry = threadIdx.y;
+  __shared__ float4 part[8][64];
+  const int cg = threadIdx.x & 63, ry = threadIdx.x >> 6;
+  const int c = (blockIdx.x * 64 + cg) * 4;
   const int per = (rows + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
-  float acc = 0.f;
-  if (c < cols)
-    for (int r = r0 + ry; r < r1; r += 8) acc += to_float<T>(dY[(size_t)r * ld + c]);
-  part[ry][threadIdx.x] = acc;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < cols4) {
+    int r = r0 + ry;
+    for (; r + 24 < r1; r += 32) {                     // four independent loads in flight
+      const float4 v0 = load4(dY + (size_t)r * ld + c), v1 = load4(dY + (size_t)(r + 8) * ld + c);
+      const float4 v2 = load4(dY + (size_t)(r + 16) * ld + c), v3 = load4(dY + (size_t)(r + 24) * ld + c);
+      acc.x += (v0.x + v1.x) + (v2.x + v3.x); acc.y += (v0.y + v1.y) + (v2.y + v3.y);
+      acc.z += (v0.z + v1.z) + (v2.z + v3.z); acc.w += (v0.w + v1.w) + (v2.w + v3.w);
+    }
+    for (; r < r1; r += 8) {
+      const float4 v = load4(dY + (size_t)r * ld + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  part[ry][cg] = acc;
   __syncthreads();
-  if (ry == 0 && c < cols) {
-    float t = 0.f;
+  if (ry == 0 && c < cols4) {
+    float4 t = part[0][cg];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x];
-    partial[(size_t)blockIdx.y * cols + c] = t;
+    for (int i = 1; i < 8; ++i) { t.x += part[i][cg].x; t.y += part[i][cg].y; t.z += part[i][cg].z; t.w += part[i][cg].w; }
+    store4(partial + (size_t)blockIdx.y * cols4 + c, t);
   }
 }
 __global__ void __launch_bounds__(256)
-colsum_reduce_kernel(const float* __restrict__ partial, int chunks, int cols, float* __restrict__ out) {
+colsum_reduce_kernel(const float* __restrict__ partial, int chunks, int cols, int cols4, float* __restrict__ out) {
   pdl_enter();
   const int c = blockIdx.x * 256 + threadIdx.x;
   if (c >= cols) return;
   float t = 0.f;
-  for (int i = 0; i < chunks; ++i) t += partial[(size_t)i * cols + c];
+#pragma unroll 8
+  for (int i = 0; i < chunks; ++i) t += partial[(size_t)i * cols4 + c];
   out[c] += t;
 }
 
@@ -413,11 +442,19 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ a2, 
 __global__ void __launch_bounds__(256)
 ln_param_reduce_kernel(const float* __restrict__ partial, int nparts, float* __restrict__ ga, float* __restrict__ gb) {
   pdl_enter();
-  const int c = blockIdx.x * 256 + threadIdx.x;       // 0 .. 2*kD-1
-  if (c >= 2 * kD) return;
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x, py = threadIdx.y;       // c in [0, 2*kD)
   float t = 0.f;
-  for (int p = 0; p < nparts; ++p) t += partial[(size_t)p * 2 * kD + c];
-  if (c < kD) ga[c] += t; else gb[c - kD] += t;
+#pragma unroll 4
+  for (int p = py; p < nparts; p += 8) t += partial[(size_t)p * 2 * kD + c];
+  red[py][threadIdx.x] = t;
+  __syncthreads();
+  if (py == 0) {
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v += red[i][threadIdx.x];
+    if (c < kD) ga[c] += v; else gb[c - kD] += v;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -646,34 +683,44 @@ embed_bwd_kernel(const float* __restrict__ dx, const int* __restrict__ ids, int 
   }
 }
 
-// Embedding backward for a tiny id space (syn_embed: 10 ids; constant word: 1 id): deterministic.
-// One CTA per 64 columns; 4 row lanes accumulate per-id sums in shared memory, then a fixed-order combine.
-//   ids == nullptr: every row has id `const_id`.
+// Embedding backward for a tiny id space (syn_embed: 10 ids; constant word: 1 id): deterministic, two stages.
+//   stage 1: CTA = 64 columns x one row chunk, 4 row lanes accumulate per-id sums in shared memory
+//            -> partial[chunk][id][512]
+//   stage 2: g_lut[id, c] += sqrt(d) * sum over chunks.      ids == nullptr: every row has id `const_id` (slot 0).
 constexpr int kSmallIds = 10;
 __global__ void __launch_bounds__(256)
-embed_small_bwd_kernel(const float* __restrict__ dx, const int* __restrict__ ids, int ids_stride, int ids_off, int const_id, int T, int rows,
-                       float sqrt_d, float* __restrict__ g_lut) {
+embed_small_partial_kernel(const float* __restrict__ dx, const int* __restrict__ ids, int ids_stride, int ids_off, int T, int rows,
+                           float* __restrict__ partial) {
   pdl_enter();
   __shared__ float acc[4][kSmallIds][64];
   const int c = threadIdx.x & 63, rl = threadIdx.x >> 6, col = blockIdx.x * 64 + c;
   for (int i = 0; i < kSmallIds; ++i) acc[rl][i][c] = 0.f;
-  for (int row = rl; row < rows; row += 4) {
-    int id = const_id;
+  const int per = (rows + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
+  for (int row = r0 + rl; row < r1; row += 4) {
+    int slot = 0;
     if (ids) {
       const int b = row / T, r = row - b * T;
-      id = ids[(size_t)b * ids_stride + ids_off + r];
+      slot = ids[(size_t)b * ids_stride + ids_off + r];
     }
-    const int slot = ids ? id : 0;
     if (slot >= 0 && slot < kSmallIds) acc[rl][slot][c] += dx[(size_t)row * kD + col];
   }
   __syncthreads();
   if (rl == 0) {
-    for (int i = 0; i < kSmallIds; ++i) {
-      const float t = ((acc[0][i][c] + acc[1][i][c]) + acc[2][i][c]) + acc[3][i][c];
-      const int id = ids ? i : const_id;
-      if (ids || i == 0) g_lut[(size_t)id * kD + col] += t * sqrt_d;
-    }
+    for (int i = 0; i < kSmallIds; ++i)
+      partial[((size_t)blockIdx.y * kSmallIds + i) * kD + col] = ((acc[0][i][c] + acc[1][i][c]) + acc[2][i][c]) + acc[3][i][c];
   }
+}
+__global__ void __launch_bounds__(256)
+embed_small_reduce_kernel(const float* __restrict__ partial, int chunks, int n_ids, int const_id, float sqrt_d, float* __restrict__ g_lut) {
+  pdl_enter();
+  const int i = blockIdx.x * 256 + threadIdx.x;                        // (id slot, column)
+  if (i >= n_ids * kD) return;
+  const int slot = i / kD, col = i - slot * kD;
+  float t = 0.f;
+#pragma unroll 4
+  for (int ch = 0; ch < chunks; ++ch) t += partial[((size_t)ch * kSmallIds + slot) * kD + col];
+  const int id = const_id >= 0 ? const_id : slot;
+  g_lut[(size_t)id * kD + col] += t * sqrt_d;
 }
 
 // Criterion for the bounding heads fused with its gradient (losses.py:340-349): for row (n, p), p < phrase_num[n]:
