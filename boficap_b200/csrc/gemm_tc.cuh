@@ -8,8 +8,9 @@
 //     ReLU, residual add and the fp32 / bf16 down-conversion, stage 32 x 128-byte sub-tiles in swizzled
 //     shared memory and write them with TMA stores (cp.async.bulk.tensor, M / N tails clipped in hardware).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (TMEM lane quadrant = warp % 4).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..9 = epilogue (TMEM lane quadrant = warp % 4; the two warps of a quadrant take alternate column chunks,
+// which halves the serial TMEM-load -> math -> staging -> TMA-store chain per tile).
 // Pipelines: full[s]/empty[s] mbarriers between TMA and MMA, one tmem_full mbarrier MMA -> epilogue.
 // Persistent CTAs (one per SM) with a double-buffered TMEM accumulator: the epilogue of one tile overlaps
 // the main loop of the next.
@@ -24,7 +25,7 @@ namespace tc {
 constexpr int kBM = 128;   // UMMA M (TMEM lanes)
 constexpr int kBK = 64;    // 64 bf16 = one 128-byte swizzle row
 constexpr int kUK = 16;    // UMMA K for 16-bit inputs
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -117,8 +118,8 @@ struct SmemLayout {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kOutOffset = STAGES * kStageBytes;          // epilogue staging: 4 warps x 2 x 4 KB
-  static constexpr int kOutBytes = 4 * 2 * 4096;
+  static constexpr int kOutOffset = STAGES * kStageBytes;          // epilogue staging: 8 warps x 4 KB
+  static constexpr int kOutBytes = 8 * 4096;
   static constexpr int kBarOffset = kOutOffset + kOutBytes;
   static constexpr int kTotal = kBarOffset + 256 + 1024;   // barriers + alignment slack
 };
@@ -137,6 +138,11 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tmap, uint3
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
 }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -189,7 +195,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(smem_u32(&tmem_full_bar[a]), 1);
-        mbar_init(smem_u32(&tmem_empty_bar[a]), 4);   // one arrival per epilogue warp
+        mbar_init(smem_u32(&tmem_empty_bar[a]), 8);   // one arrival per epilogue warp
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -269,11 +275,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // Epilogue: TMEM -> registers (one accumulator row per thread) -> bias / ReLU / residual -> swizzled smem
     // staging tile (32 rows x 128 B) -> TMA store.  Full-line coalesced writes, M / N tails clipped by the
-    // tensor map; two staging tiles per warp so the store of chunk i overlaps the math of chunk i+1.
+    // tensor map.  Eight warps: warp `quad + 4*half + 2` owns TMEM lanes [32*quad, +32) and the column chunks
+    // c = half, half + 2, ...
     constexpr int CC = 128 / (int)sizeof(TOut);      // output columns per 128-byte staging row
     const int quad = warp & 3;                       // TMEM lanes [32*quad, 32*quad+32)
-    const uint32_t stage0 = smem_u32(smem + L::kOutOffset + quad * 8192);
-    int t = 0, nstore = 0;
+    const int half = (warp - 2) >> 2;
+    const uint32_t sbuf = smem_u32(smem + L::kOutOffset + (warp - 2) * 4096);
+    const uint32_t srow = sbuf + (uint32_t)lane * 128u;
+    int t = 0;
     for (int item = blockIdx.x; item < ntiles; item += gridDim.x, ++t) {
       const int tile = item % ntiles_mn;
       const int m0 = (tile / tiles_n) * kBM, n0 = (tile % tiles_n) * BN;
@@ -282,28 +291,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int row = m0 + quad * 32 + lane;
       const bool row_ok = row < M;
       constexpr int NC = BN / CC;
-      // The residual does not depend on the accumulator: fetch the first two chunks of this thread's row
-      // before waiting for the MMAs, and keep two chunks in flight while the tile drains.
+      constexpr int NI = (NC + 1) / 2;                          // chunks per warp
+      // The residual does not depend on the accumulator: fetch this warp's first chunk before waiting for the MMAs and
+      // keep the next one in flight while a chunk drains.  Loads are COALESCED (lane l reads 16 bytes of row
+      // j*4 + l/8 at column chunk l%8: every warp instruction covers four whole 128-byte lines) and are transposed to
+      // the row-per-thread layout through the warp's swizzled staging tile.
       constexpr int RV = RESID ? 8 : 1;                         // residual only exists on the fp32-output path
-      float4 res[3][RV];
+      float4 res[2][RV];
       auto fetch_res = [&](float4 (&dst)[RV], int c) {
         if constexpr (RESID) {
           const int n = n0 + c * CC;
-          if (row_ok && c < NC && n + CC <= N) {
+          if (c < NC && n + CC <= N) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = *reinterpret_cast<const float4*>(residual + (size_t)row * ldr + n + 4 * j);
+            for (int j = 0; j < 8; ++j) {
+              const int rr = m0 + quad * 32 + j * 4 + (lane >> 3);
+              dst[j] = (rr < M) ? *reinterpret_cast<const float4*>(residual + (size_t)rr * ldr + n + 4 * (lane & 7))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
           }
         }
       };
-      fetch_res(res[0], 0);
-      fetch_res(res[1], 1);
+      fetch_res(res[0], half);
       mbar_wait(smem_u32(&tmem_full_bar[as]), aph);
       tcgen05_fence_after();
 #pragma unroll
-      for (int c = 0; c < NC; ++c) {
+      for (int i = 0; i < NI; ++i) {
+        const int c = half + 2 * i;
         const int n = n0 + c * CC;
-        if (n >= N) break;                            // warp-uniform
-        fetch_res(res[(c + 2) % 3], c + 2);
+        if (c >= NC || n >= N) break;                 // warp-uniform
+        fetch_res(res[(i + 1) & 1], c + 2);
         const bool full = (n + CC <= N);              // warp-uniform
         float4 bb[CC / 4];
         if (full) {
@@ -319,6 +335,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + c * CC + 32), r1);
           }
         }
+        if constexpr (RESID) {
+          if (full) {
+            // transpose the coalesced residual registers into this thread's row through the staging tile
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int rl = j * 4 + (lane >> 3);
+              const float4 v = res[i & 1][j];
+              st_shared_v4(sbuf + (uint32_t)rl * 128u + (uint32_t)(((lane & 7) ^ (rl & 7)) * 16), __float_as_uint(v.x), __float_as_uint(v.y),
+                           __float_as_uint(v.z), __float_as_uint(v.w));
+            }
+            __syncwarp();
+          }
+        }
         if (full) {
 #pragma unroll
           for (int j = 0; j < CC; j += 4) {
@@ -326,10 +357,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                    __uint_as_float(r[j + 2]) + bb[j / 4].z, __uint_as_float(r[j + 3]) + bb[j / 4].w);
             if constexpr (RELU) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
             if constexpr (RESID) {
-              if (row_ok) {
-                const float4 rr = res[c % 3][j / 4];
-                x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
-              }
+              const float4 rr = ld_shared_v4(srow + (uint32_t)(((j / 4) ^ (lane & 7)) * 16));
+              x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
             }
             r[j] = __float_as_uint(x.x); r[j + 1] = __float_as_uint(x.y);
             r[j + 2] = __float_as_uint(x.z); r[j + 3] = __float_as_uint(x.w);
@@ -347,11 +376,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             r[j] = __float_as_uint(x);
           }
         }
-        // the staging tile used two stores ago must have been read out by the TMA engine
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        // this warp's staging tile must have been read out by the TMA engine (its previous store); on the residual path
+        // every lane must also be done reading its residual row before the tile is overwritten
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
-        const uint32_t sbuf = stage0 + (uint32_t)(nstore & 1) * 4096u;
-        const uint32_t srow = sbuf + (uint32_t)lane * 128u;
         if constexpr (CC == 32) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -371,7 +399,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if constexpr (REDUCE) tma_reduce_add_2d(&tmC, sbuf, n, m0 + quad * 32);
           else tma_store_2d(&tmC, sbuf, n, m0 + quad * 32);
         }
-        ++nstore;
       }
       tcgen05_fence_before();
       __syncwarp();
