@@ -234,7 +234,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--workload", default="decode", choices=["decode", "xe"],
                     help="decode = BASELINE.json's headline metric; xe = XE training step (config 5: 256 images x 5 captions per GPU)")
-    ap.add_argument("--depth", type=int, default=2, help="batches in flight (engine handles x streams, boficap_b200/pipeline.py)")
+    ap.add_argument("--depth", type=int, default=3, help="batches in flight (engine handles x streams, boficap_b200/pipeline.py)")
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", 0))
