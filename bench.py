@@ -141,6 +141,7 @@ def bench_xe(a, rank, local_rank, world):
     model = models.setup(opt)
     model.load_state_dict(synth.synth_state_dict(cfg, 0, a.calib))
     model = model.cuda()
+    model.train(not a.no_dropout)             # train(): dropout 0.1 / 0.5 on, as in the reference's training loop
     model.train_bind()
     flat_w, flat_g = model.flat_params(), model.flat_grads()
     flat_p = torch.nn.Parameter(flat_w)          # same storage: Adam over the whole buffer == Adam over every tensor
@@ -204,7 +205,7 @@ def bench_xe(a, rank, local_rank, world):
                 "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": a.precision,
                 "data": "synthetic",
                 "config": {"workload": "uic_sd XE training step (forward + criterion + backward + all-reduce + Adam), %d images x %d captions per GPU, "
-                                       "%d regions, %s, dropout off" % (B, spi, R, a.precision),
+                                       "%d regions, %s, dropout %s" % (B, spi, R, a.precision, "off" if a.no_dropout else "on (p=0.1, att_embed 0.5)"),
                            "parallelism": "data-parallel replicas x%d, one NCCL all-reduce of the %.0f MB flat gradient buffer" % (world, flat_g.numel() * 4 / 1e6)},
                 "loss_first": first, "loss_last": float(losses[0]), "gpu_launches": launches * a.steps, "clocks": clocks,
                 "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05), all %d launches of a step" % g["launches"],
@@ -234,6 +235,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--workload", default="decode", choices=["decode", "xe"],
                     help="decode = BASELINE.json's headline metric; xe = XE training step (config 5: 256 images x 5 captions per GPU)")
+    ap.add_argument("--no-dropout", action="store_true", help="xe workload: eval() arithmetic (dropout off)")
     ap.add_argument("--depth", type=int, default=3, help="batches in flight (engine handles x streams, boficap_b200/pipeline.py)")
     a = ap.parse_args()
 

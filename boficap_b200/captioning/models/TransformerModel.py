@@ -90,6 +90,8 @@ class TransformerModel(nn.Module):
         self._engine = None
         self._engine_key = None
         self._bound = None          # (flat_w, flat_g, version stamp) once the parameters are views of the training buffers
+        self.bofi_dropout_seed = 0  # base seed of the counter-based dropout masks; the step counter is added to it
+        self._train_steps = 0
 
     # ---- training: parameters as views of the library's flat buffers ---------------------------
     def train_bind(self, device=None, precision=None):
@@ -171,7 +173,14 @@ class TransformerModel(nn.Module):
             raise RuntimeError("boficap_b200 runs on CUDA tensors only (no CPU fallback)")
         if self._bound is None:
             self.train_bind(att_feats.device)
-        return self.engine(att_feats.device)
+        eng = self.engine(att_feats.device)
+        # nn.Module.train() / eval() decide, as for the reference's nn.Dropout modules
+        if self.training:
+            eng.train_set_dropout(self.cfg.dropout, self.cfg.drop_prob_lm, self.bofi_dropout_seed + self._train_steps)
+            self._train_steps += 1
+        else:
+            eng.train_set_dropout(0.0, 0.0, 0)
+        return eng
 
     def _forward(self, fc_feats, att_feats, seq, att_masks=None, phrase_num=None, phrase_length=None, phrase_syn=None,
                  extend_phrase_syn_seq=None, extend_phrase_seq=None, extend_phrase_seq_mask=None, glat_p=-1.0):

@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(128)
 attention_bwd_mma_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restrict__ K, const bf16* __restrict__ V, int ldkv,
                          const bf16* __restrict__ dO, int ldo, bf16* __restrict__ dQ, int lddq, bf16* __restrict__ dK, bf16* __restrict__ dV,
                          int lddkv, int Tq, int Tk, int qpk, const int* __restrict__ vis, int vis_bs, int vis_qs, int vis_div, float scale,
-                         int accumulate_kv) {
+                         int accumulate_kv, Drop drop) {
   pdl_enter();
   extern __shared__ __align__(16) uint8_t bw_smem[];
   constexpr int TKP = KT * 16;
@@ -146,6 +146,12 @@ attention_bwd_mma_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __rest
 #pragma unroll
       for (int nt = 0; nt < 2 * KT; ++nt) {
         sacc[nt][0] *= inv0; sacc[nt][1] *= inv0; sacc[nt][2] *= inv1; sacc[nt][3] *= inv1;      // P
+        if (drop.thresh) {                               // dP = d(P_dropped) o mask / (1 - p)
+          const int c = nt * 8 + 2 * t4;
+          const int g0 = kb * nq + r0, g1 = kb * nq + r1;
+          pacc[nt][0] *= drop_mul(drop, att_idx(g0, head, c)); pacc[nt][1] *= drop_mul(drop, att_idx(g0, head, c + 1));
+          pacc[nt][2] *= drop_mul(drop, att_idx(g1, head, c)); pacc[nt][3] *= drop_mul(drop, att_idx(g1, head, c + 1));
+        }
         d0 += sacc[nt][0] * pacc[nt][0] + sacc[nt][1] * pacc[nt][1];
         d1 += sacc[nt][2] * pacc[nt][2] + sacc[nt][3] * pacc[nt][3];
       }
@@ -162,8 +168,14 @@ attention_bwd_mma_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __rest
         dsa[nt >> 1][(nt & 1) * 2 + 0] = ds01;
         dsa[nt >> 1][(nt & 1) * 2 + 1] = ds23;
         const int c = nt * 8 + 2 * t4;
-        *reinterpret_cast<uint32_t*>(Ps + (m0 + g) * PP + c) = pack2_bf16(sacc[nt][0], sacc[nt][1]);
-        *reinterpret_cast<uint32_t*>(Ps + (m0 + g + 8) * PP + c) = pack2_bf16(sacc[nt][2], sacc[nt][3]);
+        float k0 = 1.f, k1 = 1.f, k2 = 1.f, k3 = 1.f;     // dV uses the dropped probabilities
+        if (drop.thresh) {
+          const int g0 = kb * nq + r0, g1 = kb * nq + r1;
+          k0 = drop_mul(drop, att_idx(g0, head, c)); k1 = drop_mul(drop, att_idx(g0, head, c + 1));
+          k2 = drop_mul(drop, att_idx(g1, head, c)); k3 = drop_mul(drop, att_idx(g1, head, c + 1));
+        }
+        *reinterpret_cast<uint32_t*>(Ps + (m0 + g) * PP + c) = pack2_bf16(sacc[nt][0] * k0, sacc[nt][1] * k1);
+        *reinterpret_cast<uint32_t*>(Ps + (m0 + g + 8) * PP + c) = pack2_bf16(sacc[nt][2] * k2, sacc[nt][3] * k3);
         *reinterpret_cast<uint32_t*>(Ds + (m0 + g) * PP + c) = ds01;
         *reinterpret_cast<uint32_t*>(Ds + (m0 + g + 8) * PP + c) = ds23;
       }

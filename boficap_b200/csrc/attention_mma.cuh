@@ -36,7 +36,7 @@ template <int KT>
 __global__ void __launch_bounds__(128)
 attention_mma_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restrict__ K, const bf16* __restrict__ V, int ldkv,
                      bf16* __restrict__ O, int ldo, int Tq, int Tk, const int* __restrict__ vis, int vis_bs, int vis_qs,
-                     int vis_div, int kv_div, float scale, const int* live_rows) {
+                     int vis_div, int kv_div, float scale, const int* live_rows, Drop drop) {
   pdl_enter();
   if (step_is_dead(live_rows)) return;
   extern __shared__ __align__(16) uint8_t att_smem[];
@@ -125,8 +125,14 @@ attention_mma_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restrict
       const float p2 = __expf(sacc[nt][2] - sub1), p3 = __expf(sacc[nt][3] - sub1);
       sum0 += p0 + p1;
       sum1 += p2 + p3;
-      pa[nt >> 1][(nt & 1) * 2 + 0] = pack2_bf16(p0, p1);     // a0a1 / a4a5 : row g
-      pa[nt >> 1][(nt & 1) * 2 + 1] = pack2_bf16(p2, p3);     // a2a3 / a6a7 : row g+8
+      float k0 = 1.f, k1 = 1.f, k2 = 1.f, k3 = 1.f;           // dropout on the probabilities (training only)
+      if (drop.thresh) {
+        const int c = nt * 8 + 2 * t4;
+        k0 = drop_mul(drop, att_idx(b * Tq + r0, head, c)); k1 = drop_mul(drop, att_idx(b * Tq + r0, head, c + 1));
+        k2 = drop_mul(drop, att_idx(b * Tq + r1, head, c)); k3 = drop_mul(drop, att_idx(b * Tq + r1, head, c + 1));
+      }
+      pa[nt >> 1][(nt & 1) * 2 + 0] = pack2_bf16(p0 * k0, p1 * k1);     // a0a1 / a4a5 : row g
+      pa[nt >> 1][(nt & 1) * 2 + 1] = pack2_bf16(p2 * k2, p3 * k3);     // a2a3 / a6a7 : row g+8
     }
     sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
     sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
@@ -170,7 +176,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 attention_row_kernel(const T* __restrict__ Q, int ldq, const T* __restrict__ K, const T* __restrict__ V, int ldkv,
                      T* __restrict__ O, int ldo, int Tk, const int* __restrict__ vis, int vis_div, int kv_div, float scale,
-                     const int* live_rows, const int* __restrict__ finished) {
+                     const int* live_rows, const int* __restrict__ finished, Drop drop) {
   pdl_enter();
   if (step_is_dead(live_rows)) return;
   if (finished && finished[blockIdx.x]) return;
@@ -219,7 +225,7 @@ attention_row_kernel(const T* __restrict__ Q, int ldq, const T* __restrict__ K, 
 #pragma unroll
   for (int jj = 0; jj < kMaxKeys / 32; ++jj) {
     const int j = jj * 32 + lane;
-    if (j < Tk) ps[head][j] = sc[jj] / sum;
+    if (j < Tk) ps[head][j] = sc[jj] / sum * drop_mul(drop, att_idx(b, head, j));
   }
   __syncwarp();
   float o0 = 0.f, o1 = 0.f;
@@ -257,7 +263,7 @@ constexpr int kRowsPerCta = 4;
 __global__ void __launch_bounds__(kRowsPerCta * 256)
 attention_row_bf16_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restrict__ K, const bf16* __restrict__ V, int ldkv,
                           bf16* __restrict__ O, int ldo, int nb, int Tk, const int* __restrict__ vis, int vis_div, int kv_div,
-                          float scale, const int* live_rows, const int* __restrict__ finished) {
+                          float scale, const int* live_rows, const int* __restrict__ finished, Drop drop) {
   pdl_enter();
   if (step_is_dead(live_rows)) return;
   __shared__ float ps[kRowsPerCta * 8][kMaxKeys];
@@ -323,7 +329,7 @@ attention_row_bf16_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __res
   const float inv = 1.f / sum;
 #pragma unroll
   for (int p = 0; p < kMaxKeys / 8; ++p) {
-    if (p < npass && sub == 0) ps[warp][p * 8 + kslot] = sc[p] * inv;
+    if (p < npass && sub == 0) ps[warp][p * 8 + kslot] = sc[p] * inv * drop_mul(drop, att_idx(b, head, p * 8 + kslot));
   }
   __syncwarp();
   // ---- P.V ----

@@ -80,6 +80,25 @@ inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+// Dropout (training path only).  Counter-based: the keep/drop decision of element `idx` of dropout site `key` is a pure
+// function (murmur3 finaliser), so the backward pass regenerates the mask instead of storing it, and the CPU oracle can
+// reproduce it exactly (oracle/bofi_oracle.py:drop_mask).  thresh = p * 2^32 (0 = disabled), scale = 1 / (1 - p).
+struct Drop {
+  uint32_t key = 0, thresh = 0;
+  float scale = 1.f;
+};
+__host__ __device__ __forceinline__ uint32_t drop_hash(uint32_t key, uint32_t idx) {
+  uint32_t h = (idx * 0x9E3779B1u) ^ key;
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
+}
+__device__ __forceinline__ float drop_mul(const Drop& d, uint32_t idx) {      // 0 or 1/(1-p); 1 when disabled
+  if (d.thresh == 0) return 1.f;
+  return drop_hash(d.key, idx) >= d.thresh ? d.scale : 0.f;
+}
+// element index of an attention probability: (global query row, head, key)
+__device__ __forceinline__ uint32_t att_idx(int qrow, int head, int key) { return ((uint32_t)qrow * 8u + (uint32_t)head) * 128u + (uint32_t)key; }
+
 // Work of a bounding step is skipped once every row has finished (device-side `break` of
 // TransformerModel.py:1869-1870): kernels of the step read the live-row counter first.
 __device__ __forceinline__ bool step_is_dead(const int* live_rows) {

@@ -297,21 +297,21 @@ static int layernorm(bofi_engine* e, cudaStream_t s, const float* x, size_t in_s
 template <int KT>
 static cudaError_t launch_attention_mma(cudaStream_t s, dim3 grid, size_t smem, const bf16* Q, int ldq, const bf16* K, const bf16* V,
                                         int ldkv, bf16* O, int ldo, int Tq, int Tk, const int* vis, int vis_bs, int vis_qs,
-                                        int vis_div, int kv_div, float scale, const int* live) {
+                                        int vis_div, int kv_div, float scale, const int* live, Drop drop) {
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t err = cudaFuncSetAttribute(attention_mma_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     configured = smem;
   }
-  launch_k(attention_mma_kernel<KT>, grid, 128, smem, s, Q, ldq, K, V, ldkv, O, ldo, Tq, Tk, vis, vis_bs, vis_qs, vis_div, kv_div, scale, live);
+  launch_k(attention_mma_kernel<KT>, grid, 128, smem, s, Q, ldq, K, V, ldkv, O, ldo, Tq, Tk, vis, vis_bs, vis_qs, vis_div, kv_div, scale, live, drop);
   return cudaGetLastError();
 }
 
 template <typename T>
 static int attention(bofi_engine* e, cudaStream_t s, const T* Q, int ldq, const T* K, const T* V, int ldkv, T* O, int ldo,
                      int nb, int Tq, int Tk, const int* vis, int vis_bs, int vis_qs, int vis_div, int kv_div,
-                     const int* live, const int* finished = nullptr) {
+                     const int* live, const int* finished = nullptr, Drop drop = Drop()) {
   if (nb <= 0) return BOFI_OK;
   if (Tk > kMaxKeys || Tq > kMaxKeys) return fail(BOFI_ERR_INVALID, "attention over %d x %d (max %d)", Tq, Tk, kMaxKeys);
   const float scale = 1.0f / sqrtf((float)kHeadDim);
@@ -320,9 +320,9 @@ static int attention(bofi_engine* e, cudaStream_t s, const T* Q, int ldq, const 
   if (Tq == 1 && !e->attn_simt_only) {
     if constexpr (std::is_same<T, bf16>::value)
       launch_k(attention_row_bf16_kernel, ceil_div(nb, kRowsPerCta), kRowsPerCta * 256, 0, s, Q, ldq, K, V, ldkv, O, ldo, nb, Tk, vis, vis_div,
-               kv_div, scale, live, finished);
+               kv_div, scale, live, finished, drop);
     else
-      launch_k(attention_row_kernel<T>, nb, 256, 0, s, Q, ldq, K, V, ldkv, O, ldo, Tk, vis, vis_div, kv_div, scale, live, finished);
+      launch_k(attention_row_kernel<T>, nb, 256, 0, s, Q, ldq, K, V, ldkv, O, ldo, Tk, vis, vis_div, kv_div, scale, live, finished, drop);
     CU_TRY(cudaGetLastError());
     return BOFI_OK;
   }
@@ -332,7 +332,7 @@ static int attention(bofi_engine* e, cudaStream_t s, const T* Q, int ldq, const 
       const size_t smem = attention_mma_smem_bytes(KT, Tq);
       dim3 grid(e->cfg.heads, nb);
       cudaError_t err = cudaErrorInvalidValue;
-#define BOFI_ATT_CASE(n) case n: err = launch_attention_mma<n>(s, grid, smem, Q, ldq, K, V, ldkv, O, ldo, Tq, Tk, vis, vis_bs, vis_qs, vis_div, kv_div, scale, live); break;
+#define BOFI_ATT_CASE(n) case n: err = launch_attention_mma<n>(s, grid, smem, Q, ldq, K, V, ldkv, O, ldo, Tq, Tk, vis, vis_bs, vis_qs, vis_div, kv_div, scale, live, drop); break;
       switch (KT) {
         BOFI_ATT_CASE(1) BOFI_ATT_CASE(2) BOFI_ATT_CASE(3) BOFI_ATT_CASE(4)
         BOFI_ATT_CASE(5) BOFI_ATT_CASE(6) BOFI_ATT_CASE(7) BOFI_ATT_CASE(8)
@@ -350,7 +350,7 @@ static int attention(bofi_engine* e, cudaStream_t s, const T* Q, int ldq, const 
     configured = attention_smem_bytes(kMaxKeys);
   }
   dim3 grid(e->cfg.heads, nb);
-  launch_k(attention_kernel<T>, grid, 128, smem, s, Q, ldq, K, V, ldkv, O, ldo, Tq, Tk, vis, vis_bs, vis_qs, vis_div, kv_div, scale, live);
+  launch_k(attention_kernel<T>, grid, 128, smem, s, Q, ldq, K, V, ldkv, O, ldo, Tq, Tk, vis, vis_bs, vis_qs, vis_div, kv_div, scale, live, drop);
   CU_TRY(cudaGetLastError());
   return BOFI_OK;
 }
@@ -867,7 +867,7 @@ static void train_release(bofi_engine* e) {
   if (!e->train) return;
   TrainState& t = e->train->st;
   t.arena.release();
-  DevBuf* all[] = {&t.tr_a, &t.tr_b, &t.tr_w, &t.zeros, &t.ln_partial, &t.cs_partial, &t.scratch_f32, &t.dkv, &t.dmem};
+  DevBuf* all[] = {&t.tr_a, &t.tr_b, &t.tr_w, &t.zeros, &t.ln_partial, &t.cs_partial, &t.scratch_f32, &t.dkv, &t.dmem, &t.zbuf};
   for (DevBuf* b : all) b->release();
   delete e->train;
   e->train = nullptr;

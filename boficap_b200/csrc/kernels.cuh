@@ -63,7 +63,7 @@ template <typename T>
 __global__ void __launch_bounds__(128)
 attention_kernel(const T* __restrict__ Q, int ldq, const T* __restrict__ K, const T* __restrict__ V, int ldkv,
                  T* __restrict__ O, int ldo, int Tq, int Tk, const int* __restrict__ vis, int vis_bs, int vis_qs,
-                 int vis_div, int kv_div, float scale, const int* live_rows) {
+                 int vis_div, int kv_div, float scale, const int* live_rows, Drop drop) {
   pdl_enter();
   if (step_is_dead(live_rows)) return;
   extern __shared__ float smem[];
@@ -121,7 +121,7 @@ attention_kernel(const T* __restrict__ Q, int ldq, const T* __restrict__ K, cons
 #pragma unroll
     for (int jj = 0; jj < kMaxKeys / 32; ++jj) {
       const int j = jj * 32 + lane;
-      if (j < Tk) p[j] = sc[jj] / sum;
+      if (j < Tk) p[j] = sc[jj] / sum * drop_mul(drop, att_idx(b * Tq + t, head, j));
     }
     __syncwarp();
     float o0 = 0.f, o1 = 0.f;

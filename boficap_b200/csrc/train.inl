@@ -61,6 +61,7 @@ struct LayerTape {        // T-typed buffers are void*
   float* x2 = nullptr;
   void *y2 = nullptr, *ffh = nullptr;
   float* x_out = nullptr;
+  Drop d_sa_att, d_sa_out, d_ca_att, d_ca_out, d_ffh, d_ffn_out;     // dropout sites of the layer (disabled when p == 0)
 };
 struct BoundTape {
   float* x_in = nullptr;          // [N*Tb, 512]
@@ -69,12 +70,14 @@ struct BoundTape {
   LayerTape lt;                   // rows (n, p): ao, x1, y1, q, ao2, x2, y2, ffh, x_out
   float* hn = nullptr;            // [Mb, 512] length_predictor.norm output (fp32: the heads are fp32)
   float* hid = nullptr;           // [Mb, 200]
+  Drop d_embed, d_hid;
 };
 struct DecTape {
   float* x_in = nullptr;
   std::vector<LayerTape> layers;
   void* y_final = nullptr;        // [N*T, 512]
   float* logits = nullptr;        // [N*T, Vpad] (fused-loss path) or nullptr
+  Drop d_embed;
 };
 struct TrainState {
   bool valid = false;
@@ -92,13 +95,73 @@ struct TrainState {
   std::vector<void*> kv;          // [B*R, 1024] per bounding / decoder layer
   BoundTape sa_b, na_b;
   DecTape sa_d, na_d;
-  DevBuf tr_a, tr_b, tr_w, zeros, ln_partial, cs_partial, scratch_f32, dkv, dmem;
+  DevBuf tr_a, tr_b, tr_w, zeros, ln_partial, cs_partial, scratch_f32, dkv, dmem, zbuf;
+  // Dropout (train() mode of the reference): p_sub = opt.dropout at every sub-layer output, attention probability,
+  // FFN hidden, positional encoding and head hidden; p_att = opt.drop_prob_lm after att_embed's ReLU.  Sites are numbered
+  // in forward order from 0 every step; key(site) = drop_hash(seed, site); the backward pass reuses the keys.
+  float p_sub = 0.f, p_att = 0.f;
+  uint32_t seed = 0, site = 0;
+  Drop d_att_embed;
+  Drop next_drop(float p) {
+    Drop d;
+    if (p > 0.f) {
+      d.key = drop_hash(seed, site);
+      d.thresh = (uint32_t)std::min(4294967295.0, (double)p * 4294967296.0);
+      d.scale = 1.0f / (1.0f - p);
+    }
+    ++site;
+    return d;
+  }
 };
+
+template <typename T>
+static int sublayer_out(bofi_engine* e, cudaStream_t s, TrainState* ts, const T* a, int lda, const Lin& lin, const float* x_in, float* x_out,
+                        int rows, const Drop& d);
 
 static TrainState* train_state(bofi_engine* e);
 
 template <typename T> static T* aalloc(TrainState* ts, size_t n) { return reinterpret_cast<T*>(ts->arena.alloc(n * sizeof(T))); }
 #define A_TRY(ptr) do { if (!(ptr)) return fail(BOFI_ERR_NOMEM, "training arena allocation failed"); } while (0)
+
+// ---- dropout helpers ------------------------------------------------------------------------------------------
+template <typename T>
+static int dropout_inplace(bofi_engine* e, cudaStream_t s, T* x, size_t n, const Drop& d) {
+  if (!d.thresh) return BOFI_OK;
+  ProfScope prof(e, s, PC_OTHER, 0.0, 2.0 * n * sizeof(T));
+  launch_k(dropout_inplace_kernel<T>, 148 * 8, 256, 0, s, x, n / 4, d);
+  CU_TRY(cudaGetLastError());
+  return BOFI_OK;
+}
+template <typename TIn, typename TOut>
+static int dropout_apply(bofi_engine* e, cudaStream_t s, const TIn* in, TOut* out, size_t n, const Drop& d) {
+  ProfScope prof(e, s, PC_OTHER, 0.0, (double)n * (sizeof(TIn) + sizeof(TOut)));
+  launch_k(dropout_apply_kernel<TIn, TOut>, 148 * 8, 256, 0, s, in, out, n / 4, d);
+  CU_TRY(cudaGetLastError());
+  return BOFI_OK;
+}
+// SublayerConnection output: x_out = x_in + dropout(a . W^T + b).  Without dropout the residual add is the GEMM epilogue;
+// with dropout the GEMM writes the sub-layer output z and one fused pass applies mask, scale and residual.
+template <typename T>
+static int sublayer_out(bofi_engine* e, cudaStream_t s, TrainState* ts, const T* a, int lda, const Lin& lin, const float* x_in, float* x_out,
+                        int rows, const Drop& d) {
+  if (!d.thresh) return linear<T, float>(e, s, a, lda, lin, x_in, kD, x_out, kD, rows, 0, nullptr);
+  RC_TRY(ts->zbuf.reserve((size_t)rows * kD * sizeof(T)));
+  T* z = ts->zbuf.as<T>();
+  RC_TRY((linear<T, T>(e, s, a, lda, lin, nullptr, 0, z, kD, rows, 0, nullptr)));
+  ProfScope prof(e, s, PC_OTHER, 0.0, (double)rows * kD * (sizeof(T) + 8));
+  launch_k(drop_add_kernel<T>, 148 * 8, 256, 0, s, (const T*)z, x_in, x_out, (size_t)rows * kD / 4, d);
+  CU_TRY(cudaGetLastError());
+  return BOFI_OK;
+}
+// gradient w.r.t. the sub-layer output z: dz = dxT o mask / (1 - p)  (dxT itself when dropout is off)
+template <typename T>
+static int sublayer_grad(bofi_engine* e, cudaStream_t s, TrainState* ts, const T* dxT, int rows, const Drop& d, const T** dz) {
+  if (!d.thresh) { *dz = dxT; return BOFI_OK; }
+  RC_TRY(ts->zbuf.reserve((size_t)rows * kD * sizeof(T)));
+  RC_TRY((dropout_apply<T, T>(e, s, dxT, ts->zbuf.as<T>(), (size_t)rows * kD, d)));
+  *dz = ts->zbuf.as<T>();
+  return BOFI_OK;
+}
 
 // ---- forward pieces -----------------------------------------------------------------------------------------
 // One pre-norm layer with every intermediate kept (same kernels as run_layer).
@@ -114,8 +177,11 @@ static int t_layer_fwd(bofi_engine* e, cudaStream_t s, TrainState* ts, const Lay
   tp.y0 = y0; tp.qkv = qkv; tp.ao = ao; tp.x1 = x1;
   RC_TRY(layernorm<T>(e, s, x_in, kD, ly.ln[0], y0, kD, rows, nullptr, nullptr));
   RC_TRY((linear<T, T>(e, s, y0, kD, ly.sa.qkv, nullptr, 0, qkv, 3 * kD, rows, 0, nullptr)));
-  RC_TRY(attention<T>(e, s, qkv, 3 * kD, qkv + kD, qkv + 2 * kD, 3 * kD, ao, kD, nb, Tq, Tq, self_vis, vis_bs, vis_qs, 1, 1, nullptr));
-  RC_TRY((linear<T, float>(e, s, ao, kD, ly.sa.o, x_in, kD, x1, kD, rows, 0, nullptr)));
+  tp.d_sa_att = ts->next_drop(ts->p_sub);
+  tp.d_sa_out = ts->next_drop(ts->p_sub);
+  RC_TRY(attention<T>(e, s, qkv, 3 * kD, qkv + kD, qkv + 2 * kD, 3 * kD, ao, kD, nb, Tq, Tq, self_vis, vis_bs, vis_qs, 1, 1, nullptr, nullptr,
+                      tp.d_sa_att));
+  RC_TRY(sublayer_out<T>(e, s, ts, ao, kD, ly.sa.o, x_in, x1, rows, tp.d_sa_out));
   const float* xm = x1;
   int f = 1;
   if (ly.cross) {
@@ -126,8 +192,10 @@ static int t_layer_fwd(bofi_engine* e, cudaStream_t s, TrainState* ts, const Lay
     tp.y1 = y1; tp.q = q; tp.ao2 = ao2; tp.x2 = x2;
     RC_TRY(layernorm<T>(e, s, x1, kD, ly.ln[1], y1, kD, rows, nullptr, nullptr));
     RC_TRY((linear<T, T>(e, s, y1, kD, ly.ca.q, nullptr, 0, q, kD, rows, 0, nullptr)));
-    RC_TRY(attention<T>(e, s, q, kD, kvmem, kvmem + kD, 2 * kD, ao2, kD, nb, Tq, R, mem_len, 1, 0, kv_div, kv_div, nullptr));
-    RC_TRY((linear<T, float>(e, s, ao2, kD, ly.ca.o, x1, kD, x2, kD, rows, 0, nullptr)));
+    tp.d_ca_att = ts->next_drop(ts->p_sub);
+    tp.d_ca_out = ts->next_drop(ts->p_sub);
+    RC_TRY(attention<T>(e, s, q, kD, kvmem, kvmem + kD, 2 * kD, ao2, kD, nb, Tq, R, mem_len, 1, 0, kv_div, kv_div, nullptr, nullptr, tp.d_ca_att));
+    RC_TRY(sublayer_out<T>(e, s, ts, ao2, kD, ly.ca.o, x1, x2, rows, tp.d_ca_out));
     xm = x2;
     f = 2;
   }
@@ -136,8 +204,11 @@ static int t_layer_fwd(bofi_engine* e, cudaStream_t s, TrainState* ts, const Lay
   float* xo = aalloc<float>(ts, (size_t)rows * kD); A_TRY(xo);
   tp.y2 = y2; tp.ffh = ffh; tp.x_out = xo;
   RC_TRY(layernorm<T>(e, s, xm, kD, ly.ln[f], y2, kD, rows, nullptr, nullptr));
+  tp.d_ffh = ts->next_drop(ts->p_sub);
+  tp.d_ffn_out = ts->next_drop(ts->p_sub);
   RC_TRY((linear<T, T>(e, s, y2, kD, ly.w1, nullptr, 0, ffh, dff, rows, 1, nullptr)));
-  RC_TRY((linear<T, float>(e, s, ffh, dff, ly.w2, xm, kD, xo, kD, rows, 0, nullptr)));
+  RC_TRY(dropout_inplace<T>(e, s, ffh, (size_t)rows * dff, tp.d_ffh));
+  RC_TRY(sublayer_out<T>(e, s, ts, ffh, dff, ly.w2, xm, xo, rows, tp.d_ffn_out));
   return BOFI_OK;
 }
 
@@ -154,8 +225,9 @@ static int t_bound_fwd(bofi_engine* e, cudaStream_t s, TrainState* ts, BoundTape
   T* y0 = aalloc<T>(ts, (size_t)N * Tb * kD); A_TRY(y0);
   T* qkv = aalloc<T>(ts, (size_t)N * Tb * 3 * kD); A_TRY(qkv);
   bt.y0 = y0; bt.qkv = qkv;
+  bt.d_embed = ts->next_drop(ts->p_sub);
   launch_k(embed_xe_kernel, ceil_div(N * Tb, 8), 256, 0, s, W(e, "model.tgt_embed.lut.weight"), W(e, "model.syn_embed.lut.weight"),
-           W(e, "model.pos_embed.pe"), word_ids, Tb, 0, -1, syn_ids, Tb, 0, sqrtf((float)kD), bt.x_in, N * Tb, Tb);
+           W(e, "model.pos_embed.pe"), word_ids, Tb, 0, -1, syn_ids, Tb, 0, sqrtf((float)kD), bt.x_in, N * Tb, Tb, bt.d_embed);
   CU_TRY(cudaGetLastError());
   RC_TRY(layernorm<T>(e, s, bt.x_in, kD, ly.ln[0], y0, kD, N * Tb, nullptr, nullptr));
   RC_TRY((linear<T, T>(e, s, y0, kD, ly.sa.qkv, nullptr, 0, qkv, 3 * kD, N * Tb, 0, nullptr)));
@@ -174,25 +246,35 @@ static int t_bound_fwd(bofi_engine* e, cudaStream_t s, TrainState* ts, BoundTape
   bt.hid = aalloc<float>(ts, (size_t)Mb * 200); A_TRY(bt.hid);
   bt.q_rep = aalloc<T>(ts, (size_t)Mb * kD); A_TRY(bt.q_rep);
   tp.x_in = xr; tp.ao = ao; tp.x1 = x1; tp.y1 = y1; tp.q = q; tp.ao2 = ao2; tp.x2 = x2; tp.y2 = y2; tp.ffh = ffh; tp.x_out = x3;
-  launch_k(xe_bound_self_attn_kernel<T>, Mb, 256, 0, s, (const T*)qkv, Tb, P, ts->vis_b, ao, scale);
+  tp.d_sa_att = ts->next_drop(ts->p_sub);
+  tp.d_sa_out = ts->next_drop(ts->p_sub);
+  tp.d_ca_att = ts->next_drop(ts->p_sub);
+  tp.d_ca_out = ts->next_drop(ts->p_sub);
+  tp.d_ffh = ts->next_drop(ts->p_sub);
+  tp.d_ffn_out = ts->next_drop(ts->p_sub);
+  bt.d_hid = ts->next_drop(ts->p_sub);
+  launch_k(xe_bound_self_attn_kernel<T>, Mb, 256, 0, s, (const T*)qkv, Tb, P, ts->vis_b, ao, scale, tp.d_sa_att);
   CU_TRY(cudaGetLastError());
   launch_k(repeat_row_kernel<float>, ceil_div(Mb, 8), 256, 0, s, (const float*)bt.x_in, (size_t)Tb * kD, xr, N, P);
   CU_TRY(cudaGetLastError());
-  RC_TRY((linear<T, float>(e, s, ao, kD, ly.sa.o, xr, kD, x1, kD, Mb, 0, nullptr)));
+  RC_TRY(sublayer_out<T>(e, s, ts, ao, kD, ly.sa.o, xr, x1, Mb, tp.d_sa_out));
   RC_TRY(layernorm<T>(e, s, x1, kD, ly.ln[1], y1, kD, Mb, nullptr, nullptr));
   RC_TRY((linear<T, T>(e, s, y1, kD, ly.ca.q, nullptr, 0, q, kD, Mb, 0, nullptr)));
   const T* kvm = (const T*)ts->kv[0];
-  RC_TRY(attention<T>(e, s, q, kD, kvm, kvm + kD, 2 * kD, ao2, kD, Mb, 1, ts->R, mem_len, 1, 0, ts->spi * P, ts->spi * P, nullptr));
-  RC_TRY((linear<T, float>(e, s, ao2, kD, ly.ca.o, x1, kD, x2, kD, Mb, 0, nullptr)));
+  RC_TRY(attention<T>(e, s, q, kD, kvm, kvm + kD, 2 * kD, ao2, kD, Mb, 1, ts->R, mem_len, 1, 0, ts->spi * P, ts->spi * P, nullptr, nullptr,
+                      tp.d_ca_att));
+  RC_TRY(sublayer_out<T>(e, s, ts, ao2, kD, ly.ca.o, x1, x2, Mb, tp.d_ca_out));
   RC_TRY(layernorm<T>(e, s, x2, kD, ly.ln[2], y2, kD, Mb, nullptr, nullptr));
   RC_TRY((linear<T, T>(e, s, y2, kD, ly.w1, nullptr, 0, ffh, dff, Mb, 1, nullptr)));
-  RC_TRY((linear<T, float>(e, s, ffh, dff, ly.w2, x2, kD, x3, kD, Mb, 0, nullptr)));
+  RC_TRY(dropout_inplace<T>(e, s, ffh, (size_t)Mb * dff, tp.d_ffh));
+  RC_TRY(sublayer_out<T>(e, s, ts, ffh, dff, ly.w2, x2, x3, Mb, tp.d_ffn_out));
   RC_TRY(layernorm<float>(e, s, x3, kD, e->lp_norm, bt.hn, kD, Mb, nullptr, nullptr));
   {
     cudaError_t err = gemm_simt<float, float>(s, bt.hn, kD, e->head1.w32, kD, e->head1.b, nullptr, 0, bt.hid, 200, Mb, 200, kD, 1, nullptr);
     if (err != cudaSuccess) return fail(BOFI_ERR_CUDA, "head GEMM: %s", cudaGetErrorString(err));
     e->launches++;
   }
+  RC_TRY(dropout_inplace<float>(e, s, bt.hid, (size_t)Mb * 200, bt.d_hid));
   launch_k(xe_head_logp_kernel, ceil_div(Mb, 4), 128, 0, s, (const float*)bt.hid, e->w_len2, e->b_len2, e->w_syn2, e->b_syn2, 100, 20, 10,
            len_logp, syn_logp, Mb, P, Tb - 1);
   CU_TRY(cudaGetLastError());
@@ -208,8 +290,10 @@ static int t_dec_fwd(bofi_engine* e, cudaStream_t s, TrainState* ts, DecTape& dt
   const int* mem_len = ts->att_len;
   const int nb_layers = std::max(1, c.n_len);
   dt.x_in = aalloc<float>(ts, (size_t)rows * kD); A_TRY(dt.x_in);
+  dt.d_embed = ts->next_drop(ts->p_sub);
   launch_k(embed_xe_kernel, ceil_div(rows, 8), 256, 0, s, W(e, "model.tgt_embed.lut.weight"), W(e, "model.syn_embed.lut.weight"),
-           W(e, "model.pos_embed.pe"), word_ids, T_, 0, const_word, (const int*)ts->ext_syn, Tb, 1, sqrtf((float)kD), dt.x_in, rows, T_);
+           W(e, "model.pos_embed.pe"), word_ids, T_, 0, const_word, (const int*)ts->ext_syn, Tb, 1, sqrtf((float)kD), dt.x_in, rows, T_,
+           dt.d_embed);
   CU_TRY(cudaGetLastError());
   dt.layers.assign(c.n_dec, LayerTape());
   const float* x = dt.x_in;
@@ -266,7 +350,10 @@ static int train_forward_impl(bofi_engine* e, cudaStream_t s, TrainState* ts, co
     a_in = att;
   }
   ts->x0 = aalloc<float>(ts, (size_t)M * kD); A_TRY(ts->x0);
+  ts->site = 0;
+  ts->d_att_embed = ts->next_drop(ts->p_att);
   RC_TRY((linear<T, float>(e, s, a_in, F, e->att_embed, nullptr, 0, ts->x0, kD, M, 1, nullptr)));
+  RC_TRY(dropout_inplace<float>(e, s, ts->x0, (size_t)M * kD, ts->d_att_embed));
   if (len_dev) {
     launch_k(zero_padded_rows_kernel, ceil_div(M, 8), 256, 0, s, ts->x0, len_dev, B, R);
     CU_TRY(cudaGetLastError());
@@ -446,7 +533,7 @@ static int ln_bwd(bofi_engine* e, cudaStream_t s, TrainState* ts, const Norm& n,
 template <typename T>
 static int attn_bwd(bofi_engine* e, cudaStream_t s, const T* Q, int ldq, const T* K, const T* V, int ldkv, const T* dO, int ldo, T* dQ,
                     int lddq, T* dK, T* dV, int lddkv, int n_kv_blocks, int Tq, int Tk, int qpk, const int* vis, int vis_bs, int vis_qs,
-                    int vis_div, int accumulate_kv) {
+                    int vis_div, int accumulate_kv, Drop drop = Drop()) {
   if (n_kv_blocks <= 0) return BOFI_OK;
   if (Tk > kMaxKeys) return fail(BOFI_ERR_INVALID, "attention backward over %d keys (max %d)", Tk, kMaxKeys);
   const float scale = 1.0f / sqrtf((float)kHeadDim);
@@ -466,7 +553,7 @@ static int attn_bwd(bofi_engine* e, cudaStream_t s, const T* Q, int ldq, const T
       configured = true;                                                                                                               \
     }                                                                                                                                  \
     err = launch_k(attention_bwd_mma_kernel<n>, grid, 128, sm, s, Q, ldq, K, V, ldkv, dO, ldo, dQ, lddq, dK, dV, lddkv, Tq, Tk, qpk, vis, \
-                   vis_bs, vis_qs, vis_div, scale, accumulate_kv);                                                                     \
+                   vis_bs, vis_qs, vis_div, scale, accumulate_kv, drop);                                                               \
   } break;
       switch (KT) { BOFI_ATTBM(1) BOFI_ATTBM(2) BOFI_ATTBM(3) BOFI_ATTBM(4) BOFI_ATTBM(5) BOFI_ATTBM(6) BOFI_ATTBM(7) BOFI_ATTBM(8) }
 #undef BOFI_ATTBM
@@ -483,7 +570,7 @@ static int attn_bwd(bofi_engine* e, cudaStream_t s, const T* Q, int ldq, const T
       configured = attention_bwd_smem_bytes(4 * KPT_);                                                                              \
     }                                                                                                                               \
     launch_k(attention_bwd_kernel<T, KPT_>, grid, 256, smem, s, Q, ldq, K, V, ldkv, dO, ldo, dQ, lddq, dK, dV, lddkv, Tq, Tk, qpk, vis, \
-             vis_bs, vis_qs, vis_div, scale, accumulate_kv);                                                                        \
+             vis_bs, vis_qs, vis_div, scale, accumulate_kv, drop);                                                                  \
   } while (0)
   if (Tk <= 24) BOFI_ATTB(6);
   else if (Tk <= 40) BOFI_ATTB(10);
@@ -504,28 +591,32 @@ static int t_layer_bwd(bofi_engine* e, cudaStream_t s, TrainState* ts, const Lay
   const int rows = nb * Tq, dff = e->cfg.d_ff;
   const float* xm = ly.cross ? tp.x2 : tp.x1;
   const int f = ly.cross ? 2 : 1;
-  // FFN: x_out = xm + w2(relu(w1(LN(xm))))
-  RC_TRY(lin_bwd<T>(e, s, ts, ly.w2, (const T*)tp.ffh, dff, dxT, kD, rows, g2, dff));           // g2 = d ffh [rows, dff]
+  // FFN: x_out = xm + drop(w2(drop(relu(w1(LN(xm))))))
+  const T* dz = nullptr;
+  RC_TRY(sublayer_grad<T>(e, s, ts, dxT, rows, tp.d_ffn_out, &dz));
+  RC_TRY(lin_bwd<T>(e, s, ts, ly.w2, (const T*)tp.ffh, dff, dz, kD, rows, g2, dff));            // g2 = d ffh [rows, dff]
   e->launches++;
-  launch_k(relu_bwd_kernel<T>, 148 * 8, 256, 0, s, g2, (const T*)tp.ffh, (size_t)rows * dff / 4);
+  launch_k(relu_bwd_kernel<T>, 148 * 8, 256, 0, s, g2, (const T*)tp.ffh, (size_t)rows * dff / 4, tp.d_ffh.scale);
   CU_TRY(cudaGetLastError());
   RC_TRY(lin_bwd<T>(e, s, ts, ly.w1, (const T*)tp.y2, kD, g2, dff, rows, g1, kD));               // g1 = d y2
   RC_TRY((ln_bwd<T, T>(e, s, ts, ly.ln[f], xm, g1, dx, dx, dxT, rows)));
   if (ly.cross) {
     // x2 = x1 + o(attn(q(LN(x1)), kv(mem)))
-    RC_TRY(lin_bwd<T>(e, s, ts, ly.ca.o, (const T*)tp.ao2, kD, dxT, kD, rows, g1, kD));          // g1 = d ao2
+    RC_TRY(sublayer_grad<T>(e, s, ts, dxT, rows, tp.d_ca_out, &dz));
+    RC_TRY(lin_bwd<T>(e, s, ts, ly.ca.o, (const T*)tp.ao2, kD, dz, kD, rows, g1, kD));           // g1 = d ao2
     // g2 reused as dq [rows, 512]
     RC_TRY(attn_bwd<T>(e, s, (const T*)tp.q, kD, kvmem, kvmem + kD, 2 * kD, g1, kD, g2, kD, dkv_mem, dkv_mem + kD, 2 * kD,
-                       rows / (qpk * Tq), Tq, R, qpk, mem_len, 1, 0, qpk, dkv_accumulate));
+                       rows / (qpk * Tq), Tq, R, qpk, mem_len, 1, 0, qpk, dkv_accumulate, tp.d_ca_att));
     RC_TRY(lin_bwd<T>(e, s, ts, ly.ca.q, (const T*)tp.y1, kD, g2, kD, rows, g1, kD));            // g1 = d y1
     RC_TRY((ln_bwd<T, T>(e, s, ts, ly.ln[1], tp.x1, g1, dx, dx, dxT, rows)));
   }
   if (skip_self) return BOFI_OK;
   // x1 = x_in + o(attn(qkv(LN(x_in))))
-  RC_TRY(lin_bwd<T>(e, s, ts, ly.sa.o, (const T*)tp.ao, kD, dxT, kD, rows, g1, kD));              // g1 = d ao
+  RC_TRY(sublayer_grad<T>(e, s, ts, dxT, rows, tp.d_sa_out, &dz));
+  RC_TRY(lin_bwd<T>(e, s, ts, ly.sa.o, (const T*)tp.ao, kD, dz, kD, rows, g1, kD));               // g1 = d ao
   const T* qkv = (const T*)tp.qkv;
   RC_TRY(attn_bwd<T>(e, s, qkv, 3 * kD, qkv + kD, qkv + 2 * kD, 3 * kD, g1, kD, g2, 3 * kD, g2 + kD, g2 + 2 * kD, 3 * kD, nb, Tq, Tq, 1,
-                     self_vis, vis_bs, vis_qs, 1, 0));                                           // g2 = d qkv [rows, 1536]
+                     self_vis, vis_bs, vis_qs, 1, 0, tp.d_sa_att));                              // g2 = d qkv [rows, 1536]
   RC_TRY(lin_bwd<T>(e, s, ts, ly.sa.qkv, (const T*)tp.y0, kD, g2, 3 * kD, rows, g1, kD));        // g1 = d y0
   RC_TRY((ln_bwd<T, T>(e, s, ts, ly.ln[0], tp.x_in, g1, dx, dx, dxT, rows)));
   return BOFI_OK;
@@ -547,7 +638,8 @@ static int t_dec_bwd(bofi_engine* e, cudaStream_t s, TrainState* ts, DecTape& dt
     RC_TRY(t_layer_bwd<T>(e, s, ts, e->dec[l], dt.layers[l], dx, dxT, g1, g2, N, T_, self_vis, vis_bs, vis_qs, (const T*)ts->kv[nb_layers + l],
                           dkv, first_pass ? 0 : 1, ts->R, mem_len, ts->spi, false));
   }
-  // input embeddings: x = tgt_embed(word)*sqrt(d) + syn_embed(syn)*sqrt(d) + pe
+  // input embeddings: x = drop(tgt_embed(word)*sqrt(d) + syn_embed(syn)*sqrt(d) + pe)
+  if (dt.d_embed.thresh) RC_TRY((dropout_apply<float, float>(e, s, dx, dx, (size_t)rows * kD, dt.d_embed)));
   const float sq = sqrtf((float)kD);
   if (const_word) {
     RC_TRY(embed_small_bwd(e, s, ts, dx, nullptr, 0, 0, c.bos_idx, T_, rows, G(e, "model.tgt_embed.lut.weight")));
@@ -591,7 +683,7 @@ static int t_bound_bwd(bofi_engine* e, cudaStream_t s, TrainState* ts, BoundTape
   }
   CU_TRY(cudaMemsetAsync(dhid, 0, (size_t)Mb * 256 * 4, s));
   launch_k(xe_head2_dgrad_kernel, ceil_div((size_t)Mb * 200, 256), 256, 0, s, (const float*)dzh, (const float*)bt.hid, e->w_len2, e->w_syn2, 100,
-           20, 10, dhid, 256, Mb);
+           20, 10, dhid, 256, Mb, bt.d_hid.scale);
   CU_TRY(cudaGetLastError());
   const LayerTape& tp = bt.lt;
   bool head_tc = false;
@@ -630,7 +722,9 @@ static int t_bound_bwd(bofi_engine* e, cudaStream_t s, TrainState* ts, BoundTape
   RC_TRY(t_layer_bwd<T>(e, s, ts, ly, tp, dx, dxT, g1, g2, Mb, 1, nullptr, 0, 0, (const T*)ts->kv[0], dkv, first_pass ? 0 : 1, ts->R, mem_len,
                         ts->spi * P, true));
   // self-attention sublayer: x1[(n,p)] = x_in[n, 0] + o(attn(q[n,0], K/V[n, :vis_b[n,p]]))
-  RC_TRY(lin_bwd<T>(e, s, ts, ly.sa.o, (const T*)tp.ao, kD, dxT, kD, Mb, g1, kD));                // g1 = d ao [Mb, 512]
+  const T* dz = nullptr;
+  RC_TRY(sublayer_grad<T>(e, s, ts, dxT, Mb, tp.d_sa_out, &dz));
+  RC_TRY(lin_bwd<T>(e, s, ts, ly.sa.o, (const T*)tp.ao, kD, dz, kD, Mb, g1, kD));                 // g1 = d ao [Mb, 512]
   T* q_rep = (T*)bt.q_rep;
   const T* qkv = (const T*)bt.qkv;
   e->launches += 2;
@@ -641,7 +735,7 @@ static int t_bound_bwd(bofi_engine* e, cudaStream_t s, TrainState* ts, BoundTape
   T* dqkv = g2 + (size_t)Mb * kD;
   CU_TRY(cudaMemsetAsync(dqkv, 0, (size_t)N * Tb * 3 * kD * sizeof(T), s));
   RC_TRY(attn_bwd<T>(e, s, q_rep, kD, qkv + kD, qkv + 2 * kD, 3 * kD, g1, kD, dq_rep, kD, dqkv + kD, dqkv + 2 * kD, 3 * kD, N, 1, Tb, P, ts->vis_b,
-                     1, 0, 1, 0));
+                     1, 0, 1, 0, tp.d_sa_att));
   launch_k(sum_over_passes_kernel<T, T>, ceil_div(N, 8), 256, 0, s, (const T*)dq_rep, P, dqkv, (size_t)Tb * 3 * kD, N, 0);
   CU_TRY(cudaGetLastError());
   RC_TRY(lin_bwd<T>(e, s, ts, ly.sa.qkv, (const T*)bt.y0, kD, dqkv, 3 * kD, N * Tb, g1, kD));     // g1 = d y0 [N*Tb, 512]
@@ -652,6 +746,7 @@ static int t_bound_bwd(bofi_engine* e, cudaStream_t s, TrainState* ts, BoundTape
   e->launches += 1;
   launch_k(sum_over_passes_kernel<float, float>, ceil_div(N, 8), 256, 0, s, (const float*)dx, P, dxin, (size_t)Tb * kD, N, 1);
   CU_TRY(cudaGetLastError());
+  if (bt.d_embed.thresh) RC_TRY((dropout_apply<float, float>(e, s, dxin, dxin, (size_t)N * Tb * kD, bt.d_embed)));
   const float sq = sqrtf((float)kD);
   if (word_ids) {
     ProfScope prof(e, s, PC_OTHER, 0.0, (double)N * Tb * kD * 8);
@@ -712,7 +807,7 @@ static int train_backward_impl(bofi_engine* e, cudaStream_t s, TrainState* ts, T
                           false));
   // att_embed: x0 = relu(att . W^T + b), zero on padded rows (their relu mask is false as x0 == 0 there)
   e->launches++;
-  launch_k(relu_bwd_cast_kernel<T>, 148 * 8, 256, 0, s, (const float*)dx, (const float*)ts->x0, g1, (size_t)M * kD / 4);
+  launch_k(relu_bwd_cast_kernel<T>, 148 * 8, 256, 0, s, (const float*)dx, (const float*)ts->x0, g1, (size_t)M * kD / 4, ts->d_att_embed.scale);
   CU_TRY(cudaGetLastError());
   RC_TRY(lin_bwd<T>(e, s, ts, e->att_embed, (const T*)ts->attT, F, g1, kD, M, (T*)nullptr, 0));
   return BOFI_OK;

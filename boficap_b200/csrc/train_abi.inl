@@ -195,4 +195,14 @@ extern "C" int bofi_train_step_xe(bofi_handle_t e, void* stream, const float* at
   return rc;
 }
 
+extern "C" int bofi_train_set_dropout(bofi_handle_t e, float p, float p_att_embed, uint32_t seed) {
+  if (!e) return fail(BOFI_ERR_INVALID, "null handle");
+  if (p < 0.f || p >= 1.f || p_att_embed < 0.f || p_att_embed >= 1.f) return fail(BOFI_ERR_INVALID, "dropout probabilities must be in [0, 1)");
+  TrainState* ts = train_state(e);
+  ts->p_sub = p;
+  ts->p_att = p_att_embed;
+  ts->seed = seed;
+  return BOFI_OK;
+}
+
 extern "C" int bofi_train_launches(bofi_handle_t e) { return e ? e->launches : -1; }

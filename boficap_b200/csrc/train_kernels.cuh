@@ -36,7 +36,7 @@ __global__ void xe_prepare_kernel(const int* __restrict__ labels, const int* __r
 __global__ void __launch_bounds__(256)
 embed_xe_kernel(const float* __restrict__ word_lut, const float* __restrict__ syn_lut, const float* __restrict__ pe,
                 const int* __restrict__ word_ids, int w_stride, int w_off, int const_word,
-                const int* __restrict__ syn_ids, int s_stride, int s_off, float sqrt_d, float* __restrict__ x, int rows, int T) {
+                const int* __restrict__ syn_ids, int s_stride, int s_off, float sqrt_d, float* __restrict__ x, int rows, int T, Drop drop) {
   pdl_enter();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -58,7 +58,54 @@ embed_xe_kernel(const float* __restrict__ word_lut, const float* __restrict__ sy
     }
     const float4 pp = load4(pe + (size_t)r * kD + c);
     e.x += pp.x; e.y += pp.y; e.z += pp.z; e.w += pp.w;
+    if (drop.thresh) {                                  // PositionalEncoding.dropout (:1506)
+      const uint32_t i0 = (uint32_t)row * kD + c;
+      e.x *= drop_mul(drop, i0); e.y *= drop_mul(drop, i0 + 1); e.z *= drop_mul(drop, i0 + 2); e.w *= drop_mul(drop, i0 + 3);
+    }
     store4(x + (size_t)row * kD + c, e);
+  }
+}
+
+// x[i] *= mask(i) / (1 - p), in place (FFN inner dropout :1478, att_embed dropout :1646, head dropout :376).
+template <typename T>
+__global__ void __launch_bounds__(256) dropout_inplace_kernel(T* __restrict__ x, size_t n4, Drop drop) {
+  pdl_enter();
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    float4 v = load4(x + i * 4);
+    const uint32_t i0 = (uint32_t)(i * 4);
+    v.x *= drop_mul(drop, i0); v.y *= drop_mul(drop, i0 + 1); v.z *= drop_mul(drop, i0 + 2); v.w *= drop_mul(drop, i0 + 3);
+    store4(x + i * 4, v);
+  }
+}
+// out[i] = in[i] * mask(i) / (1 - p)   (gradient of a dropout site; TIn / TOut = fp32 or the GEMM operand type)
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256) dropout_apply_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, size_t n4, Drop drop) {
+  pdl_enter();
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    float4 v = load4(in + i * 4);
+    const uint32_t i0 = (uint32_t)(i * 4);
+    v.x *= drop_mul(drop, i0); v.y *= drop_mul(drop, i0 + 1); v.z *= drop_mul(drop, i0 + 2); v.w *= drop_mul(drop, i0 + 3);
+    store4(out + i * 4, v);
+  }
+}
+// SublayerConnection (:1351-1363) with dropout: x_out = x_in + dropout(z), z = the sub-layer's output (GEMM operand type)
+template <typename T>
+__global__ void __launch_bounds__(256)
+drop_add_kernel(const T* __restrict__ z, const float* __restrict__ x_in, float* __restrict__ x_out, size_t n4, Drop drop) {
+  pdl_enter();
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    float4 v = load4(z + i * 4);
+    const float4 r = load4(x_in + i * 4);
+    const uint32_t i0 = (uint32_t)(i * 4);
+    v.x = r.x + v.x * drop_mul(drop, i0); v.y = r.y + v.y * drop_mul(drop, i0 + 1);
+    v.z = r.z + v.z * drop_mul(drop, i0 + 2); v.w = r.w + v.w * drop_mul(drop, i0 + 3);
+    store4(x_out + i * 4, v);
   }
 }
 
@@ -79,7 +126,7 @@ repeat_row_kernel(const T* __restrict__ in, size_t in_row_stride, T* __restrict_
 // One CTA per (n, p), one warp per head.  Same arithmetic order as attention_kernel.
 template <typename T>
 __global__ void __launch_bounds__(256)
-xe_bound_self_attn_kernel(const T* __restrict__ qkv, int Tb, int P, const int* __restrict__ vis_b, T* __restrict__ O, float scale) {
+xe_bound_self_attn_kernel(const T* __restrict__ qkv, int Tb, int P, const int* __restrict__ vis_b, T* __restrict__ O, float scale, Drop drop) {
   pdl_enter();
   __shared__ float qs[8][kHeadDim];
   const int row = blockIdx.x, n = row / P, head = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -106,7 +153,7 @@ xe_bound_self_attn_kernel(const T* __restrict__ qkv, int Tb, int P, const int* _
   const float mx = warp_max(s);
   const float e = (lane < nvis) ? expf(s - mx) : 0.f;
   const float sum = warp_sum(e);
-  const float p = e / sum;
+  const float p = e / sum * drop_mul(drop, att_idx(row, head, lane));
   float o0 = 0.f, o1 = 0.f;
   for (int j = 0; j < nvis; ++j) {
     const float pj = __shfl_sync(0xffffffffu, p, j);
@@ -212,7 +259,7 @@ xe_head2_wgrad_reduce_kernel(const float* __restrict__ partial, int chunks, int 
 // dhid[row, c] = (sum_o dz[row, o] * W2[o, c]) * (hid[row, c] > 0)      (classifier2 dgrad + ReLU backward)
 __global__ void __launch_bounds__(256)
 xe_head2_dgrad_kernel(const float* __restrict__ dz, const float* __restrict__ hid, const float* __restrict__ w_len,
-                      const float* __restrict__ w_syn, int Hh, int n_len, int n_syn, float* __restrict__ dhid, int ld_out, int Mb) {
+                      const float* __restrict__ w_syn, int Hh, int n_len, int n_syn, float* __restrict__ dhid, int ld_out, int Mb, float gain) {
   pdl_enter();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)Mb * 2 * Hh) return;
@@ -223,7 +270,7 @@ xe_head2_dgrad_kernel(const float* __restrict__ dz, const float* __restrict__ hi
   } else {
     for (int o = 0; o < n_syn; ++o) acc = fmaf(dz[(size_t)row * 32 + n_len + o], w_syn[o * Hh + c - Hh], acc);
   }
-  dhid[(size_t)row * ld_out + c] = hid[i] > 0.f ? acc : 0.f;
+  dhid[(size_t)row * ld_out + c] = hid[i] > 0.f ? acc * gain : 0.f;
 }
 
 // Backward of log_softmax over the vocabulary (Generator, TransformerModel.py:1315-1323):
@@ -471,7 +518,7 @@ __global__ void __launch_bounds__(256)
 attention_bwd_kernel(const T* __restrict__ Q, int ldq, const T* __restrict__ K, const T* __restrict__ V, int ldkv,
                      const T* __restrict__ dO, int ldo, T* __restrict__ dQ, int lddq, T* __restrict__ dK, T* __restrict__ dV, int lddkv,
                      int Tq, int Tk, int qpk, const int* __restrict__ vis, int vis_bs, int vis_qs, int vis_div, float scale,
-                     int accumulate_kv) {
+                     int accumulate_kv, Drop drop) {
   pdl_enter();
   extern __shared__ float bsm[];
   const int TKP = (Tk + 3) & ~3;
@@ -541,15 +588,21 @@ attention_bwd_kernel(const T* __restrict__ Q, int ldq, const T* __restrict__ K, 
         sum += sc[jj];
       }
       sum = warp_sum(sum);
-      float dsum = 0.f;
+      float dsum = 0.f, km[4];
+      const int qrow = kb * nq + qi;
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) { sc[jj] = sc[jj] / sum; dsum += sc[jj] * dp[jj]; }
+      for (int jj = 0; jj < 4; ++jj) {
+        km[jj] = drop_mul(drop, att_idx(qrow, head, jj * 32 + lane));       // dropout on the probabilities
+        sc[jj] = sc[jj] / sum;
+        dp[jj] *= km[jj];
+        dsum += sc[jj] * dp[jj];
+      }
       dsum = warp_sum(dsum);
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
         const int j = jj * 32 + lane;
         if (j < TKP) {
-          Ps[i * TKP + j] = (j < nvis) ? sc[jj] : 0.f;
+          Ps[i * TKP + j] = (j < nvis) ? sc[jj] * km[jj] : 0.f;
           Ds[i * TKP + j] = (j < nvis) ? sc[jj] * (dp[jj] - dsum) : 0.f;
         }
       }
@@ -600,27 +653,28 @@ inline size_t attention_bwd_smem_bytes(int Tk) {
 
 // d_ffh *= (ffh > 0)   (ReLU backward; ffh is the saved post-ReLU activation)
 template <typename T>
-__global__ void __launch_bounds__(256) relu_bwd_kernel(T* __restrict__ d, const T* __restrict__ act, size_t n4) {
+__global__ void __launch_bounds__(256) relu_bwd_kernel(T* __restrict__ d, const T* __restrict__ act, size_t n4, float gain) {
   pdl_enter();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n4; i += stride) {
     float4 g = load4(d + i * 4);
     const float4 a = load4(act + i * 4);
-    g.x = a.x > 0.f ? g.x : 0.f; g.y = a.y > 0.f ? g.y : 0.f; g.z = a.z > 0.f ? g.z : 0.f; g.w = a.w > 0.f ? g.w : 0.f;
+    // `act` is the saved post-ReLU (and post-dropout) activation: zero where either killed it; gain = 1/(1-p) of the dropout
+    g.x = a.x > 0.f ? g.x * gain : 0.f; g.y = a.y > 0.f ? g.y * gain : 0.f; g.z = a.z > 0.f ? g.z * gain : 0.f; g.w = a.w > 0.f ? g.w * gain : 0.f;
     store4(d + i * 4, g);
   }
 }
 // out(T) = dx * (x0 > 0)   (att_embed ReLU backward, fp32 residual gradient in, GEMM operand out)
 template <typename T>
-__global__ void __launch_bounds__(256) relu_bwd_cast_kernel(const float* __restrict__ dx, const float* __restrict__ act, T* __restrict__ out, size_t n4) {
+__global__ void __launch_bounds__(256) relu_bwd_cast_kernel(const float* __restrict__ dx, const float* __restrict__ act, T* __restrict__ out, size_t n4, float gain) {
   pdl_enter();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n4; i += stride) {
     float4 g = load4(dx + i * 4);
     const float4 a = load4(act + i * 4);
-    g.x = a.x > 0.f ? g.x : 0.f; g.y = a.y > 0.f ? g.y : 0.f; g.z = a.z > 0.f ? g.z : 0.f; g.w = a.w > 0.f ? g.w : 0.f;
+    g.x = a.x > 0.f ? g.x * gain : 0.f; g.y = a.y > 0.f ? g.y * gain : 0.f; g.z = a.z > 0.f ? g.z * gain : 0.f; g.w = a.w > 0.f ? g.w * gain : 0.f;
     store4(out + i * 4, g);
   }
 }

@@ -224,6 +224,9 @@ class BofiEngine:
         self._train_keep = (att_feats, att_len, ints)
         return losses
 
+    def train_set_dropout(self, p, p_att_embed, seed):
+        _lib.check(self.lib.bofi_train_set_dropout(self.handle, float(p), float(p_att_embed), int(seed) & 0xFFFFFFFF))
+
     def train_launches(self):
         return int(self.lib.bofi_train_launches(self.handle))
 

@@ -179,6 +179,14 @@ int bofi_train_step_xe(bofi_handle_t h, void* stream, const float* att_feats, co
                        int32_t seq_per_img, int32_t L, int32_t P, const int32_t* labels, const int32_t* phrase_num,
                        const int32_t* phrase_length, const int32_t* phrase_syn, const int32_t* ext_syn, const int32_t* ext_seq,
                        const int32_t* sa_vis, float* losses);
+/* Dropout of the reference's train() mode for the following training calls (0, 0 = off, the eval() arithmetic):
+ *   p            opt.dropout: sub-layer outputs (TransformerModel.py:1363), attention probabilities (:1430), FFN hidden
+ *                (:1478), positional encoding (:1506), bounding-head hidden (:376)
+ *   p_att_embed  opt.drop_prob_lm after att_embed's ReLU (:1646)
+ * Masks are counter-based (murmur3 finaliser of (seed, site, element index); common.cuh: Drop): the backward pass
+ * regenerates them, and oracle/bofi_oracle.py:DropSim reproduces them bit for bit.  The positional-encoding mask of
+ * the bounding input is drawn once per caption and shared by its bounding passes (the reference redraws it per pass). */
+int bofi_train_set_dropout(bofi_handle_t h, float p, float p_att_embed, uint32_t seed);
 /* Kernels enqueued by the last training call. */
 int bofi_train_launches(bofi_handle_t h);
 

@@ -420,3 +420,173 @@ class BofiOracle:
         parts = [nll(sa_len, len_t, box_mask) / denom, nll(sa_logp, words, word_mask) / denom, nll(sa_syn, syn_t, box_mask) / denom,
                  nll(na_len, len_t, box_mask) / denom, nll(na_logp, words, word_mask) / denom, nll(na_syn, syn_t, box_mask) / denom]
         return sum(parts), parts
+
+
+# ---- A16 with dropout: the CUDA path's formulation, masks reproduced bit for bit -------------------------------
+class DropSim:
+    """Counter-based dropout masks of the CUDA training path (boficap_b200/csrc/common.cuh: drop_hash / Drop,
+    train.inl: TrainState::next_drop).  Sites are numbered in forward order from 0; key(site) = drop_hash(seed, site);
+    element `idx` of a site is kept iff drop_hash(key, idx) >= p * 2^32 and then scaled by 1 / (1 - p)."""
+    M = 0xFFFFFFFF
+
+    def __init__(self, p_sub, p_att, seed):
+        self.p_sub, self.p_att, self.seed, self.site = float(p_sub), float(p_att), int(seed) & self.M, 0
+
+    @classmethod
+    def _hash(cls, key, idx):
+        h = ((idx * 0x9E3779B1) & cls.M) ^ key
+        h = h ^ (h >> 16)
+        h = (h * 0x85EBCA6B) & cls.M
+        h = h ^ (h >> 13)
+        h = (h * 0xC2B2AE35) & cls.M
+        return h ^ (h >> 16)
+
+    def _next(self, p, idx):
+        site = self.site
+        self.site += 1
+        if p <= 0:
+            return torch.ones(idx.shape)
+        key = int(self._hash(self.seed, torch.tensor(site, dtype=torch.int64)))
+        thresh = min(4294967295, int(p * 4294967296.0))
+        scale = float(torch.tensor(1.0, dtype=torch.float32) / (torch.tensor(1.0, dtype=torch.float32) - torch.tensor(p, dtype=torch.float32)))
+        return (self._hash(key, idx) >= thresh).float() * scale
+
+    def elem(self, rows, width, p=None):
+        """mask [rows, width] of an element-wise site (index = row * width + col)."""
+        idx = torch.arange(rows * width, dtype=torch.int64).view(rows, width)
+        return self._next(self.p_sub if p is None else p, idx)
+
+    def att(self, nrows, Tk):
+        """mask [nrows, heads=8, Tk] of an attention-probability site (index = ((row * 8 + head) * 128 + key))."""
+        r = torch.arange(nrows, dtype=torch.int64)[:, None, None]
+        h = torch.arange(8, dtype=torch.int64)[None, :, None]
+        k = torch.arange(Tk, dtype=torch.int64)[None, None, :]
+        return self._next(self.p_sub, (r * 8 + h) * 128 + k)
+
+
+def _fused_methods():
+    def mha_d(self, p, q_in, kv_in, mask, amask):
+        """mha with a dropout mask amask [nb*Tq, h, Tk] on the probabilities (or None)."""
+        h, d = self.cfg.h, self.cfg.d_model
+        dk = d // h
+        nb, Tq = q_in.shape[:2]
+        q = self.lin(p + ".linears.0", q_in).view(nb, -1, h, dk).transpose(1, 2)
+        k = self.lin(p + ".linears.1", kv_in).view(nb, -1, h, dk).transpose(1, 2)
+        v = self.lin(p + ".linears.2", kv_in).view(nb, -1, h, dk).transpose(1, 2)
+        scores = torch.matmul(q, k.transpose(-2, -1)) / math.sqrt(dk)
+        if mask is not None:
+            scores = scores.masked_fill(mask.unsqueeze(1) == 0, float("-inf"))
+        pattn = F.softmax(scores, dim=-1)
+        if amask is not None:
+            pattn = pattn * amask.view(nb, Tq, h, -1).transpose(1, 2)
+        x = torch.matmul(pattn, v).transpose(1, 2).contiguous().view(nb, -1, d)
+        return self.lin(p + ".linears.3", x)
+
+    def layer_d(self, p, ffname, x, memory, src_mask, tgt_mask, drop, cross):
+        nb, T = x.shape[:2]
+        flat = lambda m: m.view(nb, T, -1)
+        a1, o1 = drop.att(nb * T, T), drop.elem(nb * T, self.cfg.d_model)
+        x = x + flat(o1) * mha_d(self, p + ".self_attn", self.layer_norm(p + ".sublayer.0.norm", x), self.layer_norm(p + ".sublayer.0.norm", x), tgt_mask, a1)
+        f = 1
+        if cross:
+            a2, o2 = drop.att(nb * T, memory.shape[1]), drop.elem(nb * T, self.cfg.d_model)
+            x = x + flat(o2) * mha_d(self, p + ".src_attn", self.layer_norm(p + ".sublayer.1.norm", x), memory, src_mask, a2)
+            f = 2
+        hmask, o3 = drop.elem(nb * T, self.cfg.d_ff), drop.elem(nb * T, self.cfg.d_model)
+        y = self.layer_norm(p + ".sublayer.%d.norm" % f, x)
+        hid = F.relu(self.lin(p + "." + ffname + ".w_1", y)) * flat(hmask)
+        return x + flat(o3) * self.lin(p + "." + ffname + ".w_2", hid)
+
+    def bound_d(self, x_in, memory, src_mask, vis_b, drop):
+        """All P bounding passes as one batch of (n, p) single-query rows (N_len == 1); x_in [N, Tb, 512] already carries its
+        positional-encoding dropout; vis_b [N, P] visible-key counts of the [LEN] row."""
+        N, Tb, d = x_in.shape
+        P = vis_b.shape[1]
+        h, dk = self.cfg.h, d // self.cfg.h
+        lp = "model.length_predictor"
+        p = lp + ".LengthPredictor.0"
+        y0 = self.layer_norm(p + ".sublayer.0.norm", x_in)
+        q0 = self.lin(p + ".self_attn.linears.0", y0[:, 0]).view(N, h, dk)
+        k = self.lin(p + ".self_attn.linears.1", y0).view(N, Tb, h, dk)
+        v = self.lin(p + ".self_attn.linears.2", y0).view(N, Tb, h, dk)
+        a_self, o_self = drop.att(N * P, Tb), drop.elem(N * P, d)
+        a_cross, o_cross = drop.att(N * P, memory.shape[1]), drop.elem(N * P, d)
+        hmask, o_ffn, hidmask = drop.elem(N * P, self.cfg.d_ff), drop.elem(N * P, d), drop.elem(N * P, 200)
+        scores = torch.einsum("nhd,nkhd->nhk", q0, k) / math.sqrt(dk)                       # [N, h, Tb]
+        scores = scores[:, None].expand(N, P, h, Tb)
+        visible = torch.arange(Tb)[None, None, None, :] < vis_b[:, :, None, None]
+        pattn = F.softmax(scores.masked_fill(~visible, float("-inf")), dim=-1) * a_self.view(N, P, h, Tb)
+        ao = torch.einsum("nphk,nkhd->nphd", pattn, v).reshape(N * P, d)
+        x = x_in[:, 0].repeat_interleave(P, 0) + o_self * self.lin(p + ".self_attn.linears.3", ao)
+        mem_rep = memory.repeat_interleave(P, 0)
+        src_rep = src_mask.repeat_interleave(P, 0)
+        x = x[:, None] + (o_cross * mha_d(self, p + ".src_attn", self.layer_norm(p + ".sublayer.1.norm", x)[:, None], mem_rep, src_rep,
+                                          a_cross).squeeze(1))[:, None]
+        x = x.squeeze(1)
+        y = self.layer_norm(p + ".sublayer.2.norm", x)
+        x = x + o_ffn * self.lin(p + ".ff.w_2", F.relu(self.lin(p + ".ff.w_1", y)) * hmask)
+        hn = self.layer_norm(lp + ".norm", x)
+        hid_len = F.relu(self.lin(lp + ".Length_classifier1", hn)) * hidmask[:, :100]
+        hid_syn = F.relu(self.lin(lp + ".Syntactic_classifier1", hn)) * hidmask[:, 100:]
+        ll = F.log_softmax(self.lin(lp + ".Length_classifier2", hid_len), dim=-1).view(N, P, -1)
+        sl = F.log_softmax(self.lin(lp + ".Syntactic_classifier2", hid_syn), dim=-1).view(N, P, -1)
+        pad = lambda t: torch.cat([t, torch.zeros(N, Tb - 1 - P, t.shape[2])], 1)
+        return pad(ll), pad(sl)
+
+    def forward_xe_fused(self, att_feats, att_masks, labels, phrase_num, phrase_length, extend_phrase_syn_seq, extend_phrase_seq,
+                         extend_phrase_seq_mask, drop=None):
+        """The training forward in the CUDA path's formulation (boficap_b200/csrc/train.inl): encoder once per image, memory
+        shared by the captions of an image, all bounding passes as one batch of [LEN] rows.  With drop=None it equals
+        forward_xe (tested); with a DropSim it reproduces the CUDA path's dropout masks element for element."""
+        c = self.cfg
+        drop = drop or DropSim(0.0, 0.0, 0)
+        if labels.dim() == 3:
+            labels = labels.reshape(-1, labels.shape[2])
+            phrase_num = phrase_num.reshape(-1)
+            phrase_length = phrase_length.reshape(-1, phrase_length.shape[2])
+            extend_phrase_syn_seq = extend_phrase_syn_seq.reshape(-1, extend_phrase_syn_seq.shape[2])
+            extend_phrase_seq = extend_phrase_seq.reshape(-1, extend_phrase_seq.shape[2])
+            L = extend_phrase_seq.shape[1]
+            extend_phrase_seq_mask = extend_phrase_seq_mask.reshape(-1, L, L)
+        B, R = att_feats.shape[:2]
+        N, Tb = labels.shape
+        T, spi = Tb - 2, N // B
+        drop.site = 0
+        m_att = drop.elem(B * R, c.d_model, drop.p_att).view(B, R, -1)
+        x = F.relu(self.lin("att_embed.0", att_feats.float())) * m_att
+        if att_masks is not None:
+            x = x * att_masks[:, :, None].to(x.dtype)
+            src_mask = att_masks.unsqueeze(-2)
+        else:
+            src_mask = torch.ones(B, 1, R, dtype=torch.bool)
+        for l in range(c.N_enc):
+            x = layer_d(self, "model.encoder.layers.%d" % l, "feed_forward", x, None, None, src_mask, drop, False)
+        memory = self.layer_norm("model.encoder.norm", x)
+        memory_n, src_n = memory.repeat_interleave(spi, 0), src_mask.repeat_interleave(spi, 0)
+        phrase_num, phrase_length = phrase_num.long(), phrase_length.long()
+        P = int(phrase_num.max())
+        steps = torch.arange(P)[None, :]
+        grow = (steps >= 1) & (steps < phrase_num[:, None])
+        vis_b = 1 + torch.cumsum(torch.where(grow, phrase_length[:, :P], torch.zeros_like(phrase_length[:, :P])), 1)
+        word_seq = labels.clone().long()
+        word_seq[:, 0] = c.len_idx
+
+        def decode(word_ids, tgt_mask):
+            xin = self.decoder_input(word_ids, extend_phrase_syn_seq[:, 1:-1]) * drop.elem(N * T, c.d_model).view(N, T, -1)
+            for l in range(c.N_dec):
+                xin = layer_d(self, "model.decoder.layers.%d" % l, "feed_forward", xin, memory_n, src_n, tgt_mask, drop, True)
+            return F.log_softmax(self.logit(self.layer_norm("model.decoder.norm", xin)), dim=-1)
+
+        sa_in = self.pos(self.embed("tgt_embed", word_seq)) * drop.elem(N * Tb, c.d_model).view(N, Tb, -1)
+        sa_len, sa_syn = bound_d(self, sa_in, memory_n, src_n, vis_b, drop)
+        sa_logp = decode(extend_phrase_seq, extend_phrase_seq_mask)
+        na_in = self.pos(self.embed("syn_embed", extend_phrase_syn_seq)) * drop.elem(N * Tb, c.d_model).view(N, Tb, -1)
+        na_len, na_syn = bound_d(self, na_in, memory_n, src_n, vis_b, drop)
+        syn_mask = (torch.arange(T)[None, None, :] < (vis_b[:, -1] - 1)[:, None, None]).expand(-1, T, -1)
+        na_logp = decode(torch.full_like(extend_phrase_seq, c.bos_idx), syn_mask)
+        return sa_len, sa_syn, sa_logp, na_len, na_syn, na_logp
+
+    BofiOracle.forward_xe_fused = forward_xe_fused
+
+
+_fused_methods()

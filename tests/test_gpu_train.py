@@ -47,7 +47,7 @@ def build_model(precision):
     opt.bofi_precision = precision
     model = models.setup(opt)
     model.load_state_dict(sd)
-    return model.cuda(), cfg
+    return model.cuda().eval(), cfg          # eval(): dropout off, the arithmetic the golden vectors were recorded with
 
 
 def batch_args(B, R, adaptive, seed, cfg):
@@ -144,3 +144,62 @@ def test_xe_optimizer_step_refreshes_weights():
     # the sampling path sees the updated weights as well
     seq = model(args[0], args[1], None, opt={"sample_method": "greedy", "train_mode": "NAIC"}, mode="sample")[0]
     assert seq.shape == (B, cfg.seq_length)
+
+
+def test_xe_dropout_matches_oracle_masks_fp32():
+    """train() mode: the counter-based dropout masks are reproduced by the oracle (DropSim), so losses and gradients with
+    dropout on can be compared exactly like the eval() ones."""
+    from oracle.bofi_oracle import BofiOracle, OracleConfig, DropSim
+    B, R, adaptive, seed = CASES[1]
+    cfg = BofiConfig()
+    sd = synth.synth_state_dict(cfg, 0, "s_real")
+    for k, v in sd.items():
+        if k != "model.pos_embed.pe":
+            v.requires_grad_(True)
+    o = BofiOracle.__new__(BofiOracle)
+    o.sd, o.cfg, o.record, o.trace = sd, OracleConfig(**cfg.to_dict()), False, {}
+    fc, att, masks = synth.synth_inputs(B, R, seed=7, adaptive=adaptive)
+    bt = synth.synth_xe_batch(B, seed=seed, vocab_size=cfg.vocab_size)
+    outs = o.forward_xe_fused(att, masks, bt["labels"], bt["phrase_num"], bt["phrase_length"], bt["extend_phrase_syn_seq"],
+                              bt["extend_phrase_seq"], bt["extend_phrase_seq_mask"], drop=DropSim(cfg.dropout, cfg.drop_prob_lm, 77))
+    loss, parts = o.loss_xe(outs, bt["phrase_num"], bt["phrase_length"], bt["phrase_syn"], bt["labels"])
+    loss.backward()
+    ref_grads = {k: (v.grad.detach().clone() if v.grad is not None else torch.zeros_like(v)) for k, v in sd.items() if k != "model.pos_embed.pe"}
+    model, _ = build_model("fp32")
+    args, _ = batch_args(B, R, adaptive, seed, cfg)
+    model.train()
+    model.bofi_dropout_seed = 77
+    model.train_bind()
+    model.zero_grad()
+    losses = model.xe_step(*args).cpu().numpy()
+    np.testing.assert_allclose(losses, [float(loss)] + [float(p) for p in parts], rtol=5e-5)
+    worst, name, cos = grad_report(model, ref_grads)
+    assert worst < 2e-3 and cos > 0.99999, (worst, name, cos)
+    # eval() switches dropout off again; a second train() step draws different masks
+    model.eval()
+    l_eval = float(model.xe_step(*args)[0])
+    model.train()
+    l_train2 = float(model.xe_step(*args)[0])
+    assert abs(l_eval - float(losses[0])) > 1e-3 and abs(l_train2 - float(losses[0])) > 1e-4
+    # the autograd bridge sees the same masks as the fused step
+    model.bofi_dropout_seed, model._train_steps = 77, 0
+    outs2 = model(*args)
+    loss2, _ = BofiOracle.loss_xe(outs2, bt["phrase_num"], bt["phrase_length"], bt["phrase_syn"], bt["labels"])
+    assert abs(float(loss2) - float(losses[0])) < 5e-4
+
+
+def test_xe_dropout_bf16_statistics():
+    """bf16 / tensor-core path with dropout: finite, reproducible for a fixed seed, different across seeds."""
+    B, R, adaptive, seed = CASES[0]
+    model, cfg = build_model("bf16")
+    args, _ = batch_args(B, R, adaptive, seed, cfg)
+    model.train()
+    model.train_bind()
+    vals = []
+    for s in (5, 5, 6):
+        model.bofi_dropout_seed, model._train_steps = s, 0
+        model.zero_grad()
+        vals.append(float(model.xe_step(*args)[0]))
+        g = model.flat_grads()
+        assert torch.isfinite(g).all()
+    assert vals[0] == vals[1] and vals[0] != vals[2], vals

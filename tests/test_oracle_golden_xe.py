@@ -56,3 +56,19 @@ def test_oracle_xe_matches_reference(name):
         np.testing.assert_allclose(g.reshape(-1)[:64].numpy(), fix["ghead/" + pname], atol=1e-5 + 1e-4 * float(np.abs(fix["ghead/" + pname]).max()), rtol=0, err_msg=pname)
         if "gfull/" + pname in fix:
             np.testing.assert_allclose(g.numpy(), fix["gfull/" + pname], atol=1e-5 + 1e-4 * float(np.abs(fix["gfull/" + pname]).max()), rtol=0, err_msg=pname)
+
+
+def test_oracle_fused_formulation_equals_reference_formulation():
+    """forward_xe_fused (the CUDA path's formulation; carries the reproducible dropout masks) == forward_xe at p = 0."""
+    fix = np.load(os.path.join(GOLDEN, CASES[1] + ".npz"))
+    cfg = BofiConfig()
+    sd = synth.synth_state_dict(cfg, 0, "s_real")
+    o = BofiOracle(sd, OracleConfig(**cfg.to_dict()))
+    B, R = int(fix["B"]), int(fix["R"])
+    fc, att, masks = synth.synth_inputs(B, R, seed=int(fix["input_seed"]), adaptive=bool(fix["adaptive"]))
+    bt = synth.synth_xe_batch(B, seed=int(fix["batch_seed"]), vocab_size=cfg.vocab_size)
+    a = (att, masks, bt["labels"], bt["phrase_num"], bt["phrase_length"], bt["extend_phrase_syn_seq"], bt["extend_phrase_seq"],
+         bt["extend_phrase_seq_mask"])
+    with torch.no_grad():
+        for x, y in zip(o.forward_xe(*a), o.forward_xe_fused(*a)):
+            assert float((x - y).abs().max()) < 5e-5
