@@ -228,17 +228,18 @@ class TransformerModel(nn.Module):
         att_len = None
         if att_masks is not None:
             att_len = att_masks.data.long().sum(1).to(torch.int32)
+        if sample_method == "greedy":
+            eng.set_sampling("greedy")
+        elif sample_method == "sample":
+            # the device draws the tokens (Gumbel-max, library stream); torch's CPU generator supplies the seed so that
+            # torch.manual_seed makes a run reproducible
+            eng.set_sampling("sample", temperature, int(torch.randint(0, 2 ** 31 - 1, (1,))))
+        else:
+            raise NotImplementedError("sample_method=%r: only 'greedy' and 'sample' (the uic_sd* configs) are built" % sample_method)
         eng.encode(att_feats.float(), att_len)
         torch.cuda.synchronize(att_feats.device)
         start = time.time()
         seq, logp, pnum, plen, psyn = eng.decode(train_mode, sample_n, output_logsoftmax, True)
-        if sample_method != "greedy":
-            if train_mode != "NAIC":
-                raise NotImplementedError("multinomial sampling is only wired for NAIC in this round")
-            lp = logp / temperature
-            lp = lp.masked_fill(lp.isnan(), -10.0)
-            seq = torch.distributions.Categorical(logits=lp).sample()
-            total = plen.sum(1, keepdim=True)
-            seq = seq.masked_fill(torch.arange(self.seq_length, device=seq.device)[None, :] >= total, self.pad_idx)
+        eng.set_sampling("greedy")
         torch.cuda.synchronize(att_feats.device)
         return seq, logp, pnum, plen, psyn, time.time() - start

@@ -154,6 +154,8 @@ struct bofi_engine {
   unsigned long long bound_key[6] = {0, 0, 0, 0, 0, 0};
   int bound_launches = 0;
   int bound_eager_runs = 0;
+  Sampler sampler;                       // bofi_set_sampling: greedy (default) or multinomial for the next decodes
+  unsigned sample_calls = 0;
   struct TrainStateHolder* train = nullptr;   // XE-training tape (train.inl), created on first use
 };
 
@@ -782,7 +784,7 @@ static int decode_naic(bofi_engine* e, cudaStream_t s, int sn, int output_logsof
   {
     ProfScope prof(e, s, PC_VOCAB, 0.0, 0.0);
     launch_k(vocab_epilogue_kernel, rows * L, kVocabThreads, 0, s, e->logits.as<float>(), e->Vpad, e->V, logprobs, seq, e->st.last, -1, L,
-                                                 output_logsoftmax, nullptr);
+             output_logsoftmax, nullptr, e->sampler);
   }
   CU_TRY(cudaGetLastError());
   {
@@ -837,8 +839,10 @@ static int decode_saic(bofi_engine* e, cudaStream_t s, int sn, int output_logsof
     RC_TRY((linear<T, float>(e, s, e->y.as<T>(), kD, e->generator, nullptr, 0, e->logits.as<float>(), e->Vpad, rows * L, 0, live)));
     {
       ProfScope prof(e, s, PC_VOCAB, 0.0, 0.0);
+      Sampler sp = e->sampler;             // a fresh noise field per phrase step
+      sp.key = drop_hash(sp.key, (uint32_t)i);
       launch_k(vocab_stats_kernel, rows * L, 256, 0, s, e->logits.as<float>(), e->Vpad, e->V, e->tok.as<int>(), e->sa_mx.as<float>(),
-                                                 e->sa_lse.as<float>(), e->st);
+               e->sa_lse.as<float>(), e->st, sp);
     }
     CU_TRY(cudaGetLastError());
     if (logprobs) {
@@ -1047,6 +1051,16 @@ int bofi_sample_host(bofi_handle_t e, void* stream, int32_t mode, int32_t sn, in
   RC_TRY(bofi_sample_host_async(e, stream, mode, sn, output_logsoftmax, att_feats, att_len, B, R, seq, logprobs, phrase_num,
                                 phrase_length, phrase_syn));
   CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return BOFI_OK;
+}
+
+int bofi_set_sampling(bofi_handle_t e, int32_t method, float temperature, uint32_t seed) {
+  if (!e) return fail(BOFI_ERR_INVALID, "null handle");
+  if (method != 0 && method != 1) return fail(BOFI_ERR_INVALID, "sampling method %d (0 = greedy, 1 = multinomial)", method);
+  if (method == 1 && !(temperature > 0.f)) return fail(BOFI_ERR_INVALID, "temperature must be > 0");
+  e->sampler.enabled = method;
+  e->sampler.inv_temp = method ? 1.0f / temperature : 1.0f;
+  e->sampler.key = drop_hash(0x5A17C0DEu, seed);
   return BOFI_OK;
 }
 

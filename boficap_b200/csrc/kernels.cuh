@@ -535,12 +535,26 @@ __device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {
   return a.i < b.i ? a : b;
 }
 
+// Multinomial sampling of CaptionModel.sample_next_word (CaptionModel.py:403-431: logits / temperature, NaN -> -10,
+// Categorical(...).sample()) as a Gumbel-max: argmax_v (z_v / T + g_v), g_v = -log(-log(u_v)), u_v from the counter-based
+// hash of (key, row, v).  Same distribution as the reference, the library's own random stream (seeded by the caller).
+struct Sampler {
+  uint32_t key = 0;
+  int enabled = 0;          // 0 = greedy
+  float inv_temp = 1.f;
+};
+__device__ __forceinline__ float gumbel_score(const Sampler& sp, float z, int row, int v) {
+  const float zz = (z != z) ? -10.f : z * sp.inv_temp;
+  const float u = ((float)drop_hash(sp.key, (uint32_t)row * 16384u + (uint32_t)v) + 0.5f) * (1.0f / 4294967296.0f);
+  return zz - __logf(-__logf(u));
+}
+
 constexpr int kVocabThreads = 512;
 constexpr int kVocabVec = 5;    // float4 per thread: 512 threads x 5 x 4 = 10240 >= Vpad (9504)
 __global__ void __launch_bounds__(kVocabThreads, 3)
 vocab_epilogue_kernel(const float* __restrict__ logits, int ldl, int V, float* __restrict__ logp_out,
                       long long* __restrict__ seq_out, const int* __restrict__ total_len, int total_off, int L,
-                      int do_logsoftmax, int* __restrict__ tok_out_i32) {
+                      int do_logsoftmax, int* __restrict__ tok_out_i32, Sampler sp) {
   pdl_enter();
   // The whole row lives in registers: logits are read from HBM exactly once (128-bit loads, all independent),
   // max / argmax / sum-exp are block reductions, and the log-probs are written once.
@@ -577,6 +591,30 @@ vocab_epilogue_kernel(const float* __restrict__ logits, int ldl, int V, float* _
 #pragma unroll
   for (int w = 1; w < kVocabThreads / 32; ++w) am = better(am, s_am[w]);
   const float mx = am.v;
+  int picked = am.i;
+  if (sp.enabled) {                      // sampled token: a second block-wide argmax over the perturbed scores
+    ArgMax sm = {-INFINITY, 0x7fffffff};
+#pragma unroll
+    for (int i = 0; i < kVocabVec; ++i) {
+      const int c = (tid + i * kVocabThreads) * 4;
+      const float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (c + q < V) sm = better(sm, ArgMax{gumbel_score(sp, e[q], row, c + q), c + q});
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ArgMax other = {__shfl_xor_sync(0xffffffffu, sm.v, o), __shfl_xor_sync(0xffffffffu, sm.i, o)};
+      sm = better(sm, other);
+    }
+    __syncthreads();                     // s_am is reused
+    if (lane == 0) s_am[warp] = sm;
+    __syncthreads();
+    sm = s_am[0];
+#pragma unroll
+    for (int w = 1; w < kVocabThreads / 32; ++w) sm = better(sm, s_am[w]);
+    picked = sm.i;
+  }
   if (logp_out) {
     float* o = logp_out + (size_t)row * V;
     float lse = 0.f;
@@ -617,7 +655,7 @@ vocab_epilogue_kernel(const float* __restrict__ logits, int ldl, int V, float* _
     }
   }
   if (tid == 0) {
-    int tok = am.i;
+    int tok = picked;
     if (tok_out_i32) tok_out_i32[row] = tok;            // SAIC keeps the unpadded pick
     if (seq_out) {
       if (total_len && t >= total_len[b] + total_off) tok = 0;
@@ -666,7 +704,7 @@ __global__ void saic_prepare_kernel(DecodeState st, int rows, int Lb, int L, int
 // (the reference aborts the whole batch when any log-prob of the step is NaN, :1956-1958).
 __global__ void __launch_bounds__(256)
 vocab_stats_kernel(const float* __restrict__ logits, int ldl, int V, int* __restrict__ tok, float* __restrict__ mx_out,
-                   float* __restrict__ lse_out, DecodeState st) {
+                   float* __restrict__ lse_out, DecodeState st, Sampler sp) {
   pdl_enter();
   if (st.counters[4] == 0) return;
   __shared__ ArgMax s_am[8];
@@ -691,11 +729,28 @@ vocab_stats_kernel(const float* __restrict__ logits, int ldl, int V, int* __rest
   s = warp_sum(s);
   if (lane == 0) s_sum[warp] = s;
   __syncthreads();
+  int picked = am.i;
+  if (sp.enabled) {
+    ArgMax sm = {-INFINITY, 0x7fffffff};
+    for (int c = tid; c < V; c += 256) sm = better(sm, ArgMax{gumbel_score(sp, z[c], row, c), c});
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ArgMax other = {__shfl_xor_sync(0xffffffffu, sm.v, o), __shfl_xor_sync(0xffffffffu, sm.i, o)};
+      sm = better(sm, other);
+    }
+    __syncthreads();
+    if (lane == 0) s_am[warp] = sm;
+    __syncthreads();
+    sm = s_am[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) sm = better(sm, s_am[w]);
+    picked = sm.i;
+  }
   if (tid == 0) {
     float tot = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) tot += s_sum[w];
-    tok[row] = am.i;
+    tok[row] = picked;
     mx_out[row] = am.v;
     lse_out[row] = logf(tot);
     if (am.v != am.v) atomicExch(&st.counters[5], 1);

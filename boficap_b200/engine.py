@@ -117,6 +117,9 @@ class BofiEngine:
                 B, R, _ptr(out["seq"]), _ptr(out.get("logp")), _ptr(out["pnum"]), _ptr(out["plen"]), _ptr(out["psyn"])))
         return out
 
+    def set_sampling(self, method="greedy", temperature=1.0, seed=0):
+        _lib.check(self.lib.bofi_set_sampling(self.handle, 0 if method == "greedy" else 1, float(temperature), int(seed) & 0xFFFFFFFF))
+
     def decode_info(self):
         info = _lib.DecodeInfoC()
         with torch.cuda.device(self.device):

@@ -103,6 +103,14 @@ int bofi_decode(bofi_handle_t h, void* stream, int32_t mode, int32_t sample_n, i
                 int64_t* seq, float* logprobs, int32_t* phrase_num, int32_t* phrase_length,
                 int64_t* phrase_syn);
 
+/* sample_next_word (CaptionModel.py:383-431) for the following bofi_decode calls on this handle:
+ *   method 0  greedy: first maximal index (default)
+ *   method 1  sample_method='sample': Categorical(logits = logprobs / temperature, NaN -> -10), drawn as a Gumbel-max
+ *             with the library's counter-based random stream seeded by `seed` (same distribution as the reference,
+ *             not torch's stream).  This is the sampling half of self-critical training (loss_wrapper.py:194-209).
+ * gumbel / top-k / nucleus variants (:391-421) are not built. */
+int bofi_set_sampling(bofi_handle_t h, int32_t method, float temperature, uint32_t seed);
+
 /* AttModel._sample (AttModel.py:307-334, :419-437) end to end with HOST buffers: H2D of att_feats /
  * att_len, encode, decode, D2H of the results, then a stream synchronise.  host pointers may be
  * pageable or pinned; logprobs may be NULL. */

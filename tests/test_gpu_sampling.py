@@ -1,0 +1,106 @@
+"""sample_method='sample' (the sampling half of self-critical training, loss_wrapper.py:194-209) on the device:
+Gumbel-max draws inside the vocab epilogue.  The random stream is the library's own, so the checks are distributional."""
+import numpy as np
+import pytest
+import torch
+
+from boficap_b200 import synth
+from boficap_b200.layout import BofiConfig
+
+pytestmark = pytest.mark.gpu
+
+
+def build(calib="s_real"):
+    from boficap_b200.captioning import models
+    cfg = BofiConfig()
+    infos = synth.make_infos(cfg)
+    opt = infos["opt"]
+    opt.vocab = infos["vocab"]
+    model = models.setup(opt)
+    model.load_state_dict(synth.synth_state_dict(cfg, 0, calib))
+    return model.cuda().eval(), cfg
+
+
+def usable_inputs(model, B, sample_n=1):
+    """A synthetic batch whose LAST row predicts at least one phrase: otherwise the reference's stale fill window
+    (TransformerModel.py:1871-1873) turns every log-prob of the batch into NaN."""
+    for seed in range(7, 40):
+        fc, att, _ = synth.synth_inputs(B, 36, seed=seed)
+        fc, att = fc.cuda(), att.cuda()
+        out = model(fc, att, None, opt={"sample_method": "greedy", "train_mode": "NAIC", "sample_n": sample_n}, mode="sample")
+        if not bool(out[1].isnan().any()) and int(out[3].sum(1).min()) >= 0 and int(out[3][-1].sum()) > 0:
+            return fc, att
+    raise AssertionError("no usable synthetic batch")
+
+
+def test_naic_multinomial_sampling():
+    model, cfg = build()
+    fc, att = usable_inputs(model, 8, 2)
+    greedy = model(fc, att, None, opt={"sample_method": "greedy", "train_mode": "NAIC", "sample_n": 2}, mode="sample")
+    kw = {"sample_method": "sample", "train_mode": "NAIC", "sample_n": 2, "temperature": 1.0}
+    torch.manual_seed(5)
+    s1 = model(fc, att, None, opt=kw, mode="sample")
+    torch.manual_seed(5)
+    s2 = model(fc, att, None, opt=kw, mode="sample")
+    s3 = model(fc, att, None, opt=kw, mode="sample")
+    assert s1[0].shape == (16, cfg.seq_length)
+    # boxes and log-probs do not depend on how the words are drawn; the draw is reproducible under torch.manual_seed
+    for i in (2, 3, 4):
+        assert torch.equal(s1[i], greedy[i])
+    torch.testing.assert_close(s1[1], greedy[1], rtol=0, atol=0, equal_nan=True)
+    assert torch.equal(s1[0], s2[0]) and not torch.equal(s1[0], s3[0])
+    total = s1[3].sum(1)
+    ar = torch.arange(cfg.seq_length, device=total.device)[None, :]
+    assert (s1[0][ar >= total[:, None]] == 0).all(), "tail padding"
+    live = ar < total[:, None]
+    assert (s1[0][live] != greedy[0][live]).float().mean() > 0.5       # near-uniform random-weight distributions
+    assert int(s1[0].max()) < cfg.tgt_vocab and int(s1[0].min()) >= 0
+    # the two sample_n copies of an image share boxes but draw different words
+    j = 2 * int((total[0::2] >= 3).nonzero()[0])                       # an image with a caption of >= 3 words
+    assert torch.equal(s1[3][j], s1[3][j + 1]) and not torch.equal(s1[0][j], s1[0][j + 1])
+    # low temperature -> the draw collapses onto the greedy argmax
+    cold = model(fc, att, None, opt=dict(kw, temperature=0.002), mode="sample")
+    assert (cold[0][live] == greedy[0][live]).float().mean() > 0.97
+
+
+def test_sampling_frequencies_follow_the_softmax():
+    """Empirical frequency of the most likely word of a slot over many seeds vs softmax(logp / T)."""
+    model, cfg = build()
+    fc, att = usable_inputs(model, 4)
+    T = 0.02
+    kw = {"sample_method": "sample", "train_mode": "NAIC", "temperature": T}
+    greedy = model(fc, att, None, opt={"sample_method": "greedy", "train_mode": "NAIC"}, mode="sample")
+    logp, total = greedy[1], greedy[3].sum(1)
+    live = torch.arange(cfg.seq_length, device=total.device)[None, :] < total[:, None]
+    p_top = torch.softmax(logp.double() / T, dim=2).max(2).values[live]          # expected hit rate per live slot
+    hits, draws = torch.zeros_like(p_top), 300
+    torch.manual_seed(0)
+    for _ in range(draws):
+        s = model(fc, att, None, opt=kw, mode="sample")[0]
+        hits += (s[live] == greedy[0][live]).double()
+    freq = hits / draws
+    sigma = torch.sqrt(p_top * (1 - p_top) / draws) + 1e-3
+    z = ((freq - p_top).abs() / sigma)
+    assert float(z.max()) < 5.0, (float(z.max()), freq.tolist()[:5], p_top.tolist()[:5])
+    assert 0.05 < float(p_top.mean()) < 0.999          # the test is not vacuous
+
+
+def test_saic_multinomial_sampling():
+    model, cfg = build("s_cap")
+    fc, att, _ = synth.synth_inputs(6, 36, seed=7)
+    fc, att = fc.cuda(), att.cuda()
+    kw = {"sample_method": "sample", "train_mode": "SAIC", "sample_n": 2, "temperature": 1.0}
+    torch.manual_seed(3)
+    a = model(fc, att, None, opt=kw, mode="sample")
+    torch.manual_seed(3)
+    b = model(fc, att, None, opt=kw, mode="sample")
+    c = model(fc, att, None, opt=kw, mode="sample")
+    assert torch.equal(a[0], b[0]) and not torch.equal(a[0], c[0])
+    assert a[0].shape == (12, cfg.seq_length) and int(a[0].max()) < cfg.tgt_vocab
+    total = a[3].sum(1)
+    live = torch.arange(cfg.seq_length, device=total.device)[None, :] < total[:, None]
+    assert bool(live.any())
+    # committed slots carry their log-prob row (sums to 1 in probability), the others stay zero (TransformerModel.py:1883,1972)
+    psum = a[1].exp().sum(2)
+    assert torch.allclose(psum[live], torch.ones_like(psum[live]), atol=1e-3)
+    assert (a[1][~live] == 0).all()
