@@ -43,6 +43,7 @@ _SIGNATURES = {
     "bofi_decode": (C.c_int, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
     "bofi_sample_host": (C.c_int, [_P, _P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P]),
     "bofi_sample_host_async": (C.c_int, [_P, _P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P]),
+    "bofi_set_decode_stats": (C.c_int, [_P, _P, _P]),
     "bofi_set_sampling": (C.c_int, [_P, _I, C.c_float, C.c_uint32]),
     "bofi_get_decode_info": (C.c_int, [_P, _P, C.POINTER(DecodeInfoC)]),
     "bofi_set_profiling": (C.c_int, [_P, _I]),

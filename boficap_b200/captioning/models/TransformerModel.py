@@ -209,7 +209,18 @@ class TransformerModel(nn.Module):
         att_len = att_masks.data.long().sum(1).to(torch.int32) if att_masks is not None else None
         return eng.train_step_xe(att_feats.float(), att_len, batch)
 
-    def _sample(self, fc_feats, att_feats, att_masks=None, opt={}):
+    def sample_stats(self, fc_feats, att_feats, att_masks=None, opt={}):
+        """`_sample` for evaluation loops that only need captions, entropy and perplexity (eval_utils.py:176-184): the
+        [B, L, V] log-prob tensor is never materialised, the two statistics come out of the vocab epilogue.
+        Returns (seq, entropy [B], perplexity [B], phrase_num, phrase_length, phrase_syn, elapsed)."""
+        rows = att_feats.shape[0] * int(opt.get("sample_n", 1))
+        ent = torch.empty(rows, self.seq_length, device=att_feats.device)
+        lp = torch.empty(rows, self.seq_length, device=att_feats.device)
+        seq, _, pnum, plen, psyn, dt = self._sample(fc_feats, att_feats, att_masks, dict(opt, output_logsoftmax=1), _stats=(ent, lp))
+        denom = (seq > 3).to(ent.dtype).sum(1) + 1          # VOCAB_LOWER = 3 (eval_utils.py:144)
+        return seq, ent.sum(1) / denom, -lp.sum(1) / denom, pnum, plen, psyn, dt
+
+    def _sample(self, fc_feats, att_feats, att_masks=None, opt={}, _stats=None):
         sample_method = opt.get("sample_method", "greedy")
         beam_size = opt.get("beam_size", 1)
         temperature = opt.get("temperature", 1.0)
@@ -239,7 +250,10 @@ class TransformerModel(nn.Module):
         eng.encode(att_feats.float(), att_len)
         torch.cuda.synchronize(att_feats.device)
         start = time.time()
-        seq, logp, pnum, plen, psyn = eng.decode(train_mode, sample_n, output_logsoftmax, True)
+        if _stats is not None:
+            eng.set_decode_stats(*_stats)
+        seq, logp, pnum, plen, psyn = eng.decode(train_mode, sample_n, output_logsoftmax, _stats is None)
+        eng.set_decode_stats(None, None)
         eng.set_sampling("greedy")
         torch.cuda.synchronize(att_feats.device)
         return seq, logp, pnum, plen, psyn, time.time() - start

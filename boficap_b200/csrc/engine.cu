@@ -154,6 +154,7 @@ struct bofi_engine {
   unsigned long long bound_key[6] = {0, 0, 0, 0, 0, 0};
   int bound_launches = 0;
   int bound_eager_runs = 0;
+  float *stat_entropy = nullptr, *stat_logp = nullptr;   // bofi_set_decode_stats: optional [rows, L] outputs of the next decodes
   Sampler sampler;                       // bofi_set_sampling: greedy (default) or multinomial for the next decodes
   unsigned sample_calls = 0;
   struct TrainStateHolder* train = nullptr;   // XE-training tape (train.inl), created on first use
@@ -784,7 +785,7 @@ static int decode_naic(bofi_engine* e, cudaStream_t s, int sn, int output_logsof
   {
     ProfScope prof(e, s, PC_VOCAB, 0.0, 0.0);
     launch_k(vocab_epilogue_kernel, rows * L, kVocabThreads, 0, s, e->logits.as<float>(), e->Vpad, e->V, logprobs, seq, e->st.last, -1, L,
-             output_logsoftmax, nullptr, e->sampler);
+             output_logsoftmax, nullptr, e->sampler, e->stat_entropy, e->stat_logp);
   }
   CU_TRY(cudaGetLastError());
   {
@@ -822,6 +823,10 @@ static int decode_saic(bofi_engine* e, cudaStream_t s, int sn, int output_logsof
   }
   for (int l = 0; l < c.n_dec; ++l) RC_TRY(project_memory_kv<T>(e, s, e->dec[l].ca.kv, e->kv[nb_layers + l]));
   if (logprobs) CU_TRY(cudaMemsetAsync(logprobs, 0, (size_t)rows * L * e->V * sizeof(float), s));   // seq_logprobs = zeros (:1883)
+  if (e->stat_entropy) {
+    CU_TRY(cudaMemsetAsync(e->stat_entropy, 0, (size_t)rows * L * sizeof(float), s));
+    CU_TRY(cudaMemsetAsync(e->stat_logp, 0, (size_t)rows * L * sizeof(float), s));
+  }
   LAUNCH_OTHER((launch_k(init_state_kernel, ceil_div(rows, 128), 128, 0, s, e->st, rows, Lb, L, c.len_idx, c.bos_idx, 1)));
   const int* live = e->st.counters + 4;
   float* x = e->x.as<float>();
@@ -845,10 +850,10 @@ static int decode_saic(bofi_engine* e, cudaStream_t s, int sn, int output_logsof
                e->sa_lse.as<float>(), e->st, sp);
     }
     CU_TRY(cudaGetLastError());
-    if (logprobs) {
+    if (logprobs || e->stat_entropy) {
       ProfScope prof(e, s, PC_VOCAB, 0.0, 0.0);
       launch_k(saic_write_logp_kernel, rows * L, 256, 0, s, e->logits.as<float>(), e->Vpad, e->V, e->sa_mx.as<float>(), e->sa_lse.as<float>(),
-                                                     logprobs, e->st, L, output_logsoftmax);
+               logprobs, e->st, L, output_logsoftmax, (const int*)e->tok.as<int>(), e->stat_entropy, e->stat_logp);
     }
     CU_TRY(cudaGetLastError());
     LAUNCH_OTHER((launch_k(saic_advance_kernel, ceil_div(rows, 128), 128, 0, s, e->tok.as<int>(), e->st, rows, Lb, L, i)));
@@ -1051,6 +1056,14 @@ int bofi_sample_host(bofi_handle_t e, void* stream, int32_t mode, int32_t sn, in
   RC_TRY(bofi_sample_host_async(e, stream, mode, sn, output_logsoftmax, att_feats, att_len, B, R, seq, logprobs, phrase_num,
                                 phrase_length, phrase_syn));
   CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return BOFI_OK;
+}
+
+int bofi_set_decode_stats(bofi_handle_t e, float* slot_entropy, float* slot_logp) {
+  if (!e) return fail(BOFI_ERR_INVALID, "null handle");
+  if ((slot_entropy == nullptr) != (slot_logp == nullptr)) return fail(BOFI_ERR_INVALID, "pass both statistics buffers or neither");
+  e->stat_entropy = slot_entropy;
+  e->stat_logp = slot_logp;
   return BOFI_OK;
 }
 

@@ -554,7 +554,8 @@ constexpr int kVocabVec = 5;    // float4 per thread: 512 threads x 5 x 4 = 1024
 __global__ void __launch_bounds__(kVocabThreads, 3)
 vocab_epilogue_kernel(const float* __restrict__ logits, int ldl, int V, float* __restrict__ logp_out,
                       long long* __restrict__ seq_out, const int* __restrict__ total_len, int total_off, int L,
-                      int do_logsoftmax, int* __restrict__ tok_out_i32, Sampler sp) {
+                      int do_logsoftmax, int* __restrict__ tok_out_i32, Sampler sp, float* __restrict__ slot_entropy,
+                      float* __restrict__ slot_logp) {
   pdl_enter();
   // The whole row lives in registers: logits are read from HBM exactly once (128-bit loads, all independent),
   // max / argmax / sum-exp are block reductions, and the log-probs are written once.
@@ -615,10 +616,9 @@ vocab_epilogue_kernel(const float* __restrict__ logits, int ldl, int V, float* _
     for (int w = 1; w < kVocabThreads / 32; ++w) sm = better(sm, s_am[w]);
     picked = sm.i;
   }
-  if (logp_out) {
-    float* o = logp_out + (size_t)row * V;
-    float lse = 0.f;
-    if (do_logsoftmax) {
+  float lse = 0.f;
+  if ((logp_out && do_logsoftmax) || slot_entropy) {
+    {
       float s = 0.f;
 #pragma unroll
       for (int i = 0; i < kVocabVec; ++i) {
@@ -636,6 +636,36 @@ vocab_epilogue_kernel(const float* __restrict__ logits, int ldl, int V, float* _
       for (int w = 0; w < kVocabThreads / 32; ++w) tot += s_sum[w];
       lse = logf(tot);
     }
+  }
+  if (slot_entropy) {
+    // eval_split post-processing (captioning/utils/eval_utils.py:183-184) without the [B, L, V] tensor:
+    //   slot_entropy = -sum_v p_v log p_v ,  slot_logp = log p at the token written to seq
+    float h = 0.f;
+#pragma unroll
+    for (int i = 0; i < kVocabVec; ++i) {
+      const int c = (tid + i * kVocabThreads) * 4;
+      const float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (c + q < V) { const float lp = (e[q] - mx) - lse; h -= expf(lp) * lp; }
+    }
+    h = warp_sum(h);
+    __syncthreads();
+    if (lane == 0) s_sum[warp] = h;
+    __syncthreads();
+    if (tid == 0) {
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < kVocabThreads / 32; ++w) tot += s_sum[w];
+      int tok = picked;
+      if (total_len && t >= total_len[b] + total_off) tok = 0;
+      slot_entropy[row] = tot;
+      slot_logp[row] = (logits[(size_t)row * ldl + tok] - mx) - lse;
+    }
+    __syncthreads();
+  }
+  if (logp_out) {
+    float* o = logp_out + (size_t)row * V;
     // rows of the caller's [rows, L, V] tensor are only 4-byte aligned (V = 9491): stage through shared memory so
     // that each warp store covers 128 contiguous bytes
     __shared__ float stage[kVocabThreads * 4];
@@ -761,7 +791,8 @@ vocab_stats_kernel(const float* __restrict__ logits, int ldl, int V, int* __rest
 // ever written; the caller's tensor is zero-filled once per decode.
 __global__ void __launch_bounds__(256)
 saic_write_logp_kernel(const float* __restrict__ logits, int ldl, int V, const float* __restrict__ mx, const float* __restrict__ lse,
-                       float* __restrict__ logp_out, DecodeState st, int L, int do_logsoftmax) {
+                       float* __restrict__ logp_out, DecodeState st, int L, int do_logsoftmax, const int* __restrict__ tok,
+                       float* __restrict__ slot_entropy, float* __restrict__ slot_logp) {
   pdl_enter();
   if (st.counters[4] == 0 || st.counters[5] != 0) return;
   const int row = blockIdx.x, b = row / L, t = row - b * L;
@@ -770,10 +801,28 @@ saic_write_logp_kernel(const float* __restrict__ logits, int ldl, int V, const f
   const float* z = logits + (size_t)row * ldl;
   float* o = logp_out + (size_t)row * V;
   const float m = mx[row], l = lse[row];
-  if (do_logsoftmax) {
-    for (int c = threadIdx.x; c < V; c += 256) o[c] = (z[c] - m) - l;
-  } else {
-    for (int c = threadIdx.x; c < V; c += 256) o[c] = z[c];
+  if (logp_out) {
+    if (do_logsoftmax) {
+      for (int c = threadIdx.x; c < V; c += 256) o[c] = (z[c] - m) - l;
+    } else {
+      for (int c = threadIdx.x; c < V; c += 256) o[c] = z[c];
+    }
+  }
+  if (slot_entropy) {
+    __shared__ float s_h[8];
+    float h = 0.f;
+    for (int c = threadIdx.x; c < V; c += 256) { const float lp = (z[c] - m) - l; h -= expf(lp) * lp; }
+    h = warp_sum(h);
+    if ((threadIdx.x & 31) == 0) s_h[threadIdx.x >> 5] = h;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) tot += s_h[w];
+      // the slot this row's pick is committed to: seq[:, 1:-1] column t (TransformerModel.py:1968-1972)
+      slot_entropy[row] = tot;
+      slot_logp[row] = (z[tok[row]] - m) - l;
+    }
   }
 }
 

@@ -117,6 +117,10 @@ class BofiEngine:
                 B, R, _ptr(out["seq"]), _ptr(out.get("logp")), _ptr(out["pnum"]), _ptr(out["plen"]), _ptr(out["psyn"])))
         return out
 
+    def set_decode_stats(self, slot_entropy=None, slot_logp=None):
+        self._stats_keep = (slot_entropy, slot_logp)
+        _lib.check(self.lib.bofi_set_decode_stats(self.handle, _ptr(slot_entropy), _ptr(slot_logp)))
+
     def set_sampling(self, method="greedy", temperature=1.0, seed=0):
         _lib.check(self.lib.bofi_set_sampling(self.handle, 0 if method == "greedy" else 1, float(temperature), int(seed) & 0xFFFFFFFF))
 

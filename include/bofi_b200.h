@@ -103,6 +103,14 @@ int bofi_decode(bofi_handle_t h, void* stream, int32_t mode, int32_t sample_n, i
                 int64_t* seq, float* logprobs, int32_t* phrase_num, int32_t* phrase_length,
                 int64_t* phrase_syn);
 
+/* eval_split's entropy / perplexity (captioning/utils/eval_utils.py:183-184) without materialising seq_logprob:
+ * when set (dev f32 [rows, L] each; NULL, NULL switches it off), the following bofi_decode calls also write, per slot,
+ *   slot_entropy = -sum_v p_v log p_v   and   slot_logp = log p of the token written to seq
+ * (zero for slots SAIC never commits, as the reference's zero-initialised seq_logprobs give).  Needs output_logsoftmax = 1.
+ *   entropy[b]    =  sum_t slot_entropy[b,t] / (count(seq[b] > 3) + 1)
+ *   perplexity[b] = -sum_t slot_logp[b,t]    / (count(seq[b] > 3) + 1)          (boficap_b200/captioning/models: sample_stats) */
+int bofi_set_decode_stats(bofi_handle_t h, float* slot_entropy, float* slot_logp);
+
 /* sample_next_word (CaptionModel.py:383-431) for the following bofi_decode calls on this handle:
  *   method 0  greedy: first maximal index (default)
  *   method 1  sample_method='sample': Categorical(logits = logprobs / temperature, NaN -> -10), drawn as a Gumbel-max

@@ -104,3 +104,21 @@ def test_saic_multinomial_sampling():
     psum = a[1].exp().sum(2)
     assert torch.allclose(psum[live], torch.ones_like(psum[live]), atol=1e-3)
     assert (a[1][~live] == 0).all()
+
+
+@pytest.mark.parametrize("mode,calib", [("NAIC", "s_real"), ("SAIC", "s_cap")])
+def test_sample_stats_equal_eval_utils_formulas(mode, calib):
+    """entropy / perplexity of eval_split (eval_utils.py:183-184) from the vocab epilogue == the reference formulas on the
+    materialised log-prob tensor."""
+    import torch.nn.functional as F
+    model, cfg = build(calib)
+    fc, att = usable_inputs(model, 8)
+    kw = {"sample_method": "greedy", "train_mode": mode}
+    seq, logp, pnum, plen, psyn, _ = model(fc, att, None, opt=kw, mode="sample")
+    denom = (seq > 3).to(logp).sum(1) + 1
+    entropy = -(F.softmax(logp, dim=2) * logp).sum(2).sum(1) / denom
+    perplexity = -logp.gather(2, seq.unsqueeze(2)).squeeze(2).sum(1) / denom
+    seq2, ent2, ppl2, pnum2, plen2, psyn2, _ = model.sample_stats(fc, att, None, opt=kw)
+    assert torch.equal(seq, seq2) and torch.equal(plen, plen2)
+    torch.testing.assert_close(ent2, entropy, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(ppl2, perplexity, rtol=1e-4, atol=1e-4)
