@@ -176,19 +176,22 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 attention_row_kernel(const T* __restrict__ Q, int ldq, const T* __restrict__ K, const T* __restrict__ V, int ldkv,
                      T* __restrict__ O, int ldo, int Tk, const int* __restrict__ vis, int vis_div, int kv_div, float scale,
-                     const int* live_rows, const int* __restrict__ finished, Drop drop) {
+                     const int* live_rows, const int* __restrict__ finished, Drop drop, const int* __restrict__ rowmap, int rowmap_div,
+                     const int* rows_dev) {
   pdl_enter();
   if (step_is_dead(live_rows)) return;
   if (finished && finished[blockIdx.x]) return;
+  if (rows_dev && (int)blockIdx.x >= *rows_dev) return;
   __shared__ float qs[8][kHeadDim];
   __shared__ float ps[8][kMaxKeys];
   const int b = blockIdx.x, head = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t kvrow0 = (size_t)(b / kv_div) * Tk;
+  const int bs = rowmap ? rowmap[b] / rowmap_div : b;      // sequence the (compact) query row belongs to
+  const size_t kvrow0 = (size_t)(bs / kv_div) * Tk;
   const T* qg = Q + (size_t)b * ldq + head * kHeadDim;
   qs[head][lane] = to_float<T>(qg[lane]);
   qs[head][lane + 32] = to_float<T>(qg[lane + 32]);
   __syncwarp();
-  int nvis = vis ? vis[b / vis_div] : Tk;
+  int nvis = vis ? vis[bs / vis_div] : Tk;
   nvis = min(nvis, Tk);
   float sc[kMaxKeys / 32];
   float mx = -INFINITY;
@@ -263,16 +266,19 @@ constexpr int kRowsPerCta = 4;
 __global__ void __launch_bounds__(kRowsPerCta * 256)
 attention_row_bf16_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restrict__ K, const bf16* __restrict__ V, int ldkv,
                           bf16* __restrict__ O, int ldo, int nb, int Tk, const int* __restrict__ vis, int vis_div, int kv_div,
-                          float scale, const int* live_rows, const int* __restrict__ finished, Drop drop) {
+                          float scale, const int* live_rows, const int* __restrict__ finished, Drop drop, const int* __restrict__ rowmap,
+                          int rowmap_div, const int* rows_dev) {
   pdl_enter();
   if (step_is_dead(live_rows)) return;
   __shared__ float ps[kRowsPerCta * 8][kMaxKeys];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * kRowsPerCta + (warp >> 3), head = warp & 7;
-  if (b >= nb) return;
-  if (finished && finished[b]) return;     // bounding step: finished rows are ignored by the head
-  const size_t kvrow0 = (size_t)(b / kv_div) * Tk;
-  int nvis = vis ? vis[b / vis_div] : Tk;
+  const int head = warp & 7;
+  if (rows_dev) nb = min(nb, *rows_dev);   // compacted step: the valid-row count lives on the device
+  for (int b = blockIdx.x * kRowsPerCta + (warp >> 3); b < nb; b += gridDim.x * kRowsPerCta) {
+  if (finished && finished[b]) continue;   // bounding step: finished rows are ignored by the head
+  const int bs = rowmap ? rowmap[b] / rowmap_div : b;      // sequence the (compact) query row belongs to
+  const size_t kvrow0 = (size_t)(bs / kv_div) * Tk;
+  int nvis = vis ? vis[bs / vis_div] : Tk;
   nvis = min(nvis, Tk);
   // ---- scores ----
   const int sub = lane & 3, kslot = lane >> 2;
@@ -377,6 +383,8 @@ attention_row_bf16_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __res
     o.z = pack2_bf16(acc[4], acc[5]);
     o.w = pack2_bf16(acc[6], acc[7]);
     *reinterpret_cast<uint4*>(O + (size_t)b * ldo + head * kHeadDim + g * 8) = o;
+  }
+  __syncwarp();                            // ps[warp] is rewritten by the next row of this warp
   }
 }
 

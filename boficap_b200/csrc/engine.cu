@@ -128,6 +128,8 @@ struct bofi_engine {
   const bf16* head1_w16 = nullptr;
   DevBuf bound_in, fill_in;            // (id, position) input tables
   DevBuf sa_mx, sa_lse;                // SAIC: per (row, slot) max / log-sum-exp of the step's logits
+  DevBuf sa_cidx, sa_cache;            // incremental SAIC: compact (row, slot) list, per-layer K|V caches [n_dec][rows*L][1024]
+  bool saic_full = false;              // BOFI_SAIC=full: recompute every slot at every step (the reference formulation)
   DevBuf head1t;                       // [512][200] = [Length_classifier1 ; Syntactic_classifier1]^T
   DevBuf tab_y, tab_qkv;               // N_len == 1: LN + QKV of every (syn, position) bounding input row
   bool bound_fast = false;             // [LEN]-row-only bounding step (NAIC, N_len == 1)
@@ -150,10 +152,12 @@ struct bofi_engine {
   bool use_graph = true;
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  cudaGraphExec_t bound_exec = nullptr;
-  unsigned long long bound_key[6] = {0, 0, 0, 0, 0, 0};
-  int bound_launches = 0;
-  int bound_eager_runs = 0;
+  struct GraphSlot {                   // one captured launch sequence (NAIC bounding loop / SAIC step loop)
+    cudaGraphExec_t exec = nullptr;
+    unsigned long long key[12] = {0};
+    int launches = 0, eager_runs = 0;
+  } g_bound, g_saic;
+  const int* rows_dev = nullptr;         // when set, linear() / layernorm() only process the first *rows_dev rows (SAIC compaction)
   float *stat_entropy = nullptr, *stat_logp = nullptr;   // bofi_set_decode_stats: optional [rows, L] outputs of the next decodes
   Sampler sampler;                       // bofi_set_sampling: greedy (default) or multinomial for the next decodes
   unsigned sample_calls = 0;
@@ -277,11 +281,11 @@ static int linear(bofi_engine* e, cudaStream_t s, const T* A, int lda, const Lin
                  M, l.N, l.K);
   if constexpr (std::is_same<T, bf16>::value) {
     if (e->use_tc)
-      err = tc::gemm_tc<TOut>(s, A, lda, l.w16, l.K, l.b, resid, ldr, out, ldc, M, l.N, l.K, relu, live);
+      err = tc::gemm_tc<TOut>(s, A, lda, l.w16, l.K, l.b, resid, ldr, out, ldc, M, l.N, l.K, relu, live, e->rows_dev);
     else
-      err = gemm_simt<bf16, TOut>(s, A, lda, l.w16, l.K, l.b, resid, ldr, out, ldc, M, l.N, l.K, relu, live);
+      err = gemm_simt<bf16, TOut>(s, A, lda, l.w16, l.K, l.b, resid, ldr, out, ldc, M, l.N, l.K, relu, live, e->rows_dev);
   } else {
-    err = gemm_simt<float, TOut>(s, A, lda, l.w32, l.K, l.b, resid, ldr, out, ldc, M, l.N, l.K, relu, live);
+    err = gemm_simt<float, TOut>(s, A, lda, l.w32, l.K, l.b, resid, ldr, out, ldc, M, l.N, l.K, relu, live, e->rows_dev);
   }
   if (err != cudaSuccess) return fail(BOFI_ERR_CUDA, "gemm M=%d N=%d K=%d: %s", M, l.N, l.K, cudaGetErrorString(err));
   return BOFI_OK;
@@ -292,7 +296,8 @@ static int layernorm(bofi_engine* e, cudaStream_t s, const float* x, size_t in_s
                      size_t out_stride, int rows, float* f32_copy, const int* live) {
   if (rows <= 0) return BOFI_OK;
   ProfScope prof(e, s, PC_LAYERNORM, 8.0 * rows * kD, (double)rows * kD * (4 + sizeof(TOut) + (f32_copy ? 4 : 0)), rows);
-  launch_k(layernorm_kernel<TOut>, ceil_div(rows, 8), 256, 0, s, x, in_stride, n.a, n.b, out, out_stride, rows, f32_copy, live);
+  const int ln_grid = e->rows_dev ? std::min(ceil_div(rows, 8), 148 * 8) : ceil_div(rows, 8);
+  launch_k(layernorm_kernel<TOut>, ln_grid, 256, 0, s, x, in_stride, n.a, n.b, out, out_stride, rows, f32_copy, live, e->rows_dev);
   CU_TRY(cudaGetLastError());
   return BOFI_OK;
 }
@@ -314,7 +319,7 @@ static cudaError_t launch_attention_mma(cudaStream_t s, dim3 grid, size_t smem, 
 template <typename T>
 static int attention(bofi_engine* e, cudaStream_t s, const T* Q, int ldq, const T* K, const T* V, int ldkv, T* O, int ldo,
                      int nb, int Tq, int Tk, const int* vis, int vis_bs, int vis_qs, int vis_div, int kv_div,
-                     const int* live, const int* finished = nullptr, Drop drop = Drop()) {
+                     const int* live, const int* finished = nullptr, Drop drop = Drop(), const int* rowmap = nullptr, int rowmap_div = 1) {
   if (nb <= 0) return BOFI_OK;
   if (Tk > kMaxKeys || Tq > kMaxKeys) return fail(BOFI_ERR_INVALID, "attention over %d x %d (max %d)", Tq, Tk, kMaxKeys);
   const float scale = 1.0f / sqrtf((float)kHeadDim);
@@ -322,10 +327,10 @@ static int attention(bofi_engine* e, cudaStream_t s, const T* Q, int ldq, const 
                  nb, Tq, Tk);
   if (Tq == 1 && !e->attn_simt_only) {
     if constexpr (std::is_same<T, bf16>::value)
-      launch_k(attention_row_bf16_kernel, ceil_div(nb, kRowsPerCta), kRowsPerCta * 256, 0, s, Q, ldq, K, V, ldkv, O, ldo, nb, Tk, vis, vis_div,
-               kv_div, scale, live, finished, drop);
+      launch_k(attention_row_bf16_kernel, e->rows_dev ? std::min(ceil_div(nb, kRowsPerCta), 148 * 2) : ceil_div(nb, kRowsPerCta), kRowsPerCta * 256, 0, s, Q, ldq, K, V, ldkv, O, ldo, nb, Tk, vis, vis_div,
+               kv_div, scale, live, finished, drop, rowmap, rowmap_div, e->rows_dev);
     else
-      launch_k(attention_row_kernel<T>, nb, 256, 0, s, Q, ldq, K, V, ldkv, O, ldo, Tk, vis, vis_div, kv_div, scale, live, finished, drop);
+      launch_k(attention_row_kernel<T>, nb, 256, 0, s, Q, ldq, K, V, ldkv, O, ldo, Tk, vis, vis_div, kv_div, scale, live, finished, drop, rowmap, rowmap_div, e->rows_dev);
     CU_TRY(cudaGetLastError());
     return BOFI_OK;
   }
@@ -693,6 +698,55 @@ static int build_bound_tables(bofi_engine* e, cudaStream_t s) {
   return BOFI_OK;
 }
 
+// Runs `enqueue(stream)` -- a long sequence of small dependent launches on internal buffers whose control flow lives on the
+// device -- through a CUDA graph: the first call of a key runs eagerly (buffers grow, function attributes get set), the
+// second captures, later ones replay.  The key must cover everything baked into the launches (shapes, pointers, flags).
+template <typename F>
+static int run_graphed(bofi_engine* e, cudaStream_t s, bofi_engine::GraphSlot& g, const unsigned long long (&key)[12], F&& enqueue) {
+  const bool key_ok = memcmp(key, g.key, sizeof(key)) == 0;
+  if (!e->use_graph || e->profiling) return enqueue(s);
+  if (!e->aux_stream) {
+    CU_TRY(cudaStreamCreateWithFlags(&e->aux_stream, cudaStreamNonBlocking));
+    CU_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+  }
+  if (g.exec && key_ok) {
+    CU_TRY(cudaEventRecord(e->ev_fork, s));
+    CU_TRY(cudaStreamWaitEvent(e->aux_stream, e->ev_fork, 0));
+    CU_TRY(cudaGraphLaunch(g.exec, e->aux_stream));
+    CU_TRY(cudaEventRecord(e->ev_join, e->aux_stream));
+    CU_TRY(cudaStreamWaitEvent(s, e->ev_join, 0));
+    e->launches += g.launches;
+    return BOFI_OK;
+  }
+  if (!key_ok || g.eager_runs < 1) {
+    if (!key_ok) {
+      if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+      memcpy(g.key, key, sizeof(key));
+      g.eager_runs = 0;
+    }
+    RC_TRY(enqueue(s));
+    g.eager_runs++;
+    return BOFI_OK;
+  }
+  CU_TRY(cudaEventRecord(e->ev_fork, s));
+  CU_TRY(cudaStreamWaitEvent(e->aux_stream, e->ev_fork, 0));
+  const int before = e->launches;
+  cudaGraph_t graph = nullptr;
+  CU_TRY(cudaStreamBeginCapture(e->aux_stream, cudaStreamCaptureModeThreadLocal));
+  int rc = enqueue(e->aux_stream);
+  cudaError_t ce = cudaStreamEndCapture(e->aux_stream, &graph);
+  if (rc != BOFI_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+  if (ce != cudaSuccess) return fail(BOFI_ERR_CUDA, "graph capture: %s", cudaGetErrorString(ce));
+  g.launches = e->launches - before;
+  CU_TRY(cudaGraphInstantiate(&g.exec, graph, 0));
+  cudaGraphDestroy(graph);
+  CU_TRY(cudaGraphLaunch(g.exec, e->aux_stream));
+  CU_TRY(cudaEventRecord(e->ev_join, e->aux_stream));
+  CU_TRY(cudaStreamWaitEvent(s, e->ev_join, 0));
+  return BOFI_OK;
+}
+
 template <typename T>
 static int decode_naic(bofi_engine* e, cudaStream_t s, int sn, int output_logsoftmax, long long* seq, float* logprobs,
                        int* phrase_num, int* phrase_length, long long* phrase_syn) {
@@ -722,49 +776,9 @@ static int decode_naic(bofi_engine* e, cudaStream_t s, int sn, int output_logsof
     }
     return BOFI_OK;
   };
-  const unsigned long long key[6] = {(unsigned long long)rows, (unsigned long long)e->R, (unsigned long long)sn,
-                                     (unsigned long long)e->have_len, g_alloc_generation, (unsigned long long)e->bound_fast};
-  const bool key_ok = memcmp(key, e->bound_key, sizeof(key)) == 0;
-  if (!e->use_graph || e->profiling) {
-    RC_TRY(enqueue_bounding(s));
-  } else if (e->bound_exec && key_ok) {
-    CU_TRY(cudaEventRecord(e->ev_fork, s));
-    CU_TRY(cudaStreamWaitEvent(e->aux_stream, e->ev_fork, 0));
-    CU_TRY(cudaGraphLaunch(e->bound_exec, e->aux_stream));
-    CU_TRY(cudaEventRecord(e->ev_join, e->aux_stream));
-    CU_TRY(cudaStreamWaitEvent(s, e->ev_join, 0));
-    e->launches += e->bound_launches;
-  } else if (!key_ok || e->bound_eager_runs < 1) {
-    // first decode of a shape runs eagerly (buffers grow, function attributes get set); the next one captures
-    if (!key_ok) {
-      if (e->bound_exec) { cudaGraphExecDestroy(e->bound_exec); e->bound_exec = nullptr; }
-      memcpy(e->bound_key, key, sizeof(key));
-      e->bound_eager_runs = 0;
-    }
-    RC_TRY(enqueue_bounding(s));
-    e->bound_eager_runs++;
-  } else {
-    if (!e->aux_stream) {
-      CU_TRY(cudaStreamCreateWithFlags(&e->aux_stream, cudaStreamNonBlocking));
-      CU_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
-      CU_TRY(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
-    }
-    CU_TRY(cudaEventRecord(e->ev_fork, s));
-    CU_TRY(cudaStreamWaitEvent(e->aux_stream, e->ev_fork, 0));
-    const int before = e->launches;
-    cudaGraph_t graph = nullptr;
-    CU_TRY(cudaStreamBeginCapture(e->aux_stream, cudaStreamCaptureModeThreadLocal));
-    int rc = enqueue_bounding(e->aux_stream);
-    cudaError_t ce = cudaStreamEndCapture(e->aux_stream, &graph);
-    if (rc != BOFI_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
-    if (ce != cudaSuccess) return fail(BOFI_ERR_CUDA, "graph capture: %s", cudaGetErrorString(ce));
-    e->bound_launches = e->launches - before;
-    CU_TRY(cudaGraphInstantiate(&e->bound_exec, graph, 0));
-    cudaGraphDestroy(graph);
-    CU_TRY(cudaGraphLaunch(e->bound_exec, e->aux_stream));
-    CU_TRY(cudaEventRecord(e->ev_join, e->aux_stream));
-    CU_TRY(cudaStreamWaitEvent(s, e->ev_join, 0));
-  }
+  const unsigned long long key[12] = {(unsigned long long)rows, (unsigned long long)e->R, (unsigned long long)sn,
+                                      (unsigned long long)e->have_len, g_alloc_generation, (unsigned long long)e->bound_fast};
+  RC_TRY(run_graphed(e, s, e->g_bound, key, enqueue_bounding));
 
   // filling step (decode_NA, :570-587): all L slots of every row in parallel
   {
@@ -847,17 +861,126 @@ static int decode_saic(bofi_engine* e, cudaStream_t s, int sn, int output_logsof
       Sampler sp = e->sampler;             // a fresh noise field per phrase step
       sp.key = drop_hash(sp.key, (uint32_t)i);
       launch_k(vocab_stats_kernel, rows * L, 256, 0, s, e->logits.as<float>(), e->Vpad, e->V, e->tok.as<int>(), e->sa_mx.as<float>(),
-               e->sa_lse.as<float>(), e->st, sp);
+               e->sa_lse.as<float>(), e->st, sp, (const int*)nullptr);
     }
     CU_TRY(cudaGetLastError());
     if (logprobs || e->stat_entropy) {
       ProfScope prof(e, s, PC_VOCAB, 0.0, 0.0);
       launch_k(saic_write_logp_kernel, rows * L, 256, 0, s, e->logits.as<float>(), e->Vpad, e->V, e->sa_mx.as<float>(), e->sa_lse.as<float>(),
-               logprobs, e->st, L, output_logsoftmax, (const int*)e->tok.as<int>(), e->stat_entropy, e->stat_logp);
+               logprobs, e->st, L, output_logsoftmax, (const int*)e->tok.as<int>(), e->stat_entropy, e->stat_logp, (const int*)nullptr);
     }
     CU_TRY(cudaGetLastError());
     LAUNCH_OTHER((launch_k(saic_advance_kernel, ceil_div(rows, 128), 128, 0, s, e->tok.as<int>(), e->st, rows, Lb, L, i)));
   }
+  LAUNCH_OTHER((launch_k(export_seq_kernel, ceil_div(rows * L, 256), 256, 0, s, e->st, rows, Lb, L, seq)));
+  LAUNCH_OTHER((launch_k(export_boxes_kernel, ceil_div(rows * L, 256), 256, 0, s, e->st, rows, Lb, L, 1, phrase_num, phrase_length, phrase_syn)));
+  return BOFI_OK;
+}
+
+// core_SAIC with incremental filling (the default; BOFI_SAIC=full selects the reference formulation above).
+// The bounding step is the same; the decoder, vocab projection and pick of a step only run on the compact list of
+// slots of the phrase accepted in that step, against per-layer K/V caches of the earlier slots.  Bit-for-bit the same
+// values as decode_saic for every committed slot: a row's arithmetic does not depend on which other rows share its launch.
+template <typename T>
+static int decode_saic_incremental(bofi_engine* e, cudaStream_t s, int sn, int output_logsoftmax, long long* seq, float* logprobs,
+                                   int* phrase_num, int* phrase_length, long long* phrase_syn) {
+  const bofi_config_t& c = e->cfg;
+  const int rows = e->B * sn, Lb = e->Lb, L = e->L, slots = rows * L;
+  const int* mem_len = e->have_len ? e->attlen.as<int>() : nullptr;
+  const int nb_layers = std::max(1, c.n_len);
+  RC_TRY(e->sa_mx.reserve((size_t)slots * 4));
+  RC_TRY(e->sa_lse.reserve((size_t)slots * 4));
+  RC_TRY(e->sa_cidx.reserve((size_t)slots * 4));
+  RC_TRY(e->sa_cache.reserve((size_t)c.n_dec * slots * 2 * kD * sizeof(T)));
+  if (c.n_len == 0) {
+    RC_TRY(project_memory_kv<T>(e, s, e->lp0.ca.kv, e->kv[0]));
+  } else {
+    for (int l = 0; l < c.n_len; ++l) RC_TRY(project_memory_kv<T>(e, s, e->lp[l].ca.kv, e->kv[l]));
+  }
+  for (int l = 0; l < c.n_dec; ++l) RC_TRY(project_memory_kv<T>(e, s, e->dec[l].ca.kv, e->kv[nb_layers + l]));
+  if (logprobs) CU_TRY(cudaMemsetAsync(logprobs, 0, (size_t)slots * e->V * sizeof(float), s));   // seq_logprobs = zeros (:1883)
+  if (e->stat_entropy) {
+    CU_TRY(cudaMemsetAsync(e->stat_entropy, 0, (size_t)slots * sizeof(float), s));
+    CU_TRY(cudaMemsetAsync(e->stat_logp, 0, (size_t)slots * sizeof(float), s));
+  }
+  LAUNCH_OTHER((launch_k(init_state_kernel, ceil_div(rows, 128), 128, 0, s, e->st, rows, Lb, L, c.len_idx, c.bos_idx, 1)));
+  const int* live = e->st.counters + 4;
+  const int* mdev = e->st.counters + 6;
+  int* cidx = e->sa_cidx.as<int>();
+  float* x = e->x.as<float>();
+  T* y = e->y.as<T>();
+  T* qkv = e->qkv.as<T>();
+  T* ao = e->ao.as<T>();
+  T* q = e->q.as<T>();
+  T* ffh = e->ffh.as<T>();
+  const float sqrt_d = sqrtf((float)kD), scale = 1.0f / sqrtf((float)kHeadDim);
+  auto enqueue_steps = [&](cudaStream_t s) -> int {
+  for (int i = 1; i <= L; ++i) {
+    LAUNCH_OTHER((launch_k(saic_snapshot_kernel, 1, 1, 0, s, e->st)));
+    RC_TRY(bounding_step<T>(e, s, rows, sn, i, 1));
+    LAUNCH_OTHER((launch_k(saic_prepare_kernel, ceil_div(rows, 128), 128, 0, s, e->st, rows, Lb, L, i)));
+    LAUNCH_OTHER((launch_k(saic_compact_kernel, ceil_div(rows, 128), 128, 0, s, e->st, rows, L, i, cidx)));
+    LAUNCH_OTHER((launch_k(embed_compact_kernel, std::min(ceil_div(slots, 8), 148 * 4), 256, 0, s, W(e, "model.tgt_embed.lut.weight"), W(e, "model.syn_embed.lut.weight"),
+                           W(e, "model.pos_embed.pe"), e->st, Lb, L, (const int*)cidx, sqrt_d, x)));
+    e->rows_dev = mdev;
+    int rc = BOFI_OK;
+    for (int l = 0; l < c.n_dec && rc == BOFI_OK; ++l) {
+      const Layer& ly = e->dec[l];
+      T* cache = e->sa_cache.as<T>() + (size_t)l * slots * 2 * kD;
+      const T* kvmem = e->kv[nb_layers + l].as<T>();
+      auto layer = [&]() -> int {
+        RC_TRY(layernorm<T>(e, s, x, kD, ly.ln[0], y, kD, slots, nullptr, live));
+        RC_TRY((linear<T, T>(e, s, y, kD, ly.sa.qkv, nullptr, 0, qkv, 3 * kD, slots, 0, live)));
+        {
+          ProfScope prof(e, s, PC_OTHER, 0.0, 0.0);
+          launch_k(saic_scatter_kv_kernel<T>, std::min(ceil_div(slots, 8), 148 * 4), 256, 0, s, (const T*)qkv, (const int*)cidx, e->st, cache);
+        }
+        CU_TRY(cudaGetLastError());
+        {
+          ProfScope prof(e, s, PC_ATTENTION, 0.0, 0.0);
+          launch_k(saic_self_attn_kernel<T>, std::min(slots, 148 * 8), 256, 0, s, (const T*)qkv, (const T*)cache, (const int*)cidx, e->st, L, ao, scale);
+        }
+        CU_TRY(cudaGetLastError());
+        RC_TRY((linear<T, float>(e, s, ao, kD, ly.sa.o, x, kD, x, kD, slots, 0, live)));
+        RC_TRY(layernorm<T>(e, s, x, kD, ly.ln[1], y, kD, slots, nullptr, live));
+        RC_TRY((linear<T, T>(e, s, y, kD, ly.ca.q, nullptr, 0, q, kD, slots, 0, live)));
+        RC_TRY(attention<T>(e, s, q, kD, kvmem, kvmem + kD, 2 * kD, ao, kD, slots, 1, e->R, mem_len, 1, 0, sn, sn, live, nullptr, Drop(), cidx, L));
+        RC_TRY((linear<T, float>(e, s, ao, kD, ly.ca.o, x, kD, x, kD, slots, 0, live)));
+        RC_TRY(layernorm<T>(e, s, x, kD, ly.ln[2], y, kD, slots, nullptr, live));
+        RC_TRY((linear<T, T>(e, s, y, kD, ly.w1, nullptr, 0, ffh, c.d_ff, slots, 1, live)));
+        RC_TRY((linear<T, float>(e, s, ffh, c.d_ff, ly.w2, x, kD, x, kD, slots, 0, live)));
+        return BOFI_OK;
+      };
+      rc = layer();
+    }
+    if (rc == BOFI_OK) rc = layernorm<T>(e, s, x, kD, e->dec_norm, y, kD, slots, nullptr, live);
+    if (rc == BOFI_OK) rc = linear<T, float>(e, s, y, kD, e->generator, nullptr, 0, e->logits.as<float>(), e->Vpad, slots, 0, live);
+    e->rows_dev = nullptr;
+    RC_TRY(rc);
+    {
+      ProfScope prof(e, s, PC_VOCAB, 0.0, 0.0);
+      Sampler sp = e->sampler;
+      sp.key = drop_hash(sp.key, (uint32_t)i);
+      launch_k(vocab_stats_kernel, slots, 256, 0, s, e->logits.as<float>(), e->Vpad, e->V, e->tok.as<int>(), e->sa_mx.as<float>(),
+               e->sa_lse.as<float>(), e->st, sp, (const int*)cidx);
+    }
+    CU_TRY(cudaGetLastError());
+    if (logprobs || e->stat_entropy) {
+      ProfScope prof(e, s, PC_VOCAB, 0.0, 0.0);
+      launch_k(saic_write_logp_kernel, slots, 256, 0, s, e->logits.as<float>(), e->Vpad, e->V, e->sa_mx.as<float>(), e->sa_lse.as<float>(),
+               logprobs, e->st, L, output_logsoftmax, (const int*)e->tok.as<int>(), e->stat_entropy, e->stat_logp, (const int*)cidx);
+    }
+    CU_TRY(cudaGetLastError());
+    LAUNCH_OTHER((launch_k(saic_advance_kernel, ceil_div(rows, 128), 128, 0, s, e->tok.as<int>(), e->st, rows, Lb, L, i)));
+  }
+  return BOFI_OK;
+  };
+  // ~1900 small launches per decode: replayed as one graph (not while sampling: the noise key is a launch argument)
+  const unsigned long long key[12] = {(unsigned long long)rows, (unsigned long long)e->R, (unsigned long long)sn, (unsigned long long)e->have_len,
+                                      g_alloc_generation, (unsigned long long)(uintptr_t)logprobs, (unsigned long long)output_logsoftmax,
+                                      (unsigned long long)(uintptr_t)e->stat_entropy, (unsigned long long)(uintptr_t)e->stat_logp};
+  if (e->sampler.enabled) RC_TRY(enqueue_steps(s));
+  else RC_TRY(run_graphed(e, s, e->g_saic, key, enqueue_steps));
   LAUNCH_OTHER((launch_k(export_seq_kernel, ceil_div(rows * L, 256), 256, 0, s, e->st, rows, Lb, L, seq)));
   LAUNCH_OTHER((launch_k(export_boxes_kernel, ceil_div(rows * L, 256), 256, 0, s, e->st, rows, Lb, L, 1, phrase_num, phrase_length, phrase_syn)));
   return BOFI_OK;
@@ -922,6 +1045,8 @@ int bofi_create(const bofi_config_t* cfg, int device, bofi_handle_t* out) {
   e->use_graph = !(gg && strcmp(gg, "0") == 0);
   const char* gp = getenv("BOFI_PDL");
   if (gp) pdl_enabled() = strcmp(gp, "0") != 0;
+  const char* gs = getenv("BOFI_SAIC");
+  e->saic_full = (gs && strcmp(gs, "full") == 0);
   const char* ga = getenv("BOFI_ATTN");
   e->attn_simt_only = (ga && strcmp(ga, "simt") == 0);
   build_spec(e);
@@ -935,7 +1060,8 @@ int bofi_create(const bofi_config_t* cfg, int device, bofi_handle_t* out) {
 int bofi_destroy(bofi_handle_t e) {
   if (!e) return BOFI_OK;
   cudaSetDevice(e->device);
-  if (e->bound_exec) cudaGraphExecDestroy(e->bound_exec);
+  if (e->g_bound.exec) cudaGraphExecDestroy(e->g_bound.exec);
+  if (e->g_saic.exec) cudaGraphExecDestroy(e->g_saic.exec);
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
   if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
@@ -944,7 +1070,7 @@ int bofi_destroy(bofi_handle_t e) {
   e->flat16.release();
   for (DevBuf& b : e->kv) b.release();
   DevBuf* all[] = {&e->bound_in, &e->fill_in, &e->attT, &e->x, &e->y, &e->qkv, &e->ao, &e->q, &e->ffh, &e->memT, &e->attlen,
-                   &e->sa_mx, &e->sa_lse, &e->head1t, &e->tab_y, &e->tab_qkv, &e->hrow, &e->hid, &e->logits, &e->state_i32, &e->tok, &e->h_in, &e->h_len, &e->h_seq, &e->h_logp,
+                   &e->sa_mx, &e->sa_lse, &e->sa_cidx, &e->sa_cache, &e->head1t, &e->tab_y, &e->tab_qkv, &e->hrow, &e->hid, &e->logits, &e->state_i32, &e->tok, &e->h_in, &e->h_len, &e->h_seq, &e->h_logp,
                    &e->h_pnum, &e->h_plen, &e->h_psyn, &e->unit_a, &e->unit_w, &e->unit_o};
   for (DevBuf* b : all) b->release();
   delete e;
@@ -1015,6 +1141,9 @@ int bofi_decode(bofi_handle_t e, void* stream, int32_t mode, int32_t sn, int32_t
   CU_TRY(cudaSetDevice(e->device));
   cudaStream_t s = (cudaStream_t)stream;
   RC_TRY(reserve_decode(e, e->B, e->R, sn));
+  if (mode == BOFI_MODE_SAIC && !e->saic_full && !e->attn_simt_only)
+    return e->bf16_mode ? decode_saic_incremental<bf16>(e, s, sn, output_logsoftmax, (long long*)seq, logprobs, phrase_num, phrase_length, (long long*)phrase_syn)
+                        : decode_saic_incremental<float>(e, s, sn, output_logsoftmax, (long long*)seq, logprobs, phrase_num, phrase_length, (long long*)phrase_syn);
   if (mode == BOFI_MODE_SAIC)
     return e->bf16_mode ? decode_saic<bf16>(e, s, sn, output_logsoftmax, (long long*)seq, logprobs, phrase_num, phrase_length, (long long*)phrase_syn)
                         : decode_saic<float>(e, s, sn, output_logsoftmax, (long long*)seq, logprobs, phrase_num, phrase_length, (long long*)phrase_syn);

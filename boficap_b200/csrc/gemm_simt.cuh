@@ -17,7 +17,7 @@ template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const TIn* __restrict__ A, int lda, const TIn* __restrict__ W, int ldw,
                  const float* __restrict__ bias, const float* residual, int ldr,
-                 TOut* C, int ldc, int M, int N, int K, int relu, const int* live_rows) {
+                 TOut* C, int ldc, int M, int N, int K, int relu, const int* live_rows, const int* rows_dev) {
   pdl_enter();
   if (step_is_dead(live_rows)) return;
   __shared__ __align__(16) float As[2][kSBK][kSBM + kSPad];
@@ -25,6 +25,7 @@ gemm_simt_kernel(const TIn* __restrict__ A, int lda, const TIn* __restrict__ W, 
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int m0 = blockIdx.y * kSBM, n0 = blockIdx.x * kSBN;
+  if (rows_dev && m0 >= *rows_dev) return;            // valid-row count on the device (compacted SAIC step)
 
   // global->register staging: 128 rows x 16 k = 512 quads per operand, 2 per thread
   float4 ra[2], rb[2];
@@ -104,11 +105,11 @@ gemm_simt_kernel(const TIn* __restrict__ A, int lda, const TIn* __restrict__ W, 
 template <typename TIn, typename TOut>
 inline cudaError_t gemm_simt(cudaStream_t s, const TIn* A, int lda, const TIn* W, int ldw, const float* bias,
                              const float* residual, int ldr, TOut* C, int ldc, int M, int N, int K, int relu,
-                             const int* live_rows) {
+                             const int* live_rows, const int* rows_dev = nullptr) {
   if (M <= 0 || N <= 0) return cudaSuccess;
   if (K % kSBK != 0 || lda % 4 != 0 || ldw % 4 != 0) return cudaErrorInvalidValue;
   dim3 grid((N + kSBN - 1) / kSBN, (M + kSBM - 1) / kSBM);
-  launch_k(gemm_simt_kernel<TIn, TOut>, grid, 256, 0, s, A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, relu, live_rows);
+  launch_k(gemm_simt_kernel<TIn, TOut>, grid, 256, 0, s, A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, relu, live_rows, rows_dev);
   return cudaGetLastError();
 }
 

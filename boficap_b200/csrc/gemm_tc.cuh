@@ -165,7 +165,7 @@ template <int BN, int STAGES, typename TOut, bool RELU, bool RESID, bool A_MN = 
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, const float* residual, int ldr,
-               int M, int N, int K, int relu, const int* live_rows, int k_splits) {
+               int M, int N, int K, int relu, const int* live_rows, int k_splits, const int* rows_dev) {
   pdl_launch();
   using L = SmemLayout<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
@@ -211,7 +211,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // Everything above (barriers, TMEM, descriptor prefetch) overlaps the tail of the previous kernel; global
   // memory is only touched after the programmatic-dependency wait.  A dead bounding step walks zero tiles.
   pdl_wait();
-  const int ntiles_mn = ((M + kBM - 1) / kBM) * tiles_n;
+  // rows_dev: the number of valid A rows lives on the device (compacted SAIC step); tiles beyond it are skipped
+  const int m_eff = rows_dev ? min(M, *rows_dev) : M;
+  const int ntiles_mn = ((m_eff + kBM - 1) / kBM) * tiles_n;
   const int ntiles = step_is_dead(live_rows) ? 0 : ntiles_mn * (REDUCE ? k_splits : 1);   // work items: (tile, K slice)
 
   if (warp == 0) {
@@ -461,7 +463,7 @@ inline int num_sms() {
 template <int BN, int STAGES, typename TOut, bool RELU, bool RESID, bool A_MN = false, bool B_MN = false, bool REDUCE = false>
 inline cudaError_t launch(cudaStream_t s, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                           const float* bias, const float* residual, int ldr, int M, int N, int K, int relu,
-                          const int* live_rows, int k_splits = 1) {
+                          const int* live_rows, int k_splits = 1, const int* rows_dev = nullptr) {
   using L = SmemLayout<BN, STAGES>;
   static bool configured = false;
   if (!configured) {
@@ -471,7 +473,7 @@ inline cudaError_t launch(cudaStream_t s, const CUtensorMap& tmA, const CUtensor
   }
   const int ntiles = ((M + kBM - 1) / kBM) * ((N + BN - 1) / BN) * k_splits;
   const int grid = ntiles < num_sms() ? ntiles : num_sms();
-  launch_k(gemm_tc_kernel<BN, STAGES, TOut, RELU, RESID, A_MN, B_MN, REDUCE>, grid, kThreads, L::kTotal, s, tmA, tmB, tmC, bias, residual, ldr, M, N, K, relu, live_rows, k_splits);
+  launch_k(gemm_tc_kernel<BN, STAGES, TOut, RELU, RESID, A_MN, B_MN, REDUCE>, grid, kThreads, L::kTotal, s, tmA, tmB, tmC, bias, residual, ldr, M, N, K, relu, live_rows, k_splits, rows_dev);
   return cudaGetLastError();
 }
 
@@ -507,7 +509,7 @@ inline const CUtensorMap* cached_tmap(const void* ptr, uint64_t rows, uint64_t c
 template <typename TOut>
 inline cudaError_t gemm_tc(cudaStream_t s, const bf16* A, int lda, const bf16* W, int ldw, const float* bias,
                            const float* residual, int ldr, TOut* C, int ldc, int M, int N, int K, int relu,
-                           const int* live_rows) {
+                           const int* live_rows, const int* rows_dev = nullptr) {
   if (M <= 0 || N <= 0) return cudaSuccess;
   if (lda % 8 != 0 || ldw % 8 != 0 || (ldc * sizeof(TOut)) % 16 != 0 || (residual && ldr % 4 != 0))
     return cudaErrorInvalidValue;
@@ -519,7 +521,7 @@ inline cudaError_t gemm_tc(cudaStream_t s, const bf16* A, int lda, const bf16* W
   if (!tmA || !tmB || !tmC) return cudaErrorInvalidValue;
   if (!bias) return cudaErrorInvalidValue;          // every nn.Linear of this model has a bias
 #define BOFI_TC_LAUNCH(BN_, ST_, RELU_, RESID_) \
-  launch<BN_, ST_, TOut, RELU_, RESID_>(s, *tmA, *tmB, *tmC, bias, residual, ldr, M, N, K, relu, live_rows)
+  launch<BN_, ST_, TOut, RELU_, RESID_>(s, *tmA, *tmB, *tmC, bias, residual, ldr, M, N, K, relu, live_rows, 1, rows_dev)
   if constexpr (sizeof(TOut) == 4) {
     // fp32 outputs: plain (logits), +ReLU (att_embed), +residual (O-proj / FFN2 into the residual stream)
     if (residual && relu) return cudaErrorInvalidValue;

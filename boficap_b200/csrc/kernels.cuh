@@ -15,12 +15,12 @@ template <typename TOut>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, size_t in_stride, const float* __restrict__ a2,
                  const float* __restrict__ b2, TOut* __restrict__ out, size_t out_stride, int rows,
-                 float* __restrict__ out_f32_copy, const int* live_rows) {
+                 float* __restrict__ out_f32_copy, const int* live_rows, const int* rows_dev) {
   pdl_enter();
   if (step_is_dead(live_rows)) return;
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
+  if (rows_dev) rows = min(rows, *rows_dev);           // compacted step: the valid-row count lives on the device
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += (gridDim.x * blockDim.x) >> 5) {
   const float* xr = x + (size_t)row * in_stride;
   float4 v[4];
   float s = 0.f;
@@ -48,6 +48,7 @@ layernorm_kernel(const float* __restrict__ x, size_t in_stride, const float* __r
     o.w = a.w * v[i].w / denom + b.w;
     store4(out + (size_t)row * out_stride + c, o);
     if (out_f32_copy) store4(out_f32_copy + (size_t)row * kD + c, o);
+  }
   }
 }
 
@@ -700,7 +701,10 @@ vocab_epilogue_kernel(const float* __restrict__ logits, int ldl, int V, float* _
 // kernels of a step test the snapshot, not the running counter.  counters[5] is the "phrase nan!" flag.
 // ---------------------------------------------------------------------------------------------
 __global__ void saic_snapshot_kernel(DecodeState st) {
-  pdl_enter(); st.counters[4] = st.counters[0]; }
+  pdl_enter();
+  st.counters[4] = st.counters[0];
+  st.counters[6] = 0;          // compact (row, slot) count of the step
+}
 
 // Decoder input of the phrase accepted at step i (:1928-1948): syn label + position-wise copy of the previous
 // phrase's words (last n words when n <= m, otherwise each word stretched ct or ct+1 times), and the
@@ -734,13 +738,16 @@ __global__ void saic_prepare_kernel(DecodeState st, int rows, int Lb, int L, int
 // (the reference aborts the whole batch when any log-prob of the step is NaN, :1956-1958).
 __global__ void __launch_bounds__(256)
 vocab_stats_kernel(const float* __restrict__ logits, int ldl, int V, int* __restrict__ tok, float* __restrict__ mx_out,
-                   float* __restrict__ lse_out, DecodeState st, Sampler sp) {
+                   float* __restrict__ lse_out, DecodeState st, Sampler sp, const int* __restrict__ cidx) {
   pdl_enter();
   if (st.counters[4] == 0) return;
   __shared__ ArgMax s_am[8];
   __shared__ float s_sum[8];
-  const int row = blockIdx.x;
-  const float* z = logits + (size_t)row * ldl;
+  // compact step (cidx != nullptr): logits / mx / lse rows are compact, the pick goes to the dense (row, slot) index
+  if (cidx && (int)blockIdx.x >= st.counters[6]) return;
+  const int zrow = blockIdx.x;
+  const int row = cidx ? cidx[zrow] : zrow;
+  const float* z = logits + (size_t)zrow * ldl;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   ArgMax am = {-INFINITY, 0x7fffffff};
   for (int c = tid; c < V; c += 256) am = better(am, ArgMax{z[c], c});
@@ -781,8 +788,8 @@ vocab_stats_kernel(const float* __restrict__ logits, int ldl, int V, int* __rest
 #pragma unroll
     for (int w = 0; w < 8; ++w) tot += s_sum[w];
     tok[row] = picked;
-    mx_out[row] = am.v;
-    lse_out[row] = logf(tot);
+    mx_out[zrow] = am.v;
+    lse_out[zrow] = logf(tot);
     if (am.v != am.v) atomicExch(&st.counters[5], 1);
   }
 }
@@ -792,15 +799,21 @@ vocab_stats_kernel(const float* __restrict__ logits, int ldl, int V, int* __rest
 __global__ void __launch_bounds__(256)
 saic_write_logp_kernel(const float* __restrict__ logits, int ldl, int V, const float* __restrict__ mx, const float* __restrict__ lse,
                        float* __restrict__ logp_out, DecodeState st, int L, int do_logsoftmax, const int* __restrict__ tok,
-                       float* __restrict__ slot_entropy, float* __restrict__ slot_logp) {
+                       float* __restrict__ slot_entropy, float* __restrict__ slot_logp, const int* __restrict__ cidx) {
   pdl_enter();
   if (st.counters[4] == 0 || st.counters[5] != 0) return;
-  const int row = blockIdx.x, b = row / L, t = row - b * L;
-  const int n = st.step_len[b], p = st.last[b];
-  if (n == 0 || t < p - 1 || t >= p - 1 + n) return;
-  const float* z = logits + (size_t)row * ldl;
+  int zrow = blockIdx.x, row = zrow;
+  if (cidx) {                            // compact step: every compact row is a committed slot
+    if (zrow >= st.counters[6]) return;
+    row = cidx[zrow];
+  } else {
+    const int b = row / L, t = row - b * L;
+    const int n = st.step_len[b], p = st.last[b];
+    if (n == 0 || t < p - 1 || t >= p - 1 + n) return;
+  }
+  const float* z = logits + (size_t)zrow * ldl;
   float* o = logp_out + (size_t)row * V;
-  const float m = mx[row], l = lse[row];
+  const float m = mx[zrow], l = lse[zrow];
   if (logp_out) {
     if (do_logsoftmax) {
       for (int c = threadIdx.x; c < V; c += 256) o[c] = (z[c] - m) - l;
@@ -848,6 +861,117 @@ __global__ void saic_advance_kernel(const int* __restrict__ tok, DecodeState st,
   st.vis[b * Lb] = p + n;                                     // len_mask[j, 0, :phrase_last] = True
   st.last[b] = p + n;
   st.seq_last[b] += st.phrase_length[b * Lb + step - 1];
+}
+
+// ---- incremental SAIC (decode_saic_incremental, engine.cu) -------------------------------------------------------
+// Under the phrase-block-causal mask a decoder slot only sees slots of its own and earlier phrases, and its input is
+// fixed once its phrase is placed: hidden states of earlier phrases never change.  Each step therefore only computes the
+// slots of the phrase accepted in that step (compact list of (row, slot)), with per-layer K/V caches for the rest.
+// cidx[k] = row * L + slot for every new decoder slot of the step; counters[6] = their number (any order).
+__global__ void saic_compact_kernel(DecodeState st, int rows, int L, int step, int* __restrict__ cidx) {
+  pdl_enter();
+  if (st.counters[4] == 0) return;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= rows) return;
+  const int n = st.step_len[b];
+  // A row without a first phrase keeps an all-False phrase mask: the reference's decoder turns its rows into NaN and
+  // core_SAIC aborts the whole batch at step 1 ("phrase nan!", TransformerModel.py:1956-1958).  Rows that did get a
+  // first phrase see >= 1 key in every slot from then on, so this is the only mask-induced NaN.
+  if (step == 1 && n == 0) atomicExch(&st.counters[5], 1);
+  if (n == 0) return;
+  const int p = st.last[b];
+  const int base = atomicAdd(&st.counters[6], n);
+  for (int k = 0; k < n; ++k) cidx[base + k] = b * L + p - 1 + k;
+}
+
+// x_c[k] = word_lut[w]*sqrt(d) + syn_lut[s]*sqrt(d) + pe[slot]   for the compact rows (decode_SA input, :520-523)
+__global__ void __launch_bounds__(256)
+embed_compact_kernel(const float* __restrict__ word_lut, const float* __restrict__ syn_lut, const float* __restrict__ pe,
+                     DecodeState st, int Lb, int L, const int* __restrict__ cidx, float sqrt_d, float* __restrict__ x) {
+  pdl_enter();
+  if (st.counters[4] == 0) return;
+  const int lane = threadIdx.x & 31, mc = st.counters[6];
+  for (int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < mc; k += (gridDim.x * blockDim.x) >> 5) {
+    const int d = cidx[k], b = d / L, q = d - b * L;
+    const int w = st.ext_word[b * Lb + 1 + q], sy = st.ext_syn[b * Lb + 1 + q];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      float4 e = load4(word_lut + (size_t)w * kD + c);
+      e.x *= sqrt_d; e.y *= sqrt_d; e.z *= sqrt_d; e.w *= sqrt_d;
+      const float4 g = load4(syn_lut + (size_t)sy * kD + c);
+      e.x += g.x * sqrt_d; e.y += g.y * sqrt_d; e.z += g.z * sqrt_d; e.w += g.w * sqrt_d;
+      const float4 pp = load4(pe + (size_t)q * kD + c);
+      e.x += pp.x; e.y += pp.y; e.z += pp.z; e.w += pp.w;
+      store4(x + (size_t)k * kD + c, e);
+    }
+  }
+}
+
+// cache[cidx[k], 0:1024] = qkv_c[k, 512:1536]   (K | V of the new slots into the layer's cache)
+template <typename T>
+__global__ void __launch_bounds__(256)
+saic_scatter_kv_kernel(const T* __restrict__ qkv_c, const int* __restrict__ cidx, DecodeState st, T* __restrict__ cache) {
+  pdl_enter();
+  if (st.counters[4] == 0) return;
+  const int lane = threadIdx.x & 31, mc = st.counters[6];
+  for (int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < mc; k += (gridDim.x * blockDim.x) >> 5) {
+    const T* src = qkv_c + (size_t)k * 3 * kD + kD;
+    T* dst = cache + (size_t)cidx[k] * 2 * kD;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) store4(dst + (i * 32 + lane) * 4, load4(src + (i * 32 + lane) * 4));
+  }
+}
+
+// Self-attention of the compact query rows against their sequence's cached K/V (keys < vis_fill[row, slot]).
+// One CTA (8 warps = 8 heads) per compact row; arithmetic order as attention_kernel.
+template <typename T>
+__global__ void __launch_bounds__(256)
+saic_self_attn_kernel(const T* __restrict__ qkv_c, const T* __restrict__ cache, const int* __restrict__ cidx, DecodeState st, int L,
+                      T* __restrict__ O, float scale) {
+  pdl_enter();
+  if (st.counters[4] == 0) return;
+  __shared__ float qs[8][kHeadDim];
+  const int head = threadIdx.x >> 5, lane = threadIdx.x & 31, mc = st.counters[6];
+  for (int k = blockIdx.x; k < mc; k += gridDim.x) {
+  const int d = cidx[k], b = d / L;
+  const int nvis = min(st.vis_fill[d], L);
+  const T* qg = qkv_c + (size_t)k * 3 * kD + head * kHeadDim;
+  qs[head][lane] = to_float<T>(qg[lane]);
+  qs[head][lane + 32] = to_float<T>(qg[lane + 32]);
+  __syncwarp();
+  const T* base = cache + (size_t)b * L * 2 * kD;
+  float s = -INFINITY;
+  if (lane < nvis) {
+    const T* kr = base + (size_t)lane * 2 * kD + head * kHeadDim;
+    float dsum = 0.f;
+#pragma unroll
+    for (int c = 0; c < kHeadDim; c += 4) {
+      const float4 kq = load4(kr + c);
+      dsum = fmaf(qs[head][c], kq.x, dsum);
+      dsum = fmaf(qs[head][c + 1], kq.y, dsum);
+      dsum = fmaf(qs[head][c + 2], kq.z, dsum);
+      dsum = fmaf(qs[head][c + 3], kq.w, dsum);
+    }
+    s = dsum * scale;
+  }
+  const float mx = warp_max(s);
+  const float e = (lane < nvis) ? expf(s - mx) : 0.f;
+  const float sum = warp_sum(e);
+  const float p = e / sum;
+  float o0 = 0.f, o1 = 0.f;
+  for (int j = 0; j < nvis; ++j) {
+    const float pj = __shfl_sync(0xffffffffu, p, j);
+    const T* vr = base + (size_t)j * 2 * kD + kD + head * kHeadDim;
+    o0 = fmaf(pj, to_float<T>(vr[lane]), o0);
+    o1 = fmaf(pj, to_float<T>(vr[lane + 32]), o1);
+  }
+  if (nvis <= 0) o0 = o1 = __int_as_float(0x7fc00000);
+  T* og = O + (size_t)k * kD + head * kHeadDim;
+  og[lane] = from_float<T>(o0);
+  og[lane + 32] = from_float<T>(o1);
+  __syncwarp();                      // qs[head] is rewritten by the next compact row
+  }
 }
 
 __global__ void export_seq_kernel(DecodeState st, int rows, int Lb, int L, long long* __restrict__ seq) {
