@@ -128,6 +128,7 @@ struct bofi_engine {
   const bf16* head1_w16 = nullptr;
   DevBuf bound_in, fill_in;            // (id, position) input tables
   DevBuf sa_mx, sa_lse;                // SAIC: per (row, slot) max / log-sum-exp of the step's logits
+  DevBuf sa_bcache, sa_qkv0, sa_x0;    // incremental SAIC bounding: K|V cache [rows*Lb][1024], QKV of the [LEN] row, its input row
   DevBuf sa_cidx, sa_cache;            // incremental SAIC: compact (row, slot) list, per-layer K|V caches [n_dec][rows*L][1024]
   bool saic_full = false;              // BOFI_SAIC=full: recompute every slot at every step (the reference formulation)
   DevBuf head1t;                       // [512][200] = [Length_classifier1 ; Syntactic_classifier1]^T
@@ -907,6 +908,25 @@ static int decode_saic_incremental(bofi_engine* e, cudaStream_t s, int sn, int o
   const int* live = e->st.counters + 4;
   const int* mdev = e->st.counters + 6;
   int* cidx = e->sa_cidx.as<int>();
+  // incremental bounding (N_len == 1): constant [LEN] row -> its QKV; K|V of slot 0 into every sequence's cache
+  const bool inc_bound = (c.n_len == 1);
+  Lin kvlin;
+  if (inc_bound) {
+    const Layer& lb = e->lp[0];
+    RC_TRY(e->sa_bcache.reserve((size_t)rows * Lb * 2 * kD * sizeof(T)));
+    RC_TRY(e->sa_qkv0.reserve((size_t)3 * kD * sizeof(T) + 256));
+    RC_TRY(e->sa_x0.reserve((size_t)kD * 4));
+    kvlin = lb.sa.qkv;                       // the K|V rows of the fused Q|K|V matrix
+    if (kvlin.w32) kvlin.w32 += (size_t)kD * kD;
+    if (kvlin.w16) kvlin.w16 += (size_t)kD * kD;
+    kvlin.b += kD;
+    kvlin.N = 2 * kD;
+    LAUNCH_OTHER((launch_k(saic_len_row_kernel, 1, 128, 0, s, W(e, "model.tgt_embed.lut.weight"), W(e, "model.pos_embed.pe"), c.len_idx,
+                           sqrtf((float)kD), e->sa_x0.as<float>())));
+    RC_TRY(layernorm<T>(e, s, e->sa_x0.as<float>(), kD, lb.ln[0], e->y.as<T>(), kD, 1, nullptr, nullptr));
+    RC_TRY((linear<T, T>(e, s, e->y.as<T>(), kD, lb.sa.qkv, nullptr, 0, e->sa_qkv0.as<T>(), 3 * kD, 1, 0, nullptr)));
+    LAUNCH_OTHER((launch_k(saic_bcache_init_kernel<T>, ceil_div(rows, 8), 256, 0, s, (const T*)e->sa_qkv0.as<T>(), e->sa_bcache.as<T>(), rows, Lb)));
+  }
   float* x = e->x.as<float>();
   T* y = e->y.as<T>();
   T* qkv = e->qkv.as<T>();
@@ -917,7 +937,27 @@ static int decode_saic_incremental(bofi_engine* e, cudaStream_t s, int sn, int o
   auto enqueue_steps = [&](cudaStream_t s) -> int {
   for (int i = 1; i <= L; ++i) {
     LAUNCH_OTHER((launch_k(saic_snapshot_kernel, 1, 1, 0, s, e->st)));
-    RC_TRY(bounding_step<T>(e, s, rows, sn, i, 1));
+    if (inc_bound) {
+      const Layer& lb = e->lp[0];
+      {
+        ProfScope prof(e, s, PC_ATTENTION, 0.0, 0.0);
+        launch_k(saic_bound_self_attn_kernel<T>, rows, 256, 0, s, (const T*)e->sa_qkv0.as<T>(), (const T*)e->sa_bcache.as<T>(), Lb,
+                 (const int*)e->st.last, ao, scale, live, (const int*)e->st.finished);
+      }
+      CU_TRY(cudaGetLastError());
+      RC_TRY((linear<T, float>(e, s, ao, kD, lb.sa.o, e->sa_x0.as<float>(), 0, x, kD, rows, 0, live)));     // residual = the [LEN] input row
+      RC_TRY(layernorm<T>(e, s, x, kD, lb.ln[1], y, kD, rows, nullptr, live));
+      RC_TRY((linear<T, T>(e, s, y, kD, lb.ca.q, nullptr, 0, q, kD, rows, 0, live)));
+      RC_TRY(attention<T>(e, s, q, kD, e->kv[0].as<T>(), e->kv[0].as<T>() + kD, 2 * kD, ao, kD, rows, 1, e->R, mem_len, 1, 0, sn, sn, live,
+                          e->st.finished));
+      RC_TRY((linear<T, float>(e, s, ao, kD, lb.ca.o, x, kD, x, kD, rows, 0, live)));
+      RC_TRY(layernorm<T>(e, s, x, kD, lb.ln[2], y, kD, rows, nullptr, live));
+      RC_TRY((linear<T, T>(e, s, y, kD, lb.w1, nullptr, 0, ffh, c.d_ff, rows, 1, live)));
+      RC_TRY((linear<T, float>(e, s, ffh, c.d_ff, lb.w2, x, kD, x, kD, rows, 0, live)));
+      RC_TRY(head_step(e, s, x, kD, rows, i, i, 1));
+    } else {
+      RC_TRY(bounding_step<T>(e, s, rows, sn, i, 1));
+    }
     LAUNCH_OTHER((launch_k(saic_prepare_kernel, ceil_div(rows, 128), 128, 0, s, e->st, rows, Lb, L, i)));
     LAUNCH_OTHER((launch_k(saic_compact_kernel, ceil_div(rows, 128), 128, 0, s, e->st, rows, L, i, cidx)));
     LAUNCH_OTHER((launch_k(embed_compact_kernel, std::min(ceil_div(slots, 8), 148 * 4), 256, 0, s, W(e, "model.tgt_embed.lut.weight"), W(e, "model.syn_embed.lut.weight"),
@@ -955,8 +995,7 @@ static int decode_saic_incremental(bofi_engine* e, cudaStream_t s, int sn, int o
     }
     if (rc == BOFI_OK) rc = layernorm<T>(e, s, x, kD, e->dec_norm, y, kD, slots, nullptr, live);
     if (rc == BOFI_OK) rc = linear<T, float>(e, s, y, kD, e->generator, nullptr, 0, e->logits.as<float>(), e->Vpad, slots, 0, live);
-    e->rows_dev = nullptr;
-    RC_TRY(rc);
+    if (rc != BOFI_OK) { e->rows_dev = nullptr; return rc; }
     {
       ProfScope prof(e, s, PC_VOCAB, 0.0, 0.0);
       Sampler sp = e->sampler;
@@ -964,6 +1003,21 @@ static int decode_saic_incremental(bofi_engine* e, cudaStream_t s, int sn, int o
       launch_k(vocab_stats_kernel, slots, 256, 0, s, e->logits.as<float>(), e->Vpad, e->V, e->tok.as<int>(), e->sa_mx.as<float>(),
                e->sa_lse.as<float>(), e->st, sp, (const int*)cidx);
     }
+    if (inc_bound && rc == BOFI_OK) {
+      // K|V of the words just picked, for the bounding layer of the following steps
+      auto bkv = [&]() -> int {
+        LAUNCH_OTHER((launch_k(embed_bound_compact_kernel, std::min(ceil_div(slots, 8), 148 * 4), 256, 0, s, W(e, "model.tgt_embed.lut.weight"),
+                               W(e, "model.pos_embed.pe"), (const int*)e->tok.as<int>(), e->st, L, (const int*)cidx, sqrt_d, x)));
+        RC_TRY(layernorm<T>(e, s, x, kD, e->lp[0].ln[0], y, kD, slots, nullptr, live));
+        RC_TRY((linear<T, T>(e, s, y, kD, kvlin, nullptr, 0, qkv, 2 * kD, slots, 0, live)));
+        LAUNCH_OTHER((launch_k(saic_scatter_bkv_kernel<T>, std::min(ceil_div(slots, 8), 148 * 4), 256, 0, s, (const T*)qkv, (const int*)cidx, e->st, L,
+                               Lb, e->sa_bcache.as<T>())));
+        return BOFI_OK;
+      };
+      rc = bkv();
+    }
+    e->rows_dev = nullptr;
+    RC_TRY(rc);
     CU_TRY(cudaGetLastError());
     if (logprobs || e->stat_entropy) {
       ProfScope prof(e, s, PC_VOCAB, 0.0, 0.0);
@@ -1070,7 +1124,7 @@ int bofi_destroy(bofi_handle_t e) {
   e->flat16.release();
   for (DevBuf& b : e->kv) b.release();
   DevBuf* all[] = {&e->bound_in, &e->fill_in, &e->attT, &e->x, &e->y, &e->qkv, &e->ao, &e->q, &e->ffh, &e->memT, &e->attlen,
-                   &e->sa_mx, &e->sa_lse, &e->sa_cidx, &e->sa_cache, &e->head1t, &e->tab_y, &e->tab_qkv, &e->hrow, &e->hid, &e->logits, &e->state_i32, &e->tok, &e->h_in, &e->h_len, &e->h_seq, &e->h_logp,
+                   &e->sa_mx, &e->sa_lse, &e->sa_cidx, &e->sa_cache, &e->sa_bcache, &e->sa_qkv0, &e->sa_x0, &e->head1t, &e->tab_y, &e->tab_qkv, &e->hrow, &e->hid, &e->logits, &e->state_i32, &e->tok, &e->h_in, &e->h_len, &e->h_seq, &e->h_logp,
                    &e->h_pnum, &e->h_plen, &e->h_psyn, &e->unit_a, &e->unit_w, &e->unit_o};
   for (DevBuf* b : all) b->release();
   delete e;

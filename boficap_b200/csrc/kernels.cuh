@@ -974,6 +974,107 @@ saic_self_attn_kernel(const T* __restrict__ qkv_c, const T* __restrict__ cache, 
   }
 }
 
+// ---- incremental SAIC bounding (N_len == 1): the bounding layer's input rows are the words generated so far, so its
+// LN + K|V projection is cached per (row, slot) as well and only the [LEN] query row is evaluated per step.
+// x0[0:512] = tgt_embed[len_idx]*sqrt(d) + pe[0]   (the constant [LEN] input row, TransformerModel.py:518)
+__global__ void saic_len_row_kernel(const float* __restrict__ word_lut, const float* __restrict__ pe, int len_idx, float sqrt_d,
+                                    float* __restrict__ x0) {
+  pdl_enter();
+  for (int c = threadIdx.x; c < kD; c += blockDim.x) x0[c] = word_lut[(size_t)len_idx * kD + c] * sqrt_d + pe[c];
+}
+// bcache[b*Lb + 0, :] = K|V of the [LEN] row for every sequence b
+template <typename T>
+__global__ void __launch_bounds__(256)
+saic_bcache_init_kernel(const T* __restrict__ qkv_row, T* __restrict__ bcache, int rows, int Lb) {
+  pdl_enter();
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= rows) return;
+  T* dst = bcache + (size_t)b * Lb * 2 * kD;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) store4(dst + (i * 32 + lane) * 4, load4(qkv_row + kD + (i * 32 + lane) * 4));
+}
+// x_c[k] = tgt_embed[tok]*sqrt(d) + pe[slot + 1] for the words picked in this step (bounding-layer input rows)
+__global__ void __launch_bounds__(256)
+embed_bound_compact_kernel(const float* __restrict__ word_lut, const float* __restrict__ pe, const int* __restrict__ tok, DecodeState st,
+                           int L, const int* __restrict__ cidx, float sqrt_d, float* __restrict__ x) {
+  pdl_enter();
+  if (st.counters[4] == 0) return;
+  const int lane = threadIdx.x & 31, mc = st.counters[6];
+  for (int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < mc; k += (gridDim.x * blockDim.x) >> 5) {
+    const int d = cidx[k], b = d / L, q = d - b * L;
+    const int w = tok[d];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      float4 e = load4(word_lut + (size_t)w * kD + c);
+      e.x *= sqrt_d; e.y *= sqrt_d; e.z *= sqrt_d; e.w *= sqrt_d;
+      const float4 pp = load4(pe + (size_t)(q + 1) * kD + c);
+      e.x += pp.x; e.y += pp.y; e.z += pp.z; e.w += pp.w;
+      store4(x + (size_t)k * kD + c, e);
+    }
+  }
+}
+// bcache[(b*Lb + slot + 1), :] = kv_c[k, :]
+template <typename T>
+__global__ void __launch_bounds__(256)
+saic_scatter_bkv_kernel(const T* __restrict__ kv_c, const int* __restrict__ cidx, DecodeState st, int L, int Lb, T* __restrict__ bcache) {
+  pdl_enter();
+  if (st.counters[4] == 0) return;
+  const int lane = threadIdx.x & 31, mc = st.counters[6];
+  for (int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < mc; k += (gridDim.x * blockDim.x) >> 5) {
+    const int d = cidx[k], b = d / L, q = d - b * L;
+    const T* src = kv_c + (size_t)k * 2 * kD;
+    T* dst = bcache + ((size_t)b * Lb + q + 1) * 2 * kD;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) store4(dst + (i * 32 + lane) * 4, load4(src + (i * 32 + lane) * 4));
+  }
+}
+// Self-attention of the [LEN] row (constant query q0) over the cached K/V of the words generated so far (keys < last[b],
+// len_mask[j, 0, :phrase_last], TransformerModel.py:1975).  One CTA per sequence, one warp per head.
+template <typename T>
+__global__ void __launch_bounds__(256)
+saic_bound_self_attn_kernel(const T* __restrict__ q0, const T* __restrict__ bcache, int Lb, const int* __restrict__ last, T* __restrict__ O,
+                            float scale, const int* live_rows, const int* __restrict__ finished) {
+  pdl_enter();
+  if (step_is_dead(live_rows)) return;
+  if (finished[blockIdx.x]) return;
+  __shared__ float qs[8][kHeadDim];
+  const int b = blockIdx.x, head = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvis = min(last[b], Lb);
+  qs[head][lane] = to_float<T>(q0[head * kHeadDim + lane]);
+  qs[head][lane + 32] = to_float<T>(q0[head * kHeadDim + lane + 32]);
+  __syncwarp();
+  const T* base = bcache + (size_t)b * Lb * 2 * kD;
+  float s = -INFINITY;
+  if (lane < nvis) {
+    const T* kr = base + (size_t)lane * 2 * kD + head * kHeadDim;
+    float d = 0.f;
+#pragma unroll
+    for (int c = 0; c < kHeadDim; c += 4) {
+      const float4 kq = load4(kr + c);
+      d = fmaf(qs[head][c], kq.x, d);
+      d = fmaf(qs[head][c + 1], kq.y, d);
+      d = fmaf(qs[head][c + 2], kq.z, d);
+      d = fmaf(qs[head][c + 3], kq.w, d);
+    }
+    s = d * scale;
+  }
+  const float mx = warp_max(s);
+  const float e = (lane < nvis) ? expf(s - mx) : 0.f;
+  const float sum = warp_sum(e);
+  const float p = e / sum;
+  float o0 = 0.f, o1 = 0.f;
+  for (int j = 0; j < nvis; ++j) {
+    const float pj = __shfl_sync(0xffffffffu, p, j);
+    const T* vr = base + (size_t)j * 2 * kD + kD + head * kHeadDim;
+    o0 = fmaf(pj, to_float<T>(vr[lane]), o0);
+    o1 = fmaf(pj, to_float<T>(vr[lane + 32]), o1);
+  }
+  T* og = O + (size_t)b * kD + head * kHeadDim;
+  og[lane] = from_float<T>(o0);
+  og[lane + 32] = from_float<T>(o1);
+}
+
 __global__ void export_seq_kernel(DecodeState st, int rows, int Lb, int L, long long* __restrict__ seq) {
   pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
