@@ -442,7 +442,7 @@ def main():
                             for k, v in prof.items()}}
 
     cpu = None
-    if world == 1 or True:
+    if world == 1:          # reported on rank 0 at N = 1 only (the other ranks would be spinning in the barrier meanwhile)
         cps, sec, cores, Scpu = cpu_reference_run(a.cpu_steps, 1, cfg, sd, R, a.mode)
         cpu = {"value": cps, "unit": "captions/s", "cores": cores, "kind": "port",
                "sample": "%d images x %d calls of the oracle port (reference formulation, fp32), S=%d" % (CPU_SAMPLE_IMAGES, a.cpu_steps, Scpu)}
