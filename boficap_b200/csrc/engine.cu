@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_ln_tc.cuh"
 #include "kernels.cuh"
 #include "attention_mma.cuh"
 #include "train_kernels.cuh"
@@ -111,6 +112,8 @@ struct bofi_engine {
   int Lb = 22, L = 20, V = 0, Vpad = 0;
   bool bf16_mode = false;
   bool use_tc = true;
+  int ln_fuse_min_rows = 4096;         // below this the panel LayerNorm would be repeated by too many CTAs
+  bool ln_fuse = false;                // BOFI_LNFUSE=1: LayerNorm fused into the consuming tcgen05 GEMM (gemm_ln_tc.cuh; measured slower, off)
   bool attn_simt_only = false;         // BOFI_ATTN=simt: generic FFMA attention kernel everywhere
   bool finalized = false;
   std::unordered_map<std::string, WeightEntry> weights;
@@ -303,6 +306,23 @@ static int layernorm(bofi_engine* e, cudaStream_t s, const float* x, size_t in_s
   return BOFI_OK;
 }
 
+// out = act(LayerNorm(x) . W^T + b).  bf16 / tcgen05: one LayerNorm-fused, A-resident GEMM (gemm_ln_tc.cuh);
+// otherwise LayerNorm into `ybuf`, then the plain GEMM.
+template <typename T, typename TOut>
+static int ln_linear(bofi_engine* e, cudaStream_t s, const float* x, const Norm& n, const Lin& l, TOut* out, int ldc, int M, int relu,
+                     const int* live, T* ybuf) {
+  if constexpr (std::is_same<T, bf16>::value) {
+    if (e->use_tc && e->ln_fuse && l.K == kD && M >= e->ln_fuse_min_rows) {
+      ProfScope prof(e, s, PC_GEMM_TC, 2.0 * M * l.N * l.K, 4.0 * M * l.K + 2.0 * l.N * l.K + (double)sizeof(TOut) * M * l.N, M, l.N, l.K);
+      cudaError_t err = tc::gemm_ln_tc<TOut>(s, x, (size_t)kD, n.a, n.b, l.w16, l.b, out, ldc, M, l.N, relu, live, e->rows_dev);
+      if (err != cudaSuccess) return fail(BOFI_ERR_CUDA, "LN-fused gemm M=%d N=%d: %s", M, l.N, cudaGetErrorString(err));
+      return BOFI_OK;
+    }
+  }
+  RC_TRY(layernorm<T>(e, s, x, kD, n, ybuf, kD, M, nullptr, live));
+  return linear<T, TOut>(e, s, ybuf, kD, l, nullptr, 0, out, ldc, M, relu, live);
+}
+
 template <int KT>
 static cudaError_t launch_attention_mma(cudaStream_t s, dim3 grid, size_t smem, const bf16* Q, int ldq, const bf16* K, const bf16* V,
                                         int ldkv, bf16* O, int ldo, int Tq, int Tk, const int* vis, int vis_bs, int vis_qs,
@@ -376,22 +396,19 @@ static int run_layer(bofi_engine* e, cudaStream_t s, const Layer& ly, float* x, 
   T* qkv = e->qkv.as<T>();
   T* ao = e->ao.as<T>();
   T* ffh = e->ffh.as<T>();
-  RC_TRY(layernorm<T>(e, s, x, kD, ly.ln[0], y, kD, rows, nullptr, live));
-  RC_TRY((linear<T, T>(e, s, y, kD, ly.sa.qkv, nullptr, 0, qkv, 3 * kD, rows, 0, live)));
+  RC_TRY((ln_linear<T, T>(e, s, x, ly.ln[0], ly.sa.qkv, qkv, 3 * kD, rows, 0, live, y)));
   RC_TRY(attention<T>(e, s, qkv, 3 * kD, qkv + kD, qkv + 2 * kD, 3 * kD, ao, kD, nb, T_, T_, self_vis, self_vis_bs,
                       self_vis_qs, 1, 1, live));
   RC_TRY((linear<T, float>(e, s, ao, kD, ly.sa.o, x, kD, x, kD, rows, 0, live)));
   int f = 1;
   if (ly.cross) {
     T* q = e->q.as<T>();
-    RC_TRY(layernorm<T>(e, s, x, kD, ly.ln[1], y, kD, rows, nullptr, live));
-    RC_TRY((linear<T, T>(e, s, y, kD, ly.ca.q, nullptr, 0, q, kD, rows, 0, live)));
+    RC_TRY((ln_linear<T, T>(e, s, x, ly.ln[1], ly.ca.q, q, kD, rows, 0, live, y)));
     RC_TRY(attention<T>(e, s, q, kD, kvmem, kvmem + kD, 2 * kD, ao, kD, nb, T_, R, mem_len, 1, 0, kv_div, kv_div, live));
     RC_TRY((linear<T, float>(e, s, ao, kD, ly.ca.o, x, kD, x, kD, rows, 0, live)));
     f = 2;
   }
-  RC_TRY(layernorm<T>(e, s, x, kD, ly.ln[f], y, kD, rows, nullptr, live));
-  RC_TRY((linear<T, T>(e, s, y, kD, ly.w1, nullptr, 0, ffh, e->cfg.d_ff, rows, 1, live)));
+  RC_TRY((ln_linear<T, T>(e, s, x, ly.ln[f], ly.w1, ffh, e->cfg.d_ff, rows, 1, live, y)));
   RC_TRY((linear<T, float>(e, s, ffh, e->cfg.d_ff, ly.w2, x, kD, x, kD, rows, 0, live)));
   return BOFI_OK;
 }
@@ -676,13 +693,11 @@ static int bounding_step_fast(bofi_engine* e, cudaStream_t s, int rows, int sn, 
   }
   CU_TRY(cudaGetLastError());
   RC_TRY((linear<T, float>(e, s, ao, kD, ly.sa.o, x0, 0, x, kD, rows, 0, live)));          // residual = x0 broadcast
-  RC_TRY(layernorm<T>(e, s, x, kD, ly.ln[1], y, kD, rows, nullptr, live));
-  RC_TRY((linear<T, T>(e, s, y, kD, ly.ca.q, nullptr, 0, q, kD, rows, 0, live)));
+  RC_TRY((ln_linear<T, T>(e, s, x, ly.ln[1], ly.ca.q, q, kD, rows, 0, live, y)));
   RC_TRY(attention<T>(e, s, q, kD, e->kv[0].as<T>(), e->kv[0].as<T>() + kD, 2 * kD, ao, kD, rows, 1, e->R, mem_len, 1, 0, sn, sn, live,
                       e->st.finished));
   RC_TRY((linear<T, float>(e, s, ao, kD, ly.ca.o, x, kD, x, kD, rows, 0, live)));
-  RC_TRY(layernorm<T>(e, s, x, kD, ly.ln[2], y, kD, rows, nullptr, live));
-  RC_TRY((linear<T, T>(e, s, y, kD, ly.w1, nullptr, 0, ffh, c.d_ff, rows, 1, live)));
+  RC_TRY((ln_linear<T, T>(e, s, x, ly.ln[2], ly.w1, ffh, c.d_ff, rows, 1, live, y)));
   RC_TRY((linear<T, float>(e, s, ffh, c.d_ff, ly.w2, x, kD, x, kD, rows, 0, live)));
   RC_TRY(head_step(e, s, x, kD, rows, step_col, step_col + 1, 0));
   return BOFI_OK;
@@ -795,8 +810,7 @@ static int decode_naic(bofi_engine* e, cudaStream_t s, int sn, int output_logsof
   CU_TRY(cudaGetLastError());
   for (int l = 0; l < c.n_dec; ++l)
     RC_TRY(run_layer<T>(e, s, e->dec[l], x, rows, L, e->st.vis_fill, L, 1, e->kv[nb_layers + l].as<T>(), e->R, mem_len, sn, nullptr));
-  RC_TRY(layernorm<T>(e, s, x, kD, e->dec_norm, e->y.as<T>(), kD, rows * L, nullptr, nullptr));
-  RC_TRY((linear<T, float>(e, s, e->y.as<T>(), kD, e->generator, nullptr, 0, e->logits.as<float>(), e->Vpad, rows * L, 0, nullptr)));
+  RC_TRY((ln_linear<T, float>(e, s, x, e->dec_norm, e->generator, e->logits.as<float>(), e->Vpad, rows * L, 0, nullptr, e->y.as<T>())));
   {
     ProfScope prof(e, s, PC_VOCAB, 0.0, 0.0);
     launch_k(vocab_epilogue_kernel, rows * L, kVocabThreads, 0, s, e->logits.as<float>(), e->Vpad, e->V, logprobs, seq, e->st.last, -1, L,
@@ -946,13 +960,11 @@ static int decode_saic_incremental(bofi_engine* e, cudaStream_t s, int sn, int o
       }
       CU_TRY(cudaGetLastError());
       RC_TRY((linear<T, float>(e, s, ao, kD, lb.sa.o, e->sa_x0.as<float>(), 0, x, kD, rows, 0, live)));     // residual = the [LEN] input row
-      RC_TRY(layernorm<T>(e, s, x, kD, lb.ln[1], y, kD, rows, nullptr, live));
-      RC_TRY((linear<T, T>(e, s, y, kD, lb.ca.q, nullptr, 0, q, kD, rows, 0, live)));
+      RC_TRY((ln_linear<T, T>(e, s, x, lb.ln[1], lb.ca.q, q, kD, rows, 0, live, y)));
       RC_TRY(attention<T>(e, s, q, kD, e->kv[0].as<T>(), e->kv[0].as<T>() + kD, 2 * kD, ao, kD, rows, 1, e->R, mem_len, 1, 0, sn, sn, live,
                           e->st.finished));
       RC_TRY((linear<T, float>(e, s, ao, kD, lb.ca.o, x, kD, x, kD, rows, 0, live)));
-      RC_TRY(layernorm<T>(e, s, x, kD, lb.ln[2], y, kD, rows, nullptr, live));
-      RC_TRY((linear<T, T>(e, s, y, kD, lb.w1, nullptr, 0, ffh, c.d_ff, rows, 1, live)));
+      RC_TRY((ln_linear<T, T>(e, s, x, lb.ln[2], lb.w1, ffh, c.d_ff, rows, 1, live, y)));
       RC_TRY((linear<T, float>(e, s, ffh, c.d_ff, lb.w2, x, kD, x, kD, rows, 0, live)));
       RC_TRY(head_step(e, s, x, kD, rows, i, i, 1));
     } else {
@@ -969,8 +981,7 @@ static int decode_saic_incremental(bofi_engine* e, cudaStream_t s, int sn, int o
       T* cache = e->sa_cache.as<T>() + (size_t)l * slots * 2 * kD;
       const T* kvmem = e->kv[nb_layers + l].as<T>();
       auto layer = [&]() -> int {
-        RC_TRY(layernorm<T>(e, s, x, kD, ly.ln[0], y, kD, slots, nullptr, live));
-        RC_TRY((linear<T, T>(e, s, y, kD, ly.sa.qkv, nullptr, 0, qkv, 3 * kD, slots, 0, live)));
+        RC_TRY((ln_linear<T, T>(e, s, x, ly.ln[0], ly.sa.qkv, qkv, 3 * kD, slots, 0, live, y)));
         {
           ProfScope prof(e, s, PC_OTHER, 0.0, 0.0);
           launch_k(saic_scatter_kv_kernel<T>, std::min(ceil_div(slots, 8), 148 * 4), 256, 0, s, (const T*)qkv, (const int*)cidx, e->st, cache);
@@ -982,19 +993,16 @@ static int decode_saic_incremental(bofi_engine* e, cudaStream_t s, int sn, int o
         }
         CU_TRY(cudaGetLastError());
         RC_TRY((linear<T, float>(e, s, ao, kD, ly.sa.o, x, kD, x, kD, slots, 0, live)));
-        RC_TRY(layernorm<T>(e, s, x, kD, ly.ln[1], y, kD, slots, nullptr, live));
-        RC_TRY((linear<T, T>(e, s, y, kD, ly.ca.q, nullptr, 0, q, kD, slots, 0, live)));
+        RC_TRY((ln_linear<T, T>(e, s, x, ly.ln[1], ly.ca.q, q, kD, slots, 0, live, y)));
         RC_TRY(attention<T>(e, s, q, kD, kvmem, kvmem + kD, 2 * kD, ao, kD, slots, 1, e->R, mem_len, 1, 0, sn, sn, live, nullptr, Drop(), cidx, L));
         RC_TRY((linear<T, float>(e, s, ao, kD, ly.ca.o, x, kD, x, kD, slots, 0, live)));
-        RC_TRY(layernorm<T>(e, s, x, kD, ly.ln[2], y, kD, slots, nullptr, live));
-        RC_TRY((linear<T, T>(e, s, y, kD, ly.w1, nullptr, 0, ffh, c.d_ff, slots, 1, live)));
+        RC_TRY((ln_linear<T, T>(e, s, x, ly.ln[2], ly.w1, ffh, c.d_ff, slots, 1, live, y)));
         RC_TRY((linear<T, float>(e, s, ffh, c.d_ff, ly.w2, x, kD, x, kD, slots, 0, live)));
         return BOFI_OK;
       };
       rc = layer();
     }
-    if (rc == BOFI_OK) rc = layernorm<T>(e, s, x, kD, e->dec_norm, y, kD, slots, nullptr, live);
-    if (rc == BOFI_OK) rc = linear<T, float>(e, s, y, kD, e->generator, nullptr, 0, e->logits.as<float>(), e->Vpad, slots, 0, live);
+    if (rc == BOFI_OK) rc = ln_linear<T, float>(e, s, x, e->dec_norm, e->generator, e->logits.as<float>(), e->Vpad, slots, 0, live, y);
     if (rc != BOFI_OK) { e->rows_dev = nullptr; return rc; }
     {
       ProfScope prof(e, s, PC_VOCAB, 0.0, 0.0);
@@ -1008,8 +1016,7 @@ static int decode_saic_incremental(bofi_engine* e, cudaStream_t s, int sn, int o
       auto bkv = [&]() -> int {
         LAUNCH_OTHER((launch_k(embed_bound_compact_kernel, std::min(ceil_div(slots, 8), 148 * 4), 256, 0, s, W(e, "model.tgt_embed.lut.weight"),
                                W(e, "model.pos_embed.pe"), (const int*)e->tok.as<int>(), e->st, L, (const int*)cidx, sqrt_d, x)));
-        RC_TRY(layernorm<T>(e, s, x, kD, e->lp[0].ln[0], y, kD, slots, nullptr, live));
-        RC_TRY((linear<T, T>(e, s, y, kD, kvlin, nullptr, 0, qkv, 2 * kD, slots, 0, live)));
+        RC_TRY((ln_linear<T, T>(e, s, x, e->lp[0].ln[0], kvlin, qkv, 2 * kD, slots, 0, live, y)));
         LAUNCH_OTHER((launch_k(saic_scatter_bkv_kernel<T>, std::min(ceil_div(slots, 8), 148 * 4), 256, 0, s, (const T*)qkv, (const int*)cidx, e->st, L,
                                Lb, e->sa_bcache.as<T>())));
         return BOFI_OK;
@@ -1099,6 +1106,9 @@ int bofi_create(const bofi_config_t* cfg, int device, bofi_handle_t* out) {
   e->use_graph = !(gg && strcmp(gg, "0") == 0);
   const char* gp = getenv("BOFI_PDL");
   if (gp) pdl_enabled() = strcmp(gp, "0") != 0;
+  const char* gl = getenv("BOFI_LNFUSE");
+  e->ln_fuse = (gl && strcmp(gl, "1") == 0);
+  if (const char* gm = getenv("BOFI_LNFUSE_MIN")) e->ln_fuse_min_rows = atoi(gm);
   const char* gs = getenv("BOFI_SAIC");
   e->saic_full = (gs && strcmp(gs, "full") == 0);
   const char* ga = getenv("BOFI_ATTN");
