@@ -33,7 +33,7 @@ __device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
 
 // KT = number of 16-key tiles (Tk <= 16*KT).
 template <int KT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, KT <= 3 ? 8 : 1)     // short key ranges: cap registers at 64 so that eight CTAs share an SM
 attention_mma_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restrict__ K, const bf16* __restrict__ V, int ldkv,
                      bf16* __restrict__ O, int ldo, int Tq, int Tk, const int* __restrict__ vis, int vis_bs, int vis_qs,
                      int vis_div, int kv_div, float scale, const int* live_rows, Drop drop) {
