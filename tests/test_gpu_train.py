@@ -246,3 +246,32 @@ def test_xe_extreme_phrase_structures_fp32():
     # a ReLU pre-activation within rounding of zero can land on different sides in the two implementations and switch
     # one hidden unit's gradient path: allow isolated entries (2e-2 of the tensor's largest), keep the direction tight
     assert worst < 2e-2 and cos > 0.99999, (worst, name, cos)
+
+
+def test_xe_gradient_is_additive_over_images_bf16():
+    """Size-independent property at a larger batch (64 images x 5 captions, tensor-core path): the criterion is a sum
+    over caption rows divided by the batch's word count, so  D * g(batch) == D_a * g(half a) + D_b * g(half b)."""
+    B, R = 64, 36
+    model, cfg = build_model("bf16")
+    fc, att, _ = synth.synth_inputs(B, R, seed=21)
+    bt = synth.synth_xe_batch(B, seed=31, vocab_size=cfg.vocab_size)
+    keys = ("labels", "phrase_num", "phrase_length", "phrase_syn", "extend_phrase_syn_seq", "extend_phrase_seq", "extend_phrase_seq_mask")
+
+    def run(lo, hi):
+        sub = {k: bt[k][lo:hi].cuda() for k in keys}
+        model.zero_grad()
+        losses = model.xe_step(fc[lo:hi].cuda(), att[lo:hi].cuda(), sub["labels"], None, sub["phrase_num"], sub["phrase_length"],
+                               sub["phrase_syn"], sub["extend_phrase_syn_seq"], sub["extend_phrase_seq"], sub["extend_phrase_seq_mask"])
+        words = float((bt["phrase_length"][lo:hi].sum(-1) - 1).sum())
+        return model.flat_grads().double().clone() * words, float(losses[0]) * words
+
+    model.train_bind()
+    g_all, l_all = run(0, B)
+    g_a, l_a = run(0, B // 2)
+    g_b, l_b = run(B // 2, B)
+    assert abs(l_all - (l_a + l_b)) < 2e-3 * abs(l_all)
+    got, want = g_all, g_a + g_b
+    cos = float((got @ want) / (got.norm() * want.norm()))
+    rel = float((got - want).norm() / want.norm())
+    print("XE additivity: cosine %.6f, relative L2 difference %.4f" % (cos, rel))
+    assert cos > 0.999 and rel < 0.05
