@@ -138,7 +138,7 @@ struct bofi_engine {
   DevBuf tab_y, tab_qkv;               // N_len == 1: LN + QKV of every (syn, position) bounding input row
   bool bound_fast = false;             // [LEN]-row-only bounding step (NAIC, N_len == 1)
   // workspace
-  DevBuf attT, x, y, qkv, ao, q, ffh, memT, attlen, hrow, hid, logits, state_i32, tok;
+  DevBuf attT, x, y, qkv, ao, q, ffh, memT, attlen, logits, state_i32, tok;
   std::vector<DevBuf> kv;              // cross K/V per bounding layer then per decoder layer
   DevBuf h_in, h_len, h_seq, h_logp, h_pnum, h_plen, h_psyn;   // device staging of the *_host entry point
   DevBuf unit_a, unit_w, unit_o;
@@ -541,8 +541,6 @@ static int reserve_decode(bofi_engine* e, int B, int R, int sn) {
   RC_TRY(e->ao.reserve(dr * kD * ts));
   RC_TRY(e->q.reserve(dr * kD * ts));
   RC_TRY(e->ffh.reserve(dr * e->cfg.d_ff * ts));
-  RC_TRY(e->hrow.reserve(rows * kD * 4));
-  RC_TRY(e->hid.reserve(rows * 200 * 4));
   RC_TRY(e->logits.reserve(rows * e->L * (size_t)e->Vpad * 4));
   RC_TRY(e->tok.reserve(rows * e->L * 4));
   const int nkv = std::max(1, e->cfg.n_len) + e->cfg.n_dec;
@@ -1134,7 +1132,7 @@ int bofi_destroy(bofi_handle_t e) {
   e->flat16.release();
   for (DevBuf& b : e->kv) b.release();
   DevBuf* all[] = {&e->bound_in, &e->fill_in, &e->attT, &e->x, &e->y, &e->qkv, &e->ao, &e->q, &e->ffh, &e->memT, &e->attlen,
-                   &e->sa_mx, &e->sa_lse, &e->sa_cidx, &e->sa_cache, &e->sa_bcache, &e->sa_qkv0, &e->sa_x0, &e->head1t, &e->tab_y, &e->tab_qkv, &e->hrow, &e->hid, &e->logits, &e->state_i32, &e->tok, &e->h_in, &e->h_len, &e->h_seq, &e->h_logp,
+                   &e->sa_mx, &e->sa_lse, &e->sa_cidx, &e->sa_cache, &e->sa_bcache, &e->sa_qkv0, &e->sa_x0, &e->head1t, &e->tab_y, &e->tab_qkv, &e->logits, &e->state_i32, &e->tok, &e->h_in, &e->h_len, &e->h_seq, &e->h_logp,
                    &e->h_pnum, &e->h_plen, &e->h_psyn, &e->unit_a, &e->unit_w, &e->unit_o};
   for (DevBuf* b : all) b->release();
   delete e;
@@ -1180,7 +1178,7 @@ int64_t bofi_workspace_bytes(bofi_handle_t e, int32_t B, int32_t R, int32_t sn) 
   if (e->bf16_mode) t += M * e->cfg.att_feat_size * ts;
   t += dr * kD * 4 + dr * kD * ts * 3 + dr * 3 * kD * ts + dr * e->cfg.d_ff * ts + M * kD * ts;
   t += (int64_t)(std::max(1, e->cfg.n_len) + e->cfg.n_dec) * M * 2 * kD * ts;
-  t += rows * e->L * (int64_t)e->Vpad * 4 + rows * (kD + 200) * 4 + (int64_t)state_ints((int)rows, e->Lb, e->L) * 4;
+  t += rows * e->L * (int64_t)e->Vpad * 4 + (int64_t)state_ints((int)rows, e->Lb, e->L) * 4;
   return t + t / 8;
 }
 
