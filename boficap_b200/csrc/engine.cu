@@ -21,6 +21,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_ln_tc.cuh"
+#include "gemm_tc2.cuh"
 #include "kernels.cuh"
 #include "attention_mma.cuh"
 #include "train_kernels.cuh"
@@ -112,6 +113,7 @@ struct bofi_engine {
   int Lb = 22, L = 20, V = 0, Vpad = 0;
   bool bf16_mode = false;
   bool use_tc = true;
+  bool gemm2 = false;                  // BOFI_GEMM2=1: 2-CTA (cta_group::2) tiles for the wide GEMMs
   int ln_fuse_min_rows = 4096;         // below this the panel LayerNorm would be repeated by too many CTAs
   bool ln_fuse = false;                // BOFI_LNFUSE=1: LayerNorm fused into the consuming tcgen05 GEMM (gemm_ln_tc.cuh; measured slower, off)
   bool attn_simt_only = false;         // BOFI_ATTN=simt: generic FFMA attention kernel everywhere
@@ -284,7 +286,9 @@ static int linear(bofi_engine* e, cudaStream_t s, const T* A, int lda, const Lin
                  (double)sizeof(T) * ((double)M * l.K + (double)l.N * l.K) + (double)sizeof(TOut) * M * l.N + (resid ? 4.0 * M * l.N : 0.0),
                  M, l.N, l.K);
   if constexpr (std::is_same<T, bf16>::value) {
-    if (e->use_tc)
+    if (e->use_tc && e->gemm2 && M >= 2048 && l.N >= 512)
+      err = tc::gemm_tc2<TOut>(s, A, lda, l.w16, l.K, l.b, resid, ldr, out, ldc, M, l.N, l.K, relu, live, e->rows_dev);
+    else if (e->use_tc)
       err = tc::gemm_tc<TOut>(s, A, lda, l.w16, l.K, l.b, resid, ldr, out, ldc, M, l.N, l.K, relu, live, e->rows_dev);
     else
       err = gemm_simt<bf16, TOut>(s, A, lda, l.w16, l.K, l.b, resid, ldr, out, ldc, M, l.N, l.K, relu, live, e->rows_dev);
@@ -1104,6 +1108,8 @@ int bofi_create(const bofi_config_t* cfg, int device, bofi_handle_t* out) {
   e->use_graph = !(gg && strcmp(gg, "0") == 0);
   const char* gp = getenv("BOFI_PDL");
   if (gp) pdl_enabled() = strcmp(gp, "0") != 0;
+  const char* g2 = getenv("BOFI_GEMM2");
+  e->gemm2 = (g2 && strcmp(g2, "1") == 0);
   const char* gl = getenv("BOFI_LNFUSE");
   e->ln_fuse = (gl && strcmp(gl, "1") == 0);
   if (const char* gm = getenv("BOFI_LNFUSE_MIN")) e->ln_fuse_min_rows = atoi(gm);

@@ -1,0 +1,383 @@
+// 2-CTA tcgen05 GEMM (cta_group::2):  C[M,N] = act(A[M,K] . W[N,K]^T + bias) (+ residual) on 256 x 256 tile pairs.
+//
+// profiles/r01c_gemm_ncu_summary.txt: the K = 512 projections are bound by shared-memory FILL (13.5 TB/s of L2->SM traffic,
+// tensor pipe 58 %): a 128 x 256 tile re-loads 16 KB of A and 32 KB of W per 64-deep k-block.  A CTA pair (two SMs of a
+// TPC, cluster 2x1x1) shares the W tile: each CTA loads its own 128 rows of A and only HALF of W (16 + 16 KB), the
+// leader's single thread issues tcgen05.mma.cta_group::2 (M = 256) which reads W from both CTAs' shared memory, and
+// each SM's tensor core accumulates its 128 rows x 256 columns in its own TMEM.  Fill per MMA flop drops by a third and
+// the ring gets two more stages.  Barrier wiring:
+//   full[s]        leader only: expect_tx of BOTH CTAs' bytes; both CTAs' TMA loads (.cta_group::2) complete on it
+//   empty[s]       per CTA, released by the leader's commit with cluster multicast (frees the stage in both CTAs)
+//   tmem_full[a]   per CTA, multicast commit; tmem_empty[a]: leader's barrier, 16 arrivals (8 epilogue warps x 2 CTAs)
+// Epilogue as in gemm_tc.cuh (8 warps per CTA drain their own 128 TMEM lanes).  K-major operands only.
+//
+// MEASURED RESULT (B200, B=1024 decode): numerically identical to gemm_tc.cuh (unit errors ~3e-6 against fp32), L2->SM
+// traffic per launch down by a third -- and the same speed (FFN1 M=36864 N=2048 K=512: 74-77 us vs 73 us; Q|K|V 57-60 us vs
+// 58 us), with 5 or 6 ring stages and with one or two staging tiles per epilogue warp.  Shared-memory fill is therefore
+// NOT what holds these shapes at ~1050 TFLOP/s (64 % of the measured cuBLAS bf16 rate); the remaining suspects are the
+// per-tile epilogue (128 x 256 outputs drained through tcgen05.ld -> st.shared -> TMA store while the next tile's 8
+// k-blocks take only ~3 us) and TMA load latency against the ring depth.  Opt-in (BOFI_GEMM2=1) until it wins.
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace bofi {
+namespace tc {
+
+constexpr int k2BN = 256;
+constexpr int k2Stages = 5;
+struct Smem2 {
+  static constexpr int kABytes = kBM * kBK * 2;                    // 16 KB: this CTA's rows of A
+  static constexpr int kBBytes = (k2BN / 2) * kBK * 2;             // 16 KB: this CTA's half of W
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kOutOffset = k2Stages * kStageBytes;
+  static constexpr int kOutBytes = 8 * 2 * 4096;                   // two staging tiles per epilogue warp
+  static constexpr int kBarOffset = kOutOffset + kOutBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;
+};
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load issued by either CTA of the pair; the completion bytes go to the barrier of the pair's CTA 0 (peer bit clear)
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(tmap), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(cta)
+      : "memory");
+}
+
+template <typename TOut, bool RELU, bool RESID>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, const float* residual, int ldr,
+               int M, int N, int K, int relu, const int* live_rows, const int* rows_dev) {
+  pdl_launch();
+  constexpr int BN = k2BN, STAGES = k2Stages;
+  constexpr bool A_MN = false, B_MN = false, REDUCE = false;
+  using L = Smem2;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* full_bar = bars;                      // [STAGES]  TMA -> MMA
+  uint64_t* empty_bar = bars + STAGES;            // [STAGES]  MMA -> TMA
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;    // [2]       MMA -> epilogue
+  uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;   // [2]   epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nk_all = (K + kBK - 1) / kBK;      // a K tail is zero-filled by TMA (out-of-bounds box elements)
+  const int nk_per = nk_all;
+  const int tiles_n = (N + BN - 1) / BN;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(smem_u32(&full_bar[s]), 1);
+        mbar_init(smem_u32(&empty_bar[s]), 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(smem_u32(&tmem_full_bar[a]), 1);
+        mbar_init(smem_u32(&tmem_empty_bar[a]), 16);  // one arrival per epilogue warp of BOTH CTAs (only the leader's is used)
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();                              // barriers of both CTAs initialised, TMEM allocated on both SMs
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // Everything above (barriers, TMEM, descriptor prefetch) overlaps the tail of the previous kernel; global
+  // memory is only touched after the programmatic-dependency wait.  A dead bounding step walks zero tiles.
+  pdl_wait();
+  // rows_dev: the number of valid A rows lives on the device (compacted SAIC step); tiles beyond it are skipped
+  const int m_eff = rows_dev ? min(M, *rows_dev) : M;
+  const int ntiles_mn = ((m_eff + 2 * kBM - 1) / (2 * kBM)) * tiles_n;     // 256-row tile pairs
+  const int ntiles = step_is_dead(live_rows) ? 0 : ntiles_mn;
+  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;                  // cluster id / number of clusters
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int item = cid; item < ntiles; item += ncl) {
+        const int tile = item % ntiles_mn, kb0 = (item / ntiles_mn) * nk_per, kb1 = min(nk_all, kb0 + nk_per);
+        const int m0 = (tile / tiles_n) * 2 * kBM + (int)rank * kBM, n0 = (tile % tiles_n) * BN;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+          // both CTAs' loads complete on the LEADER's full barrier (cta_group::2 TMA: barrier address with the peer bit
+          // clear); the leader announces the bytes of the pair
+          const uint32_t fb = smem_u32(&full_bar[s]);
+          if (rank == 0) mbar_expect_tx(fb, 2 * L::kStageBytes);
+          const uint32_t a_dst = smem_u32(smem + s * L::kStageBytes);
+          tma_load_2d_2sm(a_dst, &tmA, fb, kb * kBK, m0);                                   // this CTA's 128 rows of A
+          tma_load_2d_2sm(a_dst + L::kABytes, &tmB, fb, kb * kBK, n0 + (int)rank * (BN / 2));   // this CTA's half of W
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * kBM, BN, A_MN, B_MN);
+      int it = 0, t = 0;
+      for (int item = cid; item < ntiles; item += ncl, ++t) {
+        const int kb0 = (item / ntiles_mn) * nk_per, kb1 = min(nk_all, kb0 + nk_per);
+        const int as = t & 1;
+        const uint32_t aph = (t >> 1) & 1;
+        mbar_wait(smem_u32(&tmem_empty_bar[as]), aph ^ 1);     // epilogue drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(smem_u32(&full_bar[s]), ph);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
+          const uint64_t adesc = A_MN ? make_sw128_desc_mn(a_addr) : make_sw128_desc(a_addr);
+          const uint64_t bdesc = B_MN ? make_sw128_desc_mn(a_addr + L::kABytes) : make_sw128_desc(a_addr + L::kABytes);
+          // per K step of 16: K-major +32 bytes inside the 128-byte swizzle row; MN-major +16 rows of 128 bytes (encoded >> 4)
+          constexpr uint64_t a_step = A_MN ? 128 : 2, b_step = B_MN ? 128 : 2;
+#pragma unroll
+          for (int k = 0; k < kBK / kUK; ++k) {
+            umma_bf16_2sm(tmem_d, adesc + a_step * k, bdesc + b_step * k, idesc, ((kb - kb0) | k) != 0);
+          }
+          umma_commit_2sm(smem_u32(&empty_bar[s]));      // frees the stage in BOTH CTAs when these MMAs retire
+        }
+        umma_commit_2sm(smem_u32(&tmem_full_bar[as]));   // accumulator complete: both CTAs' epilogues
+      }
+    }
+  } else {
+    // Epilogue: TMEM -> registers (one accumulator row per thread) -> bias / ReLU / residual -> swizzled smem
+    // staging tile (32 rows x 128 B) -> TMA store.  Full-line coalesced writes, M / N tails clipped by the
+    // tensor map.  Eight warps: warp `quad + 4*half + 2` owns TMEM lanes [32*quad, +32) and the column chunks
+    // c = half, half + 2, ...
+    constexpr int CC = 128 / (int)sizeof(TOut);      // output columns per 128-byte staging row
+    const int quad = warp & 3;                       // TMEM lanes [32*quad, 32*quad+32)
+    const int half = (warp - 2) >> 2;
+    // two staging tiles per warp: the TMA engine is shared with the operand loads, so a store can sit in its queue for a
+    // while; waiting for the PREVIOUS store (not the one before it) stalled the epilogue (36 % of the kernel's stall samples)
+    const uint32_t sbuf0 = smem_u32(smem + L::kOutOffset + (warp - 2) * 8192);
+    int nstore = 0;
+    int t = 0;
+    for (int item = cid; item < ntiles; item += ncl, ++t) {
+      const int tile = item % ntiles_mn;
+      const int m0 = (tile / tiles_n) * 2 * kBM + (int)rank * kBM, n0 = (tile % tiles_n) * BN;
+      const int as = t & 1;
+      const uint32_t aph = (t >> 1) & 1;
+      const int row = m0 + quad * 32 + lane;
+      const bool row_ok = row < M;
+      constexpr int NC = BN / CC;
+      constexpr int NI = (NC + 1) / 2;                          // chunks per warp
+      // The residual does not depend on the accumulator: fetch this warp's first chunk before waiting for the MMAs and
+      // keep the next one in flight while a chunk drains.  Loads are COALESCED (lane l reads 16 bytes of row
+      // j*4 + l/8 at column chunk l%8: every warp instruction covers four whole 128-byte lines) and are transposed to
+      // the row-per-thread layout through the warp's swizzled staging tile.
+      constexpr int RV = RESID ? 8 : 1;                         // residual only exists on the fp32-output path
+      float4 res[2][RV];
+      auto fetch_res = [&](float4 (&dst)[RV], int c) {
+        if constexpr (RESID) {
+          const int n = n0 + c * CC;
+          if (c < NC && n + CC <= N) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int rr = m0 + quad * 32 + j * 4 + (lane >> 3);
+              dst[j] = (rr < M) ? *reinterpret_cast<const float4*>(residual + (size_t)rr * ldr + n + 4 * (lane & 7))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+        }
+      };
+      fetch_res(res[0], half);
+      mbar_wait(smem_u32(&tmem_full_bar[as]), aph);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const int c = half + 2 * i;
+        const int n = n0 + c * CC;
+        if (c >= NC || n >= N) break;                 // warp-uniform
+        fetch_res(res[(i + 1) & 1], c + 2);
+        const bool full = (n + CC <= N);              // warp-uniform
+        const uint32_t sbuf = sbuf0 + (uint32_t)(nstore & 1) * 4096u;
+        const uint32_t srow = sbuf + (uint32_t)lane * 128u;
+        float4 bb[CC / 4];
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < CC / 4; ++j) bb[j] = *reinterpret_cast<const float4*>(bias + n + 4 * j);
+        }
+        uint32_t r[CC];
+        {
+          uint32_t(&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
+          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + c * CC), r0);
+          if constexpr (CC == 64) {
+            uint32_t(&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
+            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + c * CC + 32), r1);
+          }
+        }
+        if constexpr (RESID) {
+          if (full) {
+            // transpose the coalesced residual registers into this thread's row through the staging tile
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int rl = j * 4 + (lane >> 3);
+              const float4 v = res[i & 1][j];
+              st_shared_v4(sbuf + (uint32_t)rl * 128u + (uint32_t)(((lane & 7) ^ (rl & 7)) * 16), __float_as_uint(v.x), __float_as_uint(v.y),
+                           __float_as_uint(v.z), __float_as_uint(v.w));
+            }
+            __syncwarp();
+          }
+        }
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < CC; j += 4) {
+            float4 x = make_float4(__uint_as_float(r[j]) + bb[j / 4].x, __uint_as_float(r[j + 1]) + bb[j / 4].y,
+                                   __uint_as_float(r[j + 2]) + bb[j / 4].z, __uint_as_float(r[j + 3]) + bb[j / 4].w);
+            if constexpr (RELU) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+            if constexpr (RESID) {
+              const float4 rr = ld_shared_v4(srow + (uint32_t)(((j / 4) ^ (lane & 7)) * 16));
+              x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
+            }
+            r[j] = __float_as_uint(x.x); r[j + 1] = __float_as_uint(x.y);
+            r[j + 2] = __float_as_uint(x.z); r[j + 3] = __float_as_uint(x.w);
+          }
+        } else {
+          // N tail (only the last column tile of the vocab projection): guarded scalar path
+#pragma unroll
+          for (int j = 0; j < CC; ++j) {
+            float x = 0.f;
+            if (n + j < N) {
+              x = __uint_as_float(r[j]) + bias[n + j];
+              if constexpr (RELU) x = fmaxf(x, 0.f);
+              if constexpr (RESID) { if (row_ok) x += residual[(size_t)row * ldr + n + j]; }
+            }
+            r[j] = __float_as_uint(x);
+          }
+        }
+        // this warp's staging tile must have been read out by the TMA engine (its previous store); on the residual path
+        // every lane must also be done reading its residual row before the tile is overwritten
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        if constexpr (CC == 32) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            st_shared_v4(srow + (uint32_t)((j ^ (lane & 7)) * 16), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            st_shared_v4(srow + (uint32_t)((j ^ (lane & 7)) * 16),
+                         pack_bf16(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1])),
+                         pack_bf16(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])),
+                         pack_bf16(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])),
+                         pack_bf16(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmC, sbuf, n, m0 + quad * 32);
+        }
+        ++nstore;
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(smem_u32(&tmem_empty_bar[as]), 0);     // the leader's MMA thread waits for both CTAs
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncwarp();
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();                              // the peer may still be reading / the leader's MMAs still reading peer smem
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+  }
+}
+
+
+template <typename TOut, bool RELU, bool RESID>
+inline cudaError_t launch2(cudaStream_t s, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const float* bias,
+                           const float* residual, int ldr, int M, int N, int K, int relu, const int* live_rows, const int* rows_dev) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<TOut, RELU, RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2::kTotal);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int pairs = ((M + 2 * kBM - 1) / (2 * kBM)) * ((N + k2BN - 1) / k2BN);
+  int clusters = num_sms() / 2;
+  if (pairs < clusters) clusters = pairs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Smem2::kTotal;
+  cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<TOut, RELU, RESID>, tmA, tmB, tmC, bias, residual, ldr, M, N, K, relu, live_rows, rows_dev);
+}
+
+// Same contract as gemm_tc (K-major A [M,K], W [N,K]).
+template <typename TOut>
+inline cudaError_t gemm_tc2(cudaStream_t s, const bf16* A, int lda, const bf16* W, int ldw, const float* bias, const float* residual, int ldr,
+                            TOut* C, int ldc, int M, int N, int K, int relu, const int* live_rows, const int* rows_dev) {
+  if (M <= 0 || N <= 0) return cudaSuccess;
+  if (lda % 8 != 0 || ldw % 8 != 0 || (ldc * sizeof(TOut)) % 16 != 0 || (residual && ldr % 4 != 0) || !bias) return cudaErrorInvalidValue;
+  const CUtensorMap* tmA = cached_tmap(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBM);
+  const CUtensorMap* tmB = cached_tmap(W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, k2BN / 2);
+  const CUtensorMap* tmC = cached_tmap(C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, (int)sizeof(TOut));
+  if (!tmA || !tmB || !tmC) return cudaErrorInvalidValue;
+#define BOFI_TC2(RELU_, RESID_) launch2<TOut, RELU_, RESID_>(s, *tmA, *tmB, *tmC, bias, residual, ldr, M, N, K, relu, live_rows, rows_dev)
+  if constexpr (sizeof(TOut) == 4) {
+    if (residual && relu) return cudaErrorInvalidValue;
+    if (residual) return BOFI_TC2(false, true);
+    if (relu) return BOFI_TC2(true, false);
+    return BOFI_TC2(false, false);
+  } else {
+    if (residual) return cudaErrorInvalidValue;
+    if (relu) return BOFI_TC2(true, false);
+    return BOFI_TC2(false, false);
+  }
+#undef BOFI_TC2
+}
+
+}  // namespace tc
+}  // namespace bofi
