@@ -143,3 +143,42 @@ def test_attention_single_query_fp32(engines, Tk):
     vis = torch.randint(1, Tk + 1, (B, 1), generator=g).int()
     out = e32.attention(q.cuda(), k.cuda(), v.cuda(), vis.cuda()).cpu()
     assert (out - _attention_reference(q, k, v, vis)).abs().max().item() < 2e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env", ["BOFI_GEMM2", "BOFI_LNFUSE"])
+def test_optional_gemm_variants_reproduce_the_default_path(env, monkeypatch):
+    """The opt-in tcgen05 variants (2-CTA tiles, LayerNorm-fused A-resident GEMM) must give the default bf16 path's
+    results: same boxes, logits within bf16 rounding of the LayerNorm output."""
+    import torch
+    from boficap_b200 import synth
+    from boficap_b200.engine import BofiEngine
+    from boficap_b200.layout import BofiConfig
+    cfg = BofiConfig()
+    sd = synth.synth_state_dict(cfg, 0, "s_real")
+    fc, att_all, _ = synth.synth_inputs(2304, 36, seed=8)      # M >= 73k encoder rows: the wide-tile paths are taken
+    att_all = att_all.cuda()
+
+    def run(att):
+        eng = BofiEngine(cfg, 0, "bf16").load_state_dict(sd)
+        eng.encode(att, None)
+        out = [t.clone() for t in eng.decode("NAIC", 1, 0, True)]
+        eng.close()
+        return out
+
+    monkeypatch.delenv(env, raising=False)
+    for B in range(2048, 2304):                                # end the batch on an image that predicts a phrase (no NaN batch)
+        base = run(att_all[:B])
+        if not bool(base[1].isnan().any()):
+            break
+    else:
+        raise AssertionError("no usable batch")
+    monkeypatch.setenv(env, "1")
+    monkeypatch.setenv("BOFI_LNFUSE_MIN", "1")
+    var = run(att_all[:B])
+    same = (base[3] == var[3]).all(1)
+    assert float(same.float().mean()) > 0.95
+    a, b = base[1][same], var[1][same]
+    assert not bool(b.isnan().any())
+    err = float((a - b).abs().max())
+    assert err < (1e-5 if env == "BOFI_GEMM2" else 2e-2), err
