@@ -1062,7 +1062,7 @@ static void train_release(bofi_engine* e) {
   if (!e->train) return;
   TrainState& t = e->train->st;
   t.arena.release();
-  DevBuf* all[] = {&t.tr_a, &t.tr_b, &t.tr_w, &t.zeros, &t.ln_partial, &t.cs_partial, &t.scratch_f32, &t.dkv, &t.dmem, &t.zbuf};
+  DevBuf* all[] = {&t.tr_a, &t.tr_b, &t.tr_w, &t.zeros, &t.ln_partial, &t.cs_partial, &t.cs_tickets, &t.scratch_f32, &t.dkv, &t.dmem, &t.zbuf};
   for (DevBuf* b : all) b->release();
   delete e->train;
   e->train = nullptr;

@@ -95,7 +95,7 @@ struct TrainState {
   std::vector<void*> kv;          // [B*R, 1024] per bounding / decoder layer
   BoundTape sa_b, na_b;
   DecTape sa_d, na_d;
-  DevBuf tr_a, tr_b, tr_w, zeros, ln_partial, cs_partial, scratch_f32, dkv, dmem, zbuf;
+  DevBuf tr_a, tr_b, tr_w, zeros, ln_partial, cs_partial, cs_tickets, scratch_f32, dkv, dmem, zbuf;
   // Dropout (train() mode of the reference): p_sub = opt.dropout at every sub-layer output, attention probability,
   // FFN hidden, positional encoding and head hidden; p_att = opt.drop_prob_lm after att_embed's ReLU.  Sites are numbered
   // in forward order from 0 every step; key(site) = drop_hash(seed, site); the backward pass reuses the keys.
@@ -429,14 +429,13 @@ static int colsum(bofi_engine* e, cudaStream_t s, TrainState* ts, const T* dY, i
   const int col_blocks = ceil_div(cols4, 256);
   const int chunks = std::max(1, std::min(std::min(64, M / 64), (4 * 148) / col_blocks));
   RC_TRY(ts->cs_partial.reserve((size_t)chunks * cols4 * 4));
+  if (ts->cs_tickets.cap == 0) {
+    RC_TRY(ts->cs_tickets.reserve(256 * 4));
+    CU_TRY(cudaMemsetAsync(ts->cs_tickets.p, 0, 256 * 4, s));
+  }
   {
     ProfScope prof(e, s, PC_OTHER, 0.0, (double)M * N * sizeof(T));
-    launch_k(colsum_partial_kernel<T>, dim3(col_blocks, chunks), 512, 0, s, dY, ldy, M, cols4, ts->cs_partial.as<float>());
-  }
-  CU_TRY(cudaGetLastError());
-  {
-    ProfScope prof(e, s, PC_OTHER, 0.0, 0.0);
-    launch_k(colsum_reduce_kernel, ceil_div(N, 256), 256, 0, s, (const float*)ts->cs_partial.as<float>(), chunks, N, cols4, gb);
+    launch_k(colsum_kernel<T>, dim3(col_blocks, chunks), 512, 0, s, dY, ldy, M, N, cols4, ts->cs_partial.as<float>(), ts->cs_tickets.as<int>(), gb);
   }
   CU_TRY(cudaGetLastError());
   return BOFI_OK;

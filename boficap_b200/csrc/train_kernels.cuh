@@ -360,14 +360,17 @@ __global__ void transpose_pad_kernel(const TIn* __restrict__ in, int ld_in, TOut
   }
 }
 
-// Bias gradients gb[c] += sum_r dY[r, c] in two fixed-order stages:
-//   partial[chunk, c] = sum over the rows of the chunk (CTA = 256 columns x 8 row lanes, 8-byte / 16-byte loads of 4
-//   columns per thread), then a sum over chunks.  `cols4` = columns rounded up to 4 (pad columns of dY are zero).
+// Bias gradients gb[c] += sum_r dY[r, c], one launch, fixed summation order:
+//   every CTA (256 columns x one row chunk; 8 row lanes, 8- / 16-byte loads of 4 columns per thread) writes its partial
+//   sums; the LAST CTA of a column block to finish (ticket counter, self-resetting) adds the chunk partials in chunk order.
+// `cols4` = columns rounded up to 4 (pad columns of dY are zero).
 template <typename T>
 __global__ void __launch_bounds__(512)
-colsum_partial_kernel(const T* __restrict__ dY, int ld, int rows, int cols4, float* __restrict__ partial) {
+colsum_kernel(const T* __restrict__ dY, int ld, int rows, int cols, int cols4, float* __restrict__ partial, int* __restrict__ tickets,
+              float* __restrict__ out) {
   pdl_enter();
   __shared__ float4 part[8][64];
+  __shared__ int s_last;
   const int cg = threadIdx.x & 63, ry = threadIdx.x >> 6;
   const int c = (blockIdx.x * 64 + cg) * 4;
   const int per = (rows + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
@@ -393,16 +396,20 @@ colsum_partial_kernel(const T* __restrict__ dY, int ld, int rows, int cols4, flo
     for (int i = 1; i < 8; ++i) { t.x += part[i][cg].x; t.y += part[i][cg].y; t.z += part[i][cg].z; t.w += part[i][cg].w; }
     store4(partial + (size_t)blockIdx.y * cols4 + c, t);
   }
-}
-__global__ void __launch_bounds__(256)
-colsum_reduce_kernel(const float* __restrict__ partial, int chunks, int cols, int cols4, float* __restrict__ out) {
-  pdl_enter();
-  const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c >= cols) return;
-  float t = 0.f;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&tickets[blockIdx.x], 1) == (int)gridDim.y - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int col = blockIdx.x * 256 + threadIdx.x;
+  if (threadIdx.x < 256 && col < cols) {
+    float t = 0.f;
 #pragma unroll 8
-  for (int i = 0; i < chunks; ++i) t += partial[(size_t)i * cols4 + c];
-  out[c] += t;
+    for (int i = 0; i < (int)gridDim.y; ++i) t += __ldcg(partial + (size_t)i * cols4 + col);
+    out[col] += t;
+  }
+  if (threadIdx.x == 0) tickets[blockIdx.x] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
