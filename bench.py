@@ -131,6 +131,7 @@ def bench_xe(a, rank, local_rank, world):
     from boficap_b200 import synth
     from boficap_b200.captioning import models
     from boficap_b200.layout import BofiConfig
+    from boficap_b200.parallel import allreduce_gradients
     cfg = BofiConfig()
     B = 256 if a.batch == 1024 else a.batch
     R, spi = a.regions, 5
@@ -158,8 +159,7 @@ def bench_xe(a, rank, local_rank, world):
         flat_g.zero_()
         losses = model.xe_step(*args)
         if dist is not None:
-            dist.all_reduce(flat_g)
-            flat_g.div_(world)
+            allreduce_gradients(model)
         optim.step()
         eng.refresh_weights()
         return losses

@@ -1185,6 +1185,8 @@ int64_t bofi_workspace_bytes(bofi_handle_t e, int32_t B, int32_t R, int32_t sn) 
   t += dr * kD * 4 + dr * kD * ts * 3 + dr * 3 * kD * ts + dr * e->cfg.d_ff * ts + M * kD * ts;
   t += (int64_t)(std::max(1, e->cfg.n_len) + e->cfg.n_dec) * M * 2 * kD * ts;
   t += rows * e->L * (int64_t)e->Vpad * 4 + (int64_t)state_ints((int)rows, e->Lb, e->L) * 4;
+  // SAIC (incremental): per-layer K|V caches of the decoder slots and of the bounding slots, compact index, per-slot stats
+  t += (int64_t)e->cfg.n_dec * rows * e->L * 2 * kD * ts + rows * e->Lb * 2 * kD * ts + rows * e->L * 12;
   return t + t / 8;
 }
 

@@ -48,3 +48,13 @@ def sample_sharded(decode_fn, att_feats, att_masks=None, group=None):
     if local is None:
         raise ValueError("a rank received an empty shard (batch smaller than world size)")
     return gather_captions(local, att_feats.shape[0], group)
+
+
+def allreduce_gradients(model, group=None, average=True):
+    """Data-parallel XE training: ONE all-reduce of the flat gradient buffer the parameters' `.grad`s are views of
+    (TransformerModel.train_bind), instead of one collective per parameter tensor."""
+    flat = model.flat_grads()
+    dist.all_reduce(flat, group=group)
+    if average:
+        flat.div_(dist.get_world_size(group))
+    return flat
