@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libbofi_b200.so")
+# BOFI_LIB_PATH: load another build of the same ABI (the stall-counter build of tools/gemm_stalls.py)
+LIB_PATH = os.environ.get("BOFI_LIB_PATH") or os.path.join(_HERE, "lib", "libbofi_b200.so")
 
 ABI_VERSION = 1
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NOMEM = 0, 1, 2, 3, 4

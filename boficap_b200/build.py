@@ -25,13 +25,18 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in DEPS)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+PROF_OUT = os.path.join(HERE, "lib", "libbofi_b200_prof.so")
+
+
+def build(force=False, verbose=False, prof=False):
+    """prof=True builds lib/libbofi_b200_prof.so with the GEMM stall counters compiled in (-DBOFI_GEMM_PROF);
+    it is only ever loaded when BOFI_LIB_PATH points at it (tools/gemm_stalls.py)."""
+    if not prof and not force and not needs_build():
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    out = PROF_OUT if prof else OUT
     cmd = [nvcc_path(), "-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
-           "-shared", "-Xcompiler", "-fPIC",
-           "-o", OUT, SRC]
+           "-shared", "-Xcompiler", "-fPIC"] + (["-DBOFI_GEMM_PROF"] if prof else []) + ["-o", out, SRC]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -40,8 +45,8 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed")
     if verbose:
         print(r.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, prof="--prof" in sys.argv))

@@ -1075,6 +1075,18 @@ extern "C" {
 
 const char* bofi_last_error(void) { return g_err; }
 int bofi_abi_version(void) { return BOFI_ABI_VERSION; }
+#ifdef BOFI_GEMM_PROF
+// Profiling build only (not part of include/bofi_b200.h): the tcgen05 GEMM's stall counters, 8 shape classes x 8.
+int bofi_debug_gemm_prof(unsigned long long* out64, int reset) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return BOFI_ERR_CUDA;
+  if (out64 && cudaMemcpyFromSymbol(out64, tc::g_gemm_prof, sizeof(unsigned long long) * 64) != cudaSuccess) return BOFI_ERR_CUDA;
+  if (reset) {
+    static const unsigned long long zeros[64] = {0};
+    if (cudaMemcpyToSymbol(tc::g_gemm_prof, zeros, sizeof(zeros)) != cudaSuccess) return BOFI_ERR_CUDA;
+  }
+  return BOFI_OK;
+}
+#endif
 
 int bofi_create(const bofi_config_t* cfg, int device, bofi_handle_t* out) {
   if (!cfg || !out) return fail(BOFI_ERR_INVALID, "null argument");

@@ -51,6 +51,29 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
+// ---- optional in-kernel stall accounting (build with -DBOFI_GEMM_PROF, `python -m boficap_b200.build --prof`) ----
+// Per shape class (see prof_bucket) the roles add up where their cycles go: the MMA thread's waits on operands
+// (full) and on the epilogue (tmem_empty), the TMA thread's waits on free stages, one epilogue warp's waits on the
+// accumulator and on its staging tile.  Compiled out of the product library.
+#ifdef BOFI_GEMM_PROF
+__device__ unsigned long long g_gemm_prof[8][8];
+__device__ __forceinline__ int prof_bucket(int N, int K, bool resid) {
+  if (K == 512 && N == 2048) return 0;      // FFN1
+  if (K == 2048) return 1;                  // FFN2
+  if (K == 512 && N == 512) return resid ? 2 : 3;   // O projection / single projection
+  if (K == 512 && (N == 1536 || N == 1024)) return 4;   // fused Q|K|V, K|V
+  if (K == 512 && N > 4096) return 5;       // vocabulary
+  return 6;
+}
+#define PROF_DECL(...) long long __VA_ARGS__
+#define PROF_T() clock64()
+#define PROF_WAIT(acc, stmt) do { const long long _t = clock64(); stmt; acc += clock64() - _t; } while (0)
+#define PROF_ADD(b, i, v) atomicAdd(&g_gemm_prof[b][i], (unsigned long long)(v))
+#else
+#define PROF_DECL(...)
+#define PROF_WAIT(acc, stmt) do { stmt; } while (0)
+#endif
+
 __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -219,13 +242,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     if (lane == 0) {
       int it = 0;
+      PROF_DECL(w_slot = 0);
       for (int item = blockIdx.x; item < ntiles; item += gridDim.x) {
         const int tile = item % ntiles_mn, kb0 = (item / ntiles_mn) * nk_per, kb1 = min(nk_all, kb0 + nk_per);
         const int m0 = (tile / tiles_n) * kBM, n0 = (tile % tiles_n) * BN;
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+          PROF_WAIT(w_slot, mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1));
           const uint32_t fb = smem_u32(&full_bar[s]);
           mbar_expect_tx(fb, L::kStageBytes);
           const uint32_t a_dst = smem_u32(smem + s * L::kStageBytes);
@@ -243,22 +267,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
+#ifdef BOFI_GEMM_PROF
+      if (ntiles > (int)blockIdx.x) PROF_ADD(prof_bucket(N, K, RESID), 3, w_slot);
+#endif
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, A_MN, B_MN);
       int it = 0, t = 0;
+      PROF_DECL(w_acc = 0, w_full = 0, t_begin = PROF_T());
       for (int item = blockIdx.x; item < ntiles; item += gridDim.x, ++t) {
         const int kb0 = (item / ntiles_mn) * nk_per, kb1 = min(nk_all, kb0 + nk_per);
         const int as = t & 1;
         const uint32_t aph = (t >> 1) & 1;
-        mbar_wait(smem_u32(&tmem_empty_bar[as]), aph ^ 1);     // epilogue drained this accumulator
+        PROF_WAIT(w_acc, mbar_wait(smem_u32(&tmem_empty_bar[as]), aph ^ 1));     // epilogue drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(smem_u32(&full_bar[s]), ph);
+          PROF_WAIT(w_full, mbar_wait(smem_u32(&full_bar[s]), ph));
           tcgen05_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
           const uint64_t adesc = A_MN ? make_sw128_desc_mn(a_addr) : make_sw128_desc(a_addr);
@@ -273,6 +301,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         umma_commit(smem_u32(&tmem_full_bar[as]));   // accumulator complete
       }
+#ifdef BOFI_GEMM_PROF
+      if (t > 0) {
+        const int b = prof_bucket(N, K, RESID);
+        PROF_ADD(b, 0, PROF_T() - t_begin); PROF_ADD(b, 1, w_acc); PROF_ADD(b, 2, w_full); PROF_ADD(b, 7, 1);
+      }
+#endif
     }
   } else {
     // Epilogue: TMEM -> registers (one accumulator row per thread) -> bias / ReLU / residual -> swizzled smem
@@ -285,6 +319,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t sbuf = smem_u32(smem + L::kOutOffset + (warp - 2) * 4096);
     const uint32_t srow = sbuf + (uint32_t)lane * 128u;
     int t = 0;
+    PROF_DECL(w_tfull = 0, w_stage = 0, t_begin = PROF_T());
     for (int item = blockIdx.x; item < ntiles; item += gridDim.x, ++t) {
       const int tile = item % ntiles_mn;
       const int m0 = (tile / tiles_n) * kBM, n0 = (tile % tiles_n) * BN;
@@ -313,8 +348,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       };
+      // Bias of this warp's NI chunks (NI * CC = 128 values): ONE float4 per lane, fetched before the accumulator wait and
+      // handed out by shuffles.  The L2 is saturated by the operand stream (tools/gemm_stalls.py), so a load issued
+      // inside the drain would put microseconds of loaded L2 latency on every chunk.
+      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+      {
+        const int ci = (lane * 4) / CC, cc = half + 2 * ci;
+        const int nb = n0 + cc * CC + (lane * 4) % CC;
+        if (ci < NI && cc < NC && nb + 4 <= N) bv = *reinterpret_cast<const float4*>(bias + nb);
+      }
       fetch_res(res[0], half);
-      mbar_wait(smem_u32(&tmem_full_bar[as]), aph);
+      PROF_WAIT(w_tfull, mbar_wait(smem_u32(&tmem_full_bar[as]), aph));
       tcgen05_fence_after();
 #pragma unroll
       for (int i = 0; i < NI; ++i) {
@@ -323,11 +367,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (c >= NC || n >= N) break;                 // warp-uniform
         fetch_res(res[(i + 1) & 1], c + 2);
         const bool full = (n + CC <= N);              // warp-uniform
-        float4 bb[CC / 4];
-        if (full) {
-#pragma unroll
-          for (int j = 0; j < CC / 4; ++j) bb[j] = *reinterpret_cast<const float4*>(bias + n + 4 * j);
-        }
         uint32_t r[CC];
         {
           uint32_t(&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
@@ -355,8 +394,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (full) {
 #pragma unroll
           for (int j = 0; j < CC; j += 4) {
-            float4 x = make_float4(__uint_as_float(r[j]) + bb[j / 4].x, __uint_as_float(r[j + 1]) + bb[j / 4].y,
-                                   __uint_as_float(r[j + 2]) + bb[j / 4].z, __uint_as_float(r[j + 3]) + bb[j / 4].w);
+            const int src = i * (CC / 4) + j / 4;          // the lane holding the bias of these four columns
+            float4 x = make_float4(__uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bv.x, src),
+                                   __uint_as_float(r[j + 1]) + __shfl_sync(0xffffffffu, bv.y, src),
+                                   __uint_as_float(r[j + 2]) + __shfl_sync(0xffffffffu, bv.z, src),
+                                   __uint_as_float(r[j + 3]) + __shfl_sync(0xffffffffu, bv.w, src));
             if constexpr (RELU) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
             if constexpr (RESID) {
               const float4 rr = ld_shared_v4(srow + (uint32_t)(((j / 4) ^ (lane & 7)) * 16));
@@ -380,8 +422,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         // this warp's staging tile must have been read out by the TMA engine (its previous store); on the residual path
         // every lane must also be done reading its residual row before the tile is overwritten
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        __syncwarp();
+        PROF_WAIT(w_stage, if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); __syncwarp());
         if constexpr (CC == 32) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -406,6 +447,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[as]));
     }
+#ifdef BOFI_GEMM_PROF
+    if (warp == 2 && lane == 0 && t > 0) {
+      const int b = prof_bucket(N, K, RESID);
+      PROF_ADD(b, 4, PROF_T() - t_begin); PROF_ADD(b, 5, w_tfull); PROF_ADD(b, 6, w_stage);
+    }
+#endif
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     __syncwarp();
   }
@@ -505,6 +552,16 @@ inline const CUtensorMap* cached_tmap(const void* ptr, uint64_t rows, uint64_t c
   return &cache.emplace(key, tm).first->second;
 }
 
+// BOFI_RESID_RED=0: in-place residual adds go back through the register epilogue (A/B measurements)
+inline bool inplace_reduce() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BOFI_RESID_RED");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 // A [M,K] bf16 (pitch lda), W [N,K] bf16 (pitch ldw).  Requires K % 64 == 0, 16-byte aligned pitches.
 template <typename TOut>
 inline cudaError_t gemm_tc(cudaStream_t s, const bf16* A, int lda, const bf16* W, int ldw, const float* bias,
@@ -525,6 +582,12 @@ inline cudaError_t gemm_tc(cudaStream_t s, const bf16* A, int lda, const bf16* W
   if constexpr (sizeof(TOut) == 4) {
     // fp32 outputs: plain (logits), +ReLU (att_embed), +residual (O-proj / FFN2 into the residual stream)
     if (residual && relu) return cudaErrorInvalidValue;
+    // In-place residual (x += a . W^T + b, the O-projections and FFN2 of the decode path): the add is done by the L2 with
+    // TMA reduce stores, so the SMs never read x -- no residual loads behind the saturated operand stream, no
+    // transposes through the staging tile.  (acc + b) + x and x + (acc + b) are the same fp32 sum.
+    if (residual && inplace_reduce() && (const void*)residual == (const void*)C && ldr == ldc)
+      return wide ? launch<256, 4, TOut, false, false, false, false, true>(s, *tmA, *tmB, *tmC, bias, nullptr, 0, M, N, K, 0, live_rows, 1, rows_dev)
+                  : launch<64, 6, TOut, false, false, false, false, true>(s, *tmA, *tmB, *tmC, bias, nullptr, 0, M, N, K, 0, live_rows, 1, rows_dev);
     if (residual) return wide ? BOFI_TC_LAUNCH(256, 4, false, true) : BOFI_TC_LAUNCH(64, 6, false, true);
     if (relu) return wide ? BOFI_TC_LAUNCH(256, 4, true, false) : BOFI_TC_LAUNCH(64, 6, true, false);
     return wide ? BOFI_TC_LAUNCH(256, 4, false, false) : BOFI_TC_LAUNCH(64, 6, false, false);

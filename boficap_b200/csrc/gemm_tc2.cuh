@@ -68,14 +68,14 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
       : "memory");
 }
 
-template <typename TOut, bool RELU, bool RESID>
+template <typename TOut, bool RELU, bool RESID, bool REDUCE = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, const float* residual, int ldr,
                int M, int N, int K, int relu, const int* live_rows, const int* rows_dev) {
   pdl_launch();
   constexpr int BN = k2BN, STAGES = k2Stages;
-  constexpr bool A_MN = false, B_MN = false, REDUCE = false;
+  constexpr bool A_MN = false, B_MN = false;
   using L = Smem2;
   uint32_t rank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
@@ -131,13 +131,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0) {
     if (lane == 0) {
       int it = 0;
+      PROF_DECL(w_slot = 0);
       for (int item = cid; item < ntiles; item += ncl) {
         const int tile = item % ntiles_mn, kb0 = (item / ntiles_mn) * nk_per, kb1 = min(nk_all, kb0 + nk_per);
         const int m0 = (tile / tiles_n) * 2 * kBM + (int)rank * kBM, n0 = (tile % tiles_n) * BN;
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+          PROF_WAIT(w_slot, mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1));
           // both CTAs' loads complete on the LEADER's full barrier (cta_group::2 TMA: barrier address with the peer bit
           // clear); the leader announces the bytes of the pair
           const uint32_t fb = smem_u32(&full_bar[s]);
@@ -147,22 +148,26 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tma_load_2d_2sm(a_dst + L::kABytes, &tmB, fb, kb * kBK, n0 + (int)rank * (BN / 2));   // this CTA's half of W
         }
       }
+#ifdef BOFI_GEMM_PROF
+      if (ntiles > cid && rank == 0) PROF_ADD(prof_bucket(N, K, RESID), 3, w_slot);
+#endif
     }
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * kBM, BN, A_MN, B_MN);
       int it = 0, t = 0;
+      PROF_DECL(w_acc = 0, w_full = 0, t_begin = PROF_T());
       for (int item = cid; item < ntiles; item += ncl, ++t) {
         const int kb0 = (item / ntiles_mn) * nk_per, kb1 = min(nk_all, kb0 + nk_per);
         const int as = t & 1;
         const uint32_t aph = (t >> 1) & 1;
-        mbar_wait(smem_u32(&tmem_empty_bar[as]), aph ^ 1);     // epilogue drained this accumulator
+        PROF_WAIT(w_acc, mbar_wait(smem_u32(&tmem_empty_bar[as]), aph ^ 1));     // epilogue drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(smem_u32(&full_bar[s]), ph);
+          PROF_WAIT(w_full, mbar_wait(smem_u32(&full_bar[s]), ph));
           tcgen05_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
           const uint64_t adesc = A_MN ? make_sw128_desc_mn(a_addr) : make_sw128_desc(a_addr);
@@ -177,6 +182,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         umma_commit_2sm(smem_u32(&tmem_full_bar[as]));   // accumulator complete: both CTAs' epilogues
       }
+#ifdef BOFI_GEMM_PROF
+      if (t > 0) {
+        const int b = prof_bucket(N, K, RESID);
+        PROF_ADD(b, 0, PROF_T() - t_begin); PROF_ADD(b, 1, w_acc); PROF_ADD(b, 2, w_full); PROF_ADD(b, 7, 1);
+      }
+#endif
     }
   } else {
     // Epilogue: TMEM -> registers (one accumulator row per thread) -> bias / ReLU / residual -> swizzled smem
@@ -191,6 +202,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t sbuf0 = smem_u32(smem + L::kOutOffset + (warp - 2) * 8192);
     int nstore = 0;
     int t = 0;
+    PROF_DECL(w_tfull = 0, w_stage = 0, t_begin = PROF_T());
     for (int item = cid; item < ntiles; item += ncl, ++t) {
       const int tile = item % ntiles_mn;
       const int m0 = (tile / tiles_n) * 2 * kBM + (int)rank * kBM, n0 = (tile % tiles_n) * BN;
@@ -219,8 +231,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
       };
+      // Bias of this warp's NI chunks (NI * CC = 128 values): ONE float4 per lane, fetched before the accumulator wait and
+      // handed out by shuffles.  The L2 is saturated by the operand stream (tools/gemm_stalls.py), so a load issued
+      // inside the drain would put microseconds of loaded L2 latency on every chunk.
+      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+      {
+        const int ci = (lane * 4) / CC, cc = half + 2 * ci;
+        const int nb = n0 + cc * CC + (lane * 4) % CC;
+        if (ci < NI && cc < NC && nb + 4 <= N) bv = *reinterpret_cast<const float4*>(bias + nb);
+      }
       fetch_res(res[0], half);
-      mbar_wait(smem_u32(&tmem_full_bar[as]), aph);
+      PROF_WAIT(w_tfull, mbar_wait(smem_u32(&tmem_full_bar[as]), aph));
       tcgen05_fence_after();
 #pragma unroll
       for (int i = 0; i < NI; ++i) {
@@ -231,11 +252,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const bool full = (n + CC <= N);              // warp-uniform
         const uint32_t sbuf = sbuf0 + (uint32_t)(nstore & 1) * 4096u;
         const uint32_t srow = sbuf + (uint32_t)lane * 128u;
-        float4 bb[CC / 4];
-        if (full) {
-#pragma unroll
-          for (int j = 0; j < CC / 4; ++j) bb[j] = *reinterpret_cast<const float4*>(bias + n + 4 * j);
-        }
         uint32_t r[CC];
         {
           uint32_t(&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
@@ -263,8 +279,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (full) {
 #pragma unroll
           for (int j = 0; j < CC; j += 4) {
-            float4 x = make_float4(__uint_as_float(r[j]) + bb[j / 4].x, __uint_as_float(r[j + 1]) + bb[j / 4].y,
-                                   __uint_as_float(r[j + 2]) + bb[j / 4].z, __uint_as_float(r[j + 3]) + bb[j / 4].w);
+            const int src = i * (CC / 4) + j / 4;          // the lane holding the bias of these four columns
+            float4 x = make_float4(__uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bv.x, src),
+                                   __uint_as_float(r[j + 1]) + __shfl_sync(0xffffffffu, bv.y, src),
+                                   __uint_as_float(r[j + 2]) + __shfl_sync(0xffffffffu, bv.z, src),
+                                   __uint_as_float(r[j + 3]) + __shfl_sync(0xffffffffu, bv.w, src));
             if constexpr (RELU) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
             if constexpr (RESID) {
               const float4 rr = ld_shared_v4(srow + (uint32_t)(((j / 4) ^ (lane & 7)) * 16));
@@ -288,8 +307,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         // this warp's staging tile must have been read out by the TMA engine (its previous store); on the residual path
         // every lane must also be done reading its residual row before the tile is overwritten
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        __syncwarp();
+        PROF_WAIT(w_stage, if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); __syncwarp());
         if constexpr (CC == 32) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -306,7 +324,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&tmC, sbuf, n, m0 + quad * 32);
+          if constexpr (REDUCE) tma_reduce_add_2d(&tmC, sbuf, n, m0 + quad * 32);     // in-place residual: the L2 adds
+          else tma_store_2d(&tmC, sbuf, n, m0 + quad * 32);
         }
         ++nstore;
       }
@@ -314,6 +333,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(smem_u32(&tmem_empty_bar[as]), 0);     // the leader's MMA thread waits for both CTAs
     }
+#ifdef BOFI_GEMM_PROF
+    if (warp == 2 && lane == 0 && t > 0 && rank == 0) {
+      const int b = prof_bucket(N, K, RESID);
+      PROF_ADD(b, 4, PROF_T() - t_begin); PROF_ADD(b, 5, w_tfull); PROF_ADD(b, 6, w_stage);
+    }
+#endif
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     __syncwarp();
   }
@@ -326,12 +351,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 
-template <typename TOut, bool RELU, bool RESID>
+template <typename TOut, bool RELU, bool RESID, bool REDUCE = false>
 inline cudaError_t launch2(cudaStream_t s, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const float* bias,
                            const float* residual, int ldr, int M, int N, int K, int relu, const int* live_rows, const int* rows_dev) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<TOut, RELU, RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<TOut, RELU, RESID, REDUCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2::kTotal);
     if (e != cudaSuccess) return e;
     configured = true;
   }
@@ -352,7 +377,7 @@ inline cudaError_t launch2(cudaStream_t s, const CUtensorMap& tmA, const CUtenso
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  return cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<TOut, RELU, RESID>, tmA, tmB, tmC, bias, residual, ldr, M, N, K, relu, live_rows, rows_dev);
+  return cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<TOut, RELU, RESID, REDUCE>, tmA, tmB, tmC, bias, residual, ldr, M, N, K, relu, live_rows, rows_dev);
 }
 
 // Same contract as gemm_tc (K-major A [M,K], W [N,K]).
@@ -368,6 +393,8 @@ inline cudaError_t gemm_tc2(cudaStream_t s, const bf16* A, int lda, const bf16* 
 #define BOFI_TC2(RELU_, RESID_) launch2<TOut, RELU_, RESID_>(s, *tmA, *tmB, *tmC, bias, residual, ldr, M, N, K, relu, live_rows, rows_dev)
   if constexpr (sizeof(TOut) == 4) {
     if (residual && relu) return cudaErrorInvalidValue;
+    if (residual && inplace_reduce() && (const void*)residual == (const void*)C && ldr == ldc)
+      return launch2<TOut, false, false, true>(s, *tmA, *tmB, *tmC, bias, nullptr, 0, M, N, K, 0, live_rows, rows_dev);
     if (residual) return BOFI_TC2(false, true);
     if (relu) return BOFI_TC2(true, false);
     return BOFI_TC2(false, false);
