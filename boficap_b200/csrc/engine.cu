@@ -113,7 +113,7 @@ struct bofi_engine {
   int Lb = 22, L = 20, V = 0, Vpad = 0;
   bool bf16_mode = false;
   bool use_tc = true;
-  bool gemm2 = false;                  // BOFI_GEMM2=1: 2-CTA (cta_group::2) tiles for the wide GEMMs
+  bool gemm2 = true;                   // 2-CTA (cta_group::2) 256 x 256 tile pairs for the wide GEMMs; BOFI_GEMM2=0: 1-CTA tiles
   int ln_fuse_min_rows = 4096;         // below this the panel LayerNorm would be repeated by too many CTAs
   bool ln_fuse = false;                // BOFI_LNFUSE=1: LayerNorm fused into the consuming tcgen05 GEMM (gemm_ln_tc.cuh; measured slower, off)
   bool attn_simt_only = false;         // BOFI_ATTN=simt: generic FFMA attention kernel everywhere
@@ -282,8 +282,11 @@ static int linear(bofi_engine* e, cudaStream_t s, const T* A, int lda, const Lin
                   TOut* out, int ldc, int M, int relu, const int* live) {
   cudaError_t err;
   const bool tcpath = std::is_same<T, bf16>::value && e->use_tc;
-  ProfScope prof(e, s, tcpath ? PC_GEMM_TC : PC_GEMM_SIMT, 2.0 * M * l.N * l.K,
-                 (double)sizeof(T) * ((double)M * l.K + (double)l.N * l.K) + (double)sizeof(TOut) * M * l.N + (resid ? 4.0 * M * l.N : 0.0),
+  // A compacted SAIC step only walks the tiles below the device-side row count: M is an upper bound there, so such a
+  // launch is booked under "other" without FLOPs instead of inflating the GEMM classes' achieved rate.
+  const bool exact = e->rows_dev == nullptr;
+  ProfScope prof(e, s, !exact ? PC_OTHER : tcpath ? PC_GEMM_TC : PC_GEMM_SIMT, exact ? 2.0 * M * l.N * l.K : 0.0,
+                 !exact ? 0.0 : (double)sizeof(T) * ((double)M * l.K + (double)l.N * l.K) + (double)sizeof(TOut) * M * l.N + (resid ? 4.0 * M * l.N : 0.0),
                  M, l.N, l.K);
   if constexpr (std::is_same<T, bf16>::value) {
     if (e->use_tc && e->gemm2 && M >= 2048 && l.N >= 512)
@@ -1076,12 +1079,12 @@ extern "C" {
 const char* bofi_last_error(void) { return g_err; }
 int bofi_abi_version(void) { return BOFI_ABI_VERSION; }
 #ifdef BOFI_GEMM_PROF
-// Profiling build only (not part of include/bofi_b200.h): the tcgen05 GEMM's stall counters, 8 shape classes x 8.
+// Profiling build only (not part of include/bofi_b200.h): the tcgen05 GEMM's stall counters, 8 shape classes x 12.
 int bofi_debug_gemm_prof(unsigned long long* out64, int reset) {
   if (cudaDeviceSynchronize() != cudaSuccess) return BOFI_ERR_CUDA;
-  if (out64 && cudaMemcpyFromSymbol(out64, tc::g_gemm_prof, sizeof(unsigned long long) * 64) != cudaSuccess) return BOFI_ERR_CUDA;
+  if (out64 && cudaMemcpyFromSymbol(out64, tc::g_gemm_prof, sizeof(unsigned long long) * 96) != cudaSuccess) return BOFI_ERR_CUDA;
   if (reset) {
-    static const unsigned long long zeros[64] = {0};
+    static const unsigned long long zeros[96] = {0};
     if (cudaMemcpyToSymbol(tc::g_gemm_prof, zeros, sizeof(zeros)) != cudaSuccess) return BOFI_ERR_CUDA;
   }
   return BOFI_OK;
@@ -1121,7 +1124,7 @@ int bofi_create(const bofi_config_t* cfg, int device, bofi_handle_t* out) {
   const char* gp = getenv("BOFI_PDL");
   if (gp) pdl_enabled() = strcmp(gp, "0") != 0;
   const char* g2 = getenv("BOFI_GEMM2");
-  e->gemm2 = (g2 && strcmp(g2, "1") == 0);
+  e->gemm2 = !(g2 && strcmp(g2, "0") == 0);
   const char* gl = getenv("BOFI_LNFUSE");
   e->ln_fuse = (gl && strcmp(gl, "1") == 0);
   if (const char* gm = getenv("BOFI_LNFUSE_MIN")) e->ln_fuse_min_rows = atoi(gm);

@@ -56,7 +56,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // (full) and on the epilogue (tmem_empty), the TMA thread's waits on free stages, one epilogue warp's waits on the
 // accumulator and on its staging tile.  Compiled out of the product library.
 #ifdef BOFI_GEMM_PROF
-__device__ unsigned long long g_gemm_prof[8][8];
+__device__ unsigned long long g_gemm_prof[8][12];
 __device__ __forceinline__ int prof_bucket(int N, int K, bool resid) {
   if (K == 512 && N == 2048) return 0;      // FFN1
   if (K == 2048) return 1;                  // FFN2
@@ -319,7 +319,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t sbuf = smem_u32(smem + L::kOutOffset + (warp - 2) * 4096);
     const uint32_t srow = sbuf + (uint32_t)lane * 128u;
     int t = 0;
-    PROF_DECL(w_tfull = 0, w_stage = 0, t_begin = PROF_T());
+    PROF_DECL(w_tfull = 0, w_stage = 0, w_tld = 0, t_math = 0, t_store = 0, t_arrive = 0, t_begin = PROF_T());
     for (int item = blockIdx.x; item < ntiles; item += gridDim.x, ++t) {
       const int tile = item % ntiles_mn;
       const int m0 = (tile / tiles_n) * kBM, n0 = (tile % tiles_n) * BN;
@@ -368,6 +368,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         fetch_res(res[(i + 1) & 1], c + 2);
         const bool full = (n + CC <= N);              // warp-uniform
         uint32_t r[CC];
+        PROF_DECL(t_ld0 = PROF_T());
         {
           uint32_t(&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
           tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + c * CC), r0);
@@ -376,6 +377,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + c * CC + 32), r1);
           }
         }
+#ifdef BOFI_GEMM_PROF
+        w_tld += PROF_T() - t_ld0;
+        const long long t_m0 = PROF_T();
+#endif
         if constexpr (RESID) {
           if (full) {
             // transpose the coalesced residual registers into this thread's row through the staging tile
@@ -436,21 +441,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                          pack_bf16(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])),
                          pack_bf16(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])));
         }
+#ifdef BOFI_GEMM_PROF
+        t_math += PROF_T() - t_m0;
+        const long long t_s0 = PROF_T();
+#endif
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
           if constexpr (REDUCE) tma_reduce_add_2d(&tmC, sbuf, n, m0 + quad * 32);
           else tma_store_2d(&tmC, sbuf, n, m0 + quad * 32);
         }
+#ifdef BOFI_GEMM_PROF
+        t_store += PROF_T() - t_s0;
+#endif
       }
+      PROF_DECL(t_a0 = PROF_T());
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[as]));
+#ifdef BOFI_GEMM_PROF
+      t_arrive += PROF_T() - t_a0;
+#endif
     }
 #ifdef BOFI_GEMM_PROF
     if (warp == 2 && lane == 0 && t > 0) {
       const int b = prof_bucket(N, K, RESID);
       PROF_ADD(b, 4, PROF_T() - t_begin); PROF_ADD(b, 5, w_tfull); PROF_ADD(b, 6, w_stage);
+      PROF_ADD(b, 8, w_tld); PROF_ADD(b, 9, t_math); PROF_ADD(b, 10, t_store); PROF_ADD(b, 11, t_arrive);
     }
 #endif
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");

@@ -24,13 +24,17 @@ namespace bofi {
 namespace tc {
 
 constexpr int k2BN = 256;
-constexpr int k2Stages = 5;
+#ifndef BOFI_TC2_STAGES
+#define BOFI_TC2_STAGES 6
+#endif
+constexpr int k2Stages = BOFI_TC2_STAGES;
+constexpr int k2Staging = k2Stages >= 6 ? 1 : 2;     // staging tiles per epilogue warp (what is left of the 227 KB)
 struct Smem2 {
   static constexpr int kABytes = kBM * kBK * 2;                    // 16 KB: this CTA's rows of A
   static constexpr int kBBytes = (k2BN / 2) * kBK * 2;             // 16 KB: this CTA's half of W
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kOutOffset = k2Stages * kStageBytes;
-  static constexpr int kOutBytes = 8 * 2 * 4096;                   // two staging tiles per epilogue warp
+  static constexpr int kOutBytes = 8 * k2Staging * 4096;           // staging tiles of the eight epilogue warps
   static constexpr int kBarOffset = kOutOffset + kOutBytes;
   static constexpr int kTotal = kBarOffset + 256 + 1024;
 };
@@ -59,11 +63,14 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
                ::"r"(bar), "h"((uint16_t)3)
                : "memory");
 }
+// Default semantics (release at CTA scope), as the accumulator pipelines of the vendor's 2-SM kernels arrive remotely: what
+// this arrival publishes is "my tcgen05.ld of the accumulator are done" (tcgen05.wait::ld + fence::before_thread_sync), no
+// generic-proxy memory.  With .release.cluster the arrival alone took 32-42 % of an epilogue warp's time (tools/gemm_stalls.py).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(bar), "r"(cta)
       : "memory");
 }
@@ -199,10 +206,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int half = (warp - 2) >> 2;
     // two staging tiles per warp: the TMA engine is shared with the operand loads, so a store can sit in its queue for a
     // while; waiting for the PREVIOUS store (not the one before it) stalled the epilogue (36 % of the kernel's stall samples)
-    const uint32_t sbuf0 = smem_u32(smem + L::kOutOffset + (warp - 2) * 8192);
+    const uint32_t sbuf0 = smem_u32(smem + L::kOutOffset + (warp - 2) * (k2Staging * 4096));
     int nstore = 0;
     int t = 0;
-    PROF_DECL(w_tfull = 0, w_stage = 0, t_begin = PROF_T());
+    PROF_DECL(w_tfull = 0, w_stage = 0, w_tld = 0, t_math = 0, t_store = 0, t_arrive = 0, t_begin = PROF_T());
     for (int item = cid; item < ntiles; item += ncl, ++t) {
       const int tile = item % ntiles_mn;
       const int m0 = (tile / tiles_n) * 2 * kBM + (int)rank * kBM, n0 = (tile % tiles_n) * BN;
@@ -250,9 +257,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (c >= NC || n >= N) break;                 // warp-uniform
         fetch_res(res[(i + 1) & 1], c + 2);
         const bool full = (n + CC <= N);              // warp-uniform
-        const uint32_t sbuf = sbuf0 + (uint32_t)(nstore & 1) * 4096u;
+        const uint32_t sbuf = sbuf0 + (uint32_t)(k2Staging == 2 ? (nstore & 1) : 0) * 4096u;
         const uint32_t srow = sbuf + (uint32_t)lane * 128u;
         uint32_t r[CC];
+        PROF_DECL(t_ld0 = PROF_T());
         {
           uint32_t(&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
           tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + c * CC), r0);
@@ -261,10 +269,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + c * CC + 32), r1);
           }
         }
+#ifdef BOFI_GEMM_PROF
+        w_tld += PROF_T() - t_ld0;
+        const long long t_m0 = PROF_T();
+#endif
         if constexpr (RESID) {
           if (full) {
             // transpose the coalesced residual registers into this thread's row through the staging tile
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            if (lane == 0) { if constexpr (k2Staging == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -307,7 +319,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         // this warp's staging tile must have been read out by the TMA engine (its previous store); on the residual path
         // every lane must also be done reading its residual row before the tile is overwritten
-        PROF_WAIT(w_stage, if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); __syncwarp());
+        PROF_WAIT(w_stage, if (lane == 0) { if constexpr (k2Staging == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); } __syncwarp());
         if constexpr (CC == 32) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -321,6 +333,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                          pack_bf16(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])),
                          pack_bf16(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])));
         }
+#ifdef BOFI_GEMM_PROF
+        t_math += PROF_T() - t_m0;
+        const long long t_s0 = PROF_T();
+#endif
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
@@ -328,15 +344,23 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           else tma_store_2d(&tmC, sbuf, n, m0 + quad * 32);
         }
         ++nstore;
+#ifdef BOFI_GEMM_PROF
+        t_store += PROF_T() - t_s0;
+#endif
       }
+      PROF_DECL(t_a0 = PROF_T());
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(smem_u32(&tmem_empty_bar[as]), 0);     // the leader's MMA thread waits for both CTAs
+#ifdef BOFI_GEMM_PROF
+      t_arrive += PROF_T() - t_a0;
+#endif
     }
 #ifdef BOFI_GEMM_PROF
     if (warp == 2 && lane == 0 && t > 0 && rank == 0) {
       const int b = prof_bucket(N, K, RESID);
       PROF_ADD(b, 4, PROF_T() - t_begin); PROF_ADD(b, 5, w_tfull); PROF_ADD(b, 6, w_stage);
+      PROF_ADD(b, 8, w_tld); PROF_ADD(b, 9, t_math); PROF_ADD(b, 10, t_store); PROF_ADD(b, 11, t_arrive);
     }
 #endif
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");

@@ -148,8 +148,8 @@ def test_attention_single_query_fp32(engines, Tk):
 @pytest.mark.gpu
 @pytest.mark.parametrize("env", ["BOFI_GEMM2", "BOFI_LNFUSE"])
 def test_optional_gemm_variants_reproduce_the_default_path(env, monkeypatch):
-    """The opt-in tcgen05 variants (2-CTA tiles, LayerNorm-fused A-resident GEMM) must give the default bf16 path's
-    results: same boxes, logits within bf16 rounding of the LayerNorm output."""
+    """The other tcgen05 variants (1-CTA tiles via BOFI_GEMM2=0, the opt-in LayerNorm-fused A-resident GEMM) must give
+    the default bf16 path's results: same boxes, logits within bf16 rounding of the LayerNorm output."""
     import torch
     from boficap_b200 import synth
     from boficap_b200.engine import BofiEngine
@@ -173,7 +173,7 @@ def test_optional_gemm_variants_reproduce_the_default_path(env, monkeypatch):
             break
     else:
         raise AssertionError("no usable batch")
-    monkeypatch.setenv(env, "1")
+    monkeypatch.setenv(env, "0" if env == "BOFI_GEMM2" else "1")
     monkeypatch.setenv("BOFI_LNFUSE_MIN", "1")
     var = run(att_all[:B])
     same = (base[3] == var[3]).all(1)

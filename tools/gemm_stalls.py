@@ -45,23 +45,25 @@ def main():
     for _ in range(2):
         step()
     torch.cuda.synchronize()
-    buf = (C.c_uint64 * 64)()
+    buf = (C.c_uint64 * 96)()
     assert raw.bofi_debug_gemm_prof(buf, 1) == 0
     for _ in range(a.steps):
         step()
     assert raw.bofi_debug_gemm_prof(buf, 0) == 0
     rows = []
-    print("%-26s %8s %9s | MMA thread: %%operands %%epilogue | TMA %%slot | epilogue warp: %%accum %%staging" % ("class", "CTAs", "Mcyc/CTA"))
+    print("%-26s %8s %9s | MMA thread: %%operands %%epilogue | TMA %%slot | epilogue warp: %%accum %%staging %%tmem_ld %%math+st.shared %%fence+store %%arrive" % ("class", "CTAs", "Mcyc/CTA"))
     for b, name in enumerate(NAMES):
-        v = [int(buf[b * 8 + i]) for i in range(8)]
+        v = [int(buf[b * 12 + i]) for i in range(12)]
         if v[7] == 0:
             continue
-        mma, w_acc, w_full, w_slot, epi, w_tfull, w_stage, n = v
+        mma, w_acc, w_full, w_slot, epi, w_tfull, w_stage, n, w_tld, t_math, t_store, t_arrive = v[:12]
         rows.append(dict(cls=name, ctas=n, mma_cycles=mma, mma_wait_operands=w_full, mma_wait_epilogue=w_acc,
-                         tma_wait_slot=w_slot, epi_cycles=epi, epi_wait_accum=w_tfull, epi_wait_staging=w_stage))
-        print("%-26s %8d %9.3f |            %8.1f %9.1f | %8.1f |               %6.1f %8.1f" % (
+                         tma_wait_slot=w_slot, epi_cycles=epi, epi_wait_accum=w_tfull, epi_wait_staging=w_stage,
+                         epi_tmem_ld=w_tld, epi_math=t_math - w_stage, epi_store=t_store, epi_arrive=t_arrive))
+        print("%-26s %8d %9.3f |            %8.1f %9.1f | %8.1f |               %6.1f %8.1f %8.1f %8.1f %8.1f %8.1f" % (
             name, n, mma / n / 1e6, 100 * w_full / mma, 100 * w_acc / mma, 100 * w_slot / mma,
-            100 * w_tfull / max(epi, 1), 100 * w_stage / max(epi, 1)))
+            100 * w_tfull / max(epi, 1), 100 * w_stage / max(epi, 1), 100 * w_tld / max(epi, 1),
+            100 * (t_math - w_stage) / max(epi, 1), 100 * t_store / max(epi, 1), 100 * t_arrive / max(epi, 1)))
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/gemm_stalls.json", "w") as f:
         json.dump(dict(batch=a.batch, mode=a.mode, steps=a.steps, rows=rows), f, indent=1)
