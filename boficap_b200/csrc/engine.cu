@@ -113,6 +113,8 @@ struct bofi_engine {
   int Lb = 22, L = 20, V = 0, Vpad = 0;
   bool bf16_mode = false;
   bool use_tc = true;
+  int kps = 2;                         // k-blocks per ring stage of the 2-CTA GEMM (BOFI_KPS=1: one, 2-D boxes)
+  bool ares = false;                   // BOFI_ARES=1: A-resident 2-CTA tiles for the wide K <= 512 GEMMs (measured slower)
   bool gemm2 = true;                   // 2-CTA (cta_group::2) 256 x 256 tile pairs for the wide GEMMs; BOFI_GEMM2=0: 1-CTA tiles
   int ln_fuse_min_rows = 4096;         // below this the panel LayerNorm would be repeated by too many CTAs
   bool ln_fuse = false;                // BOFI_LNFUSE=1: LayerNorm fused into the consuming tcgen05 GEMM (gemm_ln_tc.cuh; measured slower, off)
@@ -290,7 +292,7 @@ static int linear(bofi_engine* e, cudaStream_t s, const T* A, int lda, const Lin
                  M, l.N, l.K);
   if constexpr (std::is_same<T, bf16>::value) {
     if (e->use_tc && e->gemm2 && M >= 2048 && l.N >= 512)
-      err = tc::gemm_tc2<TOut>(s, A, lda, l.w16, l.K, l.b, resid, ldr, out, ldc, M, l.N, l.K, relu, live, e->rows_dev);
+      err = tc::gemm_tc2<TOut>(s, A, lda, l.w16, l.K, l.b, resid, ldr, out, ldc, M, l.N, l.K, relu, live, e->rows_dev, e->ares, e->kps);
     else if (e->use_tc)
       err = tc::gemm_tc<TOut>(s, A, lda, l.w16, l.K, l.b, resid, ldr, out, ldc, M, l.N, l.K, relu, live, e->rows_dev);
     else
@@ -1125,6 +1127,10 @@ int bofi_create(const bofi_config_t* cfg, int device, bofi_handle_t* out) {
   if (gp) pdl_enabled() = strcmp(gp, "0") != 0;
   const char* g2 = getenv("BOFI_GEMM2");
   e->gemm2 = !(g2 && strcmp(g2, "0") == 0);
+  const char* kp = getenv("BOFI_KPS");
+  e->kps = (kp && strcmp(kp, "1") == 0) ? 1 : 2;
+  const char* ar = getenv("BOFI_ARES");
+  e->ares = (ar && strcmp(ar, "1") == 0);
   const char* gl = getenv("BOFI_LNFUSE");
   e->ln_fuse = (gl && strcmp(gl, "1") == 0);
   if (const char* gm = getenv("BOFI_LNFUSE_MIN")) e->ln_fuse_min_rows = atoi(gm);

@@ -579,6 +579,28 @@ inline bool inplace_reduce() {
   return v == 1;
 }
 
+// K-major bf16 operand [rows, cols] (pitch ld) seen as the 3-D tensor (64 k, rows, cols/64 k-blocks): one box
+// (64, box_rows, box_kb) lands as box_kb consecutive 128B-swizzled k-block tiles of box_rows x 128 bytes -- the smem
+// image of box_kb separate 2-D loads, in one instruction (see Smem2T in gemm_tc2.cuh for why that matters).
+inline const CUtensorMap* cached_tmap_kblocks(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_kb) {
+  static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapHash> cache;
+  TmapKey key{ptr, rows, cols, ld, box_rows, (int)box_kb};
+  auto it = cache.find(key);
+  if (it != cache.end()) return &it->second;
+  if (cache.size() > 8192) cache.clear();
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn || cols % 64 != 0) return nullptr;
+  CUtensorMap tm;
+  cuuint64_t gdim[3] = {64, rows, cols / 64};
+  cuuint64_t gstride[2] = {ld * 2, 128};
+  cuuint32_t box[3] = {64, box_rows, box_kb};
+  cuuint32_t estr[3] = {1, 1, 1};
+  if (fn(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return nullptr;
+  return &cache.emplace(key, tm).first->second;
+}
+
 // A [M,K] bf16 (pitch lda), W [N,K] bf16 (pitch ldw).  Requires K % 64 == 0, 16-byte aligned pitches.
 template <typename TOut>
 inline cudaError_t gemm_tc(cudaStream_t s, const bf16* A, int lda, const bf16* W, int ldw, const float* bias,

@@ -11,12 +11,15 @@
 //   tmem_full[a]   per CTA, multicast commit; tmem_empty[a]: leader's barrier, 16 arrivals (8 epilogue warps x 2 CTAs)
 // Epilogue as in gemm_tc.cuh (8 warps per CTA drain their own 128 TMEM lanes).  K-major operands only.
 //
-// MEASURED RESULT (B200, B=1024 decode): numerically identical to gemm_tc.cuh (unit errors ~3e-6 against fp32), L2->SM
-// traffic per launch down by a third -- and the same speed (FFN1 M=36864 N=2048 K=512: 74-77 us vs 73 us; Q|K|V 57-60 us vs
-// 58 us), with 5 or 6 ring stages and with one or two staging tiles per epilogue warp.  Shared-memory fill is therefore
-// NOT what holds these shapes at ~1050 TFLOP/s (64 % of the measured cuBLAS bf16 rate); the remaining suspects are the
-// per-tile epilogue (128 x 256 outputs drained through tcgen05.ld -> st.shared -> TMA store while the next tile's 8
-// k-blocks take only ~3 us) and TMA load latency against the ring depth.  Opt-in (BOFI_GEMM2=1) until it wins.
+// MEASURED (B200, B=1024 decode, tools/gemm_stalls.py + bench.py A/B, profiles/r01d_gemm_stalls.txt): numerically identical
+// to gemm_tc.cuh.  As first built (5 stages, accumulator handed back with mbarrier.arrive.release.cluster) it was no faster
+// than the 1-CTA tile: the epilogue warps spent 32-42 % of their time in that one remote arrive and the MMA thread
+// waited for them.  With the default-semantics remote arrive and a 6-stage ring (one staging tile per warp) it is the
+// default for M >= 2048, N >= 512: 166.7 k -> 174.6 k captions/s, roofline.frac 0.463 -> 0.486 (BOFI_GEMM2=0: 1-CTA tiles).
+// The A-resident mode (ARES) halves the fill again (32 B/clk/SM) but leaves only a 4 x 16 KB ring for W: the MMA thread
+// waits for operands just as long (40 %) with a quarter of the bytes in flight -- the slot turnaround (TMA issue ->
+// landed -> MMAs retired -> commit -> TMA thread) is ~3 k cycles however few bytes move, so what counts is bytes IN
+// FLIGHT, and a resident panel takes them away.  2 % slower end to end; opt-in BOFI_ARES=1.
 #pragma once
 #include "gemm_tc.cuh"
 
@@ -28,16 +31,31 @@ constexpr int k2BN = 256;
 #define BOFI_TC2_STAGES 6
 #endif
 constexpr int k2Stages = BOFI_TC2_STAGES;
-constexpr int k2Staging = k2Stages >= 6 ? 1 : 2;     // staging tiles per epilogue warp (what is left of the 227 KB)
-struct Smem2 {
-  static constexpr int kABytes = kBM * kBK * 2;                    // 16 KB: this CTA's rows of A
-  static constexpr int kBBytes = (k2BN / 2) * kBK * 2;             // 16 KB: this CTA's half of W
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kOutOffset = k2Stages * kStageBytes;
-  static constexpr int kOutBytes = 8 * k2Staging * 4096;           // staging tiles of the eight epilogue warps
+constexpr int k2PanelKB = 8;                         // A-resident mode: K <= 8 * 64
+// ARES (A-resident, K <= 512): the CTA keeps its 128 rows of A for the WHOLE contraction in shared memory (8 k-block
+// slices, 128 KB) while it walks the column tiles of that row panel, and streams only its half of W: 16 KB per CTA per
+// k-block, 32 B/clk/SM at the tensor pipe's full rate -- below the ~46 B/clk/SM the L2 delivers chip-wide, where the
+// streaming tile (32 KB per k-block) is capped at ~72 % and the 1-CTA tile (48 KB) at ~48 % (profiles/r01d_gemm_stalls.txt).
+// KPS = k-blocks per ring stage.  tools/tma_feed_bench.cu: one SM's TMA path completes about one STAGE (barrier
+// round) per ~1000 clk however many bytes it carries -- 16 KB boxes: 17 B/clk/SM, two of them per stage: 30, one
+// 64 KB box: 65-77 -- so a stage must carry as many bytes as possible per instruction.  With KPS = 2 the operands
+// are described as 3-D tensors (64 k, rows, K/64 k-blocks) and ONE box (64, 128, 2) brings two consecutive
+// 128B-swizzled k-block tiles (32 KB); a stage is 64 KB per CTA and the ring has 3 of them.
+template <bool ARES, int KPS = 1>
+struct Smem2T {
+  static constexpr int kABytes = kBM * kBK * 2;                    // 16 KB: this CTA's rows of A, one k-block
+  static constexpr int kBBytes = (k2BN / 2) * kBK * 2;             // 16 KB: this CTA's half of W, one k-block
+  static constexpr int kStages = (ARES ? 4 : k2Stages) / KPS;
+  static constexpr int kStaging = (ARES || kStages * KPS >= 6) ? 1 : 2;  // staging tiles per epilogue warp (what is left of the 227 KB)
+  static constexpr int kPanelBytes = ARES ? k2PanelKB * kABytes : 0;
+  static constexpr int kStageBytes = KPS * (ARES ? kBBytes : kABytes + kBBytes);
+  static constexpr int kRingOffset = kPanelBytes;
+  static constexpr int kOutOffset = kRingOffset + kStages * kStageBytes;
+  static constexpr int kOutBytes = 8 * kStaging * 4096;            // staging tiles of the eight epilogue warps
   static constexpr int kBarOffset = kOutOffset + kOutBytes;
-  static constexpr int kTotal = kBarOffset + 256 + 1024;
+  static constexpr int kTotal = kBarOffset + 512 + 1024;
 };
+static_assert(Smem2T<true>::kTotal <= 232448 && Smem2T<false>::kTotal <= 232448 && Smem2T<false, 2>::kTotal <= 232448, "shared memory budget");
 
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -48,6 +66,12 @@ __device__ __forceinline__ void tma_load_2d_2sm(uint32_t smem_dst, const CUtenso
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_dst), "l"(tmap), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_dst), "l"(tmap), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -75,15 +99,15 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
       : "memory");
 }
 
-template <typename TOut, bool RELU, bool RESID, bool REDUCE = false>
+template <typename TOut, bool RELU, bool RESID, bool REDUCE = false, bool ARES = false, int KPS = 1>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, const float* residual, int ldr,
                int M, int N, int K, int relu, const int* live_rows, const int* rows_dev) {
   pdl_launch();
-  constexpr int BN = k2BN, STAGES = k2Stages;
+  using L = Smem2T<ARES, KPS>;
+  constexpr int BN = k2BN, STAGES = L::kStages, k2Staging = L::kStaging;
   constexpr bool A_MN = false, B_MN = false;
-  using L = Smem2;
   uint32_t rank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
   extern __shared__ uint8_t smem_raw[];
@@ -93,7 +117,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* empty_bar = bars + STAGES;            // [STAGES]  MMA -> TMA
   uint64_t* tmem_full_bar = bars + 2 * STAGES;    // [2]       MMA -> epilogue
   uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;   // [2]   epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* a_full_bar = bars + 2 * STAGES + 4;   // [8]  ARES: A slice kb landed (both CTAs' bytes, leader's barrier)
+  uint64_t* a_empty_bar = a_full_bar + k2PanelKB;  // [8]  ARES: the panel's last tile has consumed slice kb
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty_bar + k2PanelKB);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk_all = (K + kBK - 1) / kBK;      // a K tail is zero-filled by TMA (out-of-bounds box elements)
@@ -115,6 +141,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_init(smem_u32(&tmem_full_bar[a]), 1);
         mbar_init(smem_u32(&tmem_empty_bar[a]), 16);  // one arrival per epilogue warp of BOTH CTAs (only the leader's is used)
       }
+      for (int a = 0; a < k2PanelKB; ++a) {
+        mbar_init(smem_u32(&a_full_bar[a]), 1);
+        mbar_init(smem_u32(&a_empty_bar[a]), 1);
+      }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -134,15 +164,32 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int ntiles_mn = ((m_eff + 2 * kBM - 1) / (2 * kBM)) * tiles_n;     // 256-row tile pairs
   const int ntiles = step_is_dead(live_rows) ? 0 : ntiles_mn;
   const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;                  // cluster id / number of clusters
+  // Work items of this pair: strided over the pairs, or (ARES) one contiguous range so that the column tiles of a row
+  // panel follow each other and the resident A slices are loaded once per panel.
+  const int it_begin = ARES ? (int)(((long long)cid * ntiles) / ncl) : cid;
+  const int it_end = ARES ? (int)(((long long)(cid + 1) * ntiles) / ncl) : ntiles;
+  const int it_step = ARES ? 1 : ncl;
+  uint8_t* ring = smem + L::kRingOffset;
 
   if (warp == 0) {
     if (lane == 0) {
-      int it = 0;
+      int it = 0, pc = 0;                          // ring position; ARES: row panels this pair has finished
       PROF_DECL(w_slot = 0);
-      for (int item = cid; item < ntiles; item += ncl) {
+      for (int item = it_begin; item < it_end; item += it_step) {
         const int tile = item % ntiles_mn, kb0 = (item / ntiles_mn) * nk_per, kb1 = min(nk_all, kb0 + nk_per);
         const int m0 = (tile / tiles_n) * 2 * kBM + (int)rank * kBM, n0 = (tile % tiles_n) * BN;
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const bool first = ARES && (item == it_begin || tile % tiles_n == 0);
+        const bool last = ARES && (item == it_end - 1 || tile % tiles_n == tiles_n - 1);
+        for (int kb = kb0; kb < kb1; kb += KPS, ++it) {
+          if constexpr (ARES) {
+            static_assert(!ARES || KPS == 1, "the A-resident mode keeps one k-block per stage");
+            if (first) {   // (re)load slice kb of the panel once the previous panel's last tile is done with it
+              PROF_WAIT(w_slot, mbar_wait(smem_u32(&a_empty_bar[kb]), (uint32_t)(pc & 1) ^ 1u));
+              const uint32_t ab = smem_u32(&a_full_bar[kb]);
+              if (rank == 0) mbar_expect_tx(ab, 2 * L::kABytes);
+              tma_load_2d_2sm(smem_u32(smem + kb * L::kABytes), &tmA, ab, kb * kBK, m0);
+            }
+          }
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           PROF_WAIT(w_slot, mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1));
@@ -150,44 +197,66 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           // clear); the leader announces the bytes of the pair
           const uint32_t fb = smem_u32(&full_bar[s]);
           if (rank == 0) mbar_expect_tx(fb, 2 * L::kStageBytes);
-          const uint32_t a_dst = smem_u32(smem + s * L::kStageBytes);
-          tma_load_2d_2sm(a_dst, &tmA, fb, kb * kBK, m0);                                   // this CTA's 128 rows of A
-          tma_load_2d_2sm(a_dst + L::kABytes, &tmB, fb, kb * kBK, n0 + (int)rank * (BN / 2));   // this CTA's half of W
+          const uint32_t a_dst = smem_u32(ring + s * L::kStageBytes);
+          if constexpr (KPS == 1) {
+            if constexpr (!ARES) tma_load_2d_2sm(a_dst, &tmA, fb, kb * kBK, m0);                 // this CTA's 128 rows of A
+            tma_load_2d_2sm(a_dst + (ARES ? 0 : L::kABytes), &tmB, fb, kb * kBK, n0 + (int)rank * (BN / 2));   // this CTA's half of W
+          } else {
+            // one 3-D box per operand: KPS consecutive k-block tiles  [A kb | A kb+1 | W kb | W kb+1]
+            tma_load_3d_2sm(a_dst, &tmA, fb, 0, m0, kb);
+            tma_load_3d_2sm(a_dst + KPS * L::kABytes, &tmB, fb, 0, n0 + (int)rank * (BN / 2), kb);
+          }
         }
+        if (last) ++pc;
       }
 #ifdef BOFI_GEMM_PROF
-      if (ntiles > cid && rank == 0) PROF_ADD(prof_bucket(N, K, RESID), 3, w_slot);
+      if (it_end > it_begin && rank == 0) PROF_ADD(prof_bucket(N, K, RESID), 3, w_slot);
 #endif
     }
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * kBM, BN, A_MN, B_MN);
-      int it = 0, t = 0;
+      int it = 0, t = 0, pc = 0;
       PROF_DECL(w_acc = 0, w_full = 0, t_begin = PROF_T());
-      for (int item = cid; item < ntiles; item += ncl, ++t) {
+      for (int item = it_begin; item < it_end; item += it_step, ++t) {
         const int kb0 = (item / ntiles_mn) * nk_per, kb1 = min(nk_all, kb0 + nk_per);
+        const int tile_n = (item % ntiles_mn) % tiles_n;
+        const bool first = ARES && (item == it_begin || tile_n == 0);
+        const bool last = ARES && (item == it_end - 1 || tile_n == tiles_n - 1);
         const int as = t & 1;
         const uint32_t aph = (t >> 1) & 1;
         PROF_WAIT(w_acc, mbar_wait(smem_u32(&tmem_empty_bar[as]), aph ^ 1));     // epilogue drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; kb += KPS, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
+          if constexpr (ARES) {
+            if (first) PROF_WAIT(w_full, mbar_wait(smem_u32(&a_full_bar[kb]), (uint32_t)(pc & 1)));
+          }
           PROF_WAIT(w_full, mbar_wait(smem_u32(&full_bar[s]), ph));
           tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
-          const uint64_t adesc = A_MN ? make_sw128_desc_mn(a_addr) : make_sw128_desc(a_addr);
-          const uint64_t bdesc = B_MN ? make_sw128_desc_mn(a_addr + L::kABytes) : make_sw128_desc(a_addr + L::kABytes);
-          // per K step of 16: K-major +32 bytes inside the 128-byte swizzle row; MN-major +16 rows of 128 bytes (encoded >> 4)
-          constexpr uint64_t a_step = A_MN ? 128 : 2, b_step = B_MN ? 128 : 2;
+          const uint32_t s_addr = smem_u32(ring + s * L::kStageBytes);
 #pragma unroll
-          for (int k = 0; k < kBK / kUK; ++k) {
-            umma_bf16_2sm(tmem_d, adesc + a_step * k, bdesc + b_step * k, idesc, ((kb - kb0) | k) != 0);
+          for (int kk = 0; kk < KPS; ++kk) {
+            const uint32_t a_addr = ARES ? smem_u32(smem + kb * L::kABytes) : s_addr + kk * L::kABytes;
+            const uint32_t b_addr = ARES ? s_addr : s_addr + KPS * L::kABytes + kk * L::kBBytes;
+            const uint64_t adesc = A_MN ? make_sw128_desc_mn(a_addr) : make_sw128_desc(a_addr);
+            const uint64_t bdesc = B_MN ? make_sw128_desc_mn(b_addr) : make_sw128_desc(b_addr);
+            // per K step of 16: K-major +32 bytes inside the 128-byte swizzle row; MN-major +16 rows of 128 bytes (encoded >> 4)
+            constexpr uint64_t a_step = A_MN ? 128 : 2, b_step = B_MN ? 128 : 2;
+#pragma unroll
+            for (int k = 0; k < kBK / kUK; ++k) {
+              umma_bf16_2sm(tmem_d, adesc + a_step * k, bdesc + b_step * k, idesc, ((kb - kb0) | kk | k) != 0);
+            }
           }
           umma_commit_2sm(smem_u32(&empty_bar[s]));      // frees the stage in BOTH CTAs when these MMAs retire
+          if constexpr (ARES) {
+            if (last) umma_commit_2sm(smem_u32(&a_empty_bar[kb]));   // the panel's slice may be overwritten in both CTAs
+          }
         }
         umma_commit_2sm(smem_u32(&tmem_full_bar[as]));   // accumulator complete: both CTAs' epilogues
+        if (last) ++pc;
       }
 #ifdef BOFI_GEMM_PROF
       if (t > 0) {
@@ -210,7 +279,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int nstore = 0;
     int t = 0;
     PROF_DECL(w_tfull = 0, w_stage = 0, w_tld = 0, t_math = 0, t_store = 0, t_arrive = 0, t_begin = PROF_T());
-    for (int item = cid; item < ntiles; item += ncl, ++t) {
+    for (int item = it_begin; item < it_end; item += it_step, ++t) {
       const int tile = item % ntiles_mn;
       const int m0 = (tile / tiles_n) * 2 * kBM + (int)rank * kBM, n0 = (tile % tiles_n) * BN;
       const int as = t & 1;
@@ -375,12 +444,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 
-template <typename TOut, bool RELU, bool RESID, bool REDUCE = false>
+template <typename TOut, bool RELU, bool RESID, bool REDUCE = false, bool ARES = false, int KPS = 1>
 inline cudaError_t launch2(cudaStream_t s, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const float* bias,
                            const float* residual, int ldr, int M, int N, int K, int relu, const int* live_rows, const int* rows_dev) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<TOut, RELU, RESID, REDUCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<TOut, RELU, RESID, REDUCE, ARES, KPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2T<ARES, KPS>::kTotal);
     if (e != cudaSuccess) return e;
     configured = true;
   }
@@ -390,7 +459,7 @@ inline cudaError_t launch2(cudaStream_t s, const CUtensorMap& tmA, const CUtenso
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * clusters);
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = Smem2::kTotal;
+  cfg.dynamicSmemBytes = Smem2T<ARES, KPS>::kTotal;
   cfg.stream = s;
   cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
@@ -401,33 +470,46 @@ inline cudaError_t launch2(cudaStream_t s, const CUtensorMap& tmA, const CUtenso
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  return cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<TOut, RELU, RESID, REDUCE>, tmA, tmB, tmC, bias, residual, ldr, M, N, K, relu, live_rows, rows_dev);
+  return cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<TOut, RELU, RESID, REDUCE, ARES, KPS>, tmA, tmB, tmC, bias, residual, ldr, M, N, K, relu, live_rows, rows_dev);
 }
 
-// Same contract as gemm_tc (K-major A [M,K], W [N,K]).
+// Same contract as gemm_tc (K-major A [M,K], W [N,K]).  `want_ares`: A-resident tiles where the shape allows (opt-in,
+// BOFI_ARES=1 -- measured 2 % slower end to end than the streaming tile, see the header).
 template <typename TOut>
 inline cudaError_t gemm_tc2(cudaStream_t s, const bf16* A, int lda, const bf16* W, int ldw, const float* bias, const float* residual, int ldr,
-                            TOut* C, int ldc, int M, int N, int K, int relu, const int* live_rows, const int* rows_dev) {
+                            TOut* C, int ldc, int M, int N, int K, int relu, const int* live_rows, const int* rows_dev, bool want_ares = false, int kps = 2) {
   if (M <= 0 || N <= 0) return cudaSuccess;
   if (lda % 8 != 0 || ldw % 8 != 0 || (ldc * sizeof(TOut)) % 16 != 0 || (residual && ldr % 4 != 0) || !bias) return cudaErrorInvalidValue;
-  const CUtensorMap* tmA = cached_tmap(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBM);
-  const CUtensorMap* tmB = cached_tmap(W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, k2BN / 2);
+  // A-resident tiles: the whole contraction of a row panel fits the 128 KB panel, and the panel is reused by >= 4 column tiles
+  const bool ares = want_ares && !residual && K <= k2PanelKB * kBK && N >= 4 * k2BN;
+  const bool kps2 = kps >= 2 && !ares && K % (2 * kBK) == 0;      // two k-blocks per stage, one 3-D box per operand
+  const CUtensorMap* tmA = kps2 ? cached_tmap_kblocks(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBM, 2)
+                                : cached_tmap(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBM);
+  const CUtensorMap* tmB = kps2 ? cached_tmap_kblocks(W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, k2BN / 2, 2)
+                                : cached_tmap(W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, k2BN / 2);
   const CUtensorMap* tmC = cached_tmap(C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, (int)sizeof(TOut));
   if (!tmA || !tmB || !tmC) return cudaErrorInvalidValue;
-#define BOFI_TC2(RELU_, RESID_) launch2<TOut, RELU_, RESID_>(s, *tmA, *tmB, *tmC, bias, residual, ldr, M, N, K, relu, live_rows, rows_dev)
+#define BOFI_TC2(RELU_, RESID_) \
+  (kps2 ? launch2<TOut, RELU_, RESID_, false, false, 2>(s, *tmA, *tmB, *tmC, bias, residual, ldr, M, N, K, relu, live_rows, rows_dev) \
+        : launch2<TOut, RELU_, RESID_>(s, *tmA, *tmB, *tmC, bias, residual, ldr, M, N, K, relu, live_rows, rows_dev))
+#define BOFI_TC2A(RELU_) launch2<TOut, RELU_, false, false, true>(s, *tmA, *tmB, *tmC, bias, nullptr, 0, M, N, K, relu, live_rows, rows_dev)
   if constexpr (sizeof(TOut) == 4) {
     if (residual && relu) return cudaErrorInvalidValue;
     if (residual && inplace_reduce() && (const void*)residual == (const void*)C && ldr == ldc)
-      return launch2<TOut, false, false, true>(s, *tmA, *tmB, *tmC, bias, nullptr, 0, M, N, K, 0, live_rows, rows_dev);
+      return kps2 ? launch2<TOut, false, false, true, false, 2>(s, *tmA, *tmB, *tmC, bias, nullptr, 0, M, N, K, 0, live_rows, rows_dev)
+                  : launch2<TOut, false, false, true>(s, *tmA, *tmB, *tmC, bias, nullptr, 0, M, N, K, 0, live_rows, rows_dev);
     if (residual) return BOFI_TC2(false, true);
+    if (ares) return relu ? BOFI_TC2A(true) : BOFI_TC2A(false);
     if (relu) return BOFI_TC2(true, false);
     return BOFI_TC2(false, false);
   } else {
     if (residual) return cudaErrorInvalidValue;
+    if (ares) return relu ? BOFI_TC2A(true) : BOFI_TC2A(false);
     if (relu) return BOFI_TC2(true, false);
     return BOFI_TC2(false, false);
   }
 #undef BOFI_TC2
+#undef BOFI_TC2A
 }
 
 }  // namespace tc

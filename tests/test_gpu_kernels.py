@@ -56,7 +56,10 @@ def test_linear_fp32_simt(engines, M, N, K, relu, resid):
 
 @pytest.mark.parametrize("M,N,K,relu,resid", [(128, 128, 64, False, False), (300, 512, 512, False, True),
                                               (1000, 1536, 2048, True, False), (257, 9496, 512, False, False),
-                                              (36864, 512, 2048, True, False)])
+                                              (36864, 512, 2048, True, False),
+                                              # wide K=512 shapes on 2-CTA tile pairs (M tail, N tail, K tail)
+                                              (5000, 2048, 512, True, False), (2304, 9496, 512, False, False),
+                                              (40000, 1024, 512, False, False), (2048, 1536, 448, False, False)])
 def test_linear_bf16_tcgen05(engines, M, N, K, relu, resid):
     _, e16 = engines
     g = torch.Generator().manual_seed(M + N + 1)
@@ -146,9 +149,9 @@ def test_attention_single_query_fp32(engines, Tk):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("env", ["BOFI_GEMM2", "BOFI_LNFUSE"])
+@pytest.mark.parametrize("env", ["BOFI_GEMM2", "BOFI_ARES", "BOFI_LNFUSE"])
 def test_optional_gemm_variants_reproduce_the_default_path(env, monkeypatch):
-    """The other tcgen05 variants (1-CTA tiles via BOFI_GEMM2=0, the opt-in LayerNorm-fused A-resident GEMM) must give
+    """The other tcgen05 variants (1-CTA tiles via BOFI_GEMM2=0, the opt-in A-resident 2-CTA tiles and LayerNorm-fused GEMM) must give
     the default bf16 path's results: same boxes, logits within bf16 rounding of the LayerNorm output."""
     import torch
     from boficap_b200 import synth
@@ -181,4 +184,4 @@ def test_optional_gemm_variants_reproduce_the_default_path(env, monkeypatch):
     a, b = base[1][same], var[1][same]
     assert not bool(b.isnan().any())
     err = float((a - b).abs().max())
-    assert err < (1e-5 if env == "BOFI_GEMM2" else 2e-2), err
+    assert err < (2e-2 if env == "BOFI_LNFUSE" else 1e-5), err
