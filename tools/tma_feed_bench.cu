@@ -13,6 +13,7 @@
 //   4  tensor 3D boxes (64 k, 128 rows, 2 k-blocks) = 32 KB per instruction: two consecutive 16 KB k-block tiles
 //   5  tensor 3D boxes (64 k, 128 rows, 4 k-blocks) = 64 KB per instruction
 //   6  tensor 3D boxes (64 k, 256 rows, 2 k-blocks) = 64 KB per instruction
+//   9  as 0, but the boxes of a stage alternate between TWO tensor maps (two separate buffers), as A and W do in a GEMM
 //   7  one 16 KB tensor box (TMA) + 16 KB by cp.async (LDGSTS, 16 B per thread, 128 threads of four extra warps) per stage
 //   8  32 KB per stage by cp.async only (128 threads)
 //   +10  (e.g. 11) the same, while eight other warps each keep issuing 4 KB TMA STORES (32 x 128 B, the GEMM epilogue's)
@@ -25,6 +26,19 @@
 
 using namespace bofi::tc;
 
+// SPIN=1: poll with the non-suspending mbarrier.test_wait instead of try_wait (separates the memory path from the
+// wake-up behaviour of a suspended try_wait)
+#ifdef SPIN
+__device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  }
+}
+#else
+__device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
+#endif
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -53,7 +67,7 @@ static bool make_tmap_3d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64
 __global__ void __launch_bounds__(320, 1)
 feed_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm256, const __grid_constant__ CUtensorMap tm3a,
             const __grid_constant__ CUtensorMap tm3b, const __grid_constant__ CUtensorMap tm3c, const uint8_t* flat,
-            const __grid_constant__ CUtensorMap tmS4, const __grid_constant__ CUtensorMap tmS16,
+            const __grid_constant__ CUtensorMap tmS4, const __grid_constant__ CUtensorMap tmS16, const __grid_constant__ CUtensorMap tm128b,
             int mode, int stages, int stage_bytes, int iters, int rows_total, long long* cycles, unsigned long long* stores_done) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -74,7 +88,7 @@ feed_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ C
     for (int it = 0; it < iters; ++it) {
       const int s = it % stages;
       const uint32_t ph = (it / stages) & 1;
-      mbar_wait(smem_u32(&empty[s]), ph ^ 1);
+      wait_bar(smem_u32(&empty[s]), ph ^ 1);
       const uint32_t fb = smem_u32(&full[s]);
       if (mode == 8) continue;                       // nothing for the TMA thread to do
       mbar_expect_tx(fb, mode == 7 ? 16384 : stage_bytes);
@@ -89,6 +103,8 @@ feed_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ C
         for (int i = 0; i < stage_bytes / 65536; ++i) tma_load_3d(dst + i * 65536, &tm3b, fb, 0, (r0 + 128 * i) % rows_total, (kb & 1) * 4);
       } else if (mode == 6) {
         for (int i = 0; i < stage_bytes / 65536; ++i) tma_load_3d(dst + i * 65536, &tm3c, fb, 0, r0, (kb & 3) * 2);
+      } else if (mode == 9) {
+        for (int i = 0; i < stage_bytes / 16384; ++i) tma_load_2d(dst + i * 16384, (i & 1) ? &tm128b : &tm128, fb, kb * 64, (r0 + 128 * i) % rows_total);
       } else if (mode == 0) {
         for (int i = 0; i < stage_bytes / 16384; ++i) tma_load_2d(dst + i * 16384, &tm128, fb, kb * 64, (r0 + 128 * i) % rows_total);
       } else if (mode == 1) {
@@ -102,7 +118,7 @@ feed_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ C
     for (int it = 0; it < iters; ++it) {
       const int s = it % stages;
       const uint32_t ph = (it / stages) & 1;
-      mbar_wait(smem_u32(&full[s]), ph);
+      wait_bar(smem_u32(&full[s]), ph);
       mbar_arrive(smem_u32(&empty[s]));
     }
     cycles[blockIdx.x] = clock64() - t0;
@@ -115,7 +131,7 @@ feed_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ C
     for (int it = 0; it < iters; ++it) {
       const int s = it % stages;
       const uint32_t ph = (it / stages) & 1;
-      mbar_wait(smem_u32(&empty[s]), ph ^ 1);
+      wait_bar(smem_u32(&empty[s]), ph ^ 1);
       const int kb = it & 7;
       const int r0 = (int)(((long long)blockIdx.x * 131 + (long long)(it >> 3) * 7) % (rows_total / 256)) * 256 + 128;
       const uint32_t dst = smem_u32(smem + (size_t)s * stage_bytes + (mode == 7 ? 16384 : 0));
@@ -158,6 +174,11 @@ int main() {
   cudaMalloc(&sbuf, (size_t)148 * 256 * 64 * 2);
   CUtensorMap tmS4, tmS16;
   if (!make_tmap(&tmS4, sbuf, 148 * 256, 64, 64, 32, 2) || !make_tmap(&tmS16, sbuf, 148 * 256, 64, 64, 128, 2)) { printf("tmap failed\n"); return 1; }
+  __nv_bfloat16* buf2;
+  cudaMalloc(&buf2, (size_t)rows * K * 2);
+  cudaMemset(buf2, 0, (size_t)rows * K * 2);
+  CUtensorMap tm128b;
+  if (!make_tmap(&tm128b, buf2, rows, K, K, 128, 2)) { printf("tmap failed\n"); return 1; }
   unsigned long long* stores_done;
   cudaMalloc(&stores_done, 8);
   cudaFuncSetAttribute(feed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
@@ -167,20 +188,26 @@ int main() {
   const int iters = 4000;
   struct Cfg { int mode, stages, stage_bytes, grid; };
   std::vector<Cfg> cfgs;
-  for (int grid : {148, 16}) {                       // 16 CTAs: the per-SM limit without chip-wide contention                       // 16 CTAs: the per-SM limit without chip-wide contention
+  for (int grid : {1}) {
+    if (grid == 1) break;                       // 16 CTAs: the per-SM limit without chip-wide contention                       // 16 CTAs: the per-SM limit without chip-wide contention
     for (int mode : {0, 1, 2, 4})
       for (int st : {1, 2, 4, 6}) cfgs.push_back({mode, st, 32768, grid});
     for (int mode : {5, 6})
       for (int st : {1, 2, 3}) cfgs.push_back({mode, st, 65536, grid});
     for (int st : {4, 8, 12}) cfgs.push_back({0, st, 16384, grid});
   }
-  for (int mode : {0, 10, 20, 1, 11, 21, 5, 15, 25}) cfgs.push_back({mode, mode % 10 == 5 ? 2 : 4, mode % 10 == 5 ? 65536 : 32768, 148});
+  for (int mode : {0}) cfgs.push_back({mode, mode % 10 == 5 ? 2 : 4, mode % 10 == 5 ? 65536 : 32768, 148});
+  for (int n : {2, 4}) { cfgs.push_back({0, 2, n * 16384, 148}); cfgs.push_back({9, 2, n * 16384, 148}); cfgs.push_back({9, 4, n * 16384, 148}); }
+  // how a stage's cost grows with the number of boxes on its barrier
+  for (int n : {1, 2, 3, 4, 6}) cfgs.push_back({0, 2, n * 16384, 148});
+  for (int n : {1, 2, 3}) cfgs.push_back({1, 2, n * 32768, 148});
+  for (int n : {1, 2, 3}) cfgs.push_back({4, 2, n * 32768, 148});
   for (int mode : {0, 7, 8})
     for (int st : {2, 4, 6}) cfgs.push_back({mode, st, 32768, 148});
   for (const Cfg& c : cfgs) {
     for (int rep = 0; rep < 2; ++rep) {
       cudaMemset(stores_done, 0, 8);
-      feed_kernel<<<c.grid, 320, c.stages * c.stage_bytes + 32768 + 1024>>>(tm128, tm256, tm3a, tm3b, tm3c, (const uint8_t*)buf, tmS4, tmS16, c.mode, c.stages, c.stage_bytes, iters, rows, cyc, stores_done);
+      feed_kernel<<<c.grid, 320, c.stages * c.stage_bytes + 32768 + 1024>>>(tm128, tm256, tm3a, tm3b, tm3c, (const uint8_t*)buf, tmS4, tmS16, tm128b, c.mode, c.stages, c.stage_bytes, iters, rows, cyc, stores_done);
       if (cudaDeviceSynchronize() != cudaSuccess) { printf("kernel failed: %s\n", cudaGetErrorString(cudaGetLastError())); return 1; }
     }
     std::vector<long long> h(c.grid);
