@@ -208,7 +208,7 @@ def bench_xe(a, rank, local_rank, world):
                                        "%d regions, %s, dropout %s" % (B, spi, R, a.precision, "off" if a.no_dropout else "on (p=0.1, att_embed 0.5)"),
                            "parallelism": "data-parallel replicas x%d, one NCCL all-reduce of the %.0f MB flat gradient buffer" % (world, flat_g.numel() * 4 / 1e6)},
                 "loss_first": first, "loss_last": float(losses[0]), "gpu_launches": launches * a.steps, "clocks": clocks,
-                "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05), all %d launches of a step" % g["launches"],
+                "roofline": {"bound": "tensor", "kernel": "gemm_tc2_kernel / gemm_tc_kernel (tcgen05), all %d launches of a step" % g["launches"],
                              "achieved": tf, "peak": sustained, "unit": "TFLOP/s", "frac": tf / sustained, "traffic": None,
                              "share_of_profiled_kernel_time": g["ms"] / total_ms if total_ms else None,
                              "classes": {k: {"launches": v["launches"], "ms": round(v["ms"], 3)} for k, v in prof.items()}}}
@@ -415,14 +415,15 @@ def main():
     if a.precision == "bf16" and g["ms"] > 0:
         # dominant kernel = gemm_tc_kernel (tcgen05): algorithmic flops = sum of 2*M*N*K over its launches in one
         # step, duration = sum of the CUDA-event durations around each launch (library-side, launching stream)
-        achieved, kname = gemm_tflops, "gemm_tc_kernel (tcgen05), all %d launches of a step" % g["launches"]
-        # ncu --set full capture of the FFN1 shape (profiles/r01c_gemm_ncu_summary.txt): dram read + write per launch
-        traffic = 132.9e6
+        achieved, kname = gemm_tflops, "gemm_tc2_kernel / gemm_tc_kernel (tcgen05), all %d launches of a step" % g["launches"]
+        # ncu --set full capture of the FFN1 shape (profiles/r01d_gemm_ncu_summary.txt): dram read + write per launch
+        traffic = 135.1e6
         dom = {"launches_per_step": g["launches"], "us_per_launch": g["ms"] / g["launches"] * 1e3,
                "gflop_per_launch": g["flops"] / g["launches"] / 1e9, "share_of_step": g["ms"] / total_ms,
-               "traffic_note": "traffic = ncu dram bytes of one M=36864 N=2048 K=512 launch (algorithmic 189 MB; most of the "
-                               "output stays in L2).  The same capture shows 906 MB of L2->SM fills per launch (13.5 TB/s): the K=512 "
-                               "shapes are bound by shared-memory fill, not by DRAM or the tensor pipe (58 % active)"}
+               "traffic_note": "traffic = ncu dram bytes of one M=36864 N=2048 K=512 launch of gemm_tc2_kernel (algorithmic 189 MB; most "
+                               "of the output stays in L2).  The same capture shows 605 MB of L2->SM fills per launch (906 MB with 1-CTA "
+                               "tiles); tools/gemm_stalls.py: the MMA-issuing thread waits for operands 40-55 % of the time, for the "
+                               "epilogue 1-5 % (profiles/r01d_gemm_stalls.txt)"}
         if top and top["ms"] > 0:
             dom["slowest_shape"] = {"M": top["M"], "N": top["N"], "K": top["K"], "launches": top["launches"],
                                     "us_per_launch": top["ms"] / top["launches"] * 1e3,
