@@ -556,15 +556,17 @@ __global__ void __launch_bounds__(kVocabThreads, 3)
 vocab_epilogue_kernel(const float* __restrict__ logits, int ldl, int V, float* __restrict__ logp_out,
                       long long* __restrict__ seq_out, const int* __restrict__ total_len, int total_off, int L,
                       int do_logsoftmax, int* __restrict__ tok_out_i32, Sampler sp, float* __restrict__ slot_entropy,
-                      float* __restrict__ slot_logp) {
+                      float* __restrict__ slot_logp, int row0) {
   pdl_enter();
   // The whole row lives in registers: logits are read from HBM exactly once (128-bit loads, all independent),
   // max / argmax / sum-exp are block reductions, and the log-probs are written once.
   __shared__ ArgMax s_am[kVocabThreads / 32];
   __shared__ float s_sum[kVocabThreads / 32];
-  const int row = blockIdx.x;              // b * L + t
+  // `logits` holds the rows [row0, row0 + gridDim.x) of the step (the NAIC projection runs in L2-sized row chunks);
+  // every other array is indexed by the global row
+  const int row = row0 + blockIdx.x;       // b * L + t
   const int b = row / L, t = row - b * L;
-  const float4* z4 = reinterpret_cast<const float4*>(logits + (size_t)row * ldl);
+  const float4* z4 = reinterpret_cast<const float4*>(logits + (size_t)blockIdx.x * ldl);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n4 = (V + 3) >> 2;             // ldl >= 4 * n4 (padded pitch); columns >= V are ignored below
   float4 v[kVocabVec];
@@ -661,7 +663,7 @@ vocab_epilogue_kernel(const float* __restrict__ logits, int ldl, int V, float* _
       int tok = picked;
       if (total_len && t >= total_len[b] + total_off) tok = 0;
       slot_entropy[row] = tot;
-      slot_logp[row] = (logits[(size_t)row * ldl + tok] - mx) - lse;
+      slot_logp[row] = (logits[(size_t)blockIdx.x * ldl + tok] - mx) - lse;
     }
     __syncthreads();
   }
@@ -680,7 +682,7 @@ vocab_epilogue_kernel(const float* __restrict__ logits, int ldl, int V, float* _
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int c = c0 + q * kVocabThreads + tid;
-        if (c < V) o[c] = stage[q * kVocabThreads + tid];
+        if (c < V) __stcs(o + c, stage[q * kVocabThreads + tid]);     // streamed: written once, read by nobody on the device
       }
       __syncthreads();
     }

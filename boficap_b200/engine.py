@@ -244,10 +244,12 @@ class BofiEngine:
                                                x.numel() // x.shape[-1]))
         return out
 
-    def linear(self, a, w, bias=None, residual=None, relu=False):
+    def linear(self, a, w, bias=None, residual=None, relu=False, inplace=False):
+        """Unit entry of the GEMM backends.  inplace=True: `residual` is updated in place (x += a . w^T + b), the form
+        the decode path uses for the O-projections and FFN2 (TMA reduce stores on the tcgen05 backends)."""
         M, K = a.shape
         N = w.shape[0]
-        out = torch.empty(M, N, device=a.device, dtype=torch.float32)
+        out = residual if inplace else torch.empty(M, N, device=a.device, dtype=torch.float32)
         _lib.check(self.lib.bofi_linear_f32(self.handle, self._stream(), _ptr(a), _ptr(w), _ptr(bias), _ptr(residual),
                                             _ptr(out), M, N, K, int(relu)))
         return out

@@ -78,6 +78,25 @@ def test_linear_bf16_tcgen05(engines, M, N, K, relu, resid):
     assert err < 2e-4, err
 
 
+@pytest.mark.parametrize("M,N,K", [(36864, 512, 2048), (20480, 512, 512), (300, 512, 512), (1000, 1024, 512), (2049, 520, 128)])
+def test_linear_bf16_inplace_residual(engines, M, N, K):
+    """x += a . W^T + b in place: the epilogue hands (acc + b) to the L2 as a TMA reduce-add (2-CTA pairs for M >= 2048,
+    1-CTA narrow tiles below); must equal the out-of-place residual form exactly (same fp32 sum) and the fp64 reference."""
+    _, e16 = engines
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).cuda()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    res = torch.randn(M, N, generator=g).cuda()
+    out_of_place = e16.linear(a, w, bias, res, False)
+    x = res.clone()
+    got = e16.linear(a, w, bias, x, False, inplace=True)
+    assert got.data_ptr() == x.data_ptr()
+    ref = a.bfloat16().double() @ w.bfloat16().double().T + bias.double() + res.double()
+    assert (x.double() - ref).abs().max().item() < 2e-4
+    assert torch.equal(x, out_of_place)
+
+
 def test_attention_prefix_masks_and_nan_rows(engines):
     e32, _ = engines
     g = torch.Generator().manual_seed(5)
