@@ -524,6 +524,9 @@ __global__ void fill_window_kernel(DecodeState st, int rows, int L) {
 // workspace, log-probs are written with coalesced 4-byte stores to the caller's [rows, L, V] tensor
 // (V = 9491 rows are not 16-byte aligned).
 // ---------------------------------------------------------------------------------------------
+// torch.max semantics: a NaN is the maximum, ties (and several NaNs) go to the lowest index.  (A branch-free form -- the
+// value mapped to a sortable unsigned key, candidates chosen with selects -- was measured SLOWER in the vocabulary
+// epilogue, 0.52 vs 0.44 ms: the common case here is "the running best stays", which the branches leave after two compares.)
 struct ArgMax { float v; int i; };
 __device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {
   const bool an = a.v != a.v, bn = b.v != b.v;
@@ -534,6 +537,32 @@ __device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {
   if (a.v > b.v) return a;
   if (b.v > a.v) return b;
   return a.i < b.i ? a : b;
+}
+// {last K values of prev, first 4 - K of own} on the output's 16-byte grid (see vocab_epilogue_kernel)
+template <int K>
+__device__ __forceinline__ void store_realigned(float* __restrict__ o, int c4, int n4, int V, const float (&prev)[4], const float (&own)[4]) {
+  const int c = 4 * c4;
+  if constexpr (K == 0) {
+    if (c + 3 < V) __stcs(reinterpret_cast<float4*>(o + c), make_float4(own[0], own[1], own[2], own[3]));
+    else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) if (c + q < V) __stcs(o + c + q, own[q]);
+    }
+  } else {
+    float u[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) u[q] = q < K ? prev[q + 4 - K] : own[q - K];
+    const int s0 = c - K;
+    if (c4 > 0 && s0 + 3 < V) __stcs(reinterpret_cast<float4*>(o + s0), make_float4(u[0], u[1], u[2], u[3]));
+    else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) if (s0 + q >= 0 && s0 + q < V) __stcs(o + s0 + q, u[q]);
+    }
+    if (c4 == n4 - 1) {          // the columns after the last aligned vector belong to nobody's "next" float4
+#pragma unroll
+      for (int q = 4 - K; q < 4; ++q) if (c + q < V) __stcs(o + c + q, own[q]);
+    }
+  }
 }
 
 // Multinomial sampling of CaptionModel.sample_next_word (CaptionModel.py:403-431: logits / temperature, NaN -> -10,
@@ -552,7 +581,10 @@ __device__ __forceinline__ float gumbel_score(const Sampler& sp, float z, int ro
 
 constexpr int kVocabThreads = 512;
 constexpr int kVocabVec = 5;    // float4 per thread: 512 threads x 5 x 4 = 10240 >= Vpad (9504)
-__global__ void __launch_bounds__(kVocabThreads, 3)
+#ifndef BOFI_VOCAB_OCC
+#define BOFI_VOCAB_OCC 3
+#endif
+__global__ void __launch_bounds__(kVocabThreads, BOFI_VOCAB_OCC)
 vocab_epilogue_kernel(const float* __restrict__ logits, int ldl, int V, float* __restrict__ logp_out,
                       long long* __restrict__ seq_out, const int* __restrict__ total_len, int total_off, int L,
                       int do_logsoftmax, int* __restrict__ tok_out_i32, Sampler sp, float* __restrict__ slot_entropy,
@@ -574,6 +606,11 @@ vocab_epilogue_kernel(const float* __restrict__ logits, int ldl, int V, float* _
   for (int i = 0; i < kVocabVec; ++i) {
     const int c4 = tid + i * kVocabThreads;
     v[i] = (c4 < n4) ? z4[c4] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    if (c4 == n4 - 1) {        // pad columns of the last float4 (never written by the GEMM): neutral for max and sum
+      if (4 * c4 + 1 >= V) v[i].y = -INFINITY;
+      if (4 * c4 + 2 >= V) v[i].z = -INFINITY;
+      if (4 * c4 + 3 >= V) v[i].w = -INFINITY;
+    }
   }
   ArgMax am = {-INFINITY, 0x7fffffff};
 #pragma unroll
@@ -622,15 +659,9 @@ vocab_epilogue_kernel(const float* __restrict__ logits, int ldl, int V, float* _
   float lse = 0.f;
   if ((logp_out && do_logsoftmax) || slot_entropy) {
     {
-      float s = 0.f;
+      float s = 0.f;                  // pad / filler elements are -inf: exp(-inf - mx) adds 0 (NaN exactly when the real ones do)
 #pragma unroll
-      for (int i = 0; i < kVocabVec; ++i) {
-        const int c = (tid + i * kVocabThreads) * 4;
-        const float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (c + q < V) s += expf(e[q] - mx);
-      }
+      for (int i = 0; i < kVocabVec; ++i) s += expf(v[i].x - mx) + expf(v[i].y - mx) + expf(v[i].z - mx) + expf(v[i].w - mx);
       s = warp_sum(s);
       if (lane == 0) s_sum[warp] = s;
       __syncthreads();
@@ -669,22 +700,31 @@ vocab_epilogue_kernel(const float* __restrict__ logits, int ldl, int V, float* _
   }
   if (logp_out) {
     float* o = logp_out + (size_t)row * V;
-    // rows of the caller's [rows, L, V] tensor are only 4-byte aligned (V = 9491): stage through shared memory so
-    // that each warp store covers 128 contiguous bytes
-    __shared__ float stage[kVocabThreads * 4];
+    // Rows of the caller's [rows, L, V] tensor are only 4-byte aligned (V = 9491).  Every thread re-cuts its float4 on the
+    // 16-byte grid of the OUTPUT: with k = (address of the row) mod 4 floats, the aligned vector that ends inside this
+    // thread's float4 is {last k values of the previous float4, first 4 - k of its own}.  The previous float4 comes from
+    // the neighbouring lane (lane 0 re-reads it: an L1/L2 hit); 128-bit streamed stores, no staging, no barrier.
+    const int k = (int)((reinterpret_cast<uintptr_t>(o) >> 2) & 3);
+    auto xform = [&](float4 w) {
+      if (do_logsoftmax) { w.x = (w.x - mx) - lse; w.y = (w.y - mx) - lse; w.z = (w.z - mx) - lse; w.w = (w.w - mx) - lse; }
+      return w;
+    };
 #pragma unroll
     for (int i = 0; i < kVocabVec; ++i) {
-      const int c0 = i * kVocabThreads * 4;   // columns handled by this trip of the CTA
-      float4 w = v[i];
-      if (do_logsoftmax) { w.x = (w.x - mx) - lse; w.y = (w.y - mx) - lse; w.z = (w.z - mx) - lse; w.w = (w.w - mx) - lse; }
-      *reinterpret_cast<float4*>(stage + tid * 4) = w;
-      __syncthreads();
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int c = c0 + q * kVocabThreads + tid;
-        if (c < V) __stcs(o + c, stage[q * kVocabThreads + tid]);     // streamed: written once, read by nobody on the device
+      const int c4 = tid + i * kVocabThreads;
+      const float4 w = xform(v[i]);
+      float4 p;
+      p.x = __shfl_up_sync(0xffffffffu, w.x, 1); p.y = __shfl_up_sync(0xffffffffu, w.y, 1);
+      p.z = __shfl_up_sync(0xffffffffu, w.z, 1); p.w = __shfl_up_sync(0xffffffffu, w.w, 1);
+      if (c4 >= n4) continue;
+      if (lane == 0 && c4 > 0 && k != 0) p = xform(z4[c4 - 1]);
+      const float own[4] = {w.x, w.y, w.z, w.w}, prev[4] = {p.x, p.y, p.z, p.w};
+      switch (k) {               // uniform over the CTA
+        case 0: store_realigned<0>(o, c4, n4, V, prev, own); break;
+        case 1: store_realigned<1>(o, c4, n4, V, prev, own); break;
+        case 2: store_realigned<2>(o, c4, n4, V, prev, own); break;
+        default: store_realigned<3>(o, c4, n4, V, prev, own); break;
       }
-      __syncthreads();
     }
   }
   if (tid == 0) {
