@@ -36,16 +36,14 @@ attention_bwd_mma_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __rest
   const int head = blockIdx.x, kb = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t4 = lane & 3;
-  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  // tiles are fetched with cp.async as in attention_mma_kernel (all requests in flight at once, zero-filled tails);
+  // the K/V copies are waited for together with the first Q/dO block
   for (int idx = tid; idx < TKP * 8; idx += 128) {
     const int j = idx >> 3, c = (idx & 7) * 8;
-    uint4 kq = zero4, vq = zero4;
-    if (j < Tk) {
-      kq = *reinterpret_cast<const uint4*>(K + ((size_t)kb * Tk + j) * ldkv + head * kHeadDim + c);
-      vq = *reinterpret_cast<const uint4*>(V + ((size_t)kb * Tk + j) * ldkv + head * kHeadDim + c);
-    }
-    *reinterpret_cast<uint4*>(Ks + j * kAttPitch + c) = kq;
-    *reinterpret_cast<uint4*>(Vs + j * kAttPitch + c) = vq;
+    const bool ok = j < Tk;
+    const size_t src = ((size_t)kb * Tk + (ok ? j : 0)) * ldkv + head * kHeadDim + c;
+    cp_async_16(Ks + j * kAttPitch + c, K + src, ok);
+    cp_async_16(Vs + j * kAttPitch + c, V + src, ok);
   }
   const uint32_t ks_base = (uint32_t)__cvta_generic_to_shared(Ks), vs_base = (uint32_t)__cvta_generic_to_shared(Vs);
   const uint32_t qs_base = (uint32_t)__cvta_generic_to_shared(Qs), os_base = (uint32_t)__cvta_generic_to_shared(Os);
@@ -66,15 +64,12 @@ attention_bwd_mma_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __rest
     __syncthreads();                                       // K/V staged (first trip) / previous phase 2 finished
     for (int idx = tid; idx < kBwdQ * 8; idx += 128) {
       const int i = idx >> 3, c = (idx & 7) * 8;
-      uint4 qq = zero4, oo = zero4;
-      if (q0 + i < nq) {
-        const size_t r = (size_t)kb * nq + q0 + i;
-        qq = *reinterpret_cast<const uint4*>(Q + r * ldq + head * kHeadDim + c);
-        oo = *reinterpret_cast<const uint4*>(dO + r * ldo + head * kHeadDim + c);
-      }
-      *reinterpret_cast<uint4*>(Qs + i * kAttPitch + c) = qq;
-      *reinterpret_cast<uint4*>(Os + i * kAttPitch + c) = oo;
+      const bool ok = q0 + i < nq;
+      const size_t r = (size_t)kb * nq + (ok ? q0 + i : 0);
+      cp_async_16(Qs + i * kAttPitch + c, Q + r * ldq + head * kHeadDim + c, ok);
+      cp_async_16(Os + i * kAttPitch + c, dO + r * ldo + head * kHeadDim + c, ok);
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
     // ------------------------------------------------------------------ phase 1
     {
