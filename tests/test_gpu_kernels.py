@@ -168,9 +168,9 @@ def test_attention_single_query_fp32(engines, Tk):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("env", ["BOFI_GEMM2", "BOFI_ARES", "BOFI_LNFUSE"])
+@pytest.mark.parametrize("env", ["BOFI_GEMM2", "BOFI_KPS", "BOFI_ARES", "BOFI_LNFUSE"])
 def test_optional_gemm_variants_reproduce_the_default_path(env, monkeypatch):
-    """The other tcgen05 variants (1-CTA tiles via BOFI_GEMM2=0, the opt-in A-resident 2-CTA tiles and LayerNorm-fused GEMM) must give
+    """The other tcgen05 variants (1-CTA tiles via BOFI_GEMM2=0, one k-block per stage via BOFI_KPS=1, the opt-in A-resident 2-CTA tiles and LayerNorm-fused GEMM) must give
     the default bf16 path's results: same boxes, logits within bf16 rounding of the LayerNorm output."""
     import torch
     from boficap_b200 import synth

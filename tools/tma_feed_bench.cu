@@ -16,6 +16,7 @@
 //   9  as 0, but the boxes of a stage alternate between TWO tensor maps (two separate buffers), as A and W do in a GEMM
 //   7  one 16 KB tensor box (TMA) + 16 KB by cp.async (LDGSTS, 16 B per thread, 128 threads of four extra warps) per stage
 //   8  32 KB per stage by cp.async only (128 threads)
+//   +100 every CTA reads one of only 8 tile sequences (hot L2 lines, like the W tile of a GEMM wave)
 //   +10  (e.g. 11) the same, while eight other warps each keep issuing 4 KB TMA STORES (32 x 128 B, the GEMM epilogue's)
 //   +20  (e.g. 21) the same, while two other warps each keep issuing 16 KB TMA stores (128 x 128 B)
 // Output: bytes / clk / SM over the whole run (clock64 of the slowest CTA) per (mode, stages, stage bytes, grid).
@@ -74,12 +75,14 @@ feed_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ C
   __shared__ uint64_t full[16], empty[16];
   __shared__ volatile int done_flag;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool same_tiles = mode >= 100;      // +100: every CTA walks the SAME tile sequence (what the CTAs of a GEMM wave do with W)
+  mode %= 100;
   const int st_mode = mode / 10;
   mode %= 10;
   if (threadIdx.x == 0) done_flag = 0;
   if (threadIdx.x == 0) {
-    const int extra = (mode % 10 == 7 || mode % 10 == 8) ? 128 : 0;      // cp.async.mbarrier.arrive.noinc of the LDGSTS threads
-    for (int s = 0; s < stages; ++s) { mbar_init(smem_u32(&full[s]), (mode % 10 == 8 ? 0 : 1) + extra); mbar_init(smem_u32(&empty[s]), 1); }
+    const int extra = (mode % 100 % 10 == 7 || mode % 100 % 10 == 8) ? 128 : 0;      // cp.async.mbarrier.arrive.noinc of the LDGSTS threads
+    for (int s = 0; s < stages; ++s) { mbar_init(smem_u32(&full[s]), (mode % 100 % 10 == 8 ? 0 : 1) + extra); mbar_init(smem_u32(&empty[s]), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -95,7 +98,7 @@ feed_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ C
       const uint32_t dst = smem_u32(smem + (size_t)s * stage_bytes);
       // walk an L2-resident window: k-block (it % 8), row block depends on CTA and iteration
       const int kb = it & 7;
-      const int r0 = (int)(((long long)blockIdx.x * 131 + (long long)(it >> 3) * 7) % (rows_total / 256)) * 256;
+      const int r0 = (int)(((long long)(same_tiles ? (blockIdx.x & 7) : blockIdx.x) * 131 + (long long)(it >> 3) * 7) % (rows_total / 256)) * 256;
       if (mode == 7) { tma_load_2d(dst, &tm128, fb, kb * 64, r0); continue; }
       if (mode == 4) {
         for (int i = 0; i < stage_bytes / 32768; ++i) tma_load_3d(dst + i * 32768, &tm3a, fb, 0, (r0 + 128 * i) % rows_total, (kb & 3) * 2);
@@ -197,6 +200,8 @@ int main() {
     for (int st : {4, 8, 12}) cfgs.push_back({0, st, 16384, grid});
   }
   for (int mode : {0}) cfgs.push_back({mode, mode % 10 == 5 ? 2 : 4, mode % 10 == 5 ? 65536 : 32768, 148});
+  // hot lines: 148 CTAs walking only 8 distinct tile sequences (+100) against 148 distinct ones
+  for (int mode : {0, 100, 4, 104}) { cfgs.push_back({mode, 3, 65536, 148}); cfgs.push_back({mode, 6, 32768, 148}); }
   for (int n : {2, 4}) { cfgs.push_back({0, 2, n * 16384, 148}); cfgs.push_back({9, 2, n * 16384, 148}); cfgs.push_back({9, 4, n * 16384, 148}); }
   // how a stage's cost grows with the number of boxes on its barrier
   for (int n : {1, 2, 3, 4, 6}) cfgs.push_back({0, 2, n * 16384, 148});
