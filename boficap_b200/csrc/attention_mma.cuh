@@ -305,26 +305,38 @@ attention_row_bf16_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __res
   float mx = -INFINITY;
   const int npass = (nvis + 7) >> 3;
 #pragma unroll
-  for (int p = 0; p < kMaxKeys / 8; ++p) {
-    sc[p] = -INFINITY;
-    if (p < npass) {
-      const int j = p * 8 + kslot;
-      float d = 0.f;
+  for (int p = 0; p < kMaxKeys / 8; ++p) sc[p] = -INFINITY;
+  // four passes (32 keys) per trip: their eight 16-byte key loads are issued together, then reduced -- one global
+  // latency per 32 keys instead of one per 8 (this kernel sits on the bounding loop's dependency chain)
+#pragma unroll
+  for (int p0 = 0; p0 < kMaxKeys / 8; p0 += 4) {
+    if (p0 >= npass) break;                    // uniform over the warp (one (row, head) per warp)
+    uint4 k0[4], k1[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = (p0 + u) * 8 + kslot;
+      k0[u] = k1[u] = make_uint4(0u, 0u, 0u, 0u);
       if (j < nvis) {
         const bf16* kr = K + (kvrow0 + j) * ldkv + head * kHeadDim + sub * 16;
-        const uint4 k0 = *reinterpret_cast<const uint4*>(kr), k1 = *reinterpret_cast<const uint4*>(kr + 8);
-        const uint32_t w[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+        k0[u] = *reinterpret_cast<const uint4*>(kr);
+        k1[u] = *reinterpret_cast<const uint4*>(kr + 8);
+      }
+    }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
-          d = fmaf(qf[2 * i], f.x, d);
-          d = fmaf(qf[2 * i + 1], f.y, d);
-        }
+    for (int u = 0; u < 4; ++u) {
+      const int j = (p0 + u) * 8 + kslot;
+      const uint32_t w[8] = {k0[u].x, k0[u].y, k0[u].z, k0[u].w, k1[u].x, k1[u].y, k1[u].z, k1[u].w};
+      float d = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+        d = fmaf(qf[2 * i], f.x, d);
+        d = fmaf(qf[2 * i + 1], f.y, d);
       }
       d += __shfl_xor_sync(0xffffffffu, d, 1);
       d += __shfl_xor_sync(0xffffffffu, d, 2);
-      if (j < nvis) sc[p] = d * scale;
-      mx = fmaxf(mx, sc[p]);
+      if (j < nvis) sc[p0 + u] = d * scale;
+      mx = fmaxf(mx, sc[p0 + u]);
     }
   }
   mx = warp_max(mx);
