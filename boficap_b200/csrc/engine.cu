@@ -310,7 +310,7 @@ static int layernorm(bofi_engine* e, cudaStream_t s, const float* x, size_t in_s
                      size_t out_stride, int rows, float* f32_copy, const int* live) {
   if (rows <= 0) return BOFI_OK;
   ProfScope prof(e, s, PC_LAYERNORM, 8.0 * rows * kD, (double)rows * kD * (4 + sizeof(TOut) + (f32_copy ? 4 : 0)), rows);
-  const int ln_grid = e->rows_dev ? std::min(ceil_div(rows, 8), 148 * 8) : ceil_div(rows, 8);
+  const int ln_grid = std::min(ceil_div(rows, 8), 148 * 8);      // persistent: a warp walks several rows, gain / bias stay in registers
   launch_k(layernorm_kernel<TOut>, ln_grid, 256, 0, s, x, in_stride, n.a, n.b, out, out_stride, rows, f32_copy, live, e->rows_dev);
   CU_TRY(cudaGetLastError());
   return BOFI_OK;

@@ -205,15 +205,16 @@ gemm_ln_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
         for (int q = 0; q < G; ++q) {
           const int r = ew * 16 + g * G + q, row = m0 + r;
           const float dn = sqrtf(denom[q] * (1.0f / (kLnK - 1))) + 1e-6f;
+          const float inv = 1.0f / dn;            // same arithmetic as layernorm_kernel<bf16>: one reciprocal per row
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int c = (i * 32 + lane) * 4;
             const float4 ga = *reinterpret_cast<const float4*>(ln_a + c), gb = *reinterpret_cast<const float4*>(ln_b + c);
             float4 o;
-            o.x = ga.x * v[q][i].x / dn + gb.x;
-            o.y = ga.y * v[q][i].y / dn + gb.y;
-            o.z = ga.z * v[q][i].z / dn + gb.z;
-            o.w = ga.w * v[q][i].w / dn + gb.w;
+            o.x = ga.x * v[q][i].x * inv + gb.x;
+            o.y = ga.y * v[q][i].y * inv + gb.y;
+            o.z = ga.z * v[q][i].z * inv + gb.z;
+            o.w = ga.w * v[q][i].w * inv + gb.w;
             if (row >= m_eff) o = make_float4(0.f, 0.f, 0.f, 0.f);
             // column c: k-block c/64, 16-byte chunk (c%64)/8 swizzled with the row, 8-byte half (c%8)/4
             const uint32_t addr = a_base + (uint32_t)(c >> 6) * (kBM * 128) + (uint32_t)r * 128u +

@@ -20,6 +20,13 @@ layernorm_kernel(const float* __restrict__ x, size_t in_stride, const float* __r
   if (step_is_dead(live_rows)) return;
   const int lane = threadIdx.x & 31;
   if (rows_dev) rows = min(rows, *rows_dev);           // compacted step: the valid-row count lives on the device
+  // gain / bias of this lane's 16 columns: loaded once, the grid is persistent (a warp walks several rows)
+  float4 ga[4], gb[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    ga[i] = load4(a2 + (i * 32 + lane) * 4);
+    gb[i] = load4(b2 + (i * 32 + lane) * 4);
+  }
   for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += (gridDim.x * blockDim.x) >> 5) {
   const float* xr = x + (size_t)row * in_stride;
   float4 v[4];
@@ -40,12 +47,20 @@ layernorm_kernel(const float* __restrict__ x, size_t in_stride, const float* __r
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int c = (i * 32 + lane) * 4;
-    const float4 a = load4(a2 + c), b = load4(b2 + c);
+    const float4 a = ga[i], b = gb[i];
     float4 o;
-    o.x = a.x * v[i].x / denom + b.x;
-    o.y = a.y * v[i].y / denom + b.y;
-    o.z = a.z * v[i].z / denom + b.z;
-    o.w = a.w * v[i].w / denom + b.w;
+    if (sizeof(TOut) == 4 || out_f32_copy) {  // fp32 parity path (and fp32 copies): the reference's a * (x - mean) / (std + eps) + b, divisions kept
+      o.x = a.x * v[i].x / denom + b.x;
+      o.y = a.y * v[i].y / denom + b.y;
+      o.z = a.z * v[i].z / denom + b.z;
+      o.w = a.w * v[i].w / denom + b.w;
+    } else {                                  // bf16 output: one reciprocal per row (<= 1 ulp of fp32 before the bf16 rounding)
+      const float inv = 1.0f / denom;
+      o.x = a.x * v[i].x * inv + b.x;
+      o.y = a.y * v[i].y * inv + b.y;
+      o.z = a.z * v[i].z * inv + b.z;
+      o.w = a.w * v[i].w * inv + b.w;
+    }
     store4(out + (size_t)row * out_stride + c, o);
     if (out_f32_copy) store4(out_f32_copy + (size_t)row * kD + c, o);
   }
