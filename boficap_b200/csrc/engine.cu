@@ -838,7 +838,7 @@ static int decode_naic(bofi_engine* e, cudaStream_t s, int sn, int output_logsof
         RC_TRY((linear<T, float>(e, s, e->y.as<T>() + (size_t)r0 * kD, kD, e->generator, nullptr, 0, e->logits.as<float>(), e->Vpad, n, 0, nullptr)));
       ProfScope prof(e, s, PC_VOCAB, 0.0, 0.0);
       launch_k(vocab_epilogue_kernel, n, kVocabThreads, 0, s, e->logits.as<float>(), e->Vpad, e->V, logprobs, seq, e->st.last, -1, L,
-               output_logsoftmax, nullptr, e->sampler, e->stat_entropy, e->stat_logp, r0);
+               output_logsoftmax, nullptr, e->sampler, e->stat_entropy, e->stat_logp, r0, (e->bf16_mode && !e->stat_entropy) ? 1 : 0);
       CU_TRY(cudaGetLastError());
     }
   }

@@ -603,7 +603,7 @@ __global__ void __launch_bounds__(kVocabThreads, BOFI_VOCAB_OCC)
 vocab_epilogue_kernel(const float* __restrict__ logits, int ldl, int V, float* __restrict__ logp_out,
                       long long* __restrict__ seq_out, const int* __restrict__ total_len, int total_off, int L,
                       int do_logsoftmax, int* __restrict__ tok_out_i32, Sampler sp, float* __restrict__ slot_entropy,
-                      float* __restrict__ slot_logp, int row0) {
+                      float* __restrict__ slot_logp, int row0, int fast_exp) {
   pdl_enter();
   // The whole row lives in registers: logits are read from HBM exactly once (128-bit loads, all independent),
   // max / argmax / sum-exp are block reductions, and the log-probs are written once.
@@ -675,8 +675,13 @@ vocab_epilogue_kernel(const float* __restrict__ logits, int ldl, int V, float* _
   if ((logp_out && do_logsoftmax) || slot_entropy) {
     {
       float s = 0.f;                  // pad / filler elements are -inf: exp(-inf - mx) adds 0 (NaN exactly when the real ones do)
+      if (fast_exp) {               // bf16 engine: the logits carry bf16 rounding (1e-2); ex2.approx is far inside that
 #pragma unroll
-      for (int i = 0; i < kVocabVec; ++i) s += expf(v[i].x - mx) + expf(v[i].y - mx) + expf(v[i].z - mx) + expf(v[i].w - mx);
+        for (int i = 0; i < kVocabVec; ++i) s += __expf(v[i].x - mx) + __expf(v[i].y - mx) + __expf(v[i].z - mx) + __expf(v[i].w - mx);
+      } else {
+#pragma unroll
+        for (int i = 0; i < kVocabVec; ++i) s += expf(v[i].x - mx) + expf(v[i].y - mx) + expf(v[i].z - mx) + expf(v[i].w - mx);
+      }
       s = warp_sum(s);
       if (lane == 0) s_sum[warp] = s;
       __syncthreads();
