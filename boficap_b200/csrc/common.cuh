@@ -105,4 +105,14 @@ __device__ __forceinline__ bool step_is_dead(const int* live_rows) {
   return live_rows != nullptr && *live_rows == 0;
 }
 
+// t / d from a per-row reciprocal: q = t * inv, then one FMA residual step (r = t - q d exactly, q += r * inv).  Equals
+// the IEEE quotient except in rare double-rounding cases, at 3 instructions instead of the ~10 of a true division (16 of
+// them per lane had the LayerNorm kernel issue-bound).
+__device__ __forceinline__ float ln_div(float t, float d, float inv) {
+  const float q = t * inv;
+  const float r = fmaf(-q, d, t);
+  return fmaf(r, inv, q);
+}
+
+
 }  // namespace bofi

@@ -211,10 +211,10 @@ gemm_ln_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
             const int c = (i * 32 + lane) * 4;
             const float4 ga = *reinterpret_cast<const float4*>(ln_a + c), gb = *reinterpret_cast<const float4*>(ln_b + c);
             float4 o;
-            o.x = ga.x * v[q][i].x * inv + gb.x;
-            o.y = ga.y * v[q][i].y * inv + gb.y;
-            o.z = ga.z * v[q][i].z * inv + gb.z;
-            o.w = ga.w * v[q][i].w * inv + gb.w;
+            o.x = ln_div(ga.x * v[q][i].x, dn, inv) + gb.x;
+            o.y = ln_div(ga.y * v[q][i].y, dn, inv) + gb.y;
+            o.z = ln_div(ga.z * v[q][i].z, dn, inv) + gb.z;
+            o.w = ln_div(ga.w * v[q][i].w, dn, inv) + gb.w;
             if (row >= m_eff) o = make_float4(0.f, 0.f, 0.f, 0.f);
             // column c: k-block c/64, 16-byte chunk (c%64)/8 swizzled with the row, 8-byte half (c%8)/4
             const uint32_t addr = a_base + (uint32_t)(c >> 6) * (kBM * 128) + (uint32_t)r * 128u +

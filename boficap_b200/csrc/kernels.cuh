@@ -54,12 +54,12 @@ layernorm_kernel(const float* __restrict__ x, size_t in_stride, const float* __r
       o.y = a.y * v[i].y / denom + b.y;
       o.z = a.z * v[i].z / denom + b.z;
       o.w = a.w * v[i].w / denom + b.w;
-    } else {                                  // bf16 output: one reciprocal per row (<= 1 ulp of fp32 before the bf16 rounding)
+    } else {                                  // bf16 output: one reciprocal per row + a residual correction per element
       const float inv = 1.0f / denom;
-      o.x = a.x * v[i].x * inv + b.x;
-      o.y = a.y * v[i].y * inv + b.y;
-      o.z = a.z * v[i].z * inv + b.z;
-      o.w = a.w * v[i].w * inv + b.w;
+      o.x = ln_div(a.x * v[i].x, denom, inv) + b.x;
+      o.y = ln_div(a.y * v[i].y, denom, inv) + b.y;
+      o.z = ln_div(a.z * v[i].z, denom, inv) + b.z;
+      o.w = ln_div(a.w * v[i].w, denom, inv) + b.w;
     }
     store4(out + (size_t)row * out_stride + c, o);
     if (out_f32_copy) store4(out_f32_copy + (size_t)row * kD + c, o);
