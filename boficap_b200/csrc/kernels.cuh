@@ -627,14 +627,37 @@ vocab_epilogue_kernel(const float* __restrict__ logits, int ldl, int V, float* _
       if (4 * c4 + 3 >= V) v[i].w = -INFINITY;
     }
   }
-  ArgMax am = {-INFINITY, 0x7fffffff};
+  // This thread's candidate: the maximum with FMNMX (fmaxf skips NaNs) and a NaN flag, then the lowest index holding it
+  // (descending scan, equal values overwrite).  Pad / filler elements are -inf with indices above every real one, so
+  // they can only stand when the whole row is -inf and are then overwritten by lower real indices.  A thread that saw a
+  // NaN (torch.max: NaN wins, first one) takes the general compare chain; the cross-lane reduction uses it in any case.
+  float tmax = -INFINITY;
+  bool tnan = false;
 #pragma unroll
   for (int i = 0; i < kVocabVec; ++i) {
-    const int c = (tid + i * kVocabThreads) * 4;
-    const float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+    tmax = fmaxf(fmaxf(tmax, v[i].x), fmaxf(v[i].y, fmaxf(v[i].z, v[i].w)));
+    tnan |= (v[i].x != v[i].x) | (v[i].y != v[i].y) | (v[i].z != v[i].z) | (v[i].w != v[i].w);
+  }
+  ArgMax am = {tmax, 0x7fffffff};
+  if (!tnan) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (c + q < V) am = better(am, ArgMax{e[q], c + q});
+    for (int i = kVocabVec - 1; i >= 0; --i) {
+      const int c = (tid + i * kVocabThreads) * 4;
+      if (v[i].w == tmax) am.i = c + 3;
+      if (v[i].z == tmax) am.i = c + 2;
+      if (v[i].y == tmax) am.i = c + 1;
+      if (v[i].x == tmax) am.i = c;
+    }
+  } else {
+    am = ArgMax{-INFINITY, 0x7fffffff};
+#pragma unroll
+    for (int i = 0; i < kVocabVec; ++i) {
+      const int c = (tid + i * kVocabThreads) * 4;
+      const float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (c + q < V) am = better(am, ArgMax{e[q], c + q});
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
