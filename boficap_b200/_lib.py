@@ -7,10 +7,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # BOFI_LIB_PATH: load another build of the same ABI (the stall-counter build of tools/gemm_stalls.py)
 LIB_PATH = os.environ.get("BOFI_LIB_PATH") or os.path.join(_HERE, "lib", "libbofi_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NOMEM = 0, 1, 2, 3, 4
 PRECISION = {"fp32": 0, "bf16": 1}
 MODE = {"NAIC": 0, "SAIC": 1}
+FEAT = {"float32": 0, "bfloat16": 1, "float16": 2}
 
 
 class BofiConfigC(C.Structure):
@@ -41,6 +42,10 @@ _SIGNATURES = {
     "bofi_finalize_weights": (C.c_int, [_P, _P]),
     "bofi_workspace_bytes": (C.c_int64, [_P, _I, _I, _I]),
     "bofi_encode": (C.c_int, [_P, _P, _P, _P, _I, _I, _P]),
+    "bofi_encode_ex": (C.c_int, [_P, _P, _P, _I, _P, _I, _I, _P]),
+    "bofi_masks_to_len": (C.c_int, [_P, _P, _P, _I, _I, _P]),
+    "bofi_check_masks": (C.c_int, [_P, _P, C.POINTER(C.c_int32)]),
+    "bofi_sample_host_async_ex": (C.c_int, [_P, _P, _I, _I, _I, _P, _I, _P, _I, _I, _P, _P, _P, _P, _P]),
     "bofi_decode": (C.c_int, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
     "bofi_sample_host": (C.c_int, [_P, _P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P]),
     "bofi_sample_host_async": (C.c_int, [_P, _P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P]),

@@ -9,7 +9,6 @@ Reference behaviour mirrored here (paths relative to /root/reference/captioning/
   state_dict layout            TransformerModel.py:1558-1568, :1626-1666
 The module holds NO PyTorch math for this path: without the CUDA library it raises.
 """
-import time
 
 import torch
 import torch.nn as nn
@@ -106,12 +105,32 @@ class TransformerModel(nn.Module):
             p.data = flat_w[off:off + n].view(p.shape)
             if isinstance(p, nn.Parameter):
                 p.grad = flat_g[off:off + n].view(p.shape)
-        self._bound = [flat_w, flat_g, self._version_stamp()]
+        self._bound = [flat_w, flat_g, self._version_stamp(), layout]
         self._engine_key = None
         return self
 
     def _version_stamp(self):
         return sum(p._version for p in self.parameters())
+
+    def _reattach_grads(self):
+        """`optimizer.zero_grad()` defaults to set_to_none=True (tools/train.py:210 calls it every step): it drops the
+        `.grad` views, after which `optimizer.step()` would skip every parameter while the library kept accumulating
+        into the flat buffer.  Before every training forward the views are put back; when they were dropped the flat
+        buffer is zeroed, which is what zero_grad meant."""
+        flat_g = self._bound[1]
+        lo, hi = flat_g.data_ptr(), flat_g.data_ptr() + flat_g.numel() * 4
+        missing = [(n, p) for n, p in self.named_parameters()
+                   if p.grad is None or not (lo <= p.grad.data_ptr() < hi)]
+        if not missing:
+            return
+        if any(p.grad is not None for _, p in missing):
+            raise RuntimeError("a parameter's .grad was replaced by a tensor outside the flat gradient buffer; "
+                               "use optimizer.zero_grad() / model.zero_grad() instead of assigning .grad")
+        flat_g.zero_()
+        layout = self._bound[3]
+        for n, p in missing:
+            off, k = layout[n]
+            p.grad = flat_g[off:off + k].view(p.shape)
 
     def flat_grads(self):
         return self._bound[1]
@@ -127,7 +146,9 @@ class TransformerModel(nn.Module):
 
     # ---- engine management -----------------------------------------------------------------
     def _weights_key(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        # version stamp only: load_state_dict / optimiser steps / in-place edits bump the parameters' version counters
+        # (one integer sum per call instead of a 311-tuple of pointers and versions)
+        return (self._version_stamp(), len(self._parameters) + len(self._modules))
 
     def engine(self, device=None, precision=None):
         precision = precision or self.precision
@@ -173,6 +194,7 @@ class TransformerModel(nn.Module):
             raise RuntimeError("boficap_b200 runs on CUDA tensors only (no CPU fallback)")
         if self._bound is None:
             self.train_bind(att_feats.device)
+        self._reattach_grads()
         eng = self.engine(att_feats.device)
         # nn.Module.train() / eval() decide, as for the reference's nn.Dropout modules
         if self.training:
@@ -194,7 +216,7 @@ class TransformerModel(nn.Module):
         self._train_engine(att_feats)
         batch = self._xe_batch(att_feats, seq, phrase_num, phrase_length, phrase_syn, extend_phrase_syn_seq, extend_phrase_seq,
                                extend_phrase_seq_mask)
-        att_len = att_masks.data.long().sum(1).to(torch.int32) if att_masks is not None else None
+        att_len = self._train_att_len(att_masks)
         anchor = next(self.parameters())                  # makes the outputs require grad
         return _XEForward.apply(self, att_feats.float(), att_len, batch, anchor)
 
@@ -206,8 +228,13 @@ class TransformerModel(nn.Module):
         eng = self._train_engine(att_feats)
         batch = self._xe_batch(att_feats, seq, phrase_num, phrase_length, phrase_syn, extend_phrase_syn_seq, extend_phrase_seq,
                                extend_phrase_seq_mask)
-        att_len = att_masks.data.long().sum(1).to(torch.int32) if att_masks is not None else None
+        att_len = self._train_att_len(att_masks)
         return eng.train_step_xe(att_feats.float(), att_len, batch)
+
+    def _train_att_len(self, att_masks):
+        if att_masks is None:
+            return None
+        return self._engine.masks_to_len(att_masks.data)    # a non-prefix mask is reported by the next check_masks()
 
     def sample_stats(self, fc_feats, att_feats, att_masks=None, opt={}):
         """`_sample` for evaluation loops that only need captions, entropy and perplexity (eval_utils.py:176-184): the
@@ -238,7 +265,7 @@ class TransformerModel(nn.Module):
         eng = self.engine(att_feats.device, opt.get("bofi_precision"))
         att_len = None
         if att_masks is not None:
-            att_len = att_masks.data.long().sum(1).to(torch.int32)
+            att_len = eng.masks_to_len(att_masks.data)      # counts + device-side check that the masks are prefix masks
         if sample_method == "greedy":
             eng.set_sampling("greedy")
         elif sample_method == "sample":
@@ -247,13 +274,23 @@ class TransformerModel(nn.Module):
             eng.set_sampling("sample", temperature, int(torch.randint(0, 2 ** 31 - 1, (1,))))
         else:
             raise NotImplementedError("sample_method=%r: only 'greedy' and 'sample' (the uic_sd* configs) are built" % sample_method)
-        eng.encode(att_feats.float(), att_len)
-        torch.cuda.synchronize(att_feats.device)
-        start = time.time()
+        if att_feats.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+            att_feats = att_feats.float()
+        # `elapsed` (AttModel.py:337, :425: wall clock between two device synchronisations around the core) comes from two
+        # events on the stream, so the call synchronises once, at the end, like any caller that reads the captions would
+        stream = torch.cuda.current_stream(att_feats.device)
+        eng.encode(att_feats, att_len)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
         if _stats is not None:
             eng.set_decode_stats(*_stats)
-        seq, logp, pnum, plen, psyn = eng.decode(train_mode, sample_n, output_logsoftmax, _stats is None)
+        want_logprobs = _stats is None and bool(opt.get("bofi_logprobs", True))
+        seq, logp, pnum, plen, psyn = eng.decode(train_mode, sample_n, output_logsoftmax, want_logprobs)
         eng.set_decode_stats(None, None)
         eng.set_sampling("greedy")
-        torch.cuda.synchronize(att_feats.device)
-        return seq, logp, pnum, plen, psyn, time.time() - start
+        ev1.record(stream)
+        if att_masks is not None:
+            eng.check_masks()                                # synchronises the stream; raises on a non-prefix mask
+        else:
+            ev1.synchronize()
+        return seq, logp, pnum, plen, psyn, ev0.elapsed_time(ev1) * 1e-3

@@ -43,7 +43,7 @@ template <int KT>
 __global__ void __launch_bounds__(128, KT <= 3 ? 8 : 1)     // short key ranges: cap registers at 64 so that eight CTAs share an SM
 attention_mma_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restrict__ K, const bf16* __restrict__ V, int ldkv,
                      bf16* __restrict__ O, int ldo, int Tq, int Tk, const int* __restrict__ vis, int vis_bs, int vis_qs,
-                     int vis_div, int kv_div, float scale, const int* live_rows, Drop drop) {
+                     int vis_div, int kv_div, float scale, const int* live_rows, Drop drop, const int* __restrict__ seq_off, int q_varlen) {
   pdl_enter();
   if (step_is_dead(live_rows)) return;
   extern __shared__ __align__(16) uint8_t att_smem[];
@@ -54,7 +54,15 @@ attention_mma_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restrict
   const int TQP = (Tq + 15) & ~15;
   const int head = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const size_t kvrow0 = (size_t)(b / kv_div) * Tk;
+  // Varlen layout (seq_off != nullptr): the K/V rows of sequence j are the compact rows [seq_off[j], seq_off[j+1]);
+  // q_varlen: the queries are those same rows (encoder self-attention over the valid regions only).
+  size_t kvrow0 = (size_t)(b / kv_div) * Tk, qrow0 = (size_t)b * Tq;
+  if (seq_off) {
+    const int o0 = seq_off[b / kv_div];
+    Tk = min(Tk, seq_off[b / kv_div + 1] - o0);
+    kvrow0 = (size_t)o0;
+    if (q_varlen) { qrow0 = kvrow0; Tq = Tk; }
+  }
   // All tiles are fetched with cp.async (16 bytes, L1 bypass; rows past the end zero-filled through the src-size
   // operand): every request of the CTA is in flight at once and the global latency is paid once.  The register
   // round trip it replaces (load, store, load, store ...) had the kernel stalled on long_scoreboard for 8 of every
@@ -69,7 +77,7 @@ attention_mma_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restrict
   for (int idx = tid; idx < TQP * 8; idx += 128) {
     const int t = idx >> 3, c = (idx & 7) * 8;
     const bool ok = t < Tq;
-    cp_async_16(Qs + t * kAttPitch + c, Q + ((size_t)b * Tq + (ok ? t : 0)) * ldq + head * kHeadDim + c, ok);
+    cp_async_16(Qs + t * kAttPitch + c, Q + (qrow0 + (ok ? t : 0)) * ldq + head * kHeadDim + c, ok);
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
@@ -135,8 +143,8 @@ attention_mma_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restrict
       float k0 = 1.f, k1 = 1.f, k2 = 1.f, k3 = 1.f;           // dropout on the probabilities (training only)
       if (drop.thresh) {
         const int c = nt * 8 + 2 * t4;
-        k0 = drop_mul(drop, att_idx(b * Tq + r0, head, c)); k1 = drop_mul(drop, att_idx(b * Tq + r0, head, c + 1));
-        k2 = drop_mul(drop, att_idx(b * Tq + r1, head, c)); k3 = drop_mul(drop, att_idx(b * Tq + r1, head, c + 1));
+        k0 = drop_mul(drop, att_idx((int)qrow0 + r0, head, c)); k1 = drop_mul(drop, att_idx((int)qrow0 + r0, head, c + 1));
+        k2 = drop_mul(drop, att_idx((int)qrow0 + r1, head, c)); k3 = drop_mul(drop, att_idx((int)qrow0 + r1, head, c + 1));
       }
       pa[nt >> 1][(nt & 1) * 2 + 0] = pack2_bf16(p0 * k0, p1 * k1);     // a0a1 / a4a5 : row g
       pa[nt >> 1][(nt & 1) * 2 + 1] = pack2_bf16(p2 * k2, p3 * k3);     // a2a3 / a6a7 : row g+8
@@ -166,8 +174,8 @@ attention_mma_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restrict
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       const int c = head * kHeadDim + nt * 8 + 2 * t4;
-      if (r0 < Tq) *reinterpret_cast<uint32_t*>(O + ((size_t)b * Tq + r0) * ldo + c) = pack2_bf16(oacc[nt][0] * inv0, oacc[nt][1] * inv0);
-      if (r1 < Tq) *reinterpret_cast<uint32_t*>(O + ((size_t)b * Tq + r1) * ldo + c) = pack2_bf16(oacc[nt][2] * inv1, oacc[nt][3] * inv1);
+      if (r0 < Tq) *reinterpret_cast<uint32_t*>(O + (qrow0 + r0) * ldo + c) = pack2_bf16(oacc[nt][0] * inv0, oacc[nt][1] * inv0);
+      if (r1 < Tq) *reinterpret_cast<uint32_t*>(O + (qrow0 + r1) * ldo + c) = pack2_bf16(oacc[nt][2] * inv1, oacc[nt][3] * inv1);
     }
   }
 }
@@ -184,7 +192,7 @@ __global__ void __launch_bounds__(256)
 attention_row_kernel(const T* __restrict__ Q, int ldq, const T* __restrict__ K, const T* __restrict__ V, int ldkv,
                      T* __restrict__ O, int ldo, int Tk, const int* __restrict__ vis, int vis_div, int kv_div, float scale,
                      const int* live_rows, const int* __restrict__ finished, Drop drop, const int* __restrict__ rowmap, int rowmap_div,
-                     const int* rows_dev) {
+                     const int* rows_dev, const int* __restrict__ seq_off) {
   pdl_enter();
   if (step_is_dead(live_rows)) return;
   if (finished && finished[blockIdx.x]) return;
@@ -193,7 +201,12 @@ attention_row_kernel(const T* __restrict__ Q, int ldq, const T* __restrict__ K, 
   __shared__ float ps[8][kMaxKeys];
   const int b = blockIdx.x, head = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bs = rowmap ? rowmap[b] / rowmap_div : b;      // sequence the (compact) query row belongs to
-  const size_t kvrow0 = (size_t)(bs / kv_div) * Tk;
+  size_t kvrow0 = (size_t)(bs / kv_div) * Tk;
+  if (seq_off) {                                           // varlen memory: compact K/V rows of the image
+    const int o0 = seq_off[bs / kv_div];
+    Tk = min(Tk, seq_off[bs / kv_div + 1] - o0);
+    kvrow0 = (size_t)o0;
+  }
   const T* qg = Q + (size_t)b * ldq + head * kHeadDim;
   qs[head][lane] = to_float<T>(qg[lane]);
   qs[head][lane + 32] = to_float<T>(qg[lane + 32]);
@@ -274,7 +287,7 @@ __global__ void __launch_bounds__(kRowsPerCta * 256)
 attention_row_bf16_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restrict__ K, const bf16* __restrict__ V, int ldkv,
                           bf16* __restrict__ O, int ldo, int nb, int Tk, const int* __restrict__ vis, int vis_div, int kv_div,
                           float scale, const int* live_rows, const int* __restrict__ finished, Drop drop, const int* __restrict__ rowmap,
-                          int rowmap_div, const int* rows_dev) {
+                          int rowmap_div, const int* rows_dev, const int* __restrict__ seq_off) {
   pdl_enter();
   if (step_is_dead(live_rows)) return;
   __shared__ float ps[kRowsPerCta * 8][kMaxKeys];
@@ -284,9 +297,15 @@ attention_row_bf16_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __res
   for (int b = blockIdx.x * kRowsPerCta + (warp >> 3); b < nb; b += gridDim.x * kRowsPerCta) {
   if (finished && finished[b]) continue;   // bounding step: finished rows are ignored by the head
   const int bs = rowmap ? rowmap[b] / rowmap_div : b;      // sequence the (compact) query row belongs to
-  const size_t kvrow0 = (size_t)(bs / kv_div) * Tk;
-  int nvis = vis ? vis[bs / vis_div] : Tk;
-  nvis = min(nvis, Tk);
+  size_t kvrow0 = (size_t)(bs / kv_div) * Tk;
+  int tk = Tk;
+  if (seq_off) {                                           // varlen memory: compact K/V rows of the image
+    const int o0 = seq_off[bs / kv_div];
+    tk = min(Tk, seq_off[bs / kv_div + 1] - o0);
+    kvrow0 = (size_t)o0;
+  }
+  int nvis = vis ? vis[bs / vis_div] : tk;
+  nvis = min(nvis, tk);
   // ---- scores ----
   const int sub = lane & 3, kslot = lane >> 2;
   float qf[16];

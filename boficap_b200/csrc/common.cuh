@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <type_traits>
 #include <stdint.h>
 #include <math.h>
 
@@ -79,6 +81,18 @@ inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
+
+// cudaFuncSetAttribute and the SM count are per DEVICE: one-time-setup caches are kept per device ordinal, so a second
+// device in the same process gets its own dynamic shared memory opt-in.
+template <typename V>
+struct PerDevice {
+  V v[64] = {};
+  V& get() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return v[d & 63];
+  }
+};
 
 // Dropout (training path only).  Counter-based: the keep/drop decision of element `idx` of dropout site `key` is a pure
 // function (murmur3 finaliser), so the backward pass regenerates the mask instead of storing it, and the CPU oracle can

@@ -71,7 +71,7 @@ struct DevBuf {
     return BOFI_OK;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) { cudaFree(p); ++g_alloc_generation; }     // captured graphs may hold pointers into the buffer
     p = nullptr;
     cap = 0;
   }
@@ -166,7 +166,13 @@ struct bofi_engine {
     unsigned long long key[12] = {0};
     int launches = 0, eager_runs = 0;
   } g_bound, g_saic;
-  const int* rows_dev = nullptr;         // when set, linear() / layernorm() only process the first *rows_dev rows (SAIC compaction)
+  const int* rows_dev = nullptr;         // when set, linear() / layernorm() only process the first *rows_dev rows (SAIC compaction, varlen encoder)
+  const int* varlen_total = nullptr;     // device row count of the varlen encoder (= seqoff + B + 1)
+  int rows_hint = 0;                     // profiling runs: the host copy of *rows_dev of the varlen encoder (exact FLOP accounting)
+  bool varlen = true;                    // BOFI_VARLEN=0: padded encoder (every GEMM / LN / attention over all B*R rows)
+  DevBuf xpad, seqoff, maskflag;         // varlen: padded att_embed output, row offsets [B+1] + total, prefix-mask check flag
+  const int* enc_off = nullptr;          // set while the varlen encoder layers run: compact row offset of every image
+  const int* mem_off = nullptr;          // set when the memory left by bofi_encode is compact (varlen)
   float *stat_entropy = nullptr, *stat_logp = nullptr;   // bofi_set_decode_stats: optional [rows, L] outputs of the next decodes
   Sampler sampler;                       // bofi_set_sampling: greedy (default) or multinomial for the next decodes
   unsigned sample_calls = 0;
@@ -287,10 +293,12 @@ static int linear(bofi_engine* e, cudaStream_t s, const T* A, int lda, const Lin
   const bool tcpath = std::is_same<T, bf16>::value && e->use_tc;
   // A compacted SAIC step only walks the tiles below the device-side row count: M is an upper bound there, so such a
   // launch is booked under "other" without FLOPs instead of inflating the GEMM classes' achieved rate.
-  const bool exact = e->rows_dev == nullptr;
-  ProfScope prof(e, s, !exact ? PC_OTHER : tcpath ? PC_GEMM_TC : PC_GEMM_SIMT, exact ? 2.0 * M * l.N * l.K : 0.0,
-                 !exact ? 0.0 : (double)sizeof(T) * ((double)M * l.K + (double)l.N * l.K) + (double)sizeof(TOut) * M * l.N + (resid ? 4.0 * M * l.N : 0.0),
-                 M, l.N, l.K);
+  const bool hinted = e->rows_dev != nullptr && e->rows_hint > 0 && e->rows_dev == e->varlen_total;
+  const bool exact = e->rows_dev == nullptr || hinted;
+  const int Mp = hinted ? std::min(M, e->rows_hint) : M;       // rows that do work (profiling accounting only)
+  ProfScope prof(e, s, !exact ? PC_OTHER : tcpath ? PC_GEMM_TC : PC_GEMM_SIMT, exact ? 2.0 * Mp * l.N * l.K : 0.0,
+                 !exact ? 0.0 : (double)sizeof(T) * ((double)Mp * l.K + (double)l.N * l.K) + (double)sizeof(TOut) * Mp * l.N + (resid ? 4.0 * Mp * l.N : 0.0),
+                 Mp, l.N, l.K);
   if constexpr (std::is_same<T, bf16>::value) {
     if (e->use_tc && e->gemm2 && M >= 2048 && l.N >= 512)
       err = tc::gemm_tc2<TOut>(s, A, lda, l.w16, l.K, l.b, resid, ldr, out, ldc, M, l.N, l.K, relu, live, e->rows_dev, e->ares, e->kps);
@@ -336,21 +344,24 @@ static int ln_linear(bofi_engine* e, cudaStream_t s, const float* x, const Norm&
 template <int KT>
 static cudaError_t launch_attention_mma(cudaStream_t s, dim3 grid, size_t smem, const bf16* Q, int ldq, const bf16* K, const bf16* V,
                                         int ldkv, bf16* O, int ldo, int Tq, int Tk, const int* vis, int vis_bs, int vis_qs,
-                                        int vis_div, int kv_div, float scale, const int* live, Drop drop) {
-  static size_t configured = 0;
+                                        int vis_div, int kv_div, float scale, const int* live, Drop drop, const int* seq_off, int q_varlen) {
+  static PerDevice<size_t> configured_dev;
+  size_t& configured = configured_dev.get();
   if (smem > configured) {
     cudaError_t err = cudaFuncSetAttribute(attention_mma_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     configured = smem;
   }
-  launch_k(attention_mma_kernel<KT>, grid, 128, smem, s, Q, ldq, K, V, ldkv, O, ldo, Tq, Tk, vis, vis_bs, vis_qs, vis_div, kv_div, scale, live, drop);
+  launch_k(attention_mma_kernel<KT>, grid, 128, smem, s, Q, ldq, K, V, ldkv, O, ldo, Tq, Tk, vis, vis_bs, vis_qs, vis_div, kv_div, scale, live, drop, seq_off, q_varlen);
   return cudaGetLastError();
 }
 
 template <typename T>
 static int attention(bofi_engine* e, cudaStream_t s, const T* Q, int ldq, const T* K, const T* V, int ldkv, T* O, int ldo,
                      int nb, int Tq, int Tk, const int* vis, int vis_bs, int vis_qs, int vis_div, int kv_div,
-                     const int* live, const int* finished = nullptr, Drop drop = Drop(), const int* rowmap = nullptr, int rowmap_div = 1) {
+                     const int* live, const int* finished = nullptr, Drop drop = Drop(), const int* rowmap = nullptr, int rowmap_div = 1,
+                     const int* seq_off = nullptr, int q_varlen = 0) {
+  // seq_off: varlen (compact) K/V rows per sequence, see attention_mma_kernel; q_varlen: the queries are those rows too
   if (nb <= 0) return BOFI_OK;
   if (Tk > kMaxKeys || Tq > kMaxKeys) return fail(BOFI_ERR_INVALID, "attention over %d x %d (max %d)", Tq, Tk, kMaxKeys);
   const float scale = 1.0f / sqrtf((float)kHeadDim);
@@ -359,9 +370,9 @@ static int attention(bofi_engine* e, cudaStream_t s, const T* Q, int ldq, const 
   if (Tq == 1 && !e->attn_simt_only) {
     if constexpr (std::is_same<T, bf16>::value)
       launch_k(attention_row_bf16_kernel, e->rows_dev ? std::min(ceil_div(nb, kRowsPerCta), 148 * 2) : ceil_div(nb, kRowsPerCta), kRowsPerCta * 256, 0, s, Q, ldq, K, V, ldkv, O, ldo, nb, Tk, vis, vis_div,
-               kv_div, scale, live, finished, drop, rowmap, rowmap_div, e->rows_dev);
+               kv_div, scale, live, finished, drop, rowmap, rowmap_div, e->rows_dev, seq_off);
     else
-      launch_k(attention_row_kernel<T>, nb, 256, 0, s, Q, ldq, K, V, ldkv, O, ldo, Tk, vis, vis_div, kv_div, scale, live, finished, drop, rowmap, rowmap_div, e->rows_dev);
+      launch_k(attention_row_kernel<T>, nb, 256, 0, s, Q, ldq, K, V, ldkv, O, ldo, Tk, vis, vis_div, kv_div, scale, live, finished, drop, rowmap, rowmap_div, e->rows_dev, seq_off);
     CU_TRY(cudaGetLastError());
     return BOFI_OK;
   }
@@ -371,7 +382,7 @@ static int attention(bofi_engine* e, cudaStream_t s, const T* Q, int ldq, const 
       const size_t smem = attention_mma_smem_bytes(KT, Tq);
       dim3 grid(e->cfg.heads, nb);
       cudaError_t err = cudaErrorInvalidValue;
-#define BOFI_ATT_CASE(n) case n: err = launch_attention_mma<n>(s, grid, smem, Q, ldq, K, V, ldkv, O, ldo, Tq, Tk, vis, vis_bs, vis_qs, vis_div, kv_div, scale, live, drop); break;
+#define BOFI_ATT_CASE(n) case n: err = launch_attention_mma<n>(s, grid, smem, Q, ldq, K, V, ldkv, O, ldo, Tq, Tk, vis, vis_bs, vis_qs, vis_div, kv_div, scale, live, drop, seq_off, q_varlen); break;
       switch (KT) {
         BOFI_ATT_CASE(1) BOFI_ATT_CASE(2) BOFI_ATT_CASE(3) BOFI_ATT_CASE(4)
         BOFI_ATT_CASE(5) BOFI_ATT_CASE(6) BOFI_ATT_CASE(7) BOFI_ATT_CASE(8)
@@ -382,14 +393,14 @@ static int attention(bofi_engine* e, cudaStream_t s, const T* Q, int ldq, const 
     }
   }
   const size_t smem = attention_smem_bytes(Tk);
-  static size_t configured_f = 0, configured_h = 0;
-  size_t& configured = std::is_same<T, float>::value ? configured_f : configured_h;
+  static PerDevice<size_t> configured_f, configured_h;
+  size_t& configured = std::is_same<T, float>::value ? configured_f.get() : configured_h.get();
   if (smem > configured) {
     CU_TRY(cudaFuncSetAttribute(attention_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attention_smem_bytes(kMaxKeys)));
     configured = attention_smem_bytes(kMaxKeys);
   }
   dim3 grid(e->cfg.heads, nb);
-  launch_k(attention_kernel<T>, grid, 128, smem, s, Q, ldq, K, V, ldkv, O, ldo, Tq, Tk, vis, vis_bs, vis_qs, vis_div, kv_div, scale, live, drop);
+  launch_k(attention_kernel<T>, grid, 128, smem, s, Q, ldq, K, V, ldkv, O, ldo, Tq, Tk, vis, vis_bs, vis_qs, vis_div, kv_div, scale, live, drop, seq_off, q_varlen);
   CU_TRY(cudaGetLastError());
   return BOFI_OK;
 }
@@ -408,13 +419,14 @@ static int run_layer(bofi_engine* e, cudaStream_t s, const Layer& ly, float* x, 
   T* ffh = e->ffh.as<T>();
   RC_TRY((ln_linear<T, T>(e, s, x, ly.ln[0], ly.sa.qkv, qkv, 3 * kD, rows, 0, live, y)));
   RC_TRY(attention<T>(e, s, qkv, 3 * kD, qkv + kD, qkv + 2 * kD, 3 * kD, ao, kD, nb, T_, T_, self_vis, self_vis_bs,
-                      self_vis_qs, 1, 1, live));
+                      self_vis_qs, 1, 1, live, nullptr, Drop(), nullptr, 1, e->enc_off, e->enc_off != nullptr));
   RC_TRY((linear<T, float>(e, s, ao, kD, ly.sa.o, x, kD, x, kD, rows, 0, live)));
   int f = 1;
   if (ly.cross) {
     T* q = e->q.as<T>();
     RC_TRY((ln_linear<T, T>(e, s, x, ly.ln[1], ly.ca.q, q, kD, rows, 0, live, y)));
-    RC_TRY(attention<T>(e, s, q, kD, kvmem, kvmem + kD, 2 * kD, ao, kD, nb, T_, R, mem_len, 1, 0, kv_div, kv_div, live));
+    RC_TRY(attention<T>(e, s, q, kD, kvmem, kvmem + kD, 2 * kD, ao, kD, nb, T_, R, mem_len, 1, 0, kv_div, kv_div, live, nullptr, Drop(), nullptr, 1,
+                        e->mem_off));
     RC_TRY((linear<T, float>(e, s, ao, kD, ly.ca.o, x, kD, x, kD, rows, 0, live)));
     f = 2;
   }
@@ -530,7 +542,6 @@ static size_t tsize(bofi_engine* e) { return e->bf16_mode ? 2 : 4; }
 
 static int reserve_encode(bofi_engine* e, int B, int R) {
   const size_t M = (size_t)B * R, ts = tsize(e);
-  if (e->bf16_mode) RC_TRY(e->attT.reserve(M * e->cfg.att_feat_size * ts));
   RC_TRY(e->x.reserve(M * kD * 4));
   RC_TRY(e->y.reserve(M * kD * ts));
   RC_TRY(e->qkv.reserve(M * 3 * kD * ts));
@@ -581,39 +592,93 @@ static int reserve_decode(bofi_engine* e, int B, int R, int sn) {
 
 // ---- encode --------------------------------------------------------------------------------------------
 template <typename T>
-static int encode_impl(bofi_engine* e, cudaStream_t s, const float* att, const int* att_len, int B, int R, float* memory_out) {
+static int encode_impl(bofi_engine* e, cudaStream_t s, const void* att, int fdt, const int* att_len, int B, int R, float* memory_out) {
   const int M = B * R, F = e->cfg.att_feat_size;
   RC_TRY(reserve_encode(e, B, R));
   float* x = e->x.as<float>();
+  // ---- features as the GEMM operand type.  bf16 engine + bf16 features: the caller's buffer IS the operand (TMA reads it
+  // in place, no conversion pass); anything else goes through one conversion kernel into attT.
   const T* a_in;
-  if constexpr (std::is_same<T, bf16>::value) {
-    const size_t n4 = (size_t)M * F / 4;
-    {
-      ProfScope prof(e, s, PC_OTHER, 0.0, (double)M * F * 6.0);
-      launch_k(cast_kernel<bf16>, (int)std::min<size_t>((n4 + 255) / 256, 148 * 16), 256, 0, s, att, e->attT.as<bf16>(), n4);
+  {
+    const size_t n = (size_t)M * F;
+    const bool direct = (std::is_same<T, bf16>::value && fdt == BOFI_FEAT_BF16) || (std::is_same<T, float>::value && fdt == BOFI_FEAT_F32);
+    if (direct) {
+      if (reinterpret_cast<uintptr_t>(att) & 15) return fail(BOFI_ERR_INVALID, "att_feats must be 16-byte aligned");
+      a_in = reinterpret_cast<const T*>(att);
+    } else {
+      RC_TRY(e->attT.reserve(n * sizeof(T)));
+      T* dst = e->attT.as<T>();
+      ProfScope prof(e, s, PC_OTHER, 0.0, (double)n * ((fdt == BOFI_FEAT_F32 ? 4 : 2) + sizeof(T)));
+      const int grid = (int)std::min<size_t>((n / 4 + 255) / 256, 148 * 16);
+      if (fdt == BOFI_FEAT_F32) launch_k(cast_kernel<T>, grid, 256, 0, s, reinterpret_cast<const float*>(att), dst, n / 4);
+      else if (fdt == BOFI_FEAT_F16) launch_k(convert8_kernel<__half, T>, grid, 256, 0, s, reinterpret_cast<const __half*>(att), dst, n / 8);
+      else launch_k(convert8_kernel<bf16, T>, grid, 256, 0, s, reinterpret_cast<const bf16*>(att), dst, n / 8);
+      CU_TRY(cudaGetLastError());
+      a_in = dst;
     }
-    CU_TRY(cudaGetLastError());
-    a_in = e->attT.as<bf16>();
-  } else {
-    a_in = att;
   }
-  // att_embed = Linear(2048, 512) + ReLU (TransformerModel.py:1642-1647); padded rows -> 0 (AttModel.py:46-51)
-  RC_TRY((linear<T, float>(e, s, a_in, F, e->att_embed, nullptr, 0, x, kD, M, 1, nullptr)));
   const int* len_dev = nullptr;
   e->have_len = (att_len != nullptr);
+  e->enc_off = e->mem_off = nullptr;
+  const bool varlen = att_len && e->varlen;
   if (att_len) {
     if (att_len != e->attlen.as<int>())
       CU_TRY(cudaMemcpyAsync(e->attlen.p, att_len, (size_t)B * 4, cudaMemcpyDeviceToDevice, s));
     len_dev = e->attlen.as<int>();
-    {
+  }
+  // att_embed = Linear(2048, 512) + ReLU (TransformerModel.py:1642-1647); padded rows -> 0 (AttModel.py:46-51)
+  if (!varlen) {
+    RC_TRY((linear<T, float>(e, s, a_in, F, e->att_embed, nullptr, 0, x, kD, M, 1, nullptr)));
+    if (len_dev) {
       ProfScope prof(e, s, PC_OTHER, 0.0, 0.0);
       launch_k(zero_padded_rows_kernel, ceil_div(M, 8), 256, 0, s, x, len_dev, B, R);
+      CU_TRY(cudaGetLastError());
+    }
+    for (const Layer& ly : e->enc)
+      RC_TRY(run_layer<T>(e, s, ly, x, B, R, len_dev, 1, 0, (const T*)nullptr, 0, nullptr, 1, nullptr));
+    RC_TRY(layernorm<T>(e, s, x, kD, e->enc_norm, e->memT.as<T>(), kD, M, memory_out, nullptr));
+  } else {
+    // Varlen: att_embed on the padded layout (the features arrive padded; it is 5 % of the encoder's work), then every
+    // valid row moves to its compact position and the layers only see sum(att_len) rows -- the row count lives on the
+    // device (rows_dev), so nothing synchronises.  Padded rows never exist, so they need no zeroing and no key mask.
+    RC_TRY(e->xpad.reserve((size_t)M * kD * 4));
+    RC_TRY(e->seqoff.reserve((size_t)(B + 2) * 4));
+    int* off = e->seqoff.as<int>();
+    int* total = off + B + 1;
+    RC_TRY((linear<T, float>(e, s, a_in, F, e->att_embed, nullptr, 0, e->xpad.as<float>(), kD, M, 1, nullptr)));
+    {
+      ProfScope prof(e, s, PC_OTHER, 0.0, 0.0);
+      launch_k(varlen_scan_kernel, 1, 1024, 0, s, len_dev, B, R, off, total);
     }
     CU_TRY(cudaGetLastError());
+    {
+      ProfScope prof(e, s, PC_OTHER, 0.0, (double)M * kD * 8);
+      launch_k(varlen_rows_kernel<false>, ceil_div(M, 8), 256, 0, s, (const float*)e->xpad.as<float>(), (const int*)off, B, R, x);
+    }
+    CU_TRY(cudaGetLastError());
+    e->rows_hint = 0;
+    if (e->profiling) {          // exact FLOP / byte accounting of the compact launches (profiling runs only: this synchronises)
+      int t = 0;
+      CU_TRY(cudaMemcpyAsync(&t, total, 4, cudaMemcpyDeviceToHost, s));
+      CU_TRY(cudaStreamSynchronize(s));
+      e->rows_hint = t;
+    }
+    e->rows_dev = e->varlen_total = total;
+    e->enc_off = off;
+    int rc = BOFI_OK;
+    for (size_t l = 0; l < e->enc.size() && rc == BOFI_OK; ++l)
+      rc = run_layer<T>(e, s, e->enc[l], x, B, R, len_dev, 1, 0, (const T*)nullptr, 0, nullptr, 1, nullptr);
+    if (rc == BOFI_OK) rc = layernorm<T>(e, s, x, kD, e->enc_norm, e->memT.as<T>(), kD, M, memory_out ? e->xpad.as<float>() : nullptr, nullptr);
+    e->rows_dev = nullptr;
+    e->enc_off = nullptr;
+    RC_TRY(rc);
+    if (memory_out) {
+      ProfScope prof(e, s, PC_OTHER, 0.0, 0.0);
+      launch_k(varlen_rows_kernel<true>, ceil_div(M, 8), 256, 0, s, (const float*)e->xpad.as<float>(), (const int*)off, B, R, memory_out);
+      CU_TRY(cudaGetLastError());
+    }
+    e->mem_off = off;            // memory, its K/V projections and every cross-attention of the decode use the compact rows
   }
-  for (const Layer& ly : e->enc)
-    RC_TRY(run_layer<T>(e, s, ly, x, B, R, len_dev, 1, 0, (const T*)nullptr, 0, nullptr, 1, nullptr));
-  RC_TRY(layernorm<T>(e, s, x, kD, e->enc_norm, e->memT.as<T>(), kD, M, memory_out, nullptr));
   e->B = B;
   e->R = R;
   e->have_memory = true;
@@ -623,13 +688,19 @@ static int encode_impl(bofi_engine* e, cudaStream_t s, const float* att, const i
 // ---- decode --------------------------------------------------------------------------------------------
 template <typename T>
 static int project_memory_kv(bofi_engine* e, cudaStream_t s, const Lin& kv, DevBuf& out) {
-  return linear<T, T>(e, s, e->memT.as<T>(), kD, kv, nullptr, 0, out.as<T>(), 2 * kD, e->B * e->R, 0, nullptr);
+  // varlen memory: only the compact rows exist (device-side row count)
+  const int* keep = e->rows_dev;
+  if (e->mem_off) e->rows_dev = e->mem_off + e->B + 1;
+  const int rc = linear<T, T>(e, s, e->memT.as<T>(), kD, kv, nullptr, 0, out.as<T>(), 2 * kD, e->B * e->R, 0, nullptr);
+  e->rows_dev = keep;
+  return rc;
 }
 
 // Final LayerNorm of the [LEN] row + both classifier heads + box rule, one fused launch per step.
 static int head_step(bofi_engine* e, cudaStream_t s, const float* x, size_t x_stride, int rows, int step_col, int step_no, int saic) {
   const size_t smem = sizeof(float) * (kHeadRows * kD + kHeadRows * 200 + kHeadRows * 32 + 4 * kHeadRows * 200);
-  static bool configured = false;
+  static PerDevice<bool> configured_dev;
+  bool& configured = configured_dev.get();
   if (!configured) {
     CU_TRY(cudaFuncSetAttribute(bound_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
@@ -668,7 +739,8 @@ static int bounding_step(bofi_engine* e, cudaStream_t s, int rows, int sn, int s
     T* ao = e->ao.as<T>();
     RC_TRY(layernorm<T>(e, s, x, kD, ly.ln[0], y, kD, rows, nullptr, live));
     RC_TRY((linear<T, T>(e, s, y, kD, ly.ca.q, nullptr, 0, q, kD, rows, 0, live)));
-    RC_TRY(attention<T>(e, s, q, kD, e->kv[0].as<T>(), e->kv[0].as<T>() + kD, 2 * kD, ao, kD, rows, 1, e->R, mem_len, 1, 0, sn, sn, live));
+    RC_TRY(attention<T>(e, s, q, kD, e->kv[0].as<T>(), e->kv[0].as<T>() + kD, 2 * kD, ao, kD, rows, 1, e->R, mem_len, 1, 0, sn, sn, live, nullptr, Drop(),
+                        nullptr, 1, e->mem_off));
     RC_TRY((linear<T, float>(e, s, ao, kD, ly.ca.o, x, kD, x, kD, rows, 0, live)));
   } else {
     for (int l = 0; l < c.n_len; ++l)
@@ -703,7 +775,7 @@ static int bounding_step_fast(bofi_engine* e, cudaStream_t s, int rows, int sn, 
   RC_TRY((linear<T, float>(e, s, ao, kD, ly.sa.o, x0, 0, x, kD, rows, 0, live)));          // residual = x0 broadcast
   RC_TRY((ln_linear<T, T>(e, s, x, ly.ln[1], ly.ca.q, q, kD, rows, 0, live, y)));
   RC_TRY(attention<T>(e, s, q, kD, e->kv[0].as<T>(), e->kv[0].as<T>() + kD, 2 * kD, ao, kD, rows, 1, e->R, mem_len, 1, 0, sn, sn, live,
-                      e->st.finished));
+                      e->st.finished, Drop(), nullptr, 1, e->mem_off));
   RC_TRY((linear<T, float>(e, s, ao, kD, ly.ca.o, x, kD, x, kD, rows, 0, live)));
   RC_TRY((ln_linear<T, T>(e, s, x, ly.ln[2], ly.w1, ffh, c.d_ff, rows, 1, live, y)));
   RC_TRY((linear<T, float>(e, s, ffh, c.d_ff, ly.w2, x, kD, x, kD, rows, 0, live)));
@@ -801,7 +873,8 @@ static int decode_naic(bofi_engine* e, cudaStream_t s, int sn, int output_logsof
     return BOFI_OK;
   };
   const unsigned long long key[12] = {(unsigned long long)rows, (unsigned long long)e->R, (unsigned long long)sn,
-                                      (unsigned long long)e->have_len, g_alloc_generation, (unsigned long long)e->bound_fast};
+                                      (unsigned long long)e->have_len, g_alloc_generation, (unsigned long long)e->bound_fast,
+                                      (unsigned long long)(uintptr_t)e->flat_w, (unsigned long long)(uintptr_t)e->flat16.p};
   RC_TRY(run_graphed(e, s, e->g_bound, key, enqueue_bounding));
 
   // filling step (decode_NA, :570-587): all L slots of every row in parallel
@@ -987,7 +1060,7 @@ static int decode_saic_incremental(bofi_engine* e, cudaStream_t s, int sn, int o
       RC_TRY((linear<T, float>(e, s, ao, kD, lb.sa.o, e->sa_x0.as<float>(), 0, x, kD, rows, 0, live)));     // residual = the [LEN] input row
       RC_TRY((ln_linear<T, T>(e, s, x, lb.ln[1], lb.ca.q, q, kD, rows, 0, live, y)));
       RC_TRY(attention<T>(e, s, q, kD, e->kv[0].as<T>(), e->kv[0].as<T>() + kD, 2 * kD, ao, kD, rows, 1, e->R, mem_len, 1, 0, sn, sn, live,
-                          e->st.finished));
+                          e->st.finished, Drop(), nullptr, 1, e->mem_off));
       RC_TRY((linear<T, float>(e, s, ao, kD, lb.ca.o, x, kD, x, kD, rows, 0, live)));
       RC_TRY((ln_linear<T, T>(e, s, x, lb.ln[2], lb.w1, ffh, c.d_ff, rows, 1, live, y)));
       RC_TRY((linear<T, float>(e, s, ffh, c.d_ff, lb.w2, x, kD, x, kD, rows, 0, live)));
@@ -1019,7 +1092,7 @@ static int decode_saic_incremental(bofi_engine* e, cudaStream_t s, int sn, int o
         CU_TRY(cudaGetLastError());
         RC_TRY((linear<T, float>(e, s, ao, kD, ly.sa.o, x, kD, x, kD, slots, 0, live)));
         RC_TRY((ln_linear<T, T>(e, s, x, ly.ln[1], ly.ca.q, q, kD, slots, 0, live, y)));
-        RC_TRY(attention<T>(e, s, q, kD, kvmem, kvmem + kD, 2 * kD, ao, kD, slots, 1, e->R, mem_len, 1, 0, sn, sn, live, nullptr, Drop(), cidx, L));
+        RC_TRY(attention<T>(e, s, q, kD, kvmem, kvmem + kD, 2 * kD, ao, kD, slots, 1, e->R, mem_len, 1, 0, sn, sn, live, nullptr, Drop(), cidx, L, e->mem_off));
         RC_TRY((linear<T, float>(e, s, ao, kD, ly.ca.o, x, kD, x, kD, slots, 0, live)));
         RC_TRY((ln_linear<T, T>(e, s, x, ly.ln[2], ly.w1, ffh, c.d_ff, slots, 1, live, y)));
         RC_TRY((linear<T, float>(e, s, ffh, c.d_ff, ly.w2, x, kD, x, kD, slots, 0, live)));
@@ -1064,7 +1137,8 @@ static int decode_saic_incremental(bofi_engine* e, cudaStream_t s, int sn, int o
   // ~1900 small launches per decode: replayed as one graph (not while sampling: the noise key is a launch argument)
   const unsigned long long key[12] = {(unsigned long long)rows, (unsigned long long)e->R, (unsigned long long)sn, (unsigned long long)e->have_len,
                                       g_alloc_generation, (unsigned long long)(uintptr_t)logprobs, (unsigned long long)output_logsoftmax,
-                                      (unsigned long long)(uintptr_t)e->stat_entropy, (unsigned long long)(uintptr_t)e->stat_logp};
+                                      (unsigned long long)(uintptr_t)e->stat_entropy, (unsigned long long)(uintptr_t)e->stat_logp,
+                                      (unsigned long long)(uintptr_t)e->flat_w, (unsigned long long)(uintptr_t)e->flat16.p};
   if (e->sampler.enabled) RC_TRY(enqueue_steps(s));
   else RC_TRY(run_graphed(e, s, e->g_saic, key, enqueue_steps));
   LAUNCH_OTHER((launch_k(export_seq_kernel, ceil_div(rows * L, 256), 256, 0, s, e->st, rows, Lb, L, seq)));
@@ -1118,6 +1192,10 @@ int bofi_create(const bofi_config_t* cfg, int device, bofi_handle_t* out) {
     return fail(BOFI_ERR_INVALID, "kernels are specialised for d_model=512, 8 heads (got d_model=%d heads=%d)", cfg->d_model, cfg->heads);
   if (cfg->d_ff % 64 || cfg->att_feat_size % 64) return fail(BOFI_ERR_INVALID, "d_ff / att_feat_size must be multiples of 64");
   if (cfg->seq_length + 2 > 32 || cfg->seq_length < 1) return fail(BOFI_ERR_INVALID, "seq_length %d unsupported", cfg->seq_length);
+  // the vocabulary kernels hold one row in registers (kVocabThreads x kVocabVec float4) and the sampler's noise index is
+  // row * 16384 + v: a larger vocabulary would be silently truncated, so it is refused here
+  if (cfg->tgt_vocab < 8 || cfg->tgt_vocab > kVocabThreads * kVocabVec * 4)
+    return fail(BOFI_ERR_INVALID, "tgt_vocab %d unsupported (the vocabulary kernels cover 8..%d columns)", cfg->tgt_vocab, kVocabThreads * kVocabVec * 4);
   if (cfg->n_enc < 0 || cfg->n_dec < 1 || cfg->n_len < 0) return fail(BOFI_ERR_INVALID, "bad layer counts");
   if (cfg->precision != BOFI_PRECISION_FP32 && cfg->precision != BOFI_PRECISION_BF16) return fail(BOFI_ERR_INVALID, "bad precision");
   int ndev = 0;
@@ -1156,6 +1234,8 @@ int bofi_create(const bofi_config_t* cfg, int device, bofi_handle_t* out) {
   if (const char* gm = getenv("BOFI_LNFUSE_MIN")) e->ln_fuse_min_rows = atoi(gm);
   const char* gs = getenv("BOFI_SAIC");
   e->saic_full = (gs && strcmp(gs, "full") == 0);
+  const char* gv = getenv("BOFI_VARLEN");
+  e->varlen = !(gv && strcmp(gv, "0") == 0);
   const char* ga = getenv("BOFI_ATTN");
   e->attn_simt_only = (ga && strcmp(ga, "simt") == 0);
   build_spec(e);
@@ -1180,7 +1260,7 @@ int bofi_destroy(bofi_handle_t e) {
   for (DevBuf& b : e->kv) b.release();
   DevBuf* all[] = {&e->bound_in, &e->fill_in, &e->attT, &e->x, &e->y, &e->qkv, &e->ao, &e->q, &e->ffh, &e->memT, &e->attlen,
                    &e->sa_mx, &e->sa_lse, &e->sa_cidx, &e->sa_cache, &e->sa_bcache, &e->sa_qkv0, &e->sa_x0, &e->head1t, &e->tab_y, &e->tab_qkv, &e->logits, &e->state_i32, &e->tok, &e->h_in, &e->h_len, &e->h_seq, &e->h_logp,
-                   &e->h_pnum, &e->h_plen, &e->h_psyn, &e->unit_a, &e->unit_w, &e->unit_o};
+                   &e->h_pnum, &e->h_plen, &e->h_psyn, &e->unit_a, &e->unit_w, &e->unit_o, &e->xpad, &e->seqoff, &e->maskflag};
   for (DevBuf* b : all) b->release();
   delete e;
   return BOFI_OK;
@@ -1231,16 +1311,49 @@ int64_t bofi_workspace_bytes(bofi_handle_t e, int32_t B, int32_t R, int32_t sn) 
   return t + t / 8;
 }
 
-int bofi_encode(bofi_handle_t e, void* stream, const float* att_feats, const int32_t* att_len, int32_t B, int32_t R, float* memory_out) {
+int bofi_encode_ex(bofi_handle_t e, void* stream, const void* att_feats, int32_t feat_dtype, const int32_t* att_len, int32_t B, int32_t R,
+                   float* memory_out) {
   if (!e || !att_feats) return fail(BOFI_ERR_INVALID, "null argument");
   if (!e->finalized) return fail(BOFI_ERR_STATE, "weights not finalised");
   if (B <= 0 || R <= 0 || R > kMaxKeys) return fail(BOFI_ERR_INVALID, "bad batch B=%d R=%d (R <= %d)", B, R, kMaxKeys);
+  if (feat_dtype != BOFI_FEAT_F32 && feat_dtype != BOFI_FEAT_BF16 && feat_dtype != BOFI_FEAT_F16)
+    return fail(BOFI_ERR_INVALID, "feat_dtype %d (BOFI_FEAT_F32 / BF16 / F16)", feat_dtype);
   CU_TRY(cudaSetDevice(e->device));
   e->launches = 0;
   e->have_memory = false;
   cudaStream_t s = (cudaStream_t)stream;
-  return e->bf16_mode ? encode_impl<bf16>(e, s, att_feats, att_len, B, R, memory_out)
-                      : encode_impl<float>(e, s, att_feats, att_len, B, R, memory_out);
+  return e->bf16_mode ? encode_impl<bf16>(e, s, att_feats, feat_dtype, att_len, B, R, memory_out)
+                      : encode_impl<float>(e, s, att_feats, feat_dtype, att_len, B, R, memory_out);
+}
+
+int bofi_encode(bofi_handle_t e, void* stream, const float* att_feats, const int32_t* att_len, int32_t B, int32_t R, float* memory_out) {
+  return bofi_encode_ex(e, stream, att_feats, BOFI_FEAT_F32, att_len, B, R, memory_out);
+}
+
+int bofi_masks_to_len(bofi_handle_t e, void* stream, const float* att_masks, int32_t B, int32_t R, int32_t* att_len) {
+  if (!e || !att_masks || !att_len) return fail(BOFI_ERR_INVALID, "null argument");
+  if (B <= 0 || R <= 0) return fail(BOFI_ERR_INVALID, "bad batch B=%d R=%d", B, R);
+  CU_TRY(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!e->maskflag.p) {
+    RC_TRY(e->maskflag.reserve(4));
+    CU_TRY(cudaMemsetAsync(e->maskflag.p, 0, 4, s));
+  }
+  launch_k(masks_to_len_kernel, ceil_div(B, 8), 256, 0, s, att_masks, B, R, att_len, e->maskflag.as<int>());
+  CU_TRY(cudaGetLastError());
+  return BOFI_OK;
+}
+
+int bofi_check_masks(bofi_handle_t e, void* stream, int32_t* bad) {
+  if (!e || !bad) return fail(BOFI_ERR_INVALID, "null argument");
+  *bad = 0;
+  if (!e->maskflag.p) return BOFI_OK;
+  CU_TRY(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  CU_TRY(cudaMemcpyAsync(bad, e->maskflag.p, 4, cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaMemsetAsync(e->maskflag.p, 0, 4, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  return BOFI_OK;
 }
 
 int bofi_decode(bofi_handle_t e, void* stream, int32_t mode, int32_t sn, int32_t output_logsoftmax, int64_t* seq, float* logprobs,
@@ -1262,24 +1375,27 @@ int bofi_decode(bofi_handle_t e, void* stream, int32_t mode, int32_t sn, int32_t
                       : decode_naic<float>(e, s, sn, output_logsoftmax, (long long*)seq, logprobs, phrase_num, phrase_length, (long long*)phrase_syn);
 }
 
-int bofi_sample_host_async(bofi_handle_t e, void* stream, int32_t mode, int32_t sn, int32_t output_logsoftmax, const float* att_feats,
-                           const int32_t* att_len, int32_t B, int32_t R, int64_t* seq, float* logprobs, int32_t* phrase_num,
-                           int32_t* phrase_length, int64_t* phrase_syn) {
+int bofi_sample_host_async_ex(bofi_handle_t e, void* stream, int32_t mode, int32_t sn, int32_t output_logsoftmax, const void* att_feats,
+                              int32_t feat_dtype, const int32_t* att_len, int32_t B, int32_t R, int64_t* seq, float* logprobs,
+                              int32_t* phrase_num, int32_t* phrase_length, int64_t* phrase_syn) {
   if (!e || !att_feats || !seq || !phrase_num || !phrase_length || !phrase_syn) return fail(BOFI_ERR_INVALID, "null argument");
   if (B <= 0 || R <= 0 || sn < 1) return fail(BOFI_ERR_INVALID, "bad batch");
+  if (feat_dtype != BOFI_FEAT_F32 && feat_dtype != BOFI_FEAT_BF16 && feat_dtype != BOFI_FEAT_F16)
+    return fail(BOFI_ERR_INVALID, "feat_dtype %d (BOFI_FEAT_F32 / BF16 / F16)", feat_dtype);
   CU_TRY(cudaSetDevice(e->device));
   cudaStream_t s = (cudaStream_t)stream;
   const size_t rows = (size_t)B * sn, L = e->L;
-  RC_TRY(e->h_in.reserve((size_t)B * R * e->cfg.att_feat_size * 4));
+  const size_t in_bytes = (size_t)B * R * e->cfg.att_feat_size * (feat_dtype == BOFI_FEAT_F32 ? 4 : 2);
+  RC_TRY(e->h_in.reserve(in_bytes));
   RC_TRY(e->attlen.reserve((size_t)B * 4));
   RC_TRY(e->h_seq.reserve(rows * L * 8));
   RC_TRY(e->h_pnum.reserve(rows * 4));
   RC_TRY(e->h_plen.reserve(rows * L * 4));
   RC_TRY(e->h_psyn.reserve(rows * L * 8));
   if (logprobs) RC_TRY(e->h_logp.reserve(rows * L * (size_t)e->V * 4));
-  CU_TRY(cudaMemcpyAsync(e->h_in.p, att_feats, (size_t)B * R * e->cfg.att_feat_size * 4, cudaMemcpyHostToDevice, s));
+  CU_TRY(cudaMemcpyAsync(e->h_in.p, att_feats, in_bytes, cudaMemcpyHostToDevice, s));
   if (att_len) CU_TRY(cudaMemcpyAsync(e->attlen.p, att_len, (size_t)B * 4, cudaMemcpyHostToDevice, s));
-  RC_TRY(bofi_encode(e, stream, e->h_in.as<float>(), att_len ? e->attlen.as<int>() : nullptr, B, R, nullptr));
+  RC_TRY(bofi_encode_ex(e, stream, e->h_in.p, feat_dtype, att_len ? e->attlen.as<int>() : nullptr, B, R, nullptr));
   RC_TRY(bofi_decode(e, stream, mode, sn, output_logsoftmax, e->h_seq.as<int64_t>(), logprobs ? e->h_logp.as<float>() : nullptr,
                      e->h_pnum.as<int>(), e->h_plen.as<int>(), e->h_psyn.as<int64_t>()));
   CU_TRY(cudaMemcpyAsync(seq, e->h_seq.p, rows * L * 8, cudaMemcpyDeviceToHost, s));
@@ -1288,6 +1404,13 @@ int bofi_sample_host_async(bofi_handle_t e, void* stream, int32_t mode, int32_t 
   CU_TRY(cudaMemcpyAsync(phrase_syn, e->h_psyn.p, rows * L * 8, cudaMemcpyDeviceToHost, s));
   if (logprobs) CU_TRY(cudaMemcpyAsync(logprobs, e->h_logp.p, rows * L * (size_t)e->V * 4, cudaMemcpyDeviceToHost, s));
   return BOFI_OK;
+}
+
+int bofi_sample_host_async(bofi_handle_t e, void* stream, int32_t mode, int32_t sn, int32_t output_logsoftmax, const float* att_feats,
+                           const int32_t* att_len, int32_t B, int32_t R, int64_t* seq, float* logprobs, int32_t* phrase_num,
+                           int32_t* phrase_length, int64_t* phrase_syn) {
+  return bofi_sample_host_async_ex(e, stream, mode, sn, output_logsoftmax, att_feats, BOFI_FEAT_F32, att_len, B, R, seq, logprobs, phrase_num,
+                                   phrase_length, phrase_syn);
 }
 
 int bofi_sample_host(bofi_handle_t e, void* stream, int32_t mode, int32_t sn, int32_t output_logsoftmax, const float* att_feats,

@@ -308,7 +308,8 @@ inline cudaError_t launch_ln(cudaStream_t s, const CUtensorMap& tmB, const CUten
                              const float* ln_b, const float* bias, int M, int N, int n_chunks, int grid, const int* live_rows,
                              const int* rows_dev) {
   static const int debug_skip_ln = getenv("BOFI_DEBUG_SKIP_LN") ? 1 : 0;      // timing experiments only (results are then wrong)
-  static bool configured = false;          // one flag per (TOut, RELU) instantiation
+  static PerDevice<bool> configured_dev;   // one flag per (TOut, RELU) instantiation and device
+  bool& configured = configured_dev.get();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_ln_tc_kernel<TOut, RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, LnSmem::kTotal);
     if (e != cudaSuccess) return e;

@@ -514,7 +514,8 @@ inline bool make_tmap(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t 
 }
 
 inline int num_sms() {
-  static int n = 0;
+  static PerDevice<int> count;
+  int& n = count.get();
   if (!n) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -529,7 +530,8 @@ inline cudaError_t launch(cudaStream_t s, const CUtensorMap& tmA, const CUtensor
                           const float* bias, const float* residual, int ldr, int M, int N, int K, int relu,
                           const int* live_rows, int k_splits = 1, const int* rows_dev = nullptr) {
   using L = SmemLayout<BN, STAGES>;
-  static bool configured = false;
+  static PerDevice<bool> configured_dev;
+  bool& configured = configured_dev.get();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, TOut, RELU, RESID, A_MN, B_MN, REDUCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     if (e != cudaSuccess) return e;
@@ -559,11 +561,13 @@ struct TmapHash {
   }
 };
 inline const CUtensorMap* cached_tmap(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, int elt = 2) {
-  static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapHash> cache;
+  // Callers hold the returned pointers across the next two lookups: on overflow the full map is parked in `retired`
+  // (node addresses survive the move) and only freed one overflow later, never inside a lookup sequence.
+  static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapHash> cache, retired;
   TmapKey key{ptr, rows, cols, ld, box_rows, elt};
   auto it = cache.find(key);
   if (it != cache.end()) return &it->second;
-  if (cache.size() > 8192) cache.clear();
+  if (cache.size() > 8192) { retired = std::move(cache); cache.clear(); }
   CUtensorMap tm;
   if (!make_tmap(&tm, ptr, rows, cols, ld, box_rows, elt)) return nullptr;
   return &cache.emplace(key, tm).first->second;
@@ -583,11 +587,11 @@ inline bool inplace_reduce() {
 // (64, box_rows, box_kb) lands as box_kb consecutive 128B-swizzled k-block tiles of box_rows x 128 bytes -- the smem
 // image of box_kb separate 2-D loads, in one instruction (see Smem2T in gemm_tc2.cuh for why that matters).
 inline const CUtensorMap* cached_tmap_kblocks(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_kb) {
-  static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapHash> cache;
+  static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapHash> cache, retired;   // see cached_tmap
   TmapKey key{ptr, rows, cols, ld, box_rows, (int)box_kb};
   auto it = cache.find(key);
   if (it != cache.end()) return &it->second;
-  if (cache.size() > 8192) cache.clear();
+  if (cache.size() > 8192) { retired = std::move(cache); cache.clear(); }
   EncodeTiledFn fn = get_encode_fn();
   if (!fn || cols % 64 != 0) return nullptr;
   CUtensorMap tm;

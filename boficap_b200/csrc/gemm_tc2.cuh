@@ -447,7 +447,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 template <typename TOut, bool RELU, bool RESID, bool REDUCE = false, bool ARES = false, int KPS = 1>
 inline cudaError_t launch2(cudaStream_t s, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const float* bias,
                            const float* residual, int ldr, int M, int N, int K, int relu, const int* live_rows, const int* rows_dev) {
-  static bool configured = false;
+  static PerDevice<bool> configured_dev;
+  bool& configured = configured_dev.get();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<TOut, RELU, RESID, REDUCE, ARES, KPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2T<ARES, KPS>::kTotal);
     if (e != cudaSuccess) return e;

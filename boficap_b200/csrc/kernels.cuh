@@ -79,7 +79,7 @@ template <typename T>
 __global__ void __launch_bounds__(128)
 attention_kernel(const T* __restrict__ Q, int ldq, const T* __restrict__ K, const T* __restrict__ V, int ldkv,
                  T* __restrict__ O, int ldo, int Tq, int Tk, const int* __restrict__ vis, int vis_bs, int vis_qs,
-                 int vis_div, int kv_div, float scale, const int* live_rows, Drop drop) {
+                 int vis_div, int kv_div, float scale, const int* live_rows, Drop drop, const int* __restrict__ seq_off, int q_varlen) {
   pdl_enter();
   if (step_is_dead(live_rows)) return;
   extern __shared__ float smem[];
@@ -89,7 +89,14 @@ attention_kernel(const T* __restrict__ Q, int ldq, const T* __restrict__ K, cons
   float* ps = qs + 4 * kHeadDim;            // [4][kMaxKeys]
   const int head = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const size_t kvrow0 = (size_t)(b / kv_div) * Tk;
+  // varlen layout: see attention_mma_kernel (the shared-memory carve-up above keeps the padded Tk)
+  size_t kvrow0 = (size_t)(b / kv_div) * Tk, qrow0 = (size_t)b * Tq;
+  if (seq_off) {
+    const int o0 = seq_off[b / kv_div];
+    Tk = min(Tk, seq_off[b / kv_div + 1] - o0);
+    kvrow0 = (size_t)o0;
+    if (q_varlen) { qrow0 = kvrow0; Tq = Tk; }
+  }
   for (int idx = tid; idx < Tk * (kHeadDim / 4); idx += 128) {
     const int j = idx >> 4, c = (idx & 15) * 4;
     const float4 kq = load4(K + (kvrow0 + j) * ldkv + head * kHeadDim + c);
@@ -102,7 +109,7 @@ attention_kernel(const T* __restrict__ Q, int ldq, const T* __restrict__ K, cons
   float* q = qs + warp * kHeadDim;
   float* p = ps + warp * kMaxKeys;
   for (int t = warp; t < Tq; t += 4) {
-    const T* qg = Q + ((size_t)b * Tq + t) * ldq + head * kHeadDim;
+    const T* qg = Q + (qrow0 + t) * ldq + head * kHeadDim;
     q[lane] = to_float<T>(qg[lane]);
     q[lane + 32] = to_float<T>(qg[lane + 32]);
     __syncwarp();
@@ -137,7 +144,7 @@ attention_kernel(const T* __restrict__ Q, int ldq, const T* __restrict__ K, cons
 #pragma unroll
     for (int jj = 0; jj < kMaxKeys / 32; ++jj) {
       const int j = jj * 32 + lane;
-      if (j < Tk) p[j] = sc[jj] / sum * drop_mul(drop, att_idx(b * Tq + t, head, j));
+      if (j < Tk) p[j] = sc[jj] / sum * drop_mul(drop, att_idx((int)qrow0 + t, head, j));
     }
     __syncwarp();
     float o0 = 0.f, o1 = 0.f;
@@ -147,7 +154,7 @@ attention_kernel(const T* __restrict__ Q, int ldq, const T* __restrict__ K, cons
       o1 = fmaf(pj, Vs[j * kHeadDim + lane + 32], o1);
     }
     if (nvis <= 0) o0 = o1 = __int_as_float(0x7fc00000);   // softmax over an all -inf row
-    T* og = O + ((size_t)b * Tq + t) * ldo + head * kHeadDim;
+    T* og = O + (qrow0 + t) * ldo + head * kHeadDim;
     og[lane] = from_float<T>(o0);
     og[lane + 32] = from_float<T>(o1);
     __syncwarp();
@@ -266,6 +273,113 @@ zero_padded_rows_kernel(float* __restrict__ x, const int* __restrict__ att_len, 
   if (r < att_len[b]) return;
 #pragma unroll
   for (int i = 0; i < 4; ++i) store4(x + (size_t)row * kD + (i * 32 + lane) * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Varlen encoder (pack_wrapper / PackedSequence, AttModel.py:33-51): the reference applies att_embed to the
+// valid rows only and masks the padded keys in every attention; here the valid rows are COMPACTED once after att_embed
+// (row offsets = exclusive scan of the valid-region counts) and the whole encoder, the memory K/V projections and the
+// cross-attention K/V reads work on sum(att_len) rows.  No sort, no pack.
+// ---------------------------------------------------------------------------------------------
+// seq_off[0..B] = exclusive scan of clamp(att_len, 0, R); *total = seq_off[B].  One CTA.
+__global__ void __launch_bounds__(1024) varlen_scan_kernel(const int* __restrict__ att_len, int B, int R, int* __restrict__ seq_off,
+                                                           int* __restrict__ total) {
+  pdl_enter();
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < B; base += 1024) {
+    const int i = base + tid;
+    const int v = (i < B) ? min(max(att_len[i], 0), R) : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += n;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += n;
+      }
+      s_warp[lane] = w;                      // inclusive over the warps of this chunk
+    }
+    __syncthreads();
+    const int carry = s_carry;
+    const int excl = carry + (warp ? s_warp[warp - 1] : 0) + incl - v;
+    if (i < B) seq_off[i] = excl;
+    __syncthreads();
+    if (tid == 1023) s_carry = carry + s_warp[31];
+    __syncthreads();
+  }
+  if (tid == 0) { seq_off[B] = s_carry; *total = s_carry; }
+}
+
+// compact:  xc[seq_off[b] + r] = xp[b*R + r] for r < len_b      scatter: out[b*R + r] = r < len_b ? xc[seq_off[b] + r] : 0
+// (one warp per padded row; len_b = seq_off[b+1] - seq_off[b])
+template <bool SCATTER>
+__global__ void __launch_bounds__(256)
+varlen_rows_kernel(const float* __restrict__ src, const int* __restrict__ seq_off, int B, int R, float* __restrict__ dst) {
+  pdl_enter();
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= B * R) return;
+  const int b = row / R, r = row - b * R;
+  const int o0 = seq_off[b], len = seq_off[b + 1] - o0;
+  const bool valid = r < len;
+  if (!SCATTER && !valid) return;
+  const size_t crow = (size_t)o0 + r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (SCATTER) store4(dst + (size_t)row * kD + c, valid ? load4(src + crow * kD + c) : make_float4(0.f, 0.f, 0.f, 0.f));
+    else store4(dst + crow * kD + c, load4(src + (size_t)row * kD + c));
+  }
+}
+
+// att_masks [B, R] (f32, 0 / non-zero) -> valid-region counts, and a device-side check that every mask is a PREFIX mask
+// (what dataloader.py:333-338 produces; the kernels only take counts).  One warp per image; *bad is set to 1 otherwise.
+__global__ void __launch_bounds__(256)
+masks_to_len_kernel(const float* __restrict__ masks, int B, int R, int* __restrict__ att_len, int* __restrict__ bad) {
+  pdl_enter();
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= B) return;
+  int n = 0;
+  for (int r = lane; r < R; r += 32) n += masks[(size_t)b * R + r] != 0.f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  bool ok = true;
+  for (int r = lane; r < R; r += 32) ok &= ((masks[(size_t)b * R + r] != 0.f) == (r < n));
+  if (!__all_sync(0xffffffffu, ok) && lane == 0) atomicExch(bad, 1);
+  if (lane == 0) att_len[b] = n;
+}
+
+// fp16 -> T and bf16 -> fp32 feature conversions of the *_ex entry points (128-bit loads, n % 8 == 0)
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256) convert8_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, size_t n8) {
+  pdl_enter();
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n8; i += stride) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(in + i * 8);
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+    float f[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float2 t;
+      if constexpr (std::is_same<TIn, __half>::value) t = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
+      else t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[q]));
+      f[2 * q] = t.x;
+      f[2 * q + 1] = t.y;
+    }
+    store4(out + i * 8, make_float4(f[0], f[1], f[2], f[3]));
+    store4(out + i * 8 + 4, make_float4(f[4], f[5], f[6], f[7]));
+  }
 }
 
 // (id, position) input tables.  Embeddings (x sqrt(d), TransformerModel.py:1480-1487) + sinusoid

@@ -546,7 +546,8 @@ static int attn_bwd(bofi_engine* e, cudaStream_t s, const T* Q, int ldq, const T
       cudaError_t err = cudaErrorInvalidValue;
 #define BOFI_ATTBM(n)                                                                                                                  \
   case n: {                                                                                                                            \
-    static bool configured = false;                                                                                                    \
+    static PerDevice<bool> configured_dev;                                                                                             \
+    bool& configured = configured_dev.get();                                                                                           \
     if (!configured) {                                                                                                                 \
       CU_TRY(cudaFuncSetAttribute(attention_bwd_mma_kernel<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));                 \
       configured = true;                                                                                                               \
@@ -562,7 +563,8 @@ static int attn_bwd(bofi_engine* e, cudaStream_t s, const T* Q, int ldq, const T
   }
 #define BOFI_ATTB(KPT_)                                                                                                             \
   do {                                                                                                                              \
-    static size_t configured = 0;                                                                                                   \
+    static PerDevice<size_t> configured_dev;                                                                                        \
+    size_t& configured = configured_dev.get();                                                                                      \
     if (smem > configured) {                                                                                                        \
       CU_TRY(cudaFuncSetAttribute(attention_bwd_kernel<T, KPT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,                       \
                                   (int)attention_bwd_smem_bytes(4 * KPT_)));                                                        \

@@ -21,6 +21,10 @@ extern "C" int bofi_train_bind(bofi_handle_t e, void* stream, float* flat_params
   if (flat_params != e->flat_w) {
     CU_TRY(cudaMemcpyAsync(flat_params, e->flat_w, (size_t)e->flat_numel * sizeof(float), cudaMemcpyDeviceToDevice, s));
     CU_TRY(cudaStreamSynchronize(s));
+    // captured decode graphs bake in pointers derived from flat_w (biases, LayerNorm gains, fp32 weights): drop them
+    // before the buffer they point into is freed (the graph keys carry flat_w / flat16 as well)
+    if (e->g_bound.exec) { cudaGraphExecDestroy(e->g_bound.exec); e->g_bound = bofi_engine::GraphSlot(); }
+    if (e->g_saic.exec) { cudaGraphExecDestroy(e->g_saic.exec); e->g_saic = bofi_engine::GraphSlot(); }
     e->flat_own.release();
     e->flat_w = flat_params;
   }

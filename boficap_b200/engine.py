@@ -13,6 +13,14 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
+def _feat_code(t):
+    """BOFI_FEAT_* of a region-feature tensor (fp32 as the reference's loader yields it, or the feeder's 2-byte forms)."""
+    name = str(t.dtype).replace("torch.", "")
+    if name not in _lib.FEAT:
+        raise TypeError("att_feats must be float32, bfloat16 or float16, got %s" % t.dtype)
+    return _lib.FEAT[name]
+
+
 class BofiEngine:
     def __init__(self, cfg: BofiConfig, device=0, precision="fp32"):
         if not torch.cuda.is_available():
@@ -62,14 +70,15 @@ class BofiEngine:
 
     # ---- device path -------------------------------------------------------------------------
     def encode(self, att_feats, att_len=None, want_memory=False):
-        assert att_feats.is_cuda and att_feats.dtype == torch.float32
+        assert att_feats.is_cuda
+        code = _feat_code(att_feats)
         att_feats = att_feats.contiguous()
         B, R, _ = att_feats.shape
         if att_len is not None:
             att_len = att_len.to(device=att_feats.device, dtype=torch.int32).contiguous()
         memory = torch.empty(B, R, self.cfg.d_model, device=att_feats.device) if want_memory else None
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.bofi_encode(self.handle, self._stream(), _ptr(att_feats), _ptr(att_len), B, R, _ptr(memory)))
+            _lib.check(self.lib.bofi_encode_ex(self.handle, self._stream(), _ptr(att_feats), code, _ptr(att_len), B, R, _ptr(memory)))
         self._batch = (B, R, att_feats, att_len)      # keep inputs alive until decode is enqueued
         return memory
 
@@ -96,9 +105,15 @@ class BofiEngine:
         """End-to-end call on HOST tensors (pinned or pageable): H2D, encode, decode, D2H, sync.
         sync=False only enqueues (bofi_sample_host_async): inputs / outputs must be pinned and stay alive until the
         current stream has drained."""
-        assert not att_feats.is_cuda and att_feats.dtype == torch.float32 and att_feats.is_contiguous()
+        assert not att_feats.is_cuda and att_feats.is_contiguous()
+        code = _feat_code(att_feats)
         B, R, _ = att_feats.shape
         rows, L, V = B * sample_n, self.cfg.seq_length, self.cfg.tgt_vocab
+        # a slot's buffers of an earlier call are only reused when they have exactly this call's shapes (the short last
+        # batch of an epoch, another sample_n or want_logprobs would otherwise be written past their end)
+        if out is not None and (out["seq"].shape[0] != rows or (out.get("logp") is not None) != bool(want_logprobs)
+                                or (want_logprobs and out["logp"].shape[0] != rows)):
+            out = None
         if out is None:
             out = dict(seq=torch.empty(rows, L, dtype=torch.int64).pin_memory(),
                        logp=torch.empty(rows, L, V).pin_memory() if want_logprobs else None,
@@ -108,14 +123,33 @@ class BofiEngine:
         if att_len is not None:
             att_len = att_len.to(torch.int32).contiguous()
         with torch.cuda.device(self.device):
-            fn = self.lib.bofi_sample_host if sync else self.lib.bofi_sample_host_async
             if not sync:
                 assert att_feats.is_pinned() and out["seq"].is_pinned(), "asynchronous host path needs pinned buffers"
                 self._host_keep = (att_feats, att_len, out)
-            _lib.check(fn(
-                self.handle, self._stream(), _lib.MODE[mode], sample_n, int(output_logsoftmax), _ptr(att_feats), _ptr(att_len),
+            _lib.check(self.lib.bofi_sample_host_async_ex(
+                self.handle, self._stream(), _lib.MODE[mode], sample_n, int(output_logsoftmax), _ptr(att_feats), code, _ptr(att_len),
                 B, R, _ptr(out["seq"]), _ptr(out.get("logp")), _ptr(out["pnum"]), _ptr(out["plen"]), _ptr(out["psyn"])))
+            if sync:
+                torch.cuda.current_stream(self.device).synchronize()
         return out
+
+    def masks_to_len(self, att_masks):
+        """att_masks [B, R] on the device -> int32 valid-region counts, with the device-side prefix-mask check
+        (bofi_masks_to_len); `check_masks()` raises later, at a point where the caller synchronises anyway."""
+        m = att_masks.to(torch.float32).contiguous()
+        out = torch.empty(m.shape[0], dtype=torch.int32, device=m.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bofi_masks_to_len(self.handle, self._stream(), _ptr(m), m.shape[0], m.shape[1], _ptr(out)))
+        self._mask_keep = m
+        return out
+
+    def check_masks(self):
+        bad = C.c_int32(0)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bofi_check_masks(self.handle, self._stream(), C.byref(bad)))
+        if bad.value:
+            raise ValueError("att_masks is not a prefix mask (valid regions first, as dataloader.py:333-338 builds it): this library "
+                             "keeps only the per-image count of valid regions")
 
     def set_decode_stats(self, slot_entropy=None, slot_logp=None):
         self._stats_keep = (slot_entropy, slot_logp)

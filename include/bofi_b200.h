@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define BOFI_ABI_VERSION 1
+#define BOFI_ABI_VERSION 2
 
 enum {
   BOFI_OK = 0,
@@ -40,6 +40,9 @@ enum {
 
 enum { BOFI_PRECISION_FP32 = 0, BOFI_PRECISION_BF16 = 1 };
 enum { BOFI_MODE_NAIC = 0, BOFI_MODE_SAIC = 1 };
+/* element type of a region-feature buffer handed to the *_ex entry points (the loader's `att_feats`, dataloader.py:24-86):
+ * fp32 as the reference's loader yields it, or the 2-byte forms of the pinned feeder (boficap_b200/data). */
+enum { BOFI_FEAT_F32 = 0, BOFI_FEAT_BF16 = 1, BOFI_FEAT_F16 = 2 };
 
 /* Hyper-parameters the reference reads from `opt`
  * (AttModel.py:56-75, TransformerModel.py:1631-1640, :404-411).  tgt_vocab = vocab_size + 4. */
@@ -92,6 +95,20 @@ int64_t bofi_workspace_bytes(bofi_handle_t h, int32_t B, int32_t R, int32_t samp
 int bofi_encode(bofi_handle_t h, void* stream, const float* att_feats, const int32_t* att_len,
                 int32_t B, int32_t R, float* memory_out);
 
+/* The same with 2-byte features (feat_dtype = BOFI_FEAT_*; att_feats 16-byte aligned).  A bf16 engine reads bf16 features in
+ * place (the att_embed GEMM's TMA loads them from the caller's buffer, no conversion pass); every other combination costs
+ * one conversion kernel.  Halves the bytes of the input side (147 KB instead of 295 KB per 36-region image). */
+int bofi_encode_ex(bofi_handle_t h, void* stream, const void* att_feats, int32_t feat_dtype, const int32_t* att_len,
+                   int32_t B, int32_t R, float* memory_out);
+
+/* att_masks -> att_len for bofi_encode (the reduction `att_masks.sum(1)` of a PREFIX mask, dataloader.py:333-338):
+ *   att_masks dev f32 [B,R] (0 / non-zero), att_len dev i32 [B].
+ * The kernel also checks that every row really is a prefix mask (the reference's masked_fill accepts any mask, this
+ * library only counts); a violation raises a device-side flag that bofi_check_masks reads (and clears) -- *bad = 1 --
+ * at a point where the caller synchronises anyway.  Neither call is needed when the caller already has the counts. */
+int bofi_masks_to_len(bofi_handle_t h, void* stream, const float* att_masks, int32_t B, int32_t R, int32_t* att_len);
+int bofi_check_masks(bofi_handle_t h, void* stream, int32_t* bad);
+
 /* core_NAIC / core_SAIC + logit + log_softmax + greedy sample_next_word + tail padding
  * (TransformerModel.py:1823-1986, AttModel.py:203-210, :419-437, CaptionModel.py:383-390),
  * on the memory left in the workspace by the preceding bofi_encode.  Rows = B * sample_n.
@@ -136,6 +153,13 @@ int bofi_sample_host_async(bofi_handle_t h, void* stream, int32_t mode, int32_t 
                            const float* att_feats, const int32_t* att_len, int32_t B, int32_t R,
                            int64_t* seq, float* logprobs, int32_t* phrase_num, int32_t* phrase_length,
                            int64_t* phrase_syn);
+
+/* bofi_sample_host_async with 2-byte features in (pinned) host memory: half the H2D bytes of the fp32 form, which is what
+ * bounds the end-to-end rate once several GPUs share the host's PCIe / memory bandwidth. */
+int bofi_sample_host_async_ex(bofi_handle_t h, void* stream, int32_t mode, int32_t sample_n, int32_t output_logsoftmax,
+                              const void* att_feats, int32_t feat_dtype, const int32_t* att_len, int32_t B, int32_t R,
+                              int64_t* seq, float* logprobs, int32_t* phrase_num, int32_t* phrase_length,
+                              int64_t* phrase_syn);
 
 /* Counters of the last decode (synchronises `stream`). */
 int bofi_get_decode_info(bofi_handle_t h, void* stream, bofi_decode_info_t* out);
