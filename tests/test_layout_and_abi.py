@@ -97,7 +97,7 @@ def test_create_without_gpu_reports_cuda_error():
         pytest.skip("CUDA present")
     lib = _lib.load()
     cfg = BofiConfig()
-    c = _lib.BofiConfigC(abi_version=1, tgt_vocab=cfg.tgt_vocab, att_feat_size=2048, n_enc=6, n_dec=6, n_len=1, d_model=512,
+    c = _lib.BofiConfigC(abi_version=_lib.ABI_VERSION, tgt_vocab=cfg.tgt_vocab, att_feat_size=2048, n_enc=6, n_dec=6, n_len=1, d_model=512,
                          d_ff=2048, heads=8, seq_length=20, pad_idx=0, bos_idx=1, eos_idx=2, len_idx=3, precision=0)
     h = C.c_void_p()
     rc = lib.bofi_create(C.byref(c), 0, C.byref(h))
