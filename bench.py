@@ -26,7 +26,12 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 METRIC = "captions/sec/GPU greedy BoFi decode (uic_sd, 36x2048 regions)"
-CPU_SAMPLE_IMAGES = 64
+# roofline.traffic is NOT measured by this run (ncu cannot wrap a bench value): it is the DRAM read + write bytes of one
+# launch of the dominant kernel's largest shape from the committed ncu --set full capture named here
+TRAFFIC_CONSTANT = {"bytes": 135.1e6,
+                    "source": "constant from profiles/r01d_gemm_ncu_summary.txt: dram__bytes_read.sum + dram__bytes_write.sum of one "
+                              "gemm_tc2_kernel launch M=36864 N=2048 K=512 (39.9 MB + 95.2 MB; algorithmic 189 MB, most of the output "
+                              "stays in the 126 MB L2)"}
 
 
 def useful_flops_per_caption(R, S, V=9491, n_enc=6, n_dec=6, d=512, dff=2048, L=20, Lb=22):
@@ -101,23 +106,6 @@ def measured_peaks():
     return 1590.0, 1400.0, 6650.0, "fallback"
 
 
-def cpu_reference_run(steps, warmup, cfg, sd, R, mode, images=CPU_SAMPLE_IMAGES):
-    """The reference algorithm on host cores (oracle port), bounded sample of the workload."""
-    from boficap_b200 import synth
-    from oracle.bofi_oracle import BofiOracle, OracleConfig
-    torch.set_num_threads(os.cpu_count() or 1)
-    fc, att, _ = synth.synth_inputs(images, R, seed=1)
-    o = BofiOracle(sd, OracleConfig(**cfg.to_dict()))
-    kw = {"sample_method": "greedy", "beam_size": 1, "sample_n": 1, "train_mode": mode}
-    for _ in range(warmup):
-        o.sample(fc, att, None, kw)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        o.sample(fc, att, None, kw)
-    dt = time.perf_counter() - t0
-    return images * steps / dt, dt / steps, torch.get_num_threads(), o.last_steps
-
-
 def bench_xe(a, rank, local_rank, world):
     """Config 5 of BASELINE.json: uic_sd XE training step, `--batch` images x 5 captions per GPU (default 256), forward +
     LanguageModelCriterion_UIC + backward in the library, NCCL all-reduce of the flat gradient buffer, Adam on the flat
@@ -131,7 +119,7 @@ def bench_xe(a, rank, local_rank, world):
     from boficap_b200 import synth
     from boficap_b200.captioning import models
     from boficap_b200.layout import BofiConfig
-    from boficap_b200.parallel import allreduce_gradients
+    from boficap_b200.parallel import OverlappedGradReduce
     cfg = BofiConfig()
     B = 256 if a.batch == 1024 else a.batch
     R, spi = a.regions, 5
@@ -154,12 +142,14 @@ def bench_xe(a, rank, local_rank, world):
     args = (dev(fc), dev(att), dev(bt["labels"]), dev(masks), dev(bt["phrase_num"]), dev(bt["phrase_length"]), dev(bt["phrase_syn"]),
             dev(bt["extend_phrase_syn_seq"]), dev(bt["extend_phrase_seq"]), dev(bt["extend_phrase_seq_mask"]))
     eng = model._engine
+    # bucketed all-reduce of the flat gradient buffer, the decoder-side buckets underneath the encoder's backward pass
+    reducer = OverlappedGradReduce(model, buckets=a.buckets) if dist is not None else None
 
     def step():
         flat_g.zero_()
         losses = model.xe_step(*args)
-        if dist is not None:
-            allreduce_gradients(model)
+        if reducer is not None:
+            reducer.reduce()
         optim.step()
         eng.refresh_weights()
         return losses
@@ -206,7 +196,8 @@ def bench_xe(a, rank, local_rank, world):
                 "data": "synthetic",
                 "config": {"workload": "uic_sd XE training step (forward + criterion + backward + all-reduce + Adam), %d images x %d captions per GPU, "
                                        "%d regions, %s, dropout %s" % (B, spi, R, a.precision, "off" if a.no_dropout else "on (p=0.1, att_embed 0.5)"),
-                           "parallelism": "data-parallel replicas x%d, one NCCL all-reduce of the %.0f MB flat gradient buffer" % (world, flat_g.numel() * 4 / 1e6)},
+                           "parallelism": "data-parallel replicas x%d, NCCL all-reduce of the %.0f MB flat gradient buffer in %d + 1 buckets, the decoder-side "
+                                          "buckets overlapped with the encoder's backward pass" % (world, flat_g.numel() * 4 / 1e6, a.buckets)},
                 "loss_first": first, "loss_last": float(losses[0]), "gpu_launches": launches * a.steps, "clocks": clocks,
                 "roofline": {"bound": "tensor", "kernel": "gemm_tc2_kernel / gemm_tc_kernel (tcgen05), all %d launches of a step" % g["launches"],
                              "achieved": tf, "peak": sustained, "unit": "TFLOP/s", "frac": tf / sustained, "traffic": None,
@@ -217,6 +208,109 @@ def bench_xe(a, rank, local_rank, world):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def numa_bind(local_rank):
+    """Pin this process (and with it the first-touch placement of its pinned host buffers) to the CPUs of the NUMA node
+    the GPU hangs off.  Round 1: every rank allocated on node 0 and the 8-GPU end-to-end rate stopped at 181 GB/s of
+    aggregate H2D.  Returns a description for the JSON line (None when the topology is not exposed)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[local_rank]) if vis and vis.split(",")[local_rank].isdigit() else local_rank
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(phys)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return {"gpu_numa_node": node, "bound": False}
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"gpu_numa_node": node, "bound": False}
+        os.sched_setaffinity(0, cpus)
+        return {"gpu_numa_node": node, "bound": True, "cpus": len(cpus)}
+    except Exception as ex:           # no NVML / sysfs entry: leave the placement to the OS
+        return {"bound": False, "why": type(ex).__name__}
+
+
+def workload_config(a, world):
+    """The workload description shared by both arms (`--impl ours` and `--impl reference` time the same thing)."""
+    return {"workload": "uic_sd greedy BoFi decode (%s), batch %d/GPU, %d regions x 2048" % (a.mode, a.batch, a.regions),
+            "checkpoint": "synthetic seed 0, calibration " + a.calib, "global_batch": a.batch * world,
+            "regions": ("adaptive 10..%d, prefix masks" % a.regions) if a.adaptive else a.regions,
+            "parallelism": "image-sharded replicas x%d" % world,
+            "l2": "per-step input (%.0f MB/GPU as fp32) and activations exceed the 126 MB L2" % (a.batch * a.regions * 2048 * 4 / 1e6),
+            "logprobs": "skipped" if a.no_logprobs else "materialised [B,20,V] fp32"}
+
+
+def reference_arm(a, cfg, config):
+    """`--impl reference`: the reference's CPU implementation of the path (its PyTorch-fp32 restatement, oracle/bofi_oracle.py --
+    the reference itself needs /root/reference at run time and cannot travel to the GPU box) on ALL host cores, on the arm's
+    own workload: every step is one `_sample` of the full batch unless that would run for more than a few minutes, in
+    which case the step is a bounded sample of the batch (stated in `sample`)."""
+    from boficap_b200 import synth
+    from oracle.bofi_oracle import BofiOracle, OracleConfig
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synth.synth_state_dict(cfg, 0, a.calib)
+    o = BofiOracle(sd, OracleConfig(**cfg.to_dict()))
+    kw = {"sample_method": "greedy", "beam_size": 1, "sample_n": 1, "train_mode": a.mode}
+    images = a.batch if a.cpu_images <= 0 else min(a.batch, a.cpu_images)
+    fc, att, masks = synth.synth_inputs(images, a.regions, seed=1, adaptive=a.adaptive)
+    steps, warmup = max(1, a.steps), max(1, a.warmup)
+    t0 = time.perf_counter()
+    o.sample(fc, att, masks, kw)                                  # first warm-up step, also the size probe
+    probe = time.perf_counter() - t0
+    if probe * (steps + warmup) > a.cpu_budget and images > 64:     # bounded sample of the batch
+        images = max(64, int(images * a.cpu_budget / (probe * (steps + warmup))) // 8 * 8)
+        fc, att = fc[:images].contiguous(), att[:images].contiguous()
+        masks = masks[:images].contiguous() if masks is not None else None
+        o.sample(fc, att, masks, kw)
+    for _ in range(warmup - 1):
+        o.sample(fc, att, masks, kw)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.sample(fc, att, masks, kw)
+    dt = time.perf_counter() - t0
+    cps = images * steps / dt
+    sample = ("%d of the %d images of a step, %d steps + %d warm-up; PyTorch fp32 restatement of the reference formulation "
+              "(all 22 bounding rows per step, K/V re-projected per call), %d host threads, S=%d"
+              % (images, a.batch, steps, warmup, torch.get_num_threads(), o.last_steps))
+    return {"impl": "reference", "metric": METRIC, "value": cps, "unit": "captions/s", "n_gpus": a.gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config, "bounding_steps": o.last_steps,
+            "cpu_baseline": {"value": cps, "unit": "captions/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": cps, "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def gpu_eager_bar(cfg, sd, att, masks, mode, iters=3):
+    """The GPU bar SURVEY.md section 8(d) asks for: the reference algorithm as eager PyTorch on the SAME B200 (the oracle port on
+    `cuda`: library kernels, vectorised box bookkeeping -- faster than the reference's own per-row python loops), fp32
+    and bf16 autocast, same batch, device-resident inputs."""
+    from oracle.bofi_oracle import BofiOracle, OracleConfig
+    o = BofiOracle(sd, OracleConfig(**cfg.to_dict()), device="cuda")
+    kw = {"sample_method": "greedy", "beam_size": 1, "sample_n": 1, "train_mode": mode}
+    out = {}
+    for name, ctx in (("fp32", torch.autocast("cuda", enabled=False)), ("bf16_autocast", torch.autocast("cuda", dtype=torch.bfloat16))):
+        with ctx:
+            o.sample(None, att, masks, kw)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(iters):
+                o.sample(None, att, masks, kw)
+            torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / iters
+        out[name] = {"value": att.shape[0] / dt, "unit": "captions/s", "ms_per_step": dt * 1e3, "bounding_steps": o.last_steps}
+    out["what"] = "oracle/bofi_oracle.py on cuda:0 (eager PyTorch, cuBLAS / ATen kernels), batch %d, %d calls each" % (att.shape[0], iters)
+    del o
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -230,14 +324,21 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--mode", default="NAIC", choices=["NAIC", "SAIC"])
     ap.add_argument("--adaptive", action="store_true", help="10..R valid regions per image with prefix masks (config 3)")
-    ap.add_argument("--calib", default="s_real")
+    ap.add_argument("--calib", default=None, help="synthetic checkpoint calibration (default: s_real for NAIC, s_cap for SAIC)")
     ap.add_argument("--no-logprobs", action="store_true", help="skip materialising the [B,20,V] log-prob tensor")
-    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--cpu-images", type=int, default=0, help="reference arm: images per step (0 = the full batch, bounded by --cpu-budget)")
+    ap.add_argument("--cpu-budget", type=float, default=150.0, help="reference arm: seconds of CPU work the whole run may take")
     ap.add_argument("--workload", default="decode", choices=["decode", "xe"],
                     help="decode = BASELINE.json's headline metric; xe = XE training step (config 5: 256 images x 5 captions per GPU)")
     ap.add_argument("--no-dropout", action="store_true", help="xe workload: eval() arithmetic (dropout off)")
     ap.add_argument("--depth", type=int, default=3, help="batches in flight (engine handles x streams, boficap_b200/pipeline.py)")
+    ap.add_argument("--host-dtype", default="bf16", choices=["bf16", "fp16", "fp32"], help="element type of the pinned host features of the e2e leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary legs (fp32-host e2e, drop-in class, GPU-eager bar, CPU baseline)")
+    ap.add_argument("--buckets", type=int, default=4, help="xe workload: gradient all-reduce buckets overlapped with the backward pass")
     a = ap.parse_args()
+    if a.calib is None:
+        # SAIC on the NAIC-only calibration aborts at step 1 ("phrase nan!"): its bench needs the joint calibration
+        a.calib = "s_cap" if (a.mode == "SAIC" and a.workload == "decode") else "s_real"
 
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -248,47 +349,40 @@ def main():
     from boficap_b200 import synth
     from boficap_b200.layout import BofiConfig
     cfg = BofiConfig()
-    workload = "uic_sd greedy BoFi decode (%s), batch %d/GPU, %d regions x 2048, %s" % (a.mode, a.batch, a.regions, a.precision)
-    config = {"workload": workload, "checkpoint": "synthetic seed 0, calibration " + a.calib, "global_batch": a.batch * world,
-              "regions": a.regions, "parallelism": "image-sharded replicas x%d" % world,
-              "l2": "per-step input (%.0f MB/GPU) and activations exceed the 126 MB L2" % (a.batch * a.regions * 2048 * 4 / 1e6),
-              "logprobs": "skipped" if a.no_logprobs else "materialised [B,20,V] fp32"}
+    config = workload_config(a, world)
 
     if a.impl == "reference":
         if rank != 0:
             return 0
-        sd = synth.synth_state_dict(cfg, 0, a.calib)
-        cps, sec, cores, S = cpu_reference_run(max(1, a.steps), max(1, a.warmup), cfg, sd, a.regions, a.mode)
-        sample = "%d images/step x %d steps, oracle port of the reference formulation, fp32, S=%d" % (CPU_SAMPLE_IMAGES, a.steps, S)
-        line = {"impl": "reference", "metric": METRIC, "value": cps, "unit": "captions/s", "n_gpus": a.gpus, "steps": a.steps,
-                "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": cps, "unit": "captions/s", "cores": cores, "kind": "port", "sample": sample},
-                "e2e": {"value": cps, "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        print(json.dumps(reference_arm(a, cfg, config)))
         return 0
 
     # ------------------------------------------------------------------ our arm
     assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback"
+    all_cpus = os.sched_getaffinity(0)
+    numa = numa_bind(local_rank)
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from boficap_b200.parallel import gather_captions_packed
     from boficap_b200.pipeline import BofiPipeline
 
     sd = synth.synth_state_dict(cfg, 0, a.calib)
     pipe = BofiPipeline(cfg, sd, local_rank, a.precision, depth=max(1, a.depth))
     eng = pipe.engines[0]
-    config["in_flight"] = "%d batches (one engine handle + stream each, round robin)" % pipe.depth
     B, R = a.batch, a.regions
     fc, att_host, masks = synth.synth_inputs(B, R, seed=1 + rank, adaptive=a.adaptive)
     att_host = att_host.pin_memory()
-    att = att_host.cuda(non_blocking=True)
+    # features in the feeder's format (boficap_b200/data: 2-byte elements, pinned): half the H2D bytes of the loader's fp32,
+    # and a bf16 engine's att_embed GEMM reads them in place (no conversion pass on the device)
+    host_dt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[a.host_dtype]
+    att_host_lp = att_host.to(host_dt).pin_memory() if host_dt != torch.float32 else att_host
+    att = att_host_lp.cuda(non_blocking=True)
     len_host = masks.long().sum(1).int().pin_memory() if masks is not None else None
     att_len = len_host.cuda() if len_host is not None else None
-    if a.adaptive:
-        config["regions"] = "adaptive 10..%d (mean %.1f), prefix masks" % (R, float(len_host.float().mean()))
+    notes = {"feature_dtype": a.host_dtype}
     want_lp = not a.no_logprobs
     main = torch.cuda.current_stream()
 
@@ -308,31 +402,61 @@ def main():
     torch.cuda.synchronize()
     tokens = out[3].sum(1)
     seed_shift = 0
-    while int(tokens.sum()) == 0 and seed_shift < 32:      # tiny batches: draw other images until one yields a phrase
+    while int(tokens.sum()) == 0 and seed_shift < 32 and a.mode == "NAIC":      # tiny batches: draw other images until one yields a phrase
         seed_shift += 1
         att_host.copy_(synth.synth_inputs(B, R, seed=1 + rank + 1000 * seed_shift, adaptive=False)[1])
-        att.copy_(att_host)
+        att_host_lp.copy_(att_host)
+        att.copy_(att_host_lp)
         out = step()
         torch.cuda.synchronize()
         tokens = out[3].sum(1)
     if seed_shift:
-        config["input_seed_shift"] = seed_shift
-    if int(tokens[-1]) == 0:
+        notes["input_seed_shift"] = seed_shift
+    if a.mode == "NAIC" and int(tokens[-1]) == 0:
         j = int((tokens > 0).nonzero()[-1])
         att_host[[j, B - 1]] = att_host[[B - 1, j]]
-        att.copy_(att_host)
+        att_host_lp.copy_(att_host)
+        att.copy_(att_host_lp)
         if len_host is not None:
             len_host[[j, B - 1]] = len_host[[B - 1, j]]
             att_len.copy_(len_host)
-        config["last_image"] = "swapped with image %d so that the fill window is non-empty" % j
+        notes["last_image"] = "swapped with image %d so that the fill window is non-empty" % j
     out = step()
     torch.cuda.synchronize()
     ref_seq = out[0].clone()
+    info0 = eng.decode_info()
+    if info0["nan_batch"]:
+        # a NaN batch decodes nothing (the reference returns NaN log-probs / aborts SAIC at step 1): no captions/s to report
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": None, "unit": "captions/s", "n_gpus": world, "config": config,
+                              "invalid": "nan_batch: checkpoint calibration %r yields no caption in %s mode on this batch "
+                                         "(use --calib s_cap for SAIC)" % (a.calib, a.mode), "decode_info": info0}))
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 1
+
+    gathered = [None]
+
+    def finish_ticket(t, st):
+        """Final caption gather of the N-GPU path (the one collective north_star allows), inside the timed region."""
+        if dist is None:
+            return
+        with torch.cuda.stream(st):
+            o = t.out
+            seq, pnum, plen, psyn = (o[0], o[2], o[3], o[4]) if isinstance(o, tuple) else (o["seq"], o["pnum"], o["plen"], o["psyn"])
+            if not seq.is_cuda:
+                return
+            gathered[0] = gather_captions_packed(seq, pnum, plen, psyn)
 
     def run_device(n):
         """n whole decodes, round robin over the in-flight slots; returns the tickets."""
         pipe.fork_from(main)
-        ts = [pipe.submit_device(att, att_len, a.mode, 1, 1, want_lp, reuse_outputs=True) for _ in range(n)]
+        ts = []
+        for _ in range(n):
+            t = pipe.submit_device(att, att_len, a.mode, 1, 1, want_lp, reuse_outputs=True)
+            finish_ticket(t, pipe.streams[t.slot])
+            ts.append(t)
         pipe.join_into(main)
         return ts
 
@@ -359,37 +483,85 @@ def main():
     del tickets
 
     # ---- e2e: the host-buffer entry point (H2D of the features and D2H of captions + boxes inside the timed region),
-    # pinned host input, `depth` batches in flight through bofi_sample_host_async
-    def run_host(n):
+    # pinned host input, `depth` batches in flight through bofi_sample_host_async_ex
+    def run_host(n, feats):
         pipe.fork_from(main)
-        ts = [pipe.submit_host(att_host, len_host, a.mode, 1, 1) for _ in range(n)]
+        ts = [pipe.submit_host(feats, len_host, a.mode, 1, 1) for _ in range(n)]
         pipe.join_into(main)
         return ts
 
-    for t in run_host(2 * pipe.depth):
-        host_out = t.wait()
-    barrier()
+    def time_host(feats):
+        for t in run_host(2 * pipe.depth, feats):
+            host_out = t.wait()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(main)
+        tickets = run_host(a.steps, feats)
+        e1.record(main)
+        for t in tickets:
+            host_out = t.wait()                                  # results are in host memory here
+        if dist is not None:                                     # caption gather of the N-GPU path (host results -> every rank)
+            packed = torch.cat([host_out["seq"].int(), host_out["pnum"].int()[:, None], host_out["plen"], host_out["psyn"].int()], 1).cuda()
+            allc = torch.empty((world,) + tuple(packed.shape), dtype=packed.dtype, device="cuda")
+            dist.all_gather_into_tensor(allc, packed)
+            torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        barrier()
+        return max(e0.elapsed_time(e1), wall), host_out          # device span vs host wall clock until the last result landed
+
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record(main)
-    tickets = run_host(a.steps)
-    e1.record(main)
-    for t in tickets:
-        host_out = t.wait()                                  # results are in host memory here
-    wall_e2e = (time.perf_counter() - t0) * 1e3
-    barrier()
-    ms_e2e = max(e0.elapsed_time(e1), wall_e2e)              # device span vs host wall clock until the last result landed
+    ms_e2e, host_out = time_host(att_host_lp)
     clocks = sampler.stop() if rank == 0 else None
     assert torch.equal(host_out["seq"], ref_seq.cpu()), "host-path captions differ from the device path"
-    h2d = att_host.numel() * 4 + (len_host.numel() * 4 if len_host is not None else 0)
+    h2d = att_host_lp.numel() * att_host_lp.element_size() + (len_host.numel() * 4 if len_host is not None else 0)
     d2h = sum(host_out[k].numel() * host_out[k].element_size() for k in ("seq", "pnum", "plen", "psyn"))
+    ms_e2e32 = None
+    if not a.no_extras and host_dt != torch.float32:
+        ms_e2e32, host_out32 = time_host(att_host)
+        notes["fp32_host_token_agreement"] = float((host_out32["seq"] == ref_seq.cpu()).float().mean())   # 1.0 for bf16 features
+
+    # ---- the reference-facing class: model(fc, att, masks, opt, mode='sample') on pinned host tensors, .cuda() and the
+    # read-back of the captions inside the timed region (eval_utils.py:431-445 does exactly this per batch), one batch in flight
+    ms_dropin = None
+    if not a.no_extras and world == 1:
+        from boficap_b200.captioning import models
+        infos = synth.make_infos(cfg)
+        mopt = infos["opt"]
+        mopt.vocab = infos["vocab"]
+        mopt.bofi_precision = a.precision
+        model = models.setup(mopt)
+        model.load_state_dict(sd)
+        model = model.cuda().eval()
+        fc_host = fc.pin_memory()
+        kw = {"sample_method": "greedy", "beam_size": 1, "sample_n": 1, "train_mode": a.mode, "bofi_logprobs": want_lp}
+        mk_host = masks.pin_memory() if masks is not None else None
+
+        def dropin_step():
+            f, x = fc_host.cuda(non_blocking=True), att_host.cuda(non_blocking=True)
+            m = mk_host.cuda(non_blocking=True) if mk_host is not None else None
+            r = model(f, x, m, opt=kw, mode="sample")
+            return r[0].cpu()
+
+        for _ in range(3):
+            seq_d = dropin_step()
+        notes["dropin_token_agreement"] = float((seq_d == ref_seq.cpu()).float().mean())
+        nd = max(3, a.steps // 2)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(nd):
+            dropin_step()
+        torch.cuda.synchronize()
+        ms_dropin = (time.perf_counter() - t0) * 1e3 / nd
+        del model
+        torch.cuda.empty_cache()
 
     if dist is not None:
-        t = torch.tensor([ms, ms_e2e], device="cuda")
+        t = torch.tensor([ms, ms_e2e, ms_e2e32 or 0.0], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = t.tolist()
+        ms, ms_e2e, m32 = t.tolist()
+        ms_e2e32 = m32 if ms_e2e32 is not None else None
 
     # ---- per-kernel-class profile of one more step (CUDA events around every launch of the library)
     eng.set_profiling(True)
@@ -405,25 +577,24 @@ def main():
         return 0
 
     S = info["bounding_steps"]
+    mean_regions = float(len_host.float().mean()) if len_host is not None else float(R)
     value = world * B * a.steps / (ms / 1e3)
     e2e_value = world * B * a.steps / (ms_e2e / 1e3)
     burst, sustained, hbm, how = measured_peaks()
     g = prof["gemm_tcgen05"] if a.precision == "bf16" else prof["gemm_ffma"]
     gemm_tflops = g["flops"] / (g["ms"] / 1e3) / 1e12 if g["ms"] > 0 else 0.0
-    peak = sustained if a.precision == "bf16" else 75.0
+    # the per-launch durations come from one profiled step (CUDA events around every launch, kernels run one at a time at
+    # boost clocks): the burst figure is the matching denominator; the sustained one is reported beside it
+    peak = burst if a.precision == "bf16" else 75.0
     total_ms = sum(v["ms"] for v in prof.values())
     if a.precision == "bf16" and g["ms"] > 0:
-        # dominant kernel = gemm_tc_kernel (tcgen05): algorithmic flops = sum of 2*M*N*K over its launches in one
+        # dominant kernel = the tcgen05 GEMM: algorithmic flops = sum of 2*M*N*K over its launches in one
         # step, duration = sum of the CUDA-event durations around each launch (library-side, launching stream)
         achieved, kname = gemm_tflops, "gemm_tc2_kernel / gemm_tc_kernel (tcgen05), all %d launches of a step" % g["launches"]
-        # ncu --set full capture of the FFN1 shape (profiles/r01d_gemm_ncu_summary.txt): dram read + write per launch
-        traffic = 135.1e6
+        traffic = TRAFFIC_CONSTANT["bytes"]
         dom = {"launches_per_step": g["launches"], "us_per_launch": g["ms"] / g["launches"] * 1e3,
                "gflop_per_launch": g["flops"] / g["launches"] / 1e9, "share_of_step": g["ms"] / total_ms,
-               "traffic_note": "traffic = ncu dram bytes of one M=36864 N=2048 K=512 launch of gemm_tc2_kernel (algorithmic 189 MB; most "
-                               "of the output stays in L2).  The same capture shows 605 MB of L2->SM fills per launch (906 MB with 1-CTA "
-                               "tiles); tools/gemm_stalls.py: the MMA-issuing thread waits for operands 40-55 % of the time, for the "
-                               "epilogue 1-5 % (profiles/r01d_gemm_stalls.txt)"}
+               "traffic_source": TRAFFIC_CONSTANT["source"]}
         if top and top["ms"] > 0:
             dom["slowest_shape"] = {"M": top["M"], "N": top["N"], "K": top["K"], "launches": top["launches"],
                                     "us_per_launch": top["ms"] / top["launches"] * 1e3,
@@ -431,33 +602,59 @@ def main():
     else:
         achieved, kname, traffic = gemm_tflops, "gemm_simt_kernel (FFMA), all launches", None
         dom = {"launches_per_step": g["launches"], "share_of_step": g["ms"] / total_ms if total_ms else None}
+    useful = useful_flops_per_caption(mean_regions, S)
     roofline = {"bound": "tensor", "kernel": kname,
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                "peak_source": "%s bf16 sustained (kernel timed inside a long step)" % how if a.precision == "bf16" else "nominal fp32 FFMA",
+                "peak_source": "%s bf16 burst (per-launch events of one profiled step)" % how if a.precision == "bf16" else "nominal fp32 FFMA",
+                "frac_of_sustained": achieved / sustained if a.precision == "bf16" else None,
                 "traffic": traffic, "dominant": dom,
                 "all_gemm_launches": {"launches_per_step": g["launches"], "ms_per_step": g["ms"], "tflops": gemm_tflops,
                                       "share_of_step": g["ms"] / total_ms if total_ms else None},
-                "whole_path_useful_tflops": value / world * useful_flops_per_caption(R, S) / 1e12,
-                "whole_path_frac_of_burst": value / world * useful_flops_per_caption(R, S) / 1e12 / burst,
+                "whole_path_useful_tflops": value / world * useful / 1e12,
+                "whole_path_frac_of_burst": value / world * useful / 1e12 / burst,
                 "classes": {k: {"launches": v["launches"], "ms": round(v["ms"], 4),
                                 "tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 2) if v["ms"] > 0 else 0.0,
                                 "gbs": round(v["bytes"] / (v["ms"] / 1e3) / 1e9, 1) if v["ms"] > 0 else 0.0}
                             for k, v in prof.items()}}
 
-    cpu = None
-    if world == 1:          # reported on rank 0 at N = 1 only (the other ranks would be spinning in the barrier meanwhile)
-        cps, sec, cores, Scpu = cpu_reference_run(a.cpu_steps, 1, cfg, sd, R, a.mode)
-        cpu = {"value": cps, "unit": "captions/s", "cores": cores, "kind": "port",
-               "sample": "%d images x %d calls of the oracle port (reference formulation, fp32), S=%d" % (CPU_SAMPLE_IMAGES, a.cpu_steps, Scpu)}
+    cpu = eager = None
+    if world == 1 and not a.no_extras:
+        # the GPU bar: the same algorithm as eager PyTorch on this B200
+        try:
+            eager = gpu_eager_bar(cfg, sd, att, masks.cuda() if masks is not None else None, a.mode)
+        except Exception as ex:                 # e.g. out of memory on a shared box: reported, not fatal
+            eager = {"unavailable": "%s: %s" % (type(ex).__name__, str(ex)[:200])}
+        # the CPU baseline in a fresh process (this one is pinned to one NUMA node and holds the GPU): all host cores
+        os.sched_setaffinity(0, all_cpus)
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1", "--batch", str(B),
+               "--regions", str(R), "--mode", a.mode, "--calib", a.calib, "--cpu-images", "512"] + (["--adaptive"] if a.adaptive else [])
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+            cpu = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
+        except Exception as ex:
+            cpu = {"unavailable": "%s: %s" % (type(ex).__name__, str(ex)[:200])}
 
+    e2e = {"value": e2e_value, "unit": "captions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "ms_per_step": ms_e2e / a.steps, "host_feature_dtype": a.host_dtype,
+           "api": "bofi_sample_host_async_ex, pinned host buffers (%s features), %d batches in flight%s"
+                  % (a.host_dtype, pipe.depth, ", caption all_gather inside the timed region" if world > 1 else "")}
     line = {"metric": METRIC, "value": value, "unit": "captions/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": a.precision, "data": "synthetic", "config": config,
-            "e2e": {"value": e2e_value, "unit": "captions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / a.steps,
-                    "api": "bofi_sample_host_async, pinned host buffers, %d batches in flight" % pipe.depth},
-            "gpu_launches": launches_per_step * a.steps, "bounding_steps": S, "fill_width": info["fill_width"],
-            "nan_batch": info["nan_batch"], "mean_caption_tokens": float(out[3].sum(1).float().mean()), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+            "in_flight": "%d batches (one engine handle + stream each, round robin)%s"
+                         % (pipe.depth, "; caption all_gather (244 B/image) after every batch, inside the timed region" if world > 1 else ""),
+            "e2e": e2e,
+            "e2e_fp32_host": None if ms_e2e32 is None else {
+                "value": world * B * a.steps / (ms_e2e32 / 1e3), "unit": "captions/s", "ms_per_step": ms_e2e32 / a.steps,
+                "h2d_bytes_per_step": att_host.numel() * 4 + (len_host.numel() * 4 if len_host is not None else 0)},
+            "e2e_dropin": None if ms_dropin is None else {
+                "value": B / (ms_dropin / 1e3), "unit": "captions/s", "ms_per_step": ms_dropin,
+                "api": "model(fc, att, masks, opt, mode='sample') of boficap_b200.captioning.models on pinned fp32 host tensors: "
+                       ".cuda() + _sample + seq.cpu() per step, one batch in flight"},
+            "numa": numa, "notes": notes, "mean_regions": mean_regions, "gpu_launches": launches_per_step * a.steps, "bounding_steps": S, "fill_width": info["fill_width"],
+            "nan_batch": info["nan_batch"], "mean_caption_tokens": float(out[3].sum(1).float().mean()), "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "gpu_eager": eager}
     print(json.dumps(line))
     if dist is not None:
         dist.barrier()

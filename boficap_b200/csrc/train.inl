@@ -100,6 +100,7 @@ struct TrainState {
   // FFN hidden, positional encoding and head hidden; p_att = opt.drop_prob_lm after att_embed's ReLU.  Sites are numbered
   // in forward order from 0 every step; key(site) = drop_hash(seed, site); the backward pass reuses the keys.
   float p_sub = 0.f, p_att = 0.f;
+  cudaEvent_t grad_event = nullptr;   // bofi_train_set_grad_event: recorded once every gradient outside the encoder is final
   uint32_t seed = 0, site = 0;
   Drop d_att_embed;
   Drop next_drop(float p) {
@@ -800,6 +801,10 @@ static int train_backward_impl(bofi_engine* e, cudaStream_t s, TrainState* ts, T
     }
     CU_TRY(cudaGetLastError());
   }
+  // Every gradient of the decoders, embeddings, generator and bounding head (flat entries from "model.decoder..." on) is
+  // final here; what follows only touches the encoder / att_embed entries at the front of the flat buffer.  A data-parallel
+  // caller starts the all-reduce of the back part on a side stream now, under the encoder's backward pass.
+  if (ts->grad_event) CU_TRY(cudaEventRecord(ts->grad_event, s));
   // encoder: final LayerNorm, layers, att_embed
   RC_TRY((ln_bwd<float, T>(e, s, ts, e->enc_norm, ts->enc_x_final, dmem, nullptr, dx, dxT, M)));
   const int* len_dev = ts->att_len;

@@ -209,4 +209,10 @@ extern "C" int bofi_train_set_dropout(bofi_handle_t e, float p, float p_att_embe
   return BOFI_OK;
 }
 
+extern "C" int bofi_train_set_grad_event(bofi_handle_t e, void* event) {
+  if (!e) return fail(BOFI_ERR_INVALID, "null handle");
+  train_state(e)->grad_event = (cudaEvent_t)event;
+  return BOFI_OK;
+}
+
 extern "C" int bofi_train_launches(bofi_handle_t e) { return e ? e->launches : -1; }

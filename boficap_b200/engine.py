@@ -268,6 +268,11 @@ class BofiEngine:
     def train_set_dropout(self, p, p_att_embed, seed):
         _lib.check(self.lib.bofi_train_set_dropout(self.handle, float(p), float(p_att_embed), int(seed) & 0xFFFFFFFF))
 
+    def train_set_grad_event(self, event):
+        """event: torch.cuda.Event (recorded once so that its handle exists) or None; see bofi_train_set_grad_event."""
+        self._grad_event_keep = event
+        _lib.check(self.lib.bofi_train_set_grad_event(self.handle, C.c_void_p(event.cuda_event) if event is not None else None))
+
     def train_launches(self):
         return int(self.lib.bofi_train_launches(self.handle))
 

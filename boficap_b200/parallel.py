@@ -40,6 +40,19 @@ def gather_captions(local, n_total, group=None):
     return tuple(out)
 
 
+def gather_captions_packed(seq, phrase_num, phrase_length, phrase_syn, group=None):
+    """The final caption gather as ONE collective for equal shards (bench.py, weak scaling): tokens and boxes of a shard
+    packed into one int32 row per image ([L | 1 | L | L] = 244 B at L = 20), all_gather_into_tensor, unpacked views.
+    Returns (seq i64 [W*rows, L], phrase_num i32, phrase_length i32, phrase_syn i64) of the whole job on every rank."""
+    L = seq.shape[1]
+    packed = torch.cat([seq.to(torch.int32), phrase_num.to(torch.int32)[:, None], phrase_length.to(torch.int32),
+                        phrase_syn.to(torch.int32)], 1).contiguous()
+    world = dist.get_world_size(group)
+    out = torch.empty((world * packed.shape[0], packed.shape[1]), dtype=torch.int32, device=packed.device)
+    dist.all_gather_into_tensor(out, packed, group=group)
+    return out[:, :L].long(), out[:, L], out[:, L + 1:2 * L + 1], out[:, 2 * L + 1:].long()
+
+
 def sample_sharded(decode_fn, att_feats, att_masks=None, group=None):
     """Every rank holds the full (host) batch description, decodes its own shard, gathers all captions."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -48,6 +61,43 @@ def sample_sharded(decode_fn, att_feats, att_masks=None, group=None):
     if local is None:
         raise ValueError("a rank received an empty shard (batch smaller than world size)")
     return gather_captions(local, att_feats.shape[0], group)
+
+
+class OverlappedGradReduce:
+    """Data-parallel XE training with the gradient all-reduce overlapped with the backward pass.  The flat gradient buffer
+    is cut where the library's backward pass finishes first: everything from the decoders on (embeddings, generator, bounding
+    head, the memory K/V projections) is final before the encoder's backward pass starts (bofi_train_set_grad_event), so
+    that part -- `buckets` NCCL calls so that the first bytes move early -- is reduced on a side stream underneath it; the
+    encoder / att_embed part follows on the training stream.  `finish()` joins the side stream."""
+
+    def __init__(self, model, group=None, buckets=4):
+        self.model, self.group = model, group
+        eng = model._engine
+        self.flat = model.flat_grads()
+        self.cut = eng.param_layout()["model.decoder.layers.0.self_attn.linears.0.weight"][0]
+        n_back = self.flat.numel() - self.cut
+        step = -(-n_back // max(1, buckets))
+        self.back = [self.flat[self.cut + i:min(self.cut + i + step, self.flat.numel())] for i in range(0, n_back, step)]
+        self.front = self.flat[:self.cut]
+        self.side = torch.cuda.Stream(self.flat.device)
+        self.event = torch.cuda.Event()
+        self.event.record()                      # creates the handle the library records into
+        eng.train_set_grad_event(self.event)
+
+    def reduce(self):
+        """Call right after the (asynchronous) backward pass has been enqueued on the current stream."""
+        main = torch.cuda.current_stream(self.flat.device)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self.event)     # recorded by the library inside the backward pass that was just enqueued
+            for b in self.back:
+                dist.all_reduce(b, op=dist.ReduceOp.AVG, group=self.group)
+            done = torch.cuda.Event()
+            done.record(self.side)
+        dist.all_reduce(self.front, op=dist.ReduceOp.AVG, group=self.group)
+        main.wait_event(done)
+
+    def close(self):
+        self.model._engine.train_set_grad_event(None)
 
 
 def allreduce_gradients(model, group=None, average=True):

@@ -177,3 +177,56 @@ def synth_xe_batch(B, seq_per_img=5, seq_length=16, seed=3, vocab_size=9487, len
     return dict(labels=t(labels, L + 2), phrase_num=t(pnum), phrase_length=t(plen, L + 2), phrase_syn=t(psyn, L + 2),
                 extend_phrase_syn_seq=t(ext_syn, L + 2), extend_phrase_seq=t(ext_seq, L),
                 extend_phrase_seq_mask=t(ext_mask, L * L))
+
+
+def trained_like_state_dict(cfg=None, seed=0, images=64, regions=36, max_steps=1500, lr=5e-4, target_word_nll=0.05,
+                            precision="bf16", device=0, log=None):
+    """A checkpoint whose argmax margins look like a TRAINED model's (no trained weights ship with the reference, and the
+    Xavier-initialised synthetic checkpoints decide most tokens by margins of ~1e-2, which says little about bf16).
+
+    Recipe (needs a CUDA device; deterministic up to the fp32 atomics of the word-embedding gradient): start from
+    `synth_state_dict(cfg, seed)`, and run the library's own fused XE step (`TransformerModel.xe_step`, eval() arithmetic:
+    dropout off) with Adam(lr, betas=(0.9, 0.98), eps=1e-9, 20 warm-up steps) on ONE fixed synthetic batch --
+    `synth_inputs(images, regions, seed + 101)` with one caption per image from `synth_xe_batch(images, 1, seed + 103)`,
+    so that every image has a single caption to memorise -- until the mean word NLL of both decoder passes is below
+    `target_word_nll` (or `max_steps`).  Returns (state_dict on the CPU, info) where info holds the batch, the step count
+    and the loss curve; the weights are NOT committed, only this recipe."""
+    from .captioning import models
+    cfg = cfg or BofiConfig()
+    infos = make_infos(cfg)
+    opt = infos["opt"]
+    opt.vocab = infos["vocab"]
+    opt.bofi_precision = precision
+    model = models.setup(opt)
+    model.load_state_dict(synth_state_dict(cfg, seed, None))
+    dev = torch.device("cuda", device)
+    model = model.to(dev).eval()
+    model.train_bind(dev)
+    flat_w, flat_g = model.flat_params(), model.flat_grads()
+    flat_p = torch.nn.Parameter(flat_w)
+    flat_p.grad = flat_g
+    optim = torch.optim.Adam([flat_p], lr=lr, betas=(0.9, 0.98), eps=1e-9)
+    fc, att, masks = synth_inputs(images, regions, seed=seed + 101)
+    bt = synth_xe_batch(images, seq_per_img=1, seed=seed + 103, vocab_size=cfg.vocab_size)
+    d = lambda t: t.to(dev) if t is not None else None
+    args = (d(fc), d(att), d(bt["labels"]), d(masks), d(bt["phrase_num"]), d(bt["phrase_length"]), d(bt["phrase_syn"]),
+            d(bt["extend_phrase_syn_seq"]), d(bt["extend_phrase_seq"]), d(bt["extend_phrase_seq_mask"]))
+    curve, steps = [], 0
+    for it in range(max_steps):
+        for g in optim.param_groups:
+            g["lr"] = lr * min(1.0, (it + 1) / 20.0)
+        flat_g.zero_()
+        losses = model.xe_step(*args)
+        optim.step()
+        model._engine.refresh_weights()
+        steps = it + 1
+        if it % 25 == 0 or it == max_steps - 1:
+            l = [float(v) for v in losses.cpu()]
+            curve.append((it, l))
+            if log:
+                log("trained-like step %d: total %.3f SA(len %.3f word %.3f syn %.3f) NA(len %.3f word %.3f syn %.3f)" % ((it,) + tuple(l)))
+            if max(l[2], l[5]) < target_word_nll and max(l[1], l[3], l[4], l[6]) < 4 * target_word_nll:
+                break
+    sd = {k: v.detach().float().cpu().clone() for k, v in model.state_dict().items()}
+    model._engine.close()
+    return sd, dict(att=att, masks=masks, batch=bt, steps=steps, curve=curve)

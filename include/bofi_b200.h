@@ -227,6 +227,12 @@ int bofi_train_step_xe(bofi_handle_t h, void* stream, const float* att_feats, co
  * regenerates them, and oracle/bofi_oracle.py:DropSim reproduces them bit for bit.  The positional-encoding mask of
  * the bounding input is drawn once per caption and shared by its bounding passes (the reference redraws it per pass). */
 int bofi_train_set_dropout(bofi_handle_t h, float p, float p_att_embed, uint32_t seed);
+/* Gradient all-reduce overlap (tools/train.py:99-101 runs the reference under nn.DataParallel; here: one process per GPU).
+ * `event` (a cudaEvent_t, NULL switches it off) is recorded on the training stream inside every following backward pass at
+ * the point where all gradients EXCEPT those of att_embed and model.encoder.* -- the flat entries before
+ * bofi_param_offset("model.decoder.layers.0.self_attn.linears.0.weight") -- are final: the caller waits for it on a side
+ * stream and reduces that part of the gradient buffer while the encoder's backward pass still runs. */
+int bofi_train_set_grad_event(bofi_handle_t h, void* event);
 /* Kernels enqueued by the last training call. */
 int bofi_train_launches(bofi_handle_t h);
 

@@ -60,8 +60,10 @@ class OracleConfig:
 
 
 class BofiOracle:
-    def __init__(self, state_dict, cfg=None, record=False):
-        self.sd = {k: v.detach().float() for k, v in state_dict.items()}
+    def __init__(self, state_dict, cfg=None, record=False, device="cpu"):
+        # device="cuda": the same eager PyTorch restatement on the GPU (bench.py's `gpu_eager` bar); tests use the CPU
+        self.device = torch.device(device)
+        self.sd = {k: v.detach().float().to(self.device) for k, v in state_dict.items()}
         self.cfg = cfg or OracleConfig()
         self.record = record
         self.trace = {}
@@ -320,6 +322,10 @@ class BofiOracle:
     # ---- A13: the `_sample` entry ---------------------------------------------------------
     @torch.no_grad()
     def sample(self, fc_feats, att_feats, att_masks=None, opt=None):
+        with torch.device(self.device):          # index / mask tensors are created on the oracle's device
+            return self._sample(fc_feats, att_feats, att_masks, opt)
+
+    def _sample(self, fc_feats, att_feats, att_masks=None, opt=None):
         opt = opt or {}
         mode = opt.get("train_mode", "NAIC")
         sample_n = int(opt.get("sample_n", 1))

@@ -45,3 +45,91 @@ def test_batch_512_matches_its_own_shards(eng):
     part = [t.cpu() for t in o[:1] + o[2:]]
     for a, b in zip(part, full):
         assert torch.equal(a, b[idx])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_varlen_encoder_equals_padded_formulation(precision, monkeypatch):
+    """the compact (varlen) encoder must return what the padded one returns -- bit for bit in fp32 (a row's
+    arithmetic does not depend on where the row sits), same boxes / tokens and 1e-2-close logits in bf16."""
+    from boficap_b200.engine import BofiEngine
+    cfg = BofiConfig()
+    sd = checkpoint(cfg, "s_real")
+    fc, att, masks = synth.synth_inputs(40, 100, seed=17, adaptive=True)
+    att_len = masks.long().sum(1).int().cuda()
+    var = BofiEngine(cfg, 0, precision).load_state_dict(sd)
+    monkeypatch.setenv("BOFI_VARLEN", "0")
+    pad = BofiEngine(cfg, 0, precision).load_state_dict(sd)
+    monkeypatch.delenv("BOFI_VARLEN")
+    res = []
+    for eng in (var, pad):
+        mem = eng.encode(att.cuda(), att_len, want_memory=True)
+        out = eng.decode("NAIC", 1, 0, True)
+        torch.cuda.synchronize()
+        res.append((mem.cpu(), [t.cpu() for t in out], eng.decode_info()["kernel_launches"]))
+    (mem_v, out_v, _), (mem_p, out_p, _) = res
+    valid = masks.bool()
+    if precision == "fp32":
+        assert torch.equal(mem_v[valid], mem_p[valid])
+        for a, b in zip(out_v, out_p):
+            assert torch.equal(torch.nan_to_num(a), torch.nan_to_num(b))
+    else:
+        assert (mem_v[valid] - mem_p[valid]).abs().max().item() < 5e-2
+        assert torch.equal(out_v[3], out_p[3]) and torch.equal(out_v[4], out_p[4])
+    assert (mem_v[~valid] == 0).all()                      # padded rows of the returned memory are zero-filled
+    # SAIC through the compact memory as well
+    for mode_eng in (var, pad):
+        mode_eng.encode(att.cuda(), att_len)
+    a = var.decode("SAIC", 1, 1, True)
+    b = pad.decode("SAIC", 1, 1, True)
+    torch.cuda.synchronize()
+    if precision == "fp32":
+        for x, y in zip(a, b):
+            assert torch.equal(torch.nan_to_num(x.float()), torch.nan_to_num(y.float()))
+    var.close()
+    pad.close()
+
+
+def test_non_prefix_mask_is_reported():
+    """The kernels keep only the count of valid regions; the reference's masked_fill accepts any mask.  A mask with a hole
+    must raise instead of silently decoding something else (device-side check, read at the call's own synchronisation)."""
+    from boficap_b200.captioning import models
+    cfg = BofiConfig()
+    infos = synth.make_infos(cfg)
+    opt = infos["opt"]
+    opt.vocab = infos["vocab"]
+    model = models.setup(opt)
+    model.load_state_dict(checkpoint(cfg, "s_real"))
+    model = model.cuda().eval()
+    fc, att, masks = synth.synth_inputs(6, 40, seed=3, adaptive=True)
+    kw = {"sample_method": "greedy", "train_mode": "NAIC"}
+    model(fc.cuda(), att.cuda(), masks.cuda(), opt=kw, mode="sample")            # prefix masks: fine
+    bad = masks.clone()
+    bad[2, 3] = 0.0                                                              # a hole inside the valid prefix
+    with pytest.raises(ValueError, match="prefix mask"):
+        model(fc.cuda(), att.cuda(), bad.cuda(), opt=kw, mode="sample")
+    model(fc.cuda(), att.cuda(), masks.cuda(), opt=kw, mode="sample")            # the flag was cleared
+
+
+def test_host_slot_buffers_follow_the_batch_shape():
+    """pipeline.submit_host reuses a slot's pinned outputs: a short last batch followed by a full one (or another
+    want_logprobs) must reallocate instead of writing past the old buffers."""
+    from boficap_b200.pipeline import BofiPipeline
+    cfg = BofiConfig()
+    pipe = BofiPipeline(cfg, checkpoint(cfg, "s_real"), 0, "fp32", depth=1)
+    _, small, _ = synth.synth_inputs(3, 36, seed=5)
+    _, big, _ = synth.synth_inputs(9, 36, seed=6)
+    a = pipe.submit_host(small.pin_memory()).wait()
+    assert a["seq"].shape[0] == 3
+    b = pipe.submit_host(big.pin_memory()).wait()
+    assert b["seq"].shape[0] == 9 and b.get("logp") is None
+    c = pipe.submit_host(big.pin_memory(), want_logprobs=True).wait()
+    assert c["logp"].shape == (9, cfg.seq_length, cfg.tgt_vocab)
+    ref = pipe.engines[0]
+    ref.encode(big.cuda())
+    want = ref.decode("NAIC", 1, 1, False)[0].cpu()
+    assert torch.equal(b["seq"], want) and torch.equal(c["seq"], want)
+    # the feeder's 2-byte features through the host entry point (fp32 engine: one widening kernel)
+    d = pipe.submit_host(big.to(torch.bfloat16).pin_memory()).wait()
+    ref.encode(big.to(torch.bfloat16).cuda())
+    assert torch.equal(d["seq"], ref.decode("NAIC", 1, 1, False)[0].cpu())
+    pipe.close()

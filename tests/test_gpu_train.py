@@ -275,3 +275,53 @@ def test_xe_gradient_is_additive_over_images_bf16():
     rel = float((got - want).norm() / want.norm())
     print("XE additivity: cosine %.6f, relative L2 difference %.4f" % (cos, rel))
     assert cos > 0.999 and rel < 0.05
+
+
+def test_documented_training_loop_with_optimizer_zero_grad():
+    """tools/train.py:210 / INTEGRATION.md section 2: `optimizer.zero_grad()` (set_to_none=True since torch 2.0) drops every
+    `.grad` view of the flat gradient buffer.  The next forward must put them back (and zero the buffer), otherwise
+    `optimizer.step()` silently skips all parameters from the second step on."""
+    B, R, adaptive, seed = CASES[0]
+    model, cfg = build_model("fp32")
+    args, bt = batch_args(B, R, adaptive, seed, cfg)
+    model.train_bind()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    probe = dict(model.named_parameters())["model.decoder.layers.0.feed_forward.w_1.weight"]
+    snaps, losses, gnorms = [probe.detach().clone()], [], []
+    for it in range(4):
+        opt.zero_grad()                                   # set_to_none=True: every p.grad becomes None
+        assert all(p.grad is None for p in model.parameters())
+        loss = model.xe_step(*args)[0]
+        assert all(p.grad is not None for p in model.parameters())
+        gnorms.append(float(model.flat_grads().norm()))
+        opt.step()
+        snaps.append(probe.detach().clone())
+        losses.append(float(loss))
+    for it in range(4):                                   # the weights move at EVERY step, not only the first
+        assert not torch.equal(snaps[it], snaps[it + 1]), "step %d did not update the parameters" % it
+    assert losses[-1] < losses[0]
+    # zero_grad really zeroed: the gradient norm does not grow like an accumulating buffer would (x2, x3, x4)
+    assert gnorms[3] < 2.0 * gnorms[0], gnorms
+    # the autograd bridge (loss_wrapper.py path) behaves the same
+    from oracle.bofi_oracle import BofiOracle
+    opt.zero_grad()
+    outs = model(*args)
+    l2, _ = BofiOracle.loss_xe(outs, bt["phrase_num"], bt["phrase_length"], bt["phrase_syn"], bt["labels"])
+    l2.backward()
+    before = probe.detach().clone()
+    opt.step()
+    assert not torch.equal(before, probe.detach())
+
+
+def test_decode_after_train_bind_does_not_replay_stale_graphs():
+    """bofi_train_bind frees the engine-owned parameter buffer: decode graphs captured before it must not be replayed."""
+    cfg = BofiConfig()
+    model, _ = build_model("fp32")
+    fc, att, _ = synth.synth_inputs(6, 36, seed=7)
+    kw = {"sample_method": "greedy", "train_mode": "NAIC"}
+    outs = [model(fc.cuda(), att.cuda(), None, opt=kw, mode="sample") for _ in range(3)]      # eager, capture, replay
+    model.train_bind()
+    again = [model(fc.cuda(), att.cuda(), None, opt=kw, mode="sample") for _ in range(3)]
+    for o in again:
+        assert torch.equal(o[0], outs[0][0]) and torch.equal(o[3], outs[0][3])
+        assert (o[1] - outs[0][1]).abs().max().item() < 1e-5

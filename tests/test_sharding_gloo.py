@@ -53,6 +53,12 @@ def _worker(rank, world, port, ret):
     # boxes never depend on the batch composition: they equal the unsharded decode
     whole = decode(att, masks)
     ok = ok and torch.equal(full[2], whole[2]) and torch.equal(full[3], whole[3])
+    # the one-collective packed gather of equal shards (bench.py's timed region): every rank decodes 4 images
+    a4, m4 = att[rank * 3:rank * 3 + 4], masks[rank * 3:rank * 3 + 4]
+    mine4 = decode(a4, m4)
+    packed = parallel.gather_captions_packed(*mine4)
+    ok = ok and packed[0].shape == (4 * world, 20) and packed[0].dtype == torch.int64 and packed[3].dtype == torch.int64
+    ok = ok and all(torch.equal(p[rank * 4:rank * 4 + 4].to(m.dtype), m) for p, m in zip(packed, mine4))
     ret[rank] = bool(ok)
     dist.barrier()
     dist.destroy_process_group()
