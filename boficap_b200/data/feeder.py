@@ -1,0 +1,66 @@
+"""Pinned, 2-byte, double-buffered feature feeder.
+
+The reference's loader yields fp32 numpy batches that `eval_utils.py:431-437` / `tools/train.py:205-207` copy to the GPU
+from pageable memory.  Here a background thread reads the images of the NEXT batches (FeatureReader), converts them to
+the feeder's element type (bf16 by default: half the host-to-device bytes, and a bf16 engine's att_embed GEMM reads them in
+place) while packing them into a ring of page-locked batch buffers; the consumer gets `(att_feats, att_len, keys)` whose
+tensors go straight to `bofi_sample_host_async_ex` (BofiPipeline.submit_host) or `.cuda(non_blocking=True)`.
+
+A slot is recycled `depth` batches after it was handed out, i.e. the consumer may keep `depth - 1` batches in flight --
+match it to the pipeline depth + 1.
+"""
+import queue
+import threading
+
+import torch
+
+
+class PinnedFeeder:
+    def __init__(self, reader, keys, batch_size, max_regions, feat_size=2048, dtype=torch.bfloat16, depth=4, drop_last=False, pin=None):
+        self.reader, self.keys, self.B, self.R = reader, list(keys), batch_size, max_regions
+        self.dtype, self.depth, self.drop_last = dtype, max(2, depth), drop_last
+        pin = torch.cuda.is_available() if pin is None else pin
+        mk = lambda *shape, dt: torch.zeros(*shape, dtype=dt).pin_memory() if pin else torch.zeros(*shape, dtype=dt)
+        self.slots = [(mk(batch_size, max_regions, feat_size, dt=dtype), mk(batch_size, dt=torch.int32)) for _ in range(self.depth)]
+        self.free = queue.Queue()
+        for i in range(self.depth):
+            self.free.put(i)
+        self.ready = queue.Queue(maxsize=self.depth)
+        self.held = []
+        self.thread = threading.Thread(target=self._produce, daemon=True)
+        self.thread.start()
+
+    def _produce(self):
+        try:
+            for lo in range(0, len(self.keys), self.B):
+                keys = self.keys[lo:lo + self.B]
+                if len(keys) < self.B and self.drop_last:
+                    break
+                i = self.free.get()
+                att, lens = self.slots[i]
+                n = len(keys)
+                for b, k in enumerate(keys):
+                    cnt = self.reader.get_into(k, att[b])
+                    if cnt < self.R:
+                        att[b, cnt:].zero_()                  # padded regions are zero, as dataloader.py:333-336 leaves them
+                    lens[b] = cnt
+                self.ready.put((i, n, keys))
+            self.ready.put(None)
+        except Exception as ex:                                # surfaced to the consumer
+            self.ready.put(ex)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        item = self.ready.get()
+        if item is None:
+            raise StopIteration
+        if isinstance(item, Exception):
+            raise item
+        i, n, keys = item
+        self.held.append(i)
+        if len(self.held) >= self.depth - 1:                    # the oldest batch handed out is finished by now
+            self.free.put(self.held.pop(0))
+        att, lens = self.slots[i]
+        return att[:n], lens[:n], keys

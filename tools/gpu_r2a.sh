@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 O=gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > $O/a_smi.txt 2>&1
 timeout 2400 python -m pytest tests -m gpu -q --timeout 900 > $O/a_pytest.log 2>&1; echo "pytest rc=$?" >> $O/a_pytest.log
-timeout 300 python __graft_entry__.py --smoke > $O/a_smoke.log 2>&1; echo "smoke rc=$?" >> $O/a_smoke.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/a_smoke.log 2>&1; echo "smoke rc=$?" >> $O/a_smoke.log
 timeout 900 python bench.py > $O/a_bench.json 2> $O/a_bench.err; echo "bench rc=$?" >> $O/a_bench.err
 BOFI_PROFILE_DUMP=$O/a_records.csv timeout 600 python bench.py --steps 5 --no-extras > $O/a_bench_dump.json 2>> $O/a_bench.err
 timeout 600 python bench.py --adaptive --regions 100 --batch 512 --no-extras > $O/a_adaptive.json 2>> $O/a_bench.err
