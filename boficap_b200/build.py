@@ -28,13 +28,15 @@ def needs_build():
 PROF_OUT = os.path.join(HERE, "lib", "libbofi_b200_prof.so")
 
 
-def build(force=False, verbose=False, prof=False):
+def build(force=False, verbose=False, prof=False, out=None):
     """prof=True builds lib/libbofi_b200_prof.so with the GEMM stall counters compiled in (-DBOFI_GEMM_PROF);
-    it is only ever loaded when BOFI_LIB_PATH points at it (tools/gemm_stalls.py)."""
-    if not prof and not force and not needs_build():
+    it is only ever loaded when BOFI_LIB_PATH points at it (tools/gemm_stalls.py).  `out` (or BOFI_BUILD_OUT): build to
+    another file, e.g. a candidate that is moved over the shipped library only once it is known to be good."""
+    out = out or os.environ.get("BOFI_BUILD_OUT")
+    if not prof and not force and not out and not needs_build():
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    out = PROF_OUT if prof else OUT
+    out = out or (PROF_OUT if prof else OUT)
     cmd = [nvcc_path(), "-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
            "-shared", "-Xcompiler", "-fPIC"] + (["-DBOFI_GEMM_PROF"] if prof else []) + ["-o", out, SRC]
     if verbose:

@@ -6,8 +6,8 @@ the feeder's element type (bf16 by default: half the host-to-device bytes, and a
 place) while packing them into a ring of page-locked batch buffers; the consumer gets `(att_feats, att_len, keys)` whose
 tensors go straight to `bofi_sample_host_async_ex` (BofiPipeline.submit_host) or `.cuda(non_blocking=True)`.
 
-A slot is recycled `depth` batches after it was handed out, i.e. the consumer may keep `depth - 1` batches in flight --
-match it to the pipeline depth + 1.
+Of the `depth` slots one is being filled and at least one waits in the ready queue, so a batch stays valid until
+`depth - 2` newer ones have been handed out: use depth = pipeline depth + 2 (5 for the default three batches in flight).
 """
 import queue
 import threading
@@ -16,7 +16,7 @@ import torch
 
 
 class PinnedFeeder:
-    def __init__(self, reader, keys, batch_size, max_regions, feat_size=2048, dtype=torch.bfloat16, depth=4, drop_last=False, pin=None):
+    def __init__(self, reader, keys, batch_size, max_regions, feat_size=2048, dtype=torch.bfloat16, depth=5, drop_last=False, pin=None):
         self.reader, self.keys, self.B, self.R = reader, list(keys), batch_size, max_regions
         self.dtype, self.depth, self.drop_last = dtype, max(2, depth), drop_last
         pin = torch.cuda.is_available() if pin is None else pin
