@@ -113,6 +113,20 @@ __device__ __forceinline__ float drop_mul(const Drop& d, uint32_t idx) {      //
 // element index of an attention probability: (global query row, head, key)
 __device__ __forceinline__ uint32_t att_idx(int qrow, int head, int key) { return ((uint32_t)qrow * 8u + (uint32_t)head) * 128u + (uint32_t)key; }
 
+// Multinomial sampling of CaptionModel.sample_next_word (CaptionModel.py:403-431: logits / temperature, NaN -> -10,
+// Categorical(...).sample()) as a Gumbel-max: argmax_v (z_v / T + g_v), g_v = -log(-log(u_v)), u_v from the counter-based
+// hash of (key, row, v).  Same distribution as the reference, the library's own random stream (seeded by the caller).
+struct Sampler {
+  uint32_t key = 0;
+  int enabled = 0;          // 0 = greedy
+  float inv_temp = 1.f;
+};
+__device__ __forceinline__ float gumbel_score(const Sampler& sp, float z, int row, int v) {
+  const float zz = (z != z) ? -10.f : z * sp.inv_temp;
+  const float u = ((float)drop_hash(sp.key, (uint32_t)row * 16384u + (uint32_t)v) + 0.5f) * (1.0f / 4294967296.0f);
+  return zz - __logf(-__logf(u));
+}
+
 // Work of a bounding step is skipped once every row has finished (device-side `break` of
 // TransformerModel.py:1869-1870): kernels of the step read the live-row counter first.
 __device__ __forceinline__ bool step_is_dead(const int* live_rows) {

@@ -169,6 +169,8 @@ struct bofi_engine {
   const int* rows_dev = nullptr;         // when set, linear() / layernorm() only process the first *rows_dev rows (SAIC compaction, varlen encoder)
   const int* varlen_total = nullptr;     // device row count of the varlen encoder (= seqoff + B + 1)
   int rows_hint = 0;                     // profiling runs: the host copy of *rows_dev of the varlen encoder (exact FLOP accounting)
+  bool vocab_fused = true;               // BOFI_VOCAB_FUSED=0: materialise fp32 logits + vocab_epilogue_kernel (the round-1 path)
+  DevBuf vpart;                          // fused vocabulary projection: per-(column tile, half, row) softmax / argmax records
   bool varlen = true;                    // BOFI_VARLEN=0: padded encoder (every GEMM / LN / attention over all B*R rows)
   DevBuf xpad, seqoff, maskflag;         // varlen: padded att_embed output, row offsets [B+1] + total, prefix-mask check flag
   const int* enc_off = nullptr;          // set while the varlen encoder layers run: compact row offset of every image
@@ -562,8 +564,7 @@ static int reserve_decode(bofi_engine* e, int B, int R, int sn) {
   RC_TRY(e->ao.reserve(dr * kD * ts));
   RC_TRY(e->q.reserve(dr * kD * ts));
   RC_TRY(e->ffh.reserve(dr * e->cfg.d_ff * ts));
-  RC_TRY(e->logits.reserve(rows * e->L * (size_t)e->Vpad * 4));
-  RC_TRY(e->tok.reserve(rows * e->L * 4));
+  RC_TRY(e->tok.reserve(rows * e->L * 4));      // the logits buffer is reserved by the paths that still materialise it
   const int nkv = std::max(1, e->cfg.n_len) + e->cfg.n_dec;
   if ((int)e->kv.size() < nkv) e->kv.resize(nkv);
   for (int i = 0; i < nkv; ++i) RC_TRY(e->kv[i].reserve(M * 2 * kD * ts));
@@ -900,12 +901,69 @@ static int decode_naic(bofi_engine* e, cudaStream_t s, int sn, int output_logsof
     const int total = rows * L;
     int chunk = total;
     if (e->vocab_chunk_rows > 0 && !(std::is_same<T, bf16>::value && e->use_tc && e->ln_fuse)) chunk = std::max(L, e->vocab_chunk_rows / L * L);
-    if (chunk >= total) {
+    bool fused = false;
+    if constexpr (std::is_same<T, bf16>::value) {
+      fused = e->use_tc && e->gemm2 && e->vocab_fused && chunk >= total && total >= 256 && !(e->ln_fuse && total >= e->ln_fuse_min_rows);
+      if (fused) {
+        // Fused vocabulary projection (tc::VocabEpi): pass 1 leaves per-tile softmax / argmax records, vocab_merge_kernel
+        // folds them into tokens, max and lse; pass 2 recomputes the projection and writes log-probs straight into the
+        // caller's tensor -- only when the caller wants it.  No [rows, L, Vpad] logits buffer.
+        const int nparts = 2 * ceil_div(e->V, tc::k2BN);
+        const bool want_stats = e->stat_entropy != nullptr;
+        const size_t per = (size_t)nparts * total;
+        RC_TRY(e->vpart.reserve(per * 4 * (4 + (want_stats ? 1 : 0) + (e->sampler.enabled ? 3 : 0)) + (size_t)total * 4));
+        RC_TRY(e->sa_mx.reserve((size_t)total * 4));
+        RC_TRY(e->sa_lse.reserve((size_t)total * 4));
+        tc::VocabEpi ve;
+        float* base = e->vpart.as<float>();
+        ve.pm = base; base += per;
+        ve.ps = base; base += per;
+        ve.pi = reinterpret_cast<int*>(base); base += per;
+        ve.pn = reinterpret_cast<int*>(base); base += per;
+        if (want_stats) { ve.pt = base; base += per; }
+        if (e->sampler.enabled) {
+          ve.pgv = base; base += per;
+          ve.pgi = reinterpret_cast<int*>(base); base += per;
+          ve.pgz = base; base += per;
+        }
+        ve.pz0 = want_stats ? base : nullptr;
+        ve.sp = e->sampler;
+        ve.fast_exp = want_stats ? 0 : 1;            // as vocab_epilogue_kernel: ex2.approx unless the entropy statistics are wanted
+        T* y = e->y.as<T>();
+        RC_TRY(layernorm<T>(e, s, x, kD, e->dec_norm, y, kD, total, nullptr, nullptr));
+        {
+          ProfScope prof(e, s, PC_GEMM_TC, 2.0 * total * e->V * kD, 2.0 * ((double)total * kD + (double)e->V * kD) + 16.0 * per, total, e->V, kD);
+          cudaError_t err = tc::gemm_tc2_vocab(s, y, kD, e->generator.w16, kD, e->generator.b, total, e->V, kD, 1, ve);
+          if (err != cudaSuccess) return fail(BOFI_ERR_CUDA, "vocabulary statistics GEMM: %s", cudaGetErrorString(err));
+        }
+        {
+          ProfScope prof(e, s, PC_VOCAB, 0.0, 16.0 * per);
+          launch_k(vocab_merge_kernel, ceil_div(total, 256), 256, 0, s, ve, nparts, total, L, e->sa_mx.as<float>(), e->sa_lse.as<float>(), seq,
+                   (const int*)e->st.last, -1, (int*)nullptr, e->stat_entropy, e->stat_logp);
+        }
+        CU_TRY(cudaGetLastError());
+        if (logprobs) {
+          ve.out = logprobs;
+          ve.ldo = e->V;
+          ve.mx = e->sa_mx.as<float>();
+          ve.lse = e->sa_lse.as<float>();
+          ve.do_lsm = output_logsoftmax;
+          ProfScope prof(e, s, PC_GEMM_TC, 2.0 * total * e->V * kD, 2.0 * ((double)total * kD + (double)e->V * kD) + 4.0 * total * e->V, total, e->V, kD);
+          cudaError_t err = tc::gemm_tc2_vocab(s, y, kD, e->generator.w16, kD, e->generator.b, total, e->V, kD, 2, ve);
+          if (err != cudaSuccess) return fail(BOFI_ERR_CUDA, "vocabulary log-prob GEMM: %s", cudaGetErrorString(err));
+        }
+      }
+    }
+    if (fused) {
+      chunk = total + 1;          // skip the materialising path below
+    } else if (chunk >= total) {
+      RC_TRY(e->logits.reserve((size_t)total * (size_t)e->Vpad * 4));
       RC_TRY((ln_linear<T, float>(e, s, x, e->dec_norm, e->generator, e->logits.as<float>(), e->Vpad, total, 0, nullptr, e->y.as<T>())));
     } else {
+      RC_TRY(e->logits.reserve((size_t)total * (size_t)e->Vpad * 4));
       RC_TRY(layernorm<T>(e, s, x, kD, e->dec_norm, e->y.as<T>(), kD, total, nullptr, nullptr));
     }
-    for (int r0 = 0; r0 < total; r0 += chunk) {
+    for (int r0 = 0; r0 < total && !fused; r0 += chunk) {
       const int n = std::min(chunk, total - r0);
       if (chunk < total)
         RC_TRY((linear<T, float>(e, s, e->y.as<T>() + (size_t)r0 * kD, kD, e->generator, nullptr, 0, e->logits.as<float>(), e->Vpad, n, 0, nullptr)));
@@ -943,6 +1001,7 @@ static int decode_saic(bofi_engine* e, cudaStream_t s, int sn, int output_logsof
   const int nb_layers = std::max(1, c.n_len);
   RC_TRY(e->sa_mx.reserve((size_t)rows * L * 4));
   RC_TRY(e->sa_lse.reserve((size_t)rows * L * 4));
+  RC_TRY(e->logits.reserve((size_t)rows * L * (size_t)e->Vpad * 4));
   if (c.n_len == 0) {
     RC_TRY(project_memory_kv<T>(e, s, e->lp0.ca.kv, e->kv[0]));
   } else {
@@ -1003,6 +1062,7 @@ static int decode_saic_incremental(bofi_engine* e, cudaStream_t s, int sn, int o
   const int nb_layers = std::max(1, c.n_len);
   RC_TRY(e->sa_mx.reserve((size_t)slots * 4));
   RC_TRY(e->sa_lse.reserve((size_t)slots * 4));
+  RC_TRY(e->logits.reserve((size_t)slots * (size_t)e->Vpad * 4));
   RC_TRY(e->sa_cidx.reserve((size_t)slots * 4));
   RC_TRY(e->sa_cache.reserve((size_t)c.n_dec * slots * 2 * kD * sizeof(T)));
   if (c.n_len == 0) {
@@ -1234,6 +1294,8 @@ int bofi_create(const bofi_config_t* cfg, int device, bofi_handle_t* out) {
   if (const char* gm = getenv("BOFI_LNFUSE_MIN")) e->ln_fuse_min_rows = atoi(gm);
   const char* gs = getenv("BOFI_SAIC");
   e->saic_full = (gs && strcmp(gs, "full") == 0);
+  const char* gf = getenv("BOFI_VOCAB_FUSED");
+  e->vocab_fused = !(gf && strcmp(gf, "0") == 0);
   const char* gv = getenv("BOFI_VARLEN");
   e->varlen = !(gv && strcmp(gv, "0") == 0);
   const char* ga = getenv("BOFI_ATTN");
@@ -1260,7 +1322,7 @@ int bofi_destroy(bofi_handle_t e) {
   for (DevBuf& b : e->kv) b.release();
   DevBuf* all[] = {&e->bound_in, &e->fill_in, &e->attT, &e->x, &e->y, &e->qkv, &e->ao, &e->q, &e->ffh, &e->memT, &e->attlen,
                    &e->sa_mx, &e->sa_lse, &e->sa_cidx, &e->sa_cache, &e->sa_bcache, &e->sa_qkv0, &e->sa_x0, &e->head1t, &e->tab_y, &e->tab_qkv, &e->logits, &e->state_i32, &e->tok, &e->h_in, &e->h_len, &e->h_seq, &e->h_logp,
-                   &e->h_pnum, &e->h_plen, &e->h_psyn, &e->unit_a, &e->unit_w, &e->unit_o, &e->xpad, &e->seqoff, &e->maskflag};
+                   &e->h_pnum, &e->h_plen, &e->h_psyn, &e->unit_a, &e->unit_w, &e->unit_o, &e->xpad, &e->seqoff, &e->maskflag, &e->vpart};
   for (DevBuf* b : all) b->release();
   delete e;
   return BOFI_OK;

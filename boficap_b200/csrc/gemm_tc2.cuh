@@ -99,11 +99,40 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
       : "memory");
 }
 
-template <typename TOut, bool RELU, bool RESID, bool REDUCE = false, bool ARES = false, int KPS = 1>
+// Vocabulary-projection epilogues (TransformerModel.logit :1668-1669 + F.log_softmax AttModel.py:206-209 + sample_next_word
+// CaptionModel.py:383-431), VMODE != 0.  The [rows, L, V] fp32 logits never exist in HBM:
+//   VMODE 1 (statistics)  every epilogue thread owns one row of the tile and folds its 128 columns into a running
+//            (max, sum exp(z - max), first index of the max [, sum exp(z - max) z, first NaN, Gumbel-max]) state; one record
+//            per (column tile, epilogue half, row) goes to the SoA arrays below, vocab_merge_kernel (kernels.cuh) folds the
+//            2 * ceil(N / 256) records of a row into token, max and log-sum-exp.  Nothing else is written.
+//   VMODE 2 (log-probs)   only when the caller asked for the [rows, L, V] tensor: the projection is recomputed (K = 512: 0.2
+//            ms, cheaper than writing and re-reading 1.5 GB of logits) and  (z - mx[row]) - lse[row]  goes straight to the
+//            caller's rows, whose pitch (V = 9491 floats) rules out TMA: a warp transposes its 32 x 32 block through the
+//            swizzled staging tile and writes each row segment with one 128-byte coalesced store instruction.
+struct VocabEpi {
+  float* pm = nullptr;       // [nparts][M] running max
+  float* ps = nullptr;       // [nparts][M] sum exp(z - max)
+  float* pt = nullptr;       // [nparts][M] sum exp(z - max) * z  (entropy of eval_split; nullptr = not needed)
+  int* pi = nullptr;         // [nparts][M] first column holding the max (torch.max: lowest index on ties)
+  int* pn = nullptr;         // [nparts][M] first NaN column, 0x7fffffff = none (torch.max: a NaN wins)
+  float* pgv = nullptr;      // [nparts][M] sampling: best Gumbel-perturbed score ...
+  int* pgi = nullptr;        // [nparts][M] ... its column ...
+  float* pgz = nullptr;      // [nparts][M] ... and the unperturbed logit there (log-prob of the sampled token)
+  float* pz0 = nullptr;      // [M] logit of column 0 (the token tail padding writes; statistics only, may be nullptr)
+  Sampler sp;
+  int fast_exp = 0;          // ex2.approx for the sum-exp (bf16 engine without entropy statistics)
+  float* out = nullptr;      // VMODE 2: caller's [M, ldo] tensor
+  long long ldo = 0;
+  const float* mx = nullptr; // VMODE 2: per-row max and log-sum-exp from vocab_merge_kernel
+  const float* lse = nullptr;
+  int do_lsm = 0;            // 0: raw logits (output_logsoftmax = 0)
+};
+
+template <typename TOut, bool RELU, bool RESID, bool REDUCE = false, bool ARES = false, int KPS = 1, int VMODE = 0>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, const float* residual, int ldr,
-               int M, int N, int K, int relu, const int* live_rows, const int* rows_dev) {
+               int M, int N, int K, int relu, const int* live_rows, const int* rows_dev, const VocabEpi ve) {
   pdl_launch();
   using L = Smem2T<ARES, KPS>;
   constexpr int BN = k2BN, STAGES = L::kStages, k2Staging = L::kStaging;
@@ -317,6 +346,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (ci < NI && cc < NC && nb + 4 <= N) bv = *reinterpret_cast<const float4*>(bias + nb);
       }
       fetch_res(res[0], half);
+      // vocabulary epilogues: this thread's running statistics over the columns it sees of this tile / its row's max and lse
+      float vm = -INFINITY, vs = 0.f, vt = 0.f, vgv = -INFINITY, vgz = 0.f, mx_row = 0.f, lse_row = 0.f;
+      int vi = 0x7fffffff, vn = 0x7fffffff, vgi = 0x7fffffff;
+      if constexpr (VMODE == 2) {
+        if (ve.do_lsm && row_ok) { mx_row = ve.mx[row]; lse_row = ve.lse[row]; }
+      }
       PROF_WAIT(w_tfull, mbar_wait(smem_u32(&tmem_full_bar[as]), aph));
       tcgen05_fence_after();
 #pragma unroll
@@ -342,6 +377,61 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         w_tld += PROF_T() - t_ld0;
         const long long t_m0 = PROF_T();
 #endif
+        if constexpr (VMODE == 1) {
+          static_assert(VMODE != 1 || (CC == 32 && !RELU && !RESID && !REDUCE), "statistics epilogue: fp32 logits");
+          float z[CC];
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < CC; j += 4) {
+              const int src = i * (CC / 4) + j / 4;
+              z[j] = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bv.x, src);
+              z[j + 1] = __uint_as_float(r[j + 1]) + __shfl_sync(0xffffffffu, bv.y, src);
+              z[j + 2] = __uint_as_float(r[j + 2]) + __shfl_sync(0xffffffffu, bv.z, src);
+              z[j + 3] = __uint_as_float(r[j + 3]) + __shfl_sync(0xffffffffu, bv.w, src);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CC; ++j) z[j] = (n + j < N) ? __uint_as_float(r[j]) + bias[n + j] : -INFINITY;
+          }
+          if (n == 0 && ve.pz0 != nullptr && row_ok) ve.pz0[row] = z[0];
+          float cm = -INFINITY;
+          bool anynan = false;
+#pragma unroll
+          for (int j = 0; j < CC; ++j) { cm = fmaxf(cm, z[j]); anynan |= (z[j] != z[j]); }
+          if (anynan && vn == 0x7fffffff) {
+#pragma unroll
+            for (int j = CC - 1; j >= 0; --j) if (z[j] != z[j]) vn = n + j;
+          }
+          if (cm > vm) {                    // a strictly larger value: the row's first maximum so far lies in this chunk
+#pragma unroll
+            for (int j = CC - 1; j >= 0; --j) if (z[j] == cm) vi = n + j;
+            const float sc = ve.fast_exp ? __expf(vm - cm) : expf(vm - cm);       // exp(-inf) = 0 on the first chunk
+            vs *= sc;
+            vt *= sc;
+            vm = cm;
+          }
+          if (ve.fast_exp) {
+#pragma unroll
+            for (int j = 0; j < CC; ++j) vs += __expf(z[j] - vm);
+          } else {
+#pragma unroll
+            for (int j = 0; j < CC; ++j) {
+              const float ex = expf(z[j] - vm);
+              vs += ex;
+              if (ve.pt != nullptr && (full || n + j < N)) vt = fmaf(ex, z[j], vt);
+            }
+          }
+          if (ve.sp.enabled) {
+#pragma unroll 4
+            for (int j = 0; j < CC; ++j) {
+              if (full || n + j < N) {
+                const float g = gumbel_score(ve.sp, z[j], row, n + j);
+                if (g > vgv) { vgv = g; vgi = n + j; vgz = z[j]; }
+              }
+            }
+          }
+          continue;
+        }
         if constexpr (RESID) {
           if (full) {
             // transpose the coalesced residual registers into this thread's row through the staging tile
@@ -386,6 +476,27 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             r[j] = __float_as_uint(x);
           }
         }
+        if constexpr (VMODE == 2) {
+          static_assert(VMODE != 2 || (CC == 32 && !RELU && !RESID && !REDUCE), "log-prob epilogue: fp32 output");
+          if (ve.do_lsm) {
+#pragma unroll
+            for (int j = 0; j < CC; ++j) r[j] = __float_as_uint((__uint_as_float(r[j]) - mx_row) - lse_row);
+          }
+          __syncwarp();                     // the previous chunk's row stores have read the staging tile
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            st_shared_v4(srow + (uint32_t)((j ^ (lane & 7)) * 16), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          __syncwarp();
+          const bool col_ok = n + lane < N;
+          float* orow = ve.out + (size_t)(m0 + quad * 32) * (size_t)ve.ldo + (size_t)(n + lane);
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            float v;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(sbuf + (uint32_t)rr * 128u + (uint32_t)((((lane >> 2) ^ (rr & 7)) * 16) + (lane & 3) * 4)));
+            if (col_ok && m0 + quad * 32 + rr < M) __stcs(orow + (size_t)rr * (size_t)ve.ldo, v);
+          }
+          continue;
+        }
         // this warp's staging tile must have been read out by the TMA engine (its previous store); on the residual path
         // every lane must also be done reading its residual row before the tile is overwritten
         PROF_WAIT(w_stage, if (lane == 0) { if constexpr (k2Staging == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); } __syncwarp());
@@ -417,6 +528,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         t_store += PROF_T() - t_s0;
 #endif
       }
+      if constexpr (VMODE == 1) {
+        if (row_ok) {                       // SoA records: consecutive lanes = consecutive rows, coalesced
+          const size_t at = (size_t)((tile % tiles_n) * 2 + half) * (size_t)M + (size_t)row;
+          ve.pm[at] = vm;
+          ve.ps[at] = vs;
+          ve.pi[at] = vi;
+          ve.pn[at] = vn;
+          if (ve.pt) ve.pt[at] = vt;
+          if (ve.sp.enabled) { ve.pgv[at] = vgv; ve.pgi[at] = vgi; ve.pgz[at] = vgz; }
+        }
+      }
       PROF_DECL(t_a0 = PROF_T());
       tcgen05_fence_before();
       __syncwarp();
@@ -444,13 +566,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 
-template <typename TOut, bool RELU, bool RESID, bool REDUCE = false, bool ARES = false, int KPS = 1>
+template <typename TOut, bool RELU, bool RESID, bool REDUCE = false, bool ARES = false, int KPS = 1, int VMODE = 0>
 inline cudaError_t launch2(cudaStream_t s, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const float* bias,
-                           const float* residual, int ldr, int M, int N, int K, int relu, const int* live_rows, const int* rows_dev) {
+                           const float* residual, int ldr, int M, int N, int K, int relu, const int* live_rows, const int* rows_dev,
+                           const VocabEpi& ve = VocabEpi()) {
   static PerDevice<bool> configured_dev;
   bool& configured = configured_dev.get();
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<TOut, RELU, RESID, REDUCE, ARES, KPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2T<ARES, KPS>::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<TOut, RELU, RESID, REDUCE, ARES, KPS, VMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2T<ARES, KPS>::kTotal);
     if (e != cudaSuccess) return e;
     configured = true;
   }
@@ -471,7 +594,7 @@ inline cudaError_t launch2(cudaStream_t s, const CUtensorMap& tmA, const CUtenso
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  return cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<TOut, RELU, RESID, REDUCE, ARES, KPS>, tmA, tmB, tmC, bias, residual, ldr, M, N, K, relu, live_rows, rows_dev);
+  return cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<TOut, RELU, RESID, REDUCE, ARES, KPS, VMODE>, tmA, tmB, tmC, bias, residual, ldr, M, N, K, relu, live_rows, rows_dev, ve);
 }
 
 // Same contract as gemm_tc (K-major A [M,K], W [N,K]).  `want_ares`: A-resident tiles where the shape allows (opt-in,
@@ -511,6 +634,21 @@ inline cudaError_t gemm_tc2(cudaStream_t s, const bf16* A, int lda, const bf16* 
   }
 #undef BOFI_TC2
 #undef BOFI_TC2A
+}
+
+// Vocabulary projection without a logits tensor (see VocabEpi): vmode 1 = statistics records, vmode 2 = log-probs / raw logits
+// into the caller's rows.  A [M, K] bf16 (K % 128 == 0), W [N, K] bf16, bias fp32 [N].
+inline cudaError_t gemm_tc2_vocab(cudaStream_t s, const bf16* A, int lda, const bf16* W, int ldw, const float* bias, int M, int N, int K,
+                                  int vmode, const VocabEpi& ve) {
+  if (M <= 0 || N <= 0) return cudaSuccess;
+  if (lda % 8 != 0 || ldw % 8 != 0 || !bias || K % (2 * kBK) != 0) return cudaErrorInvalidValue;
+  const CUtensorMap* tmA = cached_tmap_kblocks(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBM, 2);
+  const CUtensorMap* tmB = cached_tmap_kblocks(W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, k2BN / 2, 2);
+  if (!tmA || !tmB) return cudaErrorInvalidValue;
+  // no TMA store in either mode: the C tensor map is a placeholder (never dereferenced)
+  if (vmode == 1) return launch2<float, false, false, false, false, 2, 1>(s, *tmA, *tmB, *tmA, bias, nullptr, 0, M, N, K, 0, nullptr, nullptr, ve);
+  if (vmode == 2) return launch2<float, false, false, false, false, 2, 2>(s, *tmA, *tmB, *tmA, bias, nullptr, 0, M, N, K, 0, nullptr, nullptr, ve);
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace tc

@@ -694,20 +694,6 @@ __device__ __forceinline__ void store_realigned(float* __restrict__ o, int c4, i
   }
 }
 
-// Multinomial sampling of CaptionModel.sample_next_word (CaptionModel.py:403-431: logits / temperature, NaN -> -10,
-// Categorical(...).sample()) as a Gumbel-max: argmax_v (z_v / T + g_v), g_v = -log(-log(u_v)), u_v from the counter-based
-// hash of (key, row, v).  Same distribution as the reference, the library's own random stream (seeded by the caller).
-struct Sampler {
-  uint32_t key = 0;
-  int enabled = 0;          // 0 = greedy
-  float inv_temp = 1.f;
-};
-__device__ __forceinline__ float gumbel_score(const Sampler& sp, float z, int row, int v) {
-  const float zz = (z != z) ? -10.f : z * sp.inv_temp;
-  const float u = ((float)drop_hash(sp.key, (uint32_t)row * 16384u + (uint32_t)v) + 0.5f) * (1.0f / 4294967296.0f);
-  return zz - __logf(-__logf(u));
-}
-
 constexpr int kVocabThreads = 512;
 constexpr int kVocabVec = 5;    // float4 per thread: 512 threads x 5 x 4 = 10240 >= Vpad (9504)
 #ifndef BOFI_VOCAB_OCC
@@ -891,6 +877,59 @@ vocab_epilogue_kernel(const float* __restrict__ logits, int ldl, int V, float* _
       if (total_len && t >= total_len[b] + total_off) tok = 0;
       seq_out[row] = tok;
     }
+  }
+}
+
+// Second half of the fused vocabulary projection (tc::VocabEpi, gemm_tc2.cuh): folds the 2 * ceil(V / 256) records of a row
+// = (b, slot) into what vocab_epilogue_kernel computes from a materialised row -- the maximum with torch.max's rules (a NaN
+// wins, the lowest index on ties), log sum exp(z - max), the greedy or Gumbel-max token, tail padding
+// seq[b, sum(phrase_length[b]):] = 0, and optionally eval_split's per-slot entropy / log-prob.  One thread per row, every
+// record array is read coalesced.
+__global__ void __launch_bounds__(256)
+vocab_merge_kernel(tc::VocabEpi ve, int nparts, int M, int L, float* __restrict__ mx_out, float* __restrict__ lse_out,
+                   long long* __restrict__ seq_out, const int* __restrict__ total_len, int total_off, int* __restrict__ tok_out_i32,
+                   float* __restrict__ slot_entropy, float* __restrict__ slot_logp) {
+  pdl_enter();
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= M) return;
+  float m = -INFINITY, gv = -INFINITY, gz = 0.f;
+  int idx = 0x7fffffff, nan_at = 0x7fffffff, gi = 0x7fffffff;
+  for (int p = 0; p < nparts; ++p) {
+    const size_t at = (size_t)p * M + row;
+    const float mp = ve.pm[at];
+    const int ip = ve.pi[at];
+    nan_at = min(nan_at, ve.pn[at]);
+    if (mp > m || (mp == m && ip < idx)) { m = mp; idx = ip; }     // the two halves of a tile interleave their columns
+    if (ve.sp.enabled) {
+      const float g = ve.pgv[at];
+      const int gip = ve.pgi[at];
+      if (g > gv || (g == gv && gip < gi)) { gv = g; gi = gip; gz = ve.pgz[at]; }
+    }
+  }
+  float S = 0.f, Tz = 0.f;
+  for (int p = 0; p < nparts; ++p) {
+    const size_t at = (size_t)p * M + row;
+    const float mp = ve.pm[at], sp_ = ve.ps[at];
+    if (mp == -INFINITY && sp_ == 0.f) continue;                  // a record without valid columns (the last, partial tile)
+    const float w = ve.fast_exp ? __expf(mp - m) : expf(mp - m);
+    S = fmaf(sp_, w, S);
+    if (ve.pt) Tz = fmaf(ve.pt[at], w, Tz);
+  }
+  const bool has_nan = nan_at != 0x7fffffff;
+  const float mx = has_nan ? __int_as_float(0x7fc00000) : m;
+  const float lse = logf(S);
+  mx_out[row] = mx;
+  lse_out[row] = lse;
+  int tok = ve.sp.enabled ? gi : (has_nan ? nan_at : idx);
+  float ztok = ve.sp.enabled ? gz : mx;
+  if (tok_out_i32) tok_out_i32[row] = tok;
+  const int b = row / L, t = row - b * L;
+  if (total_len && t >= total_len[b] + total_off) { tok = 0; ztok = ve.pz0 ? ve.pz0[row] : ztok; }
+  if (seq_out) seq_out[row] = tok;
+  if (slot_entropy) {
+    // -sum p log p = (max + lse) - sum p z ;  log p(token) = (z_token - max) - lse
+    slot_entropy[row] = (mx + lse) - Tz / S;
+    slot_logp[row] = (ztok - mx) - lse;
   }
 }
 

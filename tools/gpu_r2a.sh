@@ -12,6 +12,8 @@ BOFI_VARLEN=0 timeout 600 python bench.py --adaptive --regions 100 --batch 512 -
 timeout 600 python bench.py --mode SAIC --no-extras --no-logprobs > $O/a_saic.json 2>> $O/a_bench.err
 timeout 600 python bench.py --no-extras --no-logprobs > $O/a_nolp.json 2>> $O/a_bench.err
 timeout 600 python bench.py --no-extras --depth 1 > $O/a_depth1.json 2>> $O/a_bench.err
+BOFI_VOCAB_FUSED=0 timeout 600 python bench.py --no-extras > $O/a_bench_unfused.json 2>> $O/a_bench.err
+BOFI_VOCAB_FUSED=0 timeout 600 python bench.py --no-extras --no-logprobs > $O/a_nolp_unfused.json 2>> $O/a_bench.err
 timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > $O/a_reference.json 2>> $O/a_bench.err
 timeout 600 python bench.py --workload xe > $O/a_xe.json 2>> $O/a_bench.err
 BOFI_GRAPH=0 timeout 300 python tools/one_decode.py > $O/a_one_decode.log 2>&1 && \
