@@ -64,6 +64,9 @@ _SIGNATURES = {
     "bofi_train_step_xe": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I] + [_P] * 8),
     "bofi_train_set_dropout": (C.c_int, [_P, C.c_float, C.c_float, C.c_uint32]),
     "bofi_train_launches": (C.c_int, [_P]),
+    "bofi_sc_sample": (C.c_int, [_P, _P, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P]),
+    "bofi_sc_backward": (C.c_int, [_P, _P, _P, _P]),
+    "bofi_sc_inputs": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "bofi_train_set_grad_event": (C.c_int, [_P, _P]),
     "bofi_layernorm_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, _I]),
     "bofi_linear_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I]),

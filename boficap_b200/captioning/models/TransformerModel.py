@@ -56,6 +56,27 @@ class _XEForward(torch.autograd.Function):
         return None, None, None, None, None
 
 
+class _SCSample(torch.autograd.Function):
+    """Autograd bridge of sampling in train() mode (loss_wrapper.py:194-214): bofi_sc_sample returns the sampled captions and
+    their log-probs; the gradient of a structure loss w.r.t. those log-probs goes to bofi_sc_backward, which accumulates
+    straight into the flat gradient buffer (no gradient is returned to autograd for the parameters themselves)."""
+
+    @staticmethod
+    def forward(ctx, model, att_feats, att_len, mode, sample_n, anchor):
+        seq, logp, pnum, plen, psyn = model._engine.sc_sample(att_feats, att_len, mode, sample_n)
+        ctx.model = model
+        ctx.save_for_backward(logp)
+        ctx.mark_non_differentiable(seq, pnum, plen, psyn)
+        return seq, logp, pnum, plen, psyn
+
+    @staticmethod
+    def backward(ctx, g_seq, g_logp, g_pnum, g_plen, g_psyn):
+        (logp,) = ctx.saved_tensors
+        if g_logp is not None:
+            ctx.model._engine.sc_backward(g_logp, logp)
+        return None, None, None, None, None, None
+
+
 class TransformerModel(nn.Module):
     def __init__(self, opt):
         super().__init__()
@@ -236,6 +257,25 @@ class TransformerModel(nn.Module):
             return None
         return self._engine.masks_to_len(att_masks.data)    # a non-prefix mask is reported by the next check_masks()
 
+    def _sample_with_tape(self, att_feats, att_masks, train_mode, sample_n, temperature, output_logsoftmax):
+        """`_sample` as self-critical training calls it (train() mode, sample_method='sample', gradients enabled,
+        loss_wrapper.py:194-214): the returned seq_logprobs are differentiable w.r.t. the parameters (bofi_sc_sample /
+        bofi_sc_backward); dropout is on like in every other training forward."""
+        if not output_logsoftmax:
+            raise NotImplementedError("sampling with a tape returns log-softmax outputs (output_logsoftmax=1, what nscl uses)")
+        eng = self._train_engine(att_feats)
+        att_len = self._train_att_len(att_masks)
+        eng.set_sampling("sample", temperature, int(torch.randint(0, 2 ** 31 - 1, (1,))))
+        stream = torch.cuda.current_stream(att_feats.device)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        anchor = next(self.parameters())
+        seq, logp, pnum, plen, psyn = _SCSample.apply(self, att_feats.float(), att_len, train_mode, sample_n, anchor)
+        eng.set_sampling("greedy")
+        ev1.record(stream)
+        ev1.synchronize()
+        return seq, logp, pnum, plen, psyn, ev0.elapsed_time(ev1) * 1e-3
+
     def sample_stats(self, fc_feats, att_feats, att_masks=None, opt={}):
         """`_sample` for evaluation loops that only need captions, entropy and perplexity (eval_utils.py:176-184): the
         [B, L, V] log-prob tensor is never materialised, the two statistics come out of the vocab epilogue.
@@ -262,6 +302,8 @@ class TransformerModel(nn.Module):
             raise NotImplementedError("opt['train_mode'] must be 'NAIC' or 'SAIC' for the BoFi model, got %r" % train_mode)
         if not att_feats.is_cuda:
             raise RuntimeError("boficap_b200 runs on CUDA tensors only (no CPU fallback)")
+        if self.training and torch.is_grad_enabled() and sample_method == "sample":
+            return self._sample_with_tape(att_feats, att_masks, train_mode, sample_n, temperature, output_logsoftmax)
         eng = self.engine(att_feats.device, opt.get("bofi_precision"))
         att_len = None
         if att_masks is not None:

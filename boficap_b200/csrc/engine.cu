@@ -844,12 +844,12 @@ static int run_graphed(bofi_engine* e, cudaStream_t s, bofi_engine::GraphSlot& g
   return BOFI_OK;
 }
 
+// The bounding phase of core_NAIC (:1823-1873): memory K/V of every decoder-style layer, state init, the bounding loop and the
+// (stale-index) fill window.  Leaves ext / last / vis_fill / the boxes in e->st.
 template <typename T>
-static int decode_naic(bofi_engine* e, cudaStream_t s, int sn, int output_logsoftmax, long long* seq, float* logprobs,
-                       int* phrase_num, int* phrase_length, long long* phrase_syn) {
+static int naic_bound_phase(bofi_engine* e, cudaStream_t s, int sn) {
   const bofi_config_t& c = e->cfg;
   const int rows = e->B * sn, Lb = e->Lb, L = e->L;
-  const int* mem_len = e->have_len ? e->attlen.as<int>() : nullptr;
   const int nb_layers = std::max(1, c.n_len);
   // memory K/V of every decoder-style layer, projected once (the reference re-projects per call)
   if (c.n_len == 0) {
@@ -878,12 +878,23 @@ static int decode_naic(bofi_engine* e, cudaStream_t s, int sn, int output_logsof
                                       (unsigned long long)(uintptr_t)e->flat_w, (unsigned long long)(uintptr_t)e->flat16.p};
   RC_TRY(run_graphed(e, s, e->g_bound, key, enqueue_bounding));
 
-  // filling step (decode_NA, :570-587): all L slots of every row in parallel
   {
     ProfScope prof(e, s, PC_OTHER, 0.0, 0.0);
     launch_k(fill_window_kernel, ceil_div(rows * L, 256), 256, 0, s, e->st, rows, L);
   }
   CU_TRY(cudaGetLastError());
+  return BOFI_OK;
+}
+
+template <typename T>
+static int decode_naic(bofi_engine* e, cudaStream_t s, int sn, int output_logsoftmax, long long* seq, float* logprobs,
+                       int* phrase_num, int* phrase_length, long long* phrase_syn) {
+  const bofi_config_t& c = e->cfg;
+  const int rows = e->B * sn, Lb = e->Lb, L = e->L;
+  const int* mem_len = e->have_len ? e->attlen.as<int>() : nullptr;
+  const int nb_layers = std::max(1, c.n_len);
+  RC_TRY(naic_bound_phase<T>(e, s, sn));
+  // filling step (decode_NA, :570-587): all L slots of every row in parallel
   float* x = e->x.as<float>();
   {
     ProfScope prof(e, s, PC_OTHER, 0.0, 0.0);

@@ -100,6 +100,10 @@ struct TrainState {
   // FFN hidden, positional encoding and head hidden; p_att = opt.drop_prob_lm after att_embed's ReLU.  Sites are numbered
   // in forward order from 0 every step; key(site) = drop_hash(seed, site); the backward pass reuses the keys.
   float p_sub = 0.f, p_att = 0.f;
+  // self-critical sampling (bofi_sc_sample): decoder inputs of the taped pass, copied out of the decode state
+  bool sc = false;
+  int sc_mode = 0;
+  int *sc_words = nullptr, *sc_vis = nullptr, *sc_total = nullptr;     // [N, T] word ids (SAIC) / visible keys; [N] committed words + 1
   cudaEvent_t grad_event = nullptr;   // bofi_train_set_grad_event: recorded once every gradient outside the encoder is final
   uint32_t seed = 0, site = 0;
   Drop d_att_embed;
@@ -285,7 +289,8 @@ static int t_bound_fwd(bofi_engine* e, cudaStream_t s, TrainState* ts, BoundTape
 // decode_SA / decode_NA (:520-530, :570-587) + decoder stack + final LayerNorm + vocab projection.
 template <typename T>
 static int t_dec_fwd(bofi_engine* e, cudaStream_t s, TrainState* ts, DecTape& dt, const int* word_ids, int const_word, const int* self_vis,
-                     int vis_bs, int vis_qs, float* logp_out, bool keep_logits) {
+                     int vis_bs, int vis_qs, float* logp_out, bool keep_logits, Sampler sampler = Sampler(), long long* seq_out = nullptr,
+                     const int* total_len = nullptr) {
   const bofi_config_t& c = e->cfg;
   const int N = ts->N, T_ = ts->T, Tb = ts->Tb, rows = N * T_;
   const int* mem_len = ts->att_len;
@@ -317,18 +322,18 @@ static int t_dec_fwd(bofi_engine* e, cudaStream_t s, TrainState* ts, DecTape& dt
   }
   RC_TRY((linear<T, float>(e, s, yf, kD, e->generator, nullptr, 0, logits, e->Vpad, rows, 0, nullptr)));
   if (logp_out) {
-    launch_k(vocab_epilogue_kernel, rows, kVocabThreads, 0, s, (const float*)logits, e->Vpad, e->V, logp_out, (long long*)nullptr,
-             (const int*)nullptr, 0, T_, 1, (int*)nullptr, Sampler(), (float*)nullptr, (float*)nullptr, 0, 0);
+    launch_k(vocab_epilogue_kernel, rows, kVocabThreads, 0, s, (const float*)logits, e->Vpad, e->V, logp_out, seq_out,
+             total_len, -1, T_, 1, (int*)nullptr, sampler, (float*)nullptr, (float*)nullptr, 0, 0);
     CU_TRY(cudaGetLastError());
   }
   return BOFI_OK;
 }
 
+// _prepare_feature_forward + encoder (once per image) + the memory K/V of every decoder-style layer, with tape and dropout.
 template <typename T>
-static int train_forward_impl(bofi_engine* e, cudaStream_t s, TrainState* ts, const float* att, const int* att_len, float* sa_len,
-                              float* sa_syn, float* sa_logp, float* na_len, float* na_syn, float* na_logp, bool fused_loss) {
+static int t_encode_fwd(bofi_engine* e, cudaStream_t s, TrainState* ts, const float* att, const int* att_len) {
   const bofi_config_t& c = e->cfg;
-  const int B = ts->B, R = ts->R, M = B * R, F = c.att_feat_size, N = ts->N, Tb = ts->Tb;
+  const int B = ts->B, R = ts->R, M = B * R, F = c.att_feat_size;
   // ---- _prepare_feature_forward + encoder (once per image) --------------------------------------------------
   const int* len_dev = nullptr;
   ts->have_len = (att_len != nullptr);
@@ -371,6 +376,7 @@ static int train_forward_impl(bofi_engine* e, cudaStream_t s, TrainState* ts, co
   RC_TRY(layernorm<T>(e, s, x, kD, e->enc_norm, memT, kD, M, nullptr, nullptr));
   // ---- memory K/V of the bounding layer and of every decoder layer, once -------------------------------------
   const int nb_layers = std::max(1, c.n_len);
+  ts->sc = false;
   ts->kv.assign(nb_layers + c.n_dec, nullptr);
   for (int l = 0; l < nb_layers + c.n_dec; ++l) {
     T* kv = aalloc<T>(ts, (size_t)M * 2 * kD); A_TRY(kv);
@@ -378,6 +384,15 @@ static int train_forward_impl(bofi_engine* e, cudaStream_t s, TrainState* ts, co
     const Lin& w = (l < nb_layers) ? e->lp[l].ca.kv : e->dec[l - nb_layers].ca.kv;
     RC_TRY((linear<T, T>(e, s, memT, kD, w, nullptr, 0, kv, 2 * kD, M, 0, nullptr)));
   }
+  return BOFI_OK;
+}
+
+template <typename T>
+static int train_forward_impl(bofi_engine* e, cudaStream_t s, TrainState* ts, const float* att, const int* att_len, float* sa_len,
+                              float* sa_syn, float* sa_logp, float* na_len, float* na_syn, float* na_logp, bool fused_loss) {
+  const bofi_config_t& c = e->cfg;
+  const int N = ts->N, Tb = ts->Tb;
+  RC_TRY(t_encode_fwd<T>(e, s, ts, att, att_len));
   // ---- index bookkeeping ---------------------------------------------------------------------------------------
   launch_k(xe_prepare_kernel, ceil_div(N, 128), 128, 0, s, (const int*)ts->labels, (const int*)ts->pnum, (const int*)ts->plen, N, Tb, ts->P,
            c.len_idx, ts->word_seq, ts->vis_b, ts->na_vis);
@@ -627,7 +642,8 @@ static int t_layer_bwd(bofi_engine* e, cudaStream_t s, TrainState* ts, const Lay
 // Backward of one decoder pass.  dz [rows, Vp64] = gradient w.r.t. the logits (pad columns zero).
 template <typename T>
 static int t_dec_bwd(bofi_engine* e, cudaStream_t s, TrainState* ts, DecTape& dt, T* dz, int ldz, const int* word_ids, bool const_word,
-                     const int* self_vis, int vis_bs, int vis_qs, float* dx, T* dxT, T* g1, T* g2, int first_pass) {
+                     const int* self_vis, int vis_bs, int vis_qs, float* dx, T* dxT, T* g1, T* g2, int first_pass, int word_stride = -1,
+                     int word_off = 0) {
   const bofi_config_t& c = e->cfg;
   const int N = ts->N, T_ = ts->T, Tb = ts->Tb, rows = N * T_;
   const int* mem_len = ts->att_len;
@@ -647,7 +663,8 @@ static int t_dec_bwd(bofi_engine* e, cudaStream_t s, TrainState* ts, DecTape& dt
     RC_TRY(embed_small_bwd(e, s, ts, dx, nullptr, 0, 0, c.bos_idx, T_, rows, G(e, "model.tgt_embed.lut.weight")));
   } else {
     ProfScope prof(e, s, PC_OTHER, 0.0, (double)rows * kD * 8);
-    launch_k(embed_bwd_kernel, ceil_div(rows, 8), 256, 0, s, (const float*)dx, word_ids, T_, 0, T_, rows, sq, G(e, "model.tgt_embed.lut.weight"));
+    launch_k(embed_bwd_kernel, ceil_div(rows, 8), 256, 0, s, (const float*)dx, word_ids, word_stride < 0 ? T_ : word_stride, word_off, T_, rows, sq,
+             G(e, "model.tgt_embed.lut.weight"));
   }
   CU_TRY(cudaGetLastError());
   RC_TRY(embed_small_bwd(e, s, ts, dx, ts->ext_syn, Tb, 1, 0, T_, rows, G(e, "model.syn_embed.lut.weight")));
@@ -760,6 +777,9 @@ static int t_bound_bwd(bofi_engine* e, cudaStream_t s, TrainState* ts, BoundTape
   return BOFI_OK;
 }
 
+template <typename T>
+static int t_encode_bwd(bofi_engine* e, cudaStream_t s, TrainState* ts, float* dx, T* dxT, T* g1, T* g2, int first_kv);
+
 // Backward of the whole step.  dz_sa / dz_na: logit gradients [N*T, Vp64] (T-typed, pad columns zero).
 template <typename T>
 static int train_backward_impl(bofi_engine* e, cudaStream_t s, TrainState* ts, T* dz_sa, T* dz_na, int ldz, const float* g_sa_len,
@@ -784,11 +804,21 @@ static int train_backward_impl(bofi_engine* e, cudaStream_t s, TrainState* ts, T
   RC_TRY(t_dec_bwd<T>(e, s, ts, ts->sa_d, dz_sa, ldz, ts->ext_seq, false, ts->sa_vis, T_, 1, dx, dxT, g1, g2, 0));
   RC_TRY(t_bound_bwd<T>(e, s, ts, ts->na_b, g_na_len, g_na_syn, na_len, na_syn, nullptr, ts->ext_syn, dx, dxT, g1, g2, 1));
   RC_TRY(t_bound_bwd<T>(e, s, ts, ts->sa_b, g_sa_len, g_sa_syn, sa_len, sa_syn, ts->word_seq, nullptr, dx, dxT, g1, g2, 0));
+  return t_encode_bwd<T>(e, s, ts, dx, dxT, g1, g2, 0);
+}
+
+// Backward of everything t_encode_fwd computed: the memory K/V projections of the layers [first_kv, ...) whose K/V gradients
+// the decoder-side passes left in ts->dkv, the encoder and att_embed.
+template <typename T>
+static int t_encode_bwd(bofi_engine* e, cudaStream_t s, TrainState* ts, float* dx, T* dxT, T* g1, T* g2, int first_kv) {
+  const bofi_config_t& c = e->cfg;
+  const int B = ts->B, R = ts->R, M = B * R, N = ts->N, Tb = ts->Tb, F = c.att_feat_size;
+  const int nb_layers = std::max(1, c.n_len);
   // memory K/V projections: g(kv weights) += dkv^T . mem ; d mem += dkv . Wkv   (accumulated in fp32)
   RC_TRY(ts->dmem.reserve((size_t)std::max(N * Tb, M) * kD * 4));
   float* dmem = ts->dmem.as<float>();
   CU_TRY(cudaMemsetAsync(dmem, 0, (size_t)M * kD * 4, s));
-  for (int l = 0; l < nb_layers + c.n_dec; ++l) {
+  for (int l = first_kv; l < nb_layers + c.n_dec; ++l) {
     const Lin& w = (l < nb_layers) ? e->lp[l].ca.kv : e->dec[l - nb_layers].ca.kv;
     const T* dkv = ts->dkv.as<T>() + (size_t)l * M * 2 * kD;
     RC_TRY(lin_bwd<T>(e, s, ts, w, (const T*)ts->memT, kD, dkv, 2 * kD, M, g1, kD));

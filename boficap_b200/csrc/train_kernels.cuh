@@ -273,6 +273,40 @@ xe_head2_dgrad_kernel(const float* __restrict__ dz, const float* __restrict__ hi
   dhid[(size_t)row * ld_out + c] = hid[i] > 0.f ? acc * gain : 0.f;
 }
 
+// rows (b, t) with t >= total[b] + off are set to zero (SAIC: slots that were never committed return zero log-probs,
+// TransformerModel.py:1883; their gradient is zero as well).  One warp per row.
+template <typename T>
+__global__ void __launch_bounds__(256)
+zero_tail_rows_kernel_t(T* __restrict__ x, const int* __restrict__ total, int off, int rows, int Tt, int ld) {
+  pdl_enter();
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int b = row / Tt, t = row - b * Tt;
+  if (t < total[b] + off) return;
+  T* p = x + (size_t)row * ld;
+  for (int c = lane; c < ld; c += 32) p[c] = from_float<T>(0.f);
+}
+__global__ void __launch_bounds__(256)
+zero_tail_rows_kernel(float* __restrict__ x, const int* __restrict__ total, int off, int rows, int Tt, int ld) {
+  pdl_enter();
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int b = row / Tt, t = row - b * Tt;
+  if (t < total[b] + off) return;
+  float* p = x + (size_t)row * ld;
+  for (int c = lane; c < ld; c += 32) p[c] = 0.f;
+}
+__global__ void clamp_min_i32_kernel(int* __restrict__ x, int lo, int n) {
+  pdl_enter();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = max(x[i], lo);
+}
+__global__ void fill_i32_kernel(int* __restrict__ x, int v, int n) {
+  pdl_enter();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = v;
+}
+
 // Backward of log_softmax over the vocabulary (Generator, TransformerModel.py:1315-1323):
 //   dz[row, v] = g[row, v] - exp(logp[row, v]) * sum_v g[row, v],  written as T with row pitch ldz (pad columns = 0).
 template <typename T>

@@ -265,6 +265,42 @@ class BofiEngine:
         self._train_keep = (att_feats, att_len, ints)
         return losses
 
+    # ---- self-critical sampling with a tape -------------------------------------
+    def sc_sample(self, att_feats, att_len=None, mode="NAIC", sample_n=1):
+        """bofi_sc_sample: (seq, logprobs, phrase_num, phrase_length, phrase_syn) for B * sample_n rows; the tape of the
+        encoder and of the scoring decoder pass stays in the handle until sc_backward."""
+        assert att_feats.is_cuda and att_feats.dtype == torch.float32
+        att_feats = att_feats.contiguous()
+        B, R, _ = att_feats.shape
+        rows, L, V, dev = B * sample_n, self.cfg.seq_length, self.cfg.tgt_vocab, self.device
+        if att_len is not None:
+            att_len = att_len.to(device=att_feats.device, dtype=torch.int32).contiguous()
+        seq = torch.empty(rows, L, dtype=torch.int64, device=dev)
+        logp = torch.empty(rows, L, V, dtype=torch.float32, device=dev)
+        pnum = torch.empty(rows, dtype=torch.int32, device=dev)
+        plen = torch.empty(rows, L, dtype=torch.int32, device=dev)
+        psyn = torch.empty(rows, L, dtype=torch.int64, device=dev)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bofi_sc_sample(self.handle, self._stream(), _lib.MODE[mode], sample_n, _ptr(att_feats), _ptr(att_len), B, R,
+                                               _ptr(seq), _ptr(logp), _ptr(pnum), _ptr(plen), _ptr(psyn)))
+        self._train_keep = (att_feats, att_len)
+        return seq, logp, pnum, plen, psyn
+
+    def sc_backward(self, g_logp, logp):
+        g_logp = g_logp.contiguous().float()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bofi_sc_backward(self.handle, self._stream(), _ptr(g_logp), _ptr(logp)))
+        self._train_keep = None
+
+    def sc_inputs(self, rows):
+        """Decoder inputs of the taped pass of the last sc_sample: (word_ids, syn_ids, visible keys) [rows, L], total [rows]."""
+        L, dev = self.cfg.seq_length, self.device
+        w, s_, v = (torch.empty(rows, L, dtype=torch.int32, device=dev) for _ in range(3))
+        t = torch.empty(rows, dtype=torch.int32, device=dev)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bofi_sc_inputs(self.handle, self._stream(), _ptr(w), _ptr(s_), _ptr(v), _ptr(t)))
+        return w, s_, v, t
+
     def train_set_dropout(self, p, p_att_embed, seed):
         _lib.check(self.lib.bofi_train_set_dropout(self.handle, float(p), float(p_att_embed), int(seed) & 0xFFFFFFFF))
 

@@ -219,6 +219,24 @@ int bofi_train_step_xe(bofi_handle_t h, void* stream, const float* att_feats, co
                        int32_t seq_per_img, int32_t L, int32_t P, const int32_t* labels, const int32_t* phrase_num,
                        const int32_t* phrase_length, const int32_t* phrase_syn, const int32_t* ext_syn, const int32_t* ext_seq,
                        const int32_t* sa_vis, float* losses);
+/* ---- self-critical training -----------------------------------------------------------
+ * AttModel._sample called in train() mode with sample_method='sample' (captioning/modules/loss_wrapper.py:194-214), whose
+ * seq_logprobs StructureLosses (captioning/modules/losses.py:157-176) back-propagates through.  bofi_sc_sample returns the
+ * reference's tuple for N = B * sample_n rows -- seq i64 [N, L], logprobs f32 [N, L, V] (log-softmax; SAIC: zeros where
+ * no word was committed), phrase_num i32 [N], phrase_length i32 [N, L], phrase_syn i64 [N, L] -- and keeps the tape of the
+ * differentiable part: the encoder and ONE decoder pass on the sampled boxes (NAIC) / the sampled words (SAIC).  Tokens
+ * are drawn with bofi_set_sampling's method / temperature / seed; dropout follows bofi_train_set_dropout.
+ * bofi_sc_backward(g_logprobs = d loss / d logprobs, logprobs as returned) accumulates the parameter gradients into the
+ * buffer bound by bofi_train_bind.  The boxes and the draws carry no gradient (argmax / multinomial in the reference too).
+ * att_feats dev f32 [B,R,att_feat_size]; att_len dev i32 [B] or NULL.  Needs N_len == 1 and bofi_train_bind. */
+int bofi_sc_sample(bofi_handle_t h, void* stream, int32_t mode, int32_t sample_n, const float* att_feats, const int32_t* att_len,
+                   int32_t B, int32_t R, int64_t* seq, float* logprobs, int32_t* phrase_num, int32_t* phrase_length,
+                   int64_t* phrase_syn);
+int bofi_sc_backward(bofi_handle_t h, void* stream, const float* g_logprobs, const float* logprobs);
+/* Decoder inputs of the taped pass of the last bofi_sc_sample (dev i32): word_ids / syn_ids / visible-key counts [N, L] and
+ * the committed word count + 1 per row [N] -- what a checker needs to restate the pass. */
+int bofi_sc_inputs(bofi_handle_t h, void* stream, int32_t* word_ids, int32_t* syn_ids, int32_t* vis, int32_t* total);
+
 /* Dropout of the reference's train() mode for the following training calls (0, 0 = off, the eval() arithmetic):
  *   p            opt.dropout: sub-layer outputs (TransformerModel.py:1363), attention probabilities (:1430), FFN hidden
  *                (:1478), positional encoding (:1506), bounding-head hidden (:376)

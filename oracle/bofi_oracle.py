@@ -592,7 +592,37 @@ def _fused_methods():
         na_logp = decode(torch.full_like(extend_phrase_seq, c.bos_idx), syn_mask)
         return sa_len, sa_syn, sa_logp, na_len, na_syn, na_logp
 
+    def forward_sc(self, att_feats, att_masks, word_ids, syn_ids, vis, sample_n, drop=None):
+        """The differentiable part of sampling in train() mode (AttModel._sample under loss_wrapper.py:194-214) in the CUDA
+        path's formulation (boficap_b200/csrc/train_abi.inl: sc_sample_impl): encoder once per image with dropout, then ONE
+        decoder pass on fixed inputs -- word_ids / syn_ids [N, L] (NAIC: bos everywhere + the syn label of every slot, the
+        decode_NA input :570-587; SAIC: the position-wise copied words of :1928-1948) under the prefix masks `vis` [N, L]
+        (visible keys per query slot) -- and the log-softmax of the generator.  N = B * sample_n rows, row n uses image
+        n // sample_n.  Returns log-probs [N, L, V]; autograd gives the oracle gradients of any loss on them."""
+        c = self.cfg
+        drop = drop or DropSim(0.0, 0.0, 0)
+        B, R = att_feats.shape[:2]
+        N, T = syn_ids.shape
+        drop.site = 0
+        m_att = drop.elem(B * R, c.d_model, drop.p_att).view(B, R, -1)
+        x = F.relu(self.lin("att_embed.0", att_feats.float())) * m_att
+        if att_masks is not None:
+            x = x * att_masks[:, :, None].to(x.dtype)
+            src_mask = att_masks.unsqueeze(-2)
+        else:
+            src_mask = torch.ones(B, 1, R, dtype=torch.bool)
+        for l in range(c.N_enc):
+            x = layer_d(self, "model.encoder.layers.%d" % l, "feed_forward", x, None, None, src_mask, drop, False)
+        memory = self.layer_norm("model.encoder.norm", x)
+        memory_n, src_n = memory.repeat_interleave(sample_n, 0), src_mask.repeat_interleave(sample_n, 0)
+        tgt_mask = torch.arange(T)[None, None, :] < vis.long()[:, :, None]
+        xin = self.decoder_input(word_ids.long(), syn_ids.long()) * drop.elem(N * T, c.d_model).view(N, T, -1)
+        for l in range(c.N_dec):
+            xin = layer_d(self, "model.decoder.layers.%d" % l, "feed_forward", xin, memory_n, src_n, tgt_mask, drop, True)
+        return F.log_softmax(self.logit(self.layer_norm("model.decoder.norm", xin)), dim=-1)
+
     BofiOracle.forward_xe_fused = forward_xe_fused
+    BofiOracle.forward_sc = forward_sc
 
 
 _fused_methods()

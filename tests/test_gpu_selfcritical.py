@@ -1,0 +1,130 @@
+"""GPU: sampling in train() mode with a tape (loss_wrapper.py:194-214, losses.py:157-176).
+
+The reference back-propagates a self-critical loss through the seq_logprobs that `_sample(sample_method='sample')` returns
+in train() mode.  What is differentiable there is one decoder pass on the sampled boxes / words; the CUDA path tapes exactly
+that pass (bofi_sc_sample / bofi_sc_backward).  The oracle restates it (BofiOracle.forward_sc) on the decoder inputs the
+library reports (bofi_sc_inputs), with the library's counter-based dropout masks reproduced bit for bit (DropSim), so the
+log-probs AND every parameter gradient of a new_self_critical-shaped loss are compared with dropout ON."""
+import numpy as np
+import pytest
+import torch
+
+from boficap_b200 import synth
+from boficap_b200.layout import BofiConfig
+from test_gpu_train import build_model, grad_report
+
+pytestmark = pytest.mark.gpu
+
+
+def sc_loss(logp, seq, reward):
+    """losses.py:157-176 (new_self_critical after the reward is known): -(log p(sampled word) * (reward - baseline)) averaged
+    over the sampled words (mask = seq > 0 shifted by one, as the reference builds it)."""
+    mask = (seq > 0).to(logp.dtype)
+    mask = torch.cat([mask.new_ones(mask.shape[0], 1), mask[:, :-1]], 1)
+    picked = logp.gather(2, seq.unsqueeze(2)).squeeze(2)
+    return -(picked * reward[:, None] * mask).sum() / mask.sum()
+
+
+def oracle_for_sc(calib):
+    from oracle.bofi_oracle import BofiOracle, OracleConfig
+    cfg = BofiConfig()
+    sd = synth.synth_state_dict(cfg, 0, calib)
+    for k, v in sd.items():
+        if k != "model.pos_embed.pe":
+            v.requires_grad_(True)
+    o = BofiOracle.__new__(BofiOracle)
+    o.sd, o.cfg, o.record, o.trace, o.device = sd, OracleConfig(**cfg.to_dict()), False, {}, torch.device("cpu")
+    return o, sd
+
+
+@pytest.mark.parametrize("mode,calib,adaptive", [("NAIC", "s_cap", False), ("SAIC", "s_cap", True)])
+def test_sc_sample_logprobs_and_gradients_match_oracle_fp32(mode, calib, adaptive):
+    from oracle.bofi_oracle import DropSim
+    cfg = BofiConfig()
+    B, R, sample_n, seed = 3, 14, 2, 91
+    from boficap_b200.captioning import models
+    infos = synth.make_infos(cfg)
+    opt = infos["opt"]
+    opt.vocab = infos["vocab"]
+    opt.bofi_precision = "fp32"
+    model = models.setup(opt)
+    model.load_state_dict(synth.synth_state_dict(cfg, 0, calib))
+    model = model.cuda().train()
+    model.bofi_dropout_seed = seed
+    model.train_bind()
+    fc, att, masks = synth.synth_inputs(B, R, seed=9, adaptive=adaptive)
+    kw = {"sample_method": "sample", "sample_n": sample_n, "train_mode": mode, "temperature": 1.0, "output_logsoftmax": 1}
+    torch.manual_seed(5)
+    model.zero_grad()
+    seq, logp, pnum, plen, psyn, _ = model(fc.cuda(), att.cuda(), masks.cuda() if masks is not None else None, opt=kw, mode="sample")
+    N = B * sample_n
+    assert seq.shape == (N, cfg.seq_length) and logp.shape == (N, cfg.seq_length, cfg.tgt_vocab) and logp.requires_grad
+    assert not seq.requires_grad and pnum.shape == (N,)
+    words, syns, vis, total = [t.cpu() for t in model._engine.sc_inputs(N)]
+    # the tape pass restated by the oracle, same dropout masks
+    o, sd = oracle_for_sc(calib)
+    ref = o.forward_sc(att, masks, words, syns, vis, sample_n, drop=DropSim(cfg.dropout, cfg.drop_prob_lm, seed))
+    got = logp.detach().cpu()
+    committed = torch.arange(cfg.seq_length)[None, :] < (total - 1)[:, None]
+    if mode == "SAIC":
+        assert (got[~committed] == 0).all()                                 # zeros where no word was committed (:1883)
+        err = (got[committed] - ref.detach()[committed]).abs().max().item()
+    else:
+        err = (got - ref.detach()).abs()
+        err = err[~torch.isnan(err)].max().item()
+    assert err < 1e-4, err
+    # sampled tokens are consistent with the boxes: padding beyond the committed words
+    assert (seq.cpu()[~committed] == 0).all()
+    assert torch.equal(plen.cpu().sum(1), (total - 1).to(plen.dtype).cpu())
+    # a new_self_critical-shaped loss: per-row reward, gradients of all parameters
+    reward = torch.linspace(-1.0, 1.0, N)
+    loss = sc_loss(logp, seq, reward.cuda())
+    loss.backward()
+    ref_for_loss = ref if mode == "NAIC" else torch.where(committed[:, :, None], ref, torch.zeros_like(ref))
+    loss_ref = sc_loss(ref_for_loss, seq.cpu(), reward)
+    loss_ref.backward()
+    assert abs(float(loss) - float(loss_ref)) < 1e-4 * max(1.0, abs(float(loss_ref)))
+    ref_grads = {k: (v.grad.detach().clone() if v.grad is not None else torch.zeros_like(v)) for k, v in sd.items() if k != "model.pos_embed.pe"}
+    worst, name, cos = grad_report(model, ref_grads)
+    assert worst < 2e-3 and cos > 0.99999, (worst, name, cos)
+    # parameters the sampled pass never touches keep a zero gradient (bounding head, its layer)
+    g = dict(model.named_parameters())["model.length_predictor.Length_classifier2.weight"].grad
+    assert float(g.abs().max()) == 0.0
+
+
+def test_sc_sample_n5_b256_bf16_runs_and_is_timed(capsys):
+    """The size self-critical training runs at (train_sample_n = 5): finite gradients, dropout and sampling reproducible per
+    seed, eval()/no_grad falls back to the plain decode path; the step is timed (reported, not asserted)."""
+    cfg = BofiConfig()
+    model, _ = build_model("bf16")
+    model.train()
+    model.train_bind()
+    B, R = 256, 36
+    fc, att, _ = synth.synth_inputs(B, R, seed=3)
+    fc, att = fc.cuda(), att.cuda()
+    res = {}
+    for mode in ("NAIC", "SAIC"):
+        kw = {"sample_method": "sample", "sample_n": 5, "train_mode": mode}
+        outs = []
+        for rep in range(3):
+            torch.manual_seed(11)
+            model.bofi_dropout_seed, model._train_steps = 21, 0
+            model.zero_grad()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            seq, logp, pnum, plen, psyn, _ = model(fc, att, None, opt=kw, mode="sample")
+            reward = torch.randn(seq.shape[0], device="cuda", generator=torch.Generator("cuda").manual_seed(1))
+            sc_loss(logp, seq, reward).backward()
+            e1.record()
+            torch.cuda.synchronize()
+            outs.append((seq.clone(), float(model.flat_grads().double().norm()), e0.elapsed_time(e1)))
+        assert torch.equal(outs[1][0], outs[2][0]) and outs[1][1] == pytest.approx(outs[2][1], rel=1e-3)
+        assert np.isfinite(outs[2][1]) and outs[2][1] > 0
+        res[mode] = outs[2][2]
+    with capsys.disabled():
+        print("\n[self-critical] B=256 x sample_n=5 (1280 rows), bf16, sample + loss + backward: NAIC %.2f ms, SAIC %.2f ms" % (res["NAIC"], res["SAIC"]))
+    model.eval()
+    with torch.no_grad():
+        out = model(fc[:4], att[:4], None, opt={"sample_method": "sample", "sample_n": 2, "train_mode": "NAIC"}, mode="sample")
+    assert not out[1].requires_grad and out[0].shape == (8, cfg.seq_length)

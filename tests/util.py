@@ -8,7 +8,7 @@ from boficap_b200 import synth
 from boficap_b200.layout import BofiConfig
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-GOLDEN_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith("xe_"))   # xe_*: test_oracle_golden_xe.py
+GOLDEN_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f.startswith(("naic", "saic")))   # xe_*: test_oracle_golden_xe.py, collate_*: test_data_pipeline.py
 _SD_CACHE = {}
 
 
