@@ -354,7 +354,11 @@ static cudaError_t launch_attention_mma(cudaStream_t s, dim3 grid, size_t smem, 
     if (err != cudaSuccess) return err;
     configured = smem;
   }
-  launch_k(attention_mma_kernel<KT>, grid, 128, smem, s, Q, ldq, K, V, ldkv, O, ldo, Tq, Tk, vis, vis_bs, vis_qs, vis_div, kv_div, scale, live, drop, seq_off, q_varlen);
+  // persistent: four CTAs per SM (register / shared-memory budget of the short key ranges), one for KT > 3
+  const int n_items = (int)(grid.x * grid.y), per_sm = (KT <= 3 && smem <= 56 * 1024) ? 4 : 1;
+  const int ctas = std::min(n_items, tc::num_sms() * per_sm);
+  launch_k(attention_mma_kernel<KT>, ctas, 128, smem, s, Q, ldq, K, V, ldkv, O, ldo, Tq, Tk, vis, vis_bs, vis_qs, vis_div, kv_div, scale, live, drop, seq_off,
+           q_varlen, n_items, (int)grid.x);
   return cudaGetLastError();
 }
 
@@ -940,6 +944,7 @@ static int decode_naic(bofi_engine* e, cudaStream_t s, int sn, int output_logsof
         ve.pz0 = want_stats ? base : nullptr;
         ve.sp = e->sampler;
         ve.fast_exp = want_stats ? 0 : 1;            // as vocab_epilogue_kernel: ex2.approx unless the entropy statistics are wanted
+        ve.need_lse = (want_stats || (logprobs && output_logsoftmax)) ? 1 : 0;   // greedy / sampled tokens alone need no sum-exp
         T* y = e->y.as<T>();
         RC_TRY(layernorm<T>(e, s, x, kD, e->dec_norm, y, kD, total, nullptr, nullptr));
         {

@@ -121,6 +121,7 @@ struct VocabEpi {
   float* pz0 = nullptr;      // [M] logit of column 0 (the token tail padding writes; statistics only, may be nullptr)
   Sampler sp;
   int fast_exp = 0;          // ex2.approx for the sum-exp (bf16 engine without entropy statistics)
+  int need_lse = 1;          // 0: greedy tokens only (no log-probs, no statistics): the epilogue skips every exponential
   float* out = nullptr;      // VMODE 2: caller's [M, ldo] tensor
   long long ldo = 0;
   const float* mx = nullptr; // VMODE 2: per-row max and log-sum-exp from vocab_merge_kernel
@@ -352,6 +353,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if constexpr (VMODE == 2) {
         if (ve.do_lsm && row_ok) { mx_row = ve.mx[row]; lse_row = ve.lse[row]; }
       }
+      if constexpr (VMODE == 1) {           // this warp's 128 bias values -> its (otherwise unused) staging tile
+        __syncwarp();
+        st_shared_v4(sbuf0 + (uint32_t)lane * 16u, __float_as_uint(bv.x), __float_as_uint(bv.y), __float_as_uint(bv.z), __float_as_uint(bv.w));
+        __syncwarp();
+      }
       PROF_WAIT(w_tfull, mbar_wait(smem_u32(&tmem_full_bar[as]), aph));
       tcgen05_fence_after();
 #pragma unroll
@@ -379,51 +385,76 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #endif
         if constexpr (VMODE == 1) {
           static_assert(VMODE != 1 || (CC == 32 && !RELU && !RESID && !REDUCE), "statistics epilogue: fp32 logits");
+          // z = accumulator + bias.  The bias of this warp's chunks sits in its staging tile (written once per tile below the
+          // accumulator wait): 8 broadcast ld.shared.v4 per chunk instead of 32 shuffles.
           float z[CC];
           if (full) {
 #pragma unroll
             for (int j = 0; j < CC; j += 4) {
-              const int src = i * (CC / 4) + j / 4;
-              z[j] = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bv.x, src);
-              z[j + 1] = __uint_as_float(r[j + 1]) + __shfl_sync(0xffffffffu, bv.y, src);
-              z[j + 2] = __uint_as_float(r[j + 2]) + __shfl_sync(0xffffffffu, bv.z, src);
-              z[j + 3] = __uint_as_float(r[j + 3]) + __shfl_sync(0xffffffffu, bv.w, src);
+              const float4 bq = ld_shared_v4(sbuf0 + (uint32_t)(i * CC + j) * 4u);
+              z[j] = __uint_as_float(r[j]) + bq.x;
+              z[j + 1] = __uint_as_float(r[j + 1]) + bq.y;
+              z[j + 2] = __uint_as_float(r[j + 2]) + bq.z;
+              z[j + 3] = __uint_as_float(r[j + 3]) + bq.w;
             }
           } else {
 #pragma unroll
             for (int j = 0; j < CC; ++j) z[j] = (n + j < N) ? __uint_as_float(r[j]) + bias[n + j] : -INFINITY;
           }
           if (n == 0 && ve.pz0 != nullptr && row_ok) ve.pz0[row] = z[0];
+          // chunk maximum (fmaxf skips NaNs; FMNMX3 takes two values per instruction)
           float cm = -INFINITY;
-          bool anynan = false;
 #pragma unroll
-          for (int j = 0; j < CC; ++j) { cm = fmaxf(cm, z[j]); anynan |= (z[j] != z[j]); }
-          if (anynan && vn == 0x7fffffff) {
-#pragma unroll
-            for (int j = CC - 1; j >= 0; --j) if (z[j] != z[j]) vn = n + j;
-          }
+          for (int j = 0; j < CC; j += 2) cm = fmaxf(cm, fmaxf(z[j], z[j + 1]));
           if (cm > vm) {                    // a strictly larger value: the row's first maximum so far lies in this chunk
 #pragma unroll
             for (int j = CC - 1; j >= 0; --j) if (z[j] == cm) vi = n + j;
-            const float sc = ve.fast_exp ? __expf(vm - cm) : expf(vm - cm);       // exp(-inf) = 0 on the first chunk
-            vs *= sc;
-            vt *= sc;
+            if (ve.need_lse) {
+              const float sc = ve.fast_exp ? exp2f((vm - cm) * 1.4426950408889634f) : expf(vm - cm);       // exp(-inf) = 0 on the first chunk
+              vs *= sc;
+              vt *= sc;
+            }
             vm = cm;
           }
-          if (ve.fast_exp) {
+          // NaNs are found through a sum they poison (one FADD / nothing extra per element) instead of a compare per element
+          float probe;
+          if (!ve.need_lse) {               // greedy pick without log-probs: no exponentials at all
+            float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-            for (int j = 0; j < CC; ++j) vs += __expf(z[j] - vm);
+            for (int j = 0; j < CC; j += 2) { a0 += z[j]; a1 += z[j + 1]; }
+            probe = full ? a0 + a1 : 0.f;   // (the masked tail holds -inf; its columns cannot be NaN-checked this way ...)
+            if (!full) {
+#pragma unroll
+              for (int j = 0; j < CC; ++j) if (z[j] != z[j]) probe = z[j];
+            }
+          } else if (ve.fast_exp) {
+            const float nvml = -vm * 1.4426950408889634f;
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < CC; j += 2) {
+              a0 += exp2f(fmaf(z[j], 1.4426950408889634f, nvml));
+              a1 += exp2f(fmaf(z[j + 1], 1.4426950408889634f, nvml));
+            }
+            probe = a0 + a1;
+            vs += probe;
           } else {
+            float a0 = 0.f;
 #pragma unroll
             for (int j = 0; j < CC; ++j) {
               const float ex = expf(z[j] - vm);
-              vs += ex;
+              a0 += ex;
               if (ve.pt != nullptr && (full || n + j < N)) vt = fmaf(ex, z[j], vt);
             }
+            probe = a0;
+            vs += a0;
+          }
+          if (probe != probe && vn == 0x7fffffff) {       // rare: locate the first NaN of the row (torch.max: a NaN wins)
+#pragma unroll
+            for (int j = CC - 1; j >= 0; --j) if (z[j] != z[j]) vn = n + j;
           }
           if (ve.sp.enabled) {
-#pragma unroll 4
-            for (int j = 0; j < CC; ++j) {
+#pragma unroll
+            for (int j = 0; j < CC; ++j) {       // fully unrolled: a partial unroll would index z[] dynamically and push it to local memory
               if (full || n + j < N) {
                 const float g = gumbel_score(ve.sp, z[j], row, n + j);
                 if (g > vgv) { vgv = g; vgi = n + j; vgz = z[j]; }

@@ -917,7 +917,7 @@ vocab_merge_kernel(tc::VocabEpi ve, int nparts, int M, int L, float* __restrict_
   }
   const bool has_nan = nan_at != 0x7fffffff;
   const float mx = has_nan ? __int_as_float(0x7fc00000) : m;
-  const float lse = logf(S);
+  const float lse = ve.need_lse ? logf(S) : 0.f;
   mx_out[row] = mx;
   lse_out[row] = lse;
   int tok = ve.sp.enabled ? gi : (has_nan ? nan_at : idx);

@@ -285,7 +285,7 @@ def test_documented_training_loop_with_optimizer_zero_grad():
     model, cfg = build_model("fp32")
     args, bt = batch_args(B, R, adaptive, seed, cfg)
     model.train_bind()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    opt = torch.optim.SGD(model.parameters(), lr=1e-3)
     probe = dict(model.named_parameters())["model.decoder.layers.0.feed_forward.w_1.weight"]
     snaps, losses, gnorms = [probe.detach().clone()], [], []
     for it in range(4):
@@ -317,11 +317,12 @@ def test_decode_after_train_bind_does_not_replay_stale_graphs():
     """bofi_train_bind frees the engine-owned parameter buffer: decode graphs captured before it must not be replayed."""
     cfg = BofiConfig()
     model, _ = build_model("fp32")
-    fc, att, _ = synth.synth_inputs(6, 36, seed=7)
+    fc, att, _ = synth.synth_inputs(16, 36, seed=7)
     kw = {"sample_method": "greedy", "train_mode": "NAIC"}
     outs = [model(fc.cuda(), att.cuda(), None, opt=kw, mode="sample") for _ in range(3)]      # eager, capture, replay
+    assert int(outs[0][3].sum()) > 0
     model.train_bind()
     again = [model(fc.cuda(), att.cuda(), None, opt=kw, mode="sample") for _ in range(3)]
     for o in again:
         assert torch.equal(o[0], outs[0][0]) and torch.equal(o[3], outs[0][3])
-        assert (o[1] - outs[0][1]).abs().max().item() < 1e-5
+        assert (torch.nan_to_num(o[1]) - torch.nan_to_num(outs[0][1])).abs().max().item() < 1e-5
