@@ -118,6 +118,7 @@ struct bofi_engine {
   bool ares = false;                   // BOFI_ARES=1: A-resident 2-CTA tiles for the wide K <= 512 GEMMs (measured slower)
   bool gemm2 = true;                   // 2-CTA (cta_group::2) 256 x 256 tile pairs for the wide GEMMs; BOFI_GEMM2=0: 1-CTA tiles
   int ln_fuse_min_rows = 4096;         // below this the panel LayerNorm would be repeated by too many CTAs
+  bool ln_fuse_small = false;          // BOFI_LNFUSE_SMALL=1: the same for the M <= 2048 launches of the bounding loop only (one launch less per LayerNorm)
   bool ln_fuse = false;                // BOFI_LNFUSE=1: LayerNorm fused into the consuming tcgen05 GEMM (gemm_ln_tc.cuh; measured slower, off)
   bool attn_simt_only = false;         // BOFI_ATTN=simt: generic FFMA attention kernel everywhere
   bool finalized = false;
@@ -332,7 +333,7 @@ template <typename T, typename TOut>
 static int ln_linear(bofi_engine* e, cudaStream_t s, const float* x, const Norm& n, const Lin& l, TOut* out, int ldc, int M, int relu,
                      const int* live, T* ybuf) {
   if constexpr (std::is_same<T, bf16>::value) {
-    if (e->use_tc && e->ln_fuse && l.K == kD && M >= e->ln_fuse_min_rows) {
+    if (e->use_tc && l.K == kD && ((e->ln_fuse && M >= e->ln_fuse_min_rows) || (e->ln_fuse_small && M <= 2048 && M >= 64))) {
       ProfScope prof(e, s, PC_GEMM_TC, 2.0 * M * l.N * l.K, 4.0 * M * l.K + 2.0 * l.N * l.K + (double)sizeof(TOut) * M * l.N, M, l.N, l.K);
       cudaError_t err = tc::gemm_ln_tc<TOut>(s, x, (size_t)kD, n.a, n.b, l.w16, l.b, out, ldc, M, l.N, relu, live, e->rows_dev);
       if (err != cudaSuccess) return fail(BOFI_ERR_CUDA, "LN-fused gemm M=%d N=%d: %s", M, l.N, cudaGetErrorString(err));
@@ -1308,6 +1309,8 @@ int bofi_create(const bofi_config_t* cfg, int device, bofi_handle_t* out) {
   const char* gl = getenv("BOFI_LNFUSE");
   e->ln_fuse = (gl && strcmp(gl, "1") == 0);
   if (const char* gm = getenv("BOFI_LNFUSE_MIN")) e->ln_fuse_min_rows = atoi(gm);
+  const char* gls = getenv("BOFI_LNFUSE_SMALL");
+  e->ln_fuse_small = (gls && strcmp(gls, "1") == 0);
   const char* gs = getenv("BOFI_SAIC");
   e->saic_full = (gs && strcmp(gs, "full") == 0);
   const char* gf = getenv("BOFI_VOCAB_FUSED");

@@ -99,8 +99,14 @@ def test_sc_sample_n5_b256_bf16_runs_and_is_timed(capsys):
     """The size self-critical training runs at (train_sample_n = 5): finite gradients, dropout and sampling reproducible per
     seed, eval()/no_grad falls back to the plain decode path; the step is timed (reported, not asserted)."""
     cfg = BofiConfig()
-    model, _ = build_model("bf16")
-    model.train()
+    from boficap_b200.captioning import models
+    infos = synth.make_infos(cfg)
+    opt = infos["opt"]
+    opt.vocab = infos["vocab"]
+    opt.bofi_precision = "bf16"
+    model = models.setup(opt)
+    model.load_state_dict(synth.synth_state_dict(cfg, 0, "s_cap"))    # s_cap: SAIC decodes full captions (s_real aborts at step 1)
+    model = model.cuda().train()
     model.train_bind()
     B, R = 256, 36
     fc, att, _ = synth.synth_inputs(B, R, seed=3)
