@@ -26,6 +26,7 @@
 #include "attention_mma.cuh"
 #include "train_kernels.cuh"
 #include "attention_bwd_mma.cuh"
+#include "bound_loop.cuh"
 
 using namespace bofi;
 
@@ -170,6 +171,8 @@ struct bofi_engine {
   const int* rows_dev = nullptr;         // when set, linear() / layernorm() only process the first *rows_dev rows (SAIC compaction, varlen encoder)
   const int* varlen_total = nullptr;     // device row count of the varlen encoder (= seqoff + B + 1)
   int rows_hint = 0;                     // profiling runs: the host copy of *rows_dev of the varlen encoder (exact FLOP accounting)
+  bool bound_cluster = true;             // BOFI_BOUND_CLUSTER=0: the bounding loop as ~190 small launches in a CUDA graph (the round-1 path)
+  DevBuf bl_live;                        // bound_loop_kernel: live rows per CTA of every cluster
   bool vocab_fused = true;               // BOFI_VOCAB_FUSED=0: materialise fp32 logits + vocab_epilogue_kernel (the round-1 path)
   DevBuf vpart;                          // fused vocabulary projection: per-(column tile, half, row) softmax / argmax records
   bool varlen = true;                    // BOFI_VARLEN=0: padded encoder (every GEMM / LN / attention over all B*R rows)
@@ -849,6 +852,48 @@ static int run_graphed(bofi_engine* e, cudaStream_t s, bofi_engine::GraphSlot& g
   return BOFI_OK;
 }
 
+// The whole bounding loop in one launch: clusters of 8 CTAs own 64 rows each (bound_loop.cuh).  bf16 engine, N_len == 1.
+static int bound_loop_launch(bofi_engine* e, cudaStream_t s, int rows, int sn, int nsteps) {
+  const bofi_config_t& c = e->cfg;
+  const Layer& ly = e->lp[0];
+  const int Lb = e->Lb, clusters = ceil_div(rows, kBlRows);
+  RC_TRY(e->bl_live.reserve((size_t)clusters * kBlCtas * 4));
+  BoundLoopParams p{};
+  p.w_so = ly.sa.o.w16; p.b_so = ly.sa.o.b;
+  p.w_q = ly.ca.q.w16; p.b_q = ly.ca.q.b;
+  p.w_co = ly.ca.o.w16; p.b_co = ly.ca.o.b;
+  p.w_1 = ly.w1.w16; p.b_1 = ly.w1.b;
+  p.w_2 = ly.w2.w16; p.b_2 = ly.w2.b;
+  p.ln1_a = ly.ln[1].a; p.ln1_b = ly.ln[1].b; p.ln2_a = ly.ln[2].a; p.ln2_b = ly.ln[2].b;
+  p.lnh_a = e->lp_norm.a; p.lnh_b = e->lp_norm.b;
+  p.w1t = e->head1t.as<float>(); p.b1h = e->head1.b;
+  p.w_len = e->w_len2; p.b_len = e->b_len2; p.w_syn = e->w_syn2; p.b_syn = e->b_syn2;
+  p.tab_qkv = e->tab_qkv.as<bf16>();
+  p.q_row = c.len_idx * Lb;
+  p.x0 = e->bound_in.as<float>() + (size_t)p.q_row * kD;
+  p.kv = e->kv[0].as<bf16>();
+  p.mem_len = e->have_len ? e->attlen.as<int>() : nullptr;
+  p.mem_off = e->mem_off;
+  p.R = e->R; p.sn = sn;
+  p.x = e->x.as<float>(); p.ao = e->ao.as<bf16>(); p.q = e->q.as<bf16>(); p.ffh = e->ffh.as<bf16>();
+  p.cl_live = e->bl_live.as<int>();
+  p.st = e->st;
+  p.rows = rows; p.Lb = Lb; p.L = e->L; p.nsteps = nsteps; p.d_ff = c.d_ff;
+  p.hh = 100; p.n_len = 20; p.n_syn = 10; p.syn_lo = 4; p.syn_hi = 6;
+  static PerDevice<bool> configured_dev;
+  bool& configured = configured_dev.get();
+  if (!configured) {
+    CU_TRY(cudaFuncSetAttribute(bound_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlSmem));
+    configured = true;
+  }
+  // useful work of the loop (every step on every row; steps after a cluster's last live row are skipped on the device)
+  const double per_row = 2.0 * (3.0 * kD * kD + 2.0 * (double)c.d_ff * kD + 200.0 * kD);
+  ProfScope prof(e, s, PC_OTHER, per_row * rows * nsteps, 0.0, rows, nsteps, clusters);
+  launch_k(bound_loop_kernel, clusters * kBlCtas, kBlThreads, kBlSmem, s, p);
+  CU_TRY(cudaGetLastError());
+  return BOFI_OK;
+}
+
 // The bounding phase of core_NAIC (:1823-1873): memory K/V of every decoder-style layer, state init, the bounding loop and the
 // (stale-index) fill window.  Leaves ext / last / vis_fill / the boxes in e->st.
 template <typename T>
@@ -871,6 +916,16 @@ static int naic_bound_phase(bofi_engine* e, cudaStream_t s, int sn) {
   CU_TRY(cudaGetLastError());
   const char* dbg_steps = getenv("BOFI_DEBUG_MAX_BOUND_STEPS");   // timing experiments only (results are then wrong)
   const int nsteps = dbg_steps ? std::min(L, atoi(dbg_steps)) : L;
+  bool cluster_loop = false;
+  if constexpr (std::is_same<T, bf16>::value)
+    cluster_loop = e->bound_cluster && e->bound_fast && e->use_tc && c.d_ff % (kBlCtas * 64) == 0 && c.d_ff % kD == 0 && c.heads == 8 && e->R <= kMaxKeys;
+  if (cluster_loop) {
+    RC_TRY(bound_loop_launch(e, s, rows, sn, nsteps));
+    ProfScope prof(e, s, PC_OTHER, 0.0, 0.0);
+    launch_k(fill_window_kernel, ceil_div(rows * L, 256), 256, 0, s, e->st, rows, L);
+    CU_TRY(cudaGetLastError());
+    return BOFI_OK;
+  }
   auto enqueue_bounding = [&](cudaStream_t bs) -> int {
     for (int i = 0; i < nsteps; ++i) {
       if (e->bound_fast) RC_TRY(bounding_step_fast<T>(e, bs, rows, sn, i));
@@ -1313,6 +1368,8 @@ int bofi_create(const bofi_config_t* cfg, int device, bofi_handle_t* out) {
   e->ln_fuse_small = (gls && strcmp(gls, "1") == 0);
   const char* gs = getenv("BOFI_SAIC");
   e->saic_full = (gs && strcmp(gs, "full") == 0);
+  const char* gbc = getenv("BOFI_BOUND_CLUSTER");
+  e->bound_cluster = !(gbc && strcmp(gbc, "0") == 0);
   const char* gf = getenv("BOFI_VOCAB_FUSED");
   e->vocab_fused = !(gf && strcmp(gf, "0") == 0);
   const char* gv = getenv("BOFI_VARLEN");
@@ -1341,7 +1398,7 @@ int bofi_destroy(bofi_handle_t e) {
   for (DevBuf& b : e->kv) b.release();
   DevBuf* all[] = {&e->bound_in, &e->fill_in, &e->attT, &e->x, &e->y, &e->qkv, &e->ao, &e->q, &e->ffh, &e->memT, &e->attlen,
                    &e->sa_mx, &e->sa_lse, &e->sa_cidx, &e->sa_cache, &e->sa_bcache, &e->sa_qkv0, &e->sa_x0, &e->head1t, &e->tab_y, &e->tab_qkv, &e->logits, &e->state_i32, &e->tok, &e->h_in, &e->h_len, &e->h_seq, &e->h_logp,
-                   &e->h_pnum, &e->h_plen, &e->h_psyn, &e->unit_a, &e->unit_w, &e->unit_o, &e->xpad, &e->seqoff, &e->maskflag, &e->vpart};
+                   &e->h_pnum, &e->h_plen, &e->h_psyn, &e->unit_a, &e->unit_w, &e->unit_o, &e->xpad, &e->seqoff, &e->maskflag, &e->vpart, &e->bl_live};
   for (DevBuf* b : all) b->release();
   delete e;
   return BOFI_OK;
