@@ -39,18 +39,34 @@ __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc, bo
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
 }
 
-// Persistent + double-buffered: a CTA walks work items (head, sequence) with stride gridDim.x and keeps TWO staging buffers:
-// the cp.async requests of item i+1 are in flight while the four warps run the MMAs of item i.  The one-item-per-CTA form it
-// replaces paid the whole global latency per item (ncu, round 2: 45 us for the encoder self-attention at B=1024 = 0.41 of
-// the HBM roofline, tensor pipe and DRAM both mostly idle); consecutive CTAs take consecutive heads of one sequence, i.e.
-// neighbouring 128-byte chunks of the same rows.
 template <int KT>
-__device__ __forceinline__ void attn_issue_loads(bf16* Ks, bf16* Vs, bf16* Qs, const bf16* __restrict__ Q, int ldq, const bf16* __restrict__ K,
-                                                 const bf16* __restrict__ V, int ldkv, int head, size_t qrow0, size_t kvrow0, int Tq, int Tk,
-                                                 int TQP, int tid) {
+__global__ void __launch_bounds__(128, KT <= 3 ? 8 : 1)     // short key ranges: cap registers at 64 so that eight CTAs share an SM
+attention_mma_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restrict__ K, const bf16* __restrict__ V, int ldkv,
+                     bf16* __restrict__ O, int ldo, int Tq, int Tk, const int* __restrict__ vis, int vis_bs, int vis_qs,
+                     int vis_div, int kv_div, float scale, const int* live_rows, Drop drop, const int* __restrict__ seq_off, int q_varlen) {
+  pdl_enter();
+  if (step_is_dead(live_rows)) return;
+  extern __shared__ __align__(16) uint8_t att_smem[];
   constexpr int TKP = KT * 16;
-  // 16-byte cp.async (L1 bypass; rows past the end zero-filled through the src-size operand): every request of the item is in
-  // flight at once
+  bf16* Ks = reinterpret_cast<bf16*>(att_smem);          // [TKP][72]
+  bf16* Vs = Ks + TKP * kAttPitch;                       // [TKP][72]
+  bf16* Qs = Vs + TKP * kAttPitch;                       // [TQP][72]
+  const int TQP = (Tq + 15) & ~15;
+  const int head = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // Varlen layout (seq_off != nullptr): the K/V rows of sequence j are the compact rows [seq_off[j], seq_off[j+1]);
+  // q_varlen: the queries are those same rows (encoder self-attention over the valid regions only).
+  size_t kvrow0 = (size_t)(b / kv_div) * Tk, qrow0 = (size_t)b * Tq;
+  if (seq_off) {
+    const int o0 = seq_off[b / kv_div];
+    Tk = min(Tk, seq_off[b / kv_div + 1] - o0);
+    kvrow0 = (size_t)o0;
+    if (q_varlen) { qrow0 = kvrow0; Tq = Tk; }
+  }
+  // All tiles are fetched with cp.async (16 bytes, L1 bypass; rows past the end zero-filled through the src-size
+  // operand): every request of the CTA is in flight at once and the global latency is paid once.  The register
+  // round trip it replaces (load, store, load, store ...) had the kernel stalled on long_scoreboard for 8 of every
+  // 15 issue slots (ncu, 57 us for the encoder self-attention).
   for (int idx = tid; idx < TKP * 8; idx += 128) {       // 8 x 16-byte chunks per row
     const int j = idx >> 3, c = (idx & 7) * 8;
     const bool ok = j < Tk;
@@ -63,67 +79,12 @@ __device__ __forceinline__ void attn_issue_loads(bf16* Ks, bf16* Vs, bf16* Qs, c
     const bool ok = t < Tq;
     cp_async_16(Qs + t * kAttPitch + c, Q + (qrow0 + (ok ? t : 0)) * ldq + head * kHeadDim + c, ok);
   }
-}
-
-template <int KT>
-__global__ void __launch_bounds__(128, KT <= 3 ? 4 : 1)
-attention_mma_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restrict__ K, const bf16* __restrict__ V, int ldkv,
-                     bf16* __restrict__ O, int ldo, int Tq_max, int Tk_max, const int* __restrict__ vis, int vis_bs, int vis_qs,
-                     int vis_div, int kv_div, float scale, const int* live_rows, Drop drop, const int* __restrict__ seq_off, int q_varlen,
-                     int n_items, int heads) {
-  pdl_enter();
-  if (step_is_dead(live_rows)) return;
-  extern __shared__ __align__(16) uint8_t att_smem[];
-  constexpr int TKP = KT * 16;
-  const int TQP = (Tq_max + 15) & ~15;
-  const int stage_elems = (2 * TKP + TQP) * kAttPitch;
-  bf16* stage0 = reinterpret_cast<bf16*>(att_smem);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, t4 = lane & 3;
-
-  // Varlen layout (seq_off != nullptr): the K/V rows of sequence j are the compact rows [seq_off[j], seq_off[j+1]);
-  // q_varlen: the queries are those same rows (encoder self-attention over the valid regions only).
-  auto item_geometry = [&](int item, int& head, int& b, size_t& qrow0, size_t& kvrow0, int& Tq, int& Tk) {
-    head = item % heads;
-    b = item / heads;
-    Tq = Tq_max;
-    Tk = Tk_max;
-    kvrow0 = (size_t)(b / kv_div) * Tk_max;
-    qrow0 = (size_t)b * Tq_max;
-    if (seq_off) {
-      const int o0 = seq_off[b / kv_div];
-      Tk = min(Tk_max, seq_off[b / kv_div + 1] - o0);
-      kvrow0 = (size_t)o0;
-      if (q_varlen) { qrow0 = kvrow0; Tq = Tk; }
-    }
-  };
-
-  int item = blockIdx.x;
-  if (item >= n_items) return;
-  int head, b, Tq, Tk;
-  size_t qrow0, kvrow0;
-  item_geometry(item, head, b, qrow0, kvrow0, Tq, Tk);
-  attn_issue_loads<KT>(stage0, stage0 + TKP * kAttPitch, stage0 + 2 * TKP * kAttPitch, Q, ldq, K, V, ldkv, head, qrow0, kvrow0, Tq, Tk, TQP, tid);
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  for (int it = 0; item < n_items; ++it, item += gridDim.x) {
-    bf16* Ks = stage0 + (it & 1) * stage_elems;          // [TKP][72]
-    bf16* Vs = Ks + TKP * kAttPitch;                     // [TKP][72]
-    bf16* Qs = Vs + TKP * kAttPitch;                     // [TQP][72]
-    // prefetch the next item into the other buffer (its previous reader finished before the barrier that ended the last trip)
-    const int nxt = item + gridDim.x;
-    int nhead = 0, nb_ = 0, nTq = 0, nTk = 0;
-    size_t nq0 = 0, nkv0 = 0;
-    if (nxt < n_items) {
-      item_geometry(nxt, nhead, nb_, nq0, nkv0, nTq, nTk);
-      bf16* nK = stage0 + ((it + 1) & 1) * stage_elems;
-      attn_issue_loads<KT>(nK, nK + TKP * kAttPitch, nK + 2 * TKP * kAttPitch, Q, ldq, K, V, ldkv, nhead, nq0, nkv0, nTq, nTk, TQP, tid);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 1;" ::: "memory");  // everything but the prefetch just issued has landed
-    __syncthreads();
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
   const uint32_t ks_base = (uint32_t)__cvta_generic_to_shared(Ks);
   const uint32_t vs_base = (uint32_t)__cvta_generic_to_shared(Vs);
   const uint32_t qs_base = (uint32_t)__cvta_generic_to_shared(Qs);
+  const int g = lane >> 2, t4 = lane & 3;
 
   for (int m0 = warp * 16; m0 < Tq; m0 += 64) {
     // ---- Q fragments (16 x 64) ----
@@ -217,13 +178,10 @@ attention_mma_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restrict
       if (r1 < Tq) *reinterpret_cast<uint32_t*>(O + (qrow0 + r1) * ldo + c) = pack2_bf16(oacc[nt][2] * inv1, oacc[nt][3] * inv1);
     }
   }
-    __syncthreads();                      // every warp is done with this buffer before the next trip prefetches into it
-    head = nhead; b = nb_; qrow0 = nq0; kvrow0 = nkv0; Tq = nTq; Tk = nTk;
-  }
 }
 
-inline size_t attention_mma_smem_bytes(int KT, int Tq) {      // two staging buffers (item i computes, item i+1 loads)
-  return 2 * (size_t)(2 * KT * 16 + ((Tq + 15) & ~15)) * kAttPitch * 2;
+inline size_t attention_mma_smem_bytes(int KT, int Tq) {
+  return (size_t)(2 * KT * 16 + ((Tq + 15) & ~15)) * kAttPitch * 2;
 }
 
 // Single-query attention (the [LEN] row against the image regions in the bounding step): one warp per

@@ -17,6 +17,17 @@
 // LayerNorm is fused into the staging of the A operand (each CTA normalises the 64 rows it is about to multiply), residual
 // adds are in the GEMM epilogues, activations move between phases through L2 (x fp32, ao / q / ffh bf16) under
 // barrier.cluster release / acquire.  tcgen05 would need M = 128 rows per CTA; the point here is latency, not tensor peak.
+//
+// MEASURED (B200, round 2, profiles/r02d_*): parity-green (tests/test_gpu_decode.py::test_cluster_bounding_loop_matches_launch_chain)
+// and one launch instead of ~190 -- but SLOWER than the chain it replaces, so it is opt-in (BOFI_BOUND_CLUSTER=1):
+//   B = 1024: 3.84 ms for the loop (200 us per step) -> 128.6 k captions/s against 184.5 k with the launch chain (7.96 vs 5.55 ms/step)
+//   B = 1:    2.08 ms per decode against 1.92 ms; B = 32: 2.80 vs 2.24 ms; B = 512: 4.65 vs 3.98 ms
+// A step is a chain of ~25 "issue loads, wait for the last byte, compute" stages (11 GEMM units, two attention phases with
+// four sequential (row, head) tasks per warp, two LayerNorm stagings, a 16-round-trip head) with nothing prefetched across a
+// stage: ~95 us per step even for one cluster, i.e. the latency per step of the launch chain, and under the L2 contention of
+// 128 CTAs twice that.  The launch chain spreads each of those stages over all 148 SMs.  What would make this form win is
+// prefetching the (activation-independent) weight slices one unit ahead and batching the per-task loads of the row phases;
+// ncu: issue active 26 %, tensor pipe 5 %, DRAM 0.3 %.
 #pragma once
 #include "attention_mma.cuh"
 #include "gemm_tc2.cuh"

@@ -171,7 +171,7 @@ struct bofi_engine {
   const int* rows_dev = nullptr;         // when set, linear() / layernorm() only process the first *rows_dev rows (SAIC compaction, varlen encoder)
   const int* varlen_total = nullptr;     // device row count of the varlen encoder (= seqoff + B + 1)
   int rows_hint = 0;                     // profiling runs: the host copy of *rows_dev of the varlen encoder (exact FLOP accounting)
-  bool bound_cluster = true;             // BOFI_BOUND_CLUSTER=0: the bounding loop as ~190 small launches in a CUDA graph (the round-1 path)
+  bool bound_cluster = false;            // BOFI_BOUND_CLUSTER=1: the bounding loop as ONE cluster kernel (bound_loop.cuh; parity-green, measured slower: off)
   DevBuf bl_live;                        // bound_loop_kernel: live rows per CTA of every cluster
   bool vocab_fused = true;               // BOFI_VOCAB_FUSED=0: materialise fp32 logits + vocab_epilogue_kernel (the round-1 path)
   DevBuf vpart;                          // fused vocabulary projection: per-(column tile, half, row) softmax / argmax records
@@ -358,11 +358,10 @@ static cudaError_t launch_attention_mma(cudaStream_t s, dim3 grid, size_t smem, 
     if (err != cudaSuccess) return err;
     configured = smem;
   }
-  // persistent: four CTAs per SM (register / shared-memory budget of the short key ranges), one for KT > 3
-  const int n_items = (int)(grid.x * grid.y), per_sm = (KT <= 3 && smem <= 56 * 1024) ? 4 : 1;
-  const int ctas = std::min(n_items, tc::num_sms() * per_sm);
-  launch_k(attention_mma_kernel<KT>, ctas, 128, smem, s, Q, ldq, K, V, ldkv, O, ldo, Tq, Tk, vis, vis_bs, vis_qs, vis_div, kv_div, scale, live, drop, seq_off,
-           q_varlen, n_items, (int)grid.x);
+  // One (head, sequence) per CTA.  A persistent, double-buffered form of this kernel (cp.async prefetch of the next item
+  // under the MMAs of the current one, four CTAs per SM) was built and measured in round 2: 47.8 us against 45.6 us for the
+  // encoder self-attention at B = 1024 and slower at R = 100 -- the kernel is not latency-bound -- so this form stays.
+  launch_k(attention_mma_kernel<KT>, grid, 128, smem, s, Q, ldq, K, V, ldkv, O, ldo, Tq, Tk, vis, vis_bs, vis_qs, vis_div, kv_div, scale, live, drop, seq_off, q_varlen);
   return cudaGetLastError();
 }
 
@@ -1369,7 +1368,7 @@ int bofi_create(const bofi_config_t* cfg, int device, bofi_handle_t* out) {
   const char* gs = getenv("BOFI_SAIC");
   e->saic_full = (gs && strcmp(gs, "full") == 0);
   const char* gbc = getenv("BOFI_BOUND_CLUSTER");
-  e->bound_cluster = !(gbc && strcmp(gbc, "0") == 0);
+  e->bound_cluster = (gbc && strcmp(gbc, "1") == 0);
   const char* gf = getenv("BOFI_VOCAB_FUSED");
   e->vocab_fused = !(gf && strcmp(gf, "0") == 0);
   const char* gv = getenv("BOFI_VARLEN");

@@ -237,3 +237,40 @@ def test_fast_len_row_bounding_equals_full_layer_formulation(monkeypatch):
         assert la < lb
         fast.close()
         full.close()
+
+
+def test_cluster_bounding_loop_matches_launch_chain(monkeypatch, capsys):
+    """bf16 engine: the bounding loop as ONE cluster kernel (bound_loop.cuh: 8 CTAs per 64 rows, mma.sync GEMMs) against the
+    chain of ~190 small launches it replaces (BOFI_BOUND_CLUSTER=0: tcgen05 GEMMs, separate LayerNorm / attention kernels).
+    Same arithmetic up to the accumulation order: boxes agree on almost every image; where they do, tokens and logits agree
+    like two bf16 runs do.  Ragged cluster (rows % 64 != 0), sample_n > 1 and padded regions are covered."""
+    from boficap_b200.engine import BofiEngine
+    cfg = BofiConfig()
+    sd = checkpoint(cfg, "s_cap")
+    monkeypatch.setenv("BOFI_BOUND_CLUSTER", "1")              # opt-in: measured slower than the launch chain (bound_loop.cuh)
+    new = BofiEngine(cfg, 0, "bf16").load_state_dict(sd)
+    monkeypatch.delenv("BOFI_BOUND_CLUSTER")
+    old = BofiEngine(cfg, 0, "bf16").load_state_dict(sd)
+    ref32 = engine_for(cfg, "s_cap", "fp32")
+    for (B, R, adaptive, sn) in ((70, 36, False, 2), (200, 60, True, 1), (3, 36, False, 1)):
+        fc, att, masks = synth.synth_inputs(B, R, seed=40 + B, adaptive=adaptive)
+        a = run_cuda(new, att, masks, sample_n=sn, output_logsoftmax=0)
+        la = new.decode_info()
+        b = run_cuda(old, att, masks, sample_n=sn, output_logsoftmax=0)
+        lb = old.decode_info()
+        f = run_cuda(ref32, att, masks, sample_n=sn, output_logsoftmax=0)
+        same = ((a[3] == b[3]).all(1) & (a[4] == b[4]).all(1))
+        vs32_new = ((a[3] == f[3]).all(1) & (a[4] == f[4]).all(1)).float().mean().item()
+        vs32_old = ((b[3] == f[3]).all(1) & (b[4] == f[4]).all(1)).float().mean().item()
+        with capsys.disabled():
+            print("\n[cluster bounding loop] B=%d R=%d sample_n=%d: boxes equal to the launch chain on %.1f%% of rows; vs fp32: cluster %.1f%%, chain %.1f%%; "
+                  "launches %d vs %d, S %d vs %d" % (B, R, sn, 100 * same.float().mean().item(), 100 * vs32_new, 100 * vs32_old, la["kernel_launches"],
+                                                     lb["kernel_launches"], la["bounding_steps"], lb["bounding_steps"]))
+        assert same.float().mean().item() >= 0.9
+        assert vs32_new >= vs32_old - 0.05                 # as close to the fp32 boxes as the chain is
+        assert la["kernel_launches"] < lb["kernel_launches"] - 100
+        if bool(a[3][-1].sum() == b[3][-1].sum()) and same.any():
+            err = torch.nan_to_num(a[1][same] - b[1][same]).abs().max().item()
+            assert err < 2e-2, err
+    new.close()
+    old.close()
