@@ -315,7 +315,10 @@ class TransformerModel(nn.Module):
             # torch.manual_seed makes a run reproducible
             eng.set_sampling("sample", temperature, int(torch.randint(0, 2 ** 31 - 1, (1,))))
         else:
-            raise NotImplementedError("sample_method=%r: only 'greedy' and 'sample' (the uic_sd* configs) are built" % sample_method)
+            # CaptionModel.py:391-421: the 'gumbel' and 'top<k|p>' branches reduce over dim=1, which for the BoFi model's
+            # [B, L, V] log-probs is the SLOT axis (they were written for the 2-D AIC log-probs): undefined for UIC in the reference
+            raise NotImplementedError("sample_method=%r: only 'greedy' and 'sample' are defined for the BoFi model (the reference's "
+                                      "gumbel / top-k / nucleus branches reduce over the slot axis of [B, L, V])" % sample_method)
         if att_feats.dtype not in (torch.float32, torch.bfloat16, torch.float16):
             att_feats = att_feats.float()
         # `elapsed` (AttModel.py:337, :425: wall clock between two device synchronisations around the core) comes from two
