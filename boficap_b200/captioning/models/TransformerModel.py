@@ -218,8 +218,9 @@ class TransformerModel(nn.Module):
         self._reattach_grads()
         eng = self.engine(att_feats.device)
         # nn.Module.train() / eval() decide, as for the reference's nn.Dropout modules
+        self._step_seed = self.bofi_dropout_seed + self._train_steps      # also seeds the glancing draws of this step
         if self.training:
-            eng.train_set_dropout(self.cfg.dropout, self.cfg.drop_prob_lm, self.bofi_dropout_seed + self._train_steps)
+            eng.train_set_dropout(self.cfg.dropout, self.cfg.drop_prob_lm, self._step_seed)
             self._train_steps += 1
         else:
             eng.train_set_dropout(0.0, 0.0, 0)
@@ -229,12 +230,11 @@ class TransformerModel(nn.Module):
                  extend_phrase_syn_seq=None, extend_phrase_seq=None, extend_phrase_seq_mask=None, glat_p=-1.0):
         """TransformerModel._forward, train_mode UIC (TransformerModel.py:1713-1775): the six log-prob tensors
         (SA length / syn / word, NA length / syn / word), differentiable w.r.t. the parameters."""
-        if glat_p >= 0:
-            raise NotImplementedError("glat_p >= 0 (glancing sampling, TransformerModel.py:437-464) is not built; "
-                                      "the reference default for _forward is glat_p = -1")
         if self.ss_prob > 0:
             raise NotImplementedError("scheduled sampling (ss_prob > 0, TransformerModel.py:1759-1766) is not built")
-        self._train_engine(att_feats)
+        eng = self._train_engine(att_feats)
+        # glancing (TransformerModel.py:437-464): the keep draws use the library's counter-based stream, seeded like dropout
+        eng.train_set_glat(glat_p, self._step_seed)
         batch = self._xe_batch(att_feats, seq, phrase_num, phrase_length, phrase_syn, extend_phrase_syn_seq, extend_phrase_seq,
                                extend_phrase_seq_mask)
         att_len = self._train_att_len(att_masks)
@@ -242,11 +242,12 @@ class TransformerModel(nn.Module):
         return _XEForward.apply(self, att_feats.float(), att_len, batch, anchor)
 
     def xe_step(self, fc_feats, att_feats, seq, att_masks=None, phrase_num=None, phrase_length=None, phrase_syn=None,
-                extend_phrase_syn_seq=None, extend_phrase_seq=None, extend_phrase_seq_mask=None):
+                extend_phrase_syn_seq=None, extend_phrase_seq=None, extend_phrase_seq_mask=None, glat_p=-1.0):
         """One XE training step's forward + LanguageModelCriterion_UIC(reduction='mean') + backward in a single library
         call (bofi_train_step_xe): gradients are accumulated into the parameters' `.grad`; returns the criterion's seven
         values (total, SA_length, SA_phrase, SA_syn, NA_length, NA_phrase, NA_syn) as a device tensor."""
         eng = self._train_engine(att_feats)
+        eng.train_set_glat(glat_p, self._step_seed)
         batch = self._xe_batch(att_feats, seq, phrase_num, phrase_length, phrase_syn, extend_phrase_syn_seq, extend_phrase_seq,
                                extend_phrase_seq_mask)
         att_len = self._train_att_len(att_masks)

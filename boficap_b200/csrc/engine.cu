@@ -173,7 +173,6 @@ struct bofi_engine {
   int rows_hint = 0;                     // profiling runs: the host copy of *rows_dev of the varlen encoder (exact FLOP accounting)
   bool bound_cluster = false;            // BOFI_BOUND_CLUSTER=1: the bounding loop as ONE cluster kernel (bound_loop.cuh; parity-green, measured slower: off)
   DevBuf bl_live;                        // bound_loop_kernel: live rows per CTA of every cluster
-  bool vocab_vec_store = true;           // BOFI_VOCAB_VEC=0: second vocabulary pass with 4-byte row stores (the first form)
   bool vocab_fused = true;               // BOFI_VOCAB_FUSED=0: materialise fp32 logits + vocab_epilogue_kernel (the round-1 path)
   DevBuf vpart;                          // fused vocabulary projection: per-(column tile, half, row) softmax / argmax records
   bool varlen = true;                    // BOFI_VARLEN=0: padded encoder (every GEMM / LN / attention over all B*R rows)
@@ -1020,7 +1019,6 @@ static int decode_naic(bofi_engine* e, cudaStream_t s, int sn, int output_logsof
           ve.mx = e->sa_mx.as<float>();
           ve.lse = e->sa_lse.as<float>();
           ve.do_lsm = output_logsoftmax;
-          ve.vec_store = (e->vocab_vec_store && (reinterpret_cast<uintptr_t>(logprobs) & 15) == 0) ? 1 : 0;
           ProfScope prof(e, s, PC_GEMM_TC, 2.0 * total * e->V * kD, 2.0 * ((double)total * kD + (double)e->V * kD) + 4.0 * total * e->V, total, e->V, kD);
           cudaError_t err = tc::gemm_tc2_vocab(s, y, kD, e->generator.w16, kD, e->generator.b, total, e->V, kD, 2, ve);
           if (err != cudaSuccess) return fail(BOFI_ERR_CUDA, "vocabulary log-prob GEMM: %s", cudaGetErrorString(err));
@@ -1371,8 +1369,6 @@ int bofi_create(const bofi_config_t* cfg, int device, bofi_handle_t* out) {
   e->saic_full = (gs && strcmp(gs, "full") == 0);
   const char* gbc = getenv("BOFI_BOUND_CLUSTER");
   e->bound_cluster = (gbc && strcmp(gbc, "1") == 0);
-  const char* gvv = getenv("BOFI_VOCAB_VEC");
-  e->vocab_vec_store = !(gvv && strcmp(gvv, "0") == 0);
   const char* gf = getenv("BOFI_VOCAB_FUSED");
   e->vocab_fused = !(gf && strcmp(gf, "0") == 0);
   const char* gv = getenv("BOFI_VARLEN");

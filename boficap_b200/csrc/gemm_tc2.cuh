@@ -127,7 +127,6 @@ struct VocabEpi {
   const float* mx = nullptr; // VMODE 2: per-row max and log-sum-exp from vocab_merge_kernel
   const float* lse = nullptr;
   int do_lsm = 0;            // 0: raw logits (output_logsoftmax = 0)
-  int vec_store = 0;         // VMODE 2: 16-byte stores on the output's alignment grid (needs a 16-byte aligned `out`)
 };
 
 template <typename TOut, bool RELU, bool RESID, bool REDUCE = false, bool ARES = false, int KPS = 1, int VMODE = 0>
@@ -519,38 +518,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int j = 0; j < 8; ++j)
             st_shared_v4(srow + (uint32_t)((j ^ (lane & 7)) * 16), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
           __syncwarp();
-          if (ve.vec_store) {
-            // 16-byte stores on the OUTPUT's alignment grid: the caller's rows (pitch V floats) start at any 4-byte offset, so a
-            // row's 32 floats are a head of 4 - a floats, seven aligned groups and a tail of a floats (a = row start mod 4).
-            // Eight lanes per row, four rows per pass: lane `sub` takes aligned group `sub` (one st.global.v4), lane 7 the head
-            // and tail scalars; the four floats come out of the swizzled tile one by one (their offset is not 16-byte aligned).
-            const int sub = lane & 7, rsel = lane >> 3;
-            const size_t gbase = (size_t)(m0 + quad * 32) * (size_t)ve.ldo + (size_t)n;
-#pragma unroll 4
-            for (int ps = 0; ps < 8; ++ps) {
-              const int rr = ps * 4 + rsel;
-              const size_t g0 = gbase + (size_t)rr * (size_t)ve.ldo;
-              const int a = (int)(g0 & 3);
-              const bool grp = (a == 0) || (sub < 7);
-              int cidx[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) cidx[e] = grp ? ((a ? 4 - a : 0) + 4 * sub + e) : (e < 4 - a ? e : 28 + e);
-              float v[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[e]) : "r"(sbuf + (uint32_t)rr * 128u + (uint32_t)((((cidx[e] >> 2) ^ (rr & 7)) * 16) + (cidx[e] & 3) * 4)));
-              if (m0 + quad * 32 + rr < M) {
-                float* o = ve.out + g0;
-                if (grp && n + cidx[3] < N) {
-                  __stcs(reinterpret_cast<float4*>(o + cidx[0]), make_float4(v[0], v[1], v[2], v[3]));
-                } else {
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) if (n + cidx[e] < N) __stcs(o + cidx[e], v[e]);
-                }
-              }
-            }
-            continue;
-          }
+          // (16-byte stores on the output's alignment grid -- eight lanes per row, the four floats of a group fetched one by one
+          // from the swizzled tile -- were measured SLOWER than one 128-byte row segment per instruction: 486 vs 361 us.)
           const bool col_ok = n + lane < N;
           float* orow = ve.out + (size_t)(m0 + quad * 32) * (size_t)ve.ldo + (size_t)(n + lane);
 #pragma unroll 8

@@ -51,6 +51,10 @@ struct Arena {
     chunks.clear();
     cur = off = 0;
   }
+  // scratch passes (the no-grad glancing pass): everything allocated after mark() is handed back by rewind()
+  struct Mark { size_t cur, off, used_total; };
+  Mark mark() const { return Mark{cur, off, used_total}; }
+  void rewind(const Mark& m) { cur = m.cur; off = m.off; used_total = m.used_total; }
 };
 
 struct LayerTape {        // T-typed buffers are void*
@@ -104,6 +108,10 @@ struct TrainState {
   bool sc = false;
   int sc_mode = 0;
   int *sc_words = nullptr, *sc_vis = nullptr, *sc_total = nullptr;     // [N, T] word ids (SAIC) / visible keys; [N] committed words + 1
+  // glancing training (EncoderDecoder_UIC.forward with glat_p >= 0, :437-464): the NA decoder's word inputs
+  float glat_p = -1.f;
+  uint32_t glat_seed = 0;
+  int* glat_words = nullptr;      // [N, T] bos or the ground-truth word per slot (nullptr: glancing off, constant bos)
   cudaEvent_t grad_event = nullptr;   // bofi_train_set_grad_event: recorded once every gradient outside the encoder is final
   uint32_t seed = 0, site = 0;
   Drop d_att_embed;
@@ -321,7 +329,7 @@ static int t_dec_fwd(bofi_engine* e, cudaStream_t s, TrainState* ts, DecTape& dt
     dt.logits = nullptr;
   }
   RC_TRY((linear<T, float>(e, s, yf, kD, e->generator, nullptr, 0, logits, e->Vpad, rows, 0, nullptr)));
-  if (logp_out) {
+  if (logp_out || seq_out) {
     launch_k(vocab_epilogue_kernel, rows, kVocabThreads, 0, s, (const float*)logits, e->Vpad, e->V, logp_out, seq_out,
              total_len, -1, T_, 1, (int*)nullptr, sampler, (float*)nullptr, (float*)nullptr, 0, 0);
     CU_TRY(cudaGetLastError());
@@ -407,7 +415,26 @@ static int train_forward_impl(bofi_engine* e, cudaStream_t s, TrainState* ts, co
   RC_TRY(t_dec_fwd<T>(e, s, ts, ts->sa_d, ts->ext_seq, -1, ts->sa_vis, ts->T, 1, sa_logp, fused_loss));
   // ---- NA: bounding on the syn labels, decoder on BOS + syn labels ------------------------------------------
   RC_TRY(t_bound_fwd<T>(e, s, ts, ts->na_b, nullptr, ts->ext_syn, na_len, na_syn));
-  RC_TRY(t_dec_fwd<T>(e, s, ts, ts->na_d, nullptr, c.bos_idx, ts->na_vis, 1, 0, na_logp, fused_loss));
+  ts->glat_words = nullptr;
+  if (ts->glat_p >= 0.f) {
+    // Glancing (:437-464): a no-grad NA pass on constant bos inputs predicts the words; the fraction of mismatches times glat_p is
+    // the probability with which a slot's ground-truth word replaces bos in the input of the real (taped) NA pass.  The no-grad
+    // pass draws its own dropout masks like the reference's (it runs in train() mode there too) and leaves nothing on the tape.
+    const int T_ = ts->T;
+    int* words = aalloc<int>(ts, (size_t)N * T_); A_TRY(words);
+    long long* tok = aalloc<long long>(ts, (size_t)N * T_); A_TRY(tok);
+    const Arena::Mark mark = ts->arena.mark();
+    DecTape scratch;
+    RC_TRY(t_dec_fwd<T>(e, s, ts, scratch, nullptr, c.bos_idx, ts->na_vis, 1, 0, nullptr, false, Sampler(), tok, nullptr));
+    ts->arena.rewind(mark);
+    launch_k(glat_input_kernel, ceil_div(N, 8), 256, 0, s, (const int*)ts->labels, (const int*)ts->plen, (const long long*)tok, N, T_, Tb, c.bos_idx,
+             ts->glat_p, drop_hash(ts->glat_seed, 0x474C4154u), words);
+    CU_TRY(cudaGetLastError());
+    ts->glat_words = words;
+    RC_TRY(t_dec_fwd<T>(e, s, ts, ts->na_d, words, -1, ts->na_vis, 1, 0, na_logp, fused_loss));
+  } else {
+    RC_TRY(t_dec_fwd<T>(e, s, ts, ts->na_d, nullptr, c.bos_idx, ts->na_vis, 1, 0, na_logp, fused_loss));
+  }
   return BOFI_OK;
 }
 
@@ -800,7 +827,7 @@ static int train_backward_impl(bofi_engine* e, cudaStream_t s, TrainState* ts, T
   T* g1 = e->q.as<T>();
   T* g2 = e->ffh.as<T>();
   // the four decoder-style consumers of `memory`; the first one to touch a K/V gradient overwrites, the rest add
-  RC_TRY(t_dec_bwd<T>(e, s, ts, ts->na_d, dz_na, ldz, nullptr, true, ts->na_vis, 1, 0, dx, dxT, g1, g2, 1));
+  RC_TRY(t_dec_bwd<T>(e, s, ts, ts->na_d, dz_na, ldz, ts->glat_words, ts->glat_words == nullptr, ts->na_vis, 1, 0, dx, dxT, g1, g2, 1));
   RC_TRY(t_dec_bwd<T>(e, s, ts, ts->sa_d, dz_sa, ldz, ts->ext_seq, false, ts->sa_vis, T_, 1, dx, dxT, g1, g2, 0));
   RC_TRY(t_bound_bwd<T>(e, s, ts, ts->na_b, g_na_len, g_na_syn, na_len, na_syn, nullptr, ts->ext_syn, dx, dxT, g1, g2, 1));
   RC_TRY(t_bound_bwd<T>(e, s, ts, ts->sa_b, g_sa_len, g_sa_syn, sa_len, sa_syn, ts->word_seq, nullptr, dx, dxT, g1, g2, 0));

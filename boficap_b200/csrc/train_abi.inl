@@ -364,6 +364,15 @@ extern "C" int bofi_train_set_dropout(bofi_handle_t e, float p, float p_att_embe
   return BOFI_OK;
 }
 
+extern "C" int bofi_train_set_glat(bofi_handle_t e, float glat_p, uint32_t seed) {
+  if (!e) return fail(BOFI_ERR_INVALID, "null handle");
+  if (glat_p > 1.f) return fail(BOFI_ERR_INVALID, "glat_p %g (an unmasked-token ratio in [0, 1], < 0 = off)", glat_p);
+  TrainState* ts = train_state(e);
+  ts->glat_p = glat_p;
+  ts->glat_seed = seed;
+  return BOFI_OK;
+}
+
 extern "C" int bofi_train_set_grad_event(bofi_handle_t e, void* event) {
   if (!e) return fail(BOFI_ERR_INVALID, "null handle");
   train_state(e)->grad_event = (cudaEvent_t)event;

@@ -296,6 +296,33 @@ zero_tail_rows_kernel(float* __restrict__ x, const int* __restrict__ total, int 
   float* p = x + (size_t)row * ld;
   for (int c = lane; c < ld; c += 32) p[c] = 0.f;
 }
+// Glancing inputs (EncoderDecoder_UIC.forward :445-461): per caption row, mismatch = (#words - #correct predictions) / #words over
+// its real word slots, keep_prob = mismatch * glat_p there (0 elsewhere); slot t takes the ground-truth word when
+// u(row, t) < keep_prob and bos otherwise.  u is the library's counter-based uniform (the reference draws torch.rand).  One warp
+// per row.  labels [N, Tb] (words at 1..T), plen [N, Tb] (slot 0 = the bos pseudo-phrase), tok i64 [N, T] the no-grad predictions.
+__global__ void __launch_bounds__(256)
+glat_input_kernel(const int* __restrict__ labels, const int* __restrict__ plen, const long long* __restrict__ tok, int N, int T, int Tb, int bos,
+                  float glat_p, uint32_t key, int* __restrict__ words) {
+  pdl_enter();
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (n >= N) return;
+  int len = 0;
+  for (int j = lane; j < Tb; j += 32) len += plen[(size_t)n * Tb + j];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) len += __shfl_xor_sync(0xffffffffu, len, o);
+  len -= 1;
+  int same = 0;
+  for (int t = lane; t < T; t += 32) same += (t < len && (int)tok[(size_t)n * T + t] == labels[(size_t)n * Tb + 1 + t]) ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) same += __shfl_xor_sync(0xffffffffu, same, o);
+  const float mismatch = len > 0 ? (float)(len - same) / (float)len : 0.f;
+  for (int t = lane; t < T; t += 32) {
+    const float keep_prob = (t < len) ? mismatch * glat_p : 0.f;
+    const float u = ((float)drop_hash(key, (uint32_t)(n * T + t)) + 0.5f) * (1.0f / 4294967296.0f);
+    words[(size_t)n * T + t] = (u < keep_prob) ? labels[(size_t)n * Tb + 1 + t] : bos;
+  }
+}
+
 __global__ void clamp_min_i32_kernel(int* __restrict__ x, int lo, int n) {
   pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -309,6 +309,9 @@ class BofiEngine:
         self._grad_event_keep = event
         _lib.check(self.lib.bofi_train_set_grad_event(self.handle, C.c_void_p(event.cuda_event) if event is not None else None))
 
+    def train_set_glat(self, glat_p, seed=0):
+        _lib.check(self.lib.bofi_train_set_glat(self.handle, float(glat_p), int(seed) & 0xFFFFFFFF))
+
     def train_launches(self):
         return int(self.lib.bofi_train_launches(self.handle))
 

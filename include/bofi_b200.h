@@ -245,6 +245,11 @@ int bofi_sc_inputs(bofi_handle_t h, void* stream, int32_t* word_ids, int32_t* sy
  * regenerates them, and oracle/bofi_oracle.py:DropSim reproduces them bit for bit.  The positional-encoding mask of
  * the bounding input is drawn once per caption and shared by its bounding passes (the reference redraws it per pass). */
 int bofi_train_set_dropout(bofi_handle_t h, float p, float p_att_embed, uint32_t seed);
+/* Glancing training (EncoderDecoder_UIC.forward with glat_p >= 0, TransformerModel.py:437-464; configs/uic_glat_token.yaml) for
+ * the following bofi_train_forward / bofi_train_step_xe calls: a no-grad NA decoder pass predicts the words, and every real word
+ * slot of a caption takes its ground-truth word instead of bos as NA decoder input with probability
+ * (mismatched predictions / words) * glat_p, drawn from the library's counter-based stream seeded by `seed`.  glat_p < 0: off. */
+int bofi_train_set_glat(bofi_handle_t h, float glat_p, uint32_t seed);
 /* Gradient all-reduce overlap (tools/train.py:99-101 runs the reference under nn.DataParallel; here: one process per GPU).
  * `event` (a cudaEvent_t, NULL switches it off) is recorded on the training stream inside every following backward pass at
  * the point where all gradients EXCEPT those of att_embed and model.encoder.* -- the flat entries before

@@ -540,7 +540,7 @@ def _fused_methods():
         return pad(ll), pad(sl)
 
     def forward_xe_fused(self, att_feats, att_masks, labels, phrase_num, phrase_length, extend_phrase_syn_seq, extend_phrase_seq,
-                         extend_phrase_seq_mask, drop=None):
+                         extend_phrase_seq_mask, drop=None, glat_p=-1.0, glat_seed=0):
         """The training forward in the CUDA path's formulation (boficap_b200/csrc/train.inl): encoder once per image, memory
         shared by the captions of an image, all bounding passes as one batch of [LEN] rows.  With drop=None it equals
         forward_xe (tested); with a DropSim it reproduces the CUDA path's dropout masks element for element."""
@@ -589,7 +589,25 @@ def _fused_methods():
         na_in = self.pos(self.embed("syn_embed", extend_phrase_syn_seq)) * drop.elem(N * Tb, c.d_model).view(N, Tb, -1)
         na_len, na_syn = bound_d(self, na_in, memory_n, src_n, vis_b, drop)
         syn_mask = (torch.arange(T)[None, None, :] < (vis_b[:, -1] - 1)[:, None, None]).expand(-1, T, -1)
-        na_logp = decode(torch.full_like(extend_phrase_seq, c.bos_idx), syn_mask)
+        na_words = torch.full_like(extend_phrase_seq, c.bos_idx)
+        if glat_p >= 0:
+            # glancing (EncoderDecoder_UIC.forward :437-464): no-grad NA pass -> predictions; a real word slot takes its ground-truth
+            # word with probability (mismatches / words) * glat_p.  The uniform draws are the CUDA path's counter-based ones
+            # (train_kernels.cuh: glat_input_kernel; the reference uses torch.rand), so the two inputs are identical.
+            with torch.no_grad():
+                pred = decode(na_words, syn_mask).argmax(-1)
+            real = labels[:, 1:-1].long()
+            length = phrase_length.sum(1) - 1
+            pos = torch.arange(T)[None, :] < length[:, None]
+            same = ((pred == real) & pos).sum(1)
+            mismatch = torch.where(length > 0, (length - same).float() / length.clamp(min=1).float(), torch.zeros(N))
+            keep_prob = (mismatch * torch.tensor(glat_p, dtype=torch.float32))[:, None] * pos.float()
+            key = int(DropSim._hash(int(glat_seed) & DropSim.M, torch.tensor(0x474C4154, dtype=torch.int64)))
+            u = (DropSim._hash(key, torch.arange(N * T, dtype=torch.int64)).float() + 0.5) * (1.0 / 4294967296.0)
+            keep = u.view(N, T) < keep_prob
+            na_words = torch.where(keep, real, na_words)
+            self.trace["glat_words"] = na_words
+        na_logp = decode(na_words, syn_mask)
         return sa_len, sa_syn, sa_logp, na_len, na_syn, na_logp
 
     def forward_sc(self, att_feats, att_masks, word_ids, syn_ids, vis, sample_n, drop=None):

@@ -1,7 +1,7 @@
 """Golden vectors of the XE-training forward / backward from the UNMODIFIED reference
 model and criterion imported from /root/reference (build container only; outputs committed under tests/golden/).
 
-TEST INFRASTRUCTURE.  Usage:  python oracle/make_golden_xe.py
+TEST INFRASTRUCTURE.  Usage:  python oracle/make_golden_xe.py [case ...]
 
 The reference `_forward` (TransformerModel.py:1713-1775, train_mode UIC, glat_p = -1) is run in eval() mode
 (dropout is identity, autograd still records), its six outputs go through LanguageModelCriterion_UIC
@@ -25,9 +25,13 @@ from boficap_b200 import synth  # noqa: E402
 from oracle import ref_shim  # noqa: E402
 
 CASES = [
-    # name, B, R, adaptive, batch seed
-    ("xe_b2_r12", 2, 12, False, 3),
-    ("xe_b3_r20_adaptive", 3, 20, True, 5),
+    # name, B, R, adaptive, batch seed, glat_p, glat_seed
+    ("xe_b2_r12", 2, 12, False, 3, -1.0, 0),
+    ("xe_b3_r20_adaptive", 3, 20, True, 5, -1.0, 0),
+    # glancing training (EncoderDecoder_UIC.forward :437-464, configs/uic_glat_token.yaml): the reference's torch.rand is
+    # replaced by the CUDA path's counter-based uniforms so that the glanced inputs are reproducible
+    ("xe_b3_r20_glat", 3, 20, True, 5, 0.5, 11),
+    ("xe_b2_r12_glat1", 2, 12, False, 3, 1.0, 4),
 ]
 LOGP_COLS = 32
 GRAD_HEAD = 64
@@ -47,7 +51,16 @@ def reference_criterion():
     return losses.LanguageModelCriterion_UIC()
 
 
-def run_case(name, B, R, adaptive, seed):
+def glat_uniforms(shape, glat_seed):
+    """u[n, t] of train_kernels.cuh: glat_input_kernel (== oracle DropSim hash): key = hash(seed, 'GLAT'), index n * T + t."""
+    from oracle.bofi_oracle import DropSim
+    n = int(np.prod(shape))
+    key = int(DropSim._hash(int(glat_seed) & DropSim.M, torch.tensor(0x474C4154, dtype=torch.int64)))
+    u = (DropSim._hash(key, torch.arange(n, dtype=torch.int64)).float() + 0.5) * (1.0 / 4294967296.0)
+    return u.view(*shape)
+
+
+def run_case(name, B, R, adaptive, seed, glat_p=-1.0, glat_seed=0):
     cfg = BofiConfig()
     sd = synth.synth_state_dict(cfg, 0, "s_real")
     model, _ = ref_shim.build_reference_model(sd, vocab_size=cfg.vocab_size)
@@ -60,8 +73,12 @@ def run_case(name, B, R, adaptive, seed):
     bt = synth.synth_xe_batch(B, seed=seed, vocab_size=cfg.vocab_size)
     model.eval()
     model.zero_grad()
+    rand = torch.rand
+    if glat_p >= 0:
+        torch.rand = lambda shape, **k: glat_uniforms(tuple(shape), glat_seed)
     outs = model(fc, att, bt["labels"], masks, bt["phrase_num"], bt["phrase_length"], bt["phrase_syn"],
-                 bt["extend_phrase_syn_seq"], bt["extend_phrase_seq"], bt["extend_phrase_seq_mask"], -1.0)
+                 bt["extend_phrase_syn_seq"], bt["extend_phrase_seq"], bt["extend_phrase_seq_mask"], glat_p)
+    torch.rand = rand
     losses = crit(*outs, bt["phrase_num"], bt["phrase_length"], bt["phrase_syn"], bt["labels"], reduction="mean")
     losses[0].backward()
     torch.Tensor.new_zeros = nz
@@ -69,7 +86,7 @@ def run_case(name, B, R, adaptive, seed):
     words = bt["labels"].reshape(-1, bt["labels"].shape[2])[:, 1:-1]
     fix = dict(B=np.array(B), R=np.array(R), adaptive=np.array(adaptive), input_seed=np.array(7), batch_seed=np.array(seed),
                sa_len=sa_len.numpy(), sa_syn=sa_syn.numpy(), na_len=na_len.numpy(), na_syn=na_syn.numpy(),
-               losses=np.array([float(v) for v in losses], dtype=np.float64))
+               losses=np.array([float(v) for v in losses], dtype=np.float64), glat_p=np.array(glat_p), glat_seed=np.array(glat_seed))
     for tag, lp in (("sa", sa_logp), ("na", na_logp)):
         fix[tag + "_logp_head"] = lp[:, :, :LOGP_COLS].numpy()
         fix[tag + "_logp_max"] = lp.max(2).values.numpy()
@@ -92,5 +109,7 @@ def run_case(name, B, R, adaptive, seed):
 
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
+    only = sys.argv[1:]                           # optional case names (default: all)
     for case in CASES:
-        run_case(*case)
+        if not only or case[0] in only:
+            run_case(*case)

@@ -188,6 +188,54 @@ def test_xe_dropout_matches_oracle_masks_fp32():
     assert abs(float(loss2) - float(losses[0])) < 5e-4
 
 
+@pytest.mark.parametrize("glat_p,drop_on", [(0.5, False), (1.0, False), (0.3, True)])
+def test_xe_glancing_matches_oracle_fp32(glat_p, drop_on):
+    """Glancing training (EncoderDecoder_UIC.forward with glat_p >= 0, TransformerModel.py:437-464): the no-grad NA pass, the
+    glanced decoder inputs (same counter-based uniforms as the oracle, which tests/test_oracle_golden_xe.py pins to the reference
+    with those uniforms), the six outputs, the criterion and every gradient -- incl. the word-embedding rows of the glanced words."""
+    from oracle.bofi_oracle import BofiOracle, OracleConfig, DropSim
+    B, R, adaptive, seed = CASES[1]
+    cfg = BofiConfig()
+    sd = synth.synth_state_dict(cfg, 0, "s_real")
+    for k, v in sd.items():
+        if k != "model.pos_embed.pe":
+            v.requires_grad_(True)
+    o = BofiOracle.__new__(BofiOracle)
+    o.sd, o.cfg, o.record, o.trace = sd, OracleConfig(**cfg.to_dict()), False, {}
+    fc, att, masks = synth.synth_inputs(B, R, seed=7, adaptive=adaptive)
+    bt = synth.synth_xe_batch(B, seed=seed, vocab_size=cfg.vocab_size)
+    drop = DropSim(cfg.dropout, cfg.drop_prob_lm, 31) if drop_on else None
+    outs = o.forward_xe_fused(att, masks, bt["labels"], bt["phrase_num"], bt["phrase_length"], bt["extend_phrase_syn_seq"],
+                              bt["extend_phrase_seq"], bt["extend_phrase_seq_mask"], drop=drop, glat_p=glat_p, glat_seed=31)
+    glanced = o.trace["glat_words"]
+    n_glanced = int((glanced != cfg.bos_idx).sum())
+    loss, parts = o.loss_xe(outs, bt["phrase_num"], bt["phrase_length"], bt["phrase_syn"], bt["labels"])
+    loss.backward()
+    ref_grads = {k: (v.grad.detach().clone() if v.grad is not None else torch.zeros_like(v)) for k, v in sd.items() if k != "model.pos_embed.pe"}
+    model, _ = build_model("fp32")
+    args, _ = batch_args(B, R, adaptive, seed, cfg)
+    model.train(drop_on)
+    model.bofi_dropout_seed = 31
+    model.train_bind()
+    model.zero_grad()
+    got = model(*args, glat_p=glat_p)                         # the autograd bridge (mode='forward')
+    for g, w, name in zip(got, outs, ("sa_len", "sa_syn", "sa_logp", "na_len", "na_syn", "na_logp")):
+        err = float((g.detach().cpu() - w.detach()).abs().max())
+        assert err < 1e-4, (name, err)
+    model.bofi_dropout_seed, model._train_steps = 31, 0
+    model.zero_grad()
+    losses = model.xe_step(*args, glat_p=glat_p).cpu().numpy()    # the fused step
+    np.testing.assert_allclose(losses, [float(loss)] + [float(p) for p in parts], rtol=5e-5)
+    worst, name, cos = grad_report(model, ref_grads)
+    print("glancing glat_p=%.1f dropout=%s: %d glanced slots, worst gradient error %.2e (%s)" % (glat_p, drop_on, n_glanced, worst, name))
+    assert n_glanced > 0
+    assert worst < 2e-3 and cos > 0.99999, (worst, name, cos)
+    # glat_p < 0 afterwards: back to the constant-bos formulation
+    model.bofi_dropout_seed, model._train_steps = 31, 0
+    l_off = float(model.xe_step(*args)[0])
+    assert abs(l_off - float(losses[0])) > 1e-4
+
+
 def test_xe_dropout_bf16_statistics():
     """bf16 / tensor-core path with dropout: finite, reproducible for a fixed seed, different across seeds."""
     B, R, adaptive, seed = CASES[0]
