@@ -71,6 +71,7 @@ _SIGNATURES = {
     "bofi_train_set_glat": (C.c_int, [_P, C.c_float, C.c_uint32]),
     "bofi_layernorm_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, _I]),
     "bofi_linear_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I]),
+    "bofi_linear_resid_ln": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "bofi_attention_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I]),
 }
 EXPORTS = tuple(_SIGNATURES)

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "engine.cu")
 OUT = os.path.join(HERE, "lib", "libbofi_b200.so")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("engine.cu", "common.cuh", "gemm_simt.cuh", "gemm_tc.cuh", "gemm_ln_tc.cuh", "gemm_tc2.cuh", "kernels.cuh", "attention_mma.cuh", "train_kernels.cuh", "attention_bwd_mma.cuh", "bound_loop.cuh", "train.inl", "train_abi.inl")] + \
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("engine.cu", "common.cuh", "gemm_simt.cuh", "gemm_tc.cuh", "gemm_ln_tc.cuh", "gemm_tc2.cuh", "gemm_tc2_ln.cuh", "kernels.cuh", "attention_mma.cuh", "train_kernels.cuh", "attention_bwd_mma.cuh", "bound_loop.cuh", "train.inl", "train_abi.inl")] + \
        [os.path.join(os.path.dirname(HERE), "include", "bofi_b200.h")]
 
 

@@ -22,6 +22,7 @@
 #include "gemm_tc.cuh"
 #include "gemm_ln_tc.cuh"
 #include "gemm_tc2.cuh"
+#include "gemm_tc2_ln.cuh"
 #include "kernels.cuh"
 #include "attention_mma.cuh"
 #include "train_kernels.cuh"
@@ -120,6 +121,7 @@ struct bofi_engine {
   bool gemm2 = true;                   // 2-CTA (cta_group::2) 256 x 256 tile pairs for the wide GEMMs; BOFI_GEMM2=0: 1-CTA tiles
   int ln_fuse_min_rows = 4096;         // below this the panel LayerNorm would be repeated by too many CTAs
   bool ln_fuse_small = false;          // BOFI_LNFUSE_SMALL=1: the same for the M <= 2048 launches of the bounding loop only (one launch less per LayerNorm)
+  bool ln_epi = true;                  // BOFI_LNEPI=0: residual GEMMs and the LayerNorm after them as two launches (gemm_tc2_ln.cuh fuses them for M >= 2048)
   bool ln_fuse = false;                // BOFI_LNFUSE=1: LayerNorm fused into the consuming tcgen05 GEMM (gemm_ln_tc.cuh; measured slower, off)
   bool attn_simt_only = false;         // BOFI_ATTN=simt: generic FFMA attention kernel everywhere
   bool finalized = false;
@@ -347,6 +349,31 @@ static int ln_linear(bofi_engine* e, cudaStream_t s, const float* x, const Norm&
   return linear<T, TOut>(e, s, ybuf, kD, l, nullptr, 0, out, ldc, M, relu, live);
 }
 
+// x += A . W^T + b  followed by  y = LayerNorm_next(x):  ONE launch on the bf16 / tcgen05 path for the big row counts (the
+// residual GEMM's epilogue normalises the finished rows, gemm_tc2_ln.cuh), otherwise the residual GEMM and layernorm_kernel.
+template <typename T>
+static bool ln_epi_applies(const bofi_engine* e, int M, const Lin& l) {
+  return std::is_same<T, bf16>::value && e->use_tc && e->gemm2 && e->ln_epi && !e->ln_fuse && M >= 2048 && l.N == kD && l.K % 128 == 0;
+}
+template <typename T>
+static int linear_resid_ln(bofi_engine* e, cudaStream_t s, const T* A, int lda, const Lin& l, float* x, const Norm& next, T* y, int M,
+                           const int* live) {
+  if constexpr (std::is_same<T, bf16>::value) {
+    if (ln_epi_applies<T>(e, M, l)) {
+      const bool hinted = e->rows_dev != nullptr && e->rows_hint > 0 && e->rows_dev == e->varlen_total;
+      const bool exact = e->rows_dev == nullptr || hinted;
+      const int Mp = hinted ? std::min(M, e->rows_hint) : M;
+      ProfScope prof(e, s, exact ? PC_GEMM_TC : PC_OTHER, exact ? 2.0 * Mp * l.N * l.K : 0.0,
+                     exact ? 2.0 * ((double)Mp * l.K + (double)l.N * l.K) + 10.0 * Mp * l.N : 0.0, Mp, l.N, l.K);
+      cudaError_t err = tc::gemm_tc2_ln(s, A, lda, l.w16, l.K, l.b, x, kD, next.a, next.b, y, kD, M, l.K, live, e->rows_dev);
+      if (err != cudaSuccess) return fail(BOFI_ERR_CUDA, "residual GEMM + LayerNorm M=%d K=%d: %s", M, l.K, cudaGetErrorString(err));
+      return BOFI_OK;
+    }
+  }
+  RC_TRY((linear<T, float>(e, s, A, lda, l, x, kD, x, kD, M, 0, live)));
+  return layernorm<T>(e, s, x, kD, next, y, kD, M, nullptr, live);
+}
+
 template <int KT>
 static cudaError_t launch_attention_mma(cudaStream_t s, dim3 grid, size_t smem, const bf16* Q, int ldq, const bf16* K, const bf16* V,
                                         int ldkv, bf16* O, int ldo, int Tq, int Tk, const int* vis, int vis_bs, int vis_qs,
@@ -420,27 +447,64 @@ static int attention(bofi_engine* e, cudaStream_t s, const T* Q, int ldq, const 
 template <typename T>
 static int run_layer(bofi_engine* e, cudaStream_t s, const Layer& ly, float* x, int nb, int T_, const int* self_vis,
                      int self_vis_bs, int self_vis_qs, const T* kvmem, int R, const int* mem_len, int kv_div,
-                     const int* live) {
+                     const int* live, bool y_ready = false, const Norm* next = nullptr, T* next_out = nullptr, bool* next_done = nullptr) {
+  // y_ready: e->y already holds ln[0](x) (the previous layer's FFN2 produced it).  next / next_out: the LayerNorm that follows
+  // this layer (the next layer's ln[0], or the stack's final norm) -- when the fused epilogue applies, the FFN2 launch writes
+  // it into next_out and *next_done is set; otherwise the caller runs it.
   const int rows = nb * T_;
   T* y = e->y.as<T>();
   T* qkv = e->qkv.as<T>();
   T* ao = e->ao.as<T>();
   T* ffh = e->ffh.as<T>();
-  RC_TRY((ln_linear<T, T>(e, s, x, ly.ln[0], ly.sa.qkv, qkv, 3 * kD, rows, 0, live, y)));
+  const bool epi = ln_epi_applies<T>(e, rows, ly.sa.o);
+  if (next_done) *next_done = false;
+  if (y_ready) RC_TRY((linear<T, T>(e, s, y, kD, ly.sa.qkv, nullptr, 0, qkv, 3 * kD, rows, 0, live)));
+  else RC_TRY((ln_linear<T, T>(e, s, x, ly.ln[0], ly.sa.qkv, qkv, 3 * kD, rows, 0, live, y)));
   RC_TRY(attention<T>(e, s, qkv, 3 * kD, qkv + kD, qkv + 2 * kD, 3 * kD, ao, kD, nb, T_, T_, self_vis, self_vis_bs,
                       self_vis_qs, 1, 1, live, nullptr, Drop(), nullptr, 1, e->enc_off, e->enc_off != nullptr));
-  RC_TRY((linear<T, float>(e, s, ao, kD, ly.sa.o, x, kD, x, kD, rows, 0, live)));
+  if (epi) RC_TRY(linear_resid_ln<T>(e, s, ao, kD, ly.sa.o, x, ly.ln[1], y, rows, live));
+  else RC_TRY((linear<T, float>(e, s, ao, kD, ly.sa.o, x, kD, x, kD, rows, 0, live)));
   int f = 1;
   if (ly.cross) {
     T* q = e->q.as<T>();
-    RC_TRY((ln_linear<T, T>(e, s, x, ly.ln[1], ly.ca.q, q, kD, rows, 0, live, y)));
+    if (epi) RC_TRY((linear<T, T>(e, s, y, kD, ly.ca.q, nullptr, 0, q, kD, rows, 0, live)));
+    else RC_TRY((ln_linear<T, T>(e, s, x, ly.ln[1], ly.ca.q, q, kD, rows, 0, live, y)));
     RC_TRY(attention<T>(e, s, q, kD, kvmem, kvmem + kD, 2 * kD, ao, kD, nb, T_, R, mem_len, 1, 0, kv_div, kv_div, live, nullptr, Drop(), nullptr, 1,
                         e->mem_off));
-    RC_TRY((linear<T, float>(e, s, ao, kD, ly.ca.o, x, kD, x, kD, rows, 0, live)));
+    if (epi) RC_TRY(linear_resid_ln<T>(e, s, ao, kD, ly.ca.o, x, ly.ln[2], y, rows, live));
+    else RC_TRY((linear<T, float>(e, s, ao, kD, ly.ca.o, x, kD, x, kD, rows, 0, live)));
     f = 2;
   }
-  RC_TRY((ln_linear<T, T>(e, s, x, ly.ln[f], ly.w1, ffh, e->cfg.d_ff, rows, 1, live, y)));
-  RC_TRY((linear<T, float>(e, s, ffh, e->cfg.d_ff, ly.w2, x, kD, x, kD, rows, 0, live)));
+  if (epi) RC_TRY((linear<T, T>(e, s, y, kD, ly.w1, nullptr, 0, ffh, e->cfg.d_ff, rows, 1, live)));
+  else RC_TRY((ln_linear<T, T>(e, s, x, ly.ln[f], ly.w1, ffh, e->cfg.d_ff, rows, 1, live, y)));
+  if (epi && next && next_out && ln_epi_applies<T>(e, rows, ly.w2)) {
+    RC_TRY(linear_resid_ln<T>(e, s, ffh, e->cfg.d_ff, ly.w2, x, *next, next_out, rows, live));
+    if (next_done) *next_done = true;
+  } else {
+    RC_TRY((linear<T, float>(e, s, ffh, e->cfg.d_ff, ly.w2, x, kD, x, kD, rows, 0, live)));
+  }
+  return BOFI_OK;
+}
+
+// A stack of layers + its final LayerNorm into `out` (bf16 / fp32 operand type), the inter-layer LayerNorms riding in the FFN2
+// epilogues where the fused kernel applies.  final_f32_copy: the final norm also as fp32 (bofi_encode's memory_out) -- that
+// one stays a layernorm_kernel launch.
+template <typename T>
+static int run_stack(bofi_engine* e, cudaStream_t s, const std::vector<Layer>& layers, const Norm& final_norm, T* out, float* final_f32_copy,
+                     float* x, int nb, int T_, const int* self_vis, int self_vis_bs, int self_vis_qs, const T* const* kvmem, int R,
+                     const int* mem_len, int kv_div, const int* live) {
+  bool ready = false;
+  const size_t n = layers.size();
+  for (size_t l = 0; l < n; ++l) {
+    const bool last = (l + 1 == n);
+    const Norm* next = last ? (final_f32_copy ? nullptr : &final_norm) : &layers[l + 1].ln[0];
+    T* next_out = last ? out : e->y.as<T>();
+    bool done = false;
+    RC_TRY(run_layer<T>(e, s, layers[l], x, nb, T_, self_vis, self_vis_bs, self_vis_qs, kvmem ? kvmem[l] : (const T*)nullptr, R, mem_len, kv_div, live,
+                        ready, next, next_out, &done));
+    ready = done;
+  }
+  if (!ready || n == 0) RC_TRY(layernorm<T>(e, s, x, kD, final_norm, out, kD, nb * T_, final_f32_copy, live));
   return BOFI_OK;
 }
 
@@ -642,9 +706,7 @@ static int encode_impl(bofi_engine* e, cudaStream_t s, const void* att, int fdt,
       launch_k(zero_padded_rows_kernel, ceil_div(M, 8), 256, 0, s, x, len_dev, B, R);
       CU_TRY(cudaGetLastError());
     }
-    for (const Layer& ly : e->enc)
-      RC_TRY(run_layer<T>(e, s, ly, x, B, R, len_dev, 1, 0, (const T*)nullptr, 0, nullptr, 1, nullptr));
-    RC_TRY(layernorm<T>(e, s, x, kD, e->enc_norm, e->memT.as<T>(), kD, M, memory_out, nullptr));
+    RC_TRY(run_stack<T>(e, s, e->enc, e->enc_norm, e->memT.as<T>(), memory_out, x, B, R, len_dev, 1, 0, (const T* const*)nullptr, 0, nullptr, 1, nullptr));
   } else {
     // Varlen: att_embed on the padded layout (the features arrive padded; it is 5 % of the encoder's work), then every
     // valid row moves to its compact position and the layers only see sum(att_len) rows -- the row count lives on the
@@ -673,10 +735,8 @@ static int encode_impl(bofi_engine* e, cudaStream_t s, const void* att, int fdt,
     }
     e->rows_dev = e->varlen_total = total;
     e->enc_off = off;
-    int rc = BOFI_OK;
-    for (size_t l = 0; l < e->enc.size() && rc == BOFI_OK; ++l)
-      rc = run_layer<T>(e, s, e->enc[l], x, B, R, len_dev, 1, 0, (const T*)nullptr, 0, nullptr, 1, nullptr);
-    if (rc == BOFI_OK) rc = layernorm<T>(e, s, x, kD, e->enc_norm, e->memT.as<T>(), kD, M, memory_out ? e->xpad.as<float>() : nullptr, nullptr);
+    const int rc = run_stack<T>(e, s, e->enc, e->enc_norm, e->memT.as<T>(), memory_out ? e->xpad.as<float>() : nullptr, x, B, R, len_dev, 1, 0,
+                                (const T* const*)nullptr, 0, nullptr, 1, nullptr);
     e->rows_dev = nullptr;
     e->enc_off = nullptr;
     RC_TRY(rc);
@@ -960,8 +1020,12 @@ static int decode_naic(bofi_engine* e, cudaStream_t s, int sn, int output_logsof
     launch_k(gather_table_kernel, ceil_div(rows * L, 8), 256, 0, s, e->fill_in.as<float>(), L, e->st.ext, Lb, 1, x, rows * L, L, nullptr);
   }
   CU_TRY(cudaGetLastError());
-  for (int l = 0; l < c.n_dec; ++l)
-    RC_TRY(run_layer<T>(e, s, e->dec[l], x, rows, L, e->st.vis_fill, L, 1, e->kv[nb_layers + l].as<T>(), e->R, mem_len, sn, nullptr));
+  {
+    // decoder stack + model.decoder.norm -> e->y (the vocabulary projection's operand)
+    std::vector<const T*> kvp((size_t)c.n_dec);
+    for (int l = 0; l < c.n_dec; ++l) kvp[l] = e->kv[nb_layers + l].as<T>();
+    RC_TRY(run_stack<T>(e, s, e->dec, e->dec_norm, e->y.as<T>(), nullptr, x, rows, L, e->st.vis_fill, L, 1, kvp.data(), e->R, mem_len, sn, nullptr));
+  }
   // Vocabulary projection + log-softmax.  Optionally (BOFI_VOCAB_CHUNK=<rows>) in row chunks of whole captions whose fp32
   // logits (chunk x Vpad) could stay in the 126 MB L2 between the GEMM that writes them and the epilogue that reads them.
   // Measured at B = 1024 with three batches in flight: 1280-row chunks 164.6-166.7 k captions/s, 640 rows 164.9 k, 1920 rows
@@ -1001,7 +1065,6 @@ static int decode_naic(bofi_engine* e, cudaStream_t s, int sn, int output_logsof
         ve.fast_exp = want_stats ? 0 : 1;            // as vocab_epilogue_kernel: ex2.approx unless the entropy statistics are wanted
         ve.need_lse = (want_stats || (logprobs && output_logsoftmax)) ? 1 : 0;   // greedy / sampled tokens alone need no sum-exp
         T* y = e->y.as<T>();
-        RC_TRY(layernorm<T>(e, s, x, kD, e->dec_norm, y, kD, total, nullptr, nullptr));
         {
           ProfScope prof(e, s, PC_GEMM_TC, 2.0 * total * e->V * kD, 2.0 * ((double)total * kD + (double)e->V * kD) + 16.0 * per, total, e->V, kD);
           cudaError_t err = tc::gemm_tc2_vocab(s, y, kD, e->generator.w16, kD, e->generator.b, total, e->V, kD, 1, ve);
@@ -1029,10 +1092,9 @@ static int decode_naic(bofi_engine* e, cudaStream_t s, int sn, int output_logsof
       chunk = total + 1;          // skip the materialising path below
     } else if (chunk >= total) {
       RC_TRY(e->logits.reserve((size_t)total * (size_t)e->Vpad * 4));
-      RC_TRY((ln_linear<T, float>(e, s, x, e->dec_norm, e->generator, e->logits.as<float>(), e->Vpad, total, 0, nullptr, e->y.as<T>())));
+      RC_TRY((linear<T, float>(e, s, e->y.as<T>(), kD, e->generator, nullptr, 0, e->logits.as<float>(), e->Vpad, total, 0, nullptr)));
     } else {
       RC_TRY(e->logits.reserve((size_t)total * (size_t)e->Vpad * 4));
-      RC_TRY(layernorm<T>(e, s, x, kD, e->dec_norm, e->y.as<T>(), kD, total, nullptr, nullptr));
     }
     for (int r0 = 0; r0 < total && !fused; r0 += chunk) {
       const int n = std::min(chunk, total - r0);
@@ -1095,9 +1157,11 @@ static int decode_saic(bofi_engine* e, cudaStream_t s, int sn, int output_logsof
     LAUNCH_OTHER((launch_k(embed_words_kernel, ceil_div(rows * L, 8), 256, 0, s, 
         W(e, "model.tgt_embed.lut.weight"), W(e, "model.syn_embed.lut.weight"), W(e, "model.pos_embed.pe"), e->st.ext_word,
         e->st.ext_syn, Lb, 1, sqrt_d, x, rows * L, L, live)));
-    for (int l = 0; l < c.n_dec; ++l)
-      RC_TRY(run_layer<T>(e, s, e->dec[l], x, rows, L, e->st.vis_fill, L, 1, e->kv[nb_layers + l].as<T>(), e->R, mem_len, sn, live));
-    RC_TRY(layernorm<T>(e, s, x, kD, e->dec_norm, e->y.as<T>(), kD, rows * L, nullptr, live));
+    {
+      std::vector<const T*> kvp((size_t)c.n_dec);
+      for (int l = 0; l < c.n_dec; ++l) kvp[l] = e->kv[nb_layers + l].as<T>();
+      RC_TRY(run_stack<T>(e, s, e->dec, e->dec_norm, e->y.as<T>(), nullptr, x, rows, L, e->st.vis_fill, L, 1, kvp.data(), e->R, mem_len, sn, live));
+    }
     RC_TRY((linear<T, float>(e, s, e->y.as<T>(), kD, e->generator, nullptr, 0, e->logits.as<float>(), e->Vpad, rows * L, 0, live)));
     {
       ProfScope prof(e, s, PC_VOCAB, 0.0, 0.0);
@@ -1362,6 +1426,8 @@ int bofi_create(const bofi_config_t* cfg, int device, bofi_handle_t* out) {
   e->ares = (ar && strcmp(ar, "1") == 0);
   const char* gl = getenv("BOFI_LNFUSE");
   e->ln_fuse = (gl && strcmp(gl, "1") == 0);
+  const char* gle = getenv("BOFI_LNEPI");
+  e->ln_epi = !(gle && strcmp(gle, "0") == 0);
   if (const char* gm = getenv("BOFI_LNFUSE_MIN")) e->ln_fuse_min_rows = atoi(gm);
   const char* gls = getenv("BOFI_LNFUSE_SMALL");
   e->ln_fuse_small = (gls && strcmp(gls, "1") == 0);
@@ -1657,6 +1723,28 @@ int bofi_layernorm_f32(bofi_handle_t e, void* stream, const float* x, const floa
   CU_TRY(cudaSetDevice(e->device));
   Norm n{a2, b2};
   return layernorm<float>(e, (cudaStream_t)stream, x, kD, n, out, kD, rows, nullptr, nullptr);
+}
+
+int bofi_linear_resid_ln(bofi_handle_t e, void* stream, const float* A, const float* Wt, const float* bias, float* x, const float* a2,
+                         const float* b2, float* y_out, int32_t M, int32_t K, const int32_t* rows_dev) {
+  if (!e || !A || !Wt || !bias || !x || !a2 || !b2 || !y_out) return fail(BOFI_ERR_INVALID, "null argument");
+  if (!e->bf16_mode || !e->use_tc) return fail(BOFI_ERR_STATE, "bofi_linear_resid_ln is the bf16 / tcgen05 path's kernel");
+  if (K % 128 != 0 || M <= 0) return fail(BOFI_ERR_INVALID, "K %% 128 == 0 and M > 0 required");
+  CU_TRY(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  RC_TRY(e->unit_a.reserve((size_t)M * K * 2));
+  RC_TRY(e->unit_w.reserve((size_t)kD * K * 2));
+  RC_TRY(e->unit_o.reserve((size_t)M * kD * 2));
+  launch_k(cast_kernel<bf16>, ceil_div((size_t)M * K / 4, 256), 256, 0, s, A, e->unit_a.as<bf16>(), (size_t)M * K / 4);
+  launch_k(cast_kernel<bf16>, ceil_div((size_t)kD * K / 4, 256), 256, 0, s, Wt, e->unit_w.as<bf16>(), (size_t)kD * K / 4);
+  CU_TRY(cudaGetLastError());
+  cudaError_t err = tc::gemm_tc2_ln(s, e->unit_a.as<bf16>(), K, e->unit_w.as<bf16>(), K, bias, x, kD, a2, b2, e->unit_o.as<bf16>(), kD, M, K,
+                                    nullptr, rows_dev);
+  if (err != cudaSuccess) return fail(BOFI_ERR_CUDA, "residual GEMM + LayerNorm: %s", cudaGetErrorString(err));
+  e->launches++;
+  launch_k(widen_kernel, ceil_div((size_t)M * kD / 4, 256), 256, 0, s, (const bf16*)e->unit_o.as<bf16>(), y_out, (size_t)M * kD / 4);
+  CU_TRY(cudaGetLastError());
+  return BOFI_OK;
 }
 
 int bofi_linear_f32(bofi_handle_t e, void* stream, const float* A, const float* Wt, const float* bias, const float* residual,

@@ -332,6 +332,16 @@ class BofiEngine:
                                             _ptr(out), M, N, K, int(relu)))
         return out
 
+    def linear_resid_ln(self, a, w, bias, x, ln_a, ln_b, rows_dev=None):
+        """Unit entry of the residual GEMM with the following LayerNorm in its epilogue (gemm_tc2_ln.cuh; bf16 engines):
+        x += a . w^T + bias in place, returns y = LayerNorm(x; ln_a, ln_b) as the kernel's bf16 values widened to fp32."""
+        M, K = a.shape
+        assert w.shape == (512, K) and x.shape == (M, 512)
+        y = torch.empty(M, 512, device=a.device, dtype=torch.float32)
+        _lib.check(self.lib.bofi_linear_resid_ln(self.handle, self._stream(), _ptr(a), _ptr(w), _ptr(bias), _ptr(x), _ptr(ln_a),
+                                                 _ptr(ln_b), _ptr(y), M, K, _ptr(rows_dev)))
+        return y
+
     def attention(self, q, k, v, vis=None):
         B, Tq, _ = q.shape
         Tk = k.shape[1]

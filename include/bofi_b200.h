@@ -268,6 +268,12 @@ int bofi_layernorm_f32(bofi_handle_t h, void* stream, const float* x, const floa
  * backend's operand type happens inside.  relu and residual are optional (0 / NULL). */
 int bofi_linear_f32(bofi_handle_t h, void* stream, const float* A, const float* W, const float* bias,
                     const float* residual, float* out, int32_t M, int32_t N, int32_t K, int32_t relu);
+/* The residual GEMM with the following LayerNorm in its epilogue (bf16 / tcgen05 engines only; SublayerConnection,
+ * TransformerModel.py:1351-1363, then the LayerNorm of :1338-1349):  x[M,512] += A[M,K] @ W[512,K]^T + bias in place (fp32) and
+ * y[M,512] = a2 * (x - mean) / (std + 1e-6) + b2 (computed as bf16, returned widened to f32).  All pointers dev f32; A and W
+ * are rounded to bf16 inside.  K % 128 == 0.  rows_dev (optional dev i32): only the first *rows_dev rows are computed. */
+int bofi_linear_resid_ln(bofi_handle_t h, void* stream, const float* A, const float* W, const float* bias, float* x,
+                         const float* a2, const float* b2, float* y_out, int32_t M, int32_t K, const int32_t* rows_dev);
 /* softmax(QK^T/sqrt(dk), keys >= vis masked) V for `heads` heads, fp32 dev tensors
  * (TransformerModel.py:1421-1432): q [B,Tq,d], k/v [B,Tk,d], vis i32 [B,Tq] visible-key counts. */
 int bofi_attention_f32(bofi_handle_t h, void* stream, const float* q, const float* k, const float* v,

@@ -97,6 +97,39 @@ def test_linear_bf16_inplace_residual(engines, M, N, K):
     assert torch.equal(x, out_of_place)
 
 
+@pytest.mark.parametrize("M,K,rows", [(36864, 512, None), (20480, 2048, None), (300, 512, None), (2049, 128, None), (5000, 512, 3000)])
+def test_linear_bf16_residual_layernorm_epilogue(engines, M, K, rows):
+    """gemm_tc2_ln_kernel: x += a . W^T + b in place (must equal the plain in-place residual GEMM bit for bit: same fp32 sum) and
+    y = LayerNorm(x) with the reference's formula (unbiased std, eps outside) out of the GEMM's epilogue, rounded to bf16."""
+    _, e16 = engines
+    g = torch.Generator().manual_seed(M + K)
+    a = torch.randn(M, K, generator=g).cuda()
+    w = (torch.randn(512, K, generator=g) / math.sqrt(K)).cuda()
+    bias = torch.randn(512, generator=g).cuda()
+    res = (torch.randn(M, 512, generator=g) * 2 + 0.3).cuda()
+    ln_a = (1 + 0.1 * torch.randn(512, generator=g)).cuda()
+    ln_b = (0.1 * torch.randn(512, generator=g)).cuda()
+    x_ref = e16.linear(a, w, bias, res.clone(), False, inplace=True)
+    x = res.clone()
+    rows_dev = torch.tensor([rows], dtype=torch.int32, device="cuda") if rows is not None else None
+    y = e16.linear_resid_ln(a, w, bias, x, ln_a, ln_b, rows_dev)
+    torch.cuda.synchronize()
+    n = rows if rows is not None else M
+    assert torch.equal(x[:n], x_ref[:n])
+    if rows is not None:                       # whole 256-row panels above the device-side row count are never touched
+        first_untouched = (rows + 255) // 256 * 256
+        assert torch.equal(x[first_untouched:], res[first_untouched:])
+    xd = x[:n].double()
+    ref = ln_a.double() * (xd - xd.mean(-1, keepdim=True)) / (xd.std(-1, keepdim=True) + 1e-6) + ln_b.double()
+    err = (y[:n].double() - ref).abs()
+    # bf16 output: half an ulp of the value (2^-9 relative) plus fp32 rounding of the statistics
+    tol = ref.abs() * 2.0 ** -8 + 1e-5
+    assert bool((err <= tol).all()), float((err - tol).max())
+    # and against the stand-alone kernel's bf16 rounding: identical except where a value sits on a rounding boundary
+    y2 = e16.layernorm(x[:n].contiguous(), ln_a, ln_b).bfloat16().float()
+    assert float((y[:n] != y2).float().mean()) < 1e-3
+
+
 def test_attention_prefix_masks_and_nan_rows(engines):
     e32, _ = engines
     g = torch.Generator().manual_seed(5)
