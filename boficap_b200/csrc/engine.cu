@@ -121,7 +121,7 @@ struct bofi_engine {
   bool gemm2 = true;                   // 2-CTA (cta_group::2) 256 x 256 tile pairs for the wide GEMMs; BOFI_GEMM2=0: 1-CTA tiles
   int ln_fuse_min_rows = 4096;         // below this the panel LayerNorm would be repeated by too many CTAs
   bool ln_fuse_small = false;          // BOFI_LNFUSE_SMALL=1: the same for the M <= 2048 launches of the bounding loop only (one launch less per LayerNorm)
-  bool ln_epi = true;                  // BOFI_LNEPI=0: residual GEMMs and the LayerNorm after them as two launches (gemm_tc2_ln.cuh fuses them for M >= 2048)
+  bool ln_epi = false;                 // BOFI_LNEPI=1: residual GEMM + the LayerNorm after it as ONE launch for M >= 2048 (gemm_tc2_ln.cuh; parity-green, measured slower: off)
   bool ln_fuse = false;                // BOFI_LNFUSE=1: LayerNorm fused into the consuming tcgen05 GEMM (gemm_ln_tc.cuh; measured slower, off)
   bool attn_simt_only = false;         // BOFI_ATTN=simt: generic FFMA attention kernel everywhere
   bool finalized = false;
@@ -1427,7 +1427,7 @@ int bofi_create(const bofi_config_t* cfg, int device, bofi_handle_t* out) {
   const char* gl = getenv("BOFI_LNFUSE");
   e->ln_fuse = (gl && strcmp(gl, "1") == 0);
   const char* gle = getenv("BOFI_LNEPI");
-  e->ln_epi = !(gle && strcmp(gle, "0") == 0);
+  e->ln_epi = (gle && strcmp(gle, "1") == 0);
   if (const char* gm = getenv("BOFI_LNFUSE_MIN")) e->ln_fuse_min_rows = atoi(gm);
   const char* gls = getenv("BOFI_LNFUSE_SMALL");
   e->ln_fuse_small = (gls && strcmp(gls, "1") == 0);

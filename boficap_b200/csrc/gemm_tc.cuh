@@ -80,6 +80,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
       ::"r"(smem_dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -136,11 +142,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int KPS = 1>
 struct SmemLayout {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStageBytes = KPS * (kABytes + kBBytes);   // KPS k-blocks per stage: [A kb .. A kb+KPS-1 | W kb .. W kb+KPS-1]
   static constexpr int kOutOffset = STAGES * kStageBytes;          // epilogue staging: 8 warps x 4 KB
   static constexpr int kOutBytes = 8 * 4096;
   static constexpr int kBarOffset = kOutOffset + kOutBytes;
@@ -184,13 +190,18 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // REDUCE (fp32 output only): the K range is cut into `k_splits` slices handled by different CTAs and every slice is
 // ADDED to C with a TMA reduce store (cp.reduce.async.bulk.tensor ... .add): weight gradients have few output tiles and
 // a very long contraction, and accumulate into the gradient buffer anyway.
-template <int BN, int STAGES, typename TOut, bool RELU, bool RESID, bool A_MN = false, bool B_MN = false, bool REDUCE = false>
+// KPS > 1 (K-major operands, no K split): a ring stage carries KPS consecutive k-blocks, brought by ONE 3-D box per operand
+// (cached_tmap_kblocks).  tools/tma_feed_bench.cu: a stage costs ~830 clk of fixed, non-overlapping latency whatever it
+// carries, so the 8 (K = 512) or 32 (K = 2048) one-k-block stages of a bounding-loop GEMM -- a CTA does a single tile there,
+// nothing hides the fill -- cost 4-17 us; with four k-blocks per stage it is a quarter of the rounds.
+template <int BN, int STAGES, typename TOut, bool RELU, bool RESID, bool A_MN = false, bool B_MN = false, bool REDUCE = false, int KPS = 1>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, const float* residual, int ldr,
                int M, int N, int K, int relu, const int* live_rows, int k_splits, const int* rows_dev) {
   pdl_launch();
-  using L = SmemLayout<BN, STAGES>;
+  static_assert(KPS == 1 || (!A_MN && !B_MN), "several k-blocks per stage: K-major operands only");
+  using L = SmemLayout<BN, STAGES, KPS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
@@ -202,7 +213,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk_all = (K + kBK - 1) / kBK;      // a K tail is zero-filled by TMA (out-of-bounds box elements)
-  const int nk_per = REDUCE ? (nk_all + k_splits - 1) / k_splits : nk_all;
+  const int nk_per = (REDUCE && KPS == 1) ? (nk_all + k_splits - 1) / k_splits : nk_all;   // (KPS > 1: launched with k_splits == 1)
   const int tiles_n = (N + BN - 1) / BN;
 
   if (warp == 0 && lane == 0) {
@@ -246,13 +257,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int item = blockIdx.x; item < ntiles; item += gridDim.x) {
         const int tile = item % ntiles_mn, kb0 = (item / ntiles_mn) * nk_per, kb1 = min(nk_all, kb0 + nk_per);
         const int m0 = (tile / tiles_n) * kBM, n0 = (tile % tiles_n) * BN;
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; kb += KPS, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           PROF_WAIT(w_slot, mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1));
           const uint32_t fb = smem_u32(&full_bar[s]);
           mbar_expect_tx(fb, L::kStageBytes);
           const uint32_t a_dst = smem_u32(smem + s * L::kStageBytes);
+          if constexpr (KPS > 1) {          // one 3-D box per operand: KPS consecutive 128B-swizzled k-block tiles
+            tma_load_3d(a_dst, &tmA, fb, 0, m0, kb);
+            tma_load_3d(a_dst + KPS * L::kABytes, &tmB, fb, 0, n0, kb);
+            continue;
+          }
           if constexpr (!A_MN) {
             tma_load_2d(a_dst, &tmA, fb, kb * kBK, m0);
           } else {
@@ -283,19 +299,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         PROF_WAIT(w_acc, mbar_wait(smem_u32(&tmem_empty_bar[as]), aph ^ 1));     // epilogue drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; kb += KPS, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           PROF_WAIT(w_full, mbar_wait(smem_u32(&full_bar[s]), ph));
           tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
-          const uint64_t adesc = A_MN ? make_sw128_desc_mn(a_addr) : make_sw128_desc(a_addr);
-          const uint64_t bdesc = B_MN ? make_sw128_desc_mn(a_addr + L::kABytes) : make_sw128_desc(a_addr + L::kABytes);
-          // per K step of 16: K-major +32 bytes inside the 128-byte swizzle row; MN-major +16 rows of 128 bytes (encoded >> 4)
-          constexpr uint64_t a_step = A_MN ? 128 : 2, b_step = B_MN ? 128 : 2;
+          const uint32_t s_addr = smem_u32(smem + s * L::kStageBytes);
 #pragma unroll
-          for (int k = 0; k < kBK / kUK; ++k) {
-            umma_bf16(tmem_d, adesc + a_step * k, bdesc + b_step * k, idesc, ((kb - kb0) | k) != 0);
+          for (int kk = 0; kk < KPS; ++kk) {
+            const uint32_t a_addr = s_addr + kk * L::kABytes, b_addr = s_addr + KPS * L::kABytes + kk * L::kBBytes;
+            const uint64_t adesc = A_MN ? make_sw128_desc_mn(a_addr) : make_sw128_desc(a_addr);
+            const uint64_t bdesc = B_MN ? make_sw128_desc_mn(b_addr) : make_sw128_desc(b_addr);
+            // per K step of 16: K-major +32 bytes inside the 128-byte swizzle row; MN-major +16 rows of 128 bytes (encoded >> 4)
+            constexpr uint64_t a_step = A_MN ? 128 : 2, b_step = B_MN ? 128 : 2;
+#pragma unroll
+            for (int k = 0; k < kBK / kUK; ++k) {
+              umma_bf16(tmem_d, adesc + a_step * k, bdesc + b_step * k, idesc, ((kb - kb0) | kk | k) != 0);
+            }
           }
           umma_commit(smem_u32(&empty_bar[s]));      // frees the smem stage when these MMAs retire
         }
@@ -525,21 +545,22 @@ inline int num_sms() {
   return n;
 }
 
-template <int BN, int STAGES, typename TOut, bool RELU, bool RESID, bool A_MN = false, bool B_MN = false, bool REDUCE = false>
+template <int BN, int STAGES, typename TOut, bool RELU, bool RESID, bool A_MN = false, bool B_MN = false, bool REDUCE = false, int KPS = 1>
 inline cudaError_t launch(cudaStream_t s, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                           const float* bias, const float* residual, int ldr, int M, int N, int K, int relu,
                           const int* live_rows, int k_splits = 1, const int* rows_dev = nullptr) {
-  using L = SmemLayout<BN, STAGES>;
+  using L = SmemLayout<BN, STAGES, KPS>;
+  static_assert(L::kTotal <= 232448, "shared memory budget");
   static PerDevice<bool> configured_dev;
   bool& configured = configured_dev.get();
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, TOut, RELU, RESID, A_MN, B_MN, REDUCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, TOut, RELU, RESID, A_MN, B_MN, REDUCE, KPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const int ntiles = ((M + kBM - 1) / kBM) * ((N + BN - 1) / BN) * k_splits;
   const int grid = ntiles < num_sms() ? ntiles : num_sms();
-  launch_k(gemm_tc_kernel<BN, STAGES, TOut, RELU, RESID, A_MN, B_MN, REDUCE>, grid, kThreads, L::kTotal, s, tmA, tmB, tmC, bias, residual, ldr, M, N, K, relu, live_rows, k_splits, rows_dev);
+  launch_k(gemm_tc_kernel<BN, STAGES, TOut, RELU, RESID, A_MN, B_MN, REDUCE, KPS>, grid, kThreads, L::kTotal, s, tmA, tmB, tmC, bias, residual, ldr, M, N, K, relu, live_rows, k_splits, rows_dev);
   return cudaGetLastError();
 }
 
@@ -605,6 +626,15 @@ inline const CUtensorMap* cached_tmap_kblocks(const void* ptr, uint64_t rows, ui
   return &cache.emplace(key, tm).first->second;
 }
 
+inline bool small_kps4() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BOFI_KPS_SMALL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 // A [M,K] bf16 (pitch lda), W [N,K] bf16 (pitch ldw).  Requires K % 64 == 0, 16-byte aligned pitches.
 template <typename TOut>
 inline cudaError_t gemm_tc(cudaStream_t s, const bf16* A, int lda, const bf16* W, int ldw, const float* bias,
@@ -615,13 +645,18 @@ inline cudaError_t gemm_tc(cudaStream_t s, const bf16* A, int lda, const bf16* W
     return cudaErrorInvalidValue;
   const int tiles256 = ((M + kBM - 1) / kBM) * ((N + 255) / 256);
   const bool wide = tiles256 >= num_sms() / 2;      // small problems: narrower tiles spread over more SMs
-  const CUtensorMap* tmA = cached_tmap(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBM);
-  const CUtensorMap* tmB = cached_tmap(W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, wide ? 256 : 64);
+  // narrow tiles, whole multiples of four k-blocks: four k-blocks per ring stage (see the kernel's KPS note; BOFI_KPS_SMALL=0: one)
+  const bool kps4 = !wide && small_kps4() && K % (4 * kBK) == 0;
+  const CUtensorMap* tmA = kps4 ? cached_tmap_kblocks(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBM, 4)
+                                : cached_tmap(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBM);
+  const CUtensorMap* tmB = kps4 ? cached_tmap_kblocks(W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, 64, 4)
+                                : cached_tmap(W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, wide ? 256 : 64);
   const CUtensorMap* tmC = cached_tmap(C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, (int)sizeof(TOut));
   if (!tmA || !tmB || !tmC) return cudaErrorInvalidValue;
   if (!bias) return cudaErrorInvalidValue;          // every nn.Linear of this model has a bias
 #define BOFI_TC_LAUNCH(BN_, ST_, RELU_, RESID_) \
-  launch<BN_, ST_, TOut, RELU_, RESID_>(s, *tmA, *tmB, *tmC, bias, residual, ldr, M, N, K, relu, live_rows, 1, rows_dev)
+  (kps4 && BN_ == 64 ? launch<64, 2, TOut, RELU_, RESID_, false, false, false, 4>(s, *tmA, *tmB, *tmC, bias, residual, ldr, M, N, K, relu, live_rows, 1, rows_dev) \
+                     : launch<BN_, ST_, TOut, RELU_, RESID_>(s, *tmA, *tmB, *tmC, bias, residual, ldr, M, N, K, relu, live_rows, 1, rows_dev))
   if constexpr (sizeof(TOut) == 4) {
     // fp32 outputs: plain (logits), +ReLU (att_embed), +residual (O-proj / FFN2 into the residual stream)
     if (residual && relu) return cudaErrorInvalidValue;
@@ -630,6 +665,7 @@ inline cudaError_t gemm_tc(cudaStream_t s, const bf16* A, int lda, const bf16* W
     // transposes through the staging tile.  (acc + b) + x and x + (acc + b) are the same fp32 sum.
     if (residual && inplace_reduce() && (const void*)residual == (const void*)C && ldr == ldc)
       return wide ? launch<256, 4, TOut, false, false, false, false, true>(s, *tmA, *tmB, *tmC, bias, nullptr, 0, M, N, K, 0, live_rows, 1, rows_dev)
+           : kps4 ? launch<64, 2, TOut, false, false, false, false, true, 4>(s, *tmA, *tmB, *tmC, bias, nullptr, 0, M, N, K, 0, live_rows, 1, rows_dev)
                   : launch<64, 6, TOut, false, false, false, false, true>(s, *tmA, *tmB, *tmC, bias, nullptr, 0, M, N, K, 0, live_rows, 1, rows_dev);
     if (residual) return wide ? BOFI_TC_LAUNCH(256, 4, false, true) : BOFI_TC_LAUNCH(64, 6, false, true);
     if (relu) return wide ? BOFI_TC_LAUNCH(256, 4, true, false) : BOFI_TC_LAUNCH(64, 6, true, false);
