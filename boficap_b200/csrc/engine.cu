@@ -121,6 +121,7 @@ struct bofi_engine {
   bool gemm2 = true;                   // 2-CTA (cta_group::2) 256 x 256 tile pairs for the wide GEMMs; BOFI_GEMM2=0: 1-CTA tiles
   int ln_fuse_min_rows = 4096;         // below this the panel LayerNorm would be repeated by too many CTAs
   bool ln_fuse_small = false;          // BOFI_LNFUSE_SMALL=1: the same for the M <= 2048 launches of the bounding loop only (one launch less per LayerNorm)
+  bool bound_prio = false;             // BOFI_BOUND_PRIO=1: graph replays (bounding loop, SAIC step loop) on a high-priority stream (measured slower: the GEMMs of the other batches then start on fewer SMs)
   bool ln_epi = false;                 // BOFI_LNEPI=1: residual GEMM + the LayerNorm after it as ONE launch for M >= 2048 (gemm_tc2_ln.cuh; parity-green, measured slower: off)
   bool ln_fuse = false;                // BOFI_LNFUSE=1: LayerNorm fused into the consuming tcgen05 GEMM (gemm_ln_tc.cuh; measured slower, off)
   bool attn_simt_only = false;         // BOFI_ATTN=simt: generic FFMA attention kernel everywhere
@@ -870,7 +871,12 @@ static int run_graphed(bofi_engine* e, cudaStream_t s, bofi_engine::GraphSlot& g
   const bool key_ok = memcmp(key, g.key, sizeof(key)) == 0;
   if (!e->use_graph || e->profiling) return enqueue(s);
   if (!e->aux_stream) {
-    CU_TRY(cudaStreamCreateWithFlags(&e->aux_stream, cudaStreamNonBlocking));
+    // The graphs hold the latency chains (bounding loop: ~190 small dependent launches).  With several batches in flight their
+    // kernels otherwise queue behind the other batches' 148-CTA GEMMs, whose successors are already pre-launched (PDL): on a
+    // high-priority stream a chain's CTAs take the first SMs that come free (opt-in, BOFI_BOUND_PRIO=1).
+    int prio_lo = 0, prio_hi = 0;
+    CU_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CU_TRY(cudaStreamCreateWithPriority(&e->aux_stream, cudaStreamNonBlocking, e->bound_prio ? prio_hi : 0));
     CU_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
   }
@@ -1426,6 +1432,8 @@ int bofi_create(const bofi_config_t* cfg, int device, bofi_handle_t* out) {
   e->ares = (ar && strcmp(ar, "1") == 0);
   const char* gl = getenv("BOFI_LNFUSE");
   e->ln_fuse = (gl && strcmp(gl, "1") == 0);
+  const char* gbp = getenv("BOFI_BOUND_PRIO");
+  e->bound_prio = (gbp && strcmp(gbp, "1") == 0);
   const char* gle = getenv("BOFI_LNEPI");
   e->ln_epi = (gle && strcmp(gle, "1") == 0);
   if (const char* gm = getenv("BOFI_LNFUSE_MIN")) e->ln_fuse_min_rows = atoi(gm);

@@ -129,8 +129,15 @@ struct VocabEpi {
   int do_lsm = 0;            // 0: raw logits (output_logsoftmax = 0)
 };
 
-template <typename TOut, bool RELU, bool RESID, bool REDUCE = false, bool ARES = false, int KPS = 1, int VMODE = 0>
-__global__ void __launch_bounds__(kThreads, 1)
+// DYN: dynamic tile scheduling through the hardware's cluster launch control (clusterlaunchcontrol.try_cancel).  The grid has
+// one cluster per tile; a running pair, instead of walking a static stride of tiles, CANCELS a not-yet-launched cluster and takes
+// over its tile (the 16-byte answer is multicast into both CTAs' shared memory, a 2-deep ring of answers run by one extra warp).
+// Why: with several batches in flight a GEMM rarely finds all 148 SMs free -- a 64-CTA bounding-loop launch of another batch
+// holds some of them for a few microseconds -- and with the static schedule the pairs that start late finish late by exactly that
+// much while the others idle; here a late pair simply takes fewer tiles.
+constexpr int kThreadsDyn = kThreads + 32;      // + the scheduler warp (warp 10)
+template <typename TOut, bool RELU, bool RESID, bool REDUCE = false, bool ARES = false, int KPS = 1, int VMODE = 0, bool DYN = false>
+__global__ void __launch_bounds__(DYN ? kThreadsDyn : kThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, const float* residual, int ldr,
                int M, int N, int K, int relu, const int* live_rows, const int* rows_dev, const VocabEpi ve) {
@@ -149,7 +156,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;   // [2]   epilogue -> MMA
   uint64_t* a_full_bar = bars + 2 * STAGES + 4;   // [8]  ARES: A slice kb landed (both CTAs' bytes, leader's barrier)
   uint64_t* a_empty_bar = a_full_bar + k2PanelKB;  // [8]  ARES: the panel's last tile has consumed slice kb
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty_bar + k2PanelKB);
+  uint64_t* clc_full_bar = a_empty_bar + k2PanelKB;   // [2]  DYN: the answer of query q has landed (per CTA, 16 tx bytes)
+  uint64_t* clc_empty_bar = clc_full_bar + 2;         // [2]  DYN: every consumer of both CTAs has read it (the leader's is used)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(clc_empty_bar + 2);
+  uint8_t* clc_resp = smem + L::kBarOffset + 384;     // [2] x 16 B answers
+  static_assert(!(ARES && DYN), "the A-resident mode keeps its contiguous static ranges");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk_all = (K + kBK - 1) / kBK;      // a K tail is zero-filled by TMA (out-of-bounds box elements)
@@ -174,6 +185,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int a = 0; a < k2PanelKB; ++a) {
         mbar_init(smem_u32(&a_full_bar[a]), 1);
         mbar_init(smem_u32(&a_empty_bar[a]), 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(smem_u32(&clc_full_bar[a]), 1);
+        // consumers of an answer: TMA thread + 8 epilogue warps per CTA, the leader's MMA thread and scheduler thread
+        mbar_init(smem_u32(&clc_empty_bar[a]), 2 * 9 + 2);
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -200,12 +216,79 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int it_end = ARES ? (int)(((long long)(cid + 1) * ntiles) / ncl) : ntiles;
   const int it_step = ARES ? 1 : ncl;
   uint8_t* ring = smem + L::kRingOffset;
+  // ---- DYN: the tile sequence of this pair = its own cluster id, then the ids of the clusters it cancels ----------------------
+  // Reads answer q (ring slot q & 1): >= 0 the cancelled cluster's id (= its tile), -1 no pending cluster is left.  `warp_wide`:
+  // all 32 lanes call it (epilogue warps), lane 0 releases the slot.
+  auto clc_read = [&](int q) -> int {
+    const int slot = q & 1;
+    mbar_wait(smem_u32(&clc_full_bar[slot]), (uint32_t)(q >> 1) & 1u);
+    uint32_t valid = 0, cx = 0;
+    asm volatile(
+        "{\n\t.reg .pred p1;\n\t.reg .b128 resp;\n\t.reg .b32 d1, d2;\n\t"
+        "ld.shared.b128 resp, [%2];\n\t"
+        "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, resp;\n\t"
+        "selp.u32 %0, 1, 0, p1;\n\t"
+        "mov.u32 %1, 0;\n\t"
+        "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%1, d1, d2, _}, resp;\n\t}"
+        : "=r"(valid), "=r"(cx)
+        : "r"(smem_u32(clc_resp + slot * 16))
+        : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // our read precedes the next answer's (async proxy) write
+    return valid ? (int)(cx >> 1) : -1;
+  };
+  auto clc_release = [&](int q) {
+    const uint32_t eb = smem_u32(&clc_empty_bar[q & 1]);
+    if (rank == 0) mbar_arrive(eb); else mbar_arrive_cluster(eb, 0);
+  };
+  auto next_item_thread = [&](int item, int& q) -> int {          // single-thread roles
+    if constexpr (!DYN) return item + it_step;
+    const int nx = clc_read(q);
+    clc_release(q);
+    ++q;
+    return nx;
+  };
+  auto next_item_warp = [&](int item, int& q) -> int {            // epilogue warps: every lane reads, lane 0 releases
+    if constexpr (!DYN) return item + it_step;
+    const int nx = clc_read(q);
+    __syncwarp();
+    if (lane == 0) clc_release(q);
+    ++q;
+    return nx;
+  };
+  const int item0 = DYN ? cid : it_begin;
+  auto item_live = [&](int item) { return DYN ? item >= 0 : item < it_end; };
+  if constexpr (DYN) {
+    if (warp == 10 && lane == 0 && rank == 0) {
+      // scheduler: one query in flight, at most two answers ahead of the slowest consumer
+      for (int q = 0;; ++q) {
+        const int slot = q & 1;
+        mbar_wait(smem_u32(&clc_empty_bar[slot]), ((uint32_t)(q >> 1) & 1u) ^ 1u);
+        const uint32_t fb = smem_u32(&clc_full_bar[slot]);
+        mbar_expect_tx(fb, 16);                                    // arm both CTAs' barriers, then ask
+        asm volatile(
+            "{\n\t.reg .b32 ra;\n\t"
+            "mapa.shared::cluster.u32 ra, %0, 1;\n\t"
+            "mbarrier.arrive.expect_tx.shared::cluster.b64 _, [ra], 16;\n\t}"
+            ::"r"(fb)
+            : "memory");
+        asm volatile(
+            "clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 [%0], [%1];"
+            ::"r"(smem_u32(clc_resp + slot * 16)), "r"(fb)
+            : "memory");
+        const int nx = clc_read(q);
+        clc_release(q);
+        if (nx < 0) break;                                         // (a query after a failed one is undefined)
+      }
+    }
+  }
 
   if (warp == 0) {
     if (lane == 0) {
       int it = 0, pc = 0;                          // ring position; ARES: row panels this pair has finished
+      int q = 0;
       PROF_DECL(w_slot = 0);
-      for (int item = it_begin; item < it_end; item += it_step) {
+      for (int item = item0; item_live(item); item = next_item_thread(item, q)) {
+        if (DYN && item >= ntiles) continue;       // (a tile beyond the device-side row count)
         const int tile = item % ntiles_mn, kb0 = (item / ntiles_mn) * nk_per, kb1 = min(nk_all, kb0 + nk_per);
         const int m0 = (tile / tiles_n) * 2 * kBM + (int)rank * kBM, n0 = (tile % tiles_n) * BN;
         const bool first = ARES && (item == it_begin || tile % tiles_n == 0);
@@ -246,9 +329,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * kBM, BN, A_MN, B_MN);
-      int it = 0, t = 0, pc = 0;
+      int it = 0, t = 0, pc = 0, q = 0;
       PROF_DECL(w_acc = 0, w_full = 0, t_begin = PROF_T());
-      for (int item = it_begin; item < it_end; item += it_step, ++t) {
+      for (int item = item0; item_live(item); item = next_item_thread(item, q)) {
+        if (DYN && item >= ntiles) continue;
         const int kb0 = (item / ntiles_mn) * nk_per, kb1 = min(nk_all, kb0 + nk_per);
         const int tile_n = (item % ntiles_mn) % tiles_n;
         const bool first = ARES && (item == it_begin || tile_n == 0);
@@ -287,6 +371,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         umma_commit_2sm(smem_u32(&tmem_full_bar[as]));   // accumulator complete: both CTAs' epilogues
         if (last) ++pc;
+        ++t;
       }
 #ifdef BOFI_GEMM_PROF
       if (t > 0) {
@@ -295,7 +380,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
 #endif
     }
-  } else {
+  } else if (warp < 10) {
     // Epilogue: TMEM -> registers (one accumulator row per thread) -> bias / ReLU / residual -> swizzled smem
     // staging tile (32 rows x 128 B) -> TMA store.  Full-line coalesced writes, M / N tails clipped by the
     // tensor map.  Eight warps: warp `quad + 4*half + 2` owns TMEM lanes [32*quad, +32) and the column chunks
@@ -307,9 +392,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // while; waiting for the PREVIOUS store (not the one before it) stalled the epilogue (36 % of the kernel's stall samples)
     const uint32_t sbuf0 = smem_u32(smem + L::kOutOffset + (warp - 2) * (k2Staging * 4096));
     int nstore = 0;
-    int t = 0;
+    int t = 0, q = 0;
     PROF_DECL(w_tfull = 0, w_stage = 0, w_tld = 0, t_math = 0, t_store = 0, t_arrive = 0, t_begin = PROF_T());
-    for (int item = it_begin; item < it_end; item += it_step, ++t) {
+    for (int item = item0; item_live(item); item = next_item_warp(item, q)) {
+      if (DYN && item >= ntiles) continue;
       const int tile = item % ntiles_mn;
       const int m0 = (tile / tiles_n) * 2 * kBM + (int)rank * kBM, n0 = (tile % tiles_n) * BN;
       const int as = t & 1;
@@ -579,6 +665,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #ifdef BOFI_GEMM_PROF
       t_arrive += PROF_T() - t_a0;
 #endif
+      ++t;
     }
 #ifdef BOFI_GEMM_PROF
     if (warp == 2 && lane == 0 && t > 0 && rank == 0) {
@@ -599,23 +686,33 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 
-template <typename TOut, bool RELU, bool RESID, bool REDUCE = false, bool ARES = false, int KPS = 1, int VMODE = 0>
-inline cudaError_t launch2(cudaStream_t s, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const float* bias,
-                           const float* residual, int ldr, int M, int N, int K, int relu, const int* live_rows, const int* rows_dev,
-                           const VocabEpi& ve = VocabEpi()) {
+// BOFI_GEMM_DYN=1: dynamic tile scheduling (cluster launch control), see the kernel's DYN note
+inline bool gemm_dyn() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BOFI_GEMM_DYN");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+template <typename TOut, bool RELU, bool RESID, bool REDUCE, bool ARES, int KPS, int VMODE, bool DYN>
+inline cudaError_t launch2_impl(cudaStream_t s, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const float* bias,
+                                const float* residual, int ldr, int M, int N, int K, int relu, const int* live_rows, const int* rows_dev,
+                                const VocabEpi& ve) {
   static PerDevice<bool> configured_dev;
   bool& configured = configured_dev.get();
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<TOut, RELU, RESID, REDUCE, ARES, KPS, VMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2T<ARES, KPS>::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<TOut, RELU, RESID, REDUCE, ARES, KPS, VMODE, DYN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2T<ARES, KPS>::kTotal);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const int pairs = ((M + 2 * kBM - 1) / (2 * kBM)) * ((N + k2BN - 1) / k2BN);
   int clusters = num_sms() / 2;
-  if (pairs < clusters) clusters = pairs;
+  if (pairs < clusters || DYN) clusters = pairs;          // DYN: one cluster per tile, the running ones cancel the pending ones
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * clusters);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(DYN ? kThreadsDyn : kThreads);
   cfg.dynamicSmemBytes = Smem2T<ARES, KPS>::kTotal;
   cfg.stream = s;
   cudaLaunchAttribute at[2];
@@ -627,7 +724,17 @@ inline cudaError_t launch2(cudaStream_t s, const CUtensorMap& tmA, const CUtenso
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  return cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<TOut, RELU, RESID, REDUCE, ARES, KPS, VMODE>, tmA, tmB, tmC, bias, residual, ldr, M, N, K, relu, live_rows, rows_dev, ve);
+  return cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<TOut, RELU, RESID, REDUCE, ARES, KPS, VMODE, DYN>, tmA, tmB, tmC, bias, residual, ldr, M, N, K, relu, live_rows, rows_dev, ve);
+}
+
+template <typename TOut, bool RELU, bool RESID, bool REDUCE = false, bool ARES = false, int KPS = 1, int VMODE = 0>
+inline cudaError_t launch2(cudaStream_t s, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const float* bias,
+                           const float* residual, int ldr, int M, int N, int K, int relu, const int* live_rows, const int* rows_dev,
+                           const VocabEpi& ve = VocabEpi()) {
+  if constexpr (!ARES) {
+    if (gemm_dyn()) return launch2_impl<TOut, RELU, RESID, REDUCE, ARES, KPS, VMODE, true>(s, tmA, tmB, tmC, bias, residual, ldr, M, N, K, relu, live_rows, rows_dev, ve);
+  }
+  return launch2_impl<TOut, RELU, RESID, REDUCE, ARES, KPS, VMODE, false>(s, tmA, tmB, tmC, bias, residual, ldr, M, N, K, relu, live_rows, rows_dev, ve);
 }
 
 // Same contract as gemm_tc (K-major A [M,K], W [N,K]).  `want_ares`: A-resident tiles where the shape allows (opt-in,
