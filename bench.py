@@ -247,7 +247,8 @@ def workload_config(a, world):
             "regions": ("adaptive 10..%d, prefix masks" % a.regions) if a.adaptive else a.regions,
             "parallelism": "image-sharded replicas x%d" % world,
             "l2": "per-step input (%.0f MB/GPU as fp32) and activations exceed the 126 MB L2" % (a.batch * a.regions * 2048 * 4 / 1e6),
-            "logprobs": "skipped" if a.no_logprobs else "materialised [B,20,V] fp32"}
+            "logprobs": "skipped" if a.no_logprobs else ("materialised [B,20,V] fp32" + (
+                "" if a.mode != "NAIC" else ", rows on a 16-byte pitch (the [:, :, :V] view of a [B,20,9492] buffer, bofi_decode_ex)"))}
 
 
 def reference_arm(a, cfg, config):

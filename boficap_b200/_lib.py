@@ -47,6 +47,7 @@ _SIGNATURES = {
     "bofi_check_masks": (C.c_int, [_P, _P, C.POINTER(C.c_int32)]),
     "bofi_sample_host_async_ex": (C.c_int, [_P, _P, _I, _I, _I, _P, _I, _P, _I, _I, _P, _P, _P, _P, _P]),
     "bofi_decode": (C.c_int, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "bofi_decode_ex": (C.c_int, [_P, _P, _I, _I, _I, _P, _P, C.c_int64, _P, _P, _P]),
     "bofi_sample_host": (C.c_int, [_P, _P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P]),
     "bofi_sample_host_async": (C.c_int, [_P, _P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P]),
     "bofi_set_decode_stats": (C.c_int, [_P, _P, _P]),

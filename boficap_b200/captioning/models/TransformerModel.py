@@ -331,7 +331,10 @@ class TransformerModel(nn.Module):
         if _stats is not None:
             eng.set_decode_stats(*_stats)
         want_logprobs = _stats is None and bool(opt.get("bofi_logprobs", True))
-        seq, logp, pnum, plen, psyn = eng.decode(train_mode, sample_n, output_logsoftmax, want_logprobs)
+        # NAIC log-probs: rows padded to a 16-byte pitch and returned as the [:, :, :V] view (TMA stores; engine.py:decode) unless
+        # opt['bofi_dense_logprobs'] asks for the reference's contiguous tensor
+        seq, logp, pnum, plen, psyn = eng.decode(train_mode, sample_n, output_logsoftmax, want_logprobs,
+                                                 dense_logprobs=bool(opt.get("bofi_dense_logprobs", False)))
         eng.set_decode_stats(None, None)
         eng.set_sampling("greedy")
         ev1.record(stream)

@@ -121,6 +121,7 @@ struct bofi_engine {
   bool gemm2 = true;                   // 2-CTA (cta_group::2) 256 x 256 tile pairs for the wide GEMMs; BOFI_GEMM2=0: 1-CTA tiles
   int ln_fuse_min_rows = 4096;         // below this the panel LayerNorm would be repeated by too many CTAs
   bool ln_fuse_small = false;          // BOFI_LNFUSE_SMALL=1: the same for the M <= 2048 launches of the bounding loop only (one launch less per LayerNorm)
+  int logp_ld = 0;                     // pitch (floats) of the caller's log-prob rows for the running bofi_decode_ex call, 0 = dense V
   bool bound_prio = false;             // BOFI_BOUND_PRIO=1: graph replays (bounding loop, SAIC step loop) on a high-priority stream (measured slower: the GEMMs of the other batches then start on fewer SMs)
   bool ln_epi = false;                 // BOFI_LNEPI=1: residual GEMM + the LayerNorm after it as ONE launch for M >= 2048 (gemm_tc2_ln.cuh; parity-green, measured slower: off)
   bool ln_fuse = false;                // BOFI_LNFUSE=1: LayerNorm fused into the consuming tcgen05 GEMM (gemm_ln_tc.cuh; measured slower, off)
@@ -1084,7 +1085,9 @@ static int decode_naic(bofi_engine* e, cudaStream_t s, int sn, int output_logsof
         CU_TRY(cudaGetLastError());
         if (logprobs) {
           ve.out = logprobs;
-          ve.ldo = e->V;
+          ve.ldo = e->logp_ld > 0 ? e->logp_ld : e->V;
+          // rows on a 16-byte grid (a pitch padded to a multiple of four floats): plain TMA stores instead of row-segment stores
+          ve.tma_out = (ve.ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(logprobs) & 15) == 0) ? 1 : 0;
           ve.mx = e->sa_mx.as<float>();
           ve.lse = e->sa_lse.as<float>();
           ve.do_lsm = output_logsoftmax;
@@ -1108,7 +1111,7 @@ static int decode_naic(bofi_engine* e, cudaStream_t s, int sn, int output_logsof
         RC_TRY((linear<T, float>(e, s, e->y.as<T>() + (size_t)r0 * kD, kD, e->generator, nullptr, 0, e->logits.as<float>(), e->Vpad, n, 0, nullptr)));
       ProfScope prof(e, s, PC_VOCAB, 0.0, 0.0);
       launch_k(vocab_epilogue_kernel, n, kVocabThreads, 0, s, e->logits.as<float>(), e->Vpad, e->V, logprobs, seq, e->st.last, -1, L,
-               output_logsoftmax, nullptr, e->sampler, e->stat_entropy, e->stat_logp, r0, (e->bf16_mode && !e->stat_entropy) ? 1 : 0);
+               output_logsoftmax, nullptr, e->sampler, e->stat_entropy, e->stat_logp, r0, (e->bf16_mode && !e->stat_entropy) ? 1 : 0, e->logp_ld);
       CU_TRY(cudaGetLastError());
     }
   }
@@ -1569,7 +1572,15 @@ int bofi_check_masks(bofi_handle_t e, void* stream, int32_t* bad) {
 
 int bofi_decode(bofi_handle_t e, void* stream, int32_t mode, int32_t sn, int32_t output_logsoftmax, int64_t* seq, float* logprobs,
                 int32_t* phrase_num, int32_t* phrase_length, int64_t* phrase_syn) {
+  return bofi_decode_ex(e, stream, mode, sn, output_logsoftmax, seq, logprobs, 0, phrase_num, phrase_length, phrase_syn);
+}
+
+int bofi_decode_ex(bofi_handle_t e, void* stream, int32_t mode, int32_t sn, int32_t output_logsoftmax, int64_t* seq, float* logprobs,
+                   int64_t logprob_ld, int32_t* phrase_num, int32_t* phrase_length, int64_t* phrase_syn) {
   if (!e || !seq || !phrase_num || !phrase_length || !phrase_syn) return fail(BOFI_ERR_INVALID, "null argument");
+  if (logprob_ld != 0 && (logprob_ld < e->V || logprob_ld > (1 << 20))) return fail(BOFI_ERR_INVALID, "log-prob pitch %lld (0 or >= V = %d)", (long long)logprob_ld, e->V);
+  if (logprob_ld != 0 && logprob_ld != e->V && mode != BOFI_MODE_NAIC) return fail(BOFI_ERR_INVALID, "a padded log-prob pitch is an option of the NAIC path");
+  e->logp_ld = (logprob_ld == e->V) ? 0 : (int)logprob_ld;
   if (!e->have_memory) return fail(BOFI_ERR_STATE, "bofi_decode needs a preceding bofi_encode");
   if (sn < 1) return fail(BOFI_ERR_INVALID, "sample_n %d", sn);
   if (mode != BOFI_MODE_NAIC && mode != BOFI_MODE_SAIC) return fail(BOFI_ERR_INVALID, "mode %d (NAIC = 0, SAIC = 1)", mode);

@@ -127,6 +127,7 @@ struct VocabEpi {
   const float* mx = nullptr; // VMODE 2: per-row max and log-sum-exp from vocab_merge_kernel
   const float* lse = nullptr;
   int do_lsm = 0;            // 0: raw logits (output_logsoftmax = 0)
+  int tma_out = 0;           // VMODE 2: the rows of `out` are 16-byte aligned (padded pitch): plain TMA stores through tmC
 };
 
 // DYN: dynamic tile scheduling through the hardware's cluster launch control (clusterlaunchcontrol.try_cancel).  The grid has
@@ -599,6 +600,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
             for (int j = 0; j < CC; ++j) r[j] = __float_as_uint((__uint_as_float(r[j]) - mx_row) - lse_row);
           }
+          if (!ve.tma_out) {
           __syncwarp();                     // the previous chunk's row stores have read the staging tile
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -615,6 +617,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (col_ok && m0 + quad * 32 + rr < M) __stcs(orow + (size_t)rr * (size_t)ve.ldo, v);
           }
           continue;
+          }
+          // padded pitch: fall through to the staging tile + TMA store of the plain epilogue (columns >= N are clipped by tmC)
         }
         // this warp's staging tile must have been read out by the TMA engine (its previous store); on the residual path
         // every lane must also be done reading its residual row before the tile is overwritten
@@ -785,9 +789,16 @@ inline cudaError_t gemm_tc2_vocab(cudaStream_t s, const bf16* A, int lda, const 
   const CUtensorMap* tmA = cached_tmap_kblocks(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBM, 2);
   const CUtensorMap* tmB = cached_tmap_kblocks(W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, k2BN / 2, 2);
   if (!tmA || !tmB) return cudaErrorInvalidValue;
-  // no TMA store in either mode: the C tensor map is a placeholder (never dereferenced)
+  // no TMA store in the statistics pass, nor in the log-prob pass on a dense [M, V] tensor (rows only 4-byte aligned): the C
+  // tensor map is a placeholder there (never dereferenced)
   if (vmode == 1) return launch2<float, false, false, false, false, 2, 1>(s, *tmA, *tmB, *tmA, bias, nullptr, 0, M, N, K, 0, nullptr, nullptr, ve);
-  if (vmode == 2) return launch2<float, false, false, false, false, 2, 2>(s, *tmA, *tmB, *tmA, bias, nullptr, 0, M, N, K, 0, nullptr, nullptr, ve);
+  if (vmode == 2) {
+    if (!ve.tma_out) return launch2<float, false, false, false, false, 2, 2>(s, *tmA, *tmB, *tmA, bias, nullptr, 0, M, N, K, 0, nullptr, nullptr, ve);
+    const CUtensorMap a = *tmA, b = *tmB;           // (a third lookup follows: copies, see cached_tmap)
+    const CUtensorMap* tmC = cached_tmap(ve.out, (uint64_t)M, (uint64_t)N, (uint64_t)ve.ldo, 32, 4);
+    if (!tmC) return cudaErrorInvalidValue;
+    return launch2<float, false, false, false, false, 2, 2>(s, a, b, *tmC, bias, nullptr, 0, M, N, K, 0, nullptr, nullptr, ve);
+  }
   return cudaErrorInvalidValue;
 }
 

@@ -703,7 +703,7 @@ __global__ void __launch_bounds__(kVocabThreads, BOFI_VOCAB_OCC)
 vocab_epilogue_kernel(const float* __restrict__ logits, int ldl, int V, float* __restrict__ logp_out,
                       long long* __restrict__ seq_out, const int* __restrict__ total_len, int total_off, int L,
                       int do_logsoftmax, int* __restrict__ tok_out_i32, Sampler sp, float* __restrict__ slot_entropy,
-                      float* __restrict__ slot_logp, int row0, int fast_exp) {
+                      float* __restrict__ slot_logp, int row0, int fast_exp, int ldo) {
   pdl_enter();
   // The whole row lives in registers: logits are read from HBM exactly once (128-bit loads, all independent),
   // max / argmax / sum-exp are block reductions, and the log-probs are written once.
@@ -842,7 +842,7 @@ vocab_epilogue_kernel(const float* __restrict__ logits, int ldl, int V, float* _
     __syncthreads();
   }
   if (logp_out) {
-    float* o = logp_out + (size_t)row * V;
+    float* o = logp_out + (size_t)row * (size_t)(ldo > 0 ? ldo : V);     // ldo: pitch of the caller's rows (bofi_decode_ex)
     // Rows of the caller's [rows, L, V] tensor are only 4-byte aligned (V = 9491).  Every thread re-cuts its float4 on the
     // 16-byte grid of the OUTPUT: with k = (address of the row) mod 4 floats, the aligned vector that ends inside this
     // thread's float4 is {last k values of the previous float4, first 4 - k of its own}.  The previous float4 comes from

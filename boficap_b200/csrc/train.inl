@@ -331,7 +331,7 @@ static int t_dec_fwd(bofi_engine* e, cudaStream_t s, TrainState* ts, DecTape& dt
   RC_TRY((linear<T, float>(e, s, yf, kD, e->generator, nullptr, 0, logits, e->Vpad, rows, 0, nullptr)));
   if (logp_out || seq_out) {
     launch_k(vocab_epilogue_kernel, rows, kVocabThreads, 0, s, (const float*)logits, e->Vpad, e->V, logp_out, seq_out,
-             total_len, -1, T_, 1, (int*)nullptr, sampler, (float*)nullptr, (float*)nullptr, 0, 0);
+             total_len, -1, T_, 1, (int*)nullptr, sampler, (float*)nullptr, (float*)nullptr, 0, 0, 0);
     CU_TRY(cudaGetLastError());
   }
   return BOFI_OK;

@@ -82,8 +82,11 @@ class BofiEngine:
         self._batch = (B, R, att_feats, att_len)      # keep inputs alive until decode is enqueued
         return memory
 
-    def decode(self, mode="NAIC", sample_n=1, output_logsoftmax=1, want_logprobs=True, out=None):
-        """out: optional (seq, logp, pnum, plen, psyn) tensors of a previous call with the same shapes to write into."""
+    def decode(self, mode="NAIC", sample_n=1, output_logsoftmax=1, want_logprobs=True, out=None, dense_logprobs=False):
+        """out: optional (seq, logp, pnum, plen, psyn) tensors of a previous call with the same shapes to write into.
+        NAIC log-probs come back as `buf[:, :, :V]` of a [rows, L, V rounded up to a multiple of 4] allocation unless
+        dense_logprobs=True: every row then starts on a 16-byte boundary and the library writes the tensor with TMA stores
+        (bofi_decode_ex).  Same values and indexing as the reference's seq_logprob, not contiguous (`.contiguous()` if needed)."""
         B = self._batch[0]
         rows, L, V = B * sample_n, self.cfg.seq_length, self.cfg.tgt_vocab
         dev = self.device
@@ -91,13 +94,17 @@ class BofiEngine:
             seq, logp, pnum, plen, psyn = out
         else:
             seq = torch.empty(rows, L, dtype=torch.int64, device=dev)
-            logp = torch.empty(rows, L, V, dtype=torch.float32, device=dev) if want_logprobs else None
+            Vp = V if (dense_logprobs or mode != "NAIC") else (V + 3) // 4 * 4
+            logp = torch.empty(rows, L, Vp, dtype=torch.float32, device=dev)[:, :, :V] if want_logprobs else None
             pnum = torch.empty(rows, dtype=torch.int32, device=dev)
             plen = torch.empty(rows, L, dtype=torch.int32, device=dev)
             psyn = torch.empty(rows, L, dtype=torch.int64, device=dev)
+        ld = int(logp.stride(1)) if logp is not None else 0
+        if logp is not None:
+            assert logp.stride(2) == 1 and logp.stride(0) == L * ld, "log-prob buffer: [rows, L, V] rows with a common pitch"
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.bofi_decode(self.handle, self._stream(), _lib.MODE[mode], sample_n, int(output_logsoftmax),
-                                            _ptr(seq), _ptr(logp), _ptr(pnum), _ptr(plen), _ptr(psyn)))
+            _lib.check(self.lib.bofi_decode_ex(self.handle, self._stream(), _lib.MODE[mode], sample_n, int(output_logsoftmax),
+                                               _ptr(seq), _ptr(logp), ld, _ptr(pnum), _ptr(plen), _ptr(psyn)))
         return seq, logp, pnum, plen, psyn
 
     def sample_host(self, att_feats, att_len=None, mode="NAIC", sample_n=1, output_logsoftmax=1, out=None, want_logprobs=False,

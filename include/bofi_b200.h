@@ -120,6 +120,15 @@ int bofi_decode(bofi_handle_t h, void* stream, int32_t mode, int32_t sample_n, i
                 int64_t* seq, float* logprobs, int32_t* phrase_num, int32_t* phrase_length,
                 int64_t* phrase_syn);
 
+/* bofi_decode with a PITCH for the log-prob rows: logprobs is dev f32 [rows, L, logprob_ld] of which the first V columns of
+ * every row are written (logprob_ld = 0 or V: the dense tensor of bofi_decode).  NAIC only.  With a pitch that is a multiple
+ * of four floats (e.g. 9492 for V = 9491) every row starts on a 16-byte boundary and the tcgen05 engine writes the tensor with
+ * TMA stores instead of 4-byte row-segment stores -- what `seq_logprob[:, :, :V]` of a padded allocation is in PyTorch terms
+ * (same values, same indexing, a strided view). */
+int bofi_decode_ex(bofi_handle_t h, void* stream, int32_t mode, int32_t sample_n, int32_t output_logsoftmax,
+                   int64_t* seq, float* logprobs, int64_t logprob_ld, int32_t* phrase_num, int32_t* phrase_length,
+                   int64_t* phrase_syn);
+
 /* eval_split's entropy / perplexity (captioning/utils/eval_utils.py:183-184) without materialising seq_logprob:
  * when set (dev f32 [rows, L] each; NULL, NULL switches it off), the following bofi_decode calls also write, per slot,
  *   slot_entropy = -sum_v p_v log p_v   and   slot_logp = log p of the token written to seq

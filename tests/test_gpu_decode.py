@@ -305,3 +305,25 @@ def test_layernorm_epilogue_path_matches_two_launch_path(monkeypatch, capsys):
             assert err < 2e-2, err
     new.close()
     old.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_padded_logprob_pitch_equals_dense_tensor(precision):
+    """bofi_decode_ex: log-prob rows on a 16-byte pitch (V = 9491 -> 9492 floats; the tcgen05 engine then writes them with TMA
+    stores) hold exactly the values of the dense [rows, L, V] tensor; what comes back is the [:, :, :V] view."""
+    cfg = BofiConfig()
+    eng = engine_for(cfg, "s_cap", precision)
+    for (B, R, sn, lsm) in ((130, 36, 1, 1), (24, 36, 2, 0)):
+        fc, att, masks = synth.synth_inputs(B, R, seed=80 + B)
+        eng.encode(att.cuda(), None)
+        dense = eng.decode("NAIC", sn, lsm, True, dense_logprobs=True)
+        eng.encode(att.cuda(), None)
+        padded = eng.decode("NAIC", sn, lsm, True)
+        torch.cuda.synchronize()
+        assert dense[1].is_contiguous() and not padded[1].is_contiguous()
+        assert padded[1].shape == dense[1].shape and padded[1].stride(1) == (cfg.tgt_vocab + 3) // 4 * 4
+        assert torch.equal(padded[0], dense[0])
+        assert torch.equal(torch.nan_to_num(padded[1]), torch.nan_to_num(dense[1]))
+    # SAIC keeps the dense tensor
+    eng.encode(att.cuda(), None)
+    assert eng.decode("SAIC", 1, 1, True)[1].is_contiguous()
