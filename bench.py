@@ -106,6 +106,44 @@ def measured_peaks():
     return 1590.0, 1400.0, 6650.0, "fallback"
 
 
+def xe_eager_bar(cfg, sd, att, masks, bt, iters=2):
+    """The GPU bar of the XE step: the reference algorithm (oracle forward_xe + LanguageModelCriterion_UIC + autograd backward) as eager
+    PyTorch on the same B200, same batch, dropout off, fp32 and bf16 autocast.  No optimiser step in the timed region."""
+    from oracle.bofi_oracle import BofiOracle, OracleConfig
+    out = {}
+    dev = lambda t: t.cuda() if t is not None else None
+    for name, ctx in (("bf16_autocast", torch.autocast("cuda", dtype=torch.bfloat16)), ("fp32", torch.autocast("cuda", enabled=False))):
+        o = BofiOracle(sd, OracleConfig(**cfg.to_dict()), device="cuda")
+        for k, v in o.sd.items():
+            if k != "model.pos_embed.pe":
+                v.requires_grad_(True)
+
+        def step():
+            with ctx:
+                outs = o.forward_xe(dev(att), dev(masks), dev(bt["labels"]), dev(bt["phrase_num"]), dev(bt["phrase_length"]),
+                                    dev(bt["extend_phrase_syn_seq"]), dev(bt["extend_phrase_seq"]), dev(bt["extend_phrase_seq_mask"]))
+                loss, _ = o.loss_xe([t.float() for t in outs], bt["phrase_num"], bt["phrase_length"], bt["phrase_syn"], bt["labels"])
+            loss.backward()
+            for v in o.sd.values():
+                v.grad = None
+            return float(loss)
+        try:
+            step()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(iters):
+                loss = step()
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / iters
+            out[name] = {"value": att.shape[0] / dt, "unit": "images/s", "ms_per_step": dt * 1e3, "loss": loss}
+        except Exception as ex:                 # e.g. out of memory: reported, not fatal
+            out[name] = {"unavailable": "%s: %s" % (type(ex).__name__, str(ex)[:200])}
+        del o
+        torch.cuda.empty_cache()
+    out["what"] = "oracle/bofi_oracle.py forward_xe + loss_xe + backward on cuda:0 (eager PyTorch, cuBLAS / ATen), dropout off, %d calls each" % iters
+    return out
+
+
 def bench_xe(a, rank, local_rank, world):
     """Config 5 of BASELINE.json: uic_sd XE training step, `--batch` images x 5 captions per GPU (default 256), forward +
     LanguageModelCriterion_UIC + backward in the library, NCCL all-reduce of the flat gradient buffer, Adam on the flat
@@ -185,6 +223,12 @@ def bench_xe(a, rank, local_rank, world):
     model.xe_step(*args)
     prof = eng.get_profile()
     eng.set_profiling(False)
+    eager = None
+    if rank == 0 and world == 1 and not a.no_extras:
+        try:
+            eager = xe_eager_bar(cfg, synth.synth_state_dict(cfg, 0, a.calib), att, masks, bt)
+        except Exception as ex:
+            eager = {"unavailable": "%s: %s" % (type(ex).__name__, str(ex)[:200])}
     if rank == 0:
         g = prof["gemm_tcgen05"] if a.precision == "bf16" else prof["gemm_ffma"]
         burst, sustained, hbm, how = measured_peaks()
@@ -199,6 +243,7 @@ def bench_xe(a, rank, local_rank, world):
                            "parallelism": "data-parallel replicas x%d, NCCL all-reduce of the %.0f MB flat gradient buffer in %d + 1 buckets, the decoder-side "
                                           "buckets overlapped with the encoder's backward pass" % (world, flat_g.numel() * 4 / 1e6, a.buckets)},
                 "loss_first": first, "loss_last": float(losses[0]), "gpu_launches": launches * a.steps, "clocks": clocks,
+                "gpu_eager": eager,
                 "roofline": {"bound": "tensor", "kernel": "gemm_tc2_kernel / gemm_tc_kernel (tcgen05), all %d launches of a step" % g["launches"],
                              "achieved": tf, "peak": sustained, "unit": "TFLOP/s", "frac": tf / sustained, "traffic": None,
                              "share_of_profiled_kernel_time": g["ms"] / total_ms if total_ms else None,

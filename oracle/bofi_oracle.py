@@ -348,14 +348,15 @@ class BofiOracle:
         """get_predict_phrase_length_syn_SA / _NA (TransformerModel.py:476-513, :532-565): one bounding pass per
         phrase index, every pass over all rows with the mask grown by the ground-truth boxes."""
         N, Lb = phrase_length.shape
-        tgt_mask = torch.zeros(N, Lb, Lb, dtype=torch.bool)
-        len_logp = torch.zeros(N, Lb, LENGTH_DIM)
-        syn_logp = torch.zeros(N, Lb, SYN_DIM)
-        last = torch.ones(N, dtype=torch.long)
+        dev = memory.device                      # (cuda for bench.py's eager bar)
+        tgt_mask = torch.zeros(N, Lb, Lb, dtype=torch.bool, device=dev)
+        len_logp = torch.zeros(N, Lb, LENGTH_DIM, device=dev)
+        syn_logp = torch.zeros(N, Lb, SYN_DIM, device=dev)
+        last = torch.ones(N, dtype=torch.long, device=dev)
         tgt_mask[:, :, 0] = True
         _, ll, _, sl, _ = self.bounding_head(x_in, memory, src_mask, tgt_mask)
-        len_logp[:, 1], syn_logp[:, 1] = ll, sl
-        ar = torch.arange(Lb)
+        len_logp[:, 1], syn_logp[:, 1] = ll.to(len_logp.dtype), sl.to(syn_logp.dtype)
+        ar = torch.arange(Lb, device=dev)
         for i in range(1, int(phrase_num.max())):
             grow = phrase_num > i
             newlast = last + torch.where(grow, phrase_length[:, i], torch.zeros_like(last))
@@ -396,7 +397,7 @@ class BofiOracle:
         na_len, na_syn, last = self._teacher_bounding(self.pos(self.embed("syn_embed", extend_phrase_syn_seq)), memory,
                                                       src_mask, phrase_num, phrase_length)
         L = extend_phrase_seq.shape[1]
-        syn_mask = torch.arange(L)[None, None, :] < (last - 1)[:, None, None]
+        syn_mask = torch.arange(L, device=last.device)[None, None, :] < (last - 1)[:, None, None]
         syn_mask = syn_mask.expand(-1, L, -1)
         bos = torch.full_like(extend_phrase_seq, c.bos_idx)
         na_hidden = self.decoder(self.decoder_input(bos, extend_phrase_syn_seq[:, 1:-1]), memory, src_mask, syn_mask)
