@@ -119,7 +119,7 @@ def xe_eager_bar(cfg, sd, att, masks, bt, iters=2):
                 v.requires_grad_(True)
 
         def step():
-            with ctx:
+            with ctx, torch.device("cuda"):      # index / mask tensors are created on the oracle's device (as BofiOracle.sample does)
                 outs = o.forward_xe(dev(att), dev(masks), dev(bt["labels"]), dev(bt["phrase_num"]), dev(bt["phrase_length"]),
                                     dev(bt["extend_phrase_syn_seq"]), dev(bt["extend_phrase_seq"]), dev(bt["extend_phrase_seq_mask"]))
                 loss, _ = o.loss_xe([t.float() for t in outs], bt["phrase_num"], bt["phrase_length"], bt["phrase_syn"], bt["labels"])

@@ -111,12 +111,12 @@ class BofiOracle:
             att_masks = att_masks[:, :max_len].contiguous()
             x = F.relu(self.lin("att_embed.0", att_feats))
             # pack_wrapper: the module only sees the first `lens[b]` rows; padded rows come back 0
-            keep = torch.arange(max_len)[None, :] < lens[:, None]
+            keep = torch.arange(max_len, device=lens.device)[None, :] < lens[:, None]
             x = x * keep[:, :, None].to(x.dtype)
             mask = att_masks
         else:
             x = F.relu(self.lin("att_embed.0", att_feats))
-            mask = torch.ones(att_feats.shape[:2], dtype=torch.bool)
+            mask = torch.ones(att_feats.shape[:2], dtype=torch.bool, device=att_feats.device)
         return x, mask.unsqueeze(-2)
 
     # ---- A2: encoder ----------------------------------------------------------------------
