@@ -377,7 +377,9 @@ def main():
     ap.add_argument("--workload", default="decode", choices=["decode", "xe"],
                     help="decode = BASELINE.json's headline metric; xe = XE training step (config 5: 256 images x 5 captions per GPU)")
     ap.add_argument("--no-dropout", action="store_true", help="xe workload: eval() arithmetic (dropout off)")
-    ap.add_argument("--depth", type=int, default=3, help="batches in flight (engine handles x streams, boficap_b200/pipeline.py)")
+    ap.add_argument("--depth", type=int, default=3, help="engine handles x streams in flight (boficap_b200/pipeline.py)")
+    ap.add_argument("--group", type=int, default=2, help="consecutive batches decoded by ONE library call on a slot, every batch with its own "
+                                                          "fill window (bofi_set_shard): bit-identical results, one bounding loop per group")
     ap.add_argument("--host-dtype", default="bf16", choices=["bf16", "fp16", "fp32"], help="element type of the pinned host features of the e2e leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary legs (fp32-host e2e, drop-in class, GPU-eager bar, CPU baseline)")
     ap.add_argument("--buckets", type=int, default=4, help="xe workload: gradient all-reduce buckets overlapped with the backward pass")
@@ -416,7 +418,7 @@ def main():
     from boficap_b200.pipeline import BofiPipeline
 
     sd = synth.synth_state_dict(cfg, 0, a.calib)
-    pipe = BofiPipeline(cfg, sd, local_rank, a.precision, depth=max(1, a.depth))
+    pipe = BofiPipeline(cfg, sd, local_rank, a.precision, depth=max(1, a.depth), group=max(1, a.group) if a.mode == "NAIC" else 1)
     eng = pipe.engines[0]
     B, R = a.batch, a.regions
     fc, att_host, masks = synth.synth_inputs(B, R, seed=1 + rank, adaptive=a.adaptive)
@@ -500,13 +502,16 @@ def main():
         pipe.fork_from(main)
         ts = []
         for _ in range(n):
-            t = pipe.submit_device(att, att_len, a.mode, 1, 1, want_lp, reuse_outputs=True)
-            finish_ticket(t, pipe.streams[t.slot])
-            ts.append(t)
+            ts.append(pipe.submit_device(att, att_len, a.mode, 1, 1, want_lp, reuse_outputs=True))
+            for u in pipe.just_launched:                     # (a grouped submission is enqueued when its group is complete)
+                finish_ticket(u, pipe.streams[u.slot])
+        pipe.flush()
+        for u in pipe.just_launched:
+            finish_ticket(u, pipe.streams[u.slot])
         pipe.join_into(main)
         return ts
 
-    for t in run_device(max(a.warmup, 2 * pipe.depth)):     # every slot: eager run, graph capture, replay
+    for t in run_device(max(a.warmup, 2 * pipe.depth * pipe.group)):     # every slot: eager run, graph capture, replay
         t.wait()
     torch.cuda.synchronize()
     info = eng.decode_info()
@@ -524,7 +529,7 @@ def main():
     ms = ev0.elapsed_time(ev1)
     sampler.pause()
     out = tickets[-1].out
-    for t in tickets[-pipe.depth:]:                          # every slot reproduces the stand-alone decode
+    for t in tickets[-pipe.depth * pipe.group:]:             # every slot (and every batch of a group) reproduces the stand-alone decode
         assert torch.equal(t.out[0], ref_seq), "pipelined decode differs from the stand-alone decode"
     del tickets
 
@@ -537,7 +542,7 @@ def main():
         return ts
 
     def time_host(feats):
-        for t in run_host(2 * pipe.depth, feats):
+        for t in run_host(2 * pipe.depth * pipe.group, feats):
             host_out = t.wait()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -713,13 +718,16 @@ def main():
 
     e2e = {"value": e2e_value, "unit": "captions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "ms_per_step": ms_e2e / a.steps, "host_feature_dtype": a.host_dtype,
-           "api": "bofi_sample_host_async_ex, pinned host buffers (%s features), %d batches in flight%s"
-                  % (a.host_dtype, pipe.depth, ", caption all_gather inside the timed region" if world > 1 else "")}
+           "api": "%s, pinned host buffers (%s features), %d batches in flight%s"
+                  % ("bofi_sample_host_async_ex" if pipe.group == 1 else "bofi_stage_part x %d + bofi_sample_staged (batches of a group share one library call)" % pipe.group,
+                     a.host_dtype, pipe.depth * pipe.group, ", caption all_gather inside the timed region" if world > 1 else "")}
     line = {"metric": METRIC, "value": value, "unit": "captions/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": a.precision, "data": "synthetic", "config": config,
-            "in_flight": "%d batches (one engine handle + stream each, round robin)%s"
-                         % (pipe.depth, "; caption all_gather (244 B/image) after every batch, inside the timed region" if world > 1 else ""),
+            "in_flight": "%d batches (%d engine handles + streams, round robin%s)%s"
+                         % (pipe.depth * pipe.group, pipe.depth,
+                            "" if pipe.group == 1 else "; %d consecutive batches of %d share one library call, each with its own fill window" % (pipe.group, B),
+                            "; caption all_gather (244 B/image) after every batch, inside the timed region" if world > 1 else ""),
             "e2e": e2e,
             "e2e_fp32_host": None if ms_e2e32 is None else {
                 "value": world * B * a.steps / (ms_e2e32 / 1e3), "unit": "captions/s", "ms_per_step": ms_e2e32 / a.steps,

@@ -121,6 +121,7 @@ struct bofi_engine {
   bool gemm2 = true;                   // 2-CTA (cta_group::2) 256 x 256 tile pairs for the wide GEMMs; BOFI_GEMM2=0: 1-CTA tiles
   int ln_fuse_min_rows = 4096;         // below this the panel LayerNorm would be repeated by too many CTAs
   bool ln_fuse_small = false;          // BOFI_LNFUSE_SMALL=1: the same for the M <= 2048 launches of the bounding loop only (one launch less per LayerNorm)
+  int shard_images = 0;                // bofi_set_shard: the batch of a call is several batches of this many images (0: one batch)
   int logp_ld = 0;                     // pitch (floats) of the caller's log-prob rows for the running bofi_decode_ex call, 0 = dense V
   bool bound_prio = false;             // BOFI_BOUND_PRIO=1: graph replays (bounding loop, SAIC step loop) on a high-priority stream (measured slower: the GEMMs of the other batches then start on fewer SMs)
   bool ln_epi = false;                 // BOFI_LNEPI=1: residual GEMM + the LayerNorm after it as ONE launch for M >= 2048 (gemm_tc2_ln.cuh; parity-green, measured slower: off)
@@ -988,7 +989,7 @@ static int naic_bound_phase(bofi_engine* e, cudaStream_t s, int sn) {
   if (cluster_loop) {
     RC_TRY(bound_loop_launch(e, s, rows, sn, nsteps));
     ProfScope prof(e, s, PC_OTHER, 0.0, 0.0);
-    launch_k(fill_window_kernel, ceil_div(rows * L, 256), 256, 0, s, e->st, rows, L);
+    launch_k(fill_window_kernel, ceil_div(rows * L, 256), 256, 0, s, e->st, rows, L, e->shard_images * sn);
     CU_TRY(cudaGetLastError());
     return BOFI_OK;
   }
@@ -1006,7 +1007,7 @@ static int naic_bound_phase(bofi_engine* e, cudaStream_t s, int sn) {
 
   {
     ProfScope prof(e, s, PC_OTHER, 0.0, 0.0);
-    launch_k(fill_window_kernel, ceil_div(rows * L, 256), 256, 0, s, e->st, rows, L);
+    launch_k(fill_window_kernel, ceil_div(rows * L, 256), 256, 0, s, e->st, rows, L, e->shard_images * sn);
   }
   CU_TRY(cudaGetLastError());
   return BOFI_OK;
@@ -1597,27 +1598,53 @@ int bofi_decode_ex(bofi_handle_t e, void* stream, int32_t mode, int32_t sn, int3
                       : decode_naic<float>(e, s, sn, output_logsoftmax, (long long*)seq, logprobs, phrase_num, phrase_length, (long long*)phrase_syn);
 }
 
-int bofi_sample_host_async_ex(bofi_handle_t e, void* stream, int32_t mode, int32_t sn, int32_t output_logsoftmax, const void* att_feats,
-                              int32_t feat_dtype, const int32_t* att_len, int32_t B, int32_t R, int64_t* seq, float* logprobs,
-                              int32_t* phrase_num, int32_t* phrase_length, int64_t* phrase_syn) {
-  if (!e || !att_feats || !seq || !phrase_num || !phrase_length || !phrase_syn) return fail(BOFI_ERR_INVALID, "null argument");
-  if (B <= 0 || R <= 0 || sn < 1) return fail(BOFI_ERR_INVALID, "bad batch");
+int bofi_set_shard(bofi_handle_t e, int32_t shard_images) {
+  if (!e) return fail(BOFI_ERR_INVALID, "null handle");
+  if (shard_images < 0) return fail(BOFI_ERR_INVALID, "shard_images %d", shard_images);
+  e->shard_images = shard_images;
+  return BOFI_OK;
+}
+
+int bofi_stage_part(bofi_handle_t e, void* stream, const void* att_feats, int32_t feat_dtype, const int32_t* att_len, int32_t row0,
+                    int32_t Bpart, int32_t Btotal, int32_t R) {
+  if (!e || !att_feats) return fail(BOFI_ERR_INVALID, "null argument");
   if (feat_dtype != BOFI_FEAT_F32 && feat_dtype != BOFI_FEAT_BF16 && feat_dtype != BOFI_FEAT_F16)
     return fail(BOFI_ERR_INVALID, "feat_dtype %d (BOFI_FEAT_F32 / BF16 / F16)", feat_dtype);
+  if (row0 < 0 || Bpart <= 0 || row0 + Bpart > Btotal || R <= 0) return fail(BOFI_ERR_INVALID, "part rows [%d, %d) of %d", row0, row0 + Bpart, Btotal);
   CU_TRY(cudaSetDevice(e->device));
   cudaStream_t s = (cudaStream_t)stream;
-  const size_t rows = (size_t)B * sn, L = e->L;
-  const size_t in_bytes = (size_t)B * R * e->cfg.att_feat_size * (feat_dtype == BOFI_FEAT_F32 ? 4 : 2);
-  RC_TRY(e->h_in.reserve(in_bytes));
-  RC_TRY(e->attlen.reserve((size_t)B * 4));
+  const size_t per_image = (size_t)R * e->cfg.att_feat_size * (feat_dtype == BOFI_FEAT_F32 ? 4 : 2);
+  // sized for the whole batch at the first part: a later growth would drop the parts already staged
+  // The staging buffers (features, counts) are only read by bofi_encode_staged -- the counts are copied into the workspace there --
+  // so the next batch may be staged (on another stream) as soon as that call has run, underneath the decode of this one.
+  RC_TRY(e->h_in.reserve((size_t)Btotal * per_image));
+  RC_TRY(e->h_len.reserve((size_t)Btotal * 4));
+  CU_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(e->h_in.p) + (size_t)row0 * per_image, att_feats, (size_t)Bpart * per_image, cudaMemcpyDefault, s));
+  if (att_len) CU_TRY(cudaMemcpyAsync(e->h_len.as<int>() + row0, att_len, (size_t)Bpart * 4, cudaMemcpyDefault, s));
+  return BOFI_OK;
+}
+
+int bofi_encode_staged(bofi_handle_t e, void* stream, int32_t feat_dtype, int32_t have_len, int32_t B, int32_t R) {
+  if (!e) return fail(BOFI_ERR_INVALID, "null handle");
+  const size_t need = (size_t)B * R * e->cfg.att_feat_size * (feat_dtype == BOFI_FEAT_F32 ? 4 : 2);
+  if (!e->h_in.p || e->h_in.cap < need || (have_len && e->h_len.cap < (size_t)B * 4))
+    return fail(BOFI_ERR_STATE, "bofi_encode_staged: %d x %d regions were not staged (bofi_stage_part)", B, R);
+  return bofi_encode_ex(e, stream, e->h_in.p, feat_dtype, have_len ? e->h_len.as<int>() : nullptr, B, R, nullptr);
+}
+
+int bofi_decode_host_async(bofi_handle_t e, void* stream, int32_t mode, int32_t sn, int32_t output_logsoftmax, int64_t* seq, float* logprobs,
+                           int32_t* phrase_num, int32_t* phrase_length, int64_t* phrase_syn) {
+  if (!e || !seq || !phrase_num || !phrase_length || !phrase_syn) return fail(BOFI_ERR_INVALID, "null argument");
+  if (!e->have_memory) return fail(BOFI_ERR_STATE, "bofi_decode_host_async needs a preceding bofi_encode");
+  if (sn < 1) return fail(BOFI_ERR_INVALID, "sample_n %d", sn);
+  CU_TRY(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t rows = (size_t)e->B * sn, L = e->L;
   RC_TRY(e->h_seq.reserve(rows * L * 8));
   RC_TRY(e->h_pnum.reserve(rows * 4));
   RC_TRY(e->h_plen.reserve(rows * L * 4));
   RC_TRY(e->h_psyn.reserve(rows * L * 8));
   if (logprobs) RC_TRY(e->h_logp.reserve(rows * L * (size_t)e->V * 4));
-  CU_TRY(cudaMemcpyAsync(e->h_in.p, att_feats, in_bytes, cudaMemcpyHostToDevice, s));
-  if (att_len) CU_TRY(cudaMemcpyAsync(e->attlen.p, att_len, (size_t)B * 4, cudaMemcpyHostToDevice, s));
-  RC_TRY(bofi_encode_ex(e, stream, e->h_in.p, feat_dtype, att_len ? e->attlen.as<int>() : nullptr, B, R, nullptr));
   RC_TRY(bofi_decode(e, stream, mode, sn, output_logsoftmax, e->h_seq.as<int64_t>(), logprobs ? e->h_logp.as<float>() : nullptr,
                      e->h_pnum.as<int>(), e->h_plen.as<int>(), e->h_psyn.as<int64_t>()));
   CU_TRY(cudaMemcpyAsync(seq, e->h_seq.p, rows * L * 8, cudaMemcpyDeviceToHost, s));
@@ -1626,6 +1653,21 @@ int bofi_sample_host_async_ex(bofi_handle_t e, void* stream, int32_t mode, int32
   CU_TRY(cudaMemcpyAsync(phrase_syn, e->h_psyn.p, rows * L * 8, cudaMemcpyDeviceToHost, s));
   if (logprobs) CU_TRY(cudaMemcpyAsync(logprobs, e->h_logp.p, rows * L * (size_t)e->V * 4, cudaMemcpyDeviceToHost, s));
   return BOFI_OK;
+}
+
+int bofi_sample_staged(bofi_handle_t e, void* stream, int32_t mode, int32_t sn, int32_t output_logsoftmax, int32_t feat_dtype, int32_t have_len,
+                       int32_t B, int32_t R, int64_t* seq, float* logprobs, int32_t* phrase_num, int32_t* phrase_length, int64_t* phrase_syn) {
+  if (!e || !seq || !phrase_num || !phrase_length || !phrase_syn) return fail(BOFI_ERR_INVALID, "null argument");
+  RC_TRY(bofi_encode_staged(e, stream, feat_dtype, have_len, B, R));
+  return bofi_decode_host_async(e, stream, mode, sn, output_logsoftmax, seq, logprobs, phrase_num, phrase_length, phrase_syn);
+}
+
+int bofi_sample_host_async_ex(bofi_handle_t e, void* stream, int32_t mode, int32_t sn, int32_t output_logsoftmax, const void* att_feats,
+                              int32_t feat_dtype, const int32_t* att_len, int32_t B, int32_t R, int64_t* seq, float* logprobs,
+                              int32_t* phrase_num, int32_t* phrase_length, int64_t* phrase_syn) {
+  if (!e || !att_feats || !seq || !phrase_num || !phrase_length || !phrase_syn) return fail(BOFI_ERR_INVALID, "null argument");
+  RC_TRY(bofi_stage_part(e, stream, att_feats, feat_dtype, att_len, 0, B, B, R));
+  return bofi_sample_staged(e, stream, mode, sn, output_logsoftmax, feat_dtype, att_len ? 1 : 0, B, R, seq, logprobs, phrase_num, phrase_length, phrase_syn);
 }
 
 int bofi_sample_host_async(bofi_handle_t e, void* stream, int32_t mode, int32_t sn, int32_t output_logsoftmax, const float* att_feats,

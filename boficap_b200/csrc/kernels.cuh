@@ -638,12 +638,24 @@ bound_head_kernel(const float* __restrict__ x, size_t x_stride, const float* __r
 
 // NAIC fill window: every row uses w = last[rows-1] - 1 (the reference's stale loop index,
 // TransformerModel.py:1871-1873).  Also records w and the NaN-batch flag.
-__global__ void fill_window_kernel(DecodeState st, int rows, int L) {
+// shard_rows > 0: the rows are several batches of shard_rows rows decoded in one call (bofi_set_shard); every batch keeps ITS
+// window, w = last[last row of the row's batch] - 1, i.e. exactly what a stand-alone decode of that batch uses.  counters[2]
+// reports the last batch's window, counters[3] whether any batch's window is empty.
+__global__ void fill_window_kernel(DecodeState st, int rows, int L, int shard_rows) {
   pdl_enter();
-  const int w = st.last[rows - 1] - 1;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) { st.counters[2] = w; st.counters[3] = (w <= 0) ? 1 : 0; }
-  if (i < rows * L) st.vis_fill[i] = w;
+  if (i == 0) {
+    const int wl = st.last[rows - 1] - 1;
+    st.counters[2] = wl;
+    int bad = (wl <= 0) ? 1 : 0;
+    if (shard_rows > 0)
+      for (int end = shard_rows - 1; end < rows; end += shard_rows) bad |= (st.last[end] - 1 <= 0) ? 1 : 0;
+    st.counters[3] = bad;
+  }
+  if (i >= rows * L) return;
+  int end = rows - 1;
+  if (shard_rows > 0) end = min(rows - 1, (i / L / shard_rows + 1) * shard_rows - 1);
+  st.vis_fill[i] = st.last[end] - 1;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -107,6 +107,77 @@ class BofiEngine:
                                                _ptr(seq), _ptr(logp), ld, _ptr(pnum), _ptr(plen), _ptr(psyn)))
         return seq, logp, pnum, plen, psyn
 
+    # ---- several batches in one call (bofi_set_shard / bofi_stage_part / bofi_encode_staged / bofi_sample_staged) --------------
+    def set_shard(self, shard_images):
+        """The images of the following encode / decode calls are batches of `shard_images` images that keep their own fill
+        window (0: the call is one batch): bit for bit the results of separate calls, one bounding loop for all of them."""
+        _lib.check(self.lib.bofi_set_shard(self.handle, int(shard_images)))
+
+    def stage_part(self, att_feats, att_len, row0, total):
+        """Copy one batch (host pinned or device tensor) to rows [row0, row0 + B) of the library's staging buffer for `total`
+        images; asynchronous on the current stream (the source must stay alive until the stream has passed the copy)."""
+        assert att_feats.is_contiguous()
+        code = _feat_code(att_feats)
+        B, R, _ = att_feats.shape
+        if att_len is not None:
+            att_len = att_len.to(torch.int32).contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bofi_stage_part(self.handle, self._stream(), _ptr(att_feats), code, _ptr(att_len), int(row0), B, int(total), R))
+        # keep the sources alive while their copies may still be pending: this call's batch and the two before it on this handle
+        # (a handle's calls are stream-ordered, and a caller that reuses a slot has waited for the slot's previous ticket)
+        gens = getattr(self, "_stage_gens", None)
+        if gens is None:
+            gens = self._stage_gens = []
+        if row0 == 0:
+            gens.append([])
+            del gens[:-3]
+        if not gens:
+            gens.append([])
+        gens[-1].append((att_feats, att_len))
+        return code
+
+    def encode_staged(self, code, have_len, B, R):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bofi_encode_staged(self.handle, self._stream(), int(code), int(bool(have_len)), int(B), int(R)))
+        self._batch = (B, R, None, None)
+
+    def decode_host(self, mode="NAIC", sample_n=1, output_logsoftmax=1, out=None, want_logprobs=False):
+        """decode of the encoded batch, results copied to pinned host tensors (asynchronous; bofi_decode_host_async)."""
+        B = self._batch[0]
+        rows, L, V = B * sample_n, self.cfg.seq_length, self.cfg.tgt_vocab
+        if out is not None and (out["seq"].shape[0] != rows or (out.get("logp") is not None) != bool(want_logprobs)):
+            out = None
+        if out is None:
+            out = dict(seq=torch.empty(rows, L, dtype=torch.int64).pin_memory(),
+                       logp=torch.empty(rows, L, V).pin_memory() if want_logprobs else None,
+                       pnum=torch.empty(rows, dtype=torch.int32).pin_memory(),
+                       plen=torch.empty(rows, L, dtype=torch.int32).pin_memory(),
+                       psyn=torch.empty(rows, L, dtype=torch.int64).pin_memory())
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bofi_decode_host_async(
+                self.handle, self._stream(), _lib.MODE[mode], sample_n, int(output_logsoftmax),
+                _ptr(out["seq"]), _ptr(out.get("logp")), _ptr(out["pnum"]), _ptr(out["plen"]), _ptr(out["psyn"])))
+        self._host_keep = out
+        return out
+
+    def sample_staged(self, code, have_len, B, R, mode="NAIC", sample_n=1, output_logsoftmax=1, out=None, want_logprobs=False):
+        """encode + decode of the staged batch, results copied to pinned host tensors (asynchronous, as sample_host(sync=False))."""
+        rows, L, V = B * sample_n, self.cfg.seq_length, self.cfg.tgt_vocab
+        if out is not None and (out["seq"].shape[0] != rows or (out.get("logp") is not None) != bool(want_logprobs)):
+            out = None
+        if out is None:
+            out = dict(seq=torch.empty(rows, L, dtype=torch.int64).pin_memory(),
+                       logp=torch.empty(rows, L, V).pin_memory() if want_logprobs else None,
+                       pnum=torch.empty(rows, dtype=torch.int32).pin_memory(),
+                       plen=torch.empty(rows, L, dtype=torch.int32).pin_memory(),
+                       psyn=torch.empty(rows, L, dtype=torch.int64).pin_memory())
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bofi_sample_staged(
+                self.handle, self._stream(), _lib.MODE[mode], sample_n, int(output_logsoftmax), int(code), int(bool(have_len)), int(B), int(R),
+                _ptr(out["seq"]), _ptr(out.get("logp")), _ptr(out["pnum"]), _ptr(out["plen"]), _ptr(out["psyn"])))
+        self._host_keep = out
+        return out
+
     def sample_host(self, att_feats, att_len=None, mode="NAIC", sample_n=1, output_logsoftmax=1, out=None, want_logprobs=False,
                     sync=True):
         """End-to-end call on HOST tensors (pinned or pageable): H2D, encode, decode, D2H, sync.

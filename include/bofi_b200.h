@@ -129,6 +129,28 @@ int bofi_decode_ex(bofi_handle_t h, void* stream, int32_t mode, int32_t sample_n
                    int64_t* seq, float* logprobs, int64_t logprob_ld, int32_t* phrase_num, int32_t* phrase_length,
                    int64_t* phrase_syn);
 
+/* Several batches in ONE call (what nn.DataParallel replicas / successive eval batches are to the reference: independent
+ * `_sample` calls).  The only place where a row of `_sample` depends on the other rows of its batch is the fill window
+ * w = last[B-1] - 1 of core_NAIC (TransformerModel.py:1871-1873).  With bofi_set_shard(h, n) the B images of the following
+ * bofi_encode / bofi_decode calls are B / n batches of n images (the last may be shorter) and every batch keeps its own window,
+ * so the result is bit for bit what B / n separate calls give -- while the bounding loop's ~190 latency-bound launches are paid
+ * once.  n = 0: the whole call is one batch (default).  NAIC; bofi_decode_info reports the last batch's window.
+ * bofi_stage_part copies one batch (host or device memory; features [Bpart, R, F] of feat_dtype, optional att_len [Bpart]) to rows
+ * [row0, row0 + Bpart) of a library-owned device buffer for Btotal images, bofi_encode_staged runs bofi_encode_ex on that buffer,
+ * bofi_sample_staged = bofi_encode_staged + bofi_decode_host_async. */
+int bofi_set_shard(bofi_handle_t h, int32_t shard_images);
+int bofi_stage_part(bofi_handle_t h, void* stream, const void* att_feats, int32_t feat_dtype, const int32_t* att_len,
+                    int32_t row0, int32_t Bpart, int32_t Btotal, int32_t R);
+int bofi_encode_staged(bofi_handle_t h, void* stream, int32_t feat_dtype, int32_t have_len, int32_t B, int32_t R);
+int bofi_sample_staged(bofi_handle_t h, void* stream, int32_t mode, int32_t sample_n, int32_t output_logsoftmax,
+                       int32_t feat_dtype, int32_t have_len, int32_t B, int32_t R, int64_t* seq, float* logprobs,
+                       int32_t* phrase_num, int32_t* phrase_length, int64_t* phrase_syn);
+/* bofi_decode + the asynchronous device-to-host copies of the results (pinned host outputs), on the memory of the preceding
+ * bofi_encode*.  The staging buffers of bofi_stage_part are free again once bofi_encode_staged has run: a caller that records an
+ * event between bofi_encode_staged and this call can stage the next batch on a copy stream underneath this decode. */
+int bofi_decode_host_async(bofi_handle_t h, void* stream, int32_t mode, int32_t sample_n, int32_t output_logsoftmax,
+                           int64_t* seq, float* logprobs, int32_t* phrase_num, int32_t* phrase_length, int64_t* phrase_syn);
+
 /* eval_split's entropy / perplexity (captioning/utils/eval_utils.py:183-184) without materialising seq_logprob:
  * when set (dev f32 [rows, L] each; NULL, NULL switches it off), the following bofi_decode calls also write, per slot,
  *   slot_entropy = -sum_v p_v log p_v   and   slot_logp = log p of the token written to seq

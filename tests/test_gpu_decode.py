@@ -327,3 +327,84 @@ def test_padded_logprob_pitch_equals_dense_tensor(precision):
     # SAIC keeps the dense tensor
     eng.encode(att.cuda(), None)
     assert eng.decode("SAIC", 1, 1, True)[1].is_contiguous()
+
+
+def _same(a, b):
+    return torch.equal(torch.nan_to_num(a.float(), nan=-7.0), torch.nan_to_num(b.float(), nan=-7.0))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_sharded_call_equals_separate_batches(precision):
+    """bofi_set_shard: k batches decoded by ONE call, each with its own fill window w = last[end of its batch] - 1, give bit for
+    bit what k separate `_sample` calls give -- incl. a batch whose window is empty (the reference's NaN batch,
+    AttModel.py:427-428) next to healthy ones, sample_n > 1, a ragged last batch and adaptive regions."""
+    fix, cfg = load_golden("naic_b2_r36_nanbatch")          # its last image predicts no phrase: w = 0 -> NaN log-probs
+    eng = engine_for(cfg, str(fix["calib"]), precision)
+    _, att_nan, _ = golden_inputs(fix)
+    # (sizes at which a batch alone and the merged call take the same kernels: the library switches GEMM / vocabulary kernels at
+    #  256 decode rows and 2048 GEMM rows, and those differ in the last bits of the log-probs; at B = 1024 both are far above)
+    for (n, R, adaptive, sn) in ((2, 36, False, 1), (16, 36, False, 2), (14, 48, True, 1)):
+        parts = []
+        for k in range(3):
+            _, att, masks = synth.synth_inputs(n if k < 2 else max(1, n - 1), R, seed=90 + 7 * k + n, adaptive=adaptive)
+            parts.append((att, masks))
+        if R == 36 and not adaptive and n == 2:
+            parts[1] = (att_nan, None)                        # the NaN batch in the middle
+        alone = [run_cuda(eng, a, m, sample_n=sn) for a, m in parts]
+        nan_flags = [bool(torch.isnan(o[1]).any()) for o in alone]
+        att_all = torch.cat([a for a, _ in parts]).cuda()
+        len_all = torch.cat([m.long().sum(1) for _, m in parts]).int().cuda() if adaptive else None
+        eng.set_shard(n)
+        eng.encode(att_all, len_all)
+        merged = [t.cpu() for t in eng.decode("NAIC", sn, 1, True)]
+        info = eng.decode_info()
+        eng.set_shard(0)
+        lo = 0
+        for (a, _), o in zip(parts, alone):
+            hi = lo + a.shape[0] * sn
+            for x, y in zip(o, merged):
+                assert _same(x, y[lo:hi]), (precision, n, R, sn)
+            lo = hi
+        assert info["nan_batch"] == int(any(nan_flags))
+        if n == 2 and R == 36:
+            assert nan_flags[1]                               # the empty window is there, and (equality above) stays inside its batch
+
+
+def test_grouped_pipeline_tickets_equal_standalone_decodes():
+    """BofiPipeline(group=3): consecutive submissions share one library call (bofi_stage_part + bofi_set_shard); every ticket's
+    slice equals the stand-alone decode of its batch -- device and pinned-host submissions, a group that is flushed incomplete,
+    a change of batch shape in the middle of a group."""
+    from boficap_b200.pipeline import BofiPipeline
+    cfg = BofiConfig()
+    sd = checkpoint(cfg, "s_cap")
+    ref = engine_for(cfg, "s_cap", "bf16")
+    pipe = BofiPipeline(cfg, sd, 0, "bf16", depth=2, group=3)
+    batches = []
+    for k, (B, R, adaptive) in enumerate(((40, 36, False),) * 4 + ((24, 36, False),) + ((32, 50, True),) * 2):
+        _, att, masks = synth.synth_inputs(B, R, seed=120 + k, adaptive=adaptive)
+        batches.append((att.to(torch.bfloat16), masks))
+    want = []
+    for att, masks in batches:
+        ln = masks.long().sum(1).int().cuda() if masks is not None else None
+        ref.encode(att.cuda(), ln)
+        want.append([t.cpu() for t in ref.decode("NAIC", 1, 1, True)])
+    torch.cuda.synchronize()
+    # device submissions
+    tickets = [pipe.submit_device(att.cuda(), masks.long().sum(1).int().cuda() if masks is not None else None, want_logprobs=True)
+               for att, masks in batches]
+    assert [t.launched for t in tickets] == [True, True, True, True, True, False, False]     # 3 | 1 (shape change) | 1 (shape change) | 2 still open
+    for t, w in zip(tickets, want):
+        got = t.wait()
+        for x, y in zip(w, got):
+            assert _same(x, y.cpu())
+    # pinned-host submissions (results land in the slot's pinned buffers: consume a ticket before its slot is reused)
+    for i in range(0, len(batches), 3):
+        chunk = batches[i:i + 3]
+        ts = [pipe.submit_host(att.pin_memory(), masks.long().sum(1).int() if masks is not None else None, want_logprobs=True)
+              for att, masks in chunk]
+        pipe.flush()
+        for t, w in zip(ts, want[i:i + 3]):
+            got = t.wait()
+            for x, y in zip(w, (got["seq"], got["logp"], got["pnum"], got["plen"], got["psyn"])):
+                assert _same(x, y)
+    pipe.close()
