@@ -515,7 +515,7 @@ def main():
         t.wait()
     torch.cuda.synchronize()
     info = eng.decode_info()
-    launches_per_step = info["kernel_launches"]
+    launches_per_step = info["kernel_launches"]               # of one library call = one group of `pipe.group` batches (+ the staging copies)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -740,7 +740,7 @@ def main():
                 "fp32_host_serial": {"value": B / (ms_dropin_serial / 1e3), "unit": "captions/s", "ms_per_step": ms_dropin_serial,
                                      "api": "pinned fp32 host tensors, .cuda() + _sample + seq.cpu() in series (the reference eval loop's pattern, "
                                             "eval_utils.py:431-445)"}},
-            "numa": numa, "notes": notes, "mean_regions": mean_regions, "gpu_launches": launches_per_step * a.steps, "bounding_steps": S, "fill_width": info["fill_width"],
+            "numa": numa, "notes": notes, "mean_regions": mean_regions, "gpu_launches": launches_per_step * ((a.steps + pipe.group - 1) // pipe.group), "bounding_steps": S, "fill_width": info["fill_width"],
             "nan_batch": info["nan_batch"], "mean_caption_tokens": float(out[3].sum(1).float().mean()), "clocks": clocks,
             "roofline": roofline, "cpu_baseline": cpu, "gpu_eager": eager}
     print(json.dumps(line))
