@@ -158,7 +158,7 @@ def bench_xe(a, rank, local_rank, world):
     from boficap_b200.captioning import models
     from boficap_b200.layout import BofiConfig
     from boficap_b200.parallel import OverlappedGradReduce
-    cfg = BofiConfig()
+    cfg = BofiConfig(N_len=a.n_len)           # 1: uic_sd.yml; 2: uic_sd_N2.yml (two bounding layers)
     B = 256 if a.batch == 1024 else a.batch
     R, spi = a.regions, 5
     infos = synth.make_infos(cfg)
@@ -238,8 +238,9 @@ def bench_xe(a, rank, local_rank, world):
                 "value": world * B * a.steps / (ms / 1e3), "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
                 "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": a.precision,
                 "data": "synthetic",
-                "config": {"workload": "uic_sd XE training step (forward + criterion + backward + all-reduce + Adam), %d images x %d captions per GPU, "
-                                       "%d regions, %s, dropout %s" % (B, spi, R, a.precision, "off" if a.no_dropout else "on (p=0.1, att_embed 0.5)"),
+                "config": {"workload": "uic_sd%s XE training step (forward + criterion + backward + all-reduce + Adam), %d images x %d captions per GPU, "
+                                       "%d regions, %s, dropout %s" % ("" if a.n_len == 1 else "_N%d" % a.n_len, B, spi, R, a.precision,
+                                                                       "off" if a.no_dropout else "on (p=0.1, att_embed 0.5)"),
                            "parallelism": "data-parallel replicas x%d, NCCL all-reduce of the %.0f MB flat gradient buffer in %d + 1 buckets, the decoder-side "
                                           "buckets overlapped with the encoder's backward pass" % (world, flat_g.numel() * 4 / 1e6, a.buckets)},
                 "loss_first": first, "loss_last": float(losses[0]), "gpu_launches": launches * a.steps, "clocks": clocks,
@@ -378,6 +379,7 @@ def main():
                     help="decode = BASELINE.json's headline metric; xe = XE training step (config 5: 256 images x 5 captions per GPU)")
     ap.add_argument("--no-dropout", action="store_true", help="xe workload: eval() arithmetic (dropout off)")
     ap.add_argument("--depth", type=int, default=3, help="engine handles x streams in flight (boficap_b200/pipeline.py)")
+    ap.add_argument("--n-len", type=int, default=1, help="xe workload: bounding layers (configs/uic_sd_N2.yml: 2)")
     ap.add_argument("--group", type=int, default=2, help="consecutive batches decoded by ONE library call on a slot, every batch with its own "
                                                           "fill window (bofi_set_shard): bit-identical results, one bounding loop per group")
     ap.add_argument("--host-dtype", default="bf16", choices=["bf16", "fp16", "fp32"], help="element type of the pinned host features of the e2e leg")

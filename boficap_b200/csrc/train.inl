@@ -72,6 +72,7 @@ struct BoundTape {
   void *y0 = nullptr, *qkv = nullptr;   // [N*Tb, .]
   void *q_rep = nullptr;          // [Mb, 512] the [LEN] query repeated per pass (backward only needs it)
   LayerTape lt;                   // rows (n, p): ao, x1, y1, q, ao2, x2, y2, ffh, x_out
+  std::vector<LayerTape> full;    // N_len >= 2: [P][N_len] full-layer tapes over the N*Tb rows of every pass (t_bound_fwd_full)
   float* hn = nullptr;            // [Mb, 512] length_predictor.norm output (fp32: the heads are fp32)
   float* hid = nullptr;           // [Mb, 200]
   Drop d_embed, d_hid;
@@ -90,6 +91,7 @@ struct TrainState {
   Arena arena;
   int *labels = nullptr, *pnum = nullptr, *plen = nullptr, *psyn = nullptr, *ext_syn = nullptr, *ext_seq = nullptr, *sa_vis = nullptr;
   int *word_seq = nullptr, *vis_b = nullptr, *na_vis = nullptr, *n_words = nullptr, *total_words = nullptr;
+  int* vis_full = nullptr;        // N_len >= 2: [P][N][Tb] visible keys of every row at every bounding pass
   void* attT = nullptr;           // [B*R, F] GEMM operand copy of the features
   float* x0 = nullptr;            // att_embed output
   std::vector<LayerTape> enc;
@@ -99,7 +101,7 @@ struct TrainState {
   std::vector<void*> kv;          // [B*R, 1024] per bounding / decoder layer
   BoundTape sa_b, na_b;
   DecTape sa_d, na_d;
-  DevBuf tr_a, tr_b, tr_w, zeros, ln_partial, cs_partial, cs_tickets, scratch_f32, dkv, dmem, zbuf;
+  DevBuf tr_a, tr_b, tr_w, zeros, ln_partial, cs_partial, cs_tickets, scratch_f32, dkv, dmem, zbuf, dlen;
   // Dropout (train() mode of the reference): p_sub = opt.dropout at every sub-layer output, attention probability,
   // FFN hidden, positional encoding and head hidden; p_att = opt.drop_prob_lm after att_embed's ReLU.  Sites are numbered
   // in forward order from 0 every step; key(site) = drop_hash(seed, site); the backward pass reuses the keys.
@@ -294,6 +296,52 @@ static int t_bound_fwd(bofi_engine* e, cudaStream_t s, TrainState* ts, BoundTape
   return BOFI_OK;
 }
 
+// N_len >= 2 (configs/uic_sd_N2.yml): the passes in the reference's own formulation -- every pass p runs the whole LengthPredictor stack
+// over all Tb rows of every caption under that pass's mask (vis_full[p]), the [LEN] row of the last layer goes to the heads.  (The
+// [LEN]-row shortcut of t_bound_fwd needs the other rows only as keys of ONE layer; with two layers the first layer's outputs of all
+// rows are the second layer's keys.)  P * N_len full-layer tapes; the heads are those of t_bound_fwd.
+template <typename T>
+static int t_bound_fwd_full(bofi_engine* e, cudaStream_t s, TrainState* ts, BoundTape& bt, const int* word_ids, const int* syn_ids,
+                            float* len_logp, float* syn_logp) {
+  const bofi_config_t& c = e->cfg;
+  const int N = ts->N, Tb = ts->Tb, P = ts->P, Mb = ts->Mb, NL = c.n_len;
+  const int* mem_len = ts->att_len;
+  bt.x_in = aalloc<float>(ts, (size_t)N * Tb * kD); A_TRY(bt.x_in);
+  bt.d_embed = ts->next_drop(ts->p_sub);
+  launch_k(embed_xe_kernel, ceil_div(N * Tb, 8), 256, 0, s, W(e, "model.tgt_embed.lut.weight"), W(e, "model.syn_embed.lut.weight"),
+           W(e, "model.pos_embed.pe"), word_ids, Tb, 0, -1, syn_ids, Tb, 0, sqrtf((float)kD), bt.x_in, N * Tb, Tb, bt.d_embed);
+  CU_TRY(cudaGetLastError());
+  float* x3 = aalloc<float>(ts, (size_t)Mb * kD); A_TRY(x3);
+  bt.hn = aalloc<float>(ts, (size_t)Mb * kD); A_TRY(bt.hn);
+  bt.hid = aalloc<float>(ts, (size_t)Mb * 200); A_TRY(bt.hid);
+  bt.lt = LayerTape();
+  bt.lt.x_out = x3;                                   // what length_predictor.norm normalises (the head backward reads it)
+  bt.full.assign((size_t)P * NL, LayerTape());
+  for (int p = 0; p < P; ++p) {
+    const int* vis = ts->vis_full + (size_t)p * N * Tb;
+    const float* x = bt.x_in;
+    for (int l = 0; l < NL; ++l) {
+      LayerTape& tp = bt.full[(size_t)p * NL + l];
+      RC_TRY(t_layer_fwd<T>(e, s, ts, e->lp[l], tp, x, N, Tb, vis, Tb, 1, (const T*)ts->kv[l], ts->R, mem_len, ts->spi));
+      x = tp.x_out;
+    }
+    launch_k(gather_len_rows_kernel, ceil_div(N * (kD / 4), 256), 256, 0, s, x, Tb, x3, N, P, p);
+    CU_TRY(cudaGetLastError());
+  }
+  bt.d_hid = ts->next_drop(ts->p_sub);
+  RC_TRY(layernorm<float>(e, s, x3, kD, e->lp_norm, bt.hn, kD, Mb, nullptr, nullptr));
+  {
+    cudaError_t err = gemm_simt<float, float>(s, bt.hn, kD, e->head1.w32, kD, e->head1.b, nullptr, 0, bt.hid, 200, Mb, 200, kD, 1, nullptr);
+    if (err != cudaSuccess) return fail(BOFI_ERR_CUDA, "head GEMM: %s", cudaGetErrorString(err));
+    e->launches++;
+  }
+  RC_TRY(dropout_inplace<float>(e, s, bt.hid, (size_t)Mb * 200, bt.d_hid));
+  launch_k(xe_head_logp_kernel, ceil_div(Mb, 4), 128, 0, s, (const float*)bt.hid, e->w_len2, e->b_len2, e->w_syn2, e->b_syn2, 100, 20, 10,
+           len_logp, syn_logp, Mb, P, Tb - 1);
+  CU_TRY(cudaGetLastError());
+  return BOFI_OK;
+}
+
 // decode_SA / decode_NA (:520-530, :570-587) + decoder stack + final LayerNorm + vocab projection.
 template <typename T>
 static int t_dec_fwd(bofi_engine* e, cudaStream_t s, TrainState* ts, DecTape& dt, const int* word_ids, int const_word, const int* self_vis,
@@ -411,10 +459,19 @@ static int train_forward_impl(bofi_engine* e, cudaStream_t s, TrainState* ts, co
   CU_TRY(cudaMemsetAsync(na_len, 0, slots * 20 * 4, s));
   CU_TRY(cudaMemsetAsync(na_syn, 0, slots * 10 * 4, s));
   // ---- SA: bounding on the ground-truth words, decoder on the position-wise copied words ------------------
-  RC_TRY(t_bound_fwd<T>(e, s, ts, ts->sa_b, ts->word_seq, nullptr, sa_len, sa_syn));
+  const bool full_bound = c.n_len >= 2;
+  if (full_bound) {
+    ts->vis_full = aalloc<int>(ts, (size_t)ts->P * N * Tb); A_TRY(ts->vis_full);
+    launch_k(xe_vis_full_kernel, ceil_div(ts->P * N * Tb, 256), 256, 0, s, (const int*)ts->vis_b, N, ts->P, Tb, ts->vis_full);
+    CU_TRY(cudaGetLastError());
+    RC_TRY(t_bound_fwd_full<T>(e, s, ts, ts->sa_b, ts->word_seq, nullptr, sa_len, sa_syn));
+  } else {
+    RC_TRY(t_bound_fwd<T>(e, s, ts, ts->sa_b, ts->word_seq, nullptr, sa_len, sa_syn));
+  }
   RC_TRY(t_dec_fwd<T>(e, s, ts, ts->sa_d, ts->ext_seq, -1, ts->sa_vis, ts->T, 1, sa_logp, fused_loss));
   // ---- NA: bounding on the syn labels, decoder on BOS + syn labels ------------------------------------------
-  RC_TRY(t_bound_fwd<T>(e, s, ts, ts->na_b, nullptr, ts->ext_syn, na_len, na_syn));
+  if (full_bound) RC_TRY(t_bound_fwd_full<T>(e, s, ts, ts->na_b, nullptr, ts->ext_syn, na_len, na_syn));
+  else RC_TRY(t_bound_fwd<T>(e, s, ts, ts->na_b, nullptr, ts->ext_syn, na_len, na_syn));
   ts->glat_words = nullptr;
   if (ts->glat_p >= 0.f) {
     // Glancing (:437-464): a no-grad NA pass on constant bos inputs predicts the words; the fraction of mismatches times glat_p is
@@ -698,6 +755,46 @@ static int t_dec_bwd(bofi_engine* e, cudaStream_t s, TrainState* ts, DecTape& dt
   return BOFI_OK;
 }
 
+// N_len >= 2: backward of t_bound_fwd_full below the heads.  dx [Mb, 512] holds d x3 (the [LEN] rows of every pass) on entry.
+template <typename T>
+static int t_bound_bwd_full_tail(bofi_engine* e, cudaStream_t s, TrainState* ts, BoundTape& bt, const int* word_ids, const int* syn_ids,
+                                 float* dx, T* dxT, T* g1, T* g2, int first_pass) {
+  const bofi_config_t& c = e->cfg;
+  const int N = ts->N, Tb = ts->Tb, P = ts->P, Mb = ts->Mb, NL = c.n_len;
+  const int* mem_len = ts->att_len;
+  const size_t M = (size_t)ts->B * ts->R;
+  RC_TRY(ts->dlen.reserve((size_t)Mb * kD * 4));
+  float* dlen = ts->dlen.as<float>();
+  CU_TRY(cudaMemcpyAsync(dlen, dx, (size_t)Mb * kD * 4, cudaMemcpyDeviceToDevice, s));
+  RC_TRY(ts->dmem.reserve((size_t)std::max(N * Tb, ts->B * ts->R) * kD * 4));
+  float* dxin = ts->dmem.as<float>();
+  const size_t n4 = (size_t)N * Tb * (kD / 4);
+  for (int p = P - 1; p >= 0; --p) {
+    const int* vis = ts->vis_full + (size_t)p * N * Tb;
+    e->launches += 2;
+    launch_k(scatter_len_rows_kernel<T>, (unsigned)ceil_div(n4, (size_t)256), 256, 0, s, (const float*)dlen, Tb, dx, dxT, N, P, p);
+    CU_TRY(cudaGetLastError());
+    for (int l = NL - 1; l >= 0; --l) {
+      T* dkv = ts->dkv.as<T>() + (size_t)l * M * 2 * kD;
+      const int accumulate = (first_pass && p == P - 1) ? 0 : 1;       // the first pass to touch a layer's K/V gradient overwrites
+      RC_TRY(t_layer_bwd<T>(e, s, ts, e->lp[l], bt.full[(size_t)p * NL + l], dx, dxT, g1, g2, N, Tb, vis, Tb, 1, (const T*)ts->kv[l], dkv,
+                            accumulate, ts->R, mem_len, ts->spi, false));
+    }
+    launch_k(add_inplace_f32_kernel, 148 * 8, 256, 0, s, dxin, (const float*)dx, n4, p == P - 1 ? 1 : 0);   // d x_in: sum over the passes
+    CU_TRY(cudaGetLastError());
+  }
+  if (bt.d_embed.thresh) RC_TRY((dropout_apply<float, float>(e, s, dxin, dxin, (size_t)N * Tb * kD, bt.d_embed)));
+  const float sq = sqrtf((float)kD);
+  if (word_ids) {
+    ProfScope prof(e, s, PC_OTHER, 0.0, (double)N * Tb * kD * 8);
+    launch_k(embed_bwd_kernel, ceil_div(N * Tb, 8), 256, 0, s, (const float*)dxin, word_ids, Tb, 0, Tb, N * Tb, sq, G(e, "model.tgt_embed.lut.weight"));
+  } else {
+    RC_TRY(embed_small_bwd(e, s, ts, dxin, syn_ids, Tb, 0, 0, Tb, N * Tb, G(e, "model.syn_embed.lut.weight")));
+  }
+  CU_TRY(cudaGetLastError());
+  return BOFI_OK;
+}
+
 // Backward of one teacher-forced bounding pass batch.  g_len / g_syn: gradients of the [N, Tb-1, .] outputs.
 template <typename T>
 static int t_bound_bwd(bofi_engine* e, cudaStream_t s, TrainState* ts, BoundTape& bt, const float* g_len, const float* g_syn,
@@ -763,6 +860,7 @@ static int t_bound_bwd(bofi_engine* e, cudaStream_t s, TrainState* ts, BoundTape
     RC_TRY(lin_bwd<float>(e, s, ts, e->head1, bt.hn, kD, dhid, 256, Mb, dhn, kD));
     RC_TRY((ln_bwd<float, T>(e, s, ts, e->lp_norm, tp.x_out, dhn, nullptr, dx, dxT, Mb)));
   }
+  if (c.n_len >= 2) return t_bound_bwd_full_tail<T>(e, s, ts, bt, word_ids, syn_ids, dx, dxT, g1, g2, first_pass);
   // FFN + cross-attention of the (n, p) rows; K/V block = image, spi*P single-query rows per block
   T* dkv = ts->dkv.as<T>();
   RC_TRY(t_layer_bwd<T>(e, s, ts, ly, tp, dx, dxT, g1, g2, Mb, 1, nullptr, 0, 0, (const T*)ts->kv[0], dkv, first_pass ? 0 : 1, ts->R, mem_len,

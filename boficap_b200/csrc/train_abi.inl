@@ -13,7 +13,7 @@ extern "C" int bofi_param_offset(bofi_handle_t e, const char* name, int64_t* off
 
 extern "C" int bofi_train_bind(bofi_handle_t e, void* stream, float* flat_params, float* flat_grads) {
   if (!e || !flat_params || !flat_grads) return fail(BOFI_ERR_INVALID, "null argument");
-  if (e->cfg.n_len != 1) return fail(BOFI_ERR_INVALID, "the training path is built for N_len == 1 (uic_sd.yml); got N_len = %d", e->cfg.n_len);
+  if (e->cfg.n_len < 1) return fail(BOFI_ERR_INVALID, "the training path is built for N_len >= 1 (uic_sd.yml: 1, uic_sd_N2.yml: 2); got N_len = %d", e->cfg.n_len);
   for (const std::string& n : e->order)
     if (!e->weights[n].loaded) return fail(BOFI_ERR_STATE, "missing state_dict key '%s'", n.c_str());
   CU_TRY(cudaSetDevice(e->device));
@@ -47,7 +47,7 @@ static int train_begin(bofi_handle_t e, cudaStream_t s, int32_t B, int32_t R, in
                        const int32_t* phrase_num, const int32_t* phrase_length, const int32_t* phrase_syn, const int32_t* ext_syn,
                        const int32_t* ext_seq, const int32_t* sa_vis) {
   if (!e->finalized) return fail(BOFI_ERR_STATE, "weights not finalised");
-  if (e->cfg.n_len != 1) return fail(BOFI_ERR_INVALID, "the training path is built for N_len == 1 (uic_sd.yml)");
+  if (e->cfg.n_len < 1) return fail(BOFI_ERR_INVALID, "the training path is built for N_len >= 1");
   if (B <= 0 || R <= 0 || R > kMaxKeys || spi <= 0 || Lt < 1 || Lt + 2 > 32 || P < 1 || P > Lt + 1)
     return fail(BOFI_ERR_INVALID, "bad training batch B=%d R=%d seq_per_img=%d L=%d P=%d", B, R, spi, Lt, P);
   if (!labels || !phrase_num || !phrase_length || !ext_syn || !ext_seq || !sa_vis) return fail(BOFI_ERR_INVALID, "null argument");

@@ -323,6 +323,59 @@ glat_input_kernel(const int* __restrict__ labels, const int* __restrict__ plen, 
   }
 }
 
+// ---- N_len >= 2: the bounding passes in the reference's own formulation (every pass a full stack over all Tb rows) -------------
+// Visible-key counts of pass p (get_predict_phrase_length_syn_{SA,NA}, TransformerModel.py:476-513 / :532-565): the mask grows by
+// `tgt_mask[j, last:, :last+len] = True; tgt_mask[j, 0, :last+len] = True`, so at pass p row 0 and the rows at or beyond the frontier
+// see vis_b[n, p] keys, and a row inside phrase k <= p keeps what it saw when its phrase was added: vis_b[n, k].
+//   vis_b [N, P] (xe_prepare_kernel)  ->  vis_full [P][N][Tb]
+__global__ void xe_vis_full_kernel(const int* __restrict__ vis_b, int N, int P, int Tb, int* __restrict__ vis_full) {
+  pdl_enter();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * N * Tb) return;
+  const int r = i % Tb, n = (i / Tb) % N, p = i / (Tb * N);
+  const int front = vis_b[n * P + p];
+  int v = front;
+  if (r != 0 && r < front) {
+    for (int k = 0; k <= p; ++k) {
+      const int lk = vis_b[n * P + k];
+      if (r < lk) { v = lk; break; }
+    }
+  }
+  vis_full[i] = v;
+}
+// x3[(n, p)] = x[n, row 0]: the [LEN] row of pass p (LengthPredictor_UIC.forward :375 `output[:, 0, :]`)
+__global__ void gather_len_rows_kernel(const float* __restrict__ x, int Tb, float* __restrict__ x3, int N, int P, int p) {
+  pdl_enter();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;          // float4 index
+  if (i >= N * (kD / 4)) return;
+  const int n = i / (kD / 4), c = (i % (kD / 4)) * 4;
+  store4(x3 + ((size_t)n * P + p) * kD + c, load4(x + (size_t)n * Tb * kD + c));
+}
+// Gradient of a pass's stack output: zero except row 0 of every caption, which takes d x3[(n, p)]; fp32 and operand-type copies.
+template <typename T>
+__global__ void scatter_len_rows_kernel(const float* __restrict__ dlen, int Tb, float* __restrict__ dx, T* __restrict__ dxT, int N, int P, int p) {
+  pdl_enter();
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // float4 index
+  if (i >= (size_t)N * Tb * (kD / 4)) return;
+  const int c = (int)(i % (kD / 4)) * 4;
+  const size_t row = i / (kD / 4);
+  const int r = (int)(row % Tb), n = (int)(row / Tb);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (r == 0) v = load4(dlen + ((size_t)n * P + p) * kD + c);
+  store4(dx + row * kD + c, v);
+  store4(dxT + row * kD + c, v);
+}
+__global__ void add_inplace_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, size_t n4, int overwrite) {
+  pdl_enter();
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    float4 a = load4(src + i * 4);
+    if (!overwrite) { const float4 b = load4(dst + i * 4); a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+    store4(dst + i * 4, a);
+  }
+}
+
 __global__ void clamp_min_i32_kernel(int* __restrict__ x, int lo, int n) {
   pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

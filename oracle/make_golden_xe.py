@@ -32,6 +32,8 @@ CASES = [
     # replaced by the CUDA path's counter-based uniforms so that the glanced inputs are reproducible
     ("xe_b3_r20_glat", 3, 20, True, 5, 0.5, 11),
     ("xe_b2_r12_glat1", 2, 12, False, 3, 1.0, 4),
+    # two bounding layers (configs/uic_sd_N2.yml)
+    ("xe_b2_r12_nlen2", 2, 12, False, 3, -1.0, 0, {"N_len": 2}),
 ]
 LOGP_COLS = 32
 GRAD_HEAD = 64
@@ -60,10 +62,10 @@ def glat_uniforms(shape, glat_seed):
     return u.view(*shape)
 
 
-def run_case(name, B, R, adaptive, seed, glat_p=-1.0, glat_seed=0):
-    cfg = BofiConfig()
+def run_case(name, B, R, adaptive, seed, glat_p=-1.0, glat_seed=0, cfg_kw=None):
+    cfg = BofiConfig(**(cfg_kw or {}))
     sd = synth.synth_state_dict(cfg, 0, "s_real")
-    model, _ = ref_shim.build_reference_model(sd, vocab_size=cfg.vocab_size)
+    model, _ = ref_shim.build_reference_model(sd, vocab_size=cfg.vocab_size, N_enc=cfg.N_enc, N_dec=cfg.N_dec, N_len=cfg.N_len)
     # TransformerModel.py:481-482 allocates requires_grad leaves and then writes into them in place (an error on
     # torch >= 2): drop the flag, the tensors pick up the graph from the values assigned into them
     nz = torch.Tensor.new_zeros
@@ -86,7 +88,8 @@ def run_case(name, B, R, adaptive, seed, glat_p=-1.0, glat_seed=0):
     words = bt["labels"].reshape(-1, bt["labels"].shape[2])[:, 1:-1]
     fix = dict(B=np.array(B), R=np.array(R), adaptive=np.array(adaptive), input_seed=np.array(7), batch_seed=np.array(seed),
                sa_len=sa_len.numpy(), sa_syn=sa_syn.numpy(), na_len=na_len.numpy(), na_syn=na_syn.numpy(),
-               losses=np.array([float(v) for v in losses], dtype=np.float64), glat_p=np.array(glat_p), glat_seed=np.array(glat_seed))
+               losses=np.array([float(v) for v in losses], dtype=np.float64), glat_p=np.array(glat_p), glat_seed=np.array(glat_seed),
+               cfg_kw=np.array(json.dumps(cfg_kw or {})))
     for tag, lp in (("sa", sa_logp), ("na", na_logp)):
         fix[tag + "_logp_head"] = lp[:, :, :LOGP_COLS].numpy()
         fix[tag + "_logp_max"] = lp.max(2).values.numpy()

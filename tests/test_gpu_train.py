@@ -239,6 +239,90 @@ def test_xe_glancing_matches_oracle_fp32(glat_p, drop_on):
     assert abs(l_off - float(losses[0])) > 1e-4
 
 
+def _two_layer_case(precision):
+    from boficap_b200.captioning import models
+    from oracle.bofi_oracle import BofiOracle, OracleConfig
+    cfg = BofiConfig(N_len=2)
+    sd = synth.synth_state_dict(cfg, 0, "s_real")
+    osd = {k: v.clone() for k, v in sd.items()}
+    for k, v in osd.items():
+        if k != "model.pos_embed.pe":
+            v.requires_grad_(True)
+    o = BofiOracle.__new__(BofiOracle)
+    o.sd, o.cfg, o.record, o.trace = osd, OracleConfig(**cfg.to_dict()), False, {}
+    infos = synth.make_infos(cfg)
+    opt = infos["opt"]
+    opt.vocab = infos["vocab"]
+    opt.bofi_precision = precision
+    model = models.setup(opt)
+    model.load_state_dict(sd)
+    return cfg, o, osd, model.cuda().eval()
+
+
+def test_xe_two_bounding_layers_fp32():
+    """configs/uic_sd_N2.yml (N_len = 2): every bounding pass runs both LengthPredictor layers over all rows under that pass's mask
+    (train.inl: t_bound_fwd_full, the reference's own formulation).  Six outputs, criterion and all 336 gradients against the oracle,
+    which tests/test_oracle_golden_xe.py pins to the unmodified reference for this configuration (xe_b2_r12_nlen2)."""
+    from oracle.bofi_oracle import BofiOracle
+    B, R, adaptive, seed = CASES[1]
+    cfg, o, osd, model = _two_layer_case("fp32")
+    fc, att, masks = synth.synth_inputs(B, R, seed=7, adaptive=adaptive)
+    bt = synth.synth_xe_batch(B, seed=seed, vocab_size=cfg.vocab_size)
+    outs = o.forward_xe(att, masks, bt["labels"], bt["phrase_num"], bt["phrase_length"], bt["extend_phrase_syn_seq"], bt["extend_phrase_seq"],
+                        bt["extend_phrase_seq_mask"])
+    loss, parts = o.loss_xe(outs, bt["phrase_num"], bt["phrase_length"], bt["phrase_syn"], bt["labels"])
+    loss.backward()
+    ref_grads = {k: (v.grad.detach().clone() if v.grad is not None else torch.zeros_like(v)) for k, v in osd.items() if k != "model.pos_embed.pe"}
+    args, _ = batch_args(B, R, adaptive, seed, cfg)
+    got = model(*args)
+    for g, w, name in zip(got, outs, ("sa_len", "sa_syn", "sa_logp", "na_len", "na_syn", "na_logp")):
+        err = float((g.detach().cpu() - w.detach()).abs().max())
+        assert err < 1e-4, (name, err)
+    model.zero_grad()
+    losses = model.xe_step(*args).cpu().numpy()
+    np.testing.assert_allclose(losses, [float(loss)] + [float(p) for p in parts], rtol=2e-5)
+    worst, name, cos = grad_report(model, ref_grads)
+    print("N_len=2 XE step: worst gradient error %.2e (%s), worst cosine %.6f" % (worst, name, cos))
+    assert worst < 2e-3 and cos > 0.99999, (worst, name, cos)
+    # both bounding layers (and their memory K/V projections) receive gradient
+    for key in ("model.length_predictor.LengthPredictor.0.ff.w_1.weight", "model.length_predictor.LengthPredictor.1.ff.w_1.weight",
+                "model.length_predictor.LengthPredictor.1.src_attn.linears.1.weight"):
+        assert float(dict(model.named_parameters())[key].grad.abs().max()) > 0
+
+
+def test_xe_two_bounding_layers_bf16_and_dropout():
+    """N_len = 2 on the tensor-core path: losses within 2e-2 of the oracle, gradient direction kept; train() mode (dropout on) is finite
+    and reproducible for a fixed seed."""
+    from oracle.bofi_oracle import BofiOracle
+    B, R, adaptive, seed = CASES[0]
+    cfg, o, osd, model = _two_layer_case("bf16")
+    fc, att, masks = synth.synth_inputs(B, R, seed=7, adaptive=adaptive)
+    bt = synth.synth_xe_batch(B, seed=seed, vocab_size=cfg.vocab_size)
+    outs = o.forward_xe(att, masks, bt["labels"], bt["phrase_num"], bt["phrase_length"], bt["extend_phrase_syn_seq"], bt["extend_phrase_seq"],
+                        bt["extend_phrase_seq_mask"])
+    loss, parts = o.loss_xe(outs, bt["phrase_num"], bt["phrase_length"], bt["phrase_syn"], bt["labels"])
+    loss.backward()
+    ref_grads = {k: (v.grad.detach().clone() if v.grad is not None else torch.zeros_like(v)) for k, v in osd.items() if k != "model.pos_embed.pe"}
+    args, _ = batch_args(B, R, adaptive, seed, cfg)
+    model.train_bind()
+    model.zero_grad()
+    losses = model.xe_step(*args).cpu().numpy()
+    np.testing.assert_allclose(losses, [float(loss)] + [float(p) for p in parts], rtol=2e-2)
+    worst, name, cos = grad_report(model, ref_grads)
+    print("N_len=2 bf16 XE step: worst relative gradient error %.3f (%s), worst cosine %.5f" % (worst, name, cos))
+    assert cos > 0.98, (worst, name, cos)
+    model.train()
+    runs = []
+    for _ in range(2):
+        model.bofi_dropout_seed, model._train_steps = 5, 0
+        model.zero_grad()
+        l = model.xe_step(*args).cpu().numpy()
+        runs.append((l, model.flat_grads().clone()))
+    assert np.isfinite(runs[0][0]).all() and bool(torch.isfinite(runs[0][1]).all())
+    np.testing.assert_allclose(runs[0][0], runs[1][0], rtol=1e-5)
+    assert abs(float(runs[0][0][0]) - float(losses[0])) > 1e-3        # dropout changes the loss
+
+
 def test_xe_dropout_bf16_statistics():
     """bf16 / tensor-core path with dropout: finite, reproducible for a fixed seed, different across seeds."""
     B, R, adaptive, seed = CASES[0]

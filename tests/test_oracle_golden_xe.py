@@ -12,12 +12,12 @@ from boficap_b200.layout import BofiConfig
 from oracle.bofi_oracle import BofiOracle, OracleConfig
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
-CASES = ["xe_b2_r12", "xe_b3_r20_adaptive"]
+CASES = ["xe_b2_r12", "xe_b3_r20_adaptive", "xe_b2_r12_nlen2"]      # (the last: two bounding layers, configs/uic_sd_N2.yml)
 GLAT_CASES = ["xe_b3_r20_glat", "xe_b2_r12_glat1"]      # glancing training: forward_xe_fused(glat_p, glat_seed) vs the reference with the same uniforms
 
 
 def run_oracle_xe(fix, requires_grad=True):
-    cfg = BofiConfig()
+    cfg = BofiConfig(**(json.loads(str(fix["cfg_kw"])) if "cfg_kw" in fix else {}))
     sd = synth.synth_state_dict(cfg, 0, "s_real")
     if requires_grad:
         for k, v in sd.items():
