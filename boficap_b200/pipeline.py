@@ -22,7 +22,7 @@ from .engine import BofiEngine
 
 class _Group:
     """The submissions that will be decoded by one library call on one slot."""
-    __slots__ = ("slot", "key", "parts", "event", "out", "launched", "host", "kw", "att_keep", "size")
+    __slots__ = ("slot", "key", "parts", "event", "out", "launched", "host", "kw", "size")
 
     def __init__(self, slot, key, host, kw, size):
         self.slot, self.key, self.host, self.kw, self.size = slot, key, host, kw, size
@@ -30,7 +30,6 @@ class _Group:
         self.event = None
         self.out = None
         self.launched = False
-        self.att_keep = []
 
 
 class Ticket:
