@@ -379,6 +379,8 @@ def main():
                     help="decode = BASELINE.json's headline metric; xe = XE training step (config 5: 256 images x 5 captions per GPU)")
     ap.add_argument("--no-dropout", action="store_true", help="xe workload: eval() arithmetic (dropout off)")
     ap.add_argument("--depth", type=int, default=3, help="engine handles x streams in flight (boficap_b200/pipeline.py)")
+    ap.add_argument("--compact", action="store_true", help="with --adaptive: the e2e leg sends compact features (valid regions only, "
+                                                            "bofi_stage_compact) instead of the padded [B, R, F] batch")
     ap.add_argument("--n-len", type=int, default=1, help="xe workload: bounding layers (configs/uic_sd_N2.yml: 2)")
     ap.add_argument("--group", type=int, default=2, help="consecutive batches decoded by ONE library call on a slot, every batch with its own "
                                                           "fill window (bofi_set_shard): bit-identical results, one bounding loop per group")
@@ -539,7 +541,10 @@ def main():
     # pinned host input, `depth` batches in flight through bofi_sample_host_async_ex
     def run_host(n, feats):
         pipe.fork_from(main)
-        ts = [pipe.submit_host(feats, len_host, a.mode, 1, 1) for _ in range(n)]
+        if feats.dim() == 2:                                     # compact features: only the valid regions cross PCIe
+            ts = [pipe.submit_host_compact(feats, len_host, R, a.mode, 1, 1) for _ in range(n)]
+        else:
+            ts = [pipe.submit_host(feats, len_host, a.mode, 1, 1) for _ in range(n)]
         pipe.join_into(main)
         return ts
 
@@ -565,10 +570,14 @@ def main():
 
     if rank == 0:
         sampler.start()
-    ms_e2e, host_out = time_host(att_host_lp)
+    e2e_feats = att_host_lp
+    if a.compact and len_host is not None:
+        # the feeder's compact format (boficap_b200/data: PinnedFeeder(compact=True)): the valid regions only, image after image
+        e2e_feats = torch.cat([att_host_lp[b, :int(len_host[b])] for b in range(B)]).contiguous().pin_memory()
+    ms_e2e, host_out = time_host(e2e_feats)
     clocks = sampler.stop() if rank == 0 else None
     assert torch.equal(host_out["seq"], ref_seq.cpu()), "host-path captions differ from the device path"
-    h2d = att_host_lp.numel() * att_host_lp.element_size() + (len_host.numel() * 4 if len_host is not None else 0)
+    h2d = e2e_feats.numel() * e2e_feats.element_size() + (len_host.numel() * 4 if len_host is not None else 0)
     d2h = sum(host_out[k].numel() * host_out[k].element_size() for k in ("seq", "pnum", "plen", "psyn"))
     ms_e2e32 = None
     if not a.no_extras and host_dt != torch.float32:
@@ -721,7 +730,8 @@ def main():
     e2e = {"value": e2e_value, "unit": "captions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "ms_per_step": ms_e2e / a.steps, "host_feature_dtype": a.host_dtype,
            "api": "%s, pinned host buffers (%s features), %d batches in flight%s"
-                  % ("bofi_sample_host_async_ex" if pipe.group == 1 else "bofi_stage_part x %d + bofi_sample_staged (batches of a group share one library call)" % pipe.group,
+                  % ("bofi_stage_compact + bofi_encode_staged_compact + bofi_decode_host_async (compact features: sum(att_len) rows per batch)"
+                     if e2e_feats.dim() == 2 else "bofi_sample_host_async_ex" if pipe.group == 1 else "bofi_stage_part x %d + bofi_sample_staged (batches of a group share one library call)" % pipe.group,
                      a.host_dtype, pipe.depth * pipe.group, ", caption all_gather inside the timed region" if world > 1 else "")}
     line = {"metric": METRIC, "value": value, "unit": "captions/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

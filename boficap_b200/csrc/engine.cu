@@ -667,15 +667,21 @@ static int reserve_decode(bofi_engine* e, int B, int R, int sn) {
 
 // ---- encode --------------------------------------------------------------------------------------------
 template <typename T>
-static int encode_impl(bofi_engine* e, cudaStream_t s, const void* att, int fdt, const int* att_len, int B, int R, float* memory_out) {
+// compact_rows > 0: `att` holds ONLY the valid regions, image after image ([compact_rows, F] with compact_rows = sum(att_len)):
+// att_embed then runs on the compact rows directly -- no padded GEMM, no compaction pass, and a host caller copies sum(att_len)
+// rows instead of B * R.
+static int encode_impl(bofi_engine* e, cudaStream_t s, const void* att, int fdt, const int* att_len, int B, int R, float* memory_out,
+                       int compact_rows = 0) {
   const int M = B * R, F = e->cfg.att_feat_size;
+  if (compact_rows > 0 && (!att_len || !e->varlen || memory_out || compact_rows > M))
+    return fail(BOFI_ERR_INVALID, "compact features need att_len, the varlen encoder (BOFI_VARLEN), memory_out == NULL and sum(att_len) <= B * R");
   RC_TRY(reserve_encode(e, B, R));
   float* x = e->x.as<float>();
   // ---- features as the GEMM operand type.  bf16 engine + bf16 features: the caller's buffer IS the operand (TMA reads it
   // in place, no conversion pass); anything else goes through one conversion kernel into attT.
   const T* a_in;
   {
-    const size_t n = (size_t)M * F;
+    const size_t n = (size_t)(compact_rows > 0 ? compact_rows : M) * F;
     const bool direct = (std::is_same<T, bf16>::value && fdt == BOFI_FEAT_BF16) || (std::is_same<T, float>::value && fdt == BOFI_FEAT_F32);
     if (direct) {
       if (reinterpret_cast<uintptr_t>(att) & 15) return fail(BOFI_ERR_INVALID, "att_feats must be 16-byte aligned");
@@ -714,17 +720,18 @@ static int encode_impl(bofi_engine* e, cudaStream_t s, const void* att, int fdt,
     // Varlen: att_embed on the padded layout (the features arrive padded; it is 5 % of the encoder's work), then every
     // valid row moves to its compact position and the layers only see sum(att_len) rows -- the row count lives on the
     // device (rows_dev), so nothing synchronises.  Padded rows never exist, so they need no zeroing and no key mask.
-    RC_TRY(e->xpad.reserve((size_t)M * kD * 4));
+    const bool compact_in = compact_rows > 0;
+    if (!compact_in || memory_out) RC_TRY(e->xpad.reserve((size_t)M * kD * 4));
     RC_TRY(e->seqoff.reserve((size_t)(B + 2) * 4));
     int* off = e->seqoff.as<int>();
     int* total = off + B + 1;
-    RC_TRY((linear<T, float>(e, s, a_in, F, e->att_embed, nullptr, 0, e->xpad.as<float>(), kD, M, 1, nullptr)));
+    if (!compact_in) RC_TRY((linear<T, float>(e, s, a_in, F, e->att_embed, nullptr, 0, e->xpad.as<float>(), kD, M, 1, nullptr)));
     {
       ProfScope prof(e, s, PC_OTHER, 0.0, 0.0);
       launch_k(varlen_scan_kernel, 1, 1024, 0, s, len_dev, B, R, off, total);
     }
     CU_TRY(cudaGetLastError());
-    {
+    if (!compact_in) {
       ProfScope prof(e, s, PC_OTHER, 0.0, (double)M * kD * 8);
       launch_k(varlen_rows_kernel<false>, ceil_div(M, 8), 256, 0, s, (const float*)e->xpad.as<float>(), (const int*)off, B, R, x);
     }
@@ -738,6 +745,9 @@ static int encode_impl(bofi_engine* e, cudaStream_t s, const void* att, int fdt,
     }
     e->rows_dev = e->varlen_total = total;
     e->enc_off = off;
+    // compact features: att_embed straight onto the compact rows (the GEMM walks the tiles below the device-side row count)
+    // (M = the host-side row count: the tensor maps end at the last compact row, so the caller's buffer needs no slack)
+    if (compact_in) RC_TRY((linear<T, float>(e, s, a_in, F, e->att_embed, nullptr, 0, x, kD, compact_rows, 1, nullptr)));
     const int rc = run_stack<T>(e, s, e->enc, e->enc_norm, e->memT.as<T>(), memory_out ? e->xpad.as<float>() : nullptr, x, B, R, len_dev, 1, 0,
                                 (const T* const*)nullptr, 0, nullptr, 1, nullptr);
     e->rows_dev = nullptr;
@@ -1543,6 +1553,46 @@ int bofi_encode_ex(bofi_handle_t e, void* stream, const void* att_feats, int32_t
 
 int bofi_encode(bofi_handle_t e, void* stream, const float* att_feats, const int32_t* att_len, int32_t B, int32_t R, float* memory_out) {
   return bofi_encode_ex(e, stream, att_feats, BOFI_FEAT_F32, att_len, B, R, memory_out);
+}
+
+int bofi_encode_compact(bofi_handle_t e, void* stream, const void* att_compact, int32_t feat_dtype, const int32_t* att_len, int32_t total_rows,
+                        int32_t B, int32_t R) {
+  if (!e || !att_compact || !att_len) return fail(BOFI_ERR_INVALID, "null argument");
+  if (!e->finalized) return fail(BOFI_ERR_STATE, "weights not finalised");
+  if (B <= 0 || R <= 0 || R > kMaxKeys || total_rows <= 0) return fail(BOFI_ERR_INVALID, "bad batch B=%d R=%d rows=%d (R <= %d)", B, R, total_rows, kMaxKeys);
+  if (feat_dtype != BOFI_FEAT_F32 && feat_dtype != BOFI_FEAT_BF16 && feat_dtype != BOFI_FEAT_F16)
+    return fail(BOFI_ERR_INVALID, "feat_dtype %d (BOFI_FEAT_F32 / BF16 / F16)", feat_dtype);
+  CU_TRY(cudaSetDevice(e->device));
+  e->launches = 0;
+  e->have_memory = false;
+  cudaStream_t s = (cudaStream_t)stream;
+  return e->bf16_mode ? encode_impl<bf16>(e, s, att_compact, feat_dtype, att_len, B, R, nullptr, total_rows)
+                      : encode_impl<float>(e, s, att_compact, feat_dtype, att_len, B, R, nullptr, total_rows);
+}
+
+int bofi_stage_compact(bofi_handle_t e, void* stream, const void* att_compact, int32_t feat_dtype, const int32_t* att_len, int32_t total_rows,
+                       int32_t B, int32_t R) {
+  if (!e || !att_compact || !att_len) return fail(BOFI_ERR_INVALID, "null argument");
+  if (feat_dtype != BOFI_FEAT_F32 && feat_dtype != BOFI_FEAT_BF16 && feat_dtype != BOFI_FEAT_F16)
+    return fail(BOFI_ERR_INVALID, "feat_dtype %d (BOFI_FEAT_F32 / BF16 / F16)", feat_dtype);
+  if (B <= 0 || R <= 0 || total_rows <= 0 || (int64_t)total_rows > (int64_t)B * R) return fail(BOFI_ERR_INVALID, "compact rows %d of at most %d x %d", total_rows, B, R);
+  CU_TRY(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t per_row = (size_t)e->cfg.att_feat_size * (feat_dtype == BOFI_FEAT_F32 ? 4 : 2);
+  RC_TRY(e->h_in.reserve((size_t)B * R * per_row));          // the tensor map of the att_embed GEMM spans B * R rows
+  RC_TRY(e->h_len.reserve((size_t)B * 4));
+  CU_TRY(cudaMemcpyAsync(e->h_in.p, att_compact, (size_t)total_rows * per_row, cudaMemcpyDefault, s));
+  CU_TRY(cudaMemcpyAsync(e->h_len.p, att_len, (size_t)B * 4, cudaMemcpyDefault, s));
+  return BOFI_OK;
+}
+
+int bofi_encode_staged_compact(bofi_handle_t e, void* stream, int32_t feat_dtype, int32_t total_rows, int32_t B, int32_t R) {
+  if (!e) return fail(BOFI_ERR_INVALID, "null handle");
+  if (B <= 0 || R <= 0) return fail(BOFI_ERR_INVALID, "bad batch B=%d R=%d", B, R);
+  const size_t need = (size_t)B * R * e->cfg.att_feat_size * (feat_dtype == BOFI_FEAT_F32 ? 4 : 2);
+  if (!e->h_in.p || e->h_in.cap < need || e->h_len.cap < (size_t)B * 4)
+    return fail(BOFI_ERR_STATE, "bofi_encode_staged_compact: nothing staged for %d x %d regions (bofi_stage_compact)", B, R);
+  return bofi_encode_compact(e, stream, e->h_in.p, feat_dtype, e->h_len.as<int>(), total_rows, B, R);
 }
 
 int bofi_masks_to_len(bofi_handle_t e, void* stream, const float* att_masks, int32_t B, int32_t R, int32_t* att_len) {

@@ -16,9 +16,13 @@ import torch
 
 
 class PinnedFeeder:
-    def __init__(self, reader, keys, batch_size, max_regions, feat_size=2048, dtype=torch.bfloat16, depth=5, drop_last=False, pin=None):
+    def __init__(self, reader, keys, batch_size, max_regions, feat_size=2048, dtype=torch.bfloat16, depth=5, drop_last=False, pin=None,
+                 compact=False):
+        """compact=True: a batch is `(att_compact [sum(att_len), F], att_len [n], keys)` -- only the valid regions, image after image,
+        what pack_wrapper (AttModel.py:33-51) feeds att_embed -- for BofiPipeline.submit_host_compact / bofi_stage_compact: with
+        10..100 regions per image 44 % fewer bytes cross PCIe than with the padded [B, R, F] batch."""
         self.reader, self.keys, self.B, self.R = reader, list(keys), batch_size, max_regions
-        self.dtype, self.depth, self.drop_last = dtype, max(2, depth), drop_last
+        self.dtype, self.depth, self.drop_last, self.compact = dtype, max(2, depth), drop_last, compact
         pin = torch.cuda.is_available() if pin is None else pin
         mk = lambda *shape, dt: torch.zeros(*shape, dtype=dt).pin_memory() if pin else torch.zeros(*shape, dtype=dt)
         self.slots = [(mk(batch_size, max_regions, feat_size, dt=dtype), mk(batch_size, dt=torch.int32)) for _ in range(self.depth)]
@@ -39,6 +43,15 @@ class PinnedFeeder:
                 i = self.free.get()
                 att, lens = self.slots[i]
                 n = len(keys)
+                if self.compact:
+                    rows = att.view(-1, att.shape[-1])          # the same pinned memory as [B * R, F]
+                    pos = 0
+                    for b, k in enumerate(keys):
+                        cnt = self.reader.get_into(k, rows[pos:pos + self.R])
+                        lens[b] = cnt
+                        pos += cnt
+                    self.ready.put((i, n, keys, pos))
+                    continue
                 for b, k in enumerate(keys):
                     cnt = self.reader.get_into(k, att[b])
                     if cnt < self.R:
@@ -58,9 +71,11 @@ class PinnedFeeder:
             raise StopIteration
         if isinstance(item, Exception):
             raise item
-        i, n, keys = item
+        i, n, keys = item[:3]
         self.held.append(i)
         if len(self.held) >= self.depth - 1:                    # the oldest batch handed out is finished by now
             self.free.put(self.held.pop(0))
         att, lens = self.slots[i]
+        if self.compact:
+            return att.view(-1, att.shape[-1])[:item[3]], lens[:n], keys
         return att[:n], lens[:n], keys

@@ -107,6 +107,37 @@ class BofiEngine:
                                                _ptr(seq), _ptr(logp), ld, _ptr(pnum), _ptr(plen), _ptr(psyn)))
         return seq, logp, pnum, plen, psyn
 
+    # ---- compact features: only the valid regions, image after image (bofi_encode_compact / bofi_stage_compact) ----------------
+    def encode_compact(self, att_compact, att_len, R):
+        """att_compact [sum(att_len), F] device tensor (fp32 / bf16 / fp16), att_len [B]: _prepare_feature + encoder on the valid
+        regions only; same memory as encode() on the padded [B, R, F] tensor."""
+        assert att_compact.is_cuda and att_compact.is_contiguous() and att_compact.dim() == 2
+        att_len = att_len.to(device=att_compact.device, dtype=torch.int32).contiguous()
+        B = att_len.shape[0]
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bofi_encode_compact(self.handle, self._stream(), _ptr(att_compact), _feat_code(att_compact), _ptr(att_len),
+                                                    int(att_compact.shape[0]), B, int(R)))
+        self._batch = (B, R, att_compact, att_len)
+
+    def stage_compact(self, att_compact, att_len, R):
+        """Asynchronous copy of a compact batch (pinned host or device) into the library's staging buffer."""
+        assert att_compact.is_contiguous() and att_compact.dim() == 2
+        att_len = att_len.to(torch.int32).contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bofi_stage_compact(self.handle, self._stream(), _ptr(att_compact), _feat_code(att_compact), _ptr(att_len),
+                                                   int(att_compact.shape[0]), int(att_len.shape[0]), int(R)))
+        gens = getattr(self, "_stage_gens", None)
+        if gens is None:
+            gens = self._stage_gens = []
+        gens.append([(att_compact, att_len)])
+        del gens[:-3]
+        return _feat_code(att_compact)
+
+    def encode_staged_compact(self, code, total_rows, B, R):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bofi_encode_staged_compact(self.handle, self._stream(), int(code), int(total_rows), int(B), int(R)))
+        self._batch = (B, R, None, None)
+
     # ---- several batches in one call (bofi_set_shard / bofi_stage_part / bofi_encode_staged / bofi_sample_staged) --------------
     def set_shard(self, shard_images):
         """The images of the following encode / decode calls are batches of `shard_images` images that keep their own fill

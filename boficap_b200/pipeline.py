@@ -219,3 +219,31 @@ class BofiPipeline:
         t = Ticket(ev, out, slot)
         self.just_launched = launched + [t]
         return t
+
+    def submit_host_compact(self, att_compact, att_len, max_regions, mode="NAIC", sample_n=1, output_logsoftmax=1, want_logprobs=False):
+        """Pinned COMPACT host features ([sum(att_len), F]: only the valid regions, image after image; boficap_b200/data:
+        PinnedFeeder(compact=True)) -> pinned host outputs.  sum(att_len) instead of B * R rows cross PCIe and att_embed runs on
+        them directly.  One batch per library call (no grouping), staged on the slot's copy stream like submit_host."""
+        assert att_compact.is_pinned() and att_len is not None
+        if not att_len.is_pinned():
+            att_len = att_len.to(torch.int32).pin_memory()
+        launched = self._launch(self._open) if self._open is not None else []
+        slot = self._next()
+        eng, st, cs = self.engines[slot], self.streams[slot], self.copy_streams[slot]
+        B, total = int(att_len.shape[0]), int(att_compact.shape[0])
+        with torch.cuda.stream(cs):
+            cs.wait_event(self.enc_done[slot])
+            code = eng.stage_compact(att_compact, att_len, max_regions)
+            staged = torch.cuda.Event()
+            staged.record(cs)
+        with torch.cuda.stream(st):
+            st.wait_event(staged)
+            eng.encode_staged_compact(code, total, B, max_regions)
+            self.enc_done[slot].record(st)
+            out = eng.decode_host(mode, sample_n, output_logsoftmax, out=self.host_out[slot], want_logprobs=want_logprobs)
+            self.host_out[slot] = out
+            ev = torch.cuda.Event()
+            ev.record(st)
+        t = Ticket(ev, out, slot)
+        self.just_launched = launched + [t]
+        return t

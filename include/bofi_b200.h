@@ -129,6 +129,18 @@ int bofi_decode_ex(bofi_handle_t h, void* stream, int32_t mode, int32_t sample_n
                    int64_t* seq, float* logprobs, int64_t logprob_ld, int32_t* phrase_num, int32_t* phrase_length,
                    int64_t* phrase_syn);
 
+/* _prepare_feature on COMPACT features: att_compact holds only the valid regions, image after image -- [total_rows, F] with
+ * total_rows = sum(att_len) -- which is what pack_wrapper (AttModel.py:33-51) hands to att_embed.
+ * att_embed runs on those rows directly (no padded GEMM, no compaction pass) and a host caller moves sum(att_len) instead of B * R
+ * rows over PCIe.  Same memory (bit for bit) as bofi_encode_ex on the padded tensor with the same att_len.  Needs att_len.
+ * bofi_stage_compact copies a host (or device) compact batch into the library's staging buffer, bofi_encode_staged_compact encodes
+ * it; follow with bofi_decode / bofi_decode_host_async. */
+int bofi_encode_compact(bofi_handle_t h, void* stream, const void* att_compact, int32_t feat_dtype, const int32_t* att_len,
+                        int32_t total_rows, int32_t B, int32_t R);
+int bofi_stage_compact(bofi_handle_t h, void* stream, const void* att_compact, int32_t feat_dtype, const int32_t* att_len,
+                       int32_t total_rows, int32_t B, int32_t R);
+int bofi_encode_staged_compact(bofi_handle_t h, void* stream, int32_t feat_dtype, int32_t total_rows, int32_t B, int32_t R);
+
 /* Several batches in ONE call (what nn.DataParallel replicas / successive eval batches are to the reference: independent
  * `_sample` calls).  The only place where a row of `_sample` depends on the other rows of its batch is the fill window
  * w = last[B-1] - 1 of core_NAIC (TransformerModel.py:1871-1873).  With bofi_set_shard(h, n) the B images of the following

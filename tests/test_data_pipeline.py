@@ -101,3 +101,15 @@ def test_reader_dispatch_and_feeder_batches(tmp_path):
         got += ks
     assert got == keys
     assert [len(k) for *_, k in PinnedFeeder(readers[1], keys, 4, 8, feat_size=16, depth=3, pin=False, drop_last=True)] == [4, 4]
+    # compact batches: only the valid regions, image after image (what pack_wrapper hands to att_embed)
+    got = []
+    for att, lens, ks in PinnedFeeder(readers[0], keys, 4, 8, feat_size=16, dtype=torch.bfloat16, depth=4, pin=False, compact=True):
+        assert att.dim() == 2 and att.shape[0] == int(lens.sum()) and lens.shape[0] == len(ks)
+        pos = 0
+        for b, k in enumerate(ks):
+            n = feats[k].shape[0]
+            assert int(lens[b]) == n
+            assert torch.equal(att[pos:pos + n], torch.from_numpy(feats[k]).to(torch.bfloat16))
+            pos += n
+        got += ks
+    assert got == keys

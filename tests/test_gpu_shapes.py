@@ -133,3 +133,37 @@ def test_host_slot_buffers_follow_the_batch_shape():
     ref.encode(big.to(torch.bfloat16).cuda())
     assert torch.equal(d["seq"], ref.decode("NAIC", 1, 1, False)[0].cpu())
     pipe.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_compact_features_equal_padded_features(precision):
+    """bofi_encode_compact / BofiPipeline.submit_host_compact: only the valid regions, image after image (sum(att_len) rows instead of
+    B * R) give bit for bit the memory and the decode of the padded tensor with the same att_len -- device entry (fp32 and bf16
+    features) and the pinned-host pipeline entry."""
+    from boficap_b200.engine import BofiEngine
+    from boficap_b200.pipeline import BofiPipeline
+    cfg = BofiConfig()
+    sd = checkpoint(cfg, "s_cap")
+    eng = BofiEngine(cfg, 0, precision).load_state_dict(sd)
+    pipe = BofiPipeline(cfg, sd, 0, precision, depth=2, group=2)
+    for (B, R, fdt) in ((70, 60, torch.float32), (200, 100, torch.bfloat16)):
+        _, att, masks = synth.synth_inputs(B, R, seed=300 + B, adaptive=True)
+        att = att.to(fdt)
+        lens = masks.long().sum(1).int()
+        compact = torch.cat([att[b, :int(lens[b])] for b in range(B)]).contiguous()
+        assert compact.shape[0] == int(lens.sum()) < B * R
+        eng.encode(att.cuda(), lens.cuda())
+        want = [t.cpu() for t in eng.decode("NAIC", 1, 1, True)]
+        eng.encode_compact(compact.cuda(), lens.cuda(), R)
+        got = [t.cpu() for t in eng.decode("NAIC", 1, 1, True)]
+        for x, y in zip(want, got):
+            assert torch.equal(torch.nan_to_num(x.float()), torch.nan_to_num(y.float())), (precision, B, R)
+        if fdt == torch.bfloat16:
+            t1 = pipe.submit_host_compact(compact.pin_memory(), lens.pin_memory(), R, want_logprobs=True)
+            t2 = pipe.submit_host(att.pin_memory(), lens.pin_memory(), want_logprobs=True)       # (a group of one, flushed by wait)
+            for t in (t1, t2):
+                out = t.wait()
+                for x, y in zip(want, (out["seq"], out["logp"], out["pnum"], out["plen"], out["psyn"])):
+                    assert torch.equal(torch.nan_to_num(x.float()), torch.nan_to_num(y.float()))
+    pipe.close()
+    eng.close()
