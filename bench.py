@@ -181,7 +181,7 @@ def bench_xe(a, rank, local_rank, world):
             dev(bt["extend_phrase_syn_seq"]), dev(bt["extend_phrase_seq"]), dev(bt["extend_phrase_seq_mask"]))
     eng = model._engine
     # bucketed all-reduce of the flat gradient buffer, the decoder-side buckets underneath the encoder's backward pass
-    reducer = OverlappedGradReduce(model, buckets=a.buckets) if dist is not None else None
+    reducer = OverlappedGradReduce(model, buckets=a.buckets, layer_buckets=not a.no_layer_buckets) if dist is not None else None
 
     def step():
         flat_g.zero_()
@@ -241,8 +241,10 @@ def bench_xe(a, rank, local_rank, world):
                 "config": {"workload": "uic_sd%s XE training step (forward + criterion + backward + all-reduce + Adam), %d images x %d captions per GPU, "
                                        "%d regions, %s, dropout %s" % ("" if a.n_len == 1 else "_N%d" % a.n_len, B, spi, R, a.precision,
                                                                        "off" if a.no_dropout else "on (p=0.1, att_embed 0.5)"),
-                           "parallelism": "data-parallel replicas x%d, NCCL all-reduce of the %.0f MB flat gradient buffer in %d + 1 buckets, the decoder-side "
-                                          "buckets overlapped with the encoder's backward pass" % (world, flat_g.numel() * 4 / 1e6, a.buckets)},
+                           "parallelism": "data-parallel replicas x%d, NCCL all-reduce of the %.0f MB flat gradient buffer in %d + %s buckets, the decoder-side "
+                                          "buckets overlapped with the encoder's backward pass%s"
+                                          % (world, flat_g.numel() * 4 / 1e6, a.buckets, "1" if a.no_layer_buckets else "%d + 1" % cfg.N_enc,
+                                             "" if a.no_layer_buckets else ", the encoder layers' buckets with the backward pass of the layers below")},
                 "loss_first": first, "loss_last": float(losses[0]), "gpu_launches": launches * a.steps, "clocks": clocks,
                 "gpu_eager": eager,
                 "roofline": {"bound": "tensor", "kernel": "gemm_tc2_kernel / gemm_tc_kernel (tcgen05), all %d launches of a step" % g["launches"],
@@ -381,6 +383,8 @@ def main():
     ap.add_argument("--depth", type=int, default=3, help="engine handles x streams in flight (boficap_b200/pipeline.py)")
     ap.add_argument("--compact", action="store_true", help="with --adaptive: the e2e leg sends compact features (valid regions only, "
                                                             "bofi_stage_compact) instead of the padded [B, R, F] batch")
+    ap.add_argument("--no-layer-buckets", action="store_true", help="xe workload: the encoder part of the gradients as ONE all-reduce after "
+                                                                      "the backward pass instead of one per encoder layer underneath it")
     ap.add_argument("--n-len", type=int, default=1, help="xe workload: bounding layers (configs/uic_sd_N2.yml: 2)")
     ap.add_argument("--group", type=int, default=2, help="consecutive batches decoded by ONE library call on a slot, every batch with its own "
                                                           "fill window (bofi_set_shard): bit-identical results, one bounding loop per group")

@@ -77,6 +77,7 @@ _SIGNATURES = {
     "bofi_sc_backward": (C.c_int, [_P, _P, _P, _P]),
     "bofi_sc_inputs": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "bofi_train_set_grad_event": (C.c_int, [_P, _P]),
+    "bofi_train_set_layer_event": (C.c_int, [_P, _I, _P]),
     "bofi_train_set_glat": (C.c_int, [_P, C.c_float, C.c_uint32]),
     "bofi_layernorm_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, _I]),
     "bofi_linear_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I]),

@@ -115,6 +115,7 @@ struct TrainState {
   uint32_t glat_seed = 0;
   int* glat_words = nullptr;      // [N, T] bos or the ground-truth word per slot (nullptr: glancing off, constant bos)
   cudaEvent_t grad_event = nullptr;   // bofi_train_set_grad_event: recorded once every gradient outside the encoder is final
+  std::vector<cudaEvent_t> layer_events;   // bofi_train_set_layer_event: [l] recorded once encoder layer l's gradients are final
   uint32_t seed = 0, site = 0;
   Drop d_att_embed;
   Drop next_drop(float p) {
@@ -963,9 +964,12 @@ static int t_encode_bwd(bofi_engine* e, cudaStream_t s, TrainState* ts, float* d
   // encoder: final LayerNorm, layers, att_embed
   RC_TRY((ln_bwd<float, T>(e, s, ts, e->enc_norm, ts->enc_x_final, dmem, nullptr, dx, dxT, M)));
   const int* len_dev = ts->att_len;
-  for (int l = c.n_enc - 1; l >= 0; --l)
+  for (int l = c.n_enc - 1; l >= 0; --l) {
     RC_TRY(t_layer_bwd<T>(e, s, ts, e->enc[l], ts->enc[l], dx, dxT, g1, g2, B, R, len_dev, 1, 0, (const T*)nullptr, (T*)nullptr, 0, 0, nullptr, 1,
                           false));
+    // the gradients of encoder layer l (and, for the last layer, of model.encoder.norm) are final: its all-reduce may start
+    if ((size_t)l < ts->layer_events.size() && ts->layer_events[l]) CU_TRY(cudaEventRecord(ts->layer_events[l], s));
+  }
   // att_embed: x0 = relu(att . W^T + b), zero on padded rows (their relu mask is false as x0 == 0 there)
   e->launches++;
   launch_k(relu_bwd_cast_kernel<T>, 148 * 8, 256, 0, s, (const float*)dx, (const float*)ts->x0, g1, (size_t)M * kD / 4, ts->d_att_embed.scale);

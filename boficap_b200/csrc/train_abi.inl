@@ -379,4 +379,13 @@ extern "C" int bofi_train_set_grad_event(bofi_handle_t e, void* event) {
   return BOFI_OK;
 }
 
+extern "C" int bofi_train_set_layer_event(bofi_handle_t e, int32_t layer, void* event) {
+  if (!e) return fail(BOFI_ERR_INVALID, "null handle");
+  if (layer < 0 || layer >= e->cfg.n_enc) return fail(BOFI_ERR_INVALID, "encoder layer %d of %d", layer, e->cfg.n_enc);
+  TrainState* ts = train_state(e);
+  if (ts->layer_events.size() < (size_t)e->cfg.n_enc) ts->layer_events.assign((size_t)e->cfg.n_enc, nullptr);
+  ts->layer_events[layer] = (cudaEvent_t)event;
+  return BOFI_OK;
+}
+
 extern "C" int bofi_train_launches(bofi_handle_t e) { return e ? e->launches : -1; }

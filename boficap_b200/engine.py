@@ -413,6 +413,14 @@ class BofiEngine:
     def train_set_dropout(self, p, p_att_embed, seed):
         _lib.check(self.lib.bofi_train_set_dropout(self.handle, float(p), float(p_att_embed), int(seed) & 0xFFFFFFFF))
 
+    def train_set_layer_event(self, layer, event):
+        """event: torch.cuda.Event (recorded once) or None; recorded once encoder layer `layer`'s gradients are final."""
+        keep = getattr(self, "_layer_event_keep", None)
+        if keep is None:
+            keep = self._layer_event_keep = {}
+        keep[layer] = event
+        _lib.check(self.lib.bofi_train_set_layer_event(self.handle, int(layer), C.c_void_p(event.cuda_event) if event is not None else None))
+
     def train_set_grad_event(self, event):
         """event: torch.cuda.Event (recorded once so that its handle exists) or None; see bofi_train_set_grad_event."""
         self._grad_event_keep = event

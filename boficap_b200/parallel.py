@@ -70,15 +70,28 @@ class OverlappedGradReduce:
     that part -- `buckets` NCCL calls so that the first bytes move early -- is reduced on a side stream underneath it; the
     encoder / att_embed part follows on the training stream.  `finish()` joins the side stream."""
 
-    def __init__(self, model, group=None, buckets=4):
+    def __init__(self, model, group=None, buckets=4, layer_buckets=True):
+        """layer_buckets: the encoder part as well is reduced layer by layer underneath the backward pass of the layers below
+        (bofi_train_set_layer_event); only att_embed (4 MB) is left for after the backward pass."""
         self.model, self.group = model, group
         eng = model._engine
         self.flat = model.flat_grads()
-        self.cut = eng.param_layout()["model.decoder.layers.0.self_attn.linears.0.weight"][0]
+        layout = eng.param_layout()
+        self.cut = layout["model.decoder.layers.0.self_attn.linears.0.weight"][0]
+        self.layers = []                         # (event, gradient slice) from the last encoder layer down to the first
+        if layer_buckets:
+            n_enc = model.cfg.N_enc
+            starts = [layout["model.encoder.layers.%d.self_attn.linears.0.weight" % l][0] for l in range(n_enc)] + [self.cut]
+            for l in range(n_enc - 1, -1, -1):
+                ev = torch.cuda.Event()
+                ev.record()
+                eng.train_set_layer_event(l, ev)
+                self.layers.append((ev, self.flat[starts[l]:starts[l + 1]]))
+            self.front_cut = starts[0]
         n_back = self.flat.numel() - self.cut
         step = -(-n_back // max(1, buckets))
         self.back = [self.flat[self.cut + i:min(self.cut + i + step, self.flat.numel())] for i in range(0, n_back, step)]
-        self.front = self.flat[:self.cut]
+        self.front = self.flat[:self.front_cut] if self.layers else self.flat[:self.cut]
         self.side = torch.cuda.Stream(self.flat.device)
         self.event = torch.cuda.Event()
         self.event.record()                      # creates the handle the library records into
@@ -91,6 +104,9 @@ class OverlappedGradReduce:
             self.side.wait_event(self.event)     # recorded by the library inside the backward pass that was just enqueued
             for b in self.back:
                 dist.all_reduce(b, op=dist.ReduceOp.AVG, group=self.group)
+            for ev, b in self.layers:            # encoder layers, last to first, as their backward passes finish
+                self.side.wait_event(ev)
+                dist.all_reduce(b, op=dist.ReduceOp.AVG, group=self.group)
             done = torch.cuda.Event()
             done.record(self.side)
         dist.all_reduce(self.front, op=dist.ReduceOp.AVG, group=self.group)
@@ -98,6 +114,8 @@ class OverlappedGradReduce:
 
     def close(self):
         self.model._engine.train_set_grad_event(None)
+        for l in range(len(self.layers)):
+            self.model._engine.train_set_layer_event(l, None)
 
 
 def allreduce_gradients(model, group=None, average=True):

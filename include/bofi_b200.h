@@ -299,6 +299,10 @@ int bofi_train_set_glat(bofi_handle_t h, float glat_p, uint32_t seed);
  * bofi_param_offset("model.decoder.layers.0.self_attn.linears.0.weight") -- are final: the caller waits for it on a side
  * stream and reduces that part of the gradient buffer while the encoder's backward pass still runs. */
 int bofi_train_set_grad_event(bofi_handle_t h, void* event);
+/* The same for the encoder itself: `event` (NULL switches it off) is recorded once the backward pass of encoder layer `layer` has
+ * run -- the flat entries of model.encoder.layers.<layer>.* (and, for the last layer, model.encoder.norm.*) are final, so their
+ * all-reduce can run underneath the backward pass of the layers below.  Only att_embed is left for after the backward pass. */
+int bofi_train_set_layer_event(bofi_handle_t h, int32_t layer, void* event);
 /* Kernels enqueued by the last training call. */
 int bofi_train_launches(bofi_handle_t h);
 
