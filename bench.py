@@ -181,7 +181,7 @@ def bench_xe(a, rank, local_rank, world):
             dev(bt["extend_phrase_syn_seq"]), dev(bt["extend_phrase_seq"]), dev(bt["extend_phrase_seq_mask"]))
     eng = model._engine
     # bucketed all-reduce of the flat gradient buffer, the decoder-side buckets underneath the encoder's backward pass
-    reducer = OverlappedGradReduce(model, buckets=a.buckets, layer_buckets=not a.no_layer_buckets) if dist is not None else None
+    reducer = OverlappedGradReduce(model, buckets=a.buckets, layer_buckets=a.layer_buckets) if dist is not None else None
 
     def step():
         flat_g.zero_()
@@ -243,8 +243,8 @@ def bench_xe(a, rank, local_rank, world):
                                                                        "off" if a.no_dropout else "on (p=0.1, att_embed 0.5)"),
                            "parallelism": "data-parallel replicas x%d, NCCL all-reduce of the %.0f MB flat gradient buffer in %d + %s buckets, the decoder-side "
                                           "buckets overlapped with the encoder's backward pass%s"
-                                          % (world, flat_g.numel() * 4 / 1e6, a.buckets, "1" if a.no_layer_buckets else "%d + 1" % cfg.N_enc,
-                                             "" if a.no_layer_buckets else ", the encoder layers' buckets with the backward pass of the layers below")},
+                                          % (world, flat_g.numel() * 4 / 1e6, a.buckets, "%d + 1" % cfg.N_enc if a.layer_buckets else "1",
+                                             ", the encoder layers' buckets with the backward pass of the layers below" if a.layer_buckets else "")},
                 "loss_first": first, "loss_last": float(losses[0]), "gpu_launches": launches * a.steps, "clocks": clocks,
                 "gpu_eager": eager,
                 "roofline": {"bound": "tensor", "kernel": "gemm_tc2_kernel / gemm_tc_kernel (tcgen05), all %d launches of a step" % g["launches"],
@@ -383,8 +383,8 @@ def main():
     ap.add_argument("--depth", type=int, default=3, help="engine handles x streams in flight (boficap_b200/pipeline.py)")
     ap.add_argument("--compact", action="store_true", help="with --adaptive: the e2e leg sends compact features (valid regions only, "
                                                             "bofi_stage_compact) instead of the padded [B, R, F] batch")
-    ap.add_argument("--no-layer-buckets", action="store_true", help="xe workload: the encoder part of the gradients as ONE all-reduce after "
-                                                                      "the backward pass instead of one per encoder layer underneath it")
+    ap.add_argument("--layer-buckets", action="store_true", help="xe workload: the encoder part of the gradients as one all-reduce per encoder "
+                                                                  "layer underneath the backward pass instead of ONE after it (measured: no gain)")
     ap.add_argument("--n-len", type=int, default=1, help="xe workload: bounding layers (configs/uic_sd_N2.yml: 2)")
     ap.add_argument("--group", type=int, default=2, help="consecutive batches decoded by ONE library call on a slot, every batch with its own "
                                                           "fill window (bofi_set_shard): bit-identical results, one bounding loop per group")

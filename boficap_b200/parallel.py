@@ -70,9 +70,11 @@ class OverlappedGradReduce:
     that part -- `buckets` NCCL calls so that the first bytes move early -- is reduced on a side stream underneath it; the
     encoder / att_embed part follows on the training stream.  `finish()` joins the side stream."""
 
-    def __init__(self, model, group=None, buckets=4, layer_buckets=True):
+    def __init__(self, model, group=None, buckets=4, layer_buckets=False):
         """layer_buckets: the encoder part as well is reduced layer by layer underneath the backward pass of the layers below
-        (bofi_train_set_layer_event); only att_embed (4 MB) is left for after the backward pass."""
+        (bofi_train_set_layer_event); only att_embed (4 MB) is left for after the backward pass.  Same gradients
+        (tools/check_grad_reduce.py); measured at 8 GPUs: 23.99 ms per step against 23.93 ms with ONE encoder bucket after the
+        backward pass -- what an 8-GPU step costs over a 1-GPU step (+0.6 ms) is not the tail all-reduce -- so it is off."""
         self.model, self.group = model, group
         eng = model._engine
         self.flat = model.flat_grads()
