@@ -50,6 +50,7 @@ _SIGNATURES = {
     "bofi_decode_ex": (C.c_int, [_P, _P, _I, _I, _I, _P, _P, C.c_int64, _P, _P, _P]),
     "bofi_encode_compact": (C.c_int, [_P, _P, _P, _I, _P, _I, _I, _I]),
     "bofi_stage_compact": (C.c_int, [_P, _P, _P, _I, _P, _I, _I, _I]),
+    "bofi_stage_compact_part": (C.c_int, [_P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I]),
     "bofi_encode_staged_compact": (C.c_int, [_P, _P, _I, _I, _I, _I]),
     "bofi_set_shard": (C.c_int, [_P, _I]),
     "bofi_stage_part": (C.c_int, [_P, _P, _P, _I, _P, _I, _I, _I, _I]),

@@ -1570,20 +1570,27 @@ int bofi_encode_compact(bofi_handle_t e, void* stream, const void* att_compact, 
                       : encode_impl<float>(e, s, att_compact, feat_dtype, att_len, B, R, nullptr, total_rows);
 }
 
-int bofi_stage_compact(bofi_handle_t e, void* stream, const void* att_compact, int32_t feat_dtype, const int32_t* att_len, int32_t total_rows,
-                       int32_t B, int32_t R) {
+int bofi_stage_compact_part(bofi_handle_t e, void* stream, const void* att_compact, int32_t feat_dtype, const int32_t* att_len, int32_t rows_part,
+                            int32_t row0, int32_t image0, int32_t Bpart, int32_t Btotal, int32_t R) {
   if (!e || !att_compact || !att_len) return fail(BOFI_ERR_INVALID, "null argument");
   if (feat_dtype != BOFI_FEAT_F32 && feat_dtype != BOFI_FEAT_BF16 && feat_dtype != BOFI_FEAT_F16)
     return fail(BOFI_ERR_INVALID, "feat_dtype %d (BOFI_FEAT_F32 / BF16 / F16)", feat_dtype);
-  if (B <= 0 || R <= 0 || total_rows <= 0 || (int64_t)total_rows > (int64_t)B * R) return fail(BOFI_ERR_INVALID, "compact rows %d of at most %d x %d", total_rows, B, R);
+  if (Bpart <= 0 || R <= 0 || rows_part <= 0 || row0 < 0 || image0 < 0 || image0 + Bpart > Btotal ||
+      (int64_t)row0 + rows_part > (int64_t)Btotal * R || (int64_t)rows_part > (int64_t)Bpart * R)
+    return fail(BOFI_ERR_INVALID, "compact part: rows [%d, %d), images [%d, %d) of %d x %d", row0, row0 + rows_part, image0, image0 + Bpart, Btotal, R);
   CU_TRY(cudaSetDevice(e->device));
   cudaStream_t s = (cudaStream_t)stream;
   const size_t per_row = (size_t)e->cfg.att_feat_size * (feat_dtype == BOFI_FEAT_F32 ? 4 : 2);
-  RC_TRY(e->h_in.reserve((size_t)B * R * per_row));          // the tensor map of the att_embed GEMM spans B * R rows
-  RC_TRY(e->h_len.reserve((size_t)B * 4));
-  CU_TRY(cudaMemcpyAsync(e->h_in.p, att_compact, (size_t)total_rows * per_row, cudaMemcpyDefault, s));
-  CU_TRY(cudaMemcpyAsync(e->h_len.p, att_len, (size_t)B * 4, cudaMemcpyDefault, s));
+  RC_TRY(e->h_in.reserve((size_t)Btotal * R * per_row));     // sized for the whole call at the first part
+  RC_TRY(e->h_len.reserve((size_t)Btotal * 4));
+  CU_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(e->h_in.p) + (size_t)row0 * per_row, att_compact, (size_t)rows_part * per_row, cudaMemcpyDefault, s));
+  CU_TRY(cudaMemcpyAsync(e->h_len.as<int>() + image0, att_len, (size_t)Bpart * 4, cudaMemcpyDefault, s));
   return BOFI_OK;
+}
+
+int bofi_stage_compact(bofi_handle_t e, void* stream, const void* att_compact, int32_t feat_dtype, const int32_t* att_len, int32_t total_rows,
+                       int32_t B, int32_t R) {
+  return bofi_stage_compact_part(e, stream, att_compact, feat_dtype, att_len, total_rows, 0, 0, B, B, R);
 }
 
 int bofi_encode_staged_compact(bofi_handle_t e, void* stream, int32_t feat_dtype, int32_t total_rows, int32_t B, int32_t R) {

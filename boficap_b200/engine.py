@@ -119,18 +119,23 @@ class BofiEngine:
                                                     int(att_compact.shape[0]), B, int(R)))
         self._batch = (B, R, att_compact, att_len)
 
-    def stage_compact(self, att_compact, att_len, R):
-        """Asynchronous copy of a compact batch (pinned host or device) into the library's staging buffer."""
+    def stage_compact(self, att_compact, att_len, R, row0=0, image0=0, total_images=None):
+        """Asynchronous copy of a compact batch (pinned host or device) into the library's staging buffer; row0 / image0 /
+        total_images: the batch is one of several that will share a call (its compact rows follow those of the batches before)."""
         assert att_compact.is_contiguous() and att_compact.dim() == 2
         att_len = att_len.to(torch.int32).contiguous()
+        B = int(att_len.shape[0])
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.bofi_stage_compact(self.handle, self._stream(), _ptr(att_compact), _feat_code(att_compact), _ptr(att_len),
-                                                   int(att_compact.shape[0]), int(att_len.shape[0]), int(R)))
+            _lib.check(self.lib.bofi_stage_compact_part(self.handle, self._stream(), _ptr(att_compact), _feat_code(att_compact), _ptr(att_len),
+                                                        int(att_compact.shape[0]), int(row0), int(image0), B,
+                                                        int(total_images if total_images is not None else B), int(R)))
         gens = getattr(self, "_stage_gens", None)
         if gens is None:
             gens = self._stage_gens = []
-        gens.append([(att_compact, att_len)])
-        del gens[:-3]
+        if image0 == 0 or not gens:
+            gens.append([])
+            del gens[:-3]
+        gens[-1].append((att_compact, att_len))
         return _feat_code(att_compact)
 
     def encode_staged_compact(self, code, total_rows, B, R):

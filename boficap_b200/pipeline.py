@@ -22,11 +22,12 @@ from .engine import BofiEngine
 
 class _Group:
     """The submissions that will be decoded by one library call on one slot."""
-    __slots__ = ("slot", "key", "parts", "event", "out", "launched", "host", "kw", "size")
+    __slots__ = ("slot", "key", "parts", "event", "out", "launched", "host", "kw", "size", "rows")
 
     def __init__(self, slot, key, host, kw, size):
         self.slot, self.key, self.host, self.kw, self.size = slot, key, host, kw, size
         self.parts = []            # batch sizes
+        self.rows = []             # compact batches: rows (valid regions) per batch
         self.event = None
         self.out = None
         self.launched = False
@@ -132,7 +133,10 @@ class BofiPipeline:
             eng.set_shard(g.parts[0] if len(g.parts) > 1 else 0)
             if g.host:
                 st.wait_event(staged)
-                eng.encode_staged(code, have_len, total, R)
+                if g.rows:
+                    eng.encode_staged_compact(code, sum(g.rows), total, R)
+                else:
+                    eng.encode_staged(code, have_len, total, R)
                 self.enc_done[g.slot].record(st)            # the staging buffers may be refilled from here on
                 g.out = eng.decode_host(kw["mode"], kw["sample_n"], kw["output_logsoftmax"], out=self.host_out[g.slot],
                                         want_logprobs=kw["want_logprobs"])
@@ -151,10 +155,11 @@ class BofiPipeline:
             self._open = None
         return self._tickets.pop(id(g), [])
 
-    def _submit_grouped(self, host, att_feats, att_len, kw, size):
+    def _submit_grouped(self, host, att_feats, att_len, kw, size, compact_regions=0):
         from .engine import _feat_code
-        B, R, _ = att_feats.shape
-        key = (_feat_code(att_feats), att_len is not None, R, B, host, size, tuple(sorted(kw.items())))
+        compact = compact_regions > 0                       # att_feats [sum(att_len), F]: only the valid regions
+        B, R = (int(att_len.shape[0]), compact_regions) if compact else att_feats.shape[:2]
+        key = (_feat_code(att_feats), att_len is not None, R, B, host, size, compact, tuple(sorted(kw.items())))
         launched = []
         g = self._open
         if g is not None and g.key != key:                  # another shape / mode: the open group goes as it is
@@ -169,7 +174,11 @@ class BofiPipeline:
         with torch.cuda.stream(st):                         # the copy starts now, underneath whatever is running
             if host and not g.parts:
                 st.wait_event(self.enc_done[g.slot])        # (a no-op before the slot's first call)
-            eng.stage_part(att_feats, att_len, sum(g.parts), B * size)
+            if compact:
+                eng.stage_compact(att_feats, att_len, R, row0=sum(g.rows), image0=sum(g.parts), total_images=B * size)
+                g.rows.append(int(att_feats.shape[0]))
+            else:
+                eng.stage_part(att_feats, att_len, sum(g.parts), B * size)
         g.parts.append(B)
         t = Ticket(None, None, g.slot, g, len(g.parts) - 1, self)
         self._tickets[id(g)].append(t)
@@ -223,27 +232,11 @@ class BofiPipeline:
     def submit_host_compact(self, att_compact, att_len, max_regions, mode="NAIC", sample_n=1, output_logsoftmax=1, want_logprobs=False):
         """Pinned COMPACT host features ([sum(att_len), F]: only the valid regions, image after image; boficap_b200/data:
         PinnedFeeder(compact=True)) -> pinned host outputs.  sum(att_len) instead of B * R rows cross PCIe and att_embed runs on
-        them directly.  One batch per library call (no grouping), staged on the slot's copy stream like submit_host."""
-        assert att_compact.is_pinned() and att_len is not None
-        if not att_len.is_pinned():
+        them directly.  Staged on the slot's copy stream and grouped like submit_host (the compact rows of a group's batches
+        follow each other in the staging buffer)."""
+        assert att_compact.is_pinned() and att_compact.dim() == 2 and att_len is not None
+        if not att_len.is_cuda and not att_len.is_pinned():
             att_len = att_len.to(torch.int32).pin_memory()
-        launched = self._launch(self._open) if self._open is not None else []
-        slot = self._next()
-        eng, st, cs = self.engines[slot], self.streams[slot], self.copy_streams[slot]
-        B, total = int(att_len.shape[0]), int(att_compact.shape[0])
-        with torch.cuda.stream(cs):
-            cs.wait_event(self.enc_done[slot])
-            code = eng.stage_compact(att_compact, att_len, max_regions)
-            staged = torch.cuda.Event()
-            staged.record(cs)
-        with torch.cuda.stream(st):
-            st.wait_event(staged)
-            eng.encode_staged_compact(code, total, B, max_regions)
-            self.enc_done[slot].record(st)
-            out = eng.decode_host(mode, sample_n, output_logsoftmax, out=self.host_out[slot], want_logprobs=want_logprobs)
-            self.host_out[slot] = out
-            ev = torch.cuda.Event()
-            ev.record(st)
-        t = Ticket(ev, out, slot)
-        self.just_launched = launched + [t]
-        return t
+        return self._submit_grouped(True, att_compact, att_len, dict(mode=mode, sample_n=sample_n, output_logsoftmax=output_logsoftmax,
+                                                                      want_logprobs=want_logprobs, reuse_outputs=True),
+                                    self.group if mode == "NAIC" else 1, compact_regions=int(max_regions))

@@ -140,6 +140,10 @@ int bofi_encode_compact(bofi_handle_t h, void* stream, const void* att_compact, 
 int bofi_stage_compact(bofi_handle_t h, void* stream, const void* att_compact, int32_t feat_dtype, const int32_t* att_len,
                        int32_t total_rows, int32_t B, int32_t R);
 int bofi_encode_staged_compact(bofi_handle_t h, void* stream, int32_t feat_dtype, int32_t total_rows, int32_t B, int32_t R);
+/* One batch of several that will share a call (bofi_set_shard): its rows_part compact rows go to rows [row0, ...) of the staging
+ * buffer (the compact rows of the batches follow each other), its Bpart counts to images [image0, ...). */
+int bofi_stage_compact_part(bofi_handle_t h, void* stream, const void* att_compact, int32_t feat_dtype, const int32_t* att_len,
+                            int32_t rows_part, int32_t row0, int32_t image0, int32_t Bpart, int32_t Btotal, int32_t R);
 
 /* Several batches in ONE call (what nn.DataParallel replicas / successive eval batches are to the reference: independent
  * `_sample` calls).  The only place where a row of `_sample` depends on the other rows of its batch is the fill window

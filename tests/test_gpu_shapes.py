@@ -165,5 +165,21 @@ def test_compact_features_equal_padded_features(precision):
                 out = t.wait()
                 for x, y in zip(want, (out["seq"], out["logp"], out["pnum"], out["plen"], out["psyn"])):
                     assert torch.equal(torch.nan_to_num(x.float()), torch.nan_to_num(y.float()))
+    # two compact batches of the same shape share one library call (group = 2): each ticket equals its stand-alone decode
+    if precision == "bf16":
+        batches, wants = [], []
+        for k in range(2):
+            _, att, masks = synth.synth_inputs(96, 80, seed=400 + k, adaptive=True)
+            att = att.to(torch.bfloat16)
+            lens = masks.long().sum(1).int()
+            eng.encode(att.cuda(), lens.cuda())
+            wants.append([t.cpu() for t in eng.decode("NAIC", 1, 1, True)])
+            batches.append((torch.cat([att[b, :int(lens[b])] for b in range(96)]).contiguous().pin_memory(), lens.pin_memory()))
+        tickets = [pipe.submit_host_compact(c, l, 80, want_logprobs=True) for c, l in batches]
+        assert all(t.launched for t in tickets)
+        for t, w in zip(tickets, wants):
+            out = t.wait()
+            for x, y in zip(w, (out["seq"], out["logp"], out["pnum"], out["plen"], out["psyn"])):
+                assert torch.equal(torch.nan_to_num(x.float()), torch.nan_to_num(y.float()))
     pipe.close()
     eng.close()
