@@ -275,7 +275,7 @@ extern "C" int bofi_sc_sample(bofi_handle_t e, void* stream, int32_t mode, int32
   if (!e || !att_feats || !seq || !logprobs || !phrase_num || !phrase_length || !phrase_syn) return fail(BOFI_ERR_INVALID, "null argument");
   if (!e->finalized) return fail(BOFI_ERR_STATE, "weights not finalised");
   if (!e->flat_g) return fail(BOFI_ERR_STATE, "bofi_sc_sample needs bofi_train_bind (gradient buffer)");
-  if (e->cfg.n_len != 1) return fail(BOFI_ERR_INVALID, "the training path is built for N_len == 1 (uic_sd.yml)");
+  if (e->cfg.n_len < 1) return fail(BOFI_ERR_INVALID, "the training path is built for N_len >= 1");
   if (mode != BOFI_MODE_NAIC && mode != BOFI_MODE_SAIC) return fail(BOFI_ERR_INVALID, "mode %d (NAIC = 0, SAIC = 1)", mode);
   if (B <= 0 || R <= 0 || R > kMaxKeys || sample_n < 1) return fail(BOFI_ERR_INVALID, "bad batch B=%d R=%d sample_n=%d", B, R, sample_n);
   CU_TRY(cudaSetDevice(e->device));

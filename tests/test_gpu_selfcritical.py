@@ -25,9 +25,9 @@ def sc_loss(logp, seq, reward):
     return -(picked * reward[:, None] * mask).sum() / mask.sum()
 
 
-def oracle_for_sc(calib):
+def oracle_for_sc(calib, cfg=None):
     from oracle.bofi_oracle import BofiOracle, OracleConfig
-    cfg = BofiConfig()
+    cfg = cfg or BofiConfig()
     sd = synth.synth_state_dict(cfg, 0, calib)
     for k, v in sd.items():
         if k != "model.pos_embed.pe":
@@ -37,10 +37,11 @@ def oracle_for_sc(calib):
     return o, sd
 
 
-@pytest.mark.parametrize("mode,calib,adaptive", [("NAIC", "s_cap", False), ("SAIC", "s_cap", True)])
-def test_sc_sample_logprobs_and_gradients_match_oracle_fp32(mode, calib, adaptive):
+@pytest.mark.parametrize("mode,calib,adaptive,cfg_kw", [("NAIC", "s_cap", False, {}), ("SAIC", "s_cap", True, {}),
+                                                        ("NAIC", "s_real", False, {"N_len": 2})])      # (uic_sd_N2.yml: two bounding layers)
+def test_sc_sample_logprobs_and_gradients_match_oracle_fp32(mode, calib, adaptive, cfg_kw):
     from oracle.bofi_oracle import DropSim
-    cfg = BofiConfig()
+    cfg = BofiConfig(**cfg_kw)
     B, R, sample_n, seed = 3, 14, 2, 91
     from boficap_b200.captioning import models
     infos = synth.make_infos(cfg)
@@ -62,7 +63,7 @@ def test_sc_sample_logprobs_and_gradients_match_oracle_fp32(mode, calib, adaptiv
     assert not seq.requires_grad and pnum.shape == (N,)
     words, syns, vis, total = [t.cpu() for t in model._engine.sc_inputs(N)]
     # the tape pass restated by the oracle, same dropout masks
-    o, sd = oracle_for_sc(calib)
+    o, sd = oracle_for_sc(calib, cfg)
     ref = o.forward_sc(att, masks, words, syns, vis, sample_n, drop=DropSim(cfg.dropout, cfg.drop_prob_lm, seed))
     got = logp.detach().cpu()
     committed = torch.arange(cfg.seq_length)[None, :] < (total - 1)[:, None]
